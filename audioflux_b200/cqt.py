@@ -1,0 +1,94 @@
+"""Constant-Q transform object (reference binding: python/audioflux/cqt.py:20-150, 515-655;
+C: src/cqt_algorithm.c)."""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+
+from .base import Base, as_f32, np_ptr, split_batch, swap_last2
+from .capi import opt_int, opt_float
+from .lib import check
+from .types import WindowType, SpectralFilterBankNormalType, enum_value
+
+C1_HZ = 32.703196
+
+
+class CQT(Base):
+    def __init__(self, num=84, samplate=32000, low_fre=C1_HZ, bin_per_octave=12, factor=1., beta=0.,
+                 thresh=0.01, window_type=WindowType.HANN, slide_length=None,
+                 normal_type=SpectralFilterBankNormalType.AREA, is_scale=True, _lib=None):
+        super().__init__(_lib)
+        if low_fre < 27.5:
+            raise ValueError("low_fre must be >= 27.5")
+        self.num, self.samplate, self.low_fre = num, samplate, low_fre
+        self.bin_per_octave, self.factor, self.beta, self.thresh = bin_per_octave, factor, beta, thresh
+        self.window_type, self.slide_length = window_type, slide_length
+        self.normal_type, self.is_scale = normal_type, is_scale
+        status = self._lib.cqtObj_newWith(
+            C.byref(self._obj), num, opt_int(samplate), opt_float(low_fre), opt_int(bin_per_octave),
+            opt_float(factor), opt_float(beta), opt_float(thresh), opt_int(enum_value(window_type)),
+            opt_int(slide_length), opt_int(0), opt_int(enum_value(normal_type)), opt_int(int(is_scale)))
+        if status != 0 or not self._obj:
+            raise ValueError(f"cqtObj_newWith failed with status {status}")
+        self._is_created = True
+        self.fft_length = self.get_fft_length()
+        if self.slide_length is None:
+            self.slide_length = self.fft_length // 4
+
+    def cal_time_length(self, data_length):
+        return self._lib.cqtObj_calTimeLength(self._obj, data_length)
+
+    def get_fft_length(self):
+        return self._lib.cqtObj_getFFTLength(self._obj)
+
+    def get_fre_band_arr(self):
+        p = self._lib.cqtObj_getFreBandArr(self._obj)
+        return np.ctypeslib.as_array(C.cast(p, C.POINTER(C.c_float)), shape=(self.num,)).copy()
+
+    def set_scale(self, flag=True):
+        self._lib.cqtObj_setScale(self._obj, int(flag))
+
+    def get_kernel_bank(self):
+        """Additive: (kr, ki) spectral kernels [bin_per_octave, fft_length//2+1]."""
+        fn = self._require_ext("cqtObj_getKernelBank")
+        kr = np.zeros((self.bin_per_octave, self.fft_length // 2 + 1), np.float32)
+        ki = np.zeros_like(kr)
+        check(fn(self._obj, np_ptr(kr), np_ptr(ki)), "cqtObj_getKernelBank")
+        return kr, ki
+
+    def cqt_planes(self, data_arr):
+        x = as_f32(data_arr)
+        T = self.cal_time_length(x.shape[-1])
+        re = np.zeros((T, self.num), np.float32)
+        im = np.zeros((T, self.num), np.float32)
+        self._lib.cqtObj_cqt(self._obj, np_ptr(x), x.shape[-1], np_ptr(re), np_ptr(im))
+        return re, im
+
+    def cqt(self, data_arr):
+        """-> complex [..., num, T] as cqt.py:107-150."""
+        x = as_f32(data_arr)
+        lead = x.shape[:-1]
+        x2 = x.reshape(-1, x.shape[-1])
+        outs = []
+        for i in range(x2.shape[0]):
+            re, im = self.cqt_planes(x2[i])
+            outs.append(re + 1j * im)
+        out = np.stack(outs).reshape(*lead, -1, self.num)
+        return swap_last2(out)
+
+    def cqt_batch(self, data):
+        """Additive: data [B, L] (numpy host | torch cuda) -> (re, im) each [B, T, num]."""
+        fn = self._require_ext("cqtObj_cqtBatch")
+        x2, lead, kind, ptr, stream, alloc = split_batch(data)
+        B, L = x2.shape
+        T = self.cal_time_length(L)
+        re = alloc(B, T, self.num)
+        im = alloc(B, T, self.num)
+        check(fn(self._obj, ptr(x2), L, B, ptr(re), ptr(im), kind, stream), "cqtObj_cqtBatch")
+        return re.reshape(*lead, T, self.num), im.reshape(*lead, T, self.num)
+
+    def __del__(self):
+        if getattr(self, "_is_created", False):
+            self._lib.cqtObj_free(self._obj)
+            self._is_created = False

@@ -1,0 +1,677 @@
+"""CPU restatement (numpy) of audioFlux's time-frequency hot path.
+
+TEST INFRASTRUCTURE ONLY.  Nothing under ``audioflux_b200/`` may import this
+module; it is the checker used by ``tests/``, ``__graft_entry__.smoke()`` and
+the ``cpu_baseline`` leg of ``bench.py``.
+
+Every function cites the reference file:line (relative to /root/reference) it
+restates.  Arithmetic is done in float64 unless the reference's float32
+rounding decides an *integer* outcome (band-edge bin indices, kernel lengths),
+in which case the float32 steps are reproduced explicitly.
+
+Pinning: the reference ships no tests or golden vectors for this path
+(SURVEY.md section 4), so this restatement is pinned by (i) the reference itself
+compiled into ``oracle/_ref`` (tests/test_oracle_vs_ref.py, run wherever that
+library exists) and (ii) fixtures generated from that library and committed
+under ``tests/golden`` (tests/golden/make_golden.py).
+"""
+from __future__ import annotations
+
+import math
+import numpy as np
+
+f32 = np.float32
+
+# ---------------------------------------------------------------------------
+# enums (src/flux_base.h:14-168) -- plain ints shared with the C ABI
+# ---------------------------------------------------------------------------
+W_RECT, W_HANN, W_HAMM, W_BLACKMAN, W_KAISER, W_BARTLETT, W_TRIANG, W_FLATTOP, \
+    W_GAUSS, W_BLACKMAN_HARRIS, W_BLACKMAN_NUTTALL, W_BARTLETT_HANN, W_BOHMAN, W_TUKEY = range(14)
+DATA_POWER, DATA_MAG = 0, 1
+SCALE_LINEAR, SCALE_LINSPACE, SCALE_MEL, SCALE_BARK, SCALE_ERB, SCALE_OCTAVE, SCALE_LOG = range(7)
+STYLE_SLANEY, STYLE_ETSI, STYLE_GAMMATONE, STYLE_POINT, STYLE_RECT, STYLE_HANN, STYLE_HAMM, \
+    STYLE_BLACKMAN, STYLE_BOHMAN, STYLE_KAISER, STYLE_GAUSS = range(11)
+NORM_NONE, NORM_AREA, NORM_BANDWIDTH = 0, 1, 2
+RECT_LOG, RECT_CUBIC = 0, 1
+WAVE_MORSE, WAVE_MORLET, WAVE_BUMP, WAVE_PAUL, WAVE_DOG, WAVE_MEXICAN, WAVE_HERMIT, WAVE_RICKER = range(8)
+
+
+# ---------------------------------------------------------------------------
+# windows  (src/dsp/flux_window.c)
+# ---------------------------------------------------------------------------
+def _bessel_i0_series(a):
+    """15-term power series the reference uses (flux_window.c `__besselZeroOne`)."""
+    a = np.asarray(a, dtype=np.float64)
+    b = a / 2.0
+    s = np.ones_like(b)
+    num = np.ones_like(b)
+    den = 1.0
+    for k in range(1, 16):
+        num = num * b
+        den = den * k
+        s = s + (num / den) ** 2
+    return s
+
+
+def _symmetric_window(kind, L, value=None):
+    """Symmetric window of length L (flag=0 creators, flux_window.c:281-640, 737-850)."""
+    if L == 1:
+        return np.ones(1)
+    i = np.arange(L, dtype=np.float64)
+    M = L - 1
+    if kind == W_HANN:
+        w = 0.5 - 0.5 * np.cos(2 * np.pi * i / M)
+    elif kind == W_HAMM:
+        w = 0.54 - 0.46 * np.cos(2 * np.pi * i / M)
+    elif kind == W_BLACKMAN:
+        w = 0.42 - 0.5 * np.cos(2 * np.pi * i / M) + 0.08 * np.cos(4 * np.pi * i / M)
+        w[0] = w[-1] = 0.0
+    elif kind == W_KAISER:
+        beta = 5.0 if value is None or value <= 0 else value
+        v = 2.0 * i / M - 1.0
+        w = _bessel_i0_series(beta * np.sqrt(np.maximum(0.0, 1 - v * v))) / _bessel_i0_series(beta)
+    elif kind == W_BARTLETT:
+        w = 1.0 - np.abs(2.0 * i / M - 1.0)
+    elif kind == W_TRIANG:
+        if L % 2 == 0:
+            half = 2.0 * (np.arange(L // 2) + 0.5) / L
+            w = np.concatenate([half, half[::-1]])
+        else:
+            half = 2.0 * (np.arange((L + 1) // 2) + 1.0) / (L + 1)
+            w = np.concatenate([half, half[-2::-1]])
+    elif kind == W_FLATTOP:
+        a = (0.21557895, 0.41663158, 0.277263158, 0.083578947, 0.006947368)
+        w = (a[0] - a[1] * np.cos(2 * np.pi * i / M) + a[2] * np.cos(4 * np.pi * i / M)
+             - a[3] * np.cos(6 * np.pi * i / M) + a[4] * np.cos(8 * np.pi * i / M))
+    elif kind == W_GAUSS:
+        alpha = 2.5 if value is None or value <= 0 else value
+        w = np.exp(-0.5 * (alpha * (i - M / 2.0) / (M / 2.0)) ** 2)
+    elif kind == W_BLACKMAN_HARRIS:
+        a = (0.35875, 0.48829, 0.14128, 0.01168)
+        w = (a[0] - a[1] * np.cos(2 * np.pi * i / M) + a[2] * np.cos(4 * np.pi * i / M)
+             - a[3] * np.cos(6 * np.pi * i / M))
+    elif kind == W_BLACKMAN_NUTTALL:
+        a = (0.3635819, 0.4891775, 0.1365995, 0.0106411)
+        w = (a[0] - a[1] * np.cos(2 * np.pi * i / M) + a[2] * np.cos(4 * np.pi * i / M)
+             - a[3] * np.cos(6 * np.pi * i / M))
+    elif kind == W_BARTLETT_HANN:
+        r = i / M - 0.5
+        w = 0.62 - 0.48 * np.abs(r) + 0.38 * np.cos(2 * np.pi * r)
+        w[0] = w[-1] = 0.0
+    elif kind == W_BOHMAN:
+        l = np.abs(-1.0 + 2.0 * i / M)
+        w = (1 - l) * np.cos(np.pi * l) + np.sin(np.pi * l) / np.pi
+        w[0] = w[-1] = 0.0
+    elif kind == W_TUKEY:
+        a = 0.5 if value is None or not (0 <= value <= 1) else value
+        if a == 0:
+            return np.ones(L)
+        if a == 1:
+            return _symmetric_window(W_HANN, L)
+        x = i / M
+        w = np.ones(L)
+        lo = x < a / 2
+        hi = x >= 1 - a / 2
+        w[lo] = 0.5 * (1 + np.cos(2 * np.pi / a * (x[lo] - a / 2)))
+        w[hi] = 0.5 * (1 + np.cos(2 * np.pi / a * (x[hi] - 1 + a / 2)))
+    else:
+        w = np.ones(L)
+    return w
+
+
+def fft_window(win_type: int, n: int) -> np.ndarray:
+    """`window_calFFTWindow` (flux_window.c:890-940): periodic variants = symmetric
+    window of length n+1 truncated to n, except Bartlett/Triang/Bartlett-Hann/Bohman
+    which stay symmetric."""
+    if win_type == W_RECT or win_type < 0 or win_type > W_TUKEY:
+        return np.ones(n, dtype=f32)
+    if win_type in (W_BARTLETT, W_TRIANG, W_BARTLETT_HANN, W_BOHMAN):
+        return _symmetric_window(win_type, n).astype(f32)
+    return _symmetric_window(win_type, n + 1)[:n].astype(f32)
+
+
+# ---------------------------------------------------------------------------
+# STFT  (src/stft_algorithm.c:225-287, 696-803; fft sign src/dsp/fft_algorithm.c:882-891)
+# ---------------------------------------------------------------------------
+def stft_time_length(L, n, hop, is_pad=False):
+    """stft_algorithm.c:225-262."""
+    if not is_pad:
+        return 0 if L < n else (L - n) // hop + 1
+    return 0 if L <= 0 else L // hop + 1
+
+
+def stft(x, n, hop, window, is_pad=False):
+    """Full mirrored n-point spectrum per frame -> (re[T,n], im[T,n]).
+
+    is_pad=True restates the centre/constant-zero padding used by CQT
+    (stft_algorithm.c:601-694, 813-826): the `L % hop` tail is dropped when T>1,
+    then n/2 zeros are added on both sides."""
+    x = np.asarray(x, dtype=np.float64)
+    L = x.shape[0]
+    T = stft_time_length(L, n, hop, is_pad)
+    if is_pad:
+        tail = (L % hop) if T > 1 else 0
+        x = np.concatenate([np.zeros(n // 2), x[:L - tail], np.zeros(n - n // 2)])
+    if T == 0:
+        return np.zeros((0, n), f32), np.zeros((0, n), f32)
+    idx = np.arange(T)[:, None] * hop + np.arange(n)[None, :]
+    fr = x[idx] * np.asarray(window, dtype=np.float64)[None, :]
+    X = np.fft.fft(fr, axis=1)
+    return X.real.astype(f32), X.imag.astype(f32)
+
+
+# ---------------------------------------------------------------------------
+# auditory scales  (src/filterbank/auditory_filterBank.c:1023-1190) -- float32 semantics
+# ---------------------------------------------------------------------------
+def _fre_to_scale(fre, scale, ref=0.0):
+    fre = f32(fre)
+    if scale == SCALE_LINEAR:
+        return f32(np.round(f32(fre / f32(ref))))          # roundf(fre/detFre)
+    if scale == SCALE_LINSPACE:
+        return fre
+    if scale == SCALE_MEL:
+        return f32(f32(2595) * f32(math.log10(float(f32(f32(1) + f32(fre / f32(700)))))))
+    if scale == SCALE_BARK:
+        b = 26.81 * float(fre) / float(f32(f32(1960) + fre)) - 0.53    # double expression
+        b = f32(b)
+        if b < 2:
+            b = f32(float(b) + 0.15 * float(f32(f32(2) - b)))
+        elif float(b) > 20.1:
+            b = f32(float(b) + 0.22 * (float(b) - 20.1))
+        return b
+    if scale == SCALE_ERB:
+        a = f32(21.3654)
+        return f32(a * f32(math.log10(float(f32(1.0 + float(fre) * 0.004368)))))
+    if scale == SCALE_OCTAVE:
+        return f32(np.round(f32(float(f32(ref)) * math.log2(float(f32(fre / f32(440)))))))
+    if scale == SCALE_LOG:
+        return f32(math.log2(float(f32(fre / f32(440)))))
+    raise ValueError(scale)
+
+
+def _scale_to_fre(v, scale, ref=0.0):
+    v = f32(v)
+    if scale == SCALE_LINEAR:
+        return f32(v * f32(ref))
+    if scale == SCALE_LINSPACE:
+        return v
+    if scale == SCALE_MEL:
+        return f32(f32(700) * f32(f32(math.pow(10.0, float(f32(v / f32(2595))))) - f32(1)))
+    if scale == SCALE_BARK:
+        b = v
+        if b < 2:
+            b = f32((float(b) - 0.3) / 0.85)
+        elif float(b) > 20.1:
+            b = f32((float(b) + 4.422) / 1.22)
+        return f32(1960 * (float(b) + 0.53) / (26.28 - float(b)))
+    if scale == SCALE_ERB:
+        a = f32(21.3654)
+        return f32(float(f32(f32(math.pow(10.0, float(f32(v / a)))) - f32(1))) / 0.004368)
+    if scale == SCALE_OCTAVE:
+        return f32(math.pow(2.0, float(f32(v / f32(ref)))) * 440)
+    if scale == SCALE_LOG:
+        return f32(math.pow(2.0, float(v)) * 440)
+    raise ValueError(scale)
+
+
+def _linspace_f32(start, stop, length):
+    """`__vlinspace` type 0 (src/vector/flux_vector.c:2145-2162): start + i*step in float32."""
+    start, stop = f32(start), f32(stop)
+    step = f32(f32(stop - start) / f32(length - 1 if length - 1 > 0 else 1))
+    i = np.arange(length).astype(f32)
+    return (start + (i * step).astype(f32)).astype(f32)
+
+
+def revise_edges(num, low, high, scale, n_fft_or_data, sr, bpo, is_edge):
+    """`__revise*Fre` (auditory_filterBank.c:946-1021) applied inside the bank builder."""
+    low, high = f32(low), f32(high)
+    det, off = (0, 0) if is_edge else (2, 1)
+    ref = 0.0
+    if scale == SCALE_OCTAVE:
+        ref = float(bpo) if 4 <= bpo <= 48 else 12.0
+        lo = f32(_fre_to_scale(low, SCALE_OCTAVE, ref) - f32(off))
+        hi = f32(lo + f32(num - 1 + det))
+        low, high = _scale_to_fre(lo, SCALE_OCTAVE, ref), _scale_to_fre(hi, SCALE_OCTAVE, ref)
+    elif scale == SCALE_LINEAR:
+        ref = float(f32(sr * 1.0 / n_fft_or_data))
+        lo = f32(np.round(f32(low / f32(ref))) - f32(off))
+        hi = f32(lo + f32(num - 1 + det))
+        low, high = f32(lo * f32(ref)), f32(hi * f32(ref))
+    elif scale == SCALE_LINSPACE:
+        if not is_edge:
+            d = f32(f32(high - low) / f32(num - 1))
+            low, high = f32(low - d), f32(high + d)
+    elif scale == SCALE_LOG:
+        if not is_edge:
+            lo = _fre_to_scale(low, SCALE_LOG)
+            hi = _fre_to_scale(high, SCALE_LOG)
+            d = f32(f32(hi - lo) / f32(num - 1))
+            low, high = _scale_to_fre(f32(lo - d), SCALE_LOG), _scale_to_fre(f32(hi + d), SCALE_LOG)
+    return low, high, ref
+
+
+def band_edges(num, n_fft, sr, low, high, scale, ref, is_edge, slaney_bins):
+    """`__auditory_calBandEdge` (auditory_filterBank.c:594-677)."""
+    det = 0 if is_edge else 2
+    lo = _fre_to_scale(low, scale, ref)
+    hi = _fre_to_scale(high, scale, ref)
+    pts = _linspace_f32(lo, hi, num + det)
+    fre = np.array([_scale_to_fre(p, scale, ref) for p in pts], dtype=f32)
+    if not slaney_bins:
+        bins = np.round((f32(n_fft) * fre).astype(f32) / f32(sr)).astype(np.int64)
+    else:
+        grid = _linspace_f32(0, f32(f32(sr) - f32(f32(sr) / f32(n_fft))), n_fft)
+        bins = np.zeros(num + det, dtype=np.int64)
+        for i in range(num + det):
+            j = np.nonzero(grid > fre[i])[0]
+            bins[i] = j[0] if j.size else 0
+    return fre, bins
+
+
+def auditory_filterbank(num, n_fft, sr, scale=SCALE_MEL, style=STYLE_SLANEY, norm=NORM_NONE,
+                        low=0.0, high=None, bpo=12):
+    """`auditory_filterBank` (auditory_filterBank.c:56-207) for Slaney / ETSI / window styles.
+
+    Returns (bank[num, n_fft/2+1] float32, fre_band[num], bin_band[num])."""
+    if high is None:
+        high = sr / 2.0
+    if style == STYLE_GAMMATONE:
+        raise NotImplementedError("gammatone banks are checked against oracle/_ref only")
+    m = n_fft // 2 + 1
+    low, high, ref = revise_edges(num, low, high, scale, n_fft, sr, bpo, is_edge=False)
+    fre, bins = band_edges(num, n_fft, sr, low, high, scale, ref, False, style == STYLE_SLANEY)
+    bank = np.zeros((num, m), dtype=np.float64)
+    fre64 = fre.astype(np.float64)
+    if scale == SCALE_LINEAR:                      # :339-365
+        bins = bins.copy()
+        for i in range(1, num + 1):
+            bins[i] -= 1
+            bank[i - 1, bins[i]] = 1.0
+    elif style == STYLE_SLANEY:                    # :435-500, triangles in Hz
+        grid = _linspace_f32(0, f32(f32(sr) - f32(f32(sr) / f32(n_fft))), n_fft).astype(np.float64)
+        w = (fre[1:] - fre[:-1]).astype(f32).astype(np.float64)
+        for i in range(num):
+            for j in range(bins[i], bins[i + 1]):
+                bank[i, j] = f32(f32(f32(grid[j]) - fre[i]) / f32(w[i]))
+            for j in range(bins[i + 1], bins[i + 2]):
+                bank[i, j] = f32(f32(fre[i + 2] - f32(grid[j])) / f32(w[i + 1]))
+    elif style == STYLE_ETSI:                      # :373-426, triangles in bins
+        for i in range(1, num + 1):
+            l, c, r = bins[i - 1], bins[i], bins[i + 1]
+            if c > l:
+                for j in range(l, c + 1):
+                    bank[i - 1, j] = (j - l) / (c - l)
+            for j in range(c + 1, r + 1):
+                bank[i - 1, j] = (r - j) / (r - c)
+    elif style == STYLE_POINT:                     # :229-237
+        for i in range(1, num + 1):
+            bank[i - 1, bins[i]] = 1.0
+    elif style == STYLE_RECT:                      # :238-248
+        for i in range(1, num + 1):
+            bank[i - 1, bins[i - 1]:bins[i + 1] + 1] = 1.0
+    else:                                          # window-design styles :249-316
+        kind = {STYLE_HANN: W_HANN, STYLE_HAMM: W_HAMM, STYLE_BLACKMAN: W_BLACKMAN,
+                STYLE_BOHMAN: W_BOHMAN, STYLE_KAISER: W_KAISER}.get(style, W_GAUSS)
+        for i in range(1, num + 1):
+            l, c, r = bins[i - 1], bins[i], bins[i + 1]
+            if c > l:
+                w = _symmetric_window(kind, 2 * (c - l) + 1)
+                bank[i - 1, l:c + 1] = w[:c - l + 1]
+            if r > c:
+                w = _symmetric_window(kind, 2 * (r - c) + 1)
+                k0 = (2 * (r - c) + 1) // 2 + 1
+                bank[i - 1, c + 1:r + 1] = w[k0:k0 + (r - c)]
+    bank = bank.astype(f32)
+    if scale != SCALE_LINEAR and norm in (NORM_AREA, NORM_BANDWIDTH):   # :479-496
+        if norm == NORM_AREA:
+            wt = bank.astype(np.float64).sum(axis=1)
+        else:
+            wt = (fre64[2:] - fre64[:-2]) / 2.0
+        with np.errstate(divide="ignore", invalid="ignore"):   # `__mdiv_vector` keeps exact zeros (flux_vector.c:289-308)
+            bank = np.where(bank != 0, bank / wt[:, None].astype(f32), f32(0)).astype(f32)
+    return bank, fre[1:num + 1].copy(), bins[1:num + 1].astype(np.int32)
+
+
+# ---------------------------------------------------------------------------
+# BFT  (src/bft_algorithm.c:87-276 defaults, 397-540 compute)
+# ---------------------------------------------------------------------------
+def bft_revise_range(num, n_fft, sr, low, high, scale, bpo):
+    """Range defaults/revisions done in `bftObj_new` (bft_algorithm.c:158-230)."""
+    lo = f32(0.0)
+    hi = f32(sr / 2.0)
+    if low is not None and 0 <= low < sr / 2.0:
+        lo = f32(low)
+    if lo == 0 and scale in (SCALE_OCTAVE, SCALE_LOG):
+        lo = f32(f32(math.pow(2.0, float(f32(-45 / 12.0)))) * f32(440))
+        hi = f32(f32(math.pow(2.0, float(f32(38 / 12.0)))) * f32(440))
+    if high is not None and 0 < high <= sr / 2.0:
+        hi = f32(high)
+    if hi < lo:
+        lo, hi = f32(0.0), f32(sr / 2.0)
+        if scale in (SCALE_OCTAVE, SCALE_LOG):
+            lo = f32(f32(math.pow(2.0, float(f32(-45 / 12.0)))) * f32(440))
+            hi = f32(f32(math.pow(2.0, float(f32(38 / 12.0)))) * f32(440))
+    low_idx = high_idx = 0
+    if scale == SCALE_LINEAR:
+        det = f32(f32(sr) / f32(n_fft))
+        l2 = f32(np.round(f32(lo / det)))
+        h2 = f32(l2 + f32(num - 1))
+        lo, hi = f32(l2 * det), f32(h2 * det)
+        low_idx, high_idx = int(np.round(f32(lo / det))), int(np.round(f32(hi / det)))
+    elif scale == SCALE_OCTAVE:
+        l2 = _fre_to_scale(lo, SCALE_OCTAVE, float(bpo))
+        h2 = f32(l2 + f32(num - 1))
+        lo, hi = _scale_to_fre(l2, SCALE_OCTAVE, float(bpo)), _scale_to_fre(h2, SCALE_OCTAVE, float(bpo))
+    return lo, hi, low_idx, high_idx
+
+
+def bft(x, num, radix2_exp, sr, hop=None, window_type=W_HANN, scale=SCALE_MEL, style=STYLE_SLANEY,
+        norm=NORM_NONE, data_type=DATA_POWER, low=None, high=None, bpo=12, result_type=1,
+        norm_value=1.0, bank=None):
+    """`bftObj_bft` (bft_algorithm.c:397-540).  result_type 1 -> real (T,num);
+    0 -> (re, im) each (T,num)."""
+    n = 1 << radix2_exp
+    hop = n // 4 if hop is None or hop <= 0 else hop
+    lo, hi, low_idx, high_idx = bft_revise_range(num, n, sr, low, high, scale, bpo)
+    if bank is None and scale != SCALE_LINEAR:
+        bank, _, _ = auditory_filterbank(num, n, sr, scale, style, norm, lo, hi, bpo)
+    re, im = stft(x, n, hop, fft_window(window_type, n))
+    re = re[:, :n // 2 + 1].astype(np.float64)
+    im = im[:, :n // 2 + 1].astype(np.float64)
+    if result_type == 0:                                    # :457-486
+        if data_type == DATA_POWER:
+            re, im = re * re - im * im, 2 * re * im
+        if scale == SCALE_LINEAR:
+            return re[:, low_idx:high_idx + 1].astype(f32), im[:, low_idx:high_idx + 1].astype(f32)
+        B = bank.astype(np.float64)
+        return (re @ B.T).astype(f32), (im @ B.T).astype(f32)
+    p = re * re + im * im                                   # :488-529
+    if data_type == DATA_MAG:
+        p = np.sqrt(p)
+    elif norm_value != 1:
+        p = np.power(p, norm_value)
+    if scale == SCALE_LINEAR:
+        out = p[:, low_idx:high_idx + 1]
+    else:
+        out = p.astype(f32).astype(np.float64) @ bank.astype(np.float64).T
+    if data_type == DATA_MAG and norm_value != 1:
+        out = np.power(out, norm_value)
+    return out.astype(f32)
+
+
+# ---------------------------------------------------------------------------
+# xxcc  (src/feature/xxcc_algorithm.c:95-156; DCT src/dsp/fft_algorithm.c:625-674,
+#        src/dsp/dct_algorithm.c:81-110)
+# ---------------------------------------------------------------------------
+def dct2_ortho_matrix(num):
+    k = np.arange(num)[:, None]
+    j = np.arange(num)[None, :]
+    C = np.cos(np.pi * (j + 0.5) * k / num)
+    s = np.full((num, 1), math.sqrt(2.0 / num))
+    s[0, 0] = math.sqrt(1.0 / num)
+    return C * s
+
+
+def xxcc(m, cc_num, rectify=RECT_LOG):
+    m = np.asarray(m, dtype=f32)
+    T, num = m.shape
+    if cc_num > num:
+        return None
+    if rectify == RECT_CUBIC:
+        r = np.power(m.astype(np.float64), 1.0 / 3)
+    else:
+        r = np.log10(np.maximum(m, f32(1e-8)).astype(np.float64))
+    return (r.astype(f32).astype(np.float64) @ dct2_ortho_matrix(num)[:cc_num].T).astype(f32)
+
+
+# ---------------------------------------------------------------------------
+# down-by-2 resampler used inside CQT (src/dsp/resample_algorithm.c:350-403, 430-521, 546-634)
+# ---------------------------------------------------------------------------
+def decimator_taps():
+    """Quality 'Fast': 16 zero crossings, 512 samples per crossing, Kaiser beta 8.5555046,
+    roll-off 0.85, scaled by ratio 0.5 -> taps interp[256*j].  32 left taps (j=0..31) and
+    31 right taps (j=0..30, applied to x[n+1+j]) because of the integer division
+    (interpLength-offset)/step with offset 0 (left) / 256 (right)."""
+    zero_num, bit_len = 16, 512
+    L = zero_num * bit_len + 1
+    t = np.linspace(0, zero_num, L) * 0.85
+    sinc = np.where(t == 0, 1.0, np.sin(np.pi * t) / np.where(t == 0, 1.0, np.pi * t)) * 0.85
+    win = _symmetric_window(W_KAISER, 2 * (L - 1) + 1, 8.5555046)[L - 1:]
+    interp = sinc * win * 0.5
+    left = interp[0:L:256][:32]            # offset 0: (8193-0)//256 = 32 taps
+    right = interp[256:L:256][:31]         # offset 256: (8193-256)//256 = 31 taps
+    return left.astype(f32), right.astype(f32)
+
+
+def resample_down2(x):
+    x = np.asarray(x, dtype=np.float64)
+    L = x.shape[0]
+    out_len = L // 2
+    left, right = decimator_taps()
+    left = left.astype(np.float64)
+    right = right.astype(np.float64)
+    xp = np.concatenate([np.zeros(32), x, np.zeros(64)])
+    n = 2 * np.arange(out_len) + 32
+    y = np.zeros(out_len)
+    for j in range(32):
+        y += left[j] * xp[n - j]
+    for j in range(31):
+        y += right[j] * xp[n + 1 + j]
+    return (y / math.sqrt(0.5)).astype(f32)
+
+
+# ---------------------------------------------------------------------------
+# CQT  (src/cqt_algorithm.c:123-247, 845-1061, 1181-1265; src/filterbank/cqt_filterBank.c)
+# ---------------------------------------------------------------------------
+def cqt_fre_arr(min_fre, num, bpo):
+    """cqt_filterBank.c:159-184 (float32 running product)."""
+    arr = np.zeros(num, dtype=f32)
+    v = f32(math.pow(2.0, float(f32(1.0 / bpo))))      # powf, correctly rounded
+    for i in range(num // bpo):
+        f = f32(f32(min_fre) * f32(1 << i))
+        arr[i * bpo] = f
+        for j in range(1, bpo):
+            f = f32(f * v)
+            arr[i * bpo + j] = f
+    return arr
+
+
+def cqt_len_arr(fre, sr, bpo, factor=1.0, beta=0.0):
+    """cqt_filterBank.c:187-213."""
+    value = f32(f32(math.pow(2.0, float(f32(1.0 / bpo)))) - f32(1))
+    q = f32(f32(factor) / value)
+    return np.array([f32(f32(q * f32(sr)) / f32(f + f32(f32(beta) / value))) for f in fre], dtype=f32)
+
+
+def _ceil_pow2(v):
+    p = 1
+    while p < v:
+        p <<= 1
+    return p
+
+
+def cqt_kernel_bank(num, sr, min_fre=32.703196, bpo=12, factor=1.0, beta=0.0, thresh=0.01,
+                    win_type=W_HANN, norm=NORM_NONE):
+    """Top-octave spectral kernels (cqt_algorithm.c:1181-1265, cqt_filterBank.c:57-148, 253-336).
+
+    Returns dict(fft_length, fre, slen(sqrt lengths), kr, ki) with kr/ki [bpo, n/2+1]."""
+    octs = num // bpo
+    fre = cqt_fre_arr(min_fre, num, bpo)
+    top = fre[(octs - 1) * bpo:]
+    value = f32(f32(math.pow(2.0, float(f32(1.0 / bpo)))) - f32(1))
+    q = f32(f32(factor) / value)
+    n = _ceil_pow2(int(np.ceil(f32(f32(q * f32(sr)) / f32(top[0] + f32(f32(beta) / value))))))
+    len_top = cqt_len_arr(top, sr, bpo, factor, beta)
+    slen = np.sqrt(cqt_len_arr(fre, sr, bpo, factor, beta)).astype(f32)
+    wt = win_type if win_type != W_RECT else W_HANN
+    kr = np.zeros((bpo, n // 2 + 1), dtype=f32)
+    ki = np.zeros((bpo, n // 2 + 1), dtype=f32)
+    for i in range(bpo):
+        ln = int(np.ceil(len_top[i]))
+        w = fft_window(wt, ln).astype(np.float64)
+        j = np.arange(ln, dtype=np.float64)
+        ph = 2 * np.pi * j * float(top[i]) / sr
+        weight = float(len_top[i]) if norm == NORM_NONE else 1.0
+        tr = np.cos(ph) * w / weight
+        ti = np.sin(ph) * w / weight
+        if norm == NORM_AREA:
+            s = np.sqrt(tr * tr + ti * ti).sum()
+            tr, ti = tr / s, ti / s
+        elif norm == NORM_BANDWIDTH:
+            full = np.concatenate([fre, [0.0, 0.0]])
+            k = (octs - 1) * bpo + i
+            bw = (float(full[k + 1]) - float(full[k - 1])) / 2
+            tr, ti = tr / bw, ti / bw
+        tr = tr * (float(len_top[i]) / n)
+        ti = ti * (float(len_top[i]) / n)
+        buf = np.zeros(n, dtype=np.complex128)
+        st = (n - ln) // 2
+        buf[st:st + ln] = tr + 1j * ti
+        K = np.fft.fft(buf)[:n // 2 + 1]
+        keep = (K.real.astype(f32).astype(np.float64) ** 2 + K.imag.astype(f32).astype(np.float64) ** 2) > float(f32(thresh) * f32(thresh))
+        kr[i] = np.where(keep, K.real, 0).astype(f32)
+        ki[i] = np.where(keep, K.imag, 0).astype(f32)
+    return dict(fft_length=n, fre=fre, slen=slen, kr=kr, ki=ki, octs=octs)
+
+
+def cqt(x, num=84, sr=32000, min_fre=32.703196, bpo=12, factor=1.0, beta=0.0, thresh=0.01,
+        win_type=W_HANN, hop=None, norm=NORM_NONE, is_scale=True, bank=None):
+    """`cqtObj_cqt` non-continue mode (cqt_algorithm.c:463-478, 845-1061) -> (re, im) [T, num]."""
+    if bank is None:
+        bank = cqt_kernel_bank(num, sr, min_fre, bpo, factor, beta, thresh, win_type, norm)
+    n, octs, slen = bank["fft_length"], bank["octs"], bank["slen"].astype(np.float64)
+    K = bank["kr"].astype(np.float64) + 1j * bank["ki"].astype(np.float64)
+    hop = n // 4 if hop is None or hop <= 0 else hop
+    x = np.asarray(x, dtype=f32)
+    L = x.shape[0]
+    T = L // hop + 1
+    out = np.zeros((T, num), dtype=np.complex128)
+    cur = x
+    rect = np.ones(n)
+    for o in range(octs - 1, -1, -1):
+        k = octs - 1 - o
+        if k > 0:
+            cur = resample_down2(cur)
+            hop //= 2
+        re, im = stft(cur, n, hop, rect, is_pad=True)
+        S = (re[:, :n // 2 + 1].astype(np.float64) + 1j * im[:, :n // 2 + 1].astype(np.float64))
+        Tn = min(T, S.shape[0])
+        v = S[:Tn] @ K.T
+        v = v * math.sqrt(float(1 << k)) if k > 0 else v
+        if is_scale:
+            v = v / slen[None, o * bpo:(o + 1) * bpo]
+        out[:Tn, o * bpo:(o + 1) * bpo] = v
+    return out.real.astype(f32), out.imag.astype(f32)
+
+
+# ---------------------------------------------------------------------------
+# CWT  (src/cwt_algorithm.c:73-334, 361-483; src/filterbank/cwt_filterBank.c:85-290, 361-640)
+# ---------------------------------------------------------------------------
+_WAVE_DEFAULTS = {WAVE_MORSE: (3.0, 20.0), WAVE_MORLET: (6.0, 2.0), WAVE_BUMP: (5.0, 0.6),
+                  WAVE_PAUL: (4.0, 20.0), WAVE_DOG: (2.0, 2.0), WAVE_MEXICAN: (3.0, 2.0),
+                  WAVE_HERMIT: (5.0, 2.0), WAVE_RICKER: (4.0, 20.0)}
+
+
+def cwt_revise_range(num, n, sr, low, high, scale, bpo):
+    """Range handling in `cwtObj_new` (cwt_algorithm.c:137-196): same rules as BFT."""
+    lo, hi, _, _ = bft_revise_range(num, n, sr, low, high, scale, bpo)
+    return lo, hi
+
+
+def cwt_filterbank(num, n, sr, wavelet=WAVE_MORLET, scale=SCALE_OCTAVE, low=None, high=None, bpo=12,
+                   gamma=None, beta=None, pad_length=0):
+    """`cwt_filterBank` (cwt_filterBank.c:85-290).  Returns (bank[num, n+2*pad] f32, fre_band[num])."""
+    g0, b0 = _WAVE_DEFAULTS[wavelet]
+    gamma = g0 if gamma is None or gamma <= 0 else gamma
+    beta = b0 if beta is None or beta <= 0 else beta
+    if wavelet == WAVE_DOG:
+        p = int(np.round(gamma))
+        gamma = float(p) if p % 2 == 0 else 2.0
+    lo, hi = cwt_revise_range(num, n, sr, low, high, scale, bpo)
+    lo, hi, ref = revise_edges(num, lo, hi, scale, n, sr, bpo, is_edge=False)
+    fre, _ = band_edges(num, n, sr, lo, hi, scale, ref, False, False)
+    if wavelet == WAVE_MORSE:
+        cf = float(f32(np.exp(f32(1.0 / gamma * float(f32(np.log(f32(beta)) - np.log(f32(gamma))))))))
+    elif wavelet in (WAVE_MORLET, WAVE_BUMP, WAVE_RICKER):
+        cf = gamma
+    elif wavelet == WAVE_PAUL:
+        cf = gamma + 0.5
+    elif wavelet == WAVE_DOG:
+        cf = math.sqrt(gamma + 0.5)
+    elif wavelet == WAVE_MEXICAN:
+        cf = math.sqrt(2.5)
+    else:
+        cf = gamma + 1
+    wl = n + 2 * pad_length
+    w = np.zeros(wl)
+    half = wl // 2
+    w[:half + 1] = np.arange(half + 1) * 2 * np.pi / wl
+    for i, j in zip(range(half + 1, wl), range(half - 1, -1, -1)):
+        w[i] = -w[j]
+    w = w.astype(f32).astype(np.float64)
+    fsel = np.maximum(fre[1:num + 1][::-1].astype(np.float64), 1e-6)
+    s = (cf / (fsel / sr * 2 * np.pi)).astype(f32).astype(np.float64)
+    sw = (s[:, None] * w[None, :]).astype(f32).astype(np.float64)
+    pos = sw > 0
+    swp = np.where(pos, sw, 1.0)
+    with np.errstate(over="ignore", invalid="ignore", divide="ignore"):
+        if wavelet == WAVE_MORSE:
+            fac = math.exp(-beta * math.log(cf) + cf ** gamma)
+            bank = np.where(pos, 2 * fac * np.exp(beta * np.log(swp) - swp ** gamma), 0.0)
+        elif wavelet == WAVE_MORLET:
+            bank = np.where(pos, 2 * np.exp(-(swp - gamma) ** 2 / beta), 0.0)
+        elif wavelet == WAVE_BUMP:
+            v1 = (sw - gamma) / beta
+            v2 = -1.0 / (1 - v1 * v1)
+            bank = np.where(np.abs(v1) < 1 - 1e-6, 2 * math.e * np.exp(v2), 0.0)
+            bank = np.nan_to_num(bank, nan=0.0)
+        elif wavelet == WAVE_PAUL:
+            p = int(np.round(gamma))
+            prod = 1.0
+            for i in range(2 * p - 1, 1, -1):
+                prod *= i
+            fac = 2.0 ** p / math.sqrt(p * prod)
+            bank = np.where(pos, fac * swp ** gamma * np.exp(-swp), 0.0)
+        elif wavelet in (WAVE_DOG, WAVE_MEXICAN):
+            g = 2.0 if wavelet == WAVE_MEXICAN else gamma
+            p = int(np.round(g))
+            fac = -1.0 / math.sqrt(math.gamma(p + 0.5))
+            if (p // 2) % 2 == 1:
+                fac = -fac
+            bank = np.where(pos, fac * swp ** g * np.exp(-swp * swp / beta), 0.0)
+        elif wavelet == WAVE_HERMIT:
+            fac = 2.0 / math.sqrt(gamma) * math.pi ** -0.25
+            d = swp - gamma
+            bank = np.where(pos, fac * d * (1 + d) * np.exp(-d * d / beta), 0.0)
+        else:  # ricker
+            fac = 2.0 / math.sqrt(math.pi)
+            bank = np.where(pos, fac * swp * swp / gamma ** 3 * np.exp(-swp * swp / (gamma * gamma)), 0.0)
+    return bank.astype(f32), fre[1:num + 1].copy()
+
+
+def cwt(x, num=84, radix2_exp=12, sr=32000, wavelet=WAVE_MORLET, scale=SCALE_OCTAVE, low=None,
+        high=None, bpo=12, gamma=None, beta=None, is_pad=False, bank=None):
+    """`cwtObj_cwt` (cwt_algorithm.c:346-350, 361-483) -> (re, im) [num, N]; row 0 = highest band."""
+    N = 1 << radix2_exp
+    x = np.asarray(x, dtype=np.float64)[:N]
+    pad = 0
+    if is_pad:
+        pad = N // 2 if N <= 1e5 else int(math.ceil(math.log2(N)))
+    if bank is None:
+        bank, _ = cwt_filterbank(num, N, sr, wavelet, scale, low, high, bpo, gamma, beta, pad)
+    if pad:
+        x = np.concatenate([x[:pad][::-1], x, x[N - pad:][::-1]])
+    X = np.fft.fft(x)
+    y = np.fft.ifft(bank.astype(np.float64) * X[None, :], axis=1)
+    if pad:
+        y = y[:, pad:pad + N]
+    return y.real.astype(f32), y.imag.astype(f32)
+
+
+# ---------------------------------------------------------------------------
+# convenience: the benchmark path (BFT mel power, result_type=1 -> xxcc)
+# ---------------------------------------------------------------------------
+def mfcc(x, sr=48000, radix2_exp=11, hop=512, n_mels=128, cc_num=40, norm=NORM_NONE, bank=None):
+    m = bft(x, n_mels, radix2_exp, sr, hop, W_HANN, SCALE_MEL, STYLE_SLANEY, norm, DATA_POWER,
+            result_type=1, bank=bank)
+    return xxcc(m, cc_num, RECT_LOG)
