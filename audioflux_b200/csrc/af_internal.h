@@ -1,0 +1,172 @@
+/* af_internal.h -- private declarations shared by the host C files and the CUDA launchers. */
+#ifndef AF_INTERNAL_H
+#define AF_INTERNAL_H
+
+#include <stddef.h>
+#include "../../include/afb200_ext.h"
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#ifndef M_PI
+#define M_PI 3.14159265358979323846
+#endif
+
+/* ---------------- errors / device context (host/af_ctx.c) ---------------- */
+#define AF_OK 0
+#define AF_ERR_ARG 10
+#define AF_ERR_CUDA 11
+#define AF_ERR_NOGPU 12
+#define AF_ERR_UNSUPPORTED 13
+#define AF_ERR_NOMEM 14
+
+int af_fail(int code, const char *fmt, ...);      /* records message, prints to stderr, returns code */
+void af_clear_error(void);
+int af_cuda_check(int cudaError, const char *what);   /* 0 ok, else AF_ERR_CUDA (message recorded) */
+int af_device_ready(void);                        /* 0 when a usable GPU is selected, else error */
+
+typedef struct {          /* growable device buffer */
+    void *ptr;
+    size_t bytes;
+} AfDevBuf;
+int af_devbuf_reserve(AfDevBuf *b, size_t bytes);
+void af_devbuf_free(AfDevBuf *b);
+int af_dev_upload(void **dptr, const void *host, size_t bytes);   /* cudaMalloc + H2D */
+void af_dev_free(void *dptr);
+int af_stream_create(void **stream);
+void af_stream_destroy(void *stream);
+int af_stream_sync(void *stream);
+int af_memcpy_h2d(void *dst, const void *src, size_t bytes, void *stream);
+int af_memcpy_d2h(void *dst, const void *src, size_t bytes, void *stream);
+int af_memset_d(void *dst, int v, size_t bytes, void *stream);
+size_t af_dev_free_bytes(void);
+int af_sm_count(void);
+
+/* ---------------- setup-time tables (host/af_window.c, af_filterbank.c, ...) ---------------- */
+int af_window_symmetric(int windowType, int length, const float *value, double *out);
+int af_window_fft(int windowType, int length, float *out);
+
+typedef struct {
+    float low, high;      /* after the range rules of bftObj_new / cwtObj_new */
+    int lowIndex, highIndex;   /* linear scale only */
+} AfRange;
+/* range defaults + Linear/Octave revisions shared by bftObj_new and cwtObj_new; returns 0 or -1 */
+int af_revise_range(int num, int fftLength, int samplate, const float *lowFre, const float *highFre,
+                    int scaleType, int binPerOctave, AfRange *out);
+/* num+2 band edges (Hz) and their bins; slaneyBins: 1 = first grid point above the edge */
+void af_band_edges(int num, int fftLength, int samplate, float lowFre, float highFre, int scaleType,
+                   int binPerOctave, int slaneyBins, int forCwt, float *freEdge, int *binEdge);
+int af_auditory_filterbank(int num, int fftLength, int samplate, int scaleType, int styleType,
+                           int normType, float lowFre, float highFre, int binPerOctave,
+                           float *bank, float *freBandArr, int *binBandArr);
+
+/* banded view of a dense row-major bank[num][width]: per row first non-zero and count */
+typedef struct {
+    int num, width;
+    int *start, *len;     /* num each */
+    int nnz, maxLen;
+} AfBands;
+int af_bands_build(const float *bank, int num, int width, AfBands *b);
+void af_bands_free(AfBands *b);
+
+void af_decimator_taps(float *left32, float *right31);
+
+typedef struct {
+    int num, binPerOctave, octaveNum, fftLength, samplate;
+    float *freBandArr;   /* num+2 */
+    float *sLenArr;      /* num: sqrt(kernel length) */
+    float *kr, *ki;      /* binPerOctave x (fftLength/2+1) spectral kernels, thresholded */
+} AfCqtBank;
+int af_cqt_bank_build(AfCqtBank *b, int num, int samplate, float minFre, int binPerOctave, float factor,
+                      float beta, float thresh, int windowType, int normType);
+void af_cqt_bank_free(AfCqtBank *b);
+/* time-domain kernels kappa[b][n] = sum_{k<=N/2} K[b][k] e^{-2 pi i k n/N}  -> 2 x bpo x N floats */
+int af_cqt_time_kernels(const AfCqtBank *b, float *kappaRe, float *kappaIm);
+
+typedef struct {
+    int waveletType;
+    float gamma, beta, cf;
+    double factor;       /* per-wavelet constant */
+} AfWavelet;
+int af_wavelet_setup(AfWavelet *w, int waveletType, const float *gamma, const float *beta);
+float af_wavelet_eval(const AfWavelet *w, float sw);   /* psi_hat(s*omega), host reference of the device fn */
+void af_cwt_scales(int num, int dataLength, int samplate, float lowFre, float highFre, int scaleType,
+                   int binPerOctave, float cf, float *freBandArr, int *binBandArr, float *scaleArr);
+
+void af_dct2_matrix(int num, int ccNum, float *out /* ccNum x num, ortho scaled */);
+void af_fft_twiddles(int n, float *cosArr, float *sinArr /* n/2 each: cos, -sin (2 pi i/n) */);
+
+/* ---------------- kernel launchers (kernels directory), all asynchronous on `stream` ---------------- */
+typedef struct {
+    int fftLength, slideLength;
+    int dataLength;       /* samples per clip */
+    int timeLength;       /* frames per clip */
+    int batch;
+    int padLeft;          /* zeros logically prepended (CQT centre padding) */
+    int validLength;      /* samples of the clip actually used (dataLength minus dropped tail) */
+    const float *window;  /* device, fftLength (NULL = rect) */
+    const float *data;    /* device, batch x dataLength */
+} AfFrameSrc;
+
+enum { AF_STFT_FULL = 0, AF_STFT_HALF = 1, AF_STFT_POWER = 2, AF_STFT_MAG = 3, AF_STFT_SQUARE = 4 };
+/* generic framed real FFT.  FULL: planes T x n mirrored; HALF: planes T x (n/2+1);
+ * POWER/MAG: outRe = |X|^2 or |X| (optionally ^normValue when POWER), T x (n/2+1);
+ * SQUARE: (re,im) <- X^2 complex square, T x (n/2+1). */
+int af_launch_stft(const AfFrameSrc *src, int mode, float normValue, float *outRe, float *outIm, void *stream);
+
+typedef struct {
+    int num, width;               /* width = fftLength/2+1 */
+    const float *dense;           /* device num x width */
+    const int *start, *len;       /* device, num each */
+    const float *packed;          /* device, band weights row after row */
+    const int *packedOff;         /* device, num each */
+    int banded;                   /* 1: use band kernels */
+    int maxLen;
+} AfBankDev;
+/* out[r][m] = sum_k in[r][k] * bank[m][k]  (rows = batch*T); optional out <- out^postPow */
+int af_launch_bank(const AfBankDev *bank, const float *in, int rows, float postPow, float *out, void *stream);
+int af_launch_copy_cols(const float *in, int rows, int width, int lo, int count, float *out, void *stream);
+/* rectify (0 log10 clamp 1e-8 | 1 cube root) then out[r][c] = sum_m D[c][m] * rect(in[r][m]) */
+int af_launch_xxcc(const float *in, int rows, int num, int ccNum, int rectifyType, const float *dct,
+                   float *out, void *stream);
+
+typedef struct {
+    int fftLength, slideLength, num, ccNum, rectifyType, dataType;
+    float normValue;
+    const float *window, *dct;    /* device */
+    AfBankDev bank;
+    /* fused-kernel specific tables (device), built by af_mfcc_plan_build */
+    void *plan;
+} AfMfccArgs;
+int af_mfcc_fused_supported(int fftLength, int num, int ccNum, const AfBands *bands);
+int af_mfcc_plan_build(void **plan, int fftLength, int num, int ccNum, const float *window,
+                       const float *bank, const AfBands *bands, const float *dct, int dataType);
+void af_mfcc_plan_free(void *plan);
+int af_launch_mfcc_fused(void *plan, const float *data, int dataLength, int batch, int timeLength,
+                         int slideLength, int rectifyType, float *out, void *stream);
+
+int af_launch_decimate2(const float *in, int inLength, int inStride, int batch, const float *left32,
+                        const float *right31, float *out, int outStride, void *stream);
+/* out[b][t][colOff + j] (row stride num) = scale[j] * sum_n xpad[t*hop + n] * kappa[j][n];
+ * kappa2 = interleaved (re, im) pairs [bpo][fftLength] */
+int af_launch_cqt_octave(const float *sig, int sigLength, int sigStride, int batch, int validLength,
+                         int fftLength, int hop, int timeLength, int bpo, const float *kappa2,
+                         const float *scale, int num, int colOff,
+                         float *outRe, float *outIm, void *stream);
+
+typedef struct {
+    int log2n, num, batch, padLength, dataLength;
+    AfWavelet wavelet;
+    const float *scaleArr;   /* device, num */
+} AfCwtArgs;
+size_t af_cwt_workspace_bytes(const AfCwtArgs *a);
+int af_launch_cwt(const AfCwtArgs *a, const float *data, void *workspace, float *outRe, float *outIm, void *stream);
+int af_launch_cwt_bank_table(const AfCwtArgs *a, float *bank /* device num x n */, void *stream);
+
+void af_count_launch(int n);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,318 @@
+/* af_bft.c -- BFT object of the C ABI: STFT -> power / magnitude -> filter bank (-> fused MFCC).
+ * Interface spec: /root/reference/src/bft_algorithm.h:14-57; behaviour src/bft_algorithm.c:87-276
+ * (parameter rules), :397-540 (compute).  Compute = kernels/stft_generic.cu + kernels/bank_xxcc.cu,
+ * or kernels/mfcc_fused.cu for the fftLength=2048 MFCC path. */
+#include <math.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+#include "../af_internal.h"
+
+struct OpaqueBFT {
+    int num, radix2Exp, fftLength, slideLength, samplate, binPerOctave;
+    float lowFre, highFre;
+    int lowIndex, highIndex;
+    WindowType windowType;
+    SpectralDataType dataType;
+    SpectralFilterBankScaleType scaleType;
+    SpectralFilterBankStyleType styleType;
+    SpectralFilterBankNormalType normalType;
+    float normValue;
+    int resultType;
+    /* host tables */
+    float *window, *bank, *freBandArr;
+    int *binBandArr;
+    AfBands bands;
+    /* device (lazy) */
+    int devReady;
+    void *stream;
+    float *dWindow, *dBank, *dPacked;
+    int *dStart, *dLen, *dOff;
+    AfBankDev bankDev;
+    AfDevBuf dIn, dSpecRe, dSpecIm, dOutRe, dOutIm;
+    /* fused MFCC plan cache */
+    void *mfccPlan;
+    int mfccPlanCc;
+    float *dDctT; int dctReady;          /* general path: transposed DCT [num][num] */
+};
+
+int bftObj_new(BFTObj *out, int num, int radix2Exp, int *samplate, float *lowFre, float *highFre,
+               int *binPerOctave, WindowType *windowType, int *slideLength,
+               SpectralFilterBankScaleType *scaleType, SpectralFilterBankStyleType *styleType,
+               SpectralFilterBankNormalType *normalType, SpectralDataType *dataType,
+               int *isReassign, int *isTemporal) {
+    if (!out) return -1;
+    *out = NULL;
+    int r = radix2Exp ? radix2Exp : 12;
+    if (r < 1 || r > 30) { printf("radix2Exp is error!\n"); return -100; }
+    const int n = 1 << r;
+    int sr = 32000;
+    if (samplate && *samplate > 0 && *samplate <= 196000) sr = *samplate;
+    SpectralFilterBankScaleType scale = scaleType ? *scaleType : SpectralFilterBankScale_Linear;
+    if (scale > SpectralFilterBankScale_Log) { printf("scaleType is error!\n"); return 1; }
+    int bpo = 12;
+    if (binPerOctave && *binPerOctave >= 4 && *binPerOctave <= 48) bpo = *binPerOctave;
+    AfRange range;
+    if (af_revise_range(num, n, sr, lowFre, highFre, scale, bpo, &range)) {
+        printf(scale == SpectralFilterBankScale_Linear ? "scale linear: lowFre and num is large, overflow error\n"
+                                                        : "scale log: lowFre and num is large, overflow error!\n");
+        return -1;
+    }
+    if (num < 2 || num > n / 2 + 1) { printf("num is error!\n"); return -1; }
+    if ((isReassign && *isReassign) || (isTemporal && *isTemporal)) {
+        af_fail(AF_ERR_UNSUPPORTED, "bftObj_new: isReassign / isTemporal are outside the accelerated path and not supported");
+        return -2;
+    }
+    if (r > 14) { af_fail(AF_ERR_UNSUPPORTED, "bftObj_new: radix2Exp > 14 is not supported"); return -2; }
+
+    BFTObj b = (BFTObj)calloc(1, sizeof(struct OpaqueBFT));
+    if (!b) return -1;
+    b->num = num; b->radix2Exp = r; b->fftLength = n; b->samplate = sr; b->binPerOctave = bpo;
+    b->lowFre = range.low; b->highFre = range.high; b->lowIndex = range.lowIndex; b->highIndex = range.highIndex;
+    b->windowType = windowType ? *windowType : Window_Hann;
+    b->slideLength = n / 4;
+    if (slideLength && *slideLength > 0) b->slideLength = *slideLength;
+    b->dataType = dataType ? *dataType : SpectralData_Power;
+    b->scaleType = scale;
+    b->styleType = styleType ? *styleType : SpectralFilterBankStyle_Slaney;
+    b->normalType = normalType ? *normalType : SpectralFilterBankNormal_None;
+    b->normValue = 1.0f;
+
+    const int width = n / 2 + 1;
+    b->window = (float *)malloc(sizeof(float) * (size_t)n);
+    b->bank = (float *)calloc((size_t)num * width, sizeof(float));
+    b->freBandArr = (float *)calloc((size_t)num + 2, sizeof(float));
+    b->binBandArr = (int *)calloc((size_t)num + 2, sizeof(int));
+    if (!b->window || !b->bank || !b->freBandArr || !b->binBandArr) { bftObj_free(b); return -1; }
+    af_window_fft(b->windowType, n, b->window);
+    if (scale == SpectralFilterBankScale_Linear) {
+        const float det = sr / (float)n;
+        for (int i = b->lowIndex, j = 0; i <= b->highIndex && j < num; i++, j++) {
+            b->freBandArr[j] = i * det; b->binBandArr[j] = i;
+            if (i < width) b->bank[(size_t)j * width + i] = 1.0f;
+        }
+    } else if (af_auditory_filterbank(num, n, sr, scale, b->styleType, b->normalType, b->lowFre, b->highFre,
+                                      bpo, b->bank, b->freBandArr, b->binBandArr)) {
+        bftObj_free(b);
+        return -2;
+    }
+    if (af_bands_build(b->bank, num, width, &b->bands)) { bftObj_free(b); return -1; }
+    *out = b;
+    return 0;
+}
+
+int bftObj_calTimeLength(BFTObj b, int dataLength) {
+    if (!b || dataLength < b->fftLength) return 0;
+    return (dataLength - b->fftLength) / b->slideLength + 1;
+}
+float *bftObj_getFreBandArr(BFTObj b) { return b ? b->freBandArr : NULL; }
+int *bftObj_getBinBandArr(BFTObj b) { return b ? b->binBandArr : NULL; }
+void bftObj_setResultType(BFTObj b, int type) { if (b) b->resultType = type; }
+void bftObj_setDataNormValue(BFTObj b, float v) { if (b && v > 0) b->normValue = v; }
+void bftObj_getTemporalData(BFTObj b, float **e, float **r, float **z) {
+    (void)b; (void)e; (void)r; (void)z;
+    af_fail(AF_ERR_UNSUPPORTED, "bftObj_getTemporalData: temporal features are not part of libaudioflux_b200");
+}
+int bftObj_getFilterBankArr(BFTObj b, float *bank) {
+    if (!b || !bank) return af_fail(AF_ERR_ARG, "bftObj_getFilterBankArr: bad argument");
+    memcpy(bank, b->bank, sizeof(float) * (size_t)b->num * (b->fftLength / 2 + 1));
+    return AF_OK;
+}
+
+static int bft_device(BFTObj b) {
+    int rc = af_device_ready();
+    if (rc) return rc;
+    if (b->devReady) return AF_OK;
+    if ((rc = af_stream_create(&b->stream))) return rc;
+    const int width = b->fftLength / 2 + 1, num = b->num;
+    if ((rc = af_dev_upload((void **)&b->dWindow, b->window, sizeof(float) * (size_t)b->fftLength))) return rc;
+    /* banded representation when the support is sparse, dense matrix otherwise */
+    int banded = (long long)b->bands.nnz * 4 <= (long long)num * width;
+    b->bankDev.num = num; b->bankDev.width = width; b->bankDev.banded = banded; b->bankDev.maxLen = b->bands.maxLen;
+    if (banded) {
+        int *off = (int *)malloc(sizeof(int) * (size_t)num);
+        float *packed = (float *)malloc(sizeof(float) * (size_t)(b->bands.nnz > 0 ? b->bands.nnz : 1));
+        if (!off || !packed) { free(off); free(packed); return AF_ERR_NOMEM; }
+        int o = 0;
+        for (int m = 0; m < num; m++) {
+            off[m] = o;
+            memcpy(packed + o, b->bank + (size_t)m * width + b->bands.start[m], sizeof(float) * (size_t)b->bands.len[m]);
+            o += b->bands.len[m];
+        }
+        rc = af_dev_upload((void **)&b->dPacked, packed, sizeof(float) * (size_t)(o > 0 ? o : 1));
+        if (!rc) rc = af_dev_upload((void **)&b->dOff, off, sizeof(int) * (size_t)num);
+        if (!rc) rc = af_dev_upload((void **)&b->dStart, b->bands.start, sizeof(int) * (size_t)num);
+        if (!rc) rc = af_dev_upload((void **)&b->dLen, b->bands.len, sizeof(int) * (size_t)num);
+        free(off); free(packed);
+        if (rc) return rc;
+        b->bankDev.packed = b->dPacked; b->bankDev.packedOff = b->dOff; b->bankDev.start = b->dStart; b->bankDev.len = b->dLen;
+    } else {
+        if ((rc = af_dev_upload((void **)&b->dBank, b->bank, sizeof(float) * (size_t)num * width))) return rc;
+        b->bankDev.dense = b->dBank;
+    }
+    b->devReady = 1;
+    return AF_OK;
+}
+
+/* device-resident compute: dData [batch x dataLength] -> dRe (and dIm) [batch x T x num] */
+static int bft_compute(BFTObj b, const float *dData, int dataLength, int batch, float *dRe, float *dIm, void *st) {
+    const int T = bftObj_calTimeLength(b, dataLength);
+    const int width = b->fftLength / 2 + 1;
+    if (T <= 0) return AF_OK;
+    const int linear = b->scaleType == SpectralFilterBankScale_Linear;
+    const int count = b->highIndex - b->lowIndex + 1 < b->num ? b->highIndex - b->lowIndex + 1 : b->num;
+    /* the spectrum workspace is bounded: process the batch in chunks of clips */
+    const size_t perClip = sizeof(float) * (size_t)T * width;
+    size_t budget = af_dev_free_bytes() / 4;
+    if (budget < perClip) budget = perClip;
+    if (budget > ((size_t)3 << 30)) budget = (size_t)3 << 30;
+    int chunk = (int)(budget / perClip);
+    if (chunk < 1) chunk = 1;
+    if (chunk > batch) chunk = batch;
+    int rc;
+    if ((rc = af_devbuf_reserve(&b->dSpecRe, perClip * chunk))) return rc;
+    if (!b->resultType && (rc = af_devbuf_reserve(&b->dSpecIm, perClip * chunk))) return rc;
+    for (int c0 = 0; c0 < batch; c0 += chunk) {
+        const int nb = batch - c0 < chunk ? batch - c0 : chunk;
+        AfFrameSrc src;
+        memset(&src, 0, sizeof(src));
+        src.fftLength = b->fftLength; src.slideLength = b->slideLength; src.dataLength = dataLength;
+        src.timeLength = T; src.batch = nb; src.validLength = dataLength; src.window = b->dWindow;
+        src.data = dData + (size_t)c0 * dataLength;
+        const int rows = nb * T;
+        float *oRe = dRe + (size_t)c0 * T * b->num;
+        float *oIm = dIm ? dIm + (size_t)c0 * T * b->num : NULL;
+        float *sRe = (float *)b->dSpecRe.ptr, *sIm = (float *)b->dSpecIm.ptr;
+        if (b->resultType) {                                  /* real: sum_k w |z|^2 (or |z|) */
+            const int mode = b->dataType == SpectralData_Mag ? AF_STFT_MAG : AF_STFT_POWER;
+            if ((rc = af_launch_stft(&src, mode, b->normValue, sRe, NULL, st))) return rc;
+            if (linear) {
+                if ((rc = af_launch_copy_cols(sRe, rows, width, b->lowIndex, count, oRe, st))) return rc;
+            } else {
+                float post = (b->dataType == SpectralData_Mag) ? b->normValue : 1.0f;
+                if ((rc = af_launch_bank(&b->bankDev, sRe, rows, post, oRe, st))) return rc;
+            }
+        } else {                                              /* complex: sum_k w z^2 (or z) */
+            const int mode = b->dataType == SpectralData_Power ? AF_STFT_SQUARE : AF_STFT_HALF;
+            if ((rc = af_launch_stft(&src, mode, 1.0f, sRe, sIm, st))) return rc;
+            if (linear) {
+                if ((rc = af_launch_copy_cols(sRe, rows, width, b->lowIndex, count, oRe, st))) return rc;
+                if (oIm && (rc = af_launch_copy_cols(sIm, rows, width, b->lowIndex, count, oIm, st))) return rc;
+            } else {
+                if ((rc = af_launch_bank(&b->bankDev, sRe, rows, 1.0f, oRe, st))) return rc;
+                if (oIm && (rc = af_launch_bank(&b->bankDev, sIm, rows, 1.0f, oIm, st))) return rc;
+            }
+        }
+    }
+    return AF_OK;
+}
+
+int bftObj_bftBatch(BFTObj b, const float *data, int dataLength, int batch, float *mReal3, float *mImag3,
+                    int memKind, void *stream) {
+    if (!b || !data || !mReal3 || dataLength <= 0 || batch <= 0) return af_fail(AF_ERR_ARG, "bftObj_bftBatch: bad argument");
+    af_clear_error();
+    int rc = bft_device(b);
+    if (rc) return rc;
+    const int T = bftObj_calTimeLength(b, dataLength);
+    if (T <= 0) return AF_OK;
+    void *st = stream ? stream : b->stream;
+    const int needIm = !b->resultType && mImag3;
+    if (memKind == AFB200_MEM_DEVICE) {
+        st = stream;                      /* NULL = the CUDA default stream */
+        if ((rc = bft_compute(b, data, dataLength, batch, mReal3, needIm ? mImag3 : NULL, st))) return rc;
+        return AF_OK;                       /* asynchronous on the caller's stream */
+    }
+    const size_t inB = sizeof(float) * (size_t)batch * dataLength, outB = sizeof(float) * (size_t)batch * T * b->num;
+    if ((rc = af_devbuf_reserve(&b->dIn, inB)) || (rc = af_devbuf_reserve(&b->dOutRe, outB))) return rc;
+    if (needIm && (rc = af_devbuf_reserve(&b->dOutIm, outB))) return rc;
+    if ((rc = af_memcpy_h2d(b->dIn.ptr, data, inB, st))) return rc;
+    if ((rc = bft_compute(b, (const float *)b->dIn.ptr, dataLength, batch, (float *)b->dOutRe.ptr,
+                          needIm ? (float *)b->dOutIm.ptr : NULL, st))) return rc;
+    if ((rc = af_memcpy_d2h(mReal3, b->dOutRe.ptr, outB, st))) return rc;
+    if (needIm && (rc = af_memcpy_d2h(mImag3, b->dOutIm.ptr, outB, st))) return rc;
+    return af_stream_sync(st);
+}
+
+void bftObj_bft(BFTObj b, float *dataArr, int dataLength, float *mRealArr3, float *mImageArr3) {
+    if (!b || !dataArr || !mRealArr3) return;
+    bftObj_bftBatch(b, dataArr, dataLength, 1, mRealArr3, mImageArr3, AFB200_MEM_HOST, NULL);
+}
+
+/* ---- fused / composed MFCC: bft(real mode) -> rectify -> ortho DCT-II -> first ccNum ---- */
+static int mfcc_compute(BFTObj b, const float *dData, int dataLength, int batch, int ccNum, int rectifyType,
+                        float *dOut, void *st) {
+    const int T = bftObj_calTimeLength(b, dataLength);
+    int rc;
+    const int fusable = b->normValue == 1.0f && b->scaleType != SpectralFilterBankScale_Linear &&
+                        b->bankDev.banded && af_mfcc_fused_supported(b->fftLength, b->num, ccNum, &b->bands) &&
+                        b->slideLength % 4 == 0 && dataLength % 4 == 0 && ((size_t)dData & 15) == 0;
+    if (fusable) {
+        if (!b->mfccPlan || b->mfccPlanCc != ccNum) {
+            af_mfcc_plan_free(b->mfccPlan); b->mfccPlan = NULL;
+            float *dct = (float *)malloc(sizeof(float) * (size_t)ccNum * b->num);
+            if (!dct) return AF_ERR_NOMEM;
+            af_dct2_matrix(b->num, ccNum, dct);
+            rc = af_mfcc_plan_build(&b->mfccPlan, b->fftLength, b->num, ccNum, b->window, b->bank, &b->bands, dct, b->dataType);
+            free(dct);
+            if (rc) return rc;
+            b->mfccPlanCc = ccNum;
+        }
+        return af_launch_mfcc_fused(b->mfccPlan, dData, dataLength, batch, T, b->slideLength, rectifyType, dOut, st);
+    }
+    /* general composition (any fftLength / bank / alignment), still entirely on the device */
+    if (!b->dctReady) {
+        const int n = b->num;
+        float *d = (float *)malloc(sizeof(float) * (size_t)n * n), *t = (float *)malloc(sizeof(float) * (size_t)n * n);
+        if (!d || !t) { free(d); free(t); return AF_ERR_NOMEM; }
+        af_dct2_matrix(n, n, d);
+        for (int k = 0; k < n; k++) for (int j = 0; j < n; j++) t[(size_t)j * n + k] = d[(size_t)k * n + j];
+        rc = af_dev_upload((void **)&b->dDctT, t, sizeof(float) * (size_t)n * n);
+        free(d); free(t);
+        if (rc) return rc;
+        b->dctReady = 1;
+    }
+    const int savedType = b->resultType;
+    b->resultType = 1;
+    const size_t melB = sizeof(float) * (size_t)batch * T * b->num;
+    rc = af_devbuf_reserve(&b->dOutIm, melB);          /* reuse as mel scratch */
+    if (!rc) rc = bft_compute(b, dData, dataLength, batch, (float *)b->dOutIm.ptr, NULL, st);
+    b->resultType = savedType;
+    if (rc) return rc;
+    return af_launch_xxcc((const float *)b->dOutIm.ptr, batch * T, b->num, ccNum, rectifyType, b->dDctT, dOut, st);
+}
+
+int bftObj_mfccBatch(BFTObj b, const float *data, int dataLength, int batch, int ccNum, int rectifyType,
+                     float *out, int memKind, void *stream) {
+    if (!b || !data || !out || dataLength <= 0 || batch <= 0) return af_fail(AF_ERR_ARG, "bftObj_mfccBatch: bad argument");
+    if (ccNum < 1 || ccNum > b->num) return af_fail(AF_ERR_ARG, "bftObj_mfccBatch: ccNum=%d outside [1, %d]", ccNum, b->num);
+    af_clear_error();
+    int rc = bft_device(b);
+    if (rc) return rc;
+    const int T = bftObj_calTimeLength(b, dataLength);
+    if (T <= 0) return AF_OK;
+    void *st = stream ? stream : b->stream;
+    if (memKind == AFB200_MEM_DEVICE) {
+        st = stream;                      /* NULL = the CUDA default stream */
+        if ((rc = mfcc_compute(b, data, dataLength, batch, ccNum, rectifyType, out, st))) return rc;
+        return AF_OK;                       /* asynchronous on the caller's stream */
+    }
+    const size_t inB = sizeof(float) * (size_t)batch * dataLength, outB = sizeof(float) * (size_t)batch * T * ccNum;
+    if ((rc = af_devbuf_reserve(&b->dIn, inB)) || (rc = af_devbuf_reserve(&b->dOutRe, outB))) return rc;
+    if ((rc = af_memcpy_h2d(b->dIn.ptr, data, inB, st))) return rc;
+    if ((rc = mfcc_compute(b, (const float *)b->dIn.ptr, dataLength, batch, ccNum, rectifyType, (float *)b->dOutRe.ptr, st))) return rc;
+    if ((rc = af_memcpy_d2h(out, b->dOutRe.ptr, outB, st))) return rc;
+    return af_stream_sync(st);
+}
+
+void bftObj_free(BFTObj b) {
+    if (!b) return;
+    af_mfcc_plan_free(b->mfccPlan);
+    af_devbuf_free(&b->dIn); af_devbuf_free(&b->dSpecRe); af_devbuf_free(&b->dSpecIm);
+    af_devbuf_free(&b->dOutRe); af_devbuf_free(&b->dOutIm);
+    af_dev_free(b->dWindow); af_dev_free(b->dBank); af_dev_free(b->dPacked);
+    af_dev_free(b->dStart); af_dev_free(b->dLen); af_dev_free(b->dOff); af_dev_free(b->dDctT);
+    af_stream_destroy(b->stream);
+    af_bands_free(&b->bands);
+    free(b->window); free(b->bank); free(b->freBandArr); free(b->binBandArr);
+    free(b);
+}

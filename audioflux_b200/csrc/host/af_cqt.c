@@ -1,0 +1,176 @@
+/* af_cqt.c -- CQT object of the C ABI (host C; compute = kernels/cqt.cu).
+ * Interface spec: /root/reference/src/cqt_algorithm.h:14-62; behaviour src/cqt_algorithm.c:110-247
+ * (parameters), :266-299 (time length), :845-1061 (octave recursion). */
+#include <math.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+#include "../af_internal.h"
+
+struct OpaqueCQT {
+    int num, samplate, binPerOctave, octaveNum, fftLength, slideLength, isScale;
+    float minFre;
+    AfCqtBank bank;
+    float *kappa2;                 /* host: interleaved (re, im) [bpo][fftLength] */
+    float left32[32], right31[32];
+    /* device (lazy) */
+    int devReady;
+    void *stream;
+    float *dKappa2, *dLeft, *dRight, *dScale;    /* dScale: octaveNum x bpo, rebuilt when isScale flips */
+    int scaleDirty;
+    AfDevBuf dIn, dSigA, dSigB, dOutRe, dOutIm;
+};
+
+int cqtObj_newWith(CQTObj *out, int num, int *samplate, float *minFre, int *binPerOctave, float *factor,
+                   float *beta, float *thresh, WindowType *windowType, int *slideLength, int *isContinue,
+                   SpectralFilterBankNormalType *normalType, int *isScale) {
+    if (!out) return -1;
+    *out = NULL;
+    int bpo = 12;
+    if (binPerOctave && *binPerOctave > 0) bpo = *binPerOctave;
+    if (bpo % 12 != 0) { printf("binPerOctave is error\n"); return -1; }
+    if (num < bpo || num % bpo != 0) { printf("num is error\n"); return -1; }
+    int sr = 32000; float fmin = 32.703196f, fac = 1, bet = 0, thr = 0.01f;
+    if (samplate && *samplate > 0) sr = *samplate;
+    if (minFre && *minFre > 0) fmin = *minFre;
+    if (factor && *factor > 0) fac = *factor;
+    if (beta && *beta > 0) bet = *beta;
+    if (thresh && *thresh > 0) thr = *thresh;
+    if (bet != 0) { af_fail(AF_ERR_UNSUPPORTED, "cqtObj_newWith: beta != 0 (VQT) is not supported"); return -2; }
+    if (isContinue && *isContinue) { af_fail(AF_ERR_UNSUPPORTED, "cqtObj_newWith: isContinue=1 (streaming) is not supported"); return -2; }
+    CQTObj c = (CQTObj)calloc(1, sizeof(struct OpaqueCQT));
+    if (!c) return -1;
+    c->num = num; c->samplate = sr; c->binPerOctave = bpo; c->octaveNum = num / bpo; c->minFre = fmin;
+    c->isScale = isScale ? *isScale : 1;
+    if (af_cqt_bank_build(&c->bank, num, sr, fmin, bpo, fac, bet, thr, windowType ? (int)*windowType : Window_Hann,
+                          normalType ? (int)*normalType : SpectralFilterBankNormal_None)) { cqtObj_free(c); return -1; }
+    c->fftLength = c->bank.fftLength;
+    c->slideLength = (slideLength && *slideLength > 0) ? *slideLength : c->fftLength / 4;
+    if ((c->slideLength >> (c->octaveNum - 1)) < 1) {
+        af_fail(AF_ERR_ARG, "cqtObj_newWith: slideLength %d cannot be halved %d times", c->slideLength, c->octaveNum - 1);
+        cqtObj_free(c); return -1;
+    }
+    const int n = c->fftLength;
+    float *kr = (float *)malloc(sizeof(float) * (size_t)bpo * n), *ki = (float *)malloc(sizeof(float) * (size_t)bpo * n);
+    c->kappa2 = (float *)malloc(sizeof(float) * 2 * (size_t)bpo * n);
+    if (!kr || !ki || !c->kappa2 || af_cqt_time_kernels(&c->bank, kr, ki)) { free(kr); free(ki); cqtObj_free(c); return -1; }
+    for (size_t i = 0; i < (size_t)bpo * n; i++) { c->kappa2[2 * i] = kr[i]; c->kappa2[2 * i + 1] = ki[i]; }
+    free(kr); free(ki);
+    af_decimator_taps(c->left32, c->right31);
+    c->scaleDirty = 1;
+    *out = c;
+    return 0;
+}
+
+int cqtObj_new(CQTObj *out, int num, int samplate, float minFre, int *isContinue) {
+    return cqtObj_newWith(out, num, &samplate, &minFre, NULL, NULL, NULL, NULL, NULL, NULL, isContinue, NULL, NULL);
+}
+
+int cqtObj_calTimeLength(CQTObj c, int dataLength) { return (!c || dataLength <= 0) ? 0 : dataLength / c->slideLength + 1; }
+int cqtObj_getFFTLength(CQTObj c) { return c ? c->fftLength : 0; }
+float *cqtObj_getFreBandArr(CQTObj c) { return c ? c->bank.freBandArr : NULL; }
+void cqtObj_setScale(CQTObj c, int flag) { if (c && c->isScale != flag) { c->isScale = flag; c->scaleDirty = 1; } }
+
+int cqtObj_getKernelBank(CQTObj c, float *kr, float *ki) {
+    if (!c || !kr || !ki) return af_fail(AF_ERR_ARG, "cqtObj_getKernelBank: bad argument");
+    size_t n = (size_t)c->binPerOctave * (c->fftLength / 2 + 1);
+    memcpy(kr, c->bank.kr, sizeof(float) * n); memcpy(ki, c->bank.ki, sizeof(float) * n);
+    return AF_OK;
+}
+
+static int cqt_device(CQTObj c) {
+    int rc = af_device_ready();
+    if (rc) return rc;
+    if (!c->devReady) {
+        if ((rc = af_stream_create(&c->stream))) return rc;
+        if ((rc = af_dev_upload((void **)&c->dKappa2, c->kappa2, sizeof(float) * 2 * (size_t)c->binPerOctave * c->fftLength))) return rc;
+        if ((rc = af_dev_upload((void **)&c->dLeft, c->left32, sizeof(float) * 32))) return rc;
+        if ((rc = af_dev_upload((void **)&c->dRight, c->right31, sizeof(float) * 32))) return rc;
+        c->devReady = 1;
+    }
+    if (c->scaleDirty) {
+        /* per (octave step k, bin j): sqrt(2^k) [/ sqrt(len)]  (cqt_algorithm.c:972-989, 1029-1036) */
+        const int bpo = c->binPerOctave, octs = c->octaveNum;
+        float *s = (float *)malloc(sizeof(float) * (size_t)octs * bpo);
+        if (!s) return AF_ERR_NOMEM;
+        for (int k = 0; k < octs; k++) {
+            const int o = octs - 1 - k;
+            const float d = k == 0 ? 1.0f : sqrtf((float)(1 << k));
+            for (int j = 0; j < bpo; j++) {
+                float v = d;
+                if (c->isScale) v = v / c->bank.sLenArr[o * bpo + j];
+                s[k * bpo + j] = v;
+            }
+        }
+        af_dev_free(c->dScale); c->dScale = NULL;
+        rc = af_dev_upload((void **)&c->dScale, s, sizeof(float) * (size_t)octs * bpo);
+        free(s);
+        if (rc) return rc;
+        c->scaleDirty = 0;
+    }
+    return AF_OK;
+}
+
+/* dData [batch x dataLength] -> planes [batch x T x num] */
+static int cqt_compute(CQTObj c, const float *dData, int dataLength, int batch, float *dRe, float *dIm, void *st) {
+    const int T = cqtObj_calTimeLength(c, dataLength);
+    if (T <= 0) return AF_OK;
+    int rc;
+    const size_t half = sizeof(float) * (size_t)batch * (dataLength / 2 + 1);
+    if (c->octaveNum > 1 && ((rc = af_devbuf_reserve(&c->dSigA, half)) || (rc = af_devbuf_reserve(&c->dSigB, half)))) return rc;
+    const float *sig = dData;
+    int len = dataLength, stride = dataLength, hop = c->slideLength;
+    for (int k = 0; k < c->octaveNum; k++) {
+        const int o = c->octaveNum - 1 - k;
+        if (k > 0) {
+            float *dst = (float *)((k & 1) ? c->dSigA.ptr : c->dSigB.ptr);
+            const int outStride = len / 2;
+            if ((rc = af_launch_decimate2(sig, len, stride, batch, c->dLeft, c->dRight, dst, outStride, st))) return rc;
+            sig = dst; len = len / 2; stride = outStride; hop /= 2;
+        }
+        if (len <= 0 || hop < 1) break;
+        /* padded STFT semantics: drop the tail that does not fill a hop when more than one frame exists */
+        const int frames = len / hop + 1;
+        const int valid = frames > 1 ? len - len % hop : len;
+        if ((rc = af_launch_cqt_octave(sig, len, stride, batch, valid, c->fftLength, hop, T, c->binPerOctave,
+                                       c->dKappa2, c->dScale + (size_t)k * c->binPerOctave, c->num,
+                                       o * c->binPerOctave, dRe, dIm, st))) return rc;
+    }
+    return AF_OK;
+}
+
+int cqtObj_cqtBatch(CQTObj c, const float *data, int dataLength, int batch, float *mReal3, float *mImag3,
+                    int memKind, void *stream) {
+    if (!c || !data || !mReal3 || !mImag3 || dataLength <= 0 || batch <= 0) return af_fail(AF_ERR_ARG, "cqtObj_cqtBatch: bad argument");
+    af_clear_error();
+    int rc = cqt_device(c);
+    if (rc) return rc;
+    const int T = cqtObj_calTimeLength(c, dataLength);
+    void *st = stream ? stream : c->stream;
+    if (memKind == AFB200_MEM_DEVICE) {
+        st = stream;
+        return cqt_compute(c, data, dataLength, batch, mReal3, mImag3, st);
+    }
+    const size_t inB = sizeof(float) * (size_t)batch * dataLength, outB = sizeof(float) * (size_t)batch * T * c->num;
+    if ((rc = af_devbuf_reserve(&c->dIn, inB)) || (rc = af_devbuf_reserve(&c->dOutRe, outB)) || (rc = af_devbuf_reserve(&c->dOutIm, outB))) return rc;
+    if ((rc = af_memcpy_h2d(c->dIn.ptr, data, inB, st))) return rc;
+    if ((rc = cqt_compute(c, (const float *)c->dIn.ptr, dataLength, batch, (float *)c->dOutRe.ptr, (float *)c->dOutIm.ptr, st))) return rc;
+    if ((rc = af_memcpy_d2h(mReal3, c->dOutRe.ptr, outB, st)) || (rc = af_memcpy_d2h(mImag3, c->dOutIm.ptr, outB, st))) return rc;
+    return af_stream_sync(st);
+}
+
+void cqtObj_cqt(CQTObj c, float *dataArr, int dataLength, float *mRealArr3, float *mImageArr3) {
+    if (!c || !dataArr || dataLength <= 0) return;
+    cqtObj_cqtBatch(c, dataArr, dataLength, 1, mRealArr3, mImageArr3, AFB200_MEM_HOST, NULL);
+}
+
+void cqtObj_free(CQTObj c) {
+    if (!c) return;
+    af_devbuf_free(&c->dIn); af_devbuf_free(&c->dSigA); af_devbuf_free(&c->dSigB);
+    af_devbuf_free(&c->dOutRe); af_devbuf_free(&c->dOutIm);
+    af_dev_free(c->dKappa2); af_dev_free(c->dLeft); af_dev_free(c->dRight); af_dev_free(c->dScale);
+    af_stream_destroy(c->stream);
+    af_cqt_bank_free(&c->bank);
+    free(c->kappa2);
+    free(c);
+}

@@ -1,0 +1,115 @@
+/* af_ctx.c -- device context, error reporting and device-memory helpers (host C over the CUDA
+ * runtime API).  There is no CPU compute path in this library: every compute entry point ends
+ * in a kernel launch or fails with a recorded message. */
+#include <stdarg.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+#include <cuda_runtime_api.h>
+#include "../af_internal.h"
+
+#define AFB200_VERSION 100   /* 0.1.0 */
+
+static __thread char g_err[512];
+static __thread int g_device = -1;          /* -1: follow the CUDA current device */
+static long long g_launches = 0;
+
+int af_fail(int code, const char *fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+    fprintf(stderr, "[audioflux_b200] error %d: %s\n", code, g_err);
+    return code;
+}
+
+void af_clear_error(void) { g_err[0] = 0; }
+const char *afb200_lastError(void) { return g_err; }
+int afb200_version(void) { return AFB200_VERSION; }
+
+int af_cuda_check(int e, const char *what) {
+    if (e == cudaSuccess) return AF_OK;
+    return af_fail(AF_ERR_CUDA, "%s: %s", what, cudaGetErrorString((cudaError_t)e));
+}
+
+int afb200_deviceCount(void) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+    return n;
+}
+
+int afb200_setDevice(int device) {
+    int n = afb200_deviceCount();
+    if (device < 0 || device >= n) return af_fail(AF_ERR_ARG, "afb200_setDevice(%d): %d device(s) visible", device, n);
+    g_device = device;
+    return af_cuda_check(cudaSetDevice(device), "cudaSetDevice");
+}
+
+int afb200_getDevice(void) {
+    int d = -1;
+    if (cudaGetDevice(&d) != cudaSuccess) { cudaGetLastError(); return -1; }
+    return d;
+}
+
+int af_device_ready(void) {
+    if (afb200_deviceCount() <= 0)
+        return af_fail(AF_ERR_NOGPU, "no CUDA device is visible: libaudioflux_b200 has no CPU fallback");
+    if (g_device >= 0) return af_cuda_check(cudaSetDevice(g_device), "cudaSetDevice");
+    return AF_OK;
+}
+
+int afb200_deviceSynchronize(void) { return af_cuda_check(cudaDeviceSynchronize(), "cudaDeviceSynchronize"); }
+long long afb200_kernelLaunchCount(void) { return g_launches; }
+void af_count_launch(int n) { __sync_fetch_and_add(&g_launches, (long long)n); }
+
+int af_devbuf_reserve(AfDevBuf *b, size_t bytes) {
+    if (b->bytes >= bytes && b->ptr) return AF_OK;
+    if (b->ptr) { cudaFree(b->ptr); b->ptr = NULL; b->bytes = 0; }
+    if (bytes == 0) return AF_OK;
+    int e = cudaMalloc(&b->ptr, bytes);
+    if (e != cudaSuccess) { b->ptr = NULL; return af_fail(AF_ERR_NOMEM, "cudaMalloc(%zu bytes): %s", bytes, cudaGetErrorString((cudaError_t)e)); }
+    b->bytes = bytes;
+    return AF_OK;
+}
+
+void af_devbuf_free(AfDevBuf *b) { if (b->ptr) cudaFree(b->ptr); b->ptr = NULL; b->bytes = 0; }
+
+int af_dev_upload(void **dptr, const void *host, size_t bytes) {
+    *dptr = NULL;
+    if (bytes == 0) return AF_OK;
+    int e = cudaMalloc(dptr, bytes);
+    if (e != cudaSuccess) { *dptr = NULL; return af_fail(AF_ERR_NOMEM, "cudaMalloc(%zu bytes): %s", bytes, cudaGetErrorString((cudaError_t)e)); }
+    return af_cuda_check(cudaMemcpy(*dptr, host, bytes, cudaMemcpyHostToDevice), "cudaMemcpy H2D (table)");
+}
+
+void af_dev_free(void *p) { if (p) cudaFree(p); }
+
+int af_stream_create(void **s) {
+    cudaStream_t st;
+    int e = cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking);
+    if (e != cudaSuccess) { *s = NULL; return af_cuda_check(e, "cudaStreamCreate"); }
+    *s = (void *)st;
+    return AF_OK;
+}
+void af_stream_destroy(void *s) { if (s) cudaStreamDestroy((cudaStream_t)s); }
+int af_stream_sync(void *s) { return af_cuda_check(cudaStreamSynchronize((cudaStream_t)s), "cudaStreamSynchronize"); }
+int af_memcpy_h2d(void *d, const void *h, size_t n, void *s) {
+    return af_cuda_check(cudaMemcpyAsync(d, h, n, cudaMemcpyHostToDevice, (cudaStream_t)s), "cudaMemcpyAsync H2D");
+}
+int af_memcpy_d2h(void *h, const void *d, size_t n, void *s) {
+    return af_cuda_check(cudaMemcpyAsync(h, d, n, cudaMemcpyDeviceToHost, (cudaStream_t)s), "cudaMemcpyAsync D2H");
+}
+int af_memset_d(void *d, int v, size_t n, void *s) {
+    return af_cuda_check(cudaMemsetAsync(d, v, n, (cudaStream_t)s), "cudaMemsetAsync");
+}
+size_t af_dev_free_bytes(void) {
+    size_t f = 0, t = 0;
+    if (cudaMemGetInfo(&f, &t) != cudaSuccess) { cudaGetLastError(); return 0; }
+    return f;
+}
+int af_sm_count(void) {
+    int d = 0, n = 0;
+    if (cudaGetDevice(&d) != cudaSuccess) return 0;
+    if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, d) != cudaSuccess) return 0;
+    return n;
+}

@@ -1,0 +1,159 @@
+/* af_cwt.c -- CWT object of the C ABI (host C; compute = kernels/cwt.cu).
+ * Interface spec: /root/reference/src/cwt_algorithm.h:14-45; behaviour src/cwt_algorithm.c:73-334
+ * (parameters), :361-483 (compute). */
+#include <math.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+#include "../af_internal.h"
+
+struct OpaqueCWT {
+    int num, radix2Exp, dataLength, padLength, fftLength, log2fft, samplate, binPerOctave;
+    float lowFre, highFre;
+    SpectralFilterBankScaleType scaleType;
+    AfWavelet wavelet;
+    float *freBandArr, *scaleArr;
+    int *binBandArr;
+    /* device (lazy) */
+    int devReady;
+    void *stream;
+    float *dScale;
+    AfDevBuf dIn, dWork, dOutRe, dOutIm;
+};
+
+int cwtObj_new(CWTObj *out, int num, int radix2Exp, int *samplate, float *lowFre, float *highFre,
+               int *binPerOctave, WaveletContinueType *waveletType, SpectralFilterBankScaleType *scaleType,
+               float *gamma, float *beta, int *isPad) {
+    if (!out) return -1;
+    *out = NULL;
+    if (radix2Exp < 1 || radix2Exp > 30) { printf("radix2Exp is error!\n"); return -100; }
+    int sr = 32000;
+    if (samplate && *samplate > 0 && *samplate <= 196000) sr = *samplate;
+    SpectralFilterBankScaleType scale = scaleType ? *scaleType : SpectralFilterBankScale_Octave;
+    if (scale > SpectralFilterBankScale_Log) { printf("scaleType is error!\n"); return 1; }
+    int bpo = 12;
+    if (binPerOctave && *binPerOctave >= 4 && *binPerOctave <= 48) bpo = *binPerOctave;
+    const int N = 1 << radix2Exp;
+    AfRange range;
+    if (af_revise_range(num, N, sr, lowFre, highFre, scale, bpo, &range)) {
+        printf(scale == SpectralFilterBankScale_Linear ? "scale linear: lowFre and num is large, overflow error\n"
+                                                        : "scale log: lowFre and num is large, overflow error!\n");
+        return -1;
+    }
+    if (num < 2 || num > N / 2 + 1) { printf("num is error!\n"); return -1; }
+    AfWavelet w;
+    if (af_wavelet_setup(&w, waveletType ? (int)*waveletType : WaveletContinue_Morse, gamma, beta)) return -1;
+    int pad = 0;
+    if (isPad && *isPad) pad = N <= 1e5 ? N / 2 : (int)ceilf(log2f((float)N));
+    const int fftLength = N + 2 * pad;
+    if (fftLength & (fftLength - 1)) {
+        af_fail(AF_ERR_UNSUPPORTED, "cwtObj_new: isPad with 2^%d samples gives a non power-of-two length %d "
+                "(the reference falls back to an O(N^2) dense DFT there); use isPad=0", radix2Exp, fftLength);
+        return -2;
+    }
+    CWTObj c = (CWTObj)calloc(1, sizeof(struct OpaqueCWT));
+    if (!c) return -1;
+    c->num = num; c->radix2Exp = radix2Exp; c->dataLength = N; c->padLength = pad; c->fftLength = fftLength;
+    c->log2fft = radix2Exp + (pad ? 1 : 0);
+    c->samplate = sr; c->binPerOctave = bpo; c->lowFre = range.low; c->highFre = range.high; c->scaleType = scale;
+    c->wavelet = w;
+    c->freBandArr = (float *)calloc((size_t)num + 2, sizeof(float));
+    c->binBandArr = (int *)calloc((size_t)num + 2, sizeof(int));
+    c->scaleArr = (float *)calloc((size_t)num, sizeof(float));
+    if (!c->freBandArr || !c->binBandArr || !c->scaleArr) { cwtObj_free(c); return -1; }
+    af_cwt_scales(num, N, sr, c->lowFre, c->highFre, scale, bpo, w.cf, c->freBandArr, c->binBandArr, c->scaleArr);
+    *out = c;
+    return 0;
+}
+
+float *cwtObj_getFreBandArr(CWTObj c) { return c ? c->freBandArr : NULL; }
+int *cwtObj_getBinBandArr(CWTObj c) { return c ? c->binBandArr : NULL; }
+
+static int cwt_device(CWTObj c) {
+    int rc = af_device_ready();
+    if (rc) return rc;
+    if (c->devReady) return AF_OK;
+    if ((rc = af_stream_create(&c->stream))) return rc;
+    if ((rc = af_dev_upload((void **)&c->dScale, c->scaleArr, sizeof(float) * (size_t)c->num))) return rc;
+    c->devReady = 1;
+    return AF_OK;
+}
+
+static void cwt_args(CWTObj c, int batch, AfCwtArgs *a) {
+    memset(a, 0, sizeof(*a));
+    a->log2n = c->log2fft; a->num = c->num; a->batch = batch; a->padLength = c->padLength;
+    a->dataLength = c->dataLength; a->wavelet = c->wavelet; a->scaleArr = c->dScale;
+}
+
+/* dData [batch x N] -> planes [batch x num x N]; the batch is cut into chunks that fit the workspace */
+static int cwt_compute(CWTObj c, const float *dData, int batch, float *dRe, float *dIm, void *st) {
+    AfCwtArgs a;
+    cwt_args(c, 1, &a);
+    const size_t perClip = af_cwt_workspace_bytes(&a);
+    size_t budget = af_dev_free_bytes() / 3 + c->dWork.bytes;
+    if (budget > ((size_t)24 << 30)) budget = (size_t)24 << 30;
+    int chunk = (int)(budget / perClip);
+    if (chunk < 1) chunk = 1;
+    if (chunk > batch) chunk = batch;
+    while ((long long)chunk * c->num > 0x7fffffffLL / 2) chunk /= 2;
+    int rc = af_devbuf_reserve(&c->dWork, perClip * (size_t)chunk);
+    if (rc) return rc;
+    const size_t outClip = (size_t)c->num * c->dataLength;
+    for (int c0 = 0; c0 < batch; c0 += chunk) {
+        const int nb = batch - c0 < chunk ? batch - c0 : chunk;
+        cwt_args(c, nb, &a);
+        if ((rc = af_launch_cwt(&a, dData + (size_t)c0 * c->dataLength, c->dWork.ptr, dRe + (size_t)c0 * outClip,
+                                dIm + (size_t)c0 * outClip, st))) return rc;
+    }
+    return AF_OK;
+}
+
+int cwtObj_cwtBatch(CWTObj c, const float *data, int batch, float *mReal4, float *mImag4, int memKind, void *stream) {
+    if (!c || !data || !mReal4 || !mImag4 || batch <= 0) return af_fail(AF_ERR_ARG, "cwtObj_cwtBatch: bad argument");
+    af_clear_error();
+    int rc = cwt_device(c);
+    if (rc) return rc;
+    void *st = stream ? stream : c->stream;
+    if (memKind == AFB200_MEM_DEVICE) {
+        st = stream;
+        return cwt_compute(c, data, batch, mReal4, mImag4, st);
+    }
+    /* host pointers: stream clip by clip so the device footprint stays one clip's planes */
+    const size_t inB = sizeof(float) * (size_t)c->dataLength, outB = sizeof(float) * (size_t)c->num * c->dataLength;
+    if ((rc = af_devbuf_reserve(&c->dIn, inB)) || (rc = af_devbuf_reserve(&c->dOutRe, outB)) || (rc = af_devbuf_reserve(&c->dOutIm, outB))) return rc;
+    for (int b = 0; b < batch; b++) {
+        if ((rc = af_memcpy_h2d(c->dIn.ptr, data + (size_t)b * c->dataLength, inB, st))) return rc;
+        if ((rc = cwt_compute(c, (const float *)c->dIn.ptr, 1, (float *)c->dOutRe.ptr, (float *)c->dOutIm.ptr, st))) return rc;
+        if ((rc = af_memcpy_d2h(mReal4 + (size_t)b * c->num * c->dataLength, c->dOutRe.ptr, outB, st)) ||
+            (rc = af_memcpy_d2h(mImag4 + (size_t)b * c->num * c->dataLength, c->dOutIm.ptr, outB, st))) return rc;
+        if ((rc = af_stream_sync(st))) return rc;
+    }
+    return AF_OK;
+}
+
+void cwtObj_cwt(CWTObj c, float *dataArr, float *mRealArr4, float *mImageArr4) {
+    if (!c || !dataArr) return;
+    cwtObj_cwtBatch(c, dataArr, 1, mRealArr4, mImageArr4, AFB200_MEM_HOST, NULL);
+}
+
+int cwtObj_getFilterBankArr(CWTObj c, float *bank) {
+    if (!c || !bank) return af_fail(AF_ERR_ARG, "cwtObj_getFilterBankArr: bad argument");
+    /* host evaluation of the same closed form the device uses (row 0 = highest band) */
+    const int n = c->fftLength;
+    for (int i = 0; i < c->num; i++)
+        for (int k = 0; k < n; k++) {
+            float v = 0.0f;
+            if (k <= n / 2) { float omega = (float)((double)k * 2.0 * M_PI / (double)n); v = af_wavelet_eval(&c->wavelet, c->scaleArr[i] * omega); }
+            bank[(size_t)i * n + k] = v;
+        }
+    return AF_OK;
+}
+
+void cwtObj_free(CWTObj c) {
+    if (!c) return;
+    af_devbuf_free(&c->dIn); af_devbuf_free(&c->dWork); af_devbuf_free(&c->dOutRe); af_devbuf_free(&c->dOutIm);
+    af_dev_free(c->dScale);
+    af_stream_destroy(c->stream);
+    free(c->freBandArr); free(c->binBandArr); free(c->scaleArr);
+    free(c);
+}

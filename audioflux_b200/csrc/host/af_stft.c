@@ -1,0 +1,165 @@
+/* af_stft.c -- STFT object of the C ABI (host C; compute = kernels/stft_generic.cu).
+ * Interface spec: /root/reference/src/stft_algorithm.h:14-40, behaviour src/stft_algorithm.c. */
+#include <math.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+#include "../af_internal.h"
+
+struct OpaqueSTFT {
+    int radix2Exp, fftLength, slideLength;
+    WindowType windowType;
+    int useWindow;                 /* window multiply needed (non-rect or user window) */
+    float *window;                 /* host, fftLength */
+    int isPad;
+    PaddingPositionType position;
+    PaddingModeType mode;
+    float padValue1, padValue2;
+    /* device side (lazy) */
+    int devReady, windowDirty;
+    void *stream;
+    float *dWindow;
+    AfDevBuf dIn, dRe, dIm;
+};
+
+int stftObj_new(STFTObj *out, int radix2Exp, WindowType *windowType, int *slideLength, int *isContinue) {
+    if (!out) return -1;
+    *out = NULL;
+    if (radix2Exp < 1 || radix2Exp > 30) return -100;
+    if (isContinue && *isContinue) {
+        af_fail(AF_ERR_UNSUPPORTED, "stftObj_new: isContinue=1 (streaming) is not supported by libaudioflux_b200");
+        return -2;
+    }
+    STFTObj s = (STFTObj)calloc(1, sizeof(struct OpaqueSTFT));
+    if (!s) return -1;
+    s->radix2Exp = radix2Exp;
+    s->fftLength = 1 << radix2Exp;
+    s->windowType = windowType ? *windowType : Window_Rect;
+    s->slideLength = s->fftLength / 4;
+    if (slideLength && *slideLength > 0) s->slideLength = *slideLength;
+    s->window = (float *)malloc(sizeof(float) * (size_t)s->fftLength);
+    if (!s->window) { free(s); return -1; }
+    af_window_fft(s->windowType, s->fftLength, s->window);
+    s->useWindow = s->windowType != Window_Rect;
+    s->position = PaddingPosition_Center;
+    s->mode = PaddingMode_Constant;
+    s->windowDirty = 1;
+    *out = s;
+    return 0;
+}
+
+void stftObj_setSlideLength(STFTObj s, int slideLength) { if (s && slideLength > 0) s->slideLength = slideLength; }
+void stftObj_enablePadding(STFTObj s, int flag) { if (s) s->isPad = flag; }
+void stftObj_enableContinue(STFTObj s, int flag) {
+    (void)s;
+    if (flag) af_fail(AF_ERR_UNSUPPORTED, "stftObj_enableContinue: streaming mode is not supported by libaudioflux_b200");
+}
+void stftObj_setPadding(STFTObj s, PaddingPositionType *position, PaddingModeType *mode, float *v1, float *v2) {
+    if (!s || !s->isPad) return;          /* like the reference: only honoured once padding is enabled */
+    if (position) s->position = *position;
+    if (mode) s->mode = *mode;
+    if (v1) s->padValue1 = *v1;
+    if (v2) s->padValue2 = *v2;
+}
+void stftObj_useWindowDataArr(STFTObj s, float *w) {
+    if (!s || !w) return;
+    memcpy(s->window, w, sizeof(float) * (size_t)s->fftLength);
+    s->useWindow = 1; s->windowDirty = 1;
+}
+float *stftObj_getWindowDataArr(STFTObj s) { return s ? s->window : NULL; }
+
+int stftObj_calTimeLength(STFTObj s, int dataLength) {
+    if (!s) return 0;
+    if (!s->isPad) return dataLength < s->fftLength ? 0 : (dataLength - s->fftLength) / s->slideLength + 1;
+    return dataLength <= 0 ? 0 : dataLength / s->slideLength + 1;
+}
+int stftObj_calDataLength(STFTObj s, int timeLength) { return s ? (timeLength - 1) * s->slideLength + s->fftLength : 0; }
+void stftObj_debug(STFTObj s) {
+    if (s) printf("stft params is: fftLength=%d, slideLength=%d\n", s->fftLength, s->slideLength);
+}
+
+static int stft_device(STFTObj s) {
+    int rc = af_device_ready();
+    if (rc) return rc;
+    if (!s->devReady) {
+        if ((rc = af_stream_create(&s->stream))) return rc;
+        s->devReady = 1;
+    }
+    if (s->windowDirty) {
+        af_dev_free(s->dWindow); s->dWindow = NULL;
+        if ((rc = af_dev_upload((void **)&s->dWindow, s->window, sizeof(float) * (size_t)s->fftLength))) return rc;
+        s->windowDirty = 0;
+    }
+    return AF_OK;
+}
+
+static int stft_frame_src(STFTObj s, int dataLength, int batch, AfFrameSrc *src) {
+    memset(src, 0, sizeof(*src));
+    src->fftLength = s->fftLength; src->slideLength = s->slideLength;
+    src->dataLength = dataLength; src->batch = batch;
+    src->timeLength = stftObj_calTimeLength(s, dataLength);
+    src->validLength = dataLength;
+    src->window = s->useWindow ? s->dWindow : NULL;
+    if (s->isPad) {
+        if (s->mode != PaddingMode_Constant || s->padValue1 != 0.0f || s->padValue2 != 0.0f)
+            return af_fail(AF_ERR_UNSUPPORTED, "STFT padding: only constant zero padding is supported (reflect/wrap/non-zero are not)");
+        /* the tail that does not fill a hop is dropped when more than one frame exists (stft_algorithm.c:813-826) */
+        if (src->timeLength > 1) src->validLength = dataLength - dataLength % s->slideLength;
+        src->padLeft = s->position == PaddingPosition_Center ? s->fftLength / 2
+                     : s->position == PaddingPosition_Left ? s->fftLength : 0;
+    }
+    return AF_OK;
+}
+
+void stftObj_stft(STFTObj s, float *dataArr, int dataLength, float *mRealArr, float *mImageArr) {
+    if (!s || !dataArr || dataLength <= 0 || !mRealArr || !mImageArr) return;
+    af_clear_error();
+    if (stft_device(s)) return;
+    AfFrameSrc src;
+    if (stft_frame_src(s, dataLength, 1, &src)) return;
+    if (src.timeLength <= 0) return;
+    size_t plane = sizeof(float) * (size_t)src.timeLength * s->fftLength;
+    if (af_devbuf_reserve(&s->dIn, sizeof(float) * (size_t)dataLength) || af_devbuf_reserve(&s->dRe, plane) ||
+        af_devbuf_reserve(&s->dIm, plane)) return;
+    if (af_memcpy_h2d(s->dIn.ptr, dataArr, sizeof(float) * (size_t)dataLength, s->stream)) return;
+    src.data = (const float *)s->dIn.ptr;
+    if (af_launch_stft(&src, AF_STFT_FULL, 1.0f, (float *)s->dRe.ptr, (float *)s->dIm.ptr, s->stream)) return;
+    if (af_memcpy_d2h(mRealArr, s->dRe.ptr, plane, s->stream) || af_memcpy_d2h(mImageArr, s->dIm.ptr, plane, s->stream)) return;
+    af_stream_sync(s->stream);
+}
+
+int stftObj_stftBatch(STFTObj s, const float *data, int dataLength, int batch, float *mReal, float *mImag,
+                      int memKind, void *stream) {
+    if (!s || !data || !mReal || !mImag || dataLength <= 0 || batch <= 0) return af_fail(AF_ERR_ARG, "stftObj_stftBatch: bad argument");
+    af_clear_error();
+    int rc = stft_device(s);
+    if (rc) return rc;
+    AfFrameSrc src;
+    if ((rc = stft_frame_src(s, dataLength, batch, &src))) return rc;
+    if (src.timeLength <= 0) return AF_OK;
+    const size_t inBytes = sizeof(float) * (size_t)batch * dataLength;
+    const size_t plane = sizeof(float) * (size_t)batch * src.timeLength * (s->fftLength / 2 + 1);
+    void *st = stream ? stream : s->stream;
+    if (memKind == AFB200_MEM_DEVICE) {
+        st = stream;                      /* NULL = the CUDA default stream */
+        src.data = data;
+        if ((rc = af_launch_stft(&src, AF_STFT_HALF, 1.0f, mReal, mImag, st))) return rc;
+        return AF_OK;                       /* asynchronous on the caller's stream */
+    }
+    if ((rc = af_devbuf_reserve(&s->dIn, inBytes)) || (rc = af_devbuf_reserve(&s->dRe, plane)) ||
+        (rc = af_devbuf_reserve(&s->dIm, plane))) return rc;
+    if ((rc = af_memcpy_h2d(s->dIn.ptr, data, inBytes, st))) return rc;
+    src.data = (const float *)s->dIn.ptr;
+    if ((rc = af_launch_stft(&src, AF_STFT_HALF, 1.0f, (float *)s->dRe.ptr, (float *)s->dIm.ptr, st))) return rc;
+    if ((rc = af_memcpy_d2h(mReal, s->dRe.ptr, plane, st)) || (rc = af_memcpy_d2h(mImag, s->dIm.ptr, plane, st))) return rc;
+    return af_stream_sync(st);
+}
+
+void stftObj_free(STFTObj s) {
+    if (!s) return;
+    af_devbuf_free(&s->dIn); af_devbuf_free(&s->dRe); af_devbuf_free(&s->dIm);
+    af_dev_free(s->dWindow);
+    af_stream_destroy(s->stream);
+    free(s->window);
+    free(s);
+}

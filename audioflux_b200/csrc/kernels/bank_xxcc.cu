@@ -1,0 +1,141 @@
+// bank_xxcc.cu -- filter-bank contraction and cepstral (rectify + DCT-II) kernels, general path.
+//
+// Replaces the reference's `__mdot1` / `__mcdot1` contractions of bftObj_bft
+// (src/bft_algorithm.c:481-485, 515-518; src/vector/flux_vector.c:55-86) and the rectify + per-frame
+// DCT loop of xxccObj_xxcc (src/feature/xxcc_algorithm.c:124-155).
+//
+// Slaney/ETSI banks are banded (2019 non-zeros of 131 200 at n=2048, num=128), so the banded kernel
+// walks only each filter's support; dense banks (gammatone-like) use a tiled FP32 contraction.
+#include <math.h>
+#include "common.cuh"
+
+namespace {
+
+// one warp per row; lane m walks the support of filters m, m+32, ... (fixed order -> bit-stable)
+__global__ void k_bank_banded(const float *__restrict__ in, long long rows, int width, int num,
+                              const int *__restrict__ start, const int *__restrict__ len,
+                              const float *__restrict__ packed, const int *__restrict__ off,
+                              float postPow, float *__restrict__ out) {
+    const long long row = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (row >= rows) return;
+    const int lane = threadIdx.x & 31;
+    const float *x = in + row * width;
+    for (int m = lane; m < num; m += 32) {
+        const int s = start[m], l = len[m];
+        const float *w = packed + off[m];
+        float acc = 0.0f;
+        for (int i = 0; i < l; i++) acc = fmaf(x[s + i], w[i], acc);
+        if (postPow != 1.0f) acc = powf(acc, postPow);
+        out[row * num + m] = acc;
+    }
+}
+
+// out[r][m] = sum_k in[r][k] * bank[m][k]; 64x64 output tile, K-slab 16, 4x4 register micro-tile
+__global__ void __launch_bounds__(256) k_bank_dense(const float *__restrict__ in, long long rows, int width, int num,
+                                                    const float *__restrict__ bank, float postPow,
+                                                    float *__restrict__ out) {
+    __shared__ float sa[16][64 + 1], sb[16][64 + 1];
+    const long long r0 = (long long)blockIdx.x * 64;
+    const int m0 = blockIdx.y * 64;
+    const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
+    float acc[4][4] = {};
+    for (int k0 = 0; k0 < width; k0 += 16) {
+        for (int e = threadIdx.x; e < 64 * 16; e += 256) {
+            int rr = e >> 4, kk = e & 15;
+            long long r = r0 + rr; int k = k0 + kk;
+            sa[kk][rr] = (r < rows && k < width) ? in[r * width + k] : 0.0f;
+            int m = m0 + rr;
+            sb[kk][rr] = (m < num && k < width) ? bank[(long long)m * width + k] : 0.0f;
+        }
+        __syncthreads();
+#pragma unroll
+        for (int kk = 0; kk < 16; kk++) {
+            float a[4], b[4];
+#pragma unroll
+            for (int i = 0; i < 4; i++) { a[i] = sa[kk][ty * 4 + i]; b[i] = sb[kk][tx * 4 + i]; }
+#pragma unroll
+            for (int i = 0; i < 4; i++)
+#pragma unroll
+                for (int j = 0; j < 4; j++) acc[i][j] = fmaf(a[i], b[j], acc[i][j]);
+        }
+        __syncthreads();
+    }
+    for (int i = 0; i < 4; i++)
+        for (int j = 0; j < 4; j++) {
+            long long r = r0 + ty * 4 + i; int m = m0 + tx * 4 + j;
+            if (r < rows && m < num) {
+                float v = acc[i][j];
+                if (postPow != 1.0f) v = powf(v, postPow);
+                out[r * num + m] = v;
+            }
+        }
+}
+
+__global__ void k_copy_cols(const float *__restrict__ in, long long rows, int width, int lo, int count,
+                            float *__restrict__ out) {
+    long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= rows * count) return;
+    long long r = i / count; int c = (int)(i % count);
+    out[i] = in[r * width + lo + c];
+}
+
+// one warp per row: rectify into shared memory, then lane c accumulates coefficient c, c+32, ...
+// dctT is the transposed ortho DCT-II matrix [num][ccStride] so lanes read consecutive floats.
+__global__ void k_xxcc(const float *__restrict__ in, long long rows, int num, int ccNum, int rectify,
+                       const float *__restrict__ dctT, int ccStride, float *__restrict__ out) {
+    extern __shared__ float sh[];
+    const int wib = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const long long row = (long long)blockIdx.x * (blockDim.x >> 5) + wib;
+    if (row >= rows) return;
+    float *l = sh + (size_t)wib * num;
+    for (int m = lane; m < num; m += 32) {
+        float v = in[row * num + m];
+        if (rectify == CepstralRectify_CubicRoot) v = powf(v, 1.0f / 3.0f);
+        else v = log10f(v < 1e-8f ? 1e-8f : v);
+        l[m] = v;
+    }
+    __syncwarp();
+    for (int c = lane; c < ccNum; c += 32) {
+        float acc = 0.0f;
+        for (int m = 0; m < num; m++) acc = fmaf(l[m], dctT[(size_t)m * ccStride + c], acc);
+        out[row * ccNum + c] = acc;
+    }
+}
+
+}  // namespace
+
+extern "C" int af_launch_bank(const AfBankDev *bank, const float *in, int rows, float postPow, float *out, void *stream) {
+    if (rows <= 0) return AF_OK;
+    cudaStream_t st = (cudaStream_t)stream;
+    if (bank->banded) {
+        const int warps = 8;
+        k_bank_banded<<<(unsigned)((rows + warps - 1) / warps), warps * 32, 0, st>>>(
+            in, rows, bank->width, bank->num, bank->start, bank->len, bank->packed, bank->packedOff, postPow, out);
+        AF_LAUNCH_CHECK("k_bank_banded");
+    } else {
+        dim3 grid((unsigned)((rows + 63) / 64), (unsigned)((bank->num + 63) / 64));
+        k_bank_dense<<<grid, 256, 0, st>>>(in, rows, bank->width, bank->num, bank->dense, postPow, out);
+        AF_LAUNCH_CHECK("k_bank_dense");
+    }
+    return AF_OK;
+}
+
+extern "C" int af_launch_copy_cols(const float *in, int rows, int width, int lo, int count, float *out, void *stream) {
+    long long total = (long long)rows * count;
+    if (total <= 0) return AF_OK;
+    k_copy_cols<<<(unsigned)((total + 255) / 256), 256, 0, (cudaStream_t)stream>>>(in, rows, width, lo, count, out);
+    AF_LAUNCH_CHECK("k_copy_cols");
+    return AF_OK;
+}
+
+extern "C" int af_launch_xxcc(const float *in, int rows, int num, int ccNum, int rectifyType, const float *dctT,
+                              float *out, void *stream) {
+    if (rows <= 0) return AF_OK;
+    const int warps = 8;
+    size_t smem = sizeof(float) * (size_t)warps * num;
+    if (smem > 48 * 1024) return af_fail(AF_ERR_UNSUPPORTED, "xxcc: num=%d too large", num);
+    k_xxcc<<<(unsigned)((rows + warps - 1) / warps), warps * 32, smem, (cudaStream_t)stream>>>(
+        in, rows, num, ccNum, rectifyType, dctT, num, out);
+    AF_LAUNCH_CHECK("k_xxcc");
+    return AF_OK;
+}

@@ -1,0 +1,314 @@
+// cwt.cu -- continuous wavelet transform: big forward FFT of the clip, then per scale
+// (wavelet(s*omega) * spectrum) -> inverse FFT, for N = 2^12 .. 2^22 points.
+//
+// Replaces `__cwtObj_cwt` (src/cwt_algorithm.c:361-483): reflect pad (:404-414), fftObj_fft (:417-422),
+// the num x N filter-bank multiply (:426-437), num inverse FFTs fftObj_ifft (:440-459) and the crop
+// (:447-452); and the num x N float table built by cwt_filterBank (src/filterbank/cwt_filterBank.c:85-290),
+// which is evaluated on the fly here (closed form in s*omega) instead of being read from HBM.
+//
+// FFT decomposition (four-step, N = N1 * N2, both <= 4096 so each leg lives in shared memory):
+//   columns kernel : N2 strided length-N1 transforms (+ inter-leg twiddle), `kCols` adjacent columns per CTA
+//                    so global accesses are contiguous runs;
+//   rows kernel    : N1 contiguous length-N2 transforms, `rows` adjacent rows per CTA so the strided
+//                    result is written as contiguous runs.
+// For N <= 4096 the columns kernel alone is the whole transform (N2 = 1).
+// Shared-memory legs use the same Stockham radix-4/2 autosort passes as stft_generic.cu.
+#include <math.h>
+#include "common.cuh"
+
+namespace {
+
+__device__ __forceinline__ float2 cw(int k, int m, float dir) {   // exp(dir * 2 pi i k / m)
+    float s, c;
+    sincospif(dir * 2.0f * (float)k / (float)m, &s, &c);
+    return make_float2(c, s);
+}
+
+// In-place-pair Stockham FFT over `cnt` independent sequences of length n = 2^log2n stored with pitch
+// `pitch` (float2 units) in a / b.  All threads of the CTA cooperate; result pointer returned.
+__device__ float2 *block_fft_multi(float2 *a, float2 *b, int log2n, int cnt, int pitch, float dir) {
+    const int n = 1 << log2n;
+    int P = 1, rem = log2n;
+    while (rem >= 2) {
+        const int t = n >> 2;
+        for (int e = threadIdx.x; e < t * cnt; e += blockDim.x) {
+            const int s = e / t, i = e - s * t;
+            const float2 *src = a + (size_t)s * pitch;
+            float2 *dst = b + (size_t)s * pitch;
+            const int k = i & (P - 1);
+            float2 u0 = src[i], u1 = src[i + t], u2 = src[i + 2 * t], u3 = src[i + 3 * t];
+            if (k) {
+                const float2 w1 = cw(k, 4 * P, dir);
+                const float2 w2 = af_cmul(w1, w1), w3 = af_cmul(w2, w1);
+                u1 = af_cmul(u1, w1); u2 = af_cmul(u2, w2); u3 = af_cmul(u3, w3);
+            }
+            const float2 s02 = make_float2(u0.x + u2.x, u0.y + u2.y), d02 = make_float2(u0.x - u2.x, u0.y - u2.y);
+            const float2 s13 = make_float2(u1.x + u3.x, u1.y + u3.y);
+            // (u1 - u3) * (dir * i):  forward (dir=-1): (y, -x);  inverse: (-y, x)
+            const float2 d13 = make_float2(-dir * (u1.y - u3.y), dir * (u1.x - u3.x));
+            const int j = ((i - k) << 2) + k;
+            dst[j] = make_float2(s02.x + s13.x, s02.y + s13.y);
+            dst[j + P] = make_float2(d02.x + d13.x, d02.y + d13.y);
+            dst[j + 2 * P] = make_float2(s02.x - s13.x, s02.y - s13.y);
+            dst[j + 3 * P] = make_float2(d02.x - d13.x, d02.y - d13.y);
+        }
+        __syncthreads();
+        float2 *tmp = a; a = b; b = tmp;
+        P <<= 2; rem -= 2;
+    }
+    if (rem == 1) {
+        const int t = n >> 1;
+        for (int e = threadIdx.x; e < t * cnt; e += blockDim.x) {
+            const int s = e / t, i = e - s * t;
+            const float2 *src = a + (size_t)s * pitch;
+            float2 *dst = b + (size_t)s * pitch;
+            const int k = i & (P - 1);
+            const float2 u0 = src[i];
+            float2 u1 = src[i + t];
+            if (k) u1 = af_cmul(u1, cw(k, 2 * P, dir));
+            const int j = ((i - k) << 1) + k;
+            dst[j] = make_float2(u0.x + u1.x, u0.y + u1.y);
+            dst[j + P] = make_float2(u0.x - u1.x, u0.y - u1.y);
+        }
+        __syncthreads();
+        float2 *tmp = a; a = b; b = tmp;
+    }
+    return a;
+}
+
+// psi_hat(s * omega): device twin of af_wavelet_eval (host/af_cwt_bank.c)
+__device__ float wavelet_eval(int type, float g, float b, float factor, float sw) {
+    if (type == WaveletContinue_Bump) {
+        const float r = (sw - g) / b;
+        if (!(fabsf(r) < 1.0f - 1e-6f)) return 0.0f;
+        const float v = 2.0f * 2.718281828459045f * expf(-1.0f / (1.0f - r * r));
+        return isnan(v) ? 0.0f : v;
+    }
+    if (!(sw > 0.0f)) return 0.0f;
+    switch (type) {
+    case WaveletContinue_Morse: {
+        const float pw = (g == 3.0f) ? sw * sw * sw : powf(sw, g);
+        return 2.0f * factor * expf(b * logf(sw) - pw);
+    }
+    case WaveletContinue_Morlet: return 2.0f * expf(-(sw - g) * (sw - g) / b);
+    case WaveletContinue_Paul: return (float)((double)factor * pow((double)sw, (double)g) * exp(-(double)sw));
+    case WaveletContinue_DOG: case WaveletContinue_Mexican:
+        return (float)((double)factor * pow((double)sw, (double)g) * exp(-(double)sw * sw / b));
+    case WaveletContinue_Hermit: {
+        const double d = (double)sw - g;
+        return (float)((double)factor * d * (1.0 + d) * exp(-d * d / b));
+    }
+    default: {  // Ricker
+        const double x = sw, gg = g;
+        return (float)((double)factor * x * x / (gg * gg * gg) * exp(-x * x / (gg * gg)));
+    }
+    }
+}
+
+struct CwtParams {
+    const float *data;        // batch x dataLength
+    float2 *spec;             // batch x N           (forward spectrum)
+    float2 *work;             // items x N           (inter-leg buffer; items = batch or batch*num)
+    float *outRe, *outIm;     // batch x num x dataLength
+    const float *scaleArr;    // num
+    int log2N, log2N1, log2N2, N, N1, N2;
+    int dataLength, padLength, num, batch;
+    int wType; float g, b, factor;
+    int cols, rows;           // adjacent columns / rows per CTA (chosen so each leg fits shared memory)
+};
+
+__device__ __forceinline__ float load_padded(const CwtParams &p, const float *x, int i) {
+    // reflect padding of padLength on both sides (cwt_algorithm.c:404-414)
+    int j = i - p.padLength;
+    if (j < 0) j = -j - 1;
+    else if (j >= p.dataLength) j = 2 * p.dataLength - 1 - j;
+    return x[j];
+}
+
+// MODE 0: forward, input = real clip (padded) ; MODE 1: inverse, input = wavelet(s*omega_k) * spec[k]
+template <int MODE>
+__global__ void k_cwt_cols(CwtParams p) {
+    extern __shared__ __align__(16) unsigned char smemRaw[];
+    const int N1 = p.N1, N2 = p.N2, pitch = N1 + 1;
+    float2 *a = reinterpret_cast<float2 *>(smemRaw), *b = a + (size_t)p.cols * pitch;
+    const int item = blockIdx.x;                                   // MODE 0: clip ; MODE 1: clip*num + scale
+    const int clip = MODE == 0 ? item : item / p.num;
+    const int sIdx = MODE == 0 ? 0 : item % p.num;
+    const int col0 = blockIdx.y * p.cols;
+    const int nc = min(p.cols, N2 - col0);
+    const float dir = MODE == 0 ? -1.0f : 1.0f;
+    const float s = MODE == 1 ? p.scaleArr[sIdx] : 0.0f;
+
+    for (int e = threadIdx.x; e < N1 * nc; e += blockDim.x) {
+        const int i = e / nc, c = e - i * nc;
+        const int k = i * N2 + col0 + c;                           // element of the length-N sequence
+        float2 v;
+        if (MODE == 0) {
+            v = make_float2(load_padded(p, p.data + (size_t)clip * p.dataLength, k), 0.0f);
+        } else {
+            // omega_k = 2 pi k / N for k <= N/2, negative above (every family is 0 there)
+            float wv = 0.0f;
+            if (k <= p.N / 2) {
+                const float omega = (float)((double)k * 2.0 * M_PI / (double)p.N);
+                wv = wavelet_eval(p.wType, p.g, p.b, p.factor, s * omega);
+            }
+            const float2 x = p.spec[(size_t)clip * p.N + k];
+            v = make_float2(wv * x.x, wv * x.y);
+        }
+        a[(size_t)c * pitch + i] = v;
+    }
+    __syncthreads();
+    float2 *r = block_fft_multi(a, b, p.log2N1, nc, pitch, dir);
+
+    if (N2 == 1) {
+        // whole transform done: r[0][k]
+        if (MODE == 0) {
+            for (int k = threadIdx.x; k < N1; k += blockDim.x) p.spec[(size_t)clip * p.N + k] = r[k];
+        } else {
+            const float inv = 1.0f / (float)p.N;
+            float *oRe = p.outRe + (size_t)item * p.dataLength, *oIm = p.outIm + (size_t)item * p.dataLength;
+            for (int k = threadIdx.x; k < p.dataLength; k += blockDim.x) {
+                const float2 v = r[k + p.padLength];
+                oRe[k] = v.x * inv; oIm[k] = v.y * inv;
+            }
+        }
+        return;
+    }
+    // inter-leg twiddle W_N^(dir * col * k1) and store B[k1][col] (row-major k1*N2 + col)
+    float2 *wk = p.work + (size_t)item * p.N;
+    for (int e = threadIdx.x; e < N1 * nc; e += blockDim.x) {
+        const int k1 = e / nc, c = e - k1 * nc;
+        const int col = col0 + c;
+        float2 v = r[(size_t)c * pitch + k1];
+        const long long prod = (long long)col * k1;               // < N
+        float sn, cs;
+        sincospif(dir * 2.0f * (float)((double)prod / (double)p.N), &sn, &cs);
+        v = af_cmul(v, make_float2(cs, sn));
+        wk[(size_t)k1 * N2 + col] = v;
+    }
+}
+
+template <int MODE>
+__global__ void k_cwt_rows(CwtParams p) {
+    extern __shared__ __align__(16) unsigned char smemRaw[];
+    const int N1 = p.N1, N2 = p.N2, pitch = N2 + 1;
+    float2 *a = reinterpret_cast<float2 *>(smemRaw), *b = a + (size_t)p.rows * pitch;
+    const int item = blockIdx.x;
+    const int clip = MODE == 0 ? item : item / p.num;
+    const int row0 = blockIdx.y * p.rows;
+    const int nr = min(p.rows, N1 - row0);
+    const float dir = MODE == 0 ? -1.0f : 1.0f;
+    const float2 *wk = p.work + (size_t)item * p.N;
+    for (int e = threadIdx.x; e < nr * N2; e += blockDim.x) {
+        const int rr = e / N2, i = e - rr * N2;
+        a[(size_t)rr * pitch + i] = wk[(size_t)(row0 + rr) * N2 + i];
+    }
+    __syncthreads();
+    float2 *r = block_fft_multi(a, b, p.log2N2, nr, pitch, dir);
+    // result element (row k1, k2) is sequence index k1 + N1*k2
+    if (MODE == 0) {
+        float2 *sp = p.spec + (size_t)clip * p.N;
+        for (int e = threadIdx.x; e < nr * N2; e += blockDim.x) {
+            const int k2 = e / nr, rr = e - k2 * nr;
+            sp[(size_t)k2 * N1 + row0 + rr] = r[(size_t)rr * pitch + k2];
+        }
+    } else {
+        const float inv = 1.0f / (float)p.N;
+        float *oRe = p.outRe + (size_t)item * p.dataLength, *oIm = p.outIm + (size_t)item * p.dataLength;
+        for (int e = threadIdx.x; e < nr * N2; e += blockDim.x) {
+            const int k2 = e / nr, rr = e - k2 * nr;
+            const long long n = (long long)k2 * N1 + row0 + rr - p.padLength;
+            if (n < 0 || n >= p.dataLength) continue;
+            const float2 v = r[(size_t)rr * pitch + k2];
+            oRe[n] = v.x * inv; oIm[n] = v.y * inv;
+        }
+    }
+}
+
+__global__ void k_cwt_bank_table(CwtParams p, float *bank) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= (long long)p.num * p.N) return;
+    const int sIdx = (int)(i / p.N), k = (int)(i % p.N);
+    float wv = 0.0f;
+    if (k <= p.N / 2) {
+        const float omega = (float)((double)k * 2.0 * M_PI / (double)p.N);
+        wv = wavelet_eval(p.wType, p.g, p.b, p.factor, p.scaleArr[sIdx] * omega);
+    }
+    bank[i] = wv;
+}
+
+void fill_params(const AfCwtArgs *a, CwtParams *p) {
+    p->log2N = a->log2n; p->N = 1 << a->log2n;
+    p->log2N1 = a->log2n <= 12 ? a->log2n : (a->log2n + 1) / 2;
+    p->log2N2 = a->log2n - p->log2N1;
+    p->N1 = 1 << p->log2N1; p->N2 = 1 << p->log2N2;
+    p->dataLength = a->dataLength; p->padLength = a->padLength; p->num = a->num; p->batch = a->batch;
+    p->scaleArr = a->scaleArr;
+    p->wType = a->wavelet.waveletType; p->g = a->wavelet.gamma; p->b = a->wavelet.beta; p->factor = (float)a->wavelet.factor;
+    const size_t budget = 160 * 1024;
+    p->cols = p->N2 == 1 ? 1 : 8;
+    while (p->cols > 1 && sizeof(float2) * 2 * (size_t)p->cols * (p->N1 + 1) > budget) p->cols >>= 1;
+    p->rows = 16;
+    while (p->rows > 1 && sizeof(float2) * 2 * (size_t)p->rows * (p->N2 + 1) > budget) p->rows >>= 1;
+}
+
+template <typename K>
+int set_smem(K kernel, size_t bytes, const char *name) {
+    if (bytes <= 48 * 1024) return AF_OK;
+    cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+    return e == cudaSuccess ? AF_OK : af_cuda_check(e, name);
+}
+
+}  // namespace
+
+// workspace = forward spectrum (batch x N float2) + inter-leg buffer (batch x num x N float2 when N > 4096)
+extern "C" size_t af_cwt_workspace_bytes(const AfCwtArgs *a) {
+    const size_t N = (size_t)1 << a->log2n;
+    size_t bytes = sizeof(float2) * N * (size_t)a->batch;
+    if (a->log2n > 12) bytes += sizeof(float2) * N * (size_t)a->batch * a->num;
+    return bytes;
+}
+
+extern "C" int af_launch_cwt(const AfCwtArgs *a, const float *data, void *workspace, float *outRe, float *outIm, void *stream) {
+    if (a->log2n < 2 || a->log2n > 24) return af_fail(AF_ERR_UNSUPPORTED, "CWT length 2^%d is outside [2^2, 2^24]", a->log2n);
+    CwtParams p;
+    fill_params(a, &p);
+    p.data = data; p.outRe = outRe; p.outIm = outIm;
+    p.spec = static_cast<float2 *>(workspace);
+    p.work = p.spec + (size_t)p.N * a->batch;
+    cudaStream_t st = (cudaStream_t)stream;
+    int rc;
+    const int threads = 512;
+    const size_t smemC = sizeof(float2) * 2 * (size_t)p.cols * (p.N1 + 1);
+    const size_t smemR = sizeof(float2) * 2 * (size_t)p.rows * (p.N2 + 1);
+    if (smemC > 220 * 1024 || smemR > 220 * 1024) return af_fail(AF_ERR_UNSUPPORTED, "CWT length 2^%d does not fit the shared-memory FFT legs", a->log2n);
+    if ((rc = set_smem(k_cwt_cols<0>, smemC, "smem k_cwt_cols<0>")) || (rc = set_smem(k_cwt_cols<1>, smemC, "smem k_cwt_cols<1>")) ||
+        (rc = set_smem(k_cwt_rows<0>, smemR, "smem k_cwt_rows<0>")) || (rc = set_smem(k_cwt_rows<1>, smemR, "smem k_cwt_rows<1>"))) return rc;
+    const unsigned colBlocks = (unsigned)((p.N2 + p.cols - 1) / p.cols);
+    const unsigned rowBlocks = (unsigned)((p.N1 + p.rows - 1) / p.rows);
+    // forward transform of every clip
+    k_cwt_cols<0><<<dim3((unsigned)a->batch, colBlocks), threads, smemC, st>>>(p);
+    AF_LAUNCH_CHECK("k_cwt_cols<0>");
+    if (p.N2 > 1) {
+        k_cwt_rows<0><<<dim3((unsigned)a->batch, rowBlocks), threads, smemR, st>>>(p);
+        AF_LAUNCH_CHECK("k_cwt_rows<0>");
+    }
+    // per (clip, scale): wavelet * spectrum -> inverse transform -> planes
+    const unsigned items = (unsigned)(a->batch * a->num);
+    k_cwt_cols<1><<<dim3(items, colBlocks), threads, smemC, st>>>(p);
+    AF_LAUNCH_CHECK("k_cwt_cols<1>");
+    if (p.N2 > 1) {
+        k_cwt_rows<1><<<dim3(items, rowBlocks), threads, smemR, st>>>(p);
+        AF_LAUNCH_CHECK("k_cwt_rows<1>");
+    }
+    return AF_OK;
+}
+
+extern "C" int af_launch_cwt_bank_table(const AfCwtArgs *a, float *bank, void *stream) {
+    CwtParams p;
+    fill_params(a, &p);
+    const long long total = (long long)p.num * p.N;
+    k_cwt_bank_table<<<(unsigned)((total + 255) / 256), 256, 0, (cudaStream_t)stream>>>(p, bank);
+    AF_LAUNCH_CHECK("k_cwt_bank_table");
+    return AF_OK;
+}

@@ -1,0 +1,179 @@
+// stft_generic.cu -- framed real FFT for any power-of-two fftLength in [4, 16384].
+//
+// Replaces the reference's per-frame loop `__vmul(window) ; fftObj_fft` (src/stft_algorithm.c:696-715,
+// 790-801), the Hermitian mirror of `_fftObj_fft` (src/dsp/fft_algorithm.c:309-317) and the
+// T x n -> T x (n/2+1) compaction `__mccut` (src/reassign_algorithm.c:600-604), plus the |S|^2 /
+// |S| / S^2 passes of bftObj_bft (src/bft_algorithm.c:458-504) as store modes.
+//
+// One CTA per frame.  The n real samples are packed as n/2 complex points, transformed by a
+// shared-memory Stockham radix-4 (+ one radix-2 when log2(n/2) is odd) autosort FFT and unpacked
+// with the real-FFT post-pass.  This is the general path; the MFCC configuration has its own
+// fused kernel (mfcc_fused.cu).
+#include <math.h>
+#include "common.cuh"
+
+namespace {
+
+struct StftParams {
+    const float *data;
+    const float *window;
+    float *outRe, *outIm;
+    long long dataStride;   // floats between clips
+    int n, nc, log2nc;
+    int hop, timeLength, padLeft, validLength;
+    int mode;
+    float normValue;
+};
+
+__device__ __forceinline__ float2 twiddle(int k, int m) {   // exp(-2 pi i k / m)
+    float s, c;
+    sincospif(-2.0f * (float)k / (float)m, &s, &c);
+    return make_float2(c, s);
+}
+
+__global__ void k_stft_generic(StftParams p) {
+    extern __shared__ float2 smem[];
+    float2 *a = smem, *b = smem + p.nc;
+    const int frame = blockIdx.x % p.timeLength;
+    const int clip = blockIdx.x / p.timeLength;
+    const float *x = p.data + (long long)clip * p.dataStride;
+    const int nc = p.nc, n = p.n;
+
+    // load + window, 2 real samples -> 1 complex point; logical signal = zeros(padLeft) ++ x[0:valid] ++ zeros
+    const int base = frame * p.hop - p.padLeft;
+    for (int i = threadIdx.x; i < nc; i += blockDim.x) {
+        int s0 = base + 2 * i, s1 = s0 + 1;
+        float v0 = (s0 >= 0 && s0 < p.validLength) ? x[s0] : 0.0f;
+        float v1 = (s1 >= 0 && s1 < p.validLength) ? x[s1] : 0.0f;
+        if (p.window) { v0 *= p.window[2 * i]; v1 *= p.window[2 * i + 1]; }
+        a[i] = make_float2(v0, v1);
+    }
+    __syncthreads();
+
+    // Stockham autosort passes: P = product of radices already applied
+    int P = 1, rem = p.log2nc;
+    while (rem >= 2) {
+        const int t = nc >> 2;
+        for (int i = threadIdx.x; i < t; i += blockDim.x) {
+            const int k = i & (P - 1);
+            float2 u0 = a[i], u1 = a[i + t], u2 = a[i + 2 * t], u3 = a[i + 3 * t];
+            if (k) {
+                float2 w1 = twiddle(k, 4 * P);
+                float2 w2 = af_cmul(w1, w1), w3 = af_cmul(w2, w1);
+                u1 = af_cmul(u1, w1); u2 = af_cmul(u2, w2); u3 = af_cmul(u3, w3);
+            }
+            float2 s02 = make_float2(u0.x + u2.x, u0.y + u2.y), d02 = make_float2(u0.x - u2.x, u0.y - u2.y);
+            float2 s13 = make_float2(u1.x + u3.x, u1.y + u3.y);
+            float2 d13 = make_float2(u1.y - u3.y, -(u1.x - u3.x));          // (u1-u3) * (-i)
+            const int j = ((i - k) << 2) + k;
+            b[j] = make_float2(s02.x + s13.x, s02.y + s13.y);
+            b[j + P] = make_float2(d02.x + d13.x, d02.y + d13.y);
+            b[j + 2 * P] = make_float2(s02.x - s13.x, s02.y - s13.y);
+            b[j + 3 * P] = make_float2(d02.x - d13.x, d02.y - d13.y);
+        }
+        __syncthreads();
+        float2 *tmp = a; a = b; b = tmp;
+        P <<= 2; rem -= 2;
+    }
+    if (rem == 1) {
+        const int t = nc >> 1;
+        for (int i = threadIdx.x; i < t; i += blockDim.x) {
+            const int k = i & (P - 1);
+            float2 u0 = a[i], u1 = a[i + t];
+            if (k) u1 = af_cmul(u1, twiddle(k, 2 * P));
+            const int j = ((i - k) << 1) + k;
+            b[j] = make_float2(u0.x + u1.x, u0.y + u1.y);
+            b[j + P] = make_float2(u0.x - u1.x, u0.y - u1.y);
+        }
+        __syncthreads();
+        float2 *tmp = a; a = b; b = tmp;
+    }
+
+    // real-FFT post-pass: X[k] = E[k] + W_n^k O[k], k = 0..nc
+    const int width = nc + 1;
+    const long long row = (long long)clip * p.timeLength + frame;
+    for (int k = threadIdx.x; k <= nc; k += blockDim.x) {
+        float2 zk = a[k == nc ? 0 : k], zp = a[k == 0 ? 0 : nc - k];
+        float er = 0.5f * (zk.x + zp.x), ei = 0.5f * (zk.y - zp.y);
+        float orr = 0.5f * (zk.y + zp.y), oi = -0.5f * (zk.x - zp.x);
+        float2 w = twiddle(k, n);
+        float xr = er + (w.x * orr - w.y * oi), xi = ei + (w.x * oi + w.y * orr);
+        if (k == 0 || k == nc) xi = 0.0f;
+        switch (p.mode) {
+        case AF_STFT_FULL: {
+            float *re = p.outRe + row * n, *im = p.outIm + row * n;
+            re[k] = xr; im[k] = xi;
+            if (k > 0 && k < nc) { re[n - k] = xr; im[n - k] = -xi; }
+        } break;
+        case AF_STFT_HALF:
+            p.outRe[row * width + k] = xr; p.outIm[row * width + k] = xi;
+            break;
+        case AF_STFT_SQUARE:
+            p.outRe[row * width + k] = xr * xr - xi * xi; p.outIm[row * width + k] = 2.0f * xr * xi;
+            break;
+        case AF_STFT_POWER: {
+            float v = xr * xr + xi * xi;
+            if (p.normValue != 1.0f) v = powf(v, p.normValue);
+            p.outRe[row * width + k] = v;
+        } break;
+        default:
+            p.outRe[row * width + k] = sqrtf(xr * xr + xi * xi);
+        }
+    }
+}
+
+// fftLength 2: X0 = x0 + x1, X1 = x0 - x1 (kept for API completeness: radix2Exp = 1 is legal)
+__global__ void k_stft_n2(StftParams p, long long frames) {
+    long long f = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (f >= frames) return;
+    const int frame = (int)(f % p.timeLength);
+    const int clip = (int)(f / p.timeLength);
+    const float *x = p.data + (long long)clip * p.dataStride;
+    int s0 = frame * p.hop - p.padLeft;
+    float v0 = (s0 >= 0 && s0 < p.validLength) ? x[s0] : 0.0f;
+    float v1 = (s0 + 1 >= 0 && s0 + 1 < p.validLength) ? x[s0 + 1] : 0.0f;
+    if (p.window) { v0 *= p.window[0]; v1 *= p.window[1]; }
+    float X[2] = {v0 + v1, v0 - v1};
+    for (int k = 0; k < 2; k++) {
+        float xr = X[k];
+        long long o = f * 2 + k;
+        switch (p.mode) {
+        case AF_STFT_FULL: case AF_STFT_HALF: p.outRe[o] = xr; p.outIm[o] = 0.0f; break;
+        case AF_STFT_SQUARE: p.outRe[o] = xr * xr; p.outIm[o] = 0.0f; break;
+        case AF_STFT_POWER: p.outRe[o] = p.normValue != 1.0f ? powf(xr * xr, p.normValue) : xr * xr; break;
+        default: p.outRe[o] = fabsf(xr);
+        }
+    }
+}
+
+}  // namespace
+
+extern "C" int af_launch_stft(const AfFrameSrc *src, int mode, float normValue, float *outRe, float *outIm, void *stream) {
+    const int n = src->fftLength;
+    if (n < 2 || (n & (n - 1))) return af_fail(AF_ERR_ARG, "fftLength %d is not a power of two", n);
+    if (n > 16384) return af_fail(AF_ERR_UNSUPPORTED, "STFT fftLength %d > 16384 is not supported by the shared-memory FFT", n);
+    const long long frames = (long long)src->batch * src->timeLength;
+    if (frames <= 0) return AF_OK;
+    if (frames > 0x7fffffffLL) return af_fail(AF_ERR_ARG, "too many frames in one launch");
+    StftParams p;
+    p.data = src->data; p.window = src->window; p.outRe = outRe; p.outIm = outIm;
+    p.dataStride = src->dataLength; p.n = n; p.nc = n / 2;
+    p.log2nc = 0; while ((1 << p.log2nc) < p.nc) p.log2nc++;
+    p.hop = src->slideLength; p.timeLength = src->timeLength; p.padLeft = src->padLeft;
+    p.validLength = src->validLength; p.mode = mode; p.normValue = normValue;
+    cudaStream_t st = (cudaStream_t)stream;
+    if (n == 2) {
+        k_stft_n2<<<(unsigned)((frames + 255) / 256), 256, 0, st>>>(p, frames);
+        AF_LAUNCH_CHECK("k_stft_n2");
+        return AF_OK;
+    }
+    int threads = p.nc / 4; if (threads < 32) threads = 32; if (threads > 1024) threads = 1024;
+    size_t smem = sizeof(float2) * 2 * (size_t)p.nc;
+    if (smem > 48 * 1024) {
+        cudaError_t e = cudaFuncSetAttribute(k_stft_generic, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return af_cuda_check(e, "cudaFuncSetAttribute(k_stft_generic)");
+    }
+    k_stft_generic<<<(unsigned)frames, threads, smem, st>>>(p);
+    AF_LAUNCH_CHECK("k_stft_generic");
+    return AF_OK;
+}

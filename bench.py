@@ -1,0 +1,343 @@
+#!/usr/bin/env python3
+"""bench.py -- MFCC frames/s (48 kHz, n_fft=2048, hop=512, 128 mel, 40 coefficients) on N B200s.
+
+Contract (see the task statement / DESIGN.md section 6):
+  python bench.py --gpus N --steps K --warmup W            (N>1: launched under torchrun, one rank per GPU)
+  python bench.py --impl reference ...                     (the reference's own CPU path, oracle/_ref)
+One JSON line on stdout from rank 0.
+
+A "step" is one pass of the fused STFT->mel->log->DCT path over one synthetic batch:
+  N=1 : BASELINE config 2 = 1024 clips x 5 s (983 MB of samples, larger than the 126 MB L2).
+  N>1 : the same 1024 clips PER GPU (weak scaling, config 5 at N=8) followed by the NCCL all-gather
+        of the (1024, 465, 40) result blocks, which is the path's only exchange step.
+`value` is device-timed (CUDA events on the launching stream) with inputs resident in HBM;
+`e2e` goes through the public call with pinned HOST buffers, H2D and D2H inside the timed region.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.realpath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+SR, RADIX, NFFT, HOP, NMEL, NCC = 48000, 11, 2048, 512, 128, 40
+CLIP_SECONDS = 5
+L = SR * CLIP_SECONDS
+T = (L - NFFT) // HOP + 1
+BATCH_PER_GPU = 1024
+# algorithmic (compulsory) HBM bytes per clip: every sample read once + result written once
+BYTES_PER_CLIP = 4 * L + 4 * T * NCC
+BYTES_PER_FRAME_READ_MODEL = 4 * NFFT + 4 * NCC     # north-star "each frame reads its window" accounting
+FLOP_PER_FRAME = 75e3
+
+
+def measured_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            return json.load(open(p)), "measured"
+        except Exception:
+            pass
+    return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0}, "fallback"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled every 200 ms during the timed region."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+         "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index=0):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-lms", "200", "-i", str(self.index)], stdout=subprocess.PIPE, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.25)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            try:
+                sm.append(float(r[1])); mx.append(float(r[2]))
+                for n, v in zip(names, r[5:9]):
+                    if v.lower().startswith("active"):
+                        reasons.add(n)
+            except Exception:
+                continue
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+# --------------------------------------------------------------------------- reference / CPU arm
+def _cpu_worker(args):
+    lib_path, seed, clips, warm = args
+    import ctypes
+    sys.path.insert(0, ROOT)
+    import audioflux_b200 as af
+    from audioflux_b200 import capi
+    lib = ctypes.CDLL(lib_path)
+    capi.bind(lib)
+    S, D = af.SpectralFilterBankScaleType, af.SpectralDataType
+    b = af.BFT(NMEL, RADIX, SR, slide_length=HOP, scale_type=S.MEL, data_type=D.POWER, _lib=lib)
+    xx = af.XXCC(NMEL, _lib=lib)
+    x = (0.1 * np.random.default_rng(seed).standard_normal((clips, L))).astype(np.float32)
+    for i in range(warm):
+        mel, _ = b.bft_planes(x[i % clips], 1)
+        xx.xxcc_planes(mel, NCC)
+    t0 = time.perf_counter()
+    for i in range(clips):
+        mel, _ = b.bft_planes(x[i], 1)
+        xx.xxcc_planes(mel, NCC)
+    return time.perf_counter() - t0
+
+
+def cpu_reference_rate(clips_per_worker, workers, warm=1):
+    """The reference's own C path (oracle/_ref: built-in radix-2 FFT + naive double-accumulated dot; no
+    FFTW/MKL/BLAS exist in this image) on `workers` independent processes, one object each, disjoint
+    clips -- the fair all-cores figure, since the reference's OpenMP only splits frames inside a clip."""
+    from oracle import ref_lib as R
+    import multiprocessing as mp
+    if not R.available():
+        return None
+    ctx = mp.get_context("spawn")
+    with ctx.Pool(workers) as pool:
+        t0 = time.perf_counter()
+        pool.map(_cpu_worker, [(R.REF_PATH, 1234 + i, clips_per_worker, warm) for i in range(workers)])
+        wall = time.perf_counter() - t0
+        # wall includes process start + warm-up; time a second, steady pass for the rate
+        t0 = time.perf_counter()
+        times = pool.map(_cpu_worker, [(R.REF_PATH, 4321 + i, clips_per_worker, 0) for i in range(workers)])
+        wall2 = time.perf_counter() - t0
+    busy = max(times)
+    return {"frames_per_s": workers * clips_per_worker * T / busy, "busy_s": busy, "wall_s": wall2, "first_wall_s": wall}
+
+
+def run_reference_arm(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0
+    cores = os.cpu_count() or 1
+    per = max(2, int(os.environ.get("AFB200_CPU_CLIPS_PER_WORKER", "4")))
+    vals = []
+    t_all = time.perf_counter()
+    for _ in range(max(1, args.warmup // 3)):
+        cpu_reference_rate(1, cores, warm=0)
+    for _ in range(max(1, min(args.steps, 3))):
+        r = cpu_reference_rate(per, cores)
+        if r is None:
+            print(json.dumps({"impl": "reference", "unavailable": "oracle/_ref/libaudioflux_ref.so not built"}))
+            return 0
+        vals.append(r["frames_per_s"])
+    v = float(np.median(vals))
+    frames_step = per * cores * T
+    line = {
+        "metric": "mfcc_frames_per_s", "value": v, "unit": "frames/s", "impl": "reference", "n_gpus": args.gpus,
+        "steps": len(vals), "warmup": args.warmup, "ms_per_step": 1e3 * frames_step / v, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": "MFCC(40) of 5 s 48 kHz clips, n_fft=2048 hop=512 mel=128 via bftObj_bft(resultType=1)+xxccObj_xxcc",
+                   "sample": f"{per} clips x {cores} worker processes per step"},
+        "cpu_baseline": {"value": v, "unit": "frames/s", "cores": cores, "kind": "reference",
+                         "sample": f"{per * cores} clips ({frames_step} frames) per step, {cores} processes x 1 object; "
+                                   "reference built with gcc -O3, built-in radix-2 FFT + naive dot (no FFTW/MKL/BLAS in the image)"},
+        "e2e": {"value": v, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0, "wall_s": time.perf_counter() - t_all,
+    }
+    print(json.dumps(line))
+    return 0
+
+
+# --------------------------------------------------------------------------- B200 arm
+def run_b200_arm(args):
+    import torch
+    import audioflux_b200 as af
+    from audioflux_b200 import lib as L_
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist_
+        dist = dist_
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    dev = torch.device("cuda", local)
+    lib = L_.get_lib()
+
+    B = args.batch
+    S, D = af.SpectralFilterBankScaleType, af.SpectralDataType
+    bft = af.BFT(NMEL, RADIX, SR, slide_length=HOP, scale_type=S.MEL, data_type=D.POWER)
+    g = torch.Generator(device=dev).manual_seed(1234 + 2 + rank)
+    x = 0.1 * torch.randn((B, L), generator=g, device=dev, dtype=torch.float32)
+    gathered = torch.empty((world * B, T, NCC), device=dev, dtype=torch.float32) if world > 1 else None
+
+    def step():
+        out = bft.mfcc_batch(x, NCC)
+        if world > 1:
+            dist.all_gather_into_tensor(gathered, out)
+        return out
+
+    # parity gate on this very configuration before any timing counts (clip 0 vs the numpy oracle)
+    parity = None
+    if rank == 0:
+        from oracle import af_oracle as O
+        out = step()
+        torch.cuda.synchronize()
+        want = O.mfcc(x[0].cpu().numpy(), SR, RADIX, HOP, NMEL, NCC)
+        parity = float(np.abs(out[0].cpu().numpy() - want).max() / np.abs(want).max())
+        if not parity < 1e-4:
+            print(json.dumps({"error": f"parity gate failed: rel err {parity}"}))
+            return 1
+
+    for _ in range(max(args.warmup, 3)):
+        step()
+    torch.cuda.synchronize()
+    if dist:
+        dist.barrier()
+
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    launches0 = lib.afb200_kernelLaunchCount()
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps + 1)]
+    kern_ms = []
+    torch.cuda.synchronize()
+    ev[0].record()
+    for i in range(args.steps):
+        if world > 1:
+            k0, k1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            k0.record(); out = bft.mfcc_batch(x, NCC); k1.record()
+            dist.all_gather_into_tensor(gathered, out)
+            kern_ms.append((k0, k1))
+        else:
+            step()
+        ev[i + 1].record()
+    torch.cuda.synchronize()
+    if dist:
+        dist.barrier()
+    launches = lib.afb200_kernelLaunchCount() - launches0
+    clocks = sampler.stop() if rank == 0 else None
+    total_ms = ev[0].elapsed_time(ev[-1])
+    per_step = [ev[i].elapsed_time(ev[i + 1]) for i in range(args.steps)]
+    kernel_ms = float(np.mean([a.elapsed_time(b) for a, b in kern_ms])) if kern_ms else float(np.mean(per_step))
+    t = torch.tensor([total_ms], device=dev)
+    if dist:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    total_ms = float(t.item())
+    ms_step = total_ms / args.steps
+    value = world * B * T / (ms_step * 1e-3)
+
+    # ---- end to end through the public API with HOST buffers (pinned), H2D + D2H inside the timed region
+    xh = torch.empty((B, L), dtype=torch.float32).pin_memory()
+    xh.copy_(x.cpu())
+    oh = torch.empty((B, T, NCC), dtype=torch.float32).pin_memory()
+    xd = torch.empty_like(x)
+
+    def e2e_step():
+        xd.copy_(xh, non_blocking=True)
+        out = bft.mfcc_batch(xd, NCC)
+        if world > 1:
+            dist.all_gather_into_tensor(gathered, out)
+        oh.copy_(out, non_blocking=True)
+
+    for _ in range(2):
+        e2e_step()
+    torch.cuda.synchronize()
+    if dist:
+        dist.barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    n_e2e = max(3, min(args.steps, 10))
+    e0.record()
+    for _ in range(n_e2e):
+        e2e_step()
+    e1.record()
+    torch.cuda.synchronize()
+    te = torch.tensor([e0.elapsed_time(e1)], device=dev)
+    if dist:
+        dist.all_reduce(te, op=dist.ReduceOp.MAX)
+    e2e_value = world * B * T / (float(te.item()) / n_e2e * 1e-3)
+
+    if rank != 0:
+        if dist:
+            dist.destroy_process_group()
+        return 0
+
+    peaks, peak_kind = measured_peaks()
+    achieved = B * BYTES_PER_CLIP / (kernel_ms * 1e-3) / 1e9
+    cores = os.cpu_count() or 1
+    cpu = None
+    if world == 1 and not args.no_cpu_baseline:
+        cpu = cpu_reference_rate(max(2, int(os.environ.get("AFB200_CPU_CLIPS_PER_WORKER", "4"))), cores)
+    line = {
+        "metric": "mfcc_frames_per_s", "value": value, "unit": "frames/s", "n_gpus": world, "steps": args.steps,
+        "warmup": max(args.warmup, 3), "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": f"BASELINE config {'2' if world == 1 else '5-shaped'}: batch={B} x 5 s 48 kHz clips per GPU, "
+                               "STFT(2048,hop 512,hann)->mel128(slaney)->log10->DCT MFCC(40), fused kernel",
+                   "batch_per_gpu": B, "clip_samples": L, "frames_per_clip": T,
+                   "l2": "inputs (983 MB per GPU) exceed the 126 MB L2; no explicit flush needed",
+                   "collective": "nccl all_gather of (B,T,40) per step" if world > 1 else "none",
+                   "parity_rel_err_clip0": parity},
+        "clocks": clocks,
+        "e2e": {"value": e2e_value, "unit": "frames/s", "h2d_bytes_per_step": B * L * 4, "d2h_bytes_per_step": B * T * NCC * 4,
+                "steps": n_e2e},
+        "gpu_launches": int(launches),
+        "roofline": {"bound": "hbm", "achieved": achieved, "peak": peaks["hbm_gbs"], "unit": "GB/s",
+                     "frac": achieved / peaks["hbm_gbs"], "traffic": None, "peak_kind": peak_kind,
+                     "kernel": "k_mfcc_fused<5>", "kernel_ms": kernel_ms, "algorithmic_bytes_per_launch": B * BYTES_PER_CLIP,
+                     "frame_read_model_frac": (B * T * BYTES_PER_FRAME_READ_MODEL / (kernel_ms * 1e-3) / 1e9) / peaks["hbm_gbs"],
+                     "fp32_tflops": B * T * FLOP_PER_FRAME / (kernel_ms * 1e-3) / 1e12},
+        "per_step_ms": per_step,
+    }
+    if cpu:
+        line["cpu_baseline"] = {"value": cpu["frames_per_s"], "unit": "frames/s", "cores": cores, "kind": "reference",
+                                "sample": f"{cores} processes x {max(2, int(os.environ.get('AFB200_CPU_CLIPS_PER_WORKER', '4')))} clips, "
+                                          "oracle/_ref (gcc -O3, built-in radix-2 FFT + naive dot)"}
+    print(json.dumps(line))
+    if dist:
+        dist.destroy_process_group()
+    return 0
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--batch", type=int, default=BATCH_PER_GPU, help="clips per GPU (default: BASELINE config 2)")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        return run_reference_arm(args)
+    return run_b200_arm(args)
+
+
+if __name__ == "__main__":
+    sys.exit(main())

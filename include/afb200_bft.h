@@ -1,0 +1,32 @@
+/* afb200_bft.h -- BFT object: STFT -> power/magnitude -> mel/bark/erb/... filter bank.
+ * Replaces /root/reference/src/bft_algorithm.h:14-57 (implementation src/bft_algorithm.c). */
+#ifndef AFB200_BFT_H
+#define AFB200_BFT_H
+#include "afb200_types.h"
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct OpaqueBFT *BFTObj;
+
+/* bft_algorithm.c:87-276.  Returns 0 ok; -100 bad radix2Exp; 1 scale > Log; -1 bad num /
+ * range overflow; -2 for isReassign / isTemporal (outside the hot path, rejected loudly). */
+int bftObj_new(BFTObj *bftObj, int num, int radix2Exp, int *samplate, float *lowFre, float *highFre,
+               int *binPerOctave, WindowType *windowType, int *slideLength,
+               SpectralFilterBankScaleType *filterScaleType, SpectralFilterBankStyleType *filterStyleType,
+               SpectralFilterBankNormalType *filterNormalType, SpectralDataType *dataType,
+               int *isReassign, int *isTemporal);
+int bftObj_calTimeLength(BFTObj bftObj, int dataLength);          /* :550-555 */
+float *bftObj_getFreBandArr(BFTObj bftObj);                       /* :557-560, borrowed, num floats */
+int *bftObj_getBinBandArr(BFTObj bftObj);                         /* :562-565, borrowed, num ints */
+void bftObj_setResultType(BFTObj bftObj, int type);               /* :568-571, 0 complex 1 real */
+void bftObj_setDataNormValue(BFTObj bftObj, float normValue);     /* :573-578 */
+/* :397-540.  mRealArr3/mImageArr3: timeLength x num (mImageArr3 untouched when resultType=1). */
+void bftObj_bft(BFTObj bftObj, float *dataArr, int dataLength, float *mRealArr3, float *mImageArr3);
+void bftObj_getTemporalData(BFTObj bftObj, float **eArr, float **rArr, float **zArr); /* :543-548, unsupported */
+void bftObj_free(BFTObj bftObj);                                  /* :580-626 */
+
+#ifdef __cplusplus
+}
+#endif
+#endif

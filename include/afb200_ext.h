@@ -1,0 +1,71 @@
+/* afb200_ext.h -- ADDITIVE entry points of libaudioflux_b200.so (no reference counterpart).
+ *
+ * The reference API is one clip per call with host pointers (python/audioflux/bft.py:349-365
+ * loops channels in Python); fed that way a B200 is PCIe/launch bound.  These entry points
+ * take a whole batch and either host or device pointers.
+ *
+ *   memKind 0: host pointers (pageable or pinned) -- copies + sync happen inside the call.
+ *   memKind 1: device pointers on the current device -- asynchronous on `stream`
+ *              (a cudaStream_t passed as void*; NULL = the CUDA default stream).  The call
+ *              returns without synchronising; results are ordered on that stream.
+ * All return 0 on success, non-zero on failure with afb200_lastError() describing it.
+ * Layouts are the reference's: row-major, time-major, separate real/imag float planes.
+ */
+#ifndef AFB200_EXT_H
+#define AFB200_EXT_H
+#include "afb200_stft.h"
+#include "afb200_bft.h"
+#include "afb200_xxcc.h"
+#include "afb200_cqt.h"
+#include "afb200_cwt.h"
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define AFB200_MEM_HOST 0
+#define AFB200_MEM_DEVICE 1
+
+int afb200_version(void);
+int afb200_deviceCount(void);              /* 0 when no usable GPU (compute calls then fail loudly) */
+int afb200_setDevice(int device);          /* device used by objects created / run from this thread */
+int afb200_getDevice(void);
+const char *afb200_lastError(void);        /* thread-local message of the last failure */
+long long afb200_kernelLaunchCount(void);  /* kernels launched by this library since load */
+int afb200_deviceSynchronize(void);
+
+/* data: batch x dataLength; out planes: batch x T x (fftLength/2+1) */
+int stftObj_stftBatch(STFTObj stftObj, const float *data, int dataLength, int batch,
+                      float *mReal, float *mImag, int memKind, void *stream);
+/* out: batch x T x num (mImag3 may be NULL when resultType=1) */
+int bftObj_bftBatch(BFTObj bftObj, const float *data, int dataLength, int batch,
+                    float *mReal3, float *mImag3, int memKind, void *stream);
+/* fused BFT(real mode) -> rectify -> ortho DCT-II -> first ccNum.  out: batch x T x ccNum */
+int bftObj_mfccBatch(BFTObj bftObj, const float *data, int dataLength, int batch, int ccNum,
+                     int rectifyType, float *out, int memKind, void *stream);
+int bftObj_getFilterBankArr(BFTObj bftObj, float *bank /* num x (fftLength/2+1) host */);
+/* in: rows x num; out: rows x ccNum */
+int xxccObj_xxccBatch(XXCCObj xxccObj, const float *in, int rows, int ccNum, int rectifyType,
+                      float *out, int memKind, void *stream);
+/* out planes: batch x T x num */
+int cqtObj_cqtBatch(CQTObj cqtObj, const float *data, int dataLength, int batch,
+                    float *mReal3, float *mImag3, int memKind, void *stream);
+int cqtObj_getKernelBank(CQTObj cqtObj, float *kr, float *ki /* binPerOctave x (fftLength/2+1) host */);
+/* data: batch x 2^radix2Exp; out planes: batch x num x 2^radix2Exp */
+int cwtObj_cwtBatch(CWTObj cwtObj, const float *data, int batch, float *mReal4, float *mImag4,
+                    int memKind, void *stream);
+int cwtObj_getFilterBankArr(CWTObj cwtObj, float *bank /* num x fftLength host */);
+
+/* setup-time table builders, exported for parity tests against the reference's
+ * window_calFFTWindow (src/dsp/flux_window.c:890-940), auditory_filterBank
+ * (src/filterbank/auditory_filterBank.c:56-207) and the /2 resampler taps
+ * (src/dsp/resample_algorithm.c:546-634). */
+int afb200_window(int windowType, int length, float *out);
+int afb200_auditoryFilterBank(int num, int fftLength, int samplate, int scaleType, int styleType,
+                              int normType, float lowFre, float highFre, int binPerOctave,
+                              float *bank, float *freBandArr /* num */, int *binBandArr /* num */);
+int afb200_decimatorTaps(float *left32, float *right31);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

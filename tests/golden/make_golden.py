@@ -1,0 +1,76 @@
+#!/usr/bin/env python3
+"""Generate tests/golden/*.npz from the UNMODIFIED reference build (oracle/_ref).
+
+Run in the build container (needs /root/reference to have been compiled by `make -C oracle`):
+    python tests/golden/make_golden.py
+The fixtures pin both the numpy oracle (tests/test_golden.py) and the CUDA path
+(tests/test_gpu_parity.py) to outputs of the reference itself.  Inputs are seeded
+(`np.random.default_rng(seed)`), amplitude 0.1, float32 -- SURVEY.md section 8(d).
+"""
+import os
+import sys
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.realpath(__file__))))
+sys.path.insert(0, ROOT)
+
+import audioflux_b200 as af  # noqa: E402  (host-side mirror classes, driven with the reference library)
+from oracle.ref_lib import get_ref_lib  # noqa: E402
+
+HERE = os.path.dirname(os.path.realpath(__file__))
+
+
+def noise(seed, n):
+    return (0.1 * np.random.default_rng(seed).standard_normal(n)).astype(np.float32)
+
+
+def tones(seed, n, sr):
+    t = np.arange(n) / sr
+    x = 0.3 * (np.sin(2 * np.pi * 220 * t) + np.sin(2 * np.pi * 880 * t) + np.sin(2 * np.pi * 3520 * t))
+    return (x + 0.01 * np.random.default_rng(seed).standard_normal(n)).astype(np.float32)
+
+
+def main():
+    ref = get_ref_lib()
+    S, ST, N, D = (af.SpectralFilterBankScaleType, af.SpectralFilterBankStyleType,
+                   af.SpectralFilterBankNormalType, af.SpectralDataType)
+    # ---- C1: 1 s 48 kHz clip, BFT mel-128, n_fft 2048, hop 512 (+ MFCC-40) ----
+    x = noise(0, 48000)
+    b = af.BFT(128, 11, 48000, slide_length=512, scale_type=S.MEL, data_type=D.POWER, _lib=ref)
+    mel, _ = b.bft_planes(x, 1)
+    xx = af.XXCC(128, _lib=ref)
+    mfcc = xx.xxcc_planes(mel, 40)
+    zre, zim = b.bft_planes(x, 0)
+    np.savez_compressed(os.path.join(HERE, "c1_mel_mfcc.npz"), x=x, mel=mel, mfcc=mfcc, cre=zre, cim=zim,
+                        bin_band=b.get_bin_band_arr(), fre_band=b.get_fre_band_arr())
+    # tones + area norm + magnitude, bark ETSI
+    xt = tones(1, 24000, 48000)
+    b2 = af.BFT(64, 10, 48000, slide_length=256, scale_type=S.BARK, style_type=ST.ETSI, normal_type=N.AREA,
+                data_type=D.MAG, _lib=ref)
+    m2, _ = b2.bft_planes(xt, 1)
+    xx2 = af.XXCC(64, _lib=ref)
+    np.savez_compressed(os.path.join(HERE, "bark_etsi_mag.npz"), x=xt, mel=m2, cc=xx2.xxcc_planes(m2, 20),
+                        cc_cubic=xx2.xxcc_planes(m2, 13, af.CepstralRectifyType.CUBIC_ROOT))
+    # ---- STFT (full mirrored planes), hann 512 / hop 128, first 8 frames ----
+    s = af.STFT(9, af.WindowType.HANN, 128, _lib=ref)
+    xs = noise(2, 4000)
+    re, im = s.stft_planes(xs)
+    np.savez_compressed(os.path.join(HERE, "stft_512.npz"), x=xs, re=re[:8], im=im[:8], T=np.int32(re.shape[0]))
+    # ---- CQT 84 bins @ 48 kHz, 0.25 s ----
+    xc = noise(3, 12037)
+    c = af.CQT(84, 48000, _lib=ref)
+    cre, cim = c.cqt_planes(xc)
+    np.savez_compressed(os.path.join(HERE, "cqt_84.npz"), x=xc, re=cre, im=cim, fft_length=np.int32(c.fft_length))
+    # ---- CWT morlet, 36 scales, N = 2048 ----
+    xw = noise(4, 2048)
+    w = af.CWT(36, 11, 48000, wavelet_type=af.WaveletContinueType.MORLET, is_padding=False, _lib=ref)
+    wre, wim = w.cwt_planes(xw)
+    np.savez_compressed(os.path.join(HERE, "cwt_morlet.npz"), x=xw, re=wre, im=wim, fre=w.get_fre_band_arr())
+    for f in sorted(os.listdir(HERE)):
+        if f.endswith(".npz"):
+            print(f, os.path.getsize(os.path.join(HERE, f)))
+
+
+if __name__ == "__main__":
+    main()

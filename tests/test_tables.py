@@ -1,0 +1,126 @@
+"""Setup-time tables of libaudioflux_b200 (windows, auditory banks, CQT kernels, wavelet banks,
+decimator taps) against the numpy oracle, and against oracle/_ref where present.  No GPU needed:
+the builders are host C."""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+import audioflux_b200 as af
+from oracle import af_oracle as O
+
+S, ST, N, D = (af.SpectralFilterBankScaleType, af.SpectralFilterBankStyleType,
+               af.SpectralFilterBankNormalType, af.SpectralDataType)
+
+
+@pytest.mark.parametrize("wt", range(14))
+def test_windows(product_lib, wt):
+    for n in (2, 16, 512, 2048):
+        w = np.zeros(n, np.float32)
+        assert product_lib.afb200_window(wt, n, w.ctypes.data) == 0
+        assert np.abs(w - O.fft_window(wt, n)).max() < 1e-6
+
+
+def _bank(lib, num, n, sr, scale, style, norm, low, high, bpo):
+    bank = np.zeros((num, n // 2 + 1), np.float32)
+    fb = np.zeros(num, np.float32)
+    bb = np.zeros(num, np.int32)
+    assert lib.afb200_auditoryFilterBank(num, n, sr, scale, style, norm, low, high, bpo, bank.ctypes.data,
+                                         fb.ctypes.data, bb.ctypes.data) == 0
+    return bank, fb, bb
+
+
+@pytest.mark.parametrize("scale", range(1, 7))
+@pytest.mark.parametrize("style", (0, 1, 3, 4, 5, 6, 7, 8, 9, 10))
+def test_filter_banks(product_lib, scale, style):
+    for norm in (0, 1, 2):
+        for num, n, sr in ((128, 2048, 48000), (40, 1024, 16000)):
+            low = 32.703196 if scale in (5, 6) else None
+            high = None
+            if scale == 1:
+                low, high = 1000.0, sr / 2 - 1000.0
+            if scale == 6:
+                low, high = 32.703196, sr / 2 * 0.8
+            lo, hi, _, _ = O.bft_revise_range(num, n, sr, low, high, scale, 12)
+            if scale == 5 and float(hi) > sr / 2:
+                continue
+            b1, f1, i1 = _bank(product_lib, num, n, sr, scale, style, norm, float(lo), float(hi), 12)
+            b2, f2, i2 = O.auditory_filterbank(num, n, sr, scale, style, norm, float(lo), float(hi), 12)
+            assert np.array_equal(i1, i2)                       # integer outcomes: exact
+            assert np.abs(b1 - b2).max() <= 5e-5 * max(1.0, np.abs(b2).max())
+            np.testing.assert_allclose(f1, f2, rtol=2e-6, atol=1e-3)
+
+
+def test_bank_out_of_range_edges_are_clipped(product_lib):
+    # Linspace over the full band revises the edges outside [0, sr/2]; the reference writes out of
+    # bounds there, this library must clip (and not crash)
+    bank, _, _ = _bank(product_lib, 64, 1024, 16000, 1, 0, 0, 0.0, 8000.0, 12)
+    assert np.isfinite(bank).all()
+
+
+def test_bft_object_tables(product_lib):
+    b = af.BFT(128, 11, 48000, slide_length=512, scale_type=S.MEL, data_type=D.POWER)
+    assert b.cal_time_length(240000) == 465 and b.cal_time_length(48000) == 90 and b.cal_time_length(2047) == 0
+    bank, fre, bins = O.auditory_filterbank(128, 2048, 48000, O.SCALE_MEL, O.STYLE_SLANEY, O.NORM_NONE, 0.0, 24000.0)
+    assert np.array_equal(b.get_bin_band_arr(), bins)
+    np.testing.assert_allclose(b.get_fre_band_arr(), fre, rtol=2e-6)
+    got = b.get_filter_bank_arr()
+    assert np.abs(got - bank).max() < 5e-6
+    assert int((got != 0).sum()) == 2019
+
+
+def test_bft_new_status_codes(product_lib):
+    import ctypes
+    from audioflux_b200.capi import opt_int
+    obj = ctypes.c_void_p()
+    args = [None] * 12
+    assert product_lib.bftObj_new(ctypes.byref(obj), 128, 31, *args) == -100        # radix2Exp
+    assert product_lib.bftObj_new(ctypes.byref(obj), 1, 11, *args) == -1            # num < 2
+    assert product_lib.bftObj_new(ctypes.byref(obj), 4000, 11, *args) == -1         # num > n/2+1
+    a2 = list(args); a2[6] = opt_int(9)
+    assert product_lib.bftObj_new(ctypes.byref(obj), 64, 11, *a2) == 1              # scale > Log
+    a3 = list(args); a3[10] = opt_int(1)
+    assert product_lib.bftObj_new(ctypes.byref(obj), 64, 11, *a3) == -2             # isReassign: rejected loudly
+    assert product_lib.stftObj_new(ctypes.byref(obj), 0, None, None, None) == -100
+    assert product_lib.xxccObj_new(ctypes.byref(obj), 1) == -1
+    assert product_lib.cqtObj_newWith(ctypes.byref(obj), 84, None, None, opt_int(10), *([None] * 8)) == -1
+    assert product_lib.cqtObj_newWith(ctypes.byref(obj), 80, *([None] * 11)) == -1
+
+
+def test_cqt_tables(product_lib):
+    c = af.CQT(84, 48000)
+    assert c.fft_length == 512 and c.slide_length == 128 and c.cal_time_length(240000) == 1876
+    kr, ki = c.get_kernel_bank()
+    ob = O.cqt_kernel_bank(84, 48000, norm=O.NORM_AREA)
+    assert int((kr != 0).sum()) == 104
+    assert np.abs(kr - ob["kr"]).max() < 1e-6 and np.abs(ki - ob["ki"]).max() < 1e-6
+    np.testing.assert_allclose(c.get_fre_band_arr(), ob["fre"], rtol=1e-7)
+    left = np.zeros(32, np.float32)
+    right = np.zeros(31, np.float32)
+    product_lib.afb200_decimatorTaps(left.ctypes.data, right.ctypes.data)
+    l2, r2 = O.decimator_taps()
+    assert np.abs(left - l2).max() < 1e-7 and np.abs(right - r2).max() < 1e-7
+
+
+@pytest.mark.parametrize("wav", range(8))
+def test_cwt_tables(product_lib, wav):
+    w = af.CWT(84, 12, 48000, wavelet_type=af.WaveletContinueType(wav), is_padding=False)
+    ob, fre = O.cwt_filterbank(84, 4096, 48000, wav)
+    fb = w.get_filter_bank_arr()
+    assert np.abs(fb - ob).max() <= 1e-5 * np.abs(ob).max()
+    np.testing.assert_allclose(w.get_fre_band_arr(), fre, rtol=1e-6)
+    assert abs(w.get_fre_band_arr()[0] - 32.703197) < 1e-4 and abs(w.get_fre_band_arr()[83] - 3951.0667) < 1e-2
+
+
+def test_tables_against_reference_build(product_lib, ref_lib):
+    for wt in range(14):
+        p = ref_lib.window_calFFTWindow(wt, 2048)
+        w = np.ctypeslib.as_array(C.cast(p, C.POINTER(C.c_float)), shape=(2048,)).copy()
+        w2 = np.zeros(2048, np.float32)
+        product_lib.afb200_window(wt, 2048, w2.ctypes.data)
+        assert np.abs(w - w2).max() < 1e-6
+    for scale, style, norm in ((2, 0, 0), (2, 0, 1), (3, 1, 2), (4, 0, 0), (5, 0, 0)):
+        b = af.BFT(96, 11, 44100, scale_type=S(scale), style_type=ST(style), normal_type=N(norm))
+        r = af.BFT(96, 11, 44100, scale_type=S(scale), style_type=ST(style), normal_type=N(norm), _lib=ref_lib)
+        assert np.array_equal(b.get_bin_band_arr(), r.get_bin_band_arr())
+        np.testing.assert_allclose(b.get_fre_band_arr(), r.get_fre_band_arr(), rtol=1e-6)
