@@ -23,7 +23,7 @@ class LibraryNotBuilt(RuntimeError):
 
 
 def load_library(path: str):
-    lib = ctypes.CDLL(path, mode=ctypes.RTLD_GLOBAL)
+    lib = ctypes.CDLL(path)          # RTLD_LOCAL: the reference build exports the same symbol names
     present = capi.bind(lib)
     return lib, present
 
