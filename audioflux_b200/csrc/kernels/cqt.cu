@@ -50,9 +50,10 @@ struct OctParams {
     const float2 *kappa;          // [bpo][N] (re, im)
     const float *scale;           // [bpo]
     float *outRe, *outIm; long long outStride; int num, colOff;
-    int TT;                       // frames per CTA (multiple of 64)
+    int TT;                       // frames per CTA (even)
     int rowLen;                   // polyphase row pitch (floats)
     int rowsA;                    // ceil(N / hop)
+    int nChunk;                   // kernel taps resident in shared memory at a time
 };
 
 constexpr int kBinsPerPass = 12;  // bins whose kernels sit in shared memory together
@@ -61,8 +62,8 @@ constexpr int kJG = 4;            // lane-groups over bins; 3 bins per thread
 
 __global__ void k_cqt_octave(OctParams p) {
     extern __shared__ __align__(16) unsigned char smemRaw[];
-    float2 *sk = reinterpret_cast<float2 *>(smemRaw);                       // [kBinsPerPass][N]
-    float *xs = reinterpret_cast<float *>(smemRaw + sizeof(float2) * (size_t)kBinsPerPass * p.N);
+    float2 *sk = reinterpret_cast<float2 *>(smemRaw);                       // [kBinsPerPass][nChunk]
+    float *xs = reinterpret_cast<float *>(smemRaw + sizeof(float2) * (size_t)kBinsPerPass * p.nChunk);
     const int clip = blockIdx.y;
     const int t0 = blockIdx.x * p.TT;
     const float *sig = p.sig + (long long)clip * p.sigStride;
@@ -83,28 +84,35 @@ __global__ void k_cqt_octave(OctParams p) {
 
     for (int j0 = 0; j0 < p.bpo; j0 += kBinsPerPass) {
         const int nb = min(kBinsPerPass, p.bpo - j0);
-        __syncthreads();                                       // xs staged / previous pass done with sk
-        for (int i = threadIdx.x; i < nb * N; i += blockDim.x) sk[i] = p.kappa[(size_t)j0 * N + i];
-        for (int i = nb * N + threadIdx.x; i < kBinsPerPass * N; i += blockDim.x) sk[i] = make_float2(0.f, 0.f);
-        __syncthreads();
-
         float ar[kFT][3], ai[kFT][3];
 #pragma unroll
         for (int f = 0; f < kFT; f++)
 #pragma unroll
             for (int u = 0; u < 3; u++) { ar[f][u] = 0.0f; ai[f][u] = 0.0f; }
-        const float2 *k0 = sk + (size_t)(jg * 3 + 0) * N, *k1 = sk + (size_t)(jg * 3 + 1) * N, *k2 = sk + (size_t)(jg * 3 + 2) * N;
-        for (int r = 0; r < h; r++) {
-            const float *row = xs + r * p.rowLen + tl;
-            for (int a = 0, n = r; n < N; a++, n += h) {
-                const float x0 = row[a], x1 = row[a + half];
-                const float2 c0 = k0[n], c1 = k1[n], c2 = k2[n];
-                ar[0][0] = fmaf(x0, c0.x, ar[0][0]); ai[0][0] = fmaf(x0, c0.y, ai[0][0]);
-                ar[0][1] = fmaf(x0, c1.x, ar[0][1]); ai[0][1] = fmaf(x0, c1.y, ai[0][1]);
-                ar[0][2] = fmaf(x0, c2.x, ar[0][2]); ai[0][2] = fmaf(x0, c2.y, ai[0][2]);
-                ar[1][0] = fmaf(x1, c0.x, ar[1][0]); ai[1][0] = fmaf(x1, c0.y, ai[1][0]);
-                ar[1][1] = fmaf(x1, c1.x, ar[1][1]); ai[1][1] = fmaf(x1, c1.y, ai[1][1]);
-                ar[1][2] = fmaf(x1, c2.x, ar[1][2]); ai[1][2] = fmaf(x1, c2.y, ai[1][2]);
+        // the kernels of this pass are streamed through shared memory in chunks of p.nChunk taps
+        for (int n0 = 0; n0 < N; n0 += p.nChunk) {
+            const int n1 = min(N, n0 + p.nChunk), cw = n1 - n0;
+            __syncthreads();                                   // xs staged / previous chunk consumed
+            for (int i = threadIdx.x; i < kBinsPerPass * cw; i += blockDim.x) {
+                const int j = i / cw, n = i - j * cw;
+                sk[(size_t)j * p.nChunk + n] = j < nb ? p.kappa[(size_t)(j0 + j) * N + n0 + n] : make_float2(0.f, 0.f);
+            }
+            __syncthreads();
+            const float2 *k0 = sk + (size_t)(jg * 3 + 0) * p.nChunk - n0, *k1 = sk + (size_t)(jg * 3 + 1) * p.nChunk - n0,
+                         *k2 = sk + (size_t)(jg * 3 + 2) * p.nChunk - n0;
+            for (int r = 0; r < h; r++) {
+                const float *row = xs + r * p.rowLen + tl;
+                int a = n0 > r ? (n0 - r + h - 1) / h : 0;
+                for (int n = a * h + r; n < n1; a++, n += h) {
+                    const float x0 = row[a], x1 = row[a + half];
+                    const float2 c0 = k0[n], c1 = k1[n], c2 = k2[n];
+                    ar[0][0] = fmaf(x0, c0.x, ar[0][0]); ai[0][0] = fmaf(x0, c0.y, ai[0][0]);
+                    ar[0][1] = fmaf(x0, c1.x, ar[0][1]); ai[0][1] = fmaf(x0, c1.y, ai[0][1]);
+                    ar[0][2] = fmaf(x0, c2.x, ar[0][2]); ai[0][2] = fmaf(x0, c2.y, ai[0][2]);
+                    ar[1][0] = fmaf(x1, c0.x, ar[1][0]); ai[1][0] = fmaf(x1, c0.y, ai[1][0]);
+                    ar[1][1] = fmaf(x1, c1.x, ar[1][1]); ai[1][1] = fmaf(x1, c1.y, ai[1][1]);
+                    ar[1][2] = fmaf(x1, c2.x, ar[1][2]); ai[1][2] = fmaf(x1, c2.y, ai[1][2]);
+                }
             }
         }
 #pragma unroll
@@ -150,21 +158,21 @@ extern "C" int af_launch_cqt_octave(const float *sig, int sigLength, int sigStri
     p.kappa = reinterpret_cast<const float2 *>(kappa2); p.scale = scale;
     p.outRe = outRe; p.outIm = outIm; p.outStride = (long long)timeLength * num; p.num = num; p.colOff = colOff;
     p.rowsA = (fftLength + hop - 1) / hop;
-    const size_t kBytes = sizeof(float2) * (size_t)kBinsPerPass * fftLength;
-    int TT = 256;
+    p.nChunk = fftLength < 512 ? fftLength : 512;
+    const size_t kBytes = sizeof(float2) * (size_t)kBinsPerPass * p.nChunk;
+    static const int ttChoices[] = {256, 192, 128, 64, 32, 16, 8};
+    int TT = 0;
     size_t smem = 0;
-    for (; TT >= 64; TT -= 64) {
+    for (int c = 0; c < 7; c++) {
+        TT = ttChoices[c];
         int rowLen = TT + p.rowsA + 1;
         // pitch chosen so consecutive samples (r fastest) land in different banks while staging
         if (hop >= 32) rowLen |= 1; else { int want = 32 / hop; rowLen = ((rowLen + 31) / 32) * 32 + want; }
         p.rowLen = rowLen;
         smem = kBytes + sizeof(float) * (size_t)hop * rowLen;
-        if (smem <= 100 * 1024) break;
+        if (smem <= (TT > 64 ? 100 : 200) * 1024) break;
     }
-    if (TT < 64) {
-        TT = 64;
-        if (smem > 220 * 1024) return af_fail(AF_ERR_UNSUPPORTED, "cqt octave: fftLength %d with hop %d exceeds shared memory", fftLength, hop);
-    }
+    if (smem > 220 * 1024) return af_fail(AF_ERR_UNSUPPORTED, "cqt octave: fftLength %d with hop %d exceeds shared memory", fftLength, hop);
     p.TT = TT;
     cudaError_t e = cudaFuncSetAttribute(k_cqt_octave, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return af_cuda_check(e, "cudaFuncSetAttribute(k_cqt_octave)");

@@ -14,13 +14,16 @@
 //     into shared memory ONCE by a 1-D TMA bulk copy (cp.async.bulk + mbarrier complete_tx),
 //     double buffered through a full/empty mbarrier ring fed by a dedicated producer warp;
 //   * the 2048 real samples are packed as 1024 complex points and transformed as 32 x 32:
-//     lane n1 holds z[n1 + 32*n2] in registers, a generated straight-line 32-point DFT runs over n2,
-//     twiddles W_1024^(n1*k) come from a conflict-free transposed shared table, a 33-padded
-//     shared transpose regroups the data (warp-private, __syncwarp only), a second 32-point DFT runs
-//     over n1;  lane l then holds Z[l + 32*kb];
+//     lane n1 holds z[n1 + 32*n2] in registers (one complex value per 64-bit register pair, all
+//     butterflies in packed FADD2/FMUL2/FFMA2), a generated straight-line 32-point DFT runs over n2,
+//     twiddles W_1024^(n1*k) come half from a conflict-free transposed shared table and half from one
+//     extra multiply by W_64^n1, a 33-padded shared transpose regroups the data (warp-private,
+//     __syncwarp only), a second 32-point DFT runs over n1;  lane l then holds Z[l + 32*kb];
 //   * real-FFT post-pass pairs bin k with 1024-k through one warp shuffle per component (both
 //     powers |E +- W*O|^2 come from one evaluation);
-//   * the banded bank is applied lane-per-filter from a zero-padded transposed weight table;
+//   * the banded bank is applied lane-per-filter from a zero-padded transposed weight table whose
+//     per-filter start bins are shifted down (host planner) until the 32 lanes of a group read 32
+//     different banks -> conflict-free;
 //   * DCT-II: 4 lane-groups split the 128 inputs, 8 lanes x CT coefficients each, 2 xor-shuffles reduce.
 #include <math.h>
 #include <stdlib.h>
@@ -42,7 +45,7 @@ constexpr int kPsPad = 1152;        // Ps[0..1024], zeros up to kPsPad, log-mel 
 struct Plan {                       // host-side descriptor of the device tables
     float *dWindowHalf;             // 2048, window * 0.5
     float2 *dTw1;                   // [32 ka][32 n1]  W_1024^(n1*ka)
-    float2 *dTw2;                   // [512]           W_2048^k
+    float2 *dTw2;                   // [32]            W_2048^lane (post-pass base twiddle)
     float *dMelW;                   // transposed zero-padded weights, group after group: [len_g][32]
     int *dMelStart;                 // 128
     float *dDct;                    // 4 quarter blocks, each 32 rows x ctStride (+8 pad between blocks)
@@ -81,7 +84,7 @@ __host__ __device__ inline Smem carve(int spanFloats, int melWFloats, int ct) {
     s.scratchOff = o;  o += kFrameWarps * kScratchFloats * 4;
     s.windowOff = o;   o += kN * 4;
     s.tw1Off = o;      o += 1024 * 8;
-    s.tw2Off = o;      o += 512 * 8;
+    s.tw2Off = o;      o += 32 * 8;
     s.melWOff = o;     o += ((melWFloats * 4 + 15) / 16) * 16;
     s.melStartOff = o; o += kMaxNum * 4;
     s.dctOff = o;      o += 4 * (32 * ct * 8 + 8) * 4;
@@ -110,7 +113,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_mfcc_fused(Params p) {
     // ---- one-time: tables -> shared, barriers ----
     for (int i = threadIdx.x; i < kN; i += kThreads) reinterpret_cast<float *>(sWin2)[i] = p.windowHalf[i];
     for (int i = threadIdx.x; i < 1024; i += kThreads) sTw1[i] = p.tw1[i];
-    for (int i = threadIdx.x; i < 512; i += kThreads) sTw2[i] = p.tw2[i];
+    for (int i = threadIdx.x; i < 32; i += kThreads) sTw2[i] = p.tw2[i];
     for (int i = threadIdx.x; i < p.melWFloats; i += kThreads) sMelW[i] = p.melW[i];
     for (int i = threadIdx.x; i < kMaxNum; i += kThreads) sMelStart[i] = p.melStart[i];
     for (int i = threadIdx.x; i < 4 * (32 * CT * 8 + 8); i += kThreads) sDct[i] = p.dct[i];
@@ -144,10 +147,14 @@ __global__ void __launch_bounds__(kThreads, 1) k_mfcc_fused(Params p) {
 
     // ================= consumers: warp `warp` computes frame f0 + warp of every tile =================
     float *scratch = scratchAll + (size_t)warp * kScratchFloats;
-    float2 *scr2 = reinterpret_cast<float2 *>(scratch);
+    c64 *scr2 = reinterpret_cast<c64 *>(scratch);
     const int q = lane >> 3, c8 = lane & 7;
     const float *dctQ = sDct + q * (32 * CT * 8 + 8);
     const int partner = (32 - lane) & 31;
+    const c64 w16 = c_from(sTw1[16 * 32 + lane]);            // W_1024^(16*lane) = W_64^lane
+    const c64 wBase = c_from(sTw2[lane]);                    // W_2048^lane
+    const c64 *sWinC = reinterpret_cast<const c64 *>(sWin2);
+    const c64 *sTw1C = reinterpret_cast<const c64 *>(sTw1);
 
     int it = 0;
     for (long long tile = blockIdx.x; tile < p.totalTiles; tile += gridDim.x, ++it) {
@@ -160,65 +167,57 @@ __global__ void __launch_bounds__(kThreads, 1) k_mfcc_fused(Params p) {
 
         af_mbar_wait(&fullBar[stage], round & 1u);
 
-        float re[32], im[32];
+        c64 z[32];
         if (active) {
-            // ---- A: load 2048 samples (as 1024 float2), apply 0.5*window ----
-            const float2 *sp = reinterpret_cast<const float2 *>(span + (size_t)stage * p.spanFloats + warp * p.hop);
+            // ---- A: load 2048 samples (1024 packed pairs), apply 0.5*window ----
+            const c64 *sp = reinterpret_cast<const c64 *>(span + (size_t)stage * p.spanFloats + warp * p.hop);
 #pragma unroll
-            for (int j = 0; j < 32; j++) {
-                const float2 v = sp[lane + 32 * j];
-                const float2 w = sWin2[lane + 32 * j];
-                re[j] = v.x * w.x; im[j] = v.y * w.y;
-            }
+            for (int j = 0; j < 32; j++) z[j] = v_mul(sp[lane + 32 * j], sWinC[lane + 32 * j]);
         }
         __syncwarp();
         if (lane == 0) af_mbar_arrive(&emptyBar[stage]);     // span slot may be refilled
         if (!active) continue;
 
         // ---- B: 1024-point FFT as 32 x 32 ----
-        af_fft32(re, im);                                     // over n2; Y[n1=lane][ka] at AF_BR5(ka)
+        af_fft32(z);                                          // over n2; Y[n1=lane][ka] at AF_BR5(ka)
 #pragma unroll
-        for (int ka = 0; ka < 32; ka++) {
-            float yr = re[AF_BR5(ka)], yi = im[AF_BR5(ka)];
-            if (ka) {
-                const float2 w = sTw1[ka * 32 + lane];
-                const float tr = yr * w.x - yi * w.y;
-                yi = yr * w.y + yi * w.x; yr = tr;
-            }
-            scr2[ka * 33 + lane] = make_float2(yr, yi);
+        for (int ka = 0; ka < 32; ka++) {                     // times W_1024^(lane*ka) = W^(lane*(ka&15)) * W^(16*lane*(ka>>4))
+            c64 y = z[AF_BR5(ka)];
+            if (ka >= 16) y = c_mul(y, w16);
+            if (ka & 15) y = c_mul(y, sTw1C[(ka & 15) * 32 + lane]);
+            scr2[ka * 33 + lane] = y;
         }
         __syncwarp();
 #pragma unroll
-        for (int n1 = 0; n1 < 32; n1++) {
-            const float2 v = scr2[lane * 33 + n1];
-            re[n1] = v.x; im[n1] = v.y;
-        }
+        for (int n1 = 0; n1 < 32; n1++) z[n1] = scr2[lane * 33 + n1];
         __syncwarp();
-        af_fft32(re, im);                                     // over n1; Z[lane + 32*kb] at AF_BR5(kb)
+        af_fft32(z);                                          // over n1; Z[lane + 32*kb] at AF_BR5(kb)
 
         // ---- C: real-FFT post-pass + power / magnitude -> Ps[0..1024] ----
-        // (window pre-scaled by 1/2, so E' = Z[k] + conj Z[N-k] etc. need no further halving)
+        // (window pre-scaled by 1/2, so E' = Z[k] + conj Z[N-k] and O' = -i (Z[k] - conj Z[N-k]) need no halving;
+        //  X[k] = E' + W O', conj X[N-k] = E' - W O' with W = W_2048^k = W_2048^lane * W_64^kb)
 #pragma unroll
         for (int kb = 0; kb < 16; kb++) {
-            const float ar = re[AF_BR5(kb)], ai = im[AF_BR5(kb)];
-            float cr = __shfl_sync(0xffffffffu, re[AF_BR5(31 - kb)], partner);
-            float ci = __shfl_sync(0xffffffffu, im[AF_BR5(31 - kb)], partner);
-            if (lane == 0) { cr = re[AF_BR5((32 - kb) & 31)]; ci = im[AF_BR5((32 - kb) & 31)]; }
-            const float er = ar + cr, ei = ai - ci;           // E' = Z[k] + conj(Z[N-k])
-            const float orr = ai + ci, oi = cr - ar;          // O' = -i (Z[k] - conj(Z[N-k]))
-            const float2 w = sTw2[lane + 32 * kb];            // W_2048^k
-            const float wr = w.x * orr - w.y * oi, wi = w.x * oi + w.y * orr;
-            const float xr = er + wr, xi = ei + wi;           // X[k]
-            const float yr = er - wr, yi = ei - wi;           // conj X[N-k]
-            float pk = xr * xr + xi * xi, pn = yr * yr + yi * yi;
+            const c64 zk = z[AF_BR5(kb)];
+            float pr, pi;
+            c_unpack(z[AF_BR5(31 - kb)], pr, pi);
+            pr = __shfl_sync(0xffffffffu, pr, partner);
+            pi = __shfl_sync(0xffffffffu, pi, partner);
+            c64 zp = c_pack(pr, pi);
+            if (lane == 0) zp = z[AF_BR5((32 - kb) & 31)];
+            const c64 zc = c_conj(zp);
+            const c64 e = c_add(zk, zc);
+            c64 o = c_mul_mi(c_sub(zk, zc));
+            o = af_mul_w64(o, kb);                             // compile-time constant twiddle
+            const c64 wo = c_mul(o, wBase);
+            float pk = c_norm2(c_add(e, wo)), pn = c_norm2(c_sub(e, wo));
             if (p.dataType == SpectralData_Mag) { pk = sqrtf(pk); pn = sqrtf(pn); }
             const int k = lane + 32 * kb;
             scratch[k] = pk;
             scratch[kNC - k] = pn;
         }
         if (lane == 0) {                                       // k = 512 pairs with itself
-            const float zr = re[AF_BR5(16)], zi = im[AF_BR5(16)];
-            float pk = 4.0f * (zr * zr + zi * zi);
+            float pk = 4.0f * c_norm2(z[AF_BR5(16)]);
             if (p.dataType == SpectralData_Mag) pk = sqrtf(pk);
             scratch[512] = pk;
         }
@@ -229,20 +228,20 @@ __global__ void __launch_bounds__(kThreads, 1) k_mfcc_fused(Params p) {
         }
         __syncwarp();
 
-        // ---- D: banded filter bank (lane = filter within group) + rectify ----
+        // ---- D: banded filter bank (lane = filter within group, bank-conflict-free starts) + rectify ----
         {
-            const float *wg = sMelW;
+            const float *wg = sMelW + lane;
             for (int g = 0; g < p.melGroups; g++) {
-                const int len = p.melGroupLen[g];
+                const int len = p.melGroupLen[g];              // multiple of 4
                 const float *ps = scratch + sMelStart[g * 32 + lane];
-                float acc0 = 0.0f, acc1 = 0.0f;
-                int i = 0;
-                for (; i + 1 < len; i += 2) {
-                    acc0 = fmaf(ps[i], wg[i * 32 + lane], acc0);
-                    acc1 = fmaf(ps[i + 1], wg[(i + 1) * 32 + lane], acc1);
+                float acc0 = 0.0f, acc1 = 0.0f, acc2 = 0.0f, acc3 = 0.0f;
+                for (int i = 0; i < len; i += 4) {
+                    acc0 = fmaf(ps[i], wg[i * 32], acc0);
+                    acc1 = fmaf(ps[i + 1], wg[(i + 1) * 32], acc1);
+                    acc2 = fmaf(ps[i + 2], wg[(i + 2) * 32], acc2);
+                    acc3 = fmaf(ps[i + 3], wg[(i + 3) * 32], acc3);
                 }
-                if (i < len) acc0 = fmaf(ps[i], wg[i * 32 + lane], acc0);
-                float v = acc0 + acc1;
+                float v = (acc0 + acc1) + (acc2 + acc3);
                 if (p.rectify == CepstralRectify_CubicRoot) v = powf(v, 1.0f / 3.0f);
                 else v = log10f(v < 1e-8f ? 1e-8f : v);
                 scratch[kPsPad + g * 32 + lane] = v;
@@ -296,15 +295,41 @@ void free_plan(Plan *pl) {
 
 }  // namespace
 
+// Mel plan: filters are processed in groups of 32 (lane = filter).  Each filter's first tap is moved
+// down by delta in [0, 31] (extra taps get zero weight) until the 32 start bins of a group fall in 32
+// different shared-memory banks, longest filters first; group length = max(len + delta), rounded up to 4.
+static int plan_mel(const AfBands *bands, int num, int *startShifted /* kMaxNum */, int *groupLen /* 4 */) {
+    int total = 0;
+    for (int m = 0; m < kMaxNum; m++) startShifted[m] = 0;
+    for (int g = 0; g < 4; g++) groupLen[g] = 0;
+    for (int g = 0; g * 32 < num; g++) {
+        int order[32], cnt = 0;
+        for (int m = g * 32; m < num && m < g * 32 + 32; m++) order[cnt++] = m;
+        for (int i = 1; i < cnt; i++)                         // insertion sort, longest first
+            for (int j = i; j > 0 && bands->len[order[j]] > bands->len[order[j - 1]]; j--) { int t = order[j]; order[j] = order[j - 1]; order[j - 1] = t; }
+        unsigned used = 0;
+        int len = 0;
+        for (int i = 0; i < cnt; i++) {
+            const int m = order[i], s0 = bands->start[m];
+            int delta = 0;
+            while (delta < 32 && s0 - delta >= 0 && (used >> ((s0 - delta) & 31) & 1u)) delta++;
+            if (delta >= 32 || s0 - delta < 0) delta = 0;     // no free bank reachable: accept a conflict
+            used |= 1u << ((s0 - delta) & 31);
+            startShifted[m] = s0 - delta;
+            if (bands->len[m] + delta > len) len = bands->len[m] + delta;
+        }
+        len = (len + 3) & ~3;
+        groupLen[g] = len;
+        total += len * 32;
+    }
+    return total;
+}
+
 extern "C" int af_mfcc_fused_supported(int fftLength, int num, int ccNum, const AfBands *bands) {
     if (fftLength != kN || num < 1 || num > kMaxNum || ccNum < 1 || ccNum > 64 || !bands) return 0;
-    if (bands->maxLen > kPsPad - (kNC + 1)) return 0;           // padded reads must stay inside the zero pad
-    int floats = 0;
-    for (int g = 0; g * 32 < num; g++) {
-        int len = 0;
-        for (int m = g * 32; m < num && m < g * 32 + 32; m++) if (bands->len[m] > len) len = bands->len[m];
-        floats += len * 32;
-    }
+    int starts[kMaxNum], groupLen[4];
+    const int floats = plan_mel(bands, num, starts, groupLen);
+    for (int g = 0; g < 4; g++) if (groupLen[g] > kPsPad - (kNC + 1)) return 0;   // padded reads must stay inside the zero pad
     return floats * 4 <= 24 * 1024;                              // weight table budget in shared memory
 }
 
@@ -333,35 +358,28 @@ extern "C" int af_mfcc_plan_build(void **planOut, int fftLength, int num, int cc
             tw[ka * 32 + n1] = make_float2((float)cos(a), (float)sin(a));
         }
     if (rc == AF_OK) rc = af_dev_upload(reinterpret_cast<void **>(&pl->dTw1), tw, sizeof(float2) * 1024);
-    for (int k = 0; k < 512; k++) {
+    for (int k = 0; k < 32; k++) {
         double a = -2.0 * M_PI * (double)k / 2048.0;
         tw[k] = make_float2((float)cos(a), (float)sin(a));
     }
-    if (rc == AF_OK) rc = af_dev_upload(reinterpret_cast<void **>(&pl->dTw2), tw, sizeof(float2) * 512);
+    if (rc == AF_OK) rc = af_dev_upload(reinterpret_cast<void **>(&pl->dTw2), tw, sizeof(float2) * 32);
     free(tw);
 
-    // transposed, zero-padded band weights: group g -> [len_g][32]
+    // transposed, zero-padded band weights: group g -> [len_g][32], starts shifted for bank-conflict-free reads
     const int width = kNC + 1;
     pl->melGroups = (num + 31) / 32;
-    int total = 0;
-    for (int g = 0; g < pl->melGroups; g++) {
-        int len = 0;
-        for (int m = g * 32; m < num && m < g * 32 + 32; m++) if (bands->len[m] > len) len = bands->len[m];
-        pl->melGroupLen[g] = len;
-        total += len * 32;
-    }
+    int starts[kMaxNum];
+    const int total = plan_mel(bands, num, starts, pl->melGroupLen);
     pl->melWFloats = total;
     float *mw = static_cast<float *>(calloc((size_t)(total > 0 ? total : 1), sizeof(float)));
-    int starts[kMaxNum];
-    for (int m = 0; m < kMaxNum; m++) starts[m] = 0;
     int off = 0;
     for (int g = 0; g < pl->melGroups; g++) {
         for (int l = 0; l < 32; l++) {
             const int m = g * 32 + l;
             if (m >= num) continue;
-            starts[m] = bands->start[m];
+            const int delta = bands->start[m] - starts[m];
             for (int i = 0; i < bands->len[m]; i++)
-                mw[off + i * 32 + l] = bank[(size_t)m * width + bands->start[m] + i];
+                mw[off + (i + delta) * 32 + l] = bank[(size_t)m * width + bands->start[m] + i];
         }
         off += pl->melGroupLen[g] * 32;
     }
