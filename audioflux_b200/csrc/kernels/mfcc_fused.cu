@@ -24,7 +24,10 @@
 //   * the banded bank is applied lane-per-filter from a zero-padded transposed weight table whose
 //     per-filter start bins are shifted down (host planner) until the 32 lanes of a group read 32
 //     different banks -> conflict-free;
-//   * DCT-II: 4 lane-groups split the 128 inputs, 8 lanes x CT coefficients each, 2 xor-shuffles reduce.
+//   * DCT-II is the one dense GEMM-shaped piece ([frames x 128] . [128 x cc]): the frame warps drop their
+//     log-mel rows into a double-buffered 16 x 128 shared tile and a dedicated epilogue warp contracts the
+//     whole tile on the tensor cores (mma.sync m16n8k8 TF32, 3xTF32 split so the result keeps fp32 accuracy)
+//     while the frame warps are already transforming the next tile.
 #include <math.h>
 #include <stdlib.h>
 #include <string.h>
@@ -36,19 +39,21 @@ namespace {
 constexpr int kN = 2048;            // fftLength
 constexpr int kNC = 1024;           // packed complex points
 constexpr int kFrameWarps = 12;     // consumer warps = max frames per tile
-constexpr int kThreads = (kFrameWarps + 1) * 32;
+constexpr int kThreads = (kFrameWarps + 2) * 32;   // + TMA producer warp + DCT epilogue warp
+constexpr int kLPitch = 132;        // log-mel tile row pitch (floats): 4g + t -> 32 distinct banks for mma A fragments
+constexpr int kLRows = 16;          // mma M
 constexpr int kStages = 2;
 constexpr int kMaxNum = 128;        // filters (padded)
 constexpr int kScratchFloats = 33 * 32 * 2;     // per warp: transpose buffer, later P / log-mel
-constexpr int kPsPad = 1152;        // Ps[0..1024], zeros up to kPsPad, log-mel at [kPsPad, kPsPad+128)
+constexpr int kPsPad = 1152;        // Ps[0..1024], zeros up to kPsPad (padded band reads)
 
 struct Plan {                       // host-side descriptor of the device tables
     float *dWindowHalf;             // 2048, window * 0.5
-    float2 *dTw1;                   // [32 ka][32 n1]  W_1024^(n1*ka)
+    float2 *dTw1;                   // [17 ka][32 n1]  W_1024^(n1*ka), ka = 0..16
     float2 *dTw2;                   // [32]            W_2048^lane (post-pass base twiddle)
     float *dMelW;                   // transposed zero-padded weights, group after group: [len_g][32]
     int *dMelStart;                 // 128
-    float *dDct;                    // 4 quarter blocks, each 32 rows x ctStride (+8 pad between blocks)
+    float *dDct;                    // [128 m][dctPitch] ortho DCT-II, B operand of the epilogue mma (pitch % 32 == 8)
     int melGroupLen[4];
     int melGroups;
     int melWFloats;
@@ -75,7 +80,7 @@ struct Params {
 
 // shared-memory carve-up (bytes), all 16-byte aligned
 struct Smem {
-    int spanOff, scratchOff, windowOff, tw1Off, tw2Off, melWOff, melStartOff, dctOff, barOff, total;
+    int spanOff, scratchOff, windowOff, tw1Off, tw2Off, melWOff, melStartOff, dctOff, lOff, barOff, total;
 };
 
 __host__ __device__ inline Smem carve(int spanFloats, int melWFloats, int ct) {
@@ -83,12 +88,13 @@ __host__ __device__ inline Smem carve(int spanFloats, int melWFloats, int ct) {
     s.spanOff = o;     o += kStages * spanFloats * 4;
     s.scratchOff = o;  o += kFrameWarps * kScratchFloats * 4;
     s.windowOff = o;   o += kN * 4;
-    s.tw1Off = o;      o += 1024 * 8;
+    s.tw1Off = o;      o += 17 * 32 * 8;
     s.tw2Off = o;      o += 32 * 8;
     s.melWOff = o;     o += ((melWFloats * 4 + 15) / 16) * 16;
     s.melStartOff = o; o += kMaxNum * 4;
-    s.dctOff = o;      o += 4 * (32 * ct * 8 + 8) * 4;
-    s.barOff = o;      o += 2 * kStages * 8;
+    s.dctOff = o;      o += kMaxNum * (ct <= 5 ? 40 : 72) * 4;
+    s.lOff = o;        o += 2 * kLRows * kLPitch * 4;
+    s.barOff = o;      o += (2 * kStages + 4) * 8;
     s.total = o;
     return s;
 }
@@ -105,20 +111,26 @@ __global__ void __launch_bounds__(kThreads, 1) k_mfcc_fused(Params p) {
     float *sMelW = reinterpret_cast<float *>(smem + L.melWOff);
     int *sMelStart = reinterpret_cast<int *>(smem + L.melStartOff);
     float *sDct = reinterpret_cast<float *>(smem + L.dctOff);
+    float *sL = reinterpret_cast<float *>(smem + L.lOff);                 // [2][kLRows][kLPitch] log-mel tiles
     uint64_t *fullBar = reinterpret_cast<uint64_t *>(smem + L.barOff);
     uint64_t *emptyBar = fullBar + kStages;
+    uint64_t *lFull = emptyBar + kStages;                                  // [2] frame warps -> epilogue
+    uint64_t *lEmpty = lFull + 2;                                          // [2] epilogue -> frame warps
+    constexpr int kDctPitch = CT <= 5 ? 40 : 72;
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
     // ---- one-time: tables -> shared, barriers ----
     for (int i = threadIdx.x; i < kN; i += kThreads) reinterpret_cast<float *>(sWin2)[i] = p.windowHalf[i];
-    for (int i = threadIdx.x; i < 1024; i += kThreads) sTw1[i] = p.tw1[i];
+    for (int i = threadIdx.x; i < 17 * 32; i += kThreads) sTw1[i] = p.tw1[i];
     for (int i = threadIdx.x; i < 32; i += kThreads) sTw2[i] = p.tw2[i];
     for (int i = threadIdx.x; i < p.melWFloats; i += kThreads) sMelW[i] = p.melW[i];
     for (int i = threadIdx.x; i < kMaxNum; i += kThreads) sMelStart[i] = p.melStart[i];
-    for (int i = threadIdx.x; i < 4 * (32 * CT * 8 + 8); i += kThreads) sDct[i] = p.dct[i];
+    for (int i = threadIdx.x; i < kMaxNum * kDctPitch; i += kThreads) sDct[i] = p.dct[i];
+    for (int i = threadIdx.x; i < 2 * kLRows * kLPitch; i += kThreads) sL[i] = 0.0f;
     if (threadIdx.x == 0) {
         for (int s = 0; s < kStages; s++) { af_mbar_init(&fullBar[s], 1); af_mbar_init(&emptyBar[s], kFrameWarps); }
+        for (int s = 0; s < 2; s++) { af_mbar_init(&lFull[s], kFrameWarps); af_mbar_init(&lEmpty[s], 1); }
         af_fence_barrier_init();
     }
     __syncthreads();
@@ -145,11 +157,74 @@ __global__ void __launch_bounds__(kThreads, 1) k_mfcc_fused(Params p) {
         return;
     }
 
+    if (warp == kFrameWarps + 1) {
+        // ================= epilogue: DCT-II of a whole tile on the tensor cores =================
+        // out[16 x 8*CT] = L[16 x 128] . D^T[128 x 8*CT], mma.sync.m16n8k8 TF32 with the 3xTF32 split
+        // (x = hi + lo, hi = tf32(x), lo = tf32(x - hi);  lo*hi + hi*lo + hi*hi) -> fp32-level accuracy.
+        const int g = lane >> 2, t = lane & 3;
+        int it = 0;
+        for (long long tile = blockIdx.x; tile < p.totalTiles; tile += gridDim.x, ++it) {
+            const int buf = it & 1;
+            const long long clip = tile / p.tilesPerClip;
+            const int f0 = (int)(tile % p.tilesPerClip) * F;
+            const int nf = min(F, p.timeLength - f0);
+            af_mbar_wait(&lFull[buf], (uint32_t)(it >> 1) & 1u);
+            const float *A = sL + (size_t)buf * kLRows * kLPitch;
+            float acc[CT][4];
+#pragma unroll
+            for (int n = 0; n < CT; n++) { acc[n][0] = acc[n][1] = acc[n][2] = acc[n][3] = 0.0f; }
+#pragma unroll 4
+            for (int k0 = 0; k0 < kMaxNum; k0 += 8) {
+                float af[4] = {A[g * kLPitch + k0 + t], A[(g + 8) * kLPitch + k0 + t],
+                               A[g * kLPitch + k0 + t + 4], A[(g + 8) * kLPitch + k0 + t + 4]};
+                uint32_t ah[4], al[4];
+#pragma unroll
+                for (int i = 0; i < 4; i++) {
+                    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(ah[i]) : "f"(af[i]));
+                    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(al[i]) : "f"(af[i] - __uint_as_float(ah[i])));
+                }
+#pragma unroll
+                for (int n = 0; n < CT; n++) {
+                    const float bf[2] = {sDct[(k0 + t) * kDctPitch + n * 8 + g], sDct[(k0 + t + 4) * kDctPitch + n * 8 + g]};
+                    uint32_t bh[2], bl[2];
+#pragma unroll
+                    for (int i = 0; i < 2; i++) {
+                        asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(bh[i]) : "f"(bf[i]));
+                        asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(bl[i]) : "f"(bf[i] - __uint_as_float(bh[i])));
+                    }
+#define AF_MMA_TF32(A0, A1, A2, A3, B0, B1)                                                                   \
+    asm volatile("mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};" \
+                 : "+f"(acc[n][0]), "+f"(acc[n][1]), "+f"(acc[n][2]), "+f"(acc[n][3])                        \
+                 : "r"(A0), "r"(A1), "r"(A2), "r"(A3), "r"(B0), "r"(B1))
+                    AF_MMA_TF32(al[0], al[1], al[2], al[3], bh[0], bh[1]);
+                    AF_MMA_TF32(ah[0], ah[1], ah[2], ah[3], bl[0], bl[1]);
+                    AF_MMA_TF32(ah[0], ah[1], ah[2], ah[3], bh[0], bh[1]);
+#undef AF_MMA_TF32
+                }
+            }
+            __syncwarp();
+            if (lane == 0) af_mbar_arrive(&lEmpty[buf]);           // tile consumed: frame warps may overwrite it
+            // C fragment: rows g and g+8, columns n*8 + 2t, +1
+            float *o = p.out + ((long long)clip * p.timeLength + f0) * p.ccNum;
+#pragma unroll
+            for (int n = 0; n < CT; n++) {
+                const int c = n * 8 + 2 * t;
+                if (g < nf) {
+                    if (c < p.ccNum) o[(long long)g * p.ccNum + c] = acc[n][0];
+                    if (c + 1 < p.ccNum) o[(long long)g * p.ccNum + c + 1] = acc[n][1];
+                }
+                if (g + 8 < nf) {
+                    if (c < p.ccNum) o[(long long)(g + 8) * p.ccNum + c] = acc[n][2];
+                    if (c + 1 < p.ccNum) o[(long long)(g + 8) * p.ccNum + c + 1] = acc[n][3];
+                }
+            }
+        }
+        return;
+    }
+
     // ================= consumers: warp `warp` computes frame f0 + warp of every tile =================
     float *scratch = scratchAll + (size_t)warp * kScratchFloats;
     c64 *scr2 = reinterpret_cast<c64 *>(scratch);
-    const int q = lane >> 3, c8 = lane & 7;
-    const float *dctQ = sDct + q * (32 * CT * 8 + 8);
     const int partner = (32 - lane) & 31;
     const c64 w16 = c_from(sTw1[16 * 32 + lane]);            // W_1024^(16*lane) = W_64^lane
     const c64 wBase = c_from(sTw2[lane]);                    // W_2048^lane
@@ -160,7 +235,6 @@ __global__ void __launch_bounds__(kThreads, 1) k_mfcc_fused(Params p) {
     for (long long tile = blockIdx.x; tile < p.totalTiles; tile += gridDim.x, ++it) {
         const int stage = it % kStages;
         const uint32_t round = (uint32_t)(it / kStages);
-        const long long clip = tile / p.tilesPerClip;
         const int f0 = (int)(tile % p.tilesPerClip) * F;
         const int nf = min(F, p.timeLength - f0);
         const bool active = warp < nf;
@@ -176,7 +250,15 @@ __global__ void __launch_bounds__(kThreads, 1) k_mfcc_fused(Params p) {
         }
         __syncwarp();
         if (lane == 0) af_mbar_arrive(&emptyBar[stage]);     // span slot may be refilled
-        if (!active) continue;
+        const int lbuf = it & 1;
+        float *lrow = sL + ((size_t)lbuf * kLRows + warp) * kLPitch;
+        if (!active) {
+            // keep the log-mel tile protocol in step: one arrival per warp per tile, never before the
+            // epilogue released this buffer (tile it-2), else an early arrival would complete the wrong phase
+            af_mbar_wait(&lEmpty[lbuf], ((uint32_t)(it >> 1) & 1u) ^ 1u);
+            if (lane == 0) af_mbar_arrive(&lFull[lbuf]);
+            continue;
+        }
 
         // ---- B: 1024-point FFT as 32 x 32 ----
         af_fft32(z);                                          // over n2; Y[n1=lane][ka] at AF_BR5(ka)
@@ -229,6 +311,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_mfcc_fused(Params p) {
         __syncwarp();
 
         // ---- D: banded filter bank (lane = filter within group, bank-conflict-free starts) + rectify ----
+        af_mbar_wait(&lEmpty[lbuf], ((uint32_t)(it >> 1) & 1u) ^ 1u);   // epilogue done with tile it-2
         {
             const float *wg = sMelW + lane;
             for (int g = 0; g < p.melGroups; g++) {
@@ -244,45 +327,14 @@ __global__ void __launch_bounds__(kThreads, 1) k_mfcc_fused(Params p) {
                 float v = (acc0 + acc1) + (acc2 + acc3);
                 if (p.rectify == CepstralRectify_CubicRoot) v = powf(v, 1.0f / 3.0f);
                 else v = log10f(v < 1e-8f ? 1e-8f : v);
-                scratch[kPsPad + g * 32 + lane] = v;
+                lrow[g * 32 + lane] = v;
                 wg += len * 32;
             }
-            for (int g = p.melGroups; g < 4; g++) scratch[kPsPad + g * 32 + lane] = 0.0f;
+            for (int g = p.melGroups; g < 4; g++) lrow[g * 32 + lane] = 0.0f;
         }
         __syncwarp();
+        if (lane == 0) af_mbar_arrive(&lFull[lbuf]);           // row ready for the tensor-core DCT epilogue
 
-        // ---- E: DCT-II: lane (q, c8) sums inputs of quarter q into coefficients c8 + 8t ----
-        {
-            float acc[CT];
-#pragma unroll
-            for (int t = 0; t < CT; t++) acc[t] = 0.0f;
-            const float4 *l4 = reinterpret_cast<const float4 *>(scratch + kPsPad + q * 32);
-#pragma unroll
-            for (int i = 0; i < 8; i++) {
-                const float4 lv = l4[i];
-                const float lm[4] = {lv.x, lv.y, lv.z, lv.w};
-#pragma unroll
-                for (int u = 0; u < 4; u++) {
-                    const float *d = dctQ + (i * 4 + u) * (CT * 8) + c8;
-#pragma unroll
-                    for (int t = 0; t < CT; t++) acc[t] = fmaf(lm[u], d[t * 8], acc[t]);
-                }
-            }
-#pragma unroll
-            for (int t = 0; t < CT; t++) {
-                acc[t] += __shfl_xor_sync(0xffffffffu, acc[t], 8);
-                acc[t] += __shfl_xor_sync(0xffffffffu, acc[t], 16);
-            }
-            if (q == 0) {
-                float *o = p.out + ((long long)clip * p.timeLength + f0 + warp) * p.ccNum;
-#pragma unroll
-                for (int t = 0; t < CT; t++) {
-                    const int c = c8 + 8 * t;
-                    if (c < p.ccNum) o[c] = acc[t];
-                }
-            }
-        }
-        __syncwarp();
     }
 }
 
@@ -352,12 +404,12 @@ extern "C" int af_mfcc_plan_build(void **planOut, int fftLength, int num, int cc
     free(wh);
 
     float2 *tw = static_cast<float2 *>(malloc(sizeof(float2) * 1024));
-    for (int ka = 0; ka < 32 && rc == AF_OK; ka++)
+    for (int ka = 0; ka < 17 && rc == AF_OK; ka++)
         for (int n1 = 0; n1 < 32; n1++) {
             double a = -2.0 * M_PI * (double)(ka * n1) / 1024.0;
             tw[ka * 32 + n1] = make_float2((float)cos(a), (float)sin(a));
         }
-    if (rc == AF_OK) rc = af_dev_upload(reinterpret_cast<void **>(&pl->dTw1), tw, sizeof(float2) * 1024);
+    if (rc == AF_OK) rc = af_dev_upload(reinterpret_cast<void **>(&pl->dTw1), tw, sizeof(float2) * 17 * 32);
     for (int k = 0; k < 32; k++) {
         double a = -2.0 * M_PI * (double)k / 2048.0;
         tw[k] = make_float2((float)cos(a), (float)sin(a));
@@ -387,14 +439,13 @@ extern "C" int af_mfcc_plan_build(void **planOut, int fftLength, int num, int cc
     if (rc == AF_OK) rc = af_dev_upload(reinterpret_cast<void **>(&pl->dMelStart), starts, sizeof(int) * kMaxNum);
     free(mw);
 
-    // DCT table: quarter q block = rows m = 32q..32q+31, each row CT*8 floats (coefficient c at [c]),
-    // blocks separated by 8 floats so the four lane-groups hit disjoint banks
-    const int ct = pl->ct, blk = 32 * ct * 8 + 8;
-    float *dt = static_cast<float *>(calloc((size_t)4 * blk, sizeof(float)));
+    // DCT table as the mma B operand: D^T[m][c] with row pitch 40 (72 for cc > 40): pitch % 32 == 8 makes the
+    // (k0 + t, n0 + g) fragment reads hit 32 different banks; rows m >= num and columns c >= ccNum are zero
+    const int ct = pl->ct, pitch = ct <= 5 ? 40 : 72;
+    float *dt = static_cast<float *>(calloc((size_t)kMaxNum * pitch, sizeof(float)));
     for (int m = 0; m < num; m++)
-        for (int c = 0; c < ccNum; c++)
-            dt[(m / 32) * blk + (m % 32) * (ct * 8) + c] = dct[(size_t)c * num + m];
-    if (rc == AF_OK) rc = af_dev_upload(reinterpret_cast<void **>(&pl->dDct), dt, sizeof(float) * (size_t)4 * blk);
+        for (int c = 0; c < ccNum; c++) dt[(size_t)m * pitch + c] = dct[(size_t)c * num + m];
+    if (rc == AF_OK) rc = af_dev_upload(reinterpret_cast<void **>(&pl->dDct), dt, sizeof(float) * (size_t)kMaxNum * pitch);
     free(dt);
 
     if (rc != AF_OK) { free_plan(pl); return rc; }

@@ -207,7 +207,7 @@ def run_b200_arm(args):
     parity = None
     if rank == 0:
         from oracle import af_oracle as O
-        out = step()
+        out = bft.mfcc_batch(x, NCC)          # no collective here: only rank 0 runs the gate
         torch.cuda.synchronize()
         want = O.mfcc(x[0].cpu().numpy(), SR, RADIX, HOP, NMEL, NCC)
         parity = float(np.abs(out[0].cpu().numpy() - want).max() / np.abs(want).max())
