@@ -39,7 +39,8 @@ namespace {
 constexpr int kN = 2048;            // fftLength
 constexpr int kNC = 1024;           // packed complex points
 constexpr int kFrameWarps = 12;     // consumer warps = max frames per tile
-constexpr int kThreads = (kFrameWarps + 2) * 32;   // + TMA producer warp + DCT epilogue warp
+constexpr int kEpiWarps = 2;         // DCT epilogue warps, one per log-mel tile buffer (tiles alternate)
+constexpr int kThreads = (kFrameWarps + 1 + kEpiWarps) * 32;   // + TMA producer warp + DCT epilogue warps
 constexpr int kLPitch = 132;        // log-mel tile row pitch (floats): 4g + t -> 32 distinct banks for mma A fragments
 constexpr int kLRows = 16;          // mma M
 constexpr int kStages = 2;
@@ -157,14 +158,15 @@ __global__ void __launch_bounds__(kThreads, 1) k_mfcc_fused(Params p) {
         return;
     }
 
-    if (warp == kFrameWarps + 1) {
+    if (warp > kFrameWarps) {
         // ================= epilogue: DCT-II of a whole tile on the tensor cores =================
         // out[16 x 8*CT] = L[16 x 128] . D^T[128 x 8*CT], mma.sync.m16n8k8 TF32 with the 3xTF32 split
         // (x = hi + lo, hi = tf32(x), lo = tf32(x - hi);  lo*hi + hi*lo + hi*hi) -> fp32-level accuracy.
         const int g = lane >> 2, t = lane & 3;
+        const int buf = warp - (kFrameWarps + 1);                  // this warp owns log-mel buffer `buf`
         int it = 0;
         for (long long tile = blockIdx.x; tile < p.totalTiles; tile += gridDim.x, ++it) {
-            const int buf = it & 1;
+            if ((it & 1) != buf) continue;
             const long long clip = tile / p.tilesPerClip;
             const int f0 = (int)(tile % p.tilesPerClip) * F;
             const int nf = min(F, p.timeLength - f0);
@@ -177,11 +179,12 @@ __global__ void __launch_bounds__(kThreads, 1) k_mfcc_fused(Params p) {
             for (int k0 = 0; k0 < kMaxNum; k0 += 8) {
                 float af[4] = {A[g * kLPitch + k0 + t], A[(g + 8) * kLPitch + k0 + t],
                                A[g * kLPitch + k0 + t + 4], A[(g + 8) * kLPitch + k0 + t + 4]};
+                // TF32 split by truncation: hi = top 19 bits, lo = (x - hi) (exact), again cut to 19 bits
                 uint32_t ah[4], al[4];
 #pragma unroll
                 for (int i = 0; i < 4; i++) {
-                    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(ah[i]) : "f"(af[i]));
-                    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(al[i]) : "f"(af[i] - __uint_as_float(ah[i])));
+                    ah[i] = __float_as_uint(af[i]) & 0xffffe000u;
+                    al[i] = __float_as_uint(af[i] - __uint_as_float(ah[i])) & 0xffffe000u;
                 }
 #pragma unroll
                 for (int n = 0; n < CT; n++) {
@@ -189,8 +192,8 @@ __global__ void __launch_bounds__(kThreads, 1) k_mfcc_fused(Params p) {
                     uint32_t bh[2], bl[2];
 #pragma unroll
                     for (int i = 0; i < 2; i++) {
-                        asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(bh[i]) : "f"(bf[i]));
-                        asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(bl[i]) : "f"(bf[i] - __uint_as_float(bh[i])));
+                        bh[i] = __float_as_uint(bf[i]) & 0xffffe000u;
+                        bl[i] = __float_as_uint(bf[i] - __uint_as_float(bh[i])) & 0xffffe000u;
                     }
 #define AF_MMA_TF32(A0, A1, A2, A3, B0, B1)                                                                   \
     asm volatile("mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};" \
