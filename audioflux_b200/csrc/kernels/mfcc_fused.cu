@@ -38,14 +38,14 @@ namespace {
 
 constexpr int kN = 2048;            // fftLength
 constexpr int kNC = 1024;           // packed complex points
-constexpr int kFrameWarps = 12;     // consumer warps = max frames per tile
+constexpr int kFrameWarps = 15;     // consumer warps = max frames per tile (465 frames per 5 s clip = 31 x 15)
 constexpr int kEpiWarps = 2;         // DCT epilogue warps, one per log-mel tile buffer (tiles alternate)
 constexpr int kThreads = (kFrameWarps + 1 + kEpiWarps) * 32;   // + TMA producer warp + DCT epilogue warps
 constexpr int kLPitch = 132;        // log-mel tile row pitch (floats): 4g + t -> 32 distinct banks for mma A fragments
 constexpr int kLRows = 16;          // mma M
 constexpr int kStages = 2;
 constexpr int kMaxNum = 128;        // filters (padded)
-constexpr int kScratchFloats = 33 * 32 * 2;     // per warp: transpose buffer, later P / log-mel
+constexpr int kScratchFloats = 1152;            // per warp: 33x32 float transpose plane, later Ps[0..1024] + zero pad
 constexpr int kPsPad = 1152;        // Ps[0..1024], zeros up to kPsPad (padded band reads)
 
 struct Plan {                       // host-side descriptor of the device tables
@@ -227,7 +227,6 @@ __global__ void __launch_bounds__(kThreads, 1) k_mfcc_fused(Params p) {
 
     // ================= consumers: warp `warp` computes frame f0 + warp of every tile =================
     float *scratch = scratchAll + (size_t)warp * kScratchFloats;
-    c64 *scr2 = reinterpret_cast<c64 *>(scratch);
     const int partner = (32 - lane) & 31;
     const c64 w16 = c_from(sTw1[16 * 32 + lane]);            // W_1024^(16*lane) = W_64^lane
     const c64 wBase = c_from(sTw2[lane]);                    // W_2048^lane
@@ -265,17 +264,29 @@ __global__ void __launch_bounds__(kThreads, 1) k_mfcc_fused(Params p) {
 
         // ---- B: 1024-point FFT as 32 x 32 ----
         af_fft32(z);                                          // over n2; Y[n1=lane][ka] at AF_BR5(ka)
+        {
+            float yr[32], yi[32];
 #pragma unroll
-        for (int ka = 0; ka < 32; ka++) {                     // times W_1024^(lane*ka) = W^(lane*(ka&15)) * W^(16*lane*(ka>>4))
-            c64 y = z[AF_BR5(ka)];
-            if (ka >= 16) y = c_mul(y, w16);
-            if (ka & 15) y = c_mul(y, sTw1C[(ka & 15) * 32 + lane]);
-            scr2[ka * 33 + lane] = y;
+            for (int ka = 0; ka < 32; ka++) {                 // times W_1024^(lane*ka) = W^(lane*(ka&15)) * W^(16*lane*(ka>>4))
+                c64 y = z[AF_BR5(ka)];
+                if (ka >= 16) y = c_mul(y, w16);
+                if (ka & 15) y = c_mul(y, sTw1C[(ka & 15) * 32 + lane]);
+                c_unpack(y, yr[ka], yi[ka]);
+            }
+            // 32 x 32 transpose, real plane then imaginary plane, through one 33-padded float buffer
+#pragma unroll
+            for (int ka = 0; ka < 32; ka++) scratch[ka * 33 + lane] = yr[ka];
+            __syncwarp();
+#pragma unroll
+            for (int n1 = 0; n1 < 32; n1++) yr[n1] = scratch[lane * 33 + n1];
+            __syncwarp();
+#pragma unroll
+            for (int ka = 0; ka < 32; ka++) scratch[ka * 33 + lane] = yi[ka];
+            __syncwarp();
+#pragma unroll
+            for (int n1 = 0; n1 < 32; n1++) z[n1] = c_pack(yr[n1], scratch[lane * 33 + n1]);
+            __syncwarp();
         }
-        __syncwarp();
-#pragma unroll
-        for (int n1 = 0; n1 < 32; n1++) z[n1] = scr2[lane * 33 + n1];
-        __syncwarp();
         af_fft32(z);                                          // over n1; Z[lane + 32*kb] at AF_BR5(kb)
 
         // ---- C: real-FFT post-pass + power / magnitude -> Ps[0..1024] ----
