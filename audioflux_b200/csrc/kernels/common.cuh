@@ -44,6 +44,20 @@ __device__ __forceinline__ void af_mbar_wait(uint64_t *bar, uint32_t parity) {
         if (++spins > (1u << 26)) __trap();
     }
 }
+// same wait for helper warps that idle most of the time: suspend-time hint (ns) keeps them asleep in hardware
+// instead of spinning through issue slots the compute warps need; an arrival still wakes them at once
+__device__ __forceinline__ void af_mbar_wait_sleepy(uint64_t *bar, uint32_t parity) {
+    uint32_t spins = 0, ok = 0;
+    while (true) {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t}"
+            : "=r"(ok) : "r"(af_smem_u32(bar)), "r"(parity), "r"(20000u) : "memory");
+        if (ok) break;
+        if (++spins > (1u << 22)) __trap();
+    }
+}
 // global -> shared bulk async copy; bytes, src and dst must be multiples of 16
 __device__ __forceinline__ void af_tma_load_1d(void *dstSmem, const void *srcGmem, uint32_t bytes, uint64_t *bar) {
     asm volatile(

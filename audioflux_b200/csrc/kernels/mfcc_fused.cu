@@ -38,7 +38,7 @@ namespace {
 
 constexpr int kN = 2048;            // fftLength
 constexpr int kNC = 1024;           // packed complex points
-constexpr int kFrameWarps = 15;     // consumer warps = max frames per tile (465 frames per 5 s clip = 31 x 15)
+constexpr int kFrameWarps = 12;     // consumer warps = max frames per tile
 constexpr int kEpiWarps = 2;         // DCT epilogue warps, one per log-mel tile buffer (tiles alternate)
 constexpr int kThreads = (kFrameWarps + 1 + kEpiWarps) * 32;   // + TMA producer warp + DCT epilogue warps
 constexpr int kLPitch = 132;        // log-mel tile row pitch (floats): 4g + t -> 32 distinct banks for mma A fragments
@@ -145,7 +145,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_mfcc_fused(Params p) {
             for (long long tile = blockIdx.x; tile < p.totalTiles; tile += gridDim.x, ++it) {
                 const int stage = it % kStages;
                 const uint32_t round = (uint32_t)(it / kStages);
-                af_mbar_wait(&emptyBar[stage], (round & 1u) ^ 1u);
+                af_mbar_wait_sleepy(&emptyBar[stage], (round & 1u) ^ 1u);
                 const long long clip = tile / p.tilesPerClip;
                 const int f0 = (int)(tile % p.tilesPerClip) * F;
                 const int nf = min(F, p.timeLength - f0);
@@ -170,7 +170,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_mfcc_fused(Params p) {
             const long long clip = tile / p.tilesPerClip;
             const int f0 = (int)(tile % p.tilesPerClip) * F;
             const int nf = min(F, p.timeLength - f0);
-            af_mbar_wait(&lFull[buf], (uint32_t)(it >> 1) & 1u);
+            af_mbar_wait_sleepy(&lFull[buf], (uint32_t)(it >> 1) & 1u);
             const float *A = sL + (size_t)buf * kLRows * kLPitch;
             float acc[CT][4];
 #pragma unroll
@@ -327,22 +327,27 @@ __global__ void __launch_bounds__(kThreads, 1) k_mfcc_fused(Params p) {
         // ---- D: banded filter bank (lane = filter within group, bank-conflict-free starts) + rectify ----
         af_mbar_wait(&lEmpty[lbuf], ((uint32_t)(it >> 1) & 1u) ^ 1u);   // epilogue done with tile it-2
         {
-            const float *wg = sMelW + lane;
+            // weights: per group [len/4][32 lanes] float4 (LDS.128); P: two LDS.64 per 4 taps (starts are even and
+            // spread over distinct 8-byte bank pairs per half-warp by the host planner)
+            const float4 *wg4 = reinterpret_cast<const float4 *>(sMelW) + lane;
             for (int g = 0; g < p.melGroups; g++) {
-                const int len = p.melGroupLen[g];              // multiple of 4
-                const float *ps = scratch + sMelStart[g * 32 + lane];
+                const int len4 = p.melGroupLen[g] >> 2;
+                const float2 *ps2 = reinterpret_cast<const float2 *>(scratch + sMelStart[g * 32 + lane]);
                 float acc0 = 0.0f, acc1 = 0.0f, acc2 = 0.0f, acc3 = 0.0f;
-                for (int i = 0; i < len; i += 4) {
-                    acc0 = fmaf(ps[i], wg[i * 32], acc0);
-                    acc1 = fmaf(ps[i + 1], wg[(i + 1) * 32], acc1);
-                    acc2 = fmaf(ps[i + 2], wg[(i + 2) * 32], acc2);
-                    acc3 = fmaf(ps[i + 3], wg[(i + 3) * 32], acc3);
+#pragma unroll 4
+                for (int i = 0; i < len4; i++) {
+                    const float4 w = wg4[i * 32];
+                    const float2 p0 = ps2[2 * i], p1 = ps2[2 * i + 1];
+                    acc0 = fmaf(p0.x, w.x, acc0);
+                    acc1 = fmaf(p0.y, w.y, acc1);
+                    acc2 = fmaf(p1.x, w.z, acc2);
+                    acc3 = fmaf(p1.y, w.w, acc3);
                 }
                 float v = (acc0 + acc1) + (acc2 + acc3);
                 if (p.rectify == CepstralRectify_CubicRoot) v = powf(v, 1.0f / 3.0f);
                 else v = log10f(v < 1e-8f ? 1e-8f : v);
                 lrow[g * 32 + lane] = v;
-                wg += len * 32;
+                wg4 += len4 * 32;
             }
             for (int g = p.melGroups; g < 4; g++) lrow[g * 32 + lane] = 0.0f;
         }
@@ -361,28 +366,31 @@ void free_plan(Plan *pl) {
 
 }  // namespace
 
-// Mel plan: filters are processed in groups of 32 (lane = filter).  Each filter's first tap is moved
-// down by delta in [0, 31] (extra taps get zero weight) until the 32 start bins of a group fall in 32
-// different shared-memory banks, longest filters first; group length = max(len + delta), rounded up to 4.
+// Mel plan: filters are processed in groups of 32 (lane = filter).  Each filter's first tap is moved down by
+// delta (extra taps get zero weight) until the start bin is even and, within each half-warp, the 16 start bins
+// fall in 16 different 8-byte bank pairs -> the LDS.64 reads of the power spectrum are conflict-free.
+// Longest filters are placed first; group length = max(len + delta), rounded up to 4.
 static int plan_mel(const AfBands *bands, int num, int *startShifted /* kMaxNum */, int *groupLen /* 4 */) {
     int total = 0;
     for (int m = 0; m < kMaxNum; m++) startShifted[m] = 0;
     for (int g = 0; g < 4; g++) groupLen[g] = 0;
     for (int g = 0; g * 32 < num; g++) {
-        int order[32], cnt = 0;
-        for (int m = g * 32; m < num && m < g * 32 + 32; m++) order[cnt++] = m;
-        for (int i = 1; i < cnt; i++)                         // insertion sort, longest first
-            for (int j = i; j > 0 && bands->len[order[j]] > bands->len[order[j - 1]]; j--) { int t = order[j]; order[j] = order[j - 1]; order[j - 1] = t; }
-        unsigned used = 0;
         int len = 0;
-        for (int i = 0; i < cnt; i++) {
-            const int m = order[i], s0 = bands->start[m];
-            int delta = 0;
-            while (delta < 32 && s0 - delta >= 0 && (used >> ((s0 - delta) & 31) & 1u)) delta++;
-            if (delta >= 32 || s0 - delta < 0) delta = 0;     // no free bank reachable: accept a conflict
-            used |= 1u << ((s0 - delta) & 31);
-            startShifted[m] = s0 - delta;
-            if (bands->len[m] + delta > len) len = bands->len[m] + delta;
+        for (int h = 0; h < 2; h++) {                         // half-warps: lanes 16h .. 16h+15
+            int order[16], cnt = 0;
+            for (int m = g * 32 + 16 * h; m < num && m < g * 32 + 16 * h + 16; m++) order[cnt++] = m;
+            for (int i = 1; i < cnt; i++)
+                for (int j = i; j > 0 && bands->len[order[j]] > bands->len[order[j - 1]]; j--) { int t = order[j]; order[j] = order[j - 1]; order[j - 1] = t; }
+            unsigned used = 0;
+            for (int i = 0; i < cnt; i++) {
+                const int m = order[i], s0 = bands->start[m];
+                int delta = s0 & 1;                           // even start
+                while (delta < 34 && s0 - delta >= 0 && (used >> (((s0 - delta) >> 1) & 15) & 1u)) delta += 2;
+                if (delta >= 34 || s0 - delta < 0) delta = s0 & 1;   // no free bank pair reachable: accept a conflict
+                used |= 1u << (((s0 - delta) >> 1) & 15);
+                startShifted[m] = s0 - delta;
+                if (bands->len[m] + delta > len) len = bands->len[m] + delta;
+            }
         }
         len = (len + 3) & ~3;
         groupLen[g] = len;
@@ -431,7 +439,7 @@ extern "C" int af_mfcc_plan_build(void **planOut, int fftLength, int num, int cc
     if (rc == AF_OK) rc = af_dev_upload(reinterpret_cast<void **>(&pl->dTw2), tw, sizeof(float2) * 32);
     free(tw);
 
-    // transposed, zero-padded band weights: group g -> [len_g][32], starts shifted for bank-conflict-free reads
+    // zero-padded band weights: group g -> [len_g/4][32 lanes][4 taps], starts shifted for conflict-free reads
     const int width = kNC + 1;
     pl->melGroups = (num + 31) / 32;
     int starts[kMaxNum];
@@ -445,7 +453,7 @@ extern "C" int af_mfcc_plan_build(void **planOut, int fftLength, int num, int cc
             if (m >= num) continue;
             const int delta = bands->start[m] - starts[m];
             for (int i = 0; i < bands->len[m]; i++)
-                mw[off + (i + delta) * 32 + l] = bank[(size_t)m * width + bands->start[m] + i];
+                mw[off + ((i + delta) >> 2) * 128 + l * 4 + ((i + delta) & 3)] = bank[(size_t)m * width + bands->start[m] + i];
         }
         off += pl->melGroupLen[g] * 32;
     }
