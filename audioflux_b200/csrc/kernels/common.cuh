@@ -53,7 +53,7 @@ __device__ __forceinline__ void af_mbar_wait_sleepy(uint64_t *bar, uint32_t pari
             "{\n\t.reg .pred p;\n\t"
             "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
             "selp.u32 %0, 1, 0, p;\n\t}"
-            : "=r"(ok) : "r"(af_smem_u32(bar)), "r"(parity), "r"(20000u) : "memory");
+            : "=r"(ok) : "r"(af_smem_u32(bar)), "r"(parity), "r"(2000u) : "memory");
         if (ok) break;
         if (++spins > (1u << 22)) __trap();
     }

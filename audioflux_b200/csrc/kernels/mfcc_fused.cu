@@ -172,15 +172,24 @@ __global__ void __launch_bounds__(kThreads, 1) k_mfcc_fused(Params p) {
             const int nf = min(F, p.timeLength - f0);
             af_mbar_wait_sleepy(&lFull[buf], (uint32_t)(it >> 1) & 1u);
             const float *A = sL + (size_t)buf * kLRows * kLPitch;
-            float acc[CT][4];
+            // two accumulator sets (hi*hi and the two cross terms) and term-major issue order: consecutive HMMAs
+            // never touch the same accumulator, so the in-order warp is not serialised on the mma latency
+            float acc[CT][4], acx[CT][4];
 #pragma unroll
-            for (int n = 0; n < CT; n++) { acc[n][0] = acc[n][1] = acc[n][2] = acc[n][3] = 0.0f; }
-#pragma unroll 4
+            for (int n = 0; n < CT; n++) {
+                acc[n][0] = acc[n][1] = acc[n][2] = acc[n][3] = 0.0f;
+                acx[n][0] = acx[n][1] = acx[n][2] = acx[n][3] = 0.0f;
+            }
+#define AF_MMA_TF32(ACC, A0, A1, A2, A3, B0, B1)                                                              \
+    asm("mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};" \
+        : "+f"(ACC[0]), "+f"(ACC[1]), "+f"(ACC[2]), "+f"(ACC[3])                                              \
+        : "r"(A0), "r"(A1), "r"(A2), "r"(A3), "r"(B0), "r"(B1))
+#pragma unroll 2
             for (int k0 = 0; k0 < kMaxNum; k0 += 8) {
-                float af[4] = {A[g * kLPitch + k0 + t], A[(g + 8) * kLPitch + k0 + t],
-                               A[g * kLPitch + k0 + t + 4], A[(g + 8) * kLPitch + k0 + t + 4]};
+                const float af[4] = {A[g * kLPitch + k0 + t], A[(g + 8) * kLPitch + k0 + t],
+                                     A[g * kLPitch + k0 + t + 4], A[(g + 8) * kLPitch + k0 + t + 4]};
                 // TF32 split by truncation: hi = top 19 bits, lo = (x - hi) (exact), again cut to 19 bits
-                uint32_t ah[4], al[4];
+                uint32_t ah[4], al[4], bh[CT][2], bl[CT][2];
 #pragma unroll
                 for (int i = 0; i < 4; i++) {
                     ah[i] = __float_as_uint(af[i]) & 0xffffe000u;
@@ -189,22 +198,24 @@ __global__ void __launch_bounds__(kThreads, 1) k_mfcc_fused(Params p) {
 #pragma unroll
                 for (int n = 0; n < CT; n++) {
                     const float bf[2] = {sDct[(k0 + t) * kDctPitch + n * 8 + g], sDct[(k0 + t + 4) * kDctPitch + n * 8 + g]};
-                    uint32_t bh[2], bl[2];
 #pragma unroll
                     for (int i = 0; i < 2; i++) {
-                        bh[i] = __float_as_uint(bf[i]) & 0xffffe000u;
-                        bl[i] = __float_as_uint(bf[i] - __uint_as_float(bh[i])) & 0xffffe000u;
+                        bh[n][i] = __float_as_uint(bf[i]) & 0xffffe000u;
+                        bl[n][i] = __float_as_uint(bf[i] - __uint_as_float(bh[n][i])) & 0xffffe000u;
                     }
-#define AF_MMA_TF32(A0, A1, A2, A3, B0, B1)                                                                   \
-    asm volatile("mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};" \
-                 : "+f"(acc[n][0]), "+f"(acc[n][1]), "+f"(acc[n][2]), "+f"(acc[n][3])                        \
-                 : "r"(A0), "r"(A1), "r"(A2), "r"(A3), "r"(B0), "r"(B1))
-                    AF_MMA_TF32(al[0], al[1], al[2], al[3], bh[0], bh[1]);
-                    AF_MMA_TF32(ah[0], ah[1], ah[2], ah[3], bl[0], bl[1]);
-                    AF_MMA_TF32(ah[0], ah[1], ah[2], ah[3], bh[0], bh[1]);
-#undef AF_MMA_TF32
                 }
+#pragma unroll
+                for (int n = 0; n < CT; n++) AF_MMA_TF32(acx[n], al[0], al[1], al[2], al[3], bh[n][0], bh[n][1]);
+#pragma unroll
+                for (int n = 0; n < CT; n++) AF_MMA_TF32(acc[n], ah[0], ah[1], ah[2], ah[3], bh[n][0], bh[n][1]);
+#pragma unroll
+                for (int n = 0; n < CT; n++) AF_MMA_TF32(acx[n], ah[0], ah[1], ah[2], ah[3], bl[n][0], bl[n][1]);
             }
+#undef AF_MMA_TF32
+#pragma unroll
+            for (int n = 0; n < CT; n++)
+#pragma unroll
+                for (int i = 0; i < 4; i++) acc[n][i] += acx[n][i];
             __syncwarp();
             if (lane == 0) af_mbar_arrive(&lEmpty[buf]);           // tile consumed: frame warps may overwrite it
             // C fragment: rows g and g+8, columns n*8 + 2t, +1
