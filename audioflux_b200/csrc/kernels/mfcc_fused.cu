@@ -345,14 +345,19 @@ __global__ void __launch_bounds__(kThreads, 1) k_mfcc_fused(Params p) {
                 const int len4 = p.melGroupLen[g] >> 2;
                 const float2 *ps2 = reinterpret_cast<const float2 *>(scratch + sMelStart[g * 32 + lane]);
                 float acc0 = 0.0f, acc1 = 0.0f, acc2 = 0.0f, acc3 = 0.0f;
-#pragma unroll 4
+                // software pipelined: the loads of stage i+1 are in flight while stage i is accumulated
+                // (the final prefetch over-reads one stage: the tables carry one stage of padding)
+                float4 w = wg4[0];
+                float2 p0 = ps2[0], p1 = ps2[1];
+#pragma unroll 2
                 for (int i = 0; i < len4; i++) {
-                    const float4 w = wg4[i * 32];
-                    const float2 p0 = ps2[2 * i], p1 = ps2[2 * i + 1];
+                    const float4 wn = wg4[(i + 1) * 32];
+                    const float2 q0 = ps2[2 * i + 2], q1 = ps2[2 * i + 3];
                     acc0 = fmaf(p0.x, w.x, acc0);
                     acc1 = fmaf(p0.y, w.y, acc1);
                     acc2 = fmaf(p1.x, w.z, acc2);
                     acc3 = fmaf(p1.y, w.w, acc3);
+                    w = wn; p0 = q0; p1 = q1;
                 }
                 float v = (acc0 + acc1) + (acc2 + acc3);
                 if (p.rectify == CepstralRectify_CubicRoot) v = powf(v, 1.0f / 3.0f);
@@ -377,44 +382,50 @@ void free_plan(Plan *pl) {
 
 }  // namespace
 
-// Mel plan: filters are processed in groups of 32 (lane = filter).  Each filter's first tap is moved down by
-// delta (extra taps get zero weight) until the start bin is even and, within each half-warp, the 16 start bins
-// fall in 16 different 8-byte bank pairs -> the LDS.64 reads of the power spectrum are conflict-free.
-// Longest filters are placed first; group length = max(len + delta), rounded up to 4.
+// Mel plan: filters are processed in groups of 32 (lane = filter).  Each filter's first tap may be moved down by
+// delta (extra taps get zero weight): delta makes the start bin even (LDS.64 reads of the power spectrum) and,
+// where the group's length budget allows, spreads the 16 starts of a half-warp over different 8-byte bank
+// pairs.  The budget is the longest filter of the group (+1 for parity) rounded up to 4 taps, so short groups
+// of adjacent filters accept a 2-way conflict instead of padding; longest filters are placed first.
 static int plan_mel(const AfBands *bands, int num, int *startShifted /* kMaxNum */, int *groupLen /* 4 */) {
     int total = 0;
     for (int m = 0; m < kMaxNum; m++) startShifted[m] = 0;
     for (int g = 0; g < 4; g++) groupLen[g] = 0;
     for (int g = 0; g * 32 < num; g++) {
+        int gmax = 0;
+        for (int m = g * 32; m < num && m < g * 32 + 32; m++) if (bands->len[m] > gmax) gmax = bands->len[m];
+        const int cap = (gmax + 1 + 3) & ~3;
         int len = 0;
         for (int h = 0; h < 2; h++) {                         // half-warps: lanes 16h .. 16h+15
-            int order[16], cnt = 0;
+            int order[16], cnt = 0, used[16] = {0};
             for (int m = g * 32 + 16 * h; m < num && m < g * 32 + 16 * h + 16; m++) order[cnt++] = m;
             for (int i = 1; i < cnt; i++)
                 for (int j = i; j > 0 && bands->len[order[j]] > bands->len[order[j - 1]]; j--) { int t = order[j]; order[j] = order[j - 1]; order[j - 1] = t; }
-            unsigned used = 0;
             for (int i = 0; i < cnt; i++) {
                 const int m = order[i], s0 = bands->start[m];
-                int delta = s0 & 1;                           // even start
-                while (delta < 34 && s0 - delta >= 0 && (used >> (((s0 - delta) >> 1) & 15) & 1u)) delta += 2;
-                if (delta >= 34 || s0 - delta < 0) delta = s0 & 1;   // no free bank pair reachable: accept a conflict
-                used |= 1u << (((s0 - delta) >> 1) & 15);
-                startShifted[m] = s0 - delta;
-                if (bands->len[m] + delta > len) len = bands->len[m] + delta;
+                int best = -1, bestUsed = 1 << 30;
+                for (int d = s0 & 1; d < 34 && s0 - d >= 0 && bands->len[m] + d <= cap; d += 2) {
+                    const int u = used[((s0 - d) >> 1) & 15];
+                    if (u < bestUsed) { bestUsed = u; best = d; }
+                }
+                if (best < 0) best = (s0 & 1) && s0 > 0 ? 1 : 0;
+                used[((s0 - best) >> 1) & 15]++;
+                startShifted[m] = s0 - best;
+                if (bands->len[m] + best > len) len = bands->len[m] + best;
             }
         }
         len = (len + 3) & ~3;
         groupLen[g] = len;
         total += len * 32;
     }
-    return total;
+    return total + 4 * 32;                                    // one stage of padding for the pipelined prefetch
 }
 
 extern "C" int af_mfcc_fused_supported(int fftLength, int num, int ccNum, const AfBands *bands) {
     if (fftLength != kN || num < 1 || num > kMaxNum || ccNum < 1 || ccNum > 64 || !bands) return 0;
     int starts[kMaxNum], groupLen[4];
     const int floats = plan_mel(bands, num, starts, groupLen);
-    for (int g = 0; g < 4; g++) if (groupLen[g] > kPsPad - (kNC + 1)) return 0;   // padded reads must stay inside the zero pad
+    for (int g = 0; g < 4; g++) if (groupLen[g] + 4 > kPsPad - (kNC + 1)) return 0;   // padded (and prefetched) reads stay inside the zero pad
     return floats * 4 <= 24 * 1024;                              // weight table budget in shared memory
 }
 
