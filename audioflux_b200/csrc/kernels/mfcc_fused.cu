@@ -38,7 +38,10 @@ namespace {
 
 constexpr int kN = 2048;            // fftLength
 constexpr int kNC = 1024;           // packed complex points
-constexpr int kFrameWarps = 12;     // consumer warps = max frames per tile
+#ifndef AF_FRAME_WARPS
+#define AF_FRAME_WARPS 12
+#endif
+constexpr int kFrameWarps = AF_FRAME_WARPS;     // consumer warps = max frames per tile (<= 16: one mma M tile)
 constexpr int kEpiWarps = 2;         // DCT epilogue warps, one per log-mel tile buffer (tiles alternate)
 constexpr int kThreads = (kFrameWarps + 1 + kEpiWarps) * 32;   // + TMA producer warp + DCT epilogue warps
 constexpr int kLPitch = 132;        // log-mel tile row pitch (floats): 4g + t -> 32 distinct banks for mma A fragments
@@ -361,7 +364,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_mfcc_fused(Params p) {
                 }
                 float v = (acc0 + acc1) + (acc2 + acc3);
                 if (p.rectify == CepstralRectify_CubicRoot) v = powf(v, 1.0f / 3.0f);
-                else v = log10f(v < 1e-8f ? 1e-8f : v);
+                else v = __log2f(v < 1e-8f ? 1e-8f : v) * 0.30102999566398120f;   // log10 via MUFU.LG2
                 lrow[g * 32 + lane] = v;
                 wg4 += len4 * 32;
             }
