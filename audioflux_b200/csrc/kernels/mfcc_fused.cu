@@ -42,10 +42,18 @@ constexpr int kNC = 1024;           // packed complex points
 #define AF_FRAME_WARPS 12
 #endif
 constexpr int kFrameWarps = AF_FRAME_WARPS;     // consumer warps = max frames per tile (<= 16: one mma M tile)
-constexpr int kEpiWarps = 2;         // DCT epilogue warps, one per log-mel tile buffer (tiles alternate)
+#ifndef AF_EPI_WARPS
+#define AF_EPI_WARPS 2
+#endif
+#ifndef AF_CTAS_PER_SM
+#define AF_CTAS_PER_SM 1
+#endif
+constexpr int kEpiWarps = AF_EPI_WARPS;   // DCT epilogue warps; tile `it` is served by warp it % kEpiWarps
+constexpr int kCtasPerSm = AF_CTAS_PER_SM;   // independent CTAs per SM drift apart, so their phases (LSU-heavy load /
+                                             // transpose / bank vs FMA-heavy FFT) overlap instead of queueing on one pipe
 constexpr int kThreads = (kFrameWarps + 1 + kEpiWarps) * 32;   // + TMA producer warp + DCT epilogue warps
 constexpr int kLPitch = 132;        // log-mel tile row pitch (floats): 4g + t -> 32 distinct banks for mma A fragments
-constexpr int kLRows = 16;          // mma M
+constexpr int kLRows = kFrameWarps <= 8 ? 8 : 16;   // stored rows of the mma M=16 tile (rows beyond are zeros)
 constexpr int kStages = 2;
 constexpr int kMaxNum = 128;        // filters (padded)
 constexpr int kScratchFloats = 1152;            // per warp: 33x32 float transpose plane, later Ps[0..1024] + zero pad
@@ -104,7 +112,7 @@ __host__ __device__ inline Smem carve(int spanFloats, int melWFloats, int ct) {
 }
 
 template <int CT>
-__global__ void __launch_bounds__(kThreads, 1) k_mfcc_fused(Params p) {
+__global__ void __launch_bounds__(kThreads, kCtasPerSm) k_mfcc_fused(Params p) {
     extern __shared__ __align__(128) unsigned char smem[];
     const Smem L = carve(p.spanFloats, p.melWFloats, CT);
     float *span = reinterpret_cast<float *>(smem + L.spanOff);
@@ -166,10 +174,11 @@ __global__ void __launch_bounds__(kThreads, 1) k_mfcc_fused(Params p) {
         // out[16 x 8*CT] = L[16 x 128] . D^T[128 x 8*CT], mma.sync.m16n8k8 TF32 with the 3xTF32 split
         // (x = hi + lo, hi = tf32(x), lo = tf32(x - hi);  lo*hi + hi*lo + hi*hi) -> fp32-level accuracy.
         const int g = lane >> 2, t = lane & 3;
-        const int buf = warp - (kFrameWarps + 1);                  // this warp owns log-mel buffer `buf`
+        const int epi = warp - (kFrameWarps + 1);
         int it = 0;
         for (long long tile = blockIdx.x; tile < p.totalTiles; tile += gridDim.x, ++it) {
-            if ((it & 1) != buf) continue;
+            if (it % kEpiWarps != epi) continue;
+            const int buf = it & 1;
             const long long clip = tile / p.tilesPerClip;
             const int f0 = (int)(tile % p.tilesPerClip) * F;
             const int nf = min(F, p.timeLength - f0);
@@ -189,8 +198,8 @@ __global__ void __launch_bounds__(kThreads, 1) k_mfcc_fused(Params p) {
         : "r"(A0), "r"(A1), "r"(A2), "r"(A3), "r"(B0), "r"(B1))
 #pragma unroll 2
             for (int k0 = 0; k0 < kMaxNum; k0 += 8) {
-                const float af[4] = {A[g * kLPitch + k0 + t], A[(g + 8) * kLPitch + k0 + t],
-                                     A[g * kLPitch + k0 + t + 4], A[(g + 8) * kLPitch + k0 + t + 4]};
+                const float af[4] = {A[g * kLPitch + k0 + t], kLRows > 8 ? A[(g + 8) * kLPitch + k0 + t] : 0.0f,
+                                     A[g * kLPitch + k0 + t + 4], kLRows > 8 ? A[(g + 8) * kLPitch + k0 + t + 4] : 0.0f};
                 // TF32 split by truncation: hi = top 19 bits, lo = (x - hi) (exact), again cut to 19 bits
                 uint32_t ah[4], al[4], bh[CT][2], bl[CT][2];
 #pragma unroll
@@ -518,7 +527,7 @@ extern "C" int af_launch_mfcc_fused(void *plan, const float *data, int dataLengt
     p.ccNum = pl->ccNum; p.rectify = rectifyType; p.dataType = pl->dataType;
 
     // frames per tile: as many as fit the shared-memory budget (<= kFrameWarps)
-    const int budget = 227 * 1024;
+    const int budget = kCtasPerSm == 1 ? 227 * 1024 : (233472 - kCtasPerSm * 1024) / kCtasPerSm;
     int F = kFrameWarps;
     for (; F >= 1; F--) {
         int spanFloats = (F - 1) * slideLength + kN;
@@ -534,7 +543,7 @@ extern "C" int af_launch_mfcc_fused(void *plan, const float *data, int dataLengt
 
     int sms = af_sm_count();
     if (sms <= 0) sms = 148;
-    long long grid = p.totalTiles < sms ? p.totalTiles : sms;
+    long long grid = p.totalTiles < (long long)sms * kCtasPerSm ? p.totalTiles : (long long)sms * kCtasPerSm;
     cudaStream_t st = (cudaStream_t)stream;
     cudaError_t e = cudaSuccess;
 #define AF_MFCC_LAUNCH(CT_)                                                                              \
