@@ -39,9 +39,9 @@ namespace {
 constexpr int kN = 2048;            // fftLength
 constexpr int kNC = 1024;           // packed complex points
 #ifndef AF_FRAME_WARPS
-#define AF_FRAME_WARPS 12
+#define AF_FRAME_WARPS 13
 #endif
-constexpr int kFrameWarps = AF_FRAME_WARPS;     // consumer warps = max frames per tile (<= 16: one mma M tile)
+constexpr int kFrameWarps = AF_FRAME_WARPS;     // consumer warps = max frames per tile (<= 16: one mma M tile); 13 measured best (tools/sweep_frame_warps.sh)
 #ifndef AF_EPI_WARPS
 #define AF_EPI_WARPS 2
 #endif
