@@ -24,9 +24,14 @@ __device__ __forceinline__ float2 cw(int k, int m, float dir) {   // exp(dir * 2
     return make_float2(c, s);
 }
 
+// tw[j] = exp(dir * 2 pi i j / n), j < n: one table per CTA replaces a sincospif per butterfly
+__device__ void fill_twiddles(float2 *tw, int n, float dir) {
+    for (int j = threadIdx.x; j < n; j += blockDim.x) tw[j] = cw(j, n, dir);
+}
+
 // In-place-pair Stockham FFT over `cnt` independent sequences of length n = 2^log2n stored with pitch
 // `pitch` (float2 units) in a / b.  All threads of the CTA cooperate; result pointer returned.
-__device__ float2 *block_fft_multi(float2 *a, float2 *b, int log2n, int cnt, int pitch, float dir) {
+__device__ float2 *block_fft_multi(float2 *a, float2 *b, int log2n, int cnt, int pitch, float dir, const float2 *tw) {
     const int n = 1 << log2n;
     int P = 1, rem = log2n;
     while (rem >= 2) {
@@ -38,8 +43,8 @@ __device__ float2 *block_fft_multi(float2 *a, float2 *b, int log2n, int cnt, int
             const int k = i & (P - 1);
             float2 u0 = src[i], u1 = src[i + t], u2 = src[i + 2 * t], u3 = src[i + 3 * t];
             if (k) {
-                const float2 w1 = cw(k, 4 * P, dir);
-                const float2 w2 = af_cmul(w1, w1), w3 = af_cmul(w2, w1);
+                const int idx = k * (n / (4 * P));                 // exp(dir 2 pi i k / 4P) = tw[k n / 4P]
+                const float2 w1 = tw[idx], w2 = tw[2 * idx], w3 = tw[3 * idx];
                 u1 = af_cmul(u1, w1); u2 = af_cmul(u2, w2); u3 = af_cmul(u3, w3);
             }
             const float2 s02 = make_float2(u0.x + u2.x, u0.y + u2.y), d02 = make_float2(u0.x - u2.x, u0.y - u2.y);
@@ -65,7 +70,7 @@ __device__ float2 *block_fft_multi(float2 *a, float2 *b, int log2n, int cnt, int
             const int k = i & (P - 1);
             const float2 u0 = src[i];
             float2 u1 = src[i + t];
-            if (k) u1 = af_cmul(u1, cw(k, 2 * P, dir));
+            if (k) u1 = af_cmul(u1, tw[k * (n / (2 * P))]);
             const int j = ((i - k) << 1) + k;
             dst[j] = make_float2(u0.x + u1.x, u0.y + u1.y);
             dst[j + P] = make_float2(u0.x - u1.x, u0.y - u1.y);
@@ -131,6 +136,8 @@ __global__ void k_cwt_cols(CwtParams p) {
     extern __shared__ __align__(16) unsigned char smemRaw[];
     const int N1 = p.N1, N2 = p.N2, pitch = N1 + 1;
     float2 *a = reinterpret_cast<float2 *>(smemRaw), *b = a + (size_t)p.cols * pitch;
+    float2 *tw = b + (size_t)p.cols * pitch;                       // [N1] leg twiddles, then [N2] fine inter-leg twiddles
+    float2 *tf = tw + N1;
     const int item = blockIdx.x;                                   // MODE 0: clip ; MODE 1: clip*num + scale
     const int clip = MODE == 0 ? item : item / p.num;
     const int sIdx = MODE == 0 ? 0 : item % p.num;
@@ -138,6 +145,8 @@ __global__ void k_cwt_cols(CwtParams p) {
     const int nc = min(p.cols, N2 - col0);
     const float dir = MODE == 0 ? -1.0f : 1.0f;
     const float s = MODE == 1 ? p.scaleArr[sIdx] : 0.0f;
+    fill_twiddles(tw, N1, dir);
+    if (N2 > 1) for (int j = threadIdx.x; j < N2; j += blockDim.x) tf[j] = cw(j, p.N, dir);
 
     for (int e = threadIdx.x; e < N1 * nc; e += blockDim.x) {
         const int i = e / nc, c = e - i * nc;
@@ -158,7 +167,7 @@ __global__ void k_cwt_cols(CwtParams p) {
         a[(size_t)c * pitch + i] = v;
     }
     __syncthreads();
-    float2 *r = block_fft_multi(a, b, p.log2N1, nc, pitch, dir);
+    float2 *r = block_fft_multi(a, b, p.log2N1, nc, pitch, dir, tw);
 
     if (N2 == 1) {
         // whole transform done: r[0][k]
@@ -180,10 +189,8 @@ __global__ void k_cwt_cols(CwtParams p) {
         const int k1 = e / nc, c = e - k1 * nc;
         const int col = col0 + c;
         float2 v = r[(size_t)c * pitch + k1];
-        const long long prod = (long long)col * k1;               // < N
-        float sn, cs;
-        sincospif(dir * 2.0f * (float)((double)prod / (double)p.N), &sn, &cs);
-        v = af_cmul(v, make_float2(cs, sn));
+        const int prod = col * k1;                                 // < N;  exp(dir 2 pi i prod / N) = tw[prod / N2] * tf[prod % N2]
+        v = af_cmul(v, af_cmul(tw[prod >> p.log2N2], tf[prod & (N2 - 1)]));
         wk[(size_t)k1 * N2 + col] = v;
     }
 }
@@ -193,18 +200,20 @@ __global__ void k_cwt_rows(CwtParams p) {
     extern __shared__ __align__(16) unsigned char smemRaw[];
     const int N1 = p.N1, N2 = p.N2, pitch = N2 + 1;
     float2 *a = reinterpret_cast<float2 *>(smemRaw), *b = a + (size_t)p.rows * pitch;
+    float2 *tw = b + (size_t)p.rows * pitch;                       // [N2]
     const int item = blockIdx.x;
     const int clip = MODE == 0 ? item : item / p.num;
     const int row0 = blockIdx.y * p.rows;
     const int nr = min(p.rows, N1 - row0);
     const float dir = MODE == 0 ? -1.0f : 1.0f;
     const float2 *wk = p.work + (size_t)item * p.N;
+    fill_twiddles(tw, N2, dir);
     for (int e = threadIdx.x; e < nr * N2; e += blockDim.x) {
         const int rr = e / N2, i = e - rr * N2;
         a[(size_t)rr * pitch + i] = wk[(size_t)(row0 + rr) * N2 + i];
     }
     __syncthreads();
-    float2 *r = block_fft_multi(a, b, p.log2N2, nr, pitch, dir);
+    float2 *r = block_fft_multi(a, b, p.log2N2, nr, pitch, dir, tw);
     // result element (row k1, k2) is sequence index k1 + N1*k2
     if (MODE == 0) {
         float2 *sp = p.spec + (size_t)clip * p.N;
@@ -279,8 +288,8 @@ extern "C" int af_launch_cwt(const AfCwtArgs *a, const float *data, void *worksp
     cudaStream_t st = (cudaStream_t)stream;
     int rc;
     const int threads = 512;
-    const size_t smemC = sizeof(float2) * 2 * (size_t)p.cols * (p.N1 + 1);
-    const size_t smemR = sizeof(float2) * 2 * (size_t)p.rows * (p.N2 + 1);
+    const size_t smemC = sizeof(float2) * (2 * (size_t)p.cols * (p.N1 + 1) + p.N1 + p.N2);
+    const size_t smemR = sizeof(float2) * (2 * (size_t)p.rows * (p.N2 + 1) + p.N2);
     if (smemC > 220 * 1024 || smemR > 220 * 1024) return af_fail(AF_ERR_UNSUPPORTED, "CWT length 2^%d does not fit the shared-memory FFT legs", a->log2n);
     if ((rc = set_smem(k_cwt_cols<0>, smemC, "smem k_cwt_cols<0>")) || (rc = set_smem(k_cwt_cols<1>, smemC, "smem k_cwt_cols<1>")) ||
         (rc = set_smem(k_cwt_rows<0>, smemR, "smem k_cwt_rows<0>")) || (rc = set_smem(k_cwt_rows<1>, smemR, "smem k_cwt_rows<1>"))) return rc;
