@@ -16,32 +16,45 @@
 
 namespace {
 
-constexpr int kDecTile = 256;     // outputs per CTA
+constexpr int kDecThreads = 256;
+constexpr int kDecPer = 4;                       // outputs per thread (register sliding window)
+constexpr int kDecTile = kDecThreads * kDecPer;  // outputs per CTA
+__constant__ float c_decTaps[64];                // [0..31] left taps (x[2i-j]), [32..62] right taps (x[2i+1+j])
 
-__global__ void __launch_bounds__(kDecTile) k_decimate2(const float *__restrict__ in, int inLength, long long inStride,
-                                                        const float *__restrict__ left32, const float *__restrict__ right31,
-                                                        float *__restrict__ out, long long outStride) {
-    __shared__ float sx[2 * kDecTile + 64];
-    __shared__ float sl[32], sr[32];
+// out[i] = (sum_{j<32} L[j] x[2i-j] + sum_{j<31} R[j] x[2i+1+j]) / sqrt(1/2), zero outside the clip.
+// Each thread keeps a 72-sample window in registers (18 LDS.128) and produces 4 outputs: 252 FMAs with
+// the taps as constant-bank operands, instead of one shared load per FMA.
+__global__ void __launch_bounds__(kDecThreads) k_decimate2(const float *__restrict__ in, int inLength, long long inStride,
+                                                           float *__restrict__ out, long long outStride) {
+    __shared__ __align__(16) float sx[2 * kDecTile + 72];
     const int outLength = inLength / 2;
     const int o0 = blockIdx.x * kDecTile;
     const float *x = in + (long long)blockIdx.y * inStride;
-    if (threadIdx.x < 32) { sl[threadIdx.x] = left32[threadIdx.x]; sr[threadIdx.x] = threadIdx.x < 31 ? right31[threadIdx.x] : 0.0f; }
-    const int m0 = 2 * o0 - 31;                               // first input sample needed by this tile
-    for (int i = threadIdx.x; i < 2 * kDecTile + 64; i += kDecTile) {
+    const int m0 = 2 * o0 - 31;                               // sx[i] = x[m0 + i]
+    for (int i = threadIdx.x; i < 2 * kDecTile + 72; i += kDecThreads) {
         const int m = m0 + i;
         sx[i] = (m >= 0 && m < inLength) ? x[m] : 0.0f;
     }
     __syncthreads();
-    const int o = o0 + threadIdx.x;
-    if (o >= outLength) return;
-    const int c = 2 * threadIdx.x + 31;                       // position of x[2*o] in sx
-    float acc = 0.0f;
+    float w[72];
+    const float4 *s4 = reinterpret_cast<const float4 *>(sx + 8 * threadIdx.x);
 #pragma unroll
-    for (int j = 0; j < 32; j++) acc = fmaf(sl[j], sx[c - j], acc);
+    for (int v = 0; v < 18; v++) {
+        const float4 q = s4[v];
+        w[4 * v] = q.x; w[4 * v + 1] = q.y; w[4 * v + 2] = q.z; w[4 * v + 3] = q.w;
+    }
+    const float scale = 1.4142135623730951f;                  // 1 / sqrt(0.5)
 #pragma unroll
-    for (int j = 0; j < 31; j++) acc = fmaf(sr[j], sx[c + 1 + j], acc);
-    out[(long long)blockIdx.y * outStride + o] = acc / sqrtf(0.5f);
+    for (int q = 0; q < kDecPer; q++) {
+        const int c = 31 + 2 * q;                             // w[c] = x[2 * o]
+        float acc = 0.0f;
+#pragma unroll
+        for (int j = 0; j < 32; j++) acc = fmaf(c_decTaps[j], w[c - j], acc);
+#pragma unroll
+        for (int j = 0; j < 31; j++) acc = fmaf(c_decTaps[32 + j], w[c + 1 + j], acc);
+        const int o = o0 + kDecPer * threadIdx.x + q;
+        if (o < outLength) out[(long long)blockIdx.y * outStride + o] = acc * scale;
+    }
 }
 
 struct OctParams {
@@ -50,15 +63,16 @@ struct OctParams {
     const float2 *kappa;          // [bpo][N] (re, im)
     const float *scale;           // [bpo]
     float *outRe, *outIm; long long outStride; int num, colOff;
-    int TT;                       // frames per CTA (even)
+    int TT;                       // frames per CTA (multiple of kFT)
     int rowLen;                   // polyphase row pitch (floats)
     int rowsA;                    // ceil(N / hop)
     int nChunk;                   // kernel taps resident in shared memory at a time
 };
 
 constexpr int kBinsPerPass = 12;  // bins whose kernels sit in shared memory together
-constexpr int kFT = 2;            // frames per thread
-constexpr int kJG = 4;            // lane-groups over bins; 3 bins per thread
+constexpr int kFT = 4;            // frames per thread
+constexpr int kJG = 2;            // thread groups over bins
+constexpr int kBT = 6;            // bins per thread: 4 x 6 complex accumulators, 10 shared loads per 48 FMAs
 
 __global__ void k_cqt_octave(OctParams p) {
     extern __shared__ __align__(16) unsigned char smemRaw[];
@@ -78,17 +92,17 @@ __global__ void k_cqt_octave(OctParams p) {
         xs[(i % h) * p.rowLen + i / h] = v;
     }
 
-    const int tl = threadIdx.x % (p.TT / kFT);               // frame lane inside the tile
-    const int jg = threadIdx.x / (p.TT / kFT);               // bin group 0..3
-    const int half = p.TT / kFT;
+    const int quarter = p.TT / kFT;
+    const int tl = threadIdx.x % quarter;                    // frame lane inside the tile
+    const int jg = threadIdx.x / quarter;                    // bin group 0..kJG-1
 
     for (int j0 = 0; j0 < p.bpo; j0 += kBinsPerPass) {
         const int nb = min(kBinsPerPass, p.bpo - j0);
-        float ar[kFT][3], ai[kFT][3];
+        float ar[kFT][kBT], ai[kFT][kBT];
 #pragma unroll
         for (int f = 0; f < kFT; f++)
 #pragma unroll
-            for (int u = 0; u < 3; u++) { ar[f][u] = 0.0f; ai[f][u] = 0.0f; }
+            for (int u = 0; u < kBT; u++) { ar[f][u] = 0.0f; ai[f][u] = 0.0f; }
         // the kernels of this pass are streamed through shared memory in chunks of p.nChunk taps
         for (int n0 = 0; n0 < N; n0 += p.nChunk) {
             const int n1 = min(N, n0 + p.nChunk), cw = n1 - n0;
@@ -98,31 +112,35 @@ __global__ void k_cqt_octave(OctParams p) {
                 sk[(size_t)j * p.nChunk + n] = j < nb ? p.kappa[(size_t)(j0 + j) * N + n0 + n] : make_float2(0.f, 0.f);
             }
             __syncthreads();
-            const float2 *k0 = sk + (size_t)(jg * 3 + 0) * p.nChunk - n0, *k1 = sk + (size_t)(jg * 3 + 1) * p.nChunk - n0,
-                         *k2 = sk + (size_t)(jg * 3 + 2) * p.nChunk - n0;
+            const float2 *kb = sk + (size_t)(jg * kBT) * p.nChunk - n0;
             for (int r = 0; r < h; r++) {
                 const float *row = xs + r * p.rowLen + tl;
                 int a = n0 > r ? (n0 - r + h - 1) / h : 0;
+#pragma unroll 2
                 for (int n = a * h + r; n < n1; a++, n += h) {
-                    const float x0 = row[a], x1 = row[a + half];
-                    const float2 c0 = k0[n], c1 = k1[n], c2 = k2[n];
-                    ar[0][0] = fmaf(x0, c0.x, ar[0][0]); ai[0][0] = fmaf(x0, c0.y, ai[0][0]);
-                    ar[0][1] = fmaf(x0, c1.x, ar[0][1]); ai[0][1] = fmaf(x0, c1.y, ai[0][1]);
-                    ar[0][2] = fmaf(x0, c2.x, ar[0][2]); ai[0][2] = fmaf(x0, c2.y, ai[0][2]);
-                    ar[1][0] = fmaf(x1, c0.x, ar[1][0]); ai[1][0] = fmaf(x1, c0.y, ai[1][0]);
-                    ar[1][1] = fmaf(x1, c1.x, ar[1][1]); ai[1][1] = fmaf(x1, c1.y, ai[1][1]);
-                    ar[1][2] = fmaf(x1, c2.x, ar[1][2]); ai[1][2] = fmaf(x1, c2.y, ai[1][2]);
+                    float x[kFT];
+#pragma unroll
+                    for (int f = 0; f < kFT; f++) x[f] = row[a + f * quarter];
+#pragma unroll
+                    for (int u = 0; u < kBT; u++) {
+                        const float2 c = kb[(size_t)u * p.nChunk + n];
+#pragma unroll
+                        for (int f = 0; f < kFT; f++) {
+                            ar[f][u] = fmaf(x[f], c.x, ar[f][u]);
+                            ai[f][u] = fmaf(x[f], c.y, ai[f][u]);
+                        }
+                    }
                 }
             }
         }
 #pragma unroll
         for (int f = 0; f < kFT; f++) {
-            const int t = t0 + tl + f * half;
+            const int t = t0 + tl + f * quarter;
             if (t >= p.T) continue;
 #pragma unroll
-            for (int u = 0; u < 3; u++) {
-                const int j = j0 + jg * 3 + u;
-                if (j >= p.bpo || jg * 3 + u >= nb) continue;
+            for (int u = 0; u < kBT; u++) {
+                const int j = j0 + jg * kBT + u;
+                if (j >= p.bpo || jg * kBT + u >= nb) continue;
                 const float s = p.scale[j];
                 const long long o = (long long)clip * p.outStride + (long long)t * p.num + p.colOff + j;
                 p.outRe[o] = ar[f][u] * s;
@@ -139,8 +157,19 @@ extern "C" int af_launch_decimate2(const float *in, int inLength, int inStride, 
     const int outLength = inLength / 2;
     if (outLength <= 0 || batch <= 0) return AF_OK;
     if (batch > 65535) return af_fail(AF_ERR_ARG, "decimate2: batch %d > 65535 per launch", batch);
+    // taps are the same for every object (fixed "Fast" resampler): put them in constant memory once per device
+    static int tapsReady[64];
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (dev < 0 || dev >= 64 || !tapsReady[dev]) {
+        cudaError_t e = cudaMemcpyToSymbolAsync(c_decTaps, left32, 32 * sizeof(float), 0, cudaMemcpyDeviceToDevice, (cudaStream_t)stream);
+        if (e == cudaSuccess) e = cudaMemcpyToSymbolAsync(c_decTaps, right31, 31 * sizeof(float), 32 * sizeof(float), cudaMemcpyDeviceToDevice, (cudaStream_t)stream);
+        if (e == cudaSuccess) e = cudaStreamSynchronize((cudaStream_t)stream);   // first use only: visible to every stream afterwards
+        if (e != cudaSuccess) return af_cuda_check(e, "cudaMemcpyToSymbolAsync(c_decTaps)");
+        if (dev >= 0 && dev < 64) tapsReady[dev] = 1;
+    }
     dim3 grid((unsigned)((outLength + kDecTile - 1) / kDecTile), (unsigned)batch);
-    k_decimate2<<<grid, kDecTile, 0, (cudaStream_t)stream>>>(in, inLength, inStride, left32, right31, out, outStride);
+    k_decimate2<<<grid, kDecThreads, 0, (cudaStream_t)stream>>>(in, inLength, inStride, out, outStride);
     AF_LAUNCH_CHECK("k_decimate2");
     return AF_OK;
 }
@@ -160,19 +189,23 @@ extern "C" int af_launch_cqt_octave(const float *sig, int sigLength, int sigStri
     p.rowsA = (fftLength + hop - 1) / hop;
     p.nChunk = fftLength < 512 ? fftLength : 512;
     const size_t kBytes = sizeof(float2) * (size_t)kBinsPerPass * p.nChunk;
-    static const int ttChoices[] = {256, 192, 128, 64, 32, 16, 8};
+    // frames per CTA: the largest tile that still lets two CTAs share an SM (<= 100 KB); if that would drop below
+    // 256 frames (large hops: the polyphase signal tile is hop x TT floats) take the largest tile that fits at all
+    static const int ttChoices[] = {512, 256, 128, 64, 32, 16, 8};
     int TT = 0;
     size_t smem = 0;
-    for (int c = 0; c < 7; c++) {
-        TT = ttChoices[c];
-        int rowLen = TT + p.rowsA + 1;
-        // pitch chosen so consecutive samples (r fastest) land in different banks while staging
-        if (hop >= 32) rowLen |= 1; else { int want = 32 / hop; rowLen = ((rowLen + 31) / 32) * 32 + want; }
-        p.rowLen = rowLen;
-        smem = kBytes + sizeof(float) * (size_t)hop * rowLen;
-        if (smem <= (TT > 64 ? 100 : 200) * 1024) break;
+    for (int pass = 0; pass < 2 && TT == 0; pass++) {
+        for (int c = 0; c < 7; c++) {
+            const int tt = ttChoices[c];
+            if (pass == 0 && tt < 256) break;
+            int rowLen = tt + p.rowsA + 1;
+            // pitch chosen so consecutive samples (r fastest) land in different banks while staging
+            if (hop >= 32) rowLen |= 1; else { int want = 32 / hop; rowLen = ((rowLen + 31) / 32) * 32 + want; }
+            const size_t bytes = kBytes + sizeof(float) * (size_t)hop * rowLen;
+            if (bytes <= (size_t)(pass == 0 ? 100 : 200) * 1024) { TT = tt; p.rowLen = rowLen; smem = bytes; break; }
+        }
     }
-    if (smem > 220 * 1024) return af_fail(AF_ERR_UNSUPPORTED, "cqt octave: fftLength %d with hop %d exceeds shared memory", fftLength, hop);
+    if (TT == 0) return af_fail(AF_ERR_UNSUPPORTED, "cqt octave: fftLength %d with hop %d exceeds shared memory", fftLength, hop);
     p.TT = TT;
     cudaError_t e = cudaFuncSetAttribute(k_cqt_octave, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return af_cuda_check(e, "cudaFuncSetAttribute(k_cqt_octave)");
