@@ -14,6 +14,7 @@
 // For N <= 4096 the columns kernel alone is the whole transform (N2 = 1).
 // Shared-memory legs use the same Stockham radix-4/2 autosort passes as stft_generic.cu.
 #include <math.h>
+#include <stdlib.h>
 #include "common.cuh"
 
 namespace {
@@ -254,7 +255,7 @@ void fill_params(const AfCwtArgs *a, CwtParams *p) {
     p->dataLength = a->dataLength; p->padLength = a->padLength; p->num = a->num; p->batch = a->batch;
     p->scaleArr = a->scaleArr;
     p->wType = a->wavelet.waveletType; p->g = a->wavelet.gamma; p->b = a->wavelet.beta; p->factor = (float)a->wavelet.factor;
-    const size_t budget = 160 * 1024;
+    const size_t budget = (size_t)(getenv("AFB200_CWT_LEG_KB") ? atoi(getenv("AFB200_CWT_LEG_KB")) : 72) * 1024;   // per-CTA leg buffers: small enough for 2-3 CTAs per SM so load / FFT / store phases of different CTAs overlap
     p->cols = p->N2 == 1 ? 1 : 8;
     while (p->cols > 1 && sizeof(float2) * 2 * (size_t)p->cols * (p->N1 + 1) > budget) p->cols >>= 1;
     p->rows = 16;
