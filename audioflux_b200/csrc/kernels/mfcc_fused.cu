@@ -88,6 +88,7 @@ struct Params {
     int melGroups, melWFloats;
     int melGroupLen[4];
     int ccNum, rectify, dataType;
+    int skewNs;                     // one-time start delay of the upper half of the frame warps (phase decorrelation)
 };
 
 // shared-memory carve-up (bytes), all 16-byte aligned
@@ -255,6 +256,10 @@ __global__ void __launch_bounds__(kThreads, kCtasPerSm) k_mfcc_fused(Params p) {
     const c64 wBase = c_from(sTw2[lane]);                    // W_2048^lane
     const c64 *sWinC = reinterpret_cast<const c64 *>(sWin2);
     const c64 *sTw1C = reinterpret_cast<const c64 *>(sTw1);
+
+    // The frame warps would otherwise march through the phases in lockstep (all in the LSU-bound load/transpose/bank
+    // phases, then all in the FMA-bound FFTs).  Delaying half of them once puts the two halves in different phases.
+    if (p.skewNs > 0 && warp >= kFrameWarps / 2) __nanosleep(p.skewNs);
 
     int it = 0;
     for (long long tile = blockIdx.x; tile < p.totalTiles; tile += gridDim.x, ++it) {
@@ -525,6 +530,7 @@ extern "C" int af_launch_mfcc_fused(void *plan, const float *data, int dataLengt
     p.melGroups = pl->melGroups; p.melWFloats = pl->melWFloats;
     for (int g = 0; g < 4; g++) p.melGroupLen[g] = pl->melGroupLen[g];
     p.ccNum = pl->ccNum; p.rectify = rectifyType; p.dataType = pl->dataType;
+    p.skewNs = getenv("AFB200_MFCC_SKEW_NS") ? atoi(getenv("AFB200_MFCC_SKEW_NS")) : 0;
 
     // frames per tile: as many as fit the shared-memory budget (<= kFrameWarps)
     const int budget = kCtasPerSm == 1 ? 227 * 1024 : (233472 - kCtasPerSm * 1024) / kCtasPerSm;
