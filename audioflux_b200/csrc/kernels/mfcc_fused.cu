@@ -42,6 +42,9 @@ constexpr int kNC = 1024;           // packed complex points
 #define AF_FRAME_WARPS 13
 #endif
 constexpr int kFrameWarps = AF_FRAME_WARPS;     // consumer warps = max frames per tile (<= 16: one mma M tile); 13 measured best (tools/sweep_frame_warps.sh)
+#ifndef AF_ABLATE
+#define AF_ABLATE 0     // diagnostic timing builds: 1 no bank loop, 2 no post-pass, 4 no FFTs, 8 no transposes, 16 no window/sample loads
+#endif
 #ifndef AF_EPI_WARPS
 #define AF_EPI_WARPS 2
 #endif
@@ -88,7 +91,6 @@ struct Params {
     int melGroups, melWFloats;
     int melGroupLen[4];
     int ccNum, rectify, dataType;
-    int skewNs;                     // one-time start delay of the upper half of the frame warps (phase decorrelation)
 };
 
 // shared-memory carve-up (bytes), all 16-byte aligned
@@ -257,10 +259,6 @@ __global__ void __launch_bounds__(kThreads, kCtasPerSm) k_mfcc_fused(Params p) {
     const c64 *sWinC = reinterpret_cast<const c64 *>(sWin2);
     const c64 *sTw1C = reinterpret_cast<const c64 *>(sTw1);
 
-    // The frame warps would otherwise march through the phases in lockstep (all in the LSU-bound load/transpose/bank
-    // phases, then all in the FMA-bound FFTs).  Delaying half of them once puts the two halves in different phases.
-    if (p.skewNs > 0 && warp >= kFrameWarps / 2) __nanosleep(p.skewNs);
-
     int it = 0;
     for (long long tile = blockIdx.x; tile < p.totalTiles; tile += gridDim.x, ++it) {
         const int stage = it % kStages;
@@ -276,7 +274,7 @@ __global__ void __launch_bounds__(kThreads, kCtasPerSm) k_mfcc_fused(Params p) {
             // ---- A: load 2048 samples (1024 packed pairs), apply 0.5*window ----
             const c64 *sp = reinterpret_cast<const c64 *>(span + (size_t)stage * p.spanFloats + warp * p.hop);
 #pragma unroll
-            for (int j = 0; j < 32; j++) z[j] = v_mul(sp[lane + 32 * j], sWinC[lane + 32 * j]);
+            for (int j = 0; j < 32; j++) z[j] = (AF_ABLATE & 16) ? c_pack(1.0f + j, lane) : v_mul(sp[lane + 32 * j], sWinC[lane + 32 * j]);
         }
         __syncwarp();
         if (lane == 0) af_mbar_arrive(&emptyBar[stage]);     // span slot may be refilled
@@ -291,7 +289,7 @@ __global__ void __launch_bounds__(kThreads, kCtasPerSm) k_mfcc_fused(Params p) {
         }
 
         // ---- B: 1024-point FFT as 32 x 32 ----
-        af_fft32(z);                                          // over n2; Y[n1=lane][ka] at AF_BR5(ka)
+        if (!(AF_ABLATE & 4)) af_fft32(z);                    // over n2; Y[n1=lane][ka] at AF_BR5(ka)
         {
             float yr[32], yi[32];
 #pragma unroll
@@ -302,6 +300,7 @@ __global__ void __launch_bounds__(kThreads, kCtasPerSm) k_mfcc_fused(Params p) {
                 c_unpack(y, yr[ka], yi[ka]);
             }
             // 32 x 32 transpose, real plane then imaginary plane, through one 33-padded float buffer
+            if (!(AF_ABLATE & 8)) {
 #pragma unroll
             for (int ka = 0; ka < 32; ka++) scratch[ka * 33 + lane] = yr[ka];
             __syncwarp();
@@ -314,14 +313,18 @@ __global__ void __launch_bounds__(kThreads, kCtasPerSm) k_mfcc_fused(Params p) {
 #pragma unroll
             for (int n1 = 0; n1 < 32; n1++) z[n1] = c_pack(yr[n1], scratch[lane * 33 + n1]);
             __syncwarp();
+            } else {
+#pragma unroll
+                for (int n1 = 0; n1 < 32; n1++) z[n1] = c_pack(yr[n1], yi[n1]);
+            }
         }
-        af_fft32(z);                                          // over n1; Z[lane + 32*kb] at AF_BR5(kb)
+        if (!(AF_ABLATE & 4)) af_fft32(z);                    // over n1; Z[lane + 32*kb] at AF_BR5(kb)
 
         // ---- C: real-FFT post-pass + power / magnitude -> Ps[0..1024] ----
         // (window pre-scaled by 1/2, so E' = Z[k] + conj Z[N-k] and O' = -i (Z[k] - conj Z[N-k]) need no halving;
         //  X[k] = E' + W O', conj X[N-k] = E' - W O' with W = W_2048^k = W_2048^lane * W_64^kb)
 #pragma unroll
-        for (int kb = 0; kb < 16; kb++) {
+        for (int kb = 0; kb < ((AF_ABLATE & 2) ? 1 : 16); kb++) {
             const c64 zk = z[AF_BR5(kb)];
             float pr, pi;
             c_unpack(z[AF_BR5(31 - kb)], pr, pi);
@@ -359,7 +362,7 @@ __global__ void __launch_bounds__(kThreads, kCtasPerSm) k_mfcc_fused(Params p) {
             // spread over distinct 8-byte bank pairs per half-warp by the host planner)
             const float4 *wg4 = reinterpret_cast<const float4 *>(sMelW) + lane;
             for (int g = 0; g < p.melGroups; g++) {
-                const int len4 = p.melGroupLen[g] >> 2;
+                const int len4 = (AF_ABLATE & 1) ? 0 : p.melGroupLen[g] >> 2;
                 const float2 *ps2 = reinterpret_cast<const float2 *>(scratch + sMelStart[g * 32 + lane]);
                 float acc0 = 0.0f, acc1 = 0.0f, acc2 = 0.0f, acc3 = 0.0f;
                 // software pipelined: the loads of stage i+1 are in flight while stage i is accumulated
@@ -530,7 +533,6 @@ extern "C" int af_launch_mfcc_fused(void *plan, const float *data, int dataLengt
     p.melGroups = pl->melGroups; p.melWFloats = pl->melWFloats;
     for (int g = 0; g < 4; g++) p.melGroupLen[g] = pl->melGroupLen[g];
     p.ccNum = pl->ccNum; p.rectify = rectifyType; p.dataType = pl->dataType;
-    p.skewNs = getenv("AFB200_MFCC_SKEW_NS") ? atoi(getenv("AFB200_MFCC_SKEW_NS")) : 0;
 
     // frames per tile: as many as fit the shared-memory budget (<= kFrameWarps)
     const int budget = kCtasPerSm == 1 ? 227 * 1024 : (233472 - kCtasPerSm * 1024) / kCtasPerSm;

@@ -1,0 +1,23 @@
+#!/bin/bash
+# diagnostic: time the fused kernel with parts removed (results are wrong on purpose; the parity gate is skipped)
+mkdir -p gpurun_out
+for a in "$@"; do
+  touch audioflux_b200/csrc/kernels/mfcc_fused.cu
+  make -s -C audioflux_b200/csrc EXTRA_NVFLAGS="-DAF_ABLATE=$a" > /dev/null 2>&1
+  python - <<PY
+import torch, sys
+sys.path.insert(0,'.')
+import audioflux_b200 as af
+S,D=af.SpectralFilterBankScaleType, af.SpectralDataType
+b=af.BFT(128,11,48000,slide_length=512,scale_type=S.MEL,data_type=D.POWER)
+x=0.1*torch.randn((1024,240000),device='cuda')
+for _ in range(3): b.mfcc_batch(x,40)
+torch.cuda.synchronize()
+e0,e1=torch.cuda.Event(enable_timing=True),torch.cuda.Event(enable_timing=True)
+e0.record()
+for _ in range(8): b.mfcc_batch(x,40)
+e1.record(); torch.cuda.synchronize()
+print('ablate=$a', round(e0.elapsed_time(e1)/8,3),'ms')
+PY
+done
+touch audioflux_b200/csrc/kernels/mfcc_fused.cu; make -s -C audioflux_b200/csrc > /dev/null 2>&1
