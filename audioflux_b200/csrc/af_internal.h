@@ -54,9 +54,10 @@ typedef struct {
 /* range defaults + Linear/Octave revisions shared by bftObj_new and cwtObj_new; returns 0 or -1 */
 int af_revise_range(int num, int fftLength, int samplate, const float *lowFre, const float *highFre,
                     int scaleType, int binPerOctave, AfRange *out);
-/* num+2 band edges (Hz) and their bins; slaneyBins: 1 = first grid point above the edge */
+/* num+2 band edges (Hz) and their bins (isEdge=1: the num centres themselves, gammatone);
+ * slaneyBins: 1 = first grid point above the edge */
 void af_band_edges(int num, int fftLength, int samplate, float lowFre, float highFre, int scaleType,
-                   int binPerOctave, int slaneyBins, int forCwt, float *freEdge, int *binEdge);
+                   int binPerOctave, int slaneyBins, int isEdge, float *freEdge, int *binEdge);
 int af_auditory_filterbank(int num, int fftLength, int samplate, int scaleType, int styleType,
                            int normType, float lowFre, float highFre, int binPerOctave,
                            float *bank, float *freBandArr, int *binBandArr);

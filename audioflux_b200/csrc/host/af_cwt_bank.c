@@ -94,7 +94,7 @@ void af_cwt_scales(int num, int dataLength, int samplate, float lowFre, float hi
                    int bpo, float cf, float *freBandArr, int *binBandArr, float *scaleArr) {
     float *fre = (float *)calloc((size_t)num + 2, sizeof(float));
     int *bin = (int *)calloc((size_t)num + 2, sizeof(int));
-    af_band_edges(num, dataLength, samplate, lowFre, highFre, scale, bpo, 0, 1, fre, bin);
+    af_band_edges(num, dataLength, samplate, lowFre, highFre, scale, bpo, 0, 0, fre, bin);
     if (freBandArr) memcpy(freBandArr, fre + 1, sizeof(float) * (size_t)num);
     if (binBandArr) memcpy(binBandArr, bin + 1, sizeof(int) * (size_t)num);
     for (int i = num, j = 0; i >= 1; i--, j++) {

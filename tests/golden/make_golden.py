@@ -52,6 +52,19 @@ def main():
     xx2 = af.XXCC(64, _lib=ref)
     np.savez_compressed(os.path.join(HERE, "bark_etsi_mag.npz"), x=xt, mel=m2, cc=xx2.xxcc_planes(m2, 20),
                         cc_cubic=xx2.xxcc_planes(m2, 13, af.CepstralRectifyType.CUBIC_ROOT))
+    # ---- gammatone (dense bank) on the ERB scale, as af.gtcc uses it: bank + real-mode BFT + cepstrum ----
+    xg = tones(5, 16000, 32000)
+    b3 = af.BFT(64, 10, 32000, slide_length=256, scale_type=S.ERB, style_type=ST.GAMMATONE, normal_type=N.NONE,
+                data_type=D.POWER, _lib=ref)
+    import ctypes as C
+    gbank = np.zeros((64, 513), np.float32)
+    gf = np.zeros(66, np.float32)
+    gb = np.zeros(66, np.int32)
+    ref.auditory_filterBank(64, 1024, 32000, 0, 4, 2, 0, C.c_float(0.0), C.c_float(16000.0), 12, gbank.ctypes.data, gf.ctypes.data, gb.ctypes.data)
+    m3, _ = b3.bft_planes(xg, 1)
+    xx3 = af.XXCC(64, _lib=ref)
+    np.savez_compressed(os.path.join(HERE, "erb_gammatone.npz"), x=xg, bank=gbank, mel=m3, cc=xx3.xxcc_planes(m3, 13),
+                        fre_band=b3.get_fre_band_arr(), bin_band=b3.get_bin_band_arr())
     # ---- STFT (full mirrored planes), hann 512 / hop 128, first 8 frames ----
     s = af.STFT(9, af.WindowType.HANN, 128, _lib=ref)
     xs = noise(2, 4000)

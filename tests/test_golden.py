@@ -60,3 +60,13 @@ def test_cwt(golden):
     g = golden("cwt_morlet.npz")
     re, im = O.cwt(g["x"], 36, 11, 48000, O.WAVE_MORLET, O.SCALE_OCTAVE, low=32.703196, is_pad=False)
     assert rel_max(re, g["re"]) < TOL and rel_max(im, g["im"]) < TOL
+
+
+def test_gammatone_with_reference_bank(golden):
+    """The float32-faithful gammatone builder lives in the product library (the reference's values in the lowest
+    bands are float32 rounding artefacts); the oracle takes the bank from the fixture."""
+    g = golden("erb_gammatone.npz")
+    m = O.bft(g["x"], 64, 10, 32000, 256, O.W_HANN, O.SCALE_ERB, O.STYLE_GAMMATONE, O.NORM_NONE, O.DATA_POWER,
+              result_type=1, bank=g["bank"])
+    assert rel_max(m, g["mel"]) < TOL
+    assert rel_max(O.xxcc(g["mel"], 13), g["cc"]) < TOL

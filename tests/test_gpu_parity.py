@@ -138,6 +138,21 @@ def test_bark_etsi_golden(cuda_device, golden):
     assert rel_max(xx.xxcc_planes(g["mel"], 13, af.CepstralRectifyType.CUBIC_ROOT), g["cc_cubic"]) < TOL
 
 
+def test_gammatone_dense_bank_golden(torch_cuda, golden):
+    """Dense (gammatone) bank: tiled FP32 contraction path, real and complex modes, and the composed MFCC."""
+    torch = torch_cuda
+    g = golden("erb_gammatone.npz")
+    b = af.BFT(64, 10, 32000, slide_length=256, scale_type=S.ERB, style_type=ST.GAMMATONE, data_type=D.POWER)
+    m, _ = b.bft_planes(g["x"], 1)
+    assert rel_max(m, g["mel"]) < TOL
+    cc = b.mfcc_batch(torch.from_numpy(g["x"][None]).cuda(), 13)
+    torch.cuda.synchronize()
+    assert rel_max(cc[0].cpu().numpy(), g["cc"]) < TOL
+    re, im = b.bft_planes(g["x"], 0)
+    ore, oim = O.bft(g["x"], 64, 10, 32000, 256, O.W_HANN, O.SCALE_ERB, O.STYLE_GAMMATONE, 0, 0, result_type=0, bank=g["bank"])
+    assert rel_max(re, ore) < TOL and rel_max(im, oim) < TOL
+
+
 # ------------------------------------------------------------------ xxcc
 def test_xxcc_vs_oracle(cuda_device):
     m = np.abs(noise(3, 50 * 128).reshape(50, 128)) + 1e-9

@@ -124,3 +124,33 @@ def test_tables_against_reference_build(product_lib, ref_lib):
         r = af.BFT(96, 11, 44100, scale_type=S(scale), style_type=ST(style), normal_type=N(norm), _lib=ref_lib)
         assert np.array_equal(b.get_bin_band_arr(), r.get_bin_band_arr())
         np.testing.assert_allclose(b.get_fre_band_arr(), r.get_fre_band_arr(), rtol=1e-6)
+
+
+def test_gammatone_bank_matches_golden_and_reference(product_lib, golden):
+    g = golden("erb_gammatone.npz")
+    b = af.BFT(64, 10, 32000, slide_length=256, scale_type=S.ERB, style_type=ST.GAMMATONE, data_type=D.POWER)
+    got = b.get_filter_bank_arr()
+    rowmax = np.abs(g["bank"]).max(axis=1, keepdims=True)
+    assert (np.abs(got - g["bank"]) / rowmax).max() < 2e-5
+    assert np.array_equal(b.get_bin_band_arr(), g["bin_band"])
+    np.testing.assert_allclose(b.get_fre_band_arr(), g["fre_band"], rtol=1e-6)
+
+
+@pytest.mark.parametrize("scale,lo,hi", [(4, 0.0, None), (2, 0.0, None), (3, 0.0, None), (1, 500.0, 7000.0), (6, 32.703196, 7000.0)])
+def test_gammatone_banks_against_reference_build(product_lib, ref_lib, scale, lo, hi):
+    for norm in (0, 1, 2):
+        for num, r, sr in ((128, 11, 48000), (40, 10, 16000)):
+            h = sr / 2 if hi is None else hi
+            b = af.BFT(num, r, sr, low_fre=lo, high_fre=h, scale_type=S(scale), style_type=ST.GAMMATONE, normal_type=N(norm))
+            q = af.BFT(num, r, sr, low_fre=lo, high_fre=h, scale_type=S(scale), style_type=ST.GAMMATONE, normal_type=N(norm), _lib=ref_lib)
+            n = 1 << r
+            l2, h2, _, _ = O.bft_revise_range(num, n, sr, lo, h, scale, 12)
+            ref_bank = np.zeros((num + 4, n // 2 + 1), np.float32)
+            fb = np.zeros(num + 2, np.float32)
+            bb = np.zeros(num + 2, np.int32)
+            ref_lib.auditory_filterBank(num, n, sr, 0, scale, 2, norm, float(l2), float(h2), 12, ref_bank.ctypes.data,
+                                        fb.ctypes.data, bb.ctypes.data)
+            rowmax = np.abs(ref_bank[:num]).max(axis=1, keepdims=True)
+            assert (np.abs(b.get_filter_bank_arr() - ref_bank[:num]) / rowmax).max() < 5e-5
+            assert np.array_equal(b.get_bin_band_arr(), q.get_bin_band_arr())
+            np.testing.assert_allclose(b.get_fre_band_arr(), q.get_fre_band_arr(), rtol=1e-6)
