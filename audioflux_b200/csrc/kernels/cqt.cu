@@ -67,6 +67,8 @@ struct OctParams {
     int rowLen;                   // polyphase row pitch (floats)
     int rowsA;                    // ceil(N / hop)
     int nChunk;                   // kernel taps resident in shared memory at a time
+    int segs;                     // tap segments worked on by different threads (large hops: few frames fit in shared
+                                  // memory, so the taps of one frame are split to get enough threads), summed at the end
 };
 
 constexpr int kBinsPerPass = 12;  // bins whose kernels sit in shared memory together
@@ -94,7 +96,9 @@ __global__ void k_cqt_octave(OctParams p) {
 
     const int quarter = p.TT / kFT;
     const int tl = threadIdx.x % quarter;                    // frame lane inside the tile
-    const int jg = threadIdx.x / quarter;                    // bin group 0..kJG-1
+    const int jg = (threadIdx.x / quarter) % kJG;            // bin group 0..kJG-1
+    const int seg = threadIdx.x / (quarter * kJG);           // tap segment 0..segs-1: taps a in [aLo, aHi) of every phase r
+    const int aLo = (int)((long long)p.rowsA * seg / p.segs), aHi = (int)((long long)p.rowsA * (seg + 1) / p.segs);
 
     for (int j0 = 0; j0 < p.bpo; j0 += kBinsPerPass) {
         const int nb = min(kBinsPerPass, p.bpo - j0);
@@ -116,8 +120,10 @@ __global__ void k_cqt_octave(OctParams p) {
             for (int r = 0; r < h; r++) {
                 const float *row = xs + r * p.rowLen + tl;
                 int a = n0 > r ? (n0 - r + h - 1) / h : 0;
+                if (a < aLo) a = aLo;
+                const int nEnd = min(n1, aHi * h + r);
 #pragma unroll 2
-                for (int n = a * h + r; n < n1; a++, n += h) {
+                for (int n = a * h + r; n < nEnd; a++, n += h) {
                     float x[kFT];
 #pragma unroll
                     for (int f = 0; f < kFT; f++) x[f] = row[a + f * quarter];
@@ -133,10 +139,32 @@ __global__ void k_cqt_octave(OctParams p) {
                 }
             }
         }
+        if (p.segs > 1) {
+            // sum the tap segments: partial accumulators go through shared memory (the signal tile is dead by now)
+            __syncthreads();
+            float *red = xs;
+            const int slot = (jg * quarter + tl) * (2 * kFT * kBT);
+            for (int sgm = 1; sgm < p.segs; sgm++) {
+                if (seg == sgm) {
+#pragma unroll
+                    for (int f = 0; f < kFT; f++)
+#pragma unroll
+                        for (int u = 0; u < kBT; u++) { red[slot + (f * kBT + u) * 2] = ar[f][u]; red[slot + (f * kBT + u) * 2 + 1] = ai[f][u]; }
+                }
+                __syncthreads();
+                if (seg == 0) {
+#pragma unroll
+                    for (int f = 0; f < kFT; f++)
+#pragma unroll
+                        for (int u = 0; u < kBT; u++) { ar[f][u] += red[slot + (f * kBT + u) * 2]; ai[f][u] += red[slot + (f * kBT + u) * 2 + 1]; }
+                }
+                __syncthreads();
+            }
+        }
 #pragma unroll
         for (int f = 0; f < kFT; f++) {
             const int t = t0 + tl + f * quarter;
-            if (t >= p.T) continue;
+            if (t >= p.T || seg != 0) continue;
 #pragma unroll
             for (int u = 0; u < kBT; u++) {
                 const int j = j0 + jg * kBT + u;
@@ -207,10 +235,14 @@ extern "C" int af_launch_cqt_octave(const float *sig, int sigLength, int sigStri
     }
     if (TT == 0) return af_fail(AF_ERR_UNSUPPORTED, "cqt octave: fftLength %d with hop %d exceeds shared memory", fftLength, hop);
     p.TT = TT;
+    // enough threads per CTA: split the taps of a frame over up to rowsA segments until the CTA has >= 512 threads
+    p.segs = 1;
+    while (p.segs * 2 <= p.rowsA && (TT / kFT) * kJG * p.segs * 2 <= 512) p.segs *= 2;
+    if ((size_t)(TT / kFT) * kJG * 2 * kFT * kBT * sizeof(float) > sizeof(float) * (size_t)hop * p.rowLen) p.segs = 1;   // reduction scratch must fit the signal tile
     cudaError_t e = cudaFuncSetAttribute(k_cqt_octave, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return af_cuda_check(e, "cudaFuncSetAttribute(k_cqt_octave)");
     dim3 grid((unsigned)((timeLength + TT - 1) / TT), (unsigned)batch);
-    k_cqt_octave<<<grid, (TT / kFT) * kJG, smem, (cudaStream_t)stream>>>(p);
+    k_cqt_octave<<<grid, (TT / kFT) * kJG * p.segs, smem, (cudaStream_t)stream>>>(p);
     AF_LAUNCH_CHECK("k_cqt_octave");
     return AF_OK;
 }
