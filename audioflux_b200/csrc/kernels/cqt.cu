@@ -140,9 +140,10 @@ __global__ void k_cqt_octave(OctParams p) {
             }
         }
         if (p.segs > 1) {
-            // sum the tap segments: partial accumulators go through shared memory (the signal tile is dead by now)
+            // sum the tap segments: partial accumulators go through the kernel buffer (dead until the next pass reloads it;
+            // the signal tile must survive for that pass)
             __syncthreads();
-            float *red = xs;
+            float *red = reinterpret_cast<float *>(sk);
             const int slot = (jg * quarter + tl) * (2 * kFT * kBT);
             for (int sgm = 1; sgm < p.segs; sgm++) {
                 if (seg == sgm) {
@@ -238,7 +239,7 @@ extern "C" int af_launch_cqt_octave(const float *sig, int sigLength, int sigStri
     // enough threads per CTA: split the taps of a frame over up to rowsA segments until the CTA has >= 512 threads
     p.segs = 1;
     while (p.segs * 2 <= p.rowsA && (TT / kFT) * kJG * p.segs * 2 <= 512) p.segs *= 2;
-    if ((size_t)(TT / kFT) * kJG * 2 * kFT * kBT * sizeof(float) > sizeof(float) * (size_t)hop * p.rowLen) p.segs = 1;   // reduction scratch must fit the signal tile
+    if ((size_t)(TT / kFT) * kJG * 2 * kFT * kBT * sizeof(float) > kBytes) p.segs = 1;   // reduction scratch must fit the kernel buffer
     cudaError_t e = cudaFuncSetAttribute(k_cqt_octave, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return af_cuda_check(e, "cudaFuncSetAttribute(k_cqt_octave)");
     dim3 grid((unsigned)((timeLength + TT - 1) / TT), (unsigned)batch);
