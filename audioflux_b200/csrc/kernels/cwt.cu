@@ -16,6 +16,7 @@
 #include <math.h>
 #include <stdlib.h>
 #include "common.cuh"
+#include "fft32_gen.cuh"
 
 namespace {
 
@@ -235,6 +236,178 @@ __global__ void k_cwt_rows(CwtParams p) {
     }
 }
 
+// ============================================================================================
+// Fast path for N = 2^19 (BASELINE config 4): N1 = 1024 columns leg, N2 = 512 rows leg, every
+// transform done by ONE WARP in registers (generated packed-fp32 32/16-point DFTs, warp-private
+// shared-memory transposes, __syncwarp only) -- the CTA synchronises three times instead of once per
+// radix pass, and 2-3 CTAs share an SM so the load / transform / store phases of different CTAs overlap.
+// Both directions run the forward transform; the inverse is conj . DFT . conj with the conjugations
+// folded into the load (MODE 1 loads conj(wavelet * X)) and the final store.
+// ============================================================================================
+constexpr int kWCols = 8;             // columns (= warps) per CTA in the columns kernel
+constexpr int kWColPitch = 1056;      // c64 per column slot: 1024 points + room for the 33 x 32 float transpose plane
+constexpr int kWRows = 16;            // rows per CTA in the rows kernel (2 per warp)
+constexpr int kWRowPitch = 520;       // c64 per row slot
+
+// 32 x 32 complex transpose of a warp's register tile through a 33-padded float plane (real, then imaginary)
+__device__ __forceinline__ void warp_transpose32(c64 (&z)[32], float *plane, int lane, const c64 *srcBr /* values at AF_BR5 */) {
+    (void)srcBr;
+    float yr[32], yi[32];
+#pragma unroll
+    for (int ka = 0; ka < 32; ka++) c_unpack(z[ka], yr[ka], yi[ka]);
+#pragma unroll
+    for (int ka = 0; ka < 32; ka++) plane[ka * 33 + lane] = yr[ka];
+    __syncwarp();
+#pragma unroll
+    for (int n1 = 0; n1 < 32; n1++) yr[n1] = plane[lane * 33 + n1];
+    __syncwarp();
+#pragma unroll
+    for (int ka = 0; ka < 32; ka++) plane[ka * 33 + lane] = yi[ka];
+    __syncwarp();
+#pragma unroll
+    for (int n1 = 0; n1 < 32; n1++) z[n1] = c_pack(yr[n1], plane[lane * 33 + n1]);
+    __syncwarp();
+}
+
+template <int MODE>
+__global__ void __launch_bounds__(kWCols * 32) k_cwt_cols_w(CwtParams p) {
+    extern __shared__ __align__(16) unsigned char smemRaw[];
+    c64 *tile = reinterpret_cast<c64 *>(smemRaw);                              // [kWCols][kWColPitch]
+    float2 *tw1 = reinterpret_cast<float2 *>(tile + (size_t)kWCols * kWColPitch);   // [32 ka][32 n1] W_1024^(n1 ka)
+    float2 *tf = tw1 + 1024;                                                   // [N2] W_N^j (fine inter-leg twiddle)
+    const int N2 = p.N2;
+    const int item = blockIdx.x;
+    const int clip = MODE == 0 ? item : item / p.num;
+    const int col0 = blockIdx.y * kWCols;
+    const float s = MODE == 1 ? p.scaleArr[item % p.num] : 0.0f;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+    for (int j = threadIdx.x; j < 1024; j += blockDim.x) tw1[j] = cw((j >> 5) * (j & 31), 1024, -1.0f);
+    for (int j = threadIdx.x; j < N2; j += blockDim.x) tf[j] = cw(j, p.N, -1.0f);
+    for (int e = threadIdx.x; e < 1024 * kWCols; e += blockDim.x) {
+        const int i = e / kWCols, c = e - i * kWCols;
+        const int k = i * N2 + col0 + c;
+        c64 v;
+        if (MODE == 0) {
+            v = c_pack(load_padded(p, p.data + (size_t)clip * p.dataLength, k), 0.0f);
+        } else {
+            float wv = 0.0f;
+            if (k <= p.N / 2) wv = wavelet_eval(p.wType, p.g, p.b, p.factor, s * (float)((double)k * 2.0 * M_PI / (double)p.N));
+            const float2 x = p.spec[(size_t)clip * p.N + k];
+            v = c_pack(wv * x.x, -(wv * x.y));                                 // conj: inverse transform via forward DFT
+        }
+        tile[(size_t)c * kWColPitch + i] = v;
+    }
+    __syncthreads();
+
+    {   // warp `warp` transforms column `warp`: 1024 points as 32 x 32, element n = lane + 32 j
+        c64 *colp = tile + (size_t)warp * kWColPitch;
+        c64 z[32], y[32];
+#pragma unroll
+        for (int j = 0; j < 32; j++) z[j] = colp[lane + 32 * j];
+        __syncwarp();
+        af_fft32(z);
+#pragma unroll
+        for (int ka = 0; ka < 32; ka++) y[ka] = ka ? c_mul(z[AF_BR5(ka)], c_from(tw1[ka * 32 + lane])) : z[AF_BR5(0)];
+        warp_transpose32(y, reinterpret_cast<float *>(colp), lane, nullptr);
+        af_fft32(y);                                                           // X[k1 = lane + 32 kb] at AF_BR5(kb)
+        const int col = col0 + warp;
+#pragma unroll
+        for (int kb = 0; kb < 32; kb++) {
+            const int k1 = lane + 32 * kb;
+            c64 v = y[AF_BR5(kb)];
+            if (N2 > 1) {
+                const int prod = col * k1;                                     // W_N^prod = W_1024^(prod / N2) * W_N^(prod % N2)
+                const int hi = prod >> p.log2N2;
+                v = c_mul(v, c_mul(c_from(cw(hi, 1024, -1.0f)), c_from(tf[prod & (N2 - 1)])));
+            }
+            colp[k1] = v;
+        }
+    }
+    __syncthreads();
+    float2 *wk = p.work + (size_t)item * p.N;
+    for (int e = threadIdx.x; e < 1024 * kWCols; e += blockDim.x) {
+        const int k1 = e / kWCols, c = e - k1 * kWCols;
+        float re, im;
+        c_unpack(tile[(size_t)c * kWColPitch + k1], re, im);
+        wk[(size_t)k1 * N2 + col0 + c] = make_float2(re, im);
+    }
+}
+
+template <int MODE>
+__global__ void __launch_bounds__(kWRows * 16) k_cwt_rows_w(CwtParams p) {
+    extern __shared__ __align__(16) unsigned char smemRaw[];
+    c64 *tile = reinterpret_cast<c64 *>(smemRaw);                              // [kWRows][kWRowPitch]
+    float2 *tw = reinterpret_cast<float2 *>(tile + (size_t)kWRows * kWRowPitch);   // [32 ka][16 q] W_512^(q ka)
+    const int N1 = p.N1;
+    const int item = blockIdx.x;
+    const int clip = MODE == 0 ? item : item / p.num;
+    const int row0 = blockIdx.y * kWRows;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int h = lane >> 4, q = lane & 15;
+    for (int j = threadIdx.x; j < 512; j += blockDim.x) tw[j] = cw((j >> 4) * (j & 15), 512, -1.0f);
+    __syncthreads();
+
+    {   // each half-warp transforms one row of 512 points as 16 x 32: element n = q + 16 j
+        const int r = 2 * warp + h;
+        const float2 *src = p.work + (size_t)item * p.N + (size_t)(row0 + r) * 512;
+        c64 z[32];
+#pragma unroll
+        for (int j = 0; j < 32; j++) z[j] = c_from(src[q + 16 * j]);
+        af_fft32(z);                                                           // over j -> Y[q][ka] at AF_BR5(ka)
+        float *plane = reinterpret_cast<float *>(tile + (size_t)r * kWRowPitch);   // 1040 floats >= 32 x 17
+        float yr[32], yi[32];
+#pragma unroll
+        for (int ka = 0; ka < 32; ka++) {
+            c64 y = z[AF_BR5(ka)];
+            if (ka && q) y = c_mul(y, c_from(tw[ka * 16 + q]));
+            c_unpack(y, yr[ka], yi[ka]);
+        }
+        // transpose inside the half-warp: lane q2 receives columns ka = q2 and q2 + 16 (16 values of n1 each)
+        c64 u0[16], u1[16];
+        float ar[16], br[16];
+#pragma unroll
+        for (int ka = 0; ka < 32; ka++) plane[ka * 17 + q] = yr[ka];
+        __syncwarp();
+#pragma unroll
+        for (int n1 = 0; n1 < 16; n1++) { ar[n1] = plane[q * 17 + n1]; br[n1] = plane[(q + 16) * 17 + n1]; }
+        __syncwarp();
+#pragma unroll
+        for (int ka = 0; ka < 32; ka++) plane[ka * 17 + q] = yi[ka];
+        __syncwarp();
+#pragma unroll
+        for (int n1 = 0; n1 < 16; n1++) { u0[n1] = c_pack(ar[n1], plane[q * 17 + n1]); u1[n1] = c_pack(br[n1], plane[(q + 16) * 17 + n1]); }
+        __syncwarp();
+        af_fft16(u0);                                                          // X[k = q + 32 kb] at AF_BR4(kb)
+        af_fft16(u1);                                                          // X[k = q + 16 + 32 kb]
+        c64 *rowp = tile + (size_t)r * kWRowPitch;
+#pragma unroll
+        for (int kb = 0; kb < 16; kb++) { rowp[q + 32 * kb] = u0[AF_BR4(kb)]; rowp[q + 16 + 32 * kb] = u1[AF_BR4(kb)]; }
+    }
+    __syncthreads();
+    // result element (row k1, k2) is sequence index k1 + N1 * k2
+    if (MODE == 0) {
+        float2 *sp = p.spec + (size_t)clip * p.N;
+        for (int e = threadIdx.x; e < kWRows * 512; e += blockDim.x) {
+            const int k2 = e / kWRows, rr = e - k2 * kWRows;
+            float re, im;
+            c_unpack(tile[(size_t)rr * kWRowPitch + k2], re, im);
+            sp[(size_t)k2 * N1 + row0 + rr] = make_float2(re, im);
+        }
+    } else {
+        const float inv = 1.0f / (float)p.N;
+        float *oRe = p.outRe + (size_t)item * p.dataLength, *oIm = p.outIm + (size_t)item * p.dataLength;
+        for (int e = threadIdx.x; e < kWRows * 512; e += blockDim.x) {
+            const int k2 = e / kWRows, rr = e - k2 * kWRows;
+            const long long n = (long long)k2 * N1 + row0 + rr - p.padLength;
+            if (n < 0 || n >= p.dataLength) continue;
+            float re, im;
+            c_unpack(tile[(size_t)rr * kWRowPitch + k2], re, im);
+            oRe[n] = re * inv; oIm[n] = -im * inv;                             // conj back
+        }
+    }
+}
+
 __global__ void k_cwt_bank_table(CwtParams p, float *bank) {
     const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= (long long)p.num * p.N) return;
@@ -288,6 +461,23 @@ extern "C" int af_launch_cwt(const AfCwtArgs *a, const float *data, void *worksp
     p.work = p.spec + (size_t)p.N * a->batch;
     cudaStream_t st = (cudaStream_t)stream;
     int rc;
+    if (p.log2N1 == 10 && p.log2N2 == 9 && !getenv("AFB200_CWT_GENERIC")) {
+        // warp-level transforms (see k_cwt_cols_w / k_cwt_rows_w)
+        const size_t smC = sizeof(c64) * (size_t)kWCols * kWColPitch + sizeof(float2) * (1024 + p.N2);
+        const size_t smR = sizeof(c64) * (size_t)kWRows * kWRowPitch + sizeof(float2) * 512;
+        if ((rc = set_smem(k_cwt_cols_w<0>, smC, "smem k_cwt_cols_w<0>")) || (rc = set_smem(k_cwt_cols_w<1>, smC, "smem k_cwt_cols_w<1>")) ||
+            (rc = set_smem(k_cwt_rows_w<0>, smR, "smem k_cwt_rows_w<0>")) || (rc = set_smem(k_cwt_rows_w<1>, smR, "smem k_cwt_rows_w<1>"))) return rc;
+        const unsigned cb = (unsigned)(p.N2 / kWCols), rb = (unsigned)(p.N1 / kWRows), items = (unsigned)(a->batch * a->num);
+        k_cwt_cols_w<0><<<dim3((unsigned)a->batch, cb), kWCols * 32, smC, st>>>(p);
+        AF_LAUNCH_CHECK("k_cwt_cols_w<0>");
+        k_cwt_rows_w<0><<<dim3((unsigned)a->batch, rb), kWRows * 16, smR, st>>>(p);
+        AF_LAUNCH_CHECK("k_cwt_rows_w<0>");
+        k_cwt_cols_w<1><<<dim3(items, cb), kWCols * 32, smC, st>>>(p);
+        AF_LAUNCH_CHECK("k_cwt_cols_w<1>");
+        k_cwt_rows_w<1><<<dim3(items, rb), kWRows * 16, smR, st>>>(p);
+        AF_LAUNCH_CHECK("k_cwt_rows_w<1>");
+        return AF_OK;
+    }
     const int threads = 512;
     const size_t smemC = sizeof(float2) * (2 * (size_t)p.cols * (p.N1 + 1) + p.N1 + p.N2);
     const size_t smemR = sizeof(float2) * (2 * (size_t)p.rows * (p.N2 + 1) + p.N2);
