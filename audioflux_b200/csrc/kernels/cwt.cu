@@ -122,6 +122,7 @@ struct CwtParams {
     int dataLength, padLength, num, batch;
     int wType; float g, b, factor;
     int cols, rows;           // adjacent columns / rows per CTA (chosen so each leg fits shared memory)
+    int itemBase;             // first (clip, scale) item of this launch (fast path processes items in groups)
 };
 
 __device__ __forceinline__ float load_padded(const CwtParams &p, const float *x, int i) {
@@ -276,7 +277,7 @@ __global__ void __launch_bounds__(kWCols * 32) k_cwt_cols_w(CwtParams p) {
     float2 *tw1 = reinterpret_cast<float2 *>(tile + (size_t)kWCols * kWColPitch);   // [32 ka][32 n1] W_1024^(n1 ka)
     float2 *tf = tw1 + 1024;                                                   // [N2] W_N^j (fine inter-leg twiddle)
     const int N2 = p.N2;
-    const int item = blockIdx.x;
+    const int item = p.itemBase + blockIdx.x;
     const int clip = MODE == 0 ? item : item / p.num;
     const int col0 = blockIdx.y * kWCols;
     const float s = MODE == 1 ? p.scaleArr[item % p.num] : 0.0f;
@@ -340,7 +341,7 @@ __global__ void __launch_bounds__(kWRows * 16) k_cwt_rows_w(CwtParams p) {
     c64 *tile = reinterpret_cast<c64 *>(smemRaw);                              // [kWRows][kWRowPitch]
     float2 *tw = reinterpret_cast<float2 *>(tile + (size_t)kWRows * kWRowPitch);   // [32 ka][16 q] W_512^(q ka)
     const int N1 = p.N1;
-    const int item = blockIdx.x;
+    const int item = p.itemBase + blockIdx.x;
     const int clip = MODE == 0 ? item : item / p.num;
     const int row0 = blockIdx.y * kWRows;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -427,6 +428,7 @@ void fill_params(const AfCwtArgs *a, CwtParams *p) {
     p->N1 = 1 << p->log2N1; p->N2 = 1 << p->log2N2;
     p->dataLength = a->dataLength; p->padLength = a->padLength; p->num = a->num; p->batch = a->batch;
     p->scaleArr = a->scaleArr;
+    p->itemBase = 0;
     p->wType = a->wavelet.waveletType; p->g = a->wavelet.gamma; p->b = a->wavelet.beta; p->factor = (float)a->wavelet.factor;
     const size_t budget = (size_t)(getenv("AFB200_CWT_LEG_KB") ? atoi(getenv("AFB200_CWT_LEG_KB")) : 72) * 1024;   // per-CTA leg buffers: small enough for 2-3 CTAs per SM so load / FFT / store phases of different CTAs overlap
     p->cols = p->N2 == 1 ? 1 : 8;
@@ -472,10 +474,18 @@ extern "C" int af_launch_cwt(const AfCwtArgs *a, const float *data, void *worksp
         AF_LAUNCH_CHECK("k_cwt_cols_w<0>");
         k_cwt_rows_w<0><<<dim3((unsigned)a->batch, rb), kWRows * 16, smR, st>>>(p);
         AF_LAUNCH_CHECK("k_cwt_rows_w<0>");
-        k_cwt_cols_w<1><<<dim3(items, cb), kWCols * 32, smC, st>>>(p);
-        AF_LAUNCH_CHECK("k_cwt_cols_w<1>");
-        k_cwt_rows_w<1><<<dim3(items, rb), kWRows * 16, smR, st>>>(p);
-        AF_LAUNCH_CHECK("k_cwt_rows_w<1>");
+        // the two legs alternate over small groups of (clip, scale) items so that the inter-leg buffer of a group
+        // (4 MB per item) is still in the 126 MB L2 when the rows leg reads it back
+        const unsigned group = getenv("AFB200_CWT_GROUP") ? (unsigned)atoi(getenv("AFB200_CWT_GROUP")) : 12u;
+        for (unsigned i0 = 0; i0 < items; i0 += group) {
+            const unsigned n = items - i0 < group ? items - i0 : group;
+            CwtParams q = p;
+            q.itemBase = (int)i0;
+            k_cwt_cols_w<1><<<dim3(n, cb), kWCols * 32, smC, st>>>(q);
+            AF_LAUNCH_CHECK("k_cwt_cols_w<1>");
+            k_cwt_rows_w<1><<<dim3(n, rb), kWRows * 16, smR, st>>>(q);
+            AF_LAUNCH_CHECK("k_cwt_rows_w<1>");
+        }
         return AF_OK;
     }
     const int threads = 512;
