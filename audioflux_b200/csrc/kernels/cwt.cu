@@ -474,9 +474,10 @@ extern "C" int af_launch_cwt(const AfCwtArgs *a, const float *data, void *worksp
         AF_LAUNCH_CHECK("k_cwt_cols_w<0>");
         k_cwt_rows_w<0><<<dim3((unsigned)a->batch, rb), kWRows * 16, smR, st>>>(p);
         AF_LAUNCH_CHECK("k_cwt_rows_w<0>");
-        // the two legs alternate over small groups of (clip, scale) items so that the inter-leg buffer of a group
-        // (4 MB per item) is still in the 126 MB L2 when the rows leg reads it back
-        const unsigned group = getenv("AFB200_CWT_GROUP") ? (unsigned)atoi(getenv("AFB200_CWT_GROUP")) : 12u;
+        // optional: alternate the two legs over groups of (clip, scale) items (AFB200_CWT_GROUP) so that a group's
+        // inter-leg buffer is still in L2 when read back.  Measured on B200: slower than one launch pair for the
+        // whole chunk (launch tails cost more than the HBM round trip saves), so the default is a single group.
+        const unsigned group = getenv("AFB200_CWT_GROUP") && atoi(getenv("AFB200_CWT_GROUP")) > 0 ? (unsigned)atoi(getenv("AFB200_CWT_GROUP")) : items;
         for (unsigned i0 = 0; i0 < items; i0 += group) {
             const unsigned n = items - i0 < group ? items - i0 : group;
             CwtParams q = p;
