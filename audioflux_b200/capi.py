@@ -6,7 +6,7 @@ because the drop-in boundary IS this C ABI:
 
 * reference symbols  -- src/stft_algorithm.h:14-40, src/bft_algorithm.h:14-57,
   src/feature/xxcc_algorithm.h:12-39, src/cqt_algorithm.h:14-62,
-  src/cwt_algorithm.h:14-45 (signatures reproduced in include/*.h)
+  src/cwt_algorithm.h:14-45, src/spectrogram_algorithm.h:40-119 (signatures reproduced in include/*.h)
 * additive ``*Batch`` / ``afb200_*`` symbols -- include/afb200_ext.h (only bound when present)
 """
 from __future__ import annotations
@@ -46,6 +46,7 @@ REFERENCE_API = {
     "xxccObj_new": (C.c_int, [P(vp), C.c_int]),
     "xxccObj_setTimeLength": (None, [vp, C.c_int]),
     "xxccObj_xxcc": (None, [vp, vp, C.c_int, c_int_p, vp]),
+    "xxccObj_xxccStandard": (None, [vp, vp, C.c_int, vp, c_int_p, c_int_p, c_int_p, vp, vp, vp]),
     "xxccObj_free": (None, [vp]),
     # ---- CQT
     "cqtObj_new": (C.c_int, [P(vp), C.c_int, C.c_int, C.c_float, c_int_p]),
@@ -56,6 +57,8 @@ REFERENCE_API = {
     "cqtObj_getFreBandArr": (vp, [vp]),
     "cqtObj_setScale": (None, [vp, C.c_int]),
     "cqtObj_cqt": (None, [vp, vp, C.c_int, vp, vp]),
+    "cqtObj_chroma": (None, [vp, c_int_p, c_int_p, c_int_p, vp, vp, vp]),
+    "cqtObj_cqcc": (None, [vp, vp, C.c_int, c_int_p, vp]),
     "cqtObj_free": (None, [vp]),
     # ---- CWT
     "cwtObj_new": (C.c_int, [P(vp), C.c_int, C.c_int, c_int_p, c_float_p, c_float_p, c_int_p,
@@ -64,6 +67,26 @@ REFERENCE_API = {
     "cwtObj_getBinBandArr": (vp, [vp]),
     "cwtObj_cwt": (None, [vp, vp, vp, vp]),
     "cwtObj_free": (None, [vp]),
+    # ---- Spectrogram (front door; src/spectrogram_algorithm.h:40-119)
+    "spectrogramObj_new": (C.c_int, [P(vp), C.c_int, c_int_p, c_float_p, c_float_p, c_int_p, c_int_p, c_int_p,
+                                     c_int_p, c_int_p, c_int_p, c_int_p, c_int_p, c_int_p]),
+    "spectrogramObj_newLinear": (C.c_int, [P(vp), C.c_int, C.c_int, c_int_p]),
+    "spectrogramObj_newMel": (C.c_int, [P(vp), C.c_int, C.c_int, C.c_int, c_int_p]),
+    "spectrogramObj_newBark": (C.c_int, [P(vp), C.c_int, C.c_int, C.c_int, c_int_p]),
+    "spectrogramObj_newErb": (C.c_int, [P(vp), C.c_int, C.c_int, C.c_int, c_int_p]),
+    "spectrogramObj_setDataNormValue": (None, [vp, C.c_float]),
+    "spectrogramObj_calTimeLength": (C.c_int, [vp, C.c_int]),
+    "spectrogramObj_getFreBandArr": (vp, [vp]),
+    "spectrogramObj_getBinBandArr": (vp, [vp]),
+    "spectrogramObj_getBandNum": (C.c_int, [vp]),
+    "spectrogramObj_getBinBandLength": (C.c_int, [vp]),
+    "spectrogramObj_spectrogram": (None, [vp, vp, C.c_int, vp, vp]),
+    "spectrogramObj_xxcc": (None, [vp, vp, C.c_int, c_int_p, vp]),
+    "spectrogramObj_mfcc": (None, [vp, vp, C.c_int, vp]),
+    "spectrogramObj_bfcc": (None, [vp, vp, C.c_int, vp]),
+    "spectrogramObj_gtcc": (None, [vp, vp, C.c_int, vp]),
+    "spectrogramObj_lfcc": (None, [vp, vp, C.c_int, vp]),
+    "spectrogramObj_free": (None, [vp]),
 }
 
 # additive entry points of libaudioflux_b200.so (include/afb200_ext.h)
@@ -82,12 +105,19 @@ EXTENSION_API = {
     "xxccObj_xxccBatch": (C.c_int, [vp, vp, C.c_int, C.c_int, C.c_int, vp, C.c_int, vp]),
     "cqtObj_cqtBatch": (C.c_int, [vp, vp, C.c_int, C.c_int, vp, vp, C.c_int, vp]),
     "cqtObj_getKernelBank": (C.c_int, [vp, vp, vp]),
+    "cqtObj_chromaBatch": (C.c_int, [vp, vp, vp, C.c_int, C.c_int, C.c_int, C.c_int, vp, C.c_int, vp]),
+    "cqtObj_cqccBatch": (C.c_int, [vp, vp, C.c_int, C.c_int, C.c_int, vp, C.c_int, vp]),
+    "xxccObj_xxccStandardBatch": (C.c_int, [vp, vp, vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
+                                            vp, vp, vp, C.c_int, vp]),
+    "spectrogramObj_spectrogramBatch": (C.c_int, [vp, vp, C.c_int, C.c_int, vp, vp, C.c_int, vp]),
+    "spectrogramObj_mfccBatch": (C.c_int, [vp, vp, C.c_int, C.c_int, C.c_int, C.c_int, vp, C.c_int, vp]),
     "cwtObj_cwtBatch": (C.c_int, [vp, vp, C.c_int, vp, vp, C.c_int, vp]),
     "cwtObj_getFilterBankArr": (C.c_int, [vp, vp]),
     "afb200_window": (C.c_int, [C.c_int, C.c_int, vp]),
     "afb200_auditoryFilterBank": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
                                             C.c_float, C.c_float, C.c_int, vp, vp, vp]),
     "afb200_decimatorTaps": (C.c_int, [vp, vp]),
+    "afb200_chromaCqtFilterBank": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_float, vp]),
 }
 
 # setup-time builders exported (non-static) by the reference only; used by tests to
@@ -96,6 +126,7 @@ REFERENCE_BUILDERS = {
     "window_calFFTWindow": (vp, [C.c_int, C.c_int]),
     "auditory_filterBank": (None, [C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
                                    C.c_float, C.c_float, C.c_int, vp, vp, vp]),
+    "chroma_cqtFilterBank": (None, [C.c_int, C.c_int, C.c_int, c_float_p, vp]),
 }
 
 

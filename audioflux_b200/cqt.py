@@ -9,7 +9,8 @@ import numpy as np
 from .base import Base, as_f32, np_ptr, split_batch, swap_last2
 from .capi import opt_int, opt_float
 from .lib import check
-from .types import WindowType, SpectralFilterBankNormalType, enum_value
+from .types import (WindowType, SpectralFilterBankNormalType, SpectralDataType, ChromaDataNormalType,
+                    CepstralRectifyType, enum_value)
 
 C1_HZ = 32.703196
 
@@ -87,6 +88,59 @@ class CQT(Base):
         im = alloc(B, T, self.num)
         check(fn(self._obj, ptr(x2), L, B, ptr(re), ptr(im), kind, stream), "cqtObj_cqtBatch")
         return re.reshape(*lead, T, self.num), im.reshape(*lead, T, self.num)
+
+    def chroma_planes(self, re, im, chroma_num=12, data_type=SpectralDataType.POWER,
+                      norm_type=ChromaDataNormalType.MAX):
+        """Raw C layout: planes [T, num] of the LAST cqt call -> [T, chroma_num] (cqtObj_chroma,
+        src/cqt_algorithm.c:484-600)."""
+        re, im = as_f32(re), as_f32(im)
+        out = np.zeros((re.shape[0], chroma_num), np.float32)
+        self._lib.cqtObj_chroma(self._obj, opt_int(chroma_num), opt_int(enum_value(data_type)),
+                                opt_int(enum_value(norm_type)), np_ptr(re), np_ptr(im), np_ptr(out))
+        return out
+
+    def chroma(self, m_cqt_data, chroma_num=12, data_type=SpectralDataType.POWER,
+               norm_type=ChromaDataNormalType.MAX):
+        """complex [num, T] (result of the last ``cqt`` call) -> [chroma_num, T] as cqt.py:153-221."""
+        z = np.asarray(m_cqt_data)
+        if z.ndim != 2:
+            raise ValueError("chroma works on the [num, T] result of the preceding cqt() call")
+        zt = np.swapaxes(z, -1, -2)
+        return swap_last2(self.chroma_planes(zt.real, zt.imag, chroma_num, data_type, norm_type))
+
+    def chroma_batch(self, re, im, chroma_num=12, data_type=SpectralDataType.POWER,
+                     norm_type=ChromaDataNormalType.MAX):
+        """Additive: planes [..., T, num] (numpy host | torch cuda) -> [..., T, chroma_num]."""
+        fn = self._require_ext("cqtObj_chromaBatch")
+        r2, lead, kind, ptr, stream, alloc = split_batch(re)
+        i2 = split_batch(im)[0]
+        out = alloc(r2.shape[0], chroma_num)
+        check(fn(self._obj, ptr(r2), ptr(i2), r2.shape[0], chroma_num, enum_value(data_type), enum_value(norm_type),
+                 ptr(out), kind, stream), "cqtObj_chromaBatch")
+        return out.reshape(*lead, chroma_num)
+
+    def cqcc_planes(self, m_tn, cc_num=13, rectify_type=CepstralRectifyType.LOG):
+        """Raw C layout: [T, num] of the LAST cqt call -> [T, cc_num] (cqtObj_cqcc, src/cqt_algorithm.c:602-660)."""
+        m = as_f32(m_tn)
+        out = np.zeros((m.shape[0], cc_num), np.float32)
+        self._lib.cqtObj_cqcc(self._obj, np_ptr(m), cc_num, opt_int(enum_value(rectify_type)), np_ptr(out))
+        return out
+
+    def cqcc(self, m_data_arr, cc_num=13, rectify_type=CepstralRectifyType.LOG):
+        """[num, T] power / magnitude of the last cqt call -> [cc_num, T] as cqt.py:223-275."""
+        m = np.asarray(m_data_arr)
+        if np.iscomplexobj(m):
+            m = np.abs(m)
+        return swap_last2(self.cqcc_planes(np.swapaxes(as_f32(m), -1, -2), cc_num, rectify_type))
+
+    def cqcc_batch(self, m_tn, cc_num=13, rectify_type=CepstralRectifyType.LOG):
+        """Additive: [..., T, num] (numpy host | torch cuda) -> [..., T, cc_num]."""
+        fn = self._require_ext("cqtObj_cqccBatch")
+        x2, lead, kind, ptr, stream, alloc = split_batch(m_tn)
+        out = alloc(x2.shape[0], cc_num)
+        check(fn(self._obj, ptr(x2), x2.shape[0], cc_num, enum_value(rectify_type), ptr(out), kind, stream),
+              "cqtObj_cqccBatch")
+        return out.reshape(*lead, cc_num)
 
     def __del__(self):
         if getattr(self, "_is_created", False):

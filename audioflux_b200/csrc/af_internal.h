@@ -84,6 +84,8 @@ int af_cqt_bank_build(AfCqtBank *b, int num, int samplate, float minFre, int bin
 void af_cqt_bank_free(AfCqtBank *b);
 /* time-domain kernels kappa[b][n] = sum_{k<=N/2} K[b][k] e^{-2 pi i k n/N}  -> 2 x bpo x N floats */
 int af_cqt_time_kernels(const AfCqtBank *b, float *kappaRe, float *kappaIm);
+/* chroma folding matrix [num][cqtLength] of cqtObj_chroma; -1 when num does not divide binPerOctave */
+int af_chroma_cqt_bank(int num, int cqtLength, int binPerOctave, float minFre, float *bank);
 
 typedef struct {
     int waveletType;
@@ -131,6 +133,14 @@ int af_launch_copy_cols(const float *in, int rows, int width, int lo, int count,
 /* rectify (0 log10 clamp 1e-8 | 1 cube root) then out[r][c] = sum_m D[c][m] * rect(in[r][m]) */
 int af_launch_xxcc(const float *in, int rows, int num, int ccNum, int rectifyType, const float *dct,
                    float *out, void *stream);
+/* cepstra + log-energy replace/append + the reference's per-frame delta FIRs (xxcc_algorithm.c:168-296) */
+int af_launch_xxcc_standard(const float *in, const float *energy, int rows, int num, int ccNum,
+                            int rectifyType, int energyType, int order, const float *dctT,
+                            float *coe, float *d1, float *d2, void *stream);
+
+/* out[r][c] = normalise_c( sum_j bank[c][j] * (re^2+im^2 | sqrt) ) (cqt_algorithm.c:484-600) */
+int af_launch_chroma(const float *re, const float *im, int rows, int num, int chromaNum, int isMag,
+                     int normType, const float *bank, float *out, void *stream);
 
 typedef struct {
     int fftLength, slideLength, num, ccNum, rectifyType, dataType;
@@ -164,6 +174,17 @@ typedef struct {
 size_t af_cwt_workspace_bytes(const AfCwtArgs *a);
 int af_launch_cwt(const AfCwtArgs *a, const float *data, void *workspace, float *outRe, float *outIm, void *stream);
 int af_launch_cwt_bank_table(const AfCwtArgs *a, float *bank /* device num x n */, void *stream);
+
+/* ---------------- BFT core shared with the SpectrogramObj front door (host/af_bft.c) ---------------- */
+typedef struct {
+    int num, radix2Exp, samplate, binPerOctave, slideLength, lowIndex, highIndex;
+    float lowFre, highFre;
+    int windowType, dataType, scaleType, styleType, normalType;
+} AfBftSpec;
+int af_bft_create(const AfBftSpec *spec, BFTObj *out);      /* 0, -1 (memory), -2 (unsupported bank) */
+int af_bft_phase(BFTObj b, const float *data, int dataLength, int batch, int lowIndex, int count, float *phase,
+                 int memKind, void *stream);
+int af_launch_phase(const float *re, const float *im, int rows, int width, int lo, int count, float *out, void *stream);
 
 void af_count_launch(int n);
 

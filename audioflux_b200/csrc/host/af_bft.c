@@ -63,19 +63,33 @@ int bftObj_new(BFTObj *out, int num, int radix2Exp, int *samplate, float *lowFre
         af_fail(AF_ERR_UNSUPPORTED, "bftObj_new: isReassign / isTemporal are outside the accelerated path and not supported");
         return -2;
     }
-    if (r > 14) { af_fail(AF_ERR_UNSUPPORTED, "bftObj_new: radix2Exp > 14 is not supported"); return -2; }
+    AfBftSpec spec;
+    spec.num = num; spec.radix2Exp = r; spec.samplate = sr; spec.binPerOctave = bpo;
+    spec.lowFre = range.low; spec.highFre = range.high; spec.lowIndex = range.lowIndex; spec.highIndex = range.highIndex;
+    spec.windowType = windowType ? (int)*windowType : Window_Hann;
+    spec.slideLength = (slideLength && *slideLength > 0) ? *slideLength : n / 4;
+    spec.dataType = dataType ? (int)*dataType : SpectralData_Power;
+    spec.scaleType = scale;
+    spec.styleType = styleType ? (int)*styleType : SpectralFilterBankStyle_Slaney;
+    spec.normalType = normalType ? (int)*normalType : SpectralFilterBankNormal_None;
+    return af_bft_create(&spec, out);
+}
 
+/* tables of a BFT object from fully resolved parameters (shared with spectrogramObj_new, host/af_spectrogram.c) */
+int af_bft_create(const AfBftSpec *p, BFTObj *out) {
+    const int num = p->num, r = p->radix2Exp, n = 1 << r, sr = p->samplate, scale = p->scaleType;
+    *out = NULL;
+    if (r > 14) { af_fail(AF_ERR_UNSUPPORTED, "radix2Exp > 14 is not supported"); return -2; }
     BFTObj b = (BFTObj)calloc(1, sizeof(struct OpaqueBFT));
     if (!b) return -1;
-    b->num = num; b->radix2Exp = r; b->fftLength = n; b->samplate = sr; b->binPerOctave = bpo;
-    b->lowFre = range.low; b->highFre = range.high; b->lowIndex = range.lowIndex; b->highIndex = range.highIndex;
-    b->windowType = windowType ? *windowType : Window_Hann;
-    b->slideLength = n / 4;
-    if (slideLength && *slideLength > 0) b->slideLength = *slideLength;
-    b->dataType = dataType ? *dataType : SpectralData_Power;
-    b->scaleType = scale;
-    b->styleType = styleType ? *styleType : SpectralFilterBankStyle_Slaney;
-    b->normalType = normalType ? *normalType : SpectralFilterBankNormal_None;
+    b->num = num; b->radix2Exp = r; b->fftLength = n; b->samplate = sr; b->binPerOctave = p->binPerOctave;
+    b->lowFre = p->lowFre; b->highFre = p->highFre; b->lowIndex = p->lowIndex; b->highIndex = p->highIndex;
+    b->windowType = (WindowType)p->windowType;
+    b->slideLength = p->slideLength;
+    b->dataType = (SpectralDataType)p->dataType;
+    b->scaleType = (SpectralFilterBankScaleType)scale;
+    b->styleType = (SpectralFilterBankStyleType)p->styleType;
+    b->normalType = (SpectralFilterBankNormalType)p->normalType;
     b->normValue = 1.0f;
 
     const int width = n / 2 + 1;
@@ -92,7 +106,7 @@ int bftObj_new(BFTObj *out, int num, int radix2Exp, int *samplate, float *lowFre
             if (i < width) b->bank[(size_t)j * width + i] = 1.0f;
         }
     } else if (af_auditory_filterbank(num, n, sr, scale, b->styleType, b->normalType, b->lowFre, b->highFre,
-                                      bpo, b->bank, b->freBandArr, b->binBandArr)) {
+                                      p->binPerOctave, b->bank, b->freBandArr, b->binBandArr)) {
         bftObj_free(b);
         return -2;
     }
@@ -186,10 +200,10 @@ static int bft_compute(BFTObj b, const float *dData, int dataLength, int batch, 
         if (b->resultType) {                                  /* real: sum_k w |z|^2 (or |z|) */
             const int mode = b->dataType == SpectralData_Mag ? AF_STFT_MAG : AF_STFT_POWER;
             if ((rc = af_launch_stft(&src, mode, b->normValue, sRe, NULL, st))) return rc;
-            if (linear) {
+            const float post = (b->dataType == SpectralData_Mag) ? b->normValue : 1.0f;
+            if (linear && post == 1.0f) {
                 if ((rc = af_launch_copy_cols(sRe, rows, width, b->lowIndex, count, oRe, st))) return rc;
-            } else {
-                float post = (b->dataType == SpectralData_Mag) ? b->normValue : 1.0f;
+            } else {                                          /* (Linear + Mag + norm: the 0/1 bank, then ^norm) */
                 if ((rc = af_launch_bank(&b->bankDev, sRe, rows, post, oRe, st))) return rc;
             }
         } else {                                              /* complex: sum_k w z^2 (or z) */
@@ -236,6 +250,48 @@ int bftObj_bftBatch(BFTObj b, const float *data, int dataLength, int batch, floa
 void bftObj_bft(BFTObj b, float *dataArr, int dataLength, float *mRealArr3, float *mImageArr3) {
     if (!b || !dataArr || !mRealArr3) return;
     bftObj_bftBatch(b, dataArr, dataLength, 1, mRealArr3, mImageArr3, AFB200_MEM_HOST, NULL);
+}
+
+/* phase of the STFT bins lowIndex..highIndex as spectrogramObj_spectrogram reports it for the Linear scale
+ * (src/spectrogram_algorithm.c:1040-1056): atan2f(im, re < 1e-16 ? 1e-16 : re).  phase: batch x T x count. */
+int af_bft_phase(BFTObj b, const float *data, int dataLength, int batch, int lowIndex, int count, float *phase,
+                 int memKind, void *stream) {
+    if (!b || !data || !phase || dataLength <= 0 || batch <= 0) return af_fail(AF_ERR_ARG, "spectrogram phase: bad argument");
+    int rc = bft_device(b);
+    if (rc) return rc;
+    const int T = bftObj_calTimeLength(b, dataLength), width = b->fftLength / 2 + 1;
+    if (T <= 0) return AF_OK;
+    void *st = memKind == AFB200_MEM_DEVICE ? stream : (stream ? stream : b->stream);
+    const float *dData = data;
+    float *dPhase = phase;
+    const size_t inB = sizeof(float) * (size_t)batch * dataLength, outB = sizeof(float) * (size_t)batch * T * count;
+    if (memKind != AFB200_MEM_DEVICE) {
+        if ((rc = af_devbuf_reserve(&b->dIn, inB)) || (rc = af_devbuf_reserve(&b->dOutRe, outB))) return rc;
+        if ((rc = af_memcpy_h2d(b->dIn.ptr, data, inB, st))) return rc;
+        dData = (const float *)b->dIn.ptr; dPhase = (float *)b->dOutRe.ptr;
+    }
+    const size_t perClip = sizeof(float) * (size_t)T * width;
+    size_t budget = af_dev_free_bytes() / 4;
+    if (budget < perClip) budget = perClip;
+    if (budget > ((size_t)2 << 30)) budget = (size_t)2 << 30;
+    int chunk = (int)(budget / perClip);
+    if (chunk < 1) chunk = 1;
+    if (chunk > batch) chunk = batch;
+    if ((rc = af_devbuf_reserve(&b->dSpecRe, perClip * chunk)) || (rc = af_devbuf_reserve(&b->dSpecIm, perClip * chunk))) return rc;
+    for (int c0 = 0; c0 < batch; c0 += chunk) {
+        const int nb = batch - c0 < chunk ? batch - c0 : chunk;
+        AfFrameSrc src;
+        memset(&src, 0, sizeof(src));
+        src.fftLength = b->fftLength; src.slideLength = b->slideLength; src.dataLength = dataLength;
+        src.timeLength = T; src.batch = nb; src.validLength = dataLength; src.window = b->dWindow;
+        src.data = dData + (size_t)c0 * dataLength;
+        if ((rc = af_launch_stft(&src, AF_STFT_HALF, 1.0f, (float *)b->dSpecRe.ptr, (float *)b->dSpecIm.ptr, st))) return rc;
+        if ((rc = af_launch_phase((const float *)b->dSpecRe.ptr, (const float *)b->dSpecIm.ptr, nb * T, width, lowIndex, count,
+                                  dPhase + (size_t)c0 * T * count, st))) return rc;
+    }
+    if (memKind == AFB200_MEM_DEVICE) return AF_OK;
+    if ((rc = af_memcpy_d2h(phase, b->dOutRe.ptr, outB, st))) return rc;
+    return af_stream_sync(st);
 }
 
 /* ---- fused / composed MFCC: bft(real mode) -> rectify -> ortho DCT-II -> first ccNum ---- */

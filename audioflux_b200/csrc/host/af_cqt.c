@@ -19,6 +19,11 @@ struct OpaqueCQT {
     float *dKappa2, *dLeft, *dRight, *dScale;    /* dScale: octaveNum x bpo, rebuilt when isScale flips */
     int scaleDirty;
     AfDevBuf dIn, dSigA, dSigB, dOutRe, dOutIm;
+    /* post-processing of the last transform (chroma / cqcc) */
+    int timeLength;                /* frames of the last cqtObj_cqt call (cqt_algorithm.c:463-478) */
+    int chromaNum;
+    float *dChromaBank, *dDctT;
+    AfDevBuf dPostA, dPostB, dPostOut;
 };
 
 int cqtObj_newWith(CQTObj *out, int num, int *samplate, float *minFre, int *binPerOctave, float *factor,
@@ -161,13 +166,105 @@ int cqtObj_cqtBatch(CQTObj c, const float *data, int dataLength, int batch, floa
 
 void cqtObj_cqt(CQTObj c, float *dataArr, int dataLength, float *mRealArr3, float *mImageArr3) {
     if (!c || !dataArr || dataLength <= 0) return;
+    c->timeLength = cqtObj_calTimeLength(c, dataLength);
     cqtObj_cqtBatch(c, dataArr, dataLength, 1, mRealArr3, mImageArr3, AFB200_MEM_HOST, NULL);
+}
+
+/* ---- chroma: rows x num CQT planes -> rows x chromaNum (cqt_algorithm.c:484-600) ---- */
+int cqtObj_chromaBatch(CQTObj c, const float *mReal, const float *mImag, int rows, int chromaNum, int dataType,
+                       int normType, float *out, int memKind, void *stream) {
+    if (!c || !mReal || !mImag || !out || rows < 0) return af_fail(AF_ERR_ARG, "cqtObj_chromaBatch: bad argument");
+    if (chromaNum < 1 || chromaNum > c->binPerOctave || c->binPerOctave % chromaNum != 0)
+        return af_fail(AF_ERR_ARG, "cqtObj_chromaBatch: chromaNum=%d does not divide binPerOctave=%d", chromaNum, c->binPerOctave);
+    if (normType < ChromaDataNormal_None || normType > ChromaDataNormal_P1) return af_fail(AF_ERR_ARG, "cqtObj_chromaBatch: normType=%d", normType);
+    af_clear_error();
+    int rc = cqt_device(c);
+    if (rc) return rc;
+    if (chromaNum != c->chromaNum) {
+        float *bank = (float *)malloc(sizeof(float) * (size_t)chromaNum * c->num);
+        if (!bank) return AF_ERR_NOMEM;
+        af_chroma_cqt_bank(chromaNum, c->num, c->binPerOctave, c->minFre, bank);
+        af_dev_free(c->dChromaBank); c->dChromaBank = NULL;
+        rc = af_dev_upload((void **)&c->dChromaBank, bank, sizeof(float) * (size_t)chromaNum * c->num);
+        free(bank);
+        if (rc) return rc;
+        c->chromaNum = chromaNum;
+    }
+    const int isMag = dataType == SpectralData_Mag;
+    if (memKind == AFB200_MEM_DEVICE)
+        return af_launch_chroma(mReal, mImag, rows, c->num, chromaNum, isMag, normType, c->dChromaBank, out, stream);
+    void *st = stream ? stream : c->stream;
+    const size_t inB = sizeof(float) * (size_t)rows * c->num, outB = sizeof(float) * (size_t)rows * chromaNum;
+    if ((rc = af_devbuf_reserve(&c->dPostA, inB)) || (rc = af_devbuf_reserve(&c->dPostB, inB)) || (rc = af_devbuf_reserve(&c->dPostOut, outB))) return rc;
+    if ((rc = af_memcpy_h2d(c->dPostA.ptr, mReal, inB, st)) || (rc = af_memcpy_h2d(c->dPostB.ptr, mImag, inB, st))) return rc;
+    if ((rc = af_launch_chroma((const float *)c->dPostA.ptr, (const float *)c->dPostB.ptr, rows, c->num, chromaNum, isMag,
+                               normType, c->dChromaBank, (float *)c->dPostOut.ptr, st))) return rc;
+    if ((rc = af_memcpy_d2h(out, c->dPostOut.ptr, outB, st))) return rc;
+    return af_stream_sync(st);
+}
+
+void cqtObj_chroma(CQTObj c, int *chromaNum, SpectralDataType *dataType, ChromaDataNormalType *normType,
+                   float *mRealArr1, float *mImageArr1, float *mDataArr3) {
+    if (!c || !mRealArr1 || !mImageArr1 || !mDataArr3) return;
+    const int cn = chromaNum ? *chromaNum : 12;
+    if (cn < 1 || cn > c->binPerOctave || c->binPerOctave % cn != 0) {
+        printf("chromaNum and binPerOctave not map!!!");      /* cqt_algorithm.c:524-527 */
+        return;
+    }
+    if (c->timeLength <= 0) return;
+    cqtObj_chromaBatch(c, mRealArr1, mImageArr1, c->timeLength, cn, dataType ? (int)*dataType : SpectralData_Power,
+                       normType ? (int)*normType : ChromaDataNormal_Max, mDataArr3, AFB200_MEM_HOST, NULL);
+}
+
+/* ---- cqcc: rows x num (power or magnitude) -> rectify -> ortho DCT-II -> first ccNum (cqt_algorithm.c:602-660) ---- */
+int cqtObj_cqccBatch(CQTObj c, const float *in, int rows, int ccNum, int rectifyType, float *out, int memKind, void *stream) {
+    if (!c || !in || !out || rows < 0) return af_fail(AF_ERR_ARG, "cqtObj_cqccBatch: bad argument");
+    if (ccNum < 1 || ccNum > c->num) return af_fail(AF_ERR_ARG, "cqtObj_cqccBatch: ccNum=%d outside [1, %d]", ccNum, c->num);
+    af_clear_error();
+    int rc = cqt_device(c);
+    if (rc) return rc;
+    if (!c->dDctT) {
+        const int n = c->num;
+        float *d = (float *)malloc(sizeof(float) * (size_t)n * n), *t = (float *)malloc(sizeof(float) * (size_t)n * n);
+        if (!d || !t) { free(d); free(t); return AF_ERR_NOMEM; }
+        af_dct2_matrix(n, n, d);
+        for (int k = 0; k < n; k++) for (int j = 0; j < n; j++) t[(size_t)j * n + k] = d[(size_t)k * n + j];
+        rc = af_dev_upload((void **)&c->dDctT, t, sizeof(float) * (size_t)n * n);
+        free(d); free(t);
+        if (rc) return rc;
+    }
+    if (memKind == AFB200_MEM_DEVICE) return af_launch_xxcc(in, rows, c->num, ccNum, rectifyType, c->dDctT, out, stream);
+    void *st = stream ? stream : c->stream;
+    const size_t inB = sizeof(float) * (size_t)rows * c->num, outB = sizeof(float) * (size_t)rows * ccNum;
+    if ((rc = af_devbuf_reserve(&c->dPostA, inB)) || (rc = af_devbuf_reserve(&c->dPostOut, outB))) return rc;
+    if ((rc = af_memcpy_h2d(c->dPostA.ptr, in, inB, st))) return rc;
+    if ((rc = af_launch_xxcc((const float *)c->dPostA.ptr, rows, c->num, ccNum, rectifyType, c->dDctT, (float *)c->dPostOut.ptr, st))) return rc;
+    if ((rc = af_memcpy_d2h(out, c->dPostOut.ptr, outB, st))) return rc;
+    return af_stream_sync(st);
+}
+
+void cqtObj_cqcc(CQTObj c, float *mDataArr1, int ccNum, CepstralRectifyType *rectifyType, float *mDataArr2) {
+    if (!c || !mDataArr1 || !mDataArr2) return;
+    if (ccNum > c->num || ccNum < 1 || c->timeLength <= 0) return;     /* silent, like cqt_algorithm.c:625-627 */
+    cqtObj_cqccBatch(c, mDataArr1, c->timeLength, ccNum, rectifyType ? (int)*rectifyType : CepstralRectify_Log,
+                     mDataArr2, AFB200_MEM_HOST, NULL);
+}
+
+void cqtObj_cqhc(CQTObj c, float *mDataArr1, int hcNum, float *mDataArr2) {
+    (void)c; (void)mDataArr1; (void)hcNum; (void)mDataArr2;
+    af_fail(AF_ERR_UNSUPPORTED, "cqtObj_cqhc: cepstral deconvolution is not part of libaudioflux_b200");
+}
+void cqtObj_deconv(CQTObj c, float *mDataArr1, float *mDataArr2, float *mDataArr3) {
+    (void)c; (void)mDataArr1; (void)mDataArr2; (void)mDataArr3;
+    af_fail(AF_ERR_UNSUPPORTED, "cqtObj_deconv: cepstral deconvolution is not part of libaudioflux_b200");
 }
 
 void cqtObj_free(CQTObj c) {
     if (!c) return;
     af_devbuf_free(&c->dIn); af_devbuf_free(&c->dSigA); af_devbuf_free(&c->dSigB);
     af_devbuf_free(&c->dOutRe); af_devbuf_free(&c->dOutIm);
+    af_devbuf_free(&c->dPostA); af_devbuf_free(&c->dPostB); af_devbuf_free(&c->dPostOut);
+    af_dev_free(c->dChromaBank); af_dev_free(c->dDctT);
     af_dev_free(c->dKappa2); af_dev_free(c->dLeft); af_dev_free(c->dRight); af_dev_free(c->dScale);
     af_stream_destroy(c->stream);
     af_cqt_bank_free(&c->bank);

@@ -159,3 +159,38 @@ int afb200_decimatorTaps(float *left32, float *right31) {
     af_decimator_taps(left32, right31);
     return AF_OK;
 }
+
+/* 0/1 folding matrix of CQT bins onto chroma classes, bank[num][cqtLength]
+ * (chroma_cqtFilterBank, src/filterbank/chroma_filterBank.c:176-262).  With n = bpo/num bins per class, class 0
+ * is centred on the first bin of every octave (ceil(n/2) bins from the octave start plus the last n-ceil(n/2) of
+ * the octave), class i>0 takes the next n bins.  Rows are then rotated so that row 0 is pitch class C, using the
+ * reference's folded MIDI index (values above 6 are mirrored) and its integer factor num/bpo. */
+int af_chroma_cqt_bank(int num, int cqtLength, int bpo, float minFre, float *bank) {
+    if (num < 1 || num > bpo || bpo % num != 0) return -1;
+    const int n = bpo / num, offset = (int)ceilf(n / 2.0), sub = n - offset;
+    float fmin = minFre > 0 ? minFre : 32.703196f;
+    int midi = (int)roundf(12 * log2(fmin / 440) + 69);
+    midi = midi % 12;
+    if (midi > 6) midi = 12 - midi;
+    const int shift = midi * (num / bpo);
+    memset(bank, 0, sizeof(float) * (size_t)num * cqtLength);
+    for (int k = 0; k < num; k++) {
+        const int i = shift ? (k + shift) % num : k;          /* source class of output row k */
+        const int start = i ? offset + (i - 1) * n : 0;
+        for (int j = 0; j < cqtLength; j++) {
+            const int mod = j % bpo;
+            int hit;
+            if (i) hit = mod >= start && mod < start + n;
+            else hit = (mod >= 0 && mod < offset) || (sub && mod >= bpo - sub && mod < bpo);
+            if (hit) bank[(size_t)k * cqtLength + j] = 1.0f;
+        }
+    }
+    return 0;
+}
+
+int afb200_chromaCqtFilterBank(int num, int cqtLength, int binPerOctave, float minFre, float *bank) {
+    if (!bank || cqtLength < 1) return af_fail(AF_ERR_ARG, "afb200_chromaCqtFilterBank: bad argument");
+    if (af_chroma_cqt_bank(num, cqtLength, binPerOctave, minFre, bank))
+        return af_fail(AF_ERR_ARG, "afb200_chromaCqtFilterBank: num=%d does not divide binPerOctave=%d", num, binPerOctave);
+    return AF_OK;
+}

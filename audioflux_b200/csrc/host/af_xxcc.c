@@ -10,7 +10,7 @@ struct OpaqueXXCC {
     int devReady;
     void *stream;
     float *dDctT;               /* device, transposed ortho DCT-II [num][num] */
-    AfDevBuf dIn, dOut;
+    AfDevBuf dIn, dOut, dEnergy, dD1, dD2;
 };
 
 int xxccObj_new(XXCCObj *out, int num) {
@@ -72,9 +72,57 @@ void xxccObj_xxcc(XXCCObj x, float *mDataArr1, int mLength, CepstralRectifyType 
                       mDataArr2, AFB200_MEM_HOST, NULL);
 }
 
+/* batched form of xxccObj_xxccStandard (xxcc_algorithm.c:168-296).  in: rows x num, energy: rows (may be NULL
+ * when energyType = Ignore); coe / delta1 / delta2: rows x (ccNum, or ccNum+1 when energyType = Append). */
+int xxccObj_xxccStandardBatch(XXCCObj x, const float *in, const float *energy, int rows, int ccNum,
+                              int deltaWindowLength, int energyType, int rectifyType,
+                              float *coe, float *delta1, float *delta2, int memKind, void *stream) {
+    if (!x || !in || !coe || !delta1 || !delta2 || rows < 0) return af_fail(AF_ERR_ARG, "xxccObj_xxccStandardBatch: bad argument");
+    if (ccNum < 1 || ccNum > x->num) return af_fail(AF_ERR_ARG, "xxccObj_xxccStandardBatch: ccNum=%d outside [1, %d]", ccNum, x->num);
+    if (energyType < CepstralEnergy_Replace || energyType > CepstralEnergy_Ignore)
+        return af_fail(AF_ERR_ARG, "xxccObj_xxccStandardBatch: energyType=%d", energyType);
+    if (energyType != CepstralEnergy_Ignore && !energy) return af_fail(AF_ERR_ARG, "xxccObj_xxccStandardBatch: energy array required");
+    int order = 9;                                         /* :170, :205-209 */
+    if (deltaWindowLength >= 3 && deltaWindowLength % 2 == 1) order = deltaWindowLength;
+    af_clear_error();
+    int rc = xxcc_device(x);
+    if (rc) return rc;
+    void *st = stream ? stream : x->stream;
+    const int W = ccNum + (energyType == CepstralEnergy_Append ? 1 : 0);
+    if (memKind == AFB200_MEM_DEVICE)
+        return af_launch_xxcc_standard(in, energy, rows, x->num, ccNum, rectifyType, energyType, order, x->dDctT,
+                                       coe, delta1, delta2, stream);
+    const size_t inB = sizeof(float) * (size_t)rows * x->num, outB = sizeof(float) * (size_t)rows * W;
+    if ((rc = af_devbuf_reserve(&x->dIn, inB)) || (rc = af_devbuf_reserve(&x->dOut, outB)) ||
+        (rc = af_devbuf_reserve(&x->dD1, outB)) || (rc = af_devbuf_reserve(&x->dD2, outB)) ||
+        (rc = af_devbuf_reserve(&x->dEnergy, sizeof(float) * (size_t)(rows > 0 ? rows : 1)))) return rc;
+    if ((rc = af_memcpy_h2d(x->dIn.ptr, in, inB, st))) return rc;
+    if (energy && (rc = af_memcpy_h2d(x->dEnergy.ptr, energy, sizeof(float) * (size_t)rows, st))) return rc;
+    if ((rc = af_launch_xxcc_standard((const float *)x->dIn.ptr, (const float *)x->dEnergy.ptr, rows, x->num, ccNum,
+                                      rectifyType, energyType, order, x->dDctT, (float *)x->dOut.ptr,
+                                      (float *)x->dD1.ptr, (float *)x->dD2.ptr, st))) return rc;
+    if ((rc = af_memcpy_d2h(coe, x->dOut.ptr, outB, st)) || (rc = af_memcpy_d2h(delta1, x->dD1.ptr, outB, st)) ||
+        (rc = af_memcpy_d2h(delta2, x->dD2.ptr, outB, st))) return rc;
+    return af_stream_sync(st);
+}
+
+void xxccObj_xxccStandard(XXCCObj x, float *mDataArr1, int mLength, float *energyArr, int *deltaWindowLength,
+                          CepstralEnergyType *energyType, CepstralRectifyType *rectifyType,
+                          float *mCoeArr, float *mDeltaArr1, float *mDeltaArr2) {
+    if (!x || !mDataArr1 || !mCoeArr || !mDeltaArr1 || !mDeltaArr2) return;
+    if (mLength > x->num) return;                 /* silent, like xxcc_algorithm.c:196-198 */
+    if (x->timeLength <= 0 || mLength < 1) return;
+    xxccObj_xxccStandardBatch(x, mDataArr1, energyArr, x->timeLength, mLength,
+                              deltaWindowLength ? *deltaWindowLength : 9,
+                              energyType ? (int)*energyType : CepstralEnergy_Replace,
+                              rectifyType ? (int)*rectifyType : CepstralRectify_Log,
+                              mCoeArr, mDeltaArr1, mDeltaArr2, AFB200_MEM_HOST, NULL);
+}
+
 void xxccObj_free(XXCCObj x) {
     if (!x) return;
     af_devbuf_free(&x->dIn); af_devbuf_free(&x->dOut);
+    af_devbuf_free(&x->dEnergy); af_devbuf_free(&x->dD1); af_devbuf_free(&x->dD2);
     af_dev_free(x->dDctT);
     af_stream_destroy(x->stream);
     free(x);

@@ -102,6 +102,119 @@ __global__ void k_xxcc(const float *__restrict__ in, long long rows, int num, in
     }
 }
 
+// xxccObj_xxccStandard (src/feature/xxcc_algorithm.c:168-296): cepstra, then log-energy replace / append, then
+// the reference's delta and delta-delta: a causal `order`-tap FIR b[j] = (m - j) / sum_{i<=m} i^2 run ALONG THE
+// COEFFICIENT AXIS of each frame (util_delta, src/util/flux_util.c:803-815; filterDesign_filter,
+// src/dsp/filterDesign_fir.c:229-248).  One warp per frame.
+__global__ void k_xxcc_standard(const float *__restrict__ in, const float *__restrict__ energy, long long rows,
+                                int num, int ccNum, int rectify, int energyType, int order,
+                                const float *__restrict__ dctT, int ccStride,
+                                float *__restrict__ coe, float *__restrict__ d1, float *__restrict__ d2) {
+    extern __shared__ float sh[];
+    const int wib = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const long long row = (long long)blockIdx.x * (blockDim.x >> 5) + wib;
+    if (row >= rows) return;
+    const int W = ccNum + (energyType == CepstralEnergy_Append ? 1 : 0);
+    float *l = sh + (size_t)wib * (num + 2 * (num + 1));
+    float *c0 = l + num, *c1 = c0 + (num + 1);
+    for (int m = lane; m < num; m += 32) {
+        float v = in[row * num + m];
+        if (rectify == CepstralRectify_CubicRoot) v = powf(v, 1.0f / 3.0f);
+        else v = log10f(v < 1e-8f ? 1e-8f : v);
+        l[m] = v;
+    }
+    __syncwarp();
+    float e = 0.0f;
+    if (energyType != CepstralEnergy_Ignore) {
+        e = energy[row];
+        e = logf(e < 1e-8f ? 1e-8f : e);
+    }
+    for (int c = lane; c < ccNum; c += 32) {
+        float acc = 0.0f;
+        for (int m = 0; m < num; m++) acc = fmaf(l[m], dctT[(size_t)m * ccStride + c], acc);
+        if (energyType == CepstralEnergy_Replace) c0[c] = c ? acc : e;
+        else if (energyType == CepstralEnergy_Append) { c0[c + 1] = acc; if (!c) c0[0] = e; }
+        else c0[c] = acc;
+    }
+    __syncwarp();
+    const int half = order / 2;
+    float v1 = 0.0f;
+    for (int i = 1; i <= half; i++) v1 += (float)(i * i);
+    for (int i = lane; i < W; i += 32) {
+        float acc = 0.0f;
+        for (int j = 0; j < order && j <= i; j++) acc = acc + ((float)(half - j) / v1) * c0[i - j];
+        c1[i] = acc;
+        coe[row * W + i] = c0[i];
+        d1[row * W + i] = acc;
+    }
+    __syncwarp();
+    for (int i = lane; i < W; i += 32) {
+        float acc = 0.0f;
+        for (int j = 0; j < order && j <= i; j++) acc = acc + ((float)(half - j) / v1) * c1[i - j];
+        d2[row * W + i] = acc;
+    }
+}
+
+// cqtObj_chroma (src/cqt_algorithm.c:484-600): |z|^2 or |z| of each CQT bin, folded onto chroma classes by a 0/1
+// bank [chromaNum][num] (chroma_cqtFilterBank), then per-frame normalisation by max / min / L1 / L2 of |.|
+// (__mnormalize axis 1, src/vector/flux_vector.c:1058-1150; a zero norm leaves the row as it is).  Warp per frame.
+__global__ void k_chroma(const float *__restrict__ re, const float *__restrict__ im, long long rows, int num,
+                         int chromaNum, int isMag, int normType, const float *__restrict__ bank,
+                         float *__restrict__ out) {
+    extern __shared__ float sh[];
+    const int wib = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const long long row = (long long)blockIdx.x * (blockDim.x >> 5) + wib;
+    if (row >= rows) return;
+    float *sv = sh + (size_t)wib * (num + chromaNum), *cv = sv + num;
+    for (int j = lane; j < num; j += 32) {
+        const float a = re[row * num + j], b = im[row * num + j];
+        float v = a * a + b * b;
+        if (isMag) v = sqrtf(v);
+        sv[j] = v;
+    }
+    __syncwarp();
+    float red = 0.0f;
+    int first = 1;
+    for (int c = lane; c < chromaNum; c += 32) {
+        double acc = 0.0;
+        for (int j = 0; j < num; j++) acc += (double)sv[j] * (double)bank[c * num + j];
+        const float v = (float)acc, a = fabsf(v);
+        cv[c] = v;
+        if (normType == ChromaDataNormal_Max) red = first ? a : fmaxf(red, a);
+        else if (normType == ChromaDataNormal_Min) red = first ? a : fminf(red, a);
+        else if (normType == ChromaDataNormal_P2) red += a * a;
+        else red += a;
+        first = 0;
+    }
+    if (first) red = (normType == ChromaDataNormal_Min) ? INFINITY : 0.0f;      /* lanes without a class */
+    for (int o = 16; o > 0; o >>= 1) {
+        const float other = __shfl_xor_sync(0xffffffffu, red, o);
+        if (normType == ChromaDataNormal_Max) red = fmaxf(red, other);
+        else if (normType == ChromaDataNormal_Min) red = fminf(red, other);
+        else red += other;
+    }
+    if (normType == ChromaDataNormal_P2) red = sqrtf(red);
+    __syncwarp();
+    for (int c = lane; c < chromaNum; c += 32) {
+        float v = cv[c];
+        if (normType != ChromaDataNormal_None && red != 0.0f) v = v / red;
+        out[row * chromaNum + c] = v;
+    }
+}
+
+// spectrogramObj_spectrogram's Linear-scale phase (src/spectrogram_algorithm.c:1040-1056): the real part is
+// clamped from below at 1e-16 BEFORE atan2f, so every bin with a negative real part reports +-pi/2.
+__global__ void k_phase(const float *__restrict__ re, const float *__restrict__ im, long long rows, int width,
+                        int lo, int count, float *__restrict__ out) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= rows * count) return;
+    const long long r = i / count;
+    const int k = (int)(i - r * count) + lo;
+    float a = re[r * width + k];
+    if (a < 1e-16f) a = 1e-16f;
+    out[i] = atan2f(im[r * width + k], a);
+}
+
 }  // namespace
 
 extern "C" int af_launch_bank(const AfBankDev *bank, const float *in, int rows, float postPow, float *out, void *stream) {
@@ -137,5 +250,38 @@ extern "C" int af_launch_xxcc(const float *in, int rows, int num, int ccNum, int
     k_xxcc<<<(unsigned)((rows + warps - 1) / warps), warps * 32, smem, (cudaStream_t)stream>>>(
         in, rows, num, ccNum, rectifyType, dctT, num, out);
     AF_LAUNCH_CHECK("k_xxcc");
+    return AF_OK;
+}
+
+extern "C" int af_launch_xxcc_standard(const float *in, const float *energy, int rows, int num, int ccNum,
+                                       int rectifyType, int energyType, int order, const float *dctT,
+                                       float *coe, float *d1, float *d2, void *stream) {
+    if (rows <= 0) return AF_OK;
+    const int warps = 4;
+    size_t smem = sizeof(float) * (size_t)warps * (num + 2 * (num + 1));
+    if (smem > 48 * 1024) return af_fail(AF_ERR_UNSUPPORTED, "xxccStandard: num=%d too large", num);
+    k_xxcc_standard<<<(unsigned)((rows + warps - 1) / warps), warps * 32, smem, (cudaStream_t)stream>>>(
+        in, energy, rows, num, ccNum, rectifyType, energyType, order, dctT, num, coe, d1, d2);
+    AF_LAUNCH_CHECK("k_xxcc_standard");
+    return AF_OK;
+}
+
+extern "C" int af_launch_chroma(const float *re, const float *im, int rows, int num, int chromaNum, int isMag,
+                                int normType, const float *bank, float *out, void *stream) {
+    if (rows <= 0) return AF_OK;
+    const int warps = 8;
+    size_t smem = sizeof(float) * (size_t)warps * (num + chromaNum);
+    if (smem > 48 * 1024) return af_fail(AF_ERR_UNSUPPORTED, "chroma: num=%d too large", num);
+    k_chroma<<<(unsigned)((rows + warps - 1) / warps), warps * 32, smem, (cudaStream_t)stream>>>(
+        re, im, rows, num, chromaNum, isMag, normType, bank, out);
+    AF_LAUNCH_CHECK("k_chroma");
+    return AF_OK;
+}
+
+extern "C" int af_launch_phase(const float *re, const float *im, int rows, int width, int lo, int count, float *out, void *stream) {
+    long long total = (long long)rows * count;
+    if (total <= 0) return AF_OK;
+    k_phase<<<(unsigned)((total + 255) / 256), 256, 0, (cudaStream_t)stream>>>(re, im, rows, width, lo, count, out);
+    AF_LAUNCH_CHECK("k_phase");
     return AF_OK;
 }

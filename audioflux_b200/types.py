@@ -60,6 +60,20 @@ class CepstralRectifyType(Enum):
     CUBIC_ROOT = 1
 
 
+class CepstralEnergyType(Enum):
+    REPLACE = 0
+    APPEND = 1
+    IGNORE = 2
+
+
+class ChromaDataNormalType(Enum):
+    NONE = 0
+    MAX = 1
+    MIN = 2
+    P2 = 3
+    P1 = 4
+
+
 class PaddingPositionType(Enum):
     CENTER = 0
     RIGHT = 1

@@ -1,5 +1,5 @@
 /* afb200_cqt.h -- constant-Q transform.  Replaces /root/reference/src/cqt_algorithm.h:14-62
- * (src/cqt_algorithm.c); chroma/cqcc/cqhc/deconv are "next" rows and not exported yet. */
+ * (src/cqt_algorithm.c).  cqhc / deconv are exported but report "unsupported" (afb200_lastError). */
 #ifndef AFB200_CQT_H
 #define AFB200_CQT_H
 #include "afb200_types.h"
@@ -20,6 +20,14 @@ float *cqtObj_getFreBandArr(CQTObj cqtObj);                       /* :340-343, b
 void cqtObj_setScale(CQTObj cqtObj, int flag);                    /* :458-461 */
 /* :463-478.  mRealArr3/mImageArr3: timeLength x num. */
 void cqtObj_cqt(CQTObj cqtObj, float *dataArr, int dataLength, float *mRealArr3, float *mImageArr3);
+/* :484-600.  Planes of the last cqtObj_cqt call (timeLength x num) -> mDataArr3: timeLength x chromaNum.
+ * Defaults: chromaNum 12 (must divide binPerOctave), dataType Power, normType Max. */
+void cqtObj_chroma(CQTObj cqtObj, int *chromaNum, SpectralDataType *dataType, ChromaDataNormalType *normType,
+                   float *mRealArr1, float *mImageArr1, float *mDataArr3);
+/* :602-660.  mDataArr1: timeLength x num (power or magnitude) -> mDataArr2: timeLength x ccNum. */
+void cqtObj_cqcc(CQTObj cqtObj, float *mDataArr1, int ccNum, CepstralRectifyType *rectifyType, float *mDataArr2);
+void cqtObj_cqhc(CQTObj cqtObj, float *mDataArr1, int hcNum, float *mDataArr2);              /* unsupported */
+void cqtObj_deconv(CQTObj cqtObj, float *mDataArr1, float *mDataArr2, float *mDataArr3);     /* unsupported */
 void cqtObj_free(CQTObj cqtObj);
 
 #ifdef __cplusplus

@@ -18,6 +18,7 @@
 #include "afb200_xxcc.h"
 #include "afb200_cqt.h"
 #include "afb200_cwt.h"
+#include "afb200_spectrogram.h"
 #ifdef __cplusplus
 extern "C" {
 #endif
@@ -42,13 +43,29 @@ int bftObj_bftBatch(BFTObj bftObj, const float *data, int dataLength, int batch,
 /* fused BFT(real mode) -> rectify -> ortho DCT-II -> first ccNum.  out: batch x T x ccNum */
 int bftObj_mfccBatch(BFTObj bftObj, const float *data, int dataLength, int batch, int ccNum,
                      int rectifyType, float *out, int memKind, void *stream);
+/* SpectrogramObj front door: spect batch x T x bandNum (+ phase for the Linear scale, may be NULL);
+ * mfcc = the fused kernel of bftObj_mfccBatch */
+int spectrogramObj_spectrogramBatch(SpectrogramObj spectrogramObj, const float *data, int dataLength, int batch,
+                                    float *spect, float *phase, int memKind, void *stream);
+int spectrogramObj_mfccBatch(SpectrogramObj spectrogramObj, const float *data, int dataLength, int batch, int ccNum,
+                             int rectifyType, float *out, int memKind, void *stream);
 int bftObj_getFilterBankArr(BFTObj bftObj, float *bank /* num x (fftLength/2+1) host */);
 /* in: rows x num; out: rows x ccNum */
 int xxccObj_xxccBatch(XXCCObj xxccObj, const float *in, int rows, int ccNum, int rectifyType,
                       float *out, int memKind, void *stream);
+/* xxccObj_xxccStandard over `rows` frames; energy: rows (NULL allowed when energyType = Ignore);
+ * coe / delta1 / delta2: rows x (ccNum, +1 when energyType = Append) */
+int xxccObj_xxccStandardBatch(XXCCObj xxccObj, const float *in, const float *energy, int rows, int ccNum,
+                              int deltaWindowLength, int energyType, int rectifyType,
+                              float *coe, float *delta1, float *delta2, int memKind, void *stream);
 /* out planes: batch x T x num */
 int cqtObj_cqtBatch(CQTObj cqtObj, const float *data, int dataLength, int batch,
                     float *mReal3, float *mImag3, int memKind, void *stream);
+/* CQT planes rows x num -> rows x chromaNum / rows x ccNum (rows = batch*T) */
+int cqtObj_chromaBatch(CQTObj cqtObj, const float *mReal, const float *mImag, int rows, int chromaNum,
+                       int dataType, int normType, float *out, int memKind, void *stream);
+int cqtObj_cqccBatch(CQTObj cqtObj, const float *in, int rows, int ccNum, int rectifyType, float *out,
+                     int memKind, void *stream);
 int cqtObj_getKernelBank(CQTObj cqtObj, float *kr, float *ki /* binPerOctave x (fftLength/2+1) host */);
 /* data: batch x 2^radix2Exp; out planes: batch x num x 2^radix2Exp */
 int cwtObj_cwtBatch(CWTObj cwtObj, const float *data, int batch, float *mReal4, float *mImag4,
@@ -64,6 +81,8 @@ int afb200_auditoryFilterBank(int num, int fftLength, int samplate, int scaleTyp
                               int normType, float lowFre, float highFre, int binPerOctave,
                               float *bank, float *freBandArr /* num */, int *binBandArr /* num */);
 int afb200_decimatorTaps(float *left32, float *right31);
+/* chroma_cqtFilterBank (src/filterbank/chroma_filterBank.c:176-262): bank num x cqtLength */
+int afb200_chromaCqtFilterBank(int num, int cqtLength, int binPerOctave, float minFre, float *bank);
 
 #ifdef __cplusplus
 }

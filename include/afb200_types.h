@@ -34,6 +34,9 @@ typedef enum { SpectralFilterBankStyle_Slaney = 0, SpectralFilterBankStyle_ETSI,
 typedef enum { SpectralFilterBankNormal_None = 0, SpectralFilterBankNormal_Area,
                SpectralFilterBankNormal_BandWidth } SpectralFilterBankNormalType;
 
+typedef enum { ChromaDataNormal_None = 0, ChromaDataNormal_Max, ChromaDataNormal_Min, ChromaDataNormal_P2,
+               ChromaDataNormal_P1 } ChromaDataNormalType;
+
 typedef enum { CepstralRectify_Log = 0, CepstralRectify_CubicRoot } CepstralRectifyType;
 typedef enum { CepstralEnergy_Replace = 0, CepstralEnergy_Append, CepstralEnergy_Ignore } CepstralEnergyType;
 

@@ -675,3 +675,152 @@ def mfcc(x, sr=48000, radix2_exp=11, hop=512, n_mels=128, cc_num=40, norm=NORM_N
     m = bft(x, n_mels, radix2_exp, sr, hop, W_HANN, SCALE_MEL, STYLE_SLANEY, norm, DATA_POWER,
             result_type=1, bank=bank)
     return xxcc(m, cc_num, RECT_LOG)
+
+
+# ---------------------------------------------------------------------------
+# xxccStandard, CQT chroma / cqcc, SpectrogramObj front door
+# ---------------------------------------------------------------------------
+ENERGY_REPLACE, ENERGY_APPEND, ENERGY_IGNORE = 0, 1, 2
+CHROMA_NORM_NONE, CHROMA_NORM_MAX, CHROMA_NORM_MIN, CHROMA_NORM_P2, CHROMA_NORM_P1 = range(5)
+
+
+def delta_fir(x, order):
+    """`util_delta` (src/util/flux_util.c:803-815): causal FIR with taps b[j] = (m - j) / sum_{i<=m} i^2,
+    j = 0..order-1, m = order//2 (`filterDesign_smooth1`, src/dsp/filterDesign_fir.c:194-217, run through
+    `filterDesign_filter`, :229-248, with the first `order` taps), along the LAST axis."""
+    x = np.asarray(x, dtype=np.float64)
+    m = order // 2
+    v1 = float(sum(i * i for i in range(1, m + 1)))
+    b = np.array([(m - j) / v1 for j in range(order)])
+    y = np.zeros_like(x)
+    n = x.shape[-1]
+    for j in range(min(order, n)):
+        y[..., j:] += b[j] * x[..., :n - j]
+    return y
+
+
+def xxcc_standard(m, energy, cc_num, delta_window_length=9, energy_type=ENERGY_REPLACE, rectify=RECT_LOG):
+    """`xxccObj_xxccStandard` (src/feature/xxcc_algorithm.c:168-296) -> (coe, delta, delta2), each (T, W).
+    The delta FIR runs along the coefficient axis of each frame, as the reference does."""
+    order = delta_window_length if (delta_window_length >= 3 and delta_window_length % 2 == 1) else 9
+    cc = xxcc(m, cc_num, rectify).astype(np.float64)
+    if energy_type != ENERGY_IGNORE:
+        e = np.log(np.maximum(np.asarray(energy, dtype=f32), f32(1e-8)).astype(np.float64))
+    if energy_type == ENERGY_REPLACE:
+        coe = cc.copy()
+        coe[:, 0] = e
+    elif energy_type == ENERGY_APPEND:
+        coe = np.concatenate([e[:, None], cc], axis=1)
+    else:
+        coe = cc
+    coe = coe.astype(f32)
+    d1 = delta_fir(coe, order).astype(f32)
+    d2 = delta_fir(d1, order).astype(f32)
+    return coe, d1, d2
+
+
+def chroma_cqt_bank(num, cqt_length, bpo=12, min_fre=32.703196):
+    """`chroma_cqtFilterBank` (src/filterbank/chroma_filterBank.c:176-262): 0/1 matrix (num, cqt_length)."""
+    if num > bpo or bpo % num != 0:
+        return None
+    n = bpo // num
+    offset = int(math.ceil(n / 2.0))
+    sub = n - offset
+    arr = np.zeros((num, cqt_length), f32)
+    j = np.arange(cqt_length) % bpo
+    arr[0, (j < offset) | ((sub > 0) & (j >= bpo - sub))] = 1
+    for i in range(1, num):
+        start = offset + (i - 1) * n
+        arr[i, (j >= start) & (j < start + n)] = 1
+    midi = int(np.round(f32(12 * math.log2(float(f32(f32(min_fre) / f32(440)))) + 69))) % 12
+    if midi > 6:
+        midi = 12 - midi
+    shift = midi * (num // bpo)
+    return np.roll(arr, -shift, axis=0) if shift else arr
+
+
+def cqt_chroma(re, im, chroma_num=12, data_type=DATA_POWER, norm=CHROMA_NORM_MAX, bpo=12, min_fre=32.703196):
+    """`cqtObj_chroma` (src/cqt_algorithm.c:484-600); normalisation `__mnormalize` axis 1
+    (src/vector/flux_vector.c:1058-1150)."""
+    re = np.asarray(re, dtype=np.float64)
+    im = np.asarray(im, dtype=np.float64)
+    s = (re * re + im * im).astype(f32).astype(np.float64)
+    if data_type == DATA_MAG:
+        s = np.sqrt(s).astype(f32).astype(np.float64)
+    bank = chroma_cqt_bank(chroma_num, re.shape[1], bpo, min_fre).astype(np.float64)
+    out = (s @ bank.T).astype(f32).astype(np.float64)
+    if norm != CHROMA_NORM_NONE:
+        a = np.abs(out)
+        if norm == CHROMA_NORM_MAX:
+            v = a.max(axis=1)
+        elif norm == CHROMA_NORM_MIN:
+            v = a.min(axis=1)
+        elif norm == CHROMA_NORM_P2:
+            v = np.sqrt((a * a).sum(axis=1))
+        else:
+            v = a.sum(axis=1)
+        v = v.astype(f32).astype(np.float64)
+        nz = v != 0
+        out[nz] = out[nz] / v[nz, None]
+    return out.astype(f32)
+
+
+def spectrogram_params(num, sr=32000, low=None, high=None, bpo=12, radix2_exp=12, scale=SCALE_LINEAR):
+    """Parameter rules of `spectrogramObj_new` (src/spectrogram_algorithm.c:326-583) for the scale types on
+    the path -> dict(num, low, high, low_idx, high_idx, bpo)."""
+    n = 1 << radix2_exp
+    if bpo is None or bpo <= 0 or bpo % 12 != 0:
+        bpo = 12
+    if scale == SCALE_LINEAR:
+        lo, hi = f32(0.0), f32(sr / 2.0)
+        if low is not None and 0 <= low < sr / 2.0:
+            lo = f32(low)
+        if high is not None and 0 < high <= sr / 2.0:
+            hi = f32(high)
+        if hi < lo:
+            lo, hi = f32(0.0), f32(sr / 2.0)
+        det = f32(f32(sr) / f32(n))
+        li, hj = int(np.round(f32(lo / det))), int(np.round(f32(hi / det)))
+        return dict(num=hj - li + 1, low=lo, high=hi, low_idx=li, high_idx=hj, bpo=bpo)
+    lo, hi, _, _ = bft_revise_range(num, n, sr, low, high, scale, bpo)
+    return dict(num=num, low=lo, high=hi, low_idx=0, high_idx=0, bpo=bpo)
+
+
+def spectrogram(x, num=0, sr=32000, low=None, high=None, bpo=12, radix2_exp=12, window_type=W_HANN, hop=None,
+                data_type=DATA_POWER, scale=SCALE_LINEAR, style=STYLE_SLANEY, norm=NORM_NONE, norm_value=1.0,
+                want_phase=False, bank=None):
+    """`spectrogramObj_spectrogram` (src/spectrogram_algorithm.c:864-1395) -> spec (T, bandNum)
+    [, phase (T, bandNum), Linear scale only: atan2f(im, max(re, 1e-16)), :1040-1056]."""
+    n = 1 << radix2_exp
+    hop = n // 4 if hop is None or hop <= 0 else hop
+    p = spectrogram_params(num, sr, low, high, bpo, radix2_exp, scale)
+    re, im = stft(x, n, hop, fft_window(window_type, n))
+    re = re[:, :n // 2 + 1].astype(np.float64)
+    im = im[:, :n // 2 + 1].astype(np.float64)
+    s = re * re + im * im
+    if data_type == DATA_MAG:
+        s = np.sqrt(s)
+    elif norm_value != 1:
+        s = np.power(s, norm_value)
+    if scale == SCALE_LINEAR:
+        out = s[:, p["low_idx"]:p["high_idx"] + 1]
+    else:
+        if bank is None:
+            bank, _, _ = auditory_filterbank(p["num"], n, sr, scale, style, norm, p["low"], p["high"], p["bpo"])
+        out = s.astype(f32).astype(np.float64) @ bank.astype(np.float64).T
+    if data_type == DATA_MAG and norm_value != 1:
+        out = np.power(out, norm_value)
+    out = out.astype(f32)
+    if not want_phase or scale != SCALE_LINEAR:
+        return out
+    r = re[:, p["low_idx"]:p["high_idx"] + 1].astype(f32)
+    i = im[:, p["low_idx"]:p["high_idx"] + 1].astype(f32)
+    phase = np.arctan2(i, np.where(r < f32(1e-16), f32(1e-16), r)).astype(f32)
+    return out, phase
+
+
+def spectrogram_linear_bands(sr, radix2_exp, low_idx, num):
+    """`__spectrogramObj_calLinearBandArr` (src/spectrogram_algorithm.c:1909-1941)."""
+    n = 1 << radix2_exp
+    grid = _linspace_f32(f32(0), f32(sr / 2.0), n // 2 + 1)
+    return grid[low_idx:low_idx + num].copy(), np.arange(low_idx, low_idx + num, dtype=np.int32)

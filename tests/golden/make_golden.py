@@ -80,6 +80,29 @@ def main():
     w = af.CWT(36, 11, 48000, wavelet_type=af.WaveletContinueType.MORLET, is_padding=False, _lib=ref)
     wre, wim = w.cwt_planes(xw)
     np.savez_compressed(os.path.join(HERE, "cwt_morlet.npz"), x=xw, re=wre, im=wim, fre=w.get_fre_band_arr())
+    # ---- xxccStandard, CQT chroma / cqcc, SpectrogramObj front door ----
+    E, CN = af.CepstralEnergyType, af.ChromaDataNormalType
+    energy = (mel.sum(axis=1) / 128).astype(np.float32)
+    std = {}
+    for name, et, order in (("rep", E.REPLACE, 9), ("app", E.APPEND, 5), ("ign", E.IGNORE, 3)):
+        coe, d1, d2 = xx.xxcc_standard_planes(mel[:24], energy[:24], 13, order, et)
+        std[f"std_{name}_coe"], std[f"std_{name}_d1"], std[f"std_{name}_d2"] = coe, d1, d2
+    c2 = af.CQT(84, 48000, _lib=ref)
+    cre2, cim2 = c2.cqt_planes(xc)
+    chroma_max = c2.chroma_planes(cre2, cim2, 12, D.POWER, CN.MAX)
+    chroma_p2 = c2.chroma_planes(cre2, cim2, 12, D.MAG, CN.P2)
+    cqcc = c2.cqcc_planes(cre2 * cre2 + cim2 * cim2, 20)
+    xsp = tones(6, 6000, 48000)
+    sl = af.Spectrogram(samplate=48000, low_fre=100., high_fre=8000., radix2_exp=10, slide_length=256, _lib=ref)
+    lin, lin_phase = sl.spectrogram_planes(xsp, True)
+    sm = af.MelSpectrogram(num=64, samplate=48000, radix2_exp=10, slide_length=256, data_type=D.MAG, _lib=ref)
+    sm.set_data_norm_value(0.5)
+    msp = sm.spectrogram_planes(xsp)
+    mcc = sm.mfcc(np.ascontiguousarray(msp.T), 13).T
+    np.savez_compressed(os.path.join(HERE, "next_rows.npz"), energy=energy[:24], chroma_max=chroma_max,
+                        chroma_p2=chroma_p2, cqcc=cqcc, xsp=xsp, lin=lin, lin_phase=lin_phase,
+                        lin_fre=sl.get_fre_band_arr(), lin_bin=sl.get_bin_band_arr(), mel_mag=msp, mel_cc=mcc,
+                        mel_fre=sm.get_fre_band_arr(), **std)
     for f in sorted(os.listdir(HERE)):
         if f.endswith(".npz"):
             print(f, os.path.getsize(os.path.join(HERE, f)))

@@ -1,0 +1,193 @@
+"""CUDA parity of the SURVEY section 8(f) rows -- xxccObj_xxccStandard, cqtObj_chroma / cqtObj_cqcc and the
+SpectrogramObj front door -- through the C ABI: legacy single-clip entry points with host pointers and the
+additive batched entry points with device pointers, against the reference-generated fixture
+(tests/golden/next_rows.npz), the numpy oracle on seeded inputs, and oracle/_ref when it travelled.
+Tolerance |a-b| <= 1e-4 * max|b| per tensor."""
+import numpy as np
+import pytest
+
+import audioflux_b200 as af
+from conftest import noise, rel_max, tones
+from oracle import af_oracle as O
+from test_next_rows_cpu import SPEC_CASES, _phase_mask
+
+pytestmark = pytest.mark.gpu
+
+TOL = 1e-4
+S, ST, N, D = (af.SpectralFilterBankScaleType, af.SpectralFilterBankStyleType,
+               af.SpectralFilterBankNormalType, af.SpectralDataType)
+E, CN = af.CepstralEnergyType, af.ChromaDataNormalType
+
+
+@pytest.fixture(scope="module")
+def torch_cuda(cuda_device):
+    import torch
+    assert torch.cuda.is_available()
+    torch.cuda.set_device(0)
+    return torch
+
+
+# ------------------------------------------------------------------ xxccStandard
+@pytest.mark.parametrize("name,et,order", [("rep", E.REPLACE, 9), ("app", E.APPEND, 5), ("ign", E.IGNORE, 3)])
+def test_xxcc_standard_golden_legacy(cuda_device, golden, name, et, order):
+    g, c1 = golden("next_rows.npz"), golden("c1_mel_mfcc.npz")
+    x = af.XXCC(128)
+    got = x.xxcc_standard_planes(c1["mel"][:24], g["energy"], 13, order, et)
+    for a, key in zip(got, ("coe", "d1", "d2")):
+        want = g[f"std_{name}_{key}"]
+        assert a.shape == want.shape and rel_max(a, want) < TOL
+
+
+@pytest.mark.parametrize("et,order,cc,rect", [(0, 9, 13, 0), (1, 9, 13, 0), (2, 9, 20, 0), (0, 5, 40, 1), (1, 3, 5, 0),
+                                               (0, 4, 13, 0), (1, 11, 64, 0)])
+def test_xxcc_standard_batch_vs_oracle(torch_cuda, et, order, cc, rect):
+    torch = torch_cuda
+    rng = np.random.default_rng(7)
+    m = (rng.random((3, 37, 64)) ** 4 * 10).astype(np.float32)
+    m[0, 3, :5] = 0
+    e = (rng.random((3, 37)) * 3).astype(np.float32)
+    e[1, 2] = 0
+    x = af.XXCC(64)
+    got = x.xxcc_standard_batch(torch.from_numpy(m).cuda(), torch.from_numpy(e).cuda(), cc, order, et, rect)
+    host = x.xxcc_standard_batch(m, e, cc, order, et, rect)
+    for b in range(3):
+        want = O.xxcc_standard(m[b], e[b], cc, order, et, rect)
+        for a, h, w in zip(got, host, want):
+            assert tuple(a.shape) == (3,) + w.shape
+            assert rel_max(a[b].cpu().numpy(), w) < TOL
+            assert np.array_equal(a[b].cpu().numpy(), h[b])            # host and device entry: same kernel
+
+
+def test_xxcc_standard_rejects_missing_energy(cuda_device, product_lib):
+    x = af.XXCC(16)
+    m = np.ones((4, 16), np.float32)
+    outs = [np.zeros((4, 5), np.float32) for _ in range(3)]
+    rc = product_lib.xxccObj_xxccStandardBatch(x._obj, m.ctypes.data, None, 4, 5, 9, 0, 0, outs[0].ctypes.data,
+                                               outs[1].ctypes.data, outs[2].ctypes.data, 0, None)
+    assert rc != 0 and b"energy" in product_lib.afb200_lastError()
+
+
+# ------------------------------------------------------------------ CQT chroma / cqcc
+def test_chroma_cqcc_golden_legacy(cuda_device, golden):
+    g, c = golden("next_rows.npz"), golden("cqt_84.npz")
+    q = af.CQT(84, 48000)
+    re, im = q.cqt_planes(c["x"])                       # sets the object's timeLength like the reference
+    assert rel_max(re, c["re"]) < TOL and rel_max(im, c["im"]) < TOL
+    assert rel_max(q.chroma_planes(re, im, 12, D.POWER, CN.MAX), g["chroma_max"]) < TOL
+    assert rel_max(q.chroma_planes(re, im, 12, D.MAG, CN.P2), g["chroma_p2"]) < TOL
+    assert rel_max(q.cqcc_planes(re * re + im * im, 20), g["cqcc"]) < 2e-4      # error of the CQT itself rides on it
+    # reference-layout front door ([num, T] complex in, [chroma, T] out)
+    z = (re + 1j * im).T
+    assert rel_max(q.chroma(z), g["chroma_max"].T) < TOL
+
+
+@pytest.mark.parametrize("cn,dt,norm,bpo,num", [(12, 0, 1, 12, 84), (12, 1, 3, 12, 84), (12, 0, 0, 12, 84), (12, 0, 2, 12, 84),
+                                                 (12, 1, 4, 12, 84), (12, 0, 1, 24, 96), (24, 0, 1, 24, 96), (6, 1, 3, 12, 48)])
+def test_chroma_cqcc_batch_vs_oracle(torch_cuda, cn, dt, norm, bpo, num):
+    torch = torch_cuda
+    x = np.stack([tones(11, 9000, 32000), noise(12, 9000)])
+    q = af.CQT(num, 32000, bin_per_octave=bpo)
+    re, im = q.cqt_batch(torch.from_numpy(x).cuda())
+    got = q.chroma_batch(re, im, cn, dt, norm).cpu().numpy()
+    p = re * re + im * im
+    cc = q.cqcc_batch(p, 13).cpu().numpy()
+    ren, imn = re.cpu().numpy(), im.cpu().numpy()
+    for b in range(2):
+        assert rel_max(got[b], O.cqt_chroma(ren[b], imn[b], cn, dt, norm, bpo)) < TOL
+        assert rel_max(cc[b], O.xxcc(p[b].cpu().numpy(), 13)) < TOL
+    if norm == 1:
+        assert np.abs(np.abs(got).max(axis=-1) - 1).max() < 1e-6             # max-normalised rows peak at 1
+
+
+def test_chroma_rejects_bad_class_count(cuda_device, product_lib):
+    q = af.CQT(84, 32000)
+    z = np.zeros((4, 84), np.float32)
+    out = np.zeros((4, 5), np.float32)
+    assert product_lib.cqtObj_chromaBatch(q._obj, z.ctypes.data, z.ctypes.data, 4, 5, 0, 1, out.ctypes.data, 0, None) != 0
+    assert b"binPerOctave" in product_lib.afb200_lastError()
+
+
+# ------------------------------------------------------------------ SpectrogramObj front door
+def test_spectrogram_golden_legacy(cuda_device, golden):
+    g = golden("next_rows.npz")
+    x = g["xsp"]
+    sl = af.Spectrogram(samplate=48000, low_fre=100., high_fre=8000., radix2_exp=10, slide_length=256)
+    lin, ph = sl.spectrogram_planes(x, True)
+    assert lin.shape == g["lin"].shape and rel_max(lin, g["lin"]) < TOL
+    m = _phase_mask(g["lin"])
+    assert np.abs(ph - g["lin_phase"])[m].max() < 5e-3
+    assert np.array_equal(sl.get_bin_band_arr(), g["lin_bin"]) and np.array_equal(sl.get_fre_band_arr(), g["lin_fre"])
+    sm = af.MelSpectrogram(num=64, samplate=48000, radix2_exp=10, slide_length=256, data_type=D.MAG)
+    sm.set_data_norm_value(0.5)
+    mel = sm.spectrogram_planes(x)
+    assert rel_max(mel, g["mel_mag"]) < TOL
+    np.testing.assert_allclose(sm.get_fre_band_arr(), g["mel_fre"], rtol=2e-6)
+    cc = sm.mfcc(np.ascontiguousarray(mel.T), 13).T            # uses the timeLength of the spectrogram call
+    assert rel_max(cc, g["mel_cc"]) < TOL
+    assert rel_max(sm.xxcc(np.ascontiguousarray(mel.T), 13).T, g["mel_cc"]) < TOL
+    # reference layout front door: [num, T]
+    assert rel_max(sm.spectrogram(x), g["mel_mag"].T) < TOL
+
+
+@pytest.mark.parametrize("kw", SPEC_CASES)
+def test_spectrogram_batch_vs_oracle(torch_cuda, kw):
+    torch = torch_cuda
+    sr = kw["samplate"]
+    x = np.stack([tones(12, 20000, sr), noise(13, 20000)])
+    scale = af.enum_value(kw.get("filter_bank_type", S.LINEAR))
+    for dt, nv in ((D.POWER, 1.0), (D.MAG, 1.0), (D.POWER, 0.7), (D.MAG, 1.5)):
+        s = af.Spectrogram(data_type=dt, **kw)
+        if nv != 1.0:
+            s.set_data_norm_value(nv)
+        got = s.spectrogram_batch(torch.from_numpy(x).cuda(), scale == 0)
+        host = s.spectrogram_batch(x, scale == 0)
+        for b in range(2):
+            want = O.spectrogram(x[b], kw["num"], sr, kw.get("low_fre"), kw.get("high_fre"), kw.get("bin_per_octave", 12),
+                                 kw["radix2_exp"], hop=kw.get("slide_length"), data_type=af.enum_value(dt), scale=scale,
+                                 style=af.enum_value(kw.get("style_type", ST.SLANEY)),
+                                 norm=af.enum_value(kw.get("normal_type", N.NONE)), norm_value=nv, want_phase=scale == 0)
+            if scale == 0:
+                assert rel_max(got[0][b].cpu().numpy(), want[0]) < TOL
+                m = _phase_mask(want[0])
+                assert np.abs(got[1][b].cpu().numpy() - want[1])[m].max() < 5e-3
+                assert np.array_equal(got[0][b].cpu().numpy(), host[0][b])
+            else:
+                assert rel_max(got[b].cpu().numpy(), want) < TOL
+                assert np.array_equal(got[b].cpu().numpy(), host[b])
+
+
+def test_spectrogram_mfcc_batch_is_the_fused_kernel(torch_cuda, golden):
+    """MelSpectrogram -> mfcc through the front door == bftObj_mfccBatch bit for bit, and == the reference fixture."""
+    torch = torch_cuda
+    g = golden("c1_mel_mfcc.npz")
+    x = torch.from_numpy(np.stack([g["x"], noise(3, 48000)])).cuda()
+    s = af.MelSpectrogram(num=128, samplate=48000, radix2_exp=11, slide_length=512)
+    b = af.BFT(128, 11, 48000, slide_length=512, scale_type=S.MEL, data_type=D.POWER)
+    n0 = af.lib.get_lib().afb200_kernelLaunchCount()
+    a = s.mfcc_batch(x, 40)
+    assert af.lib.get_lib().afb200_kernelLaunchCount() - n0 == 1          # one fused launch
+    assert torch.equal(a, b.mfcc_batch(x, 40))
+    assert rel_max(a[0].cpu().numpy(), g["mfcc"]) < TOL
+    mel = s.spectrogram_batch(x)
+    assert rel_max(mel[0].cpu().numpy(), g["mel"]) < TOL
+
+
+def test_next_rows_against_reference_build(torch_cuda, ref_lib):
+    """Same calls into oracle/_ref (the unmodified reference) and into libaudioflux_b200."""
+    x = tones(21, 24000, 32000)
+    for kw in SPEC_CASES[:8]:
+        xr = tones(22, 24000, kw["samplate"])
+        a, r = af.Spectrogram(**kw), af.Spectrogram(_lib=ref_lib, **kw)
+        assert rel_max(a.spectrogram_planes(xr), r.spectrogram_planes(xr)) < TOL
+    qa, qr = af.CQT(84, 32000), af.CQT(84, 32000, _lib=ref_lib)
+    ra, ia = qa.cqt_planes(x)
+    rr, ir = qr.cqt_planes(x)
+    assert rel_max(qa.chroma_planes(ra, ia), qr.chroma_planes(rr, ir)) < 2e-4
+    pr = rr * rr + ir * ir
+    assert rel_max(qa.cqcc_planes(pr, 13), qr.cqcc_planes(pr, 13)) < TOL
+    m = (np.random.default_rng(5).random((30, 40)) * 4).astype(np.float32)
+    e = (np.random.default_rng(6).random(30) * 2).astype(np.float32)
+    for et in (0, 1, 2):
+        for a, r in zip(af.XXCC(40).xxcc_standard_planes(m, e, 13, 9, et),
+                        af.XXCC(40, _lib=ref_lib).xxcc_standard_planes(m, e, 13, 9, et)):
+            assert rel_max(a, r) < TOL

@@ -1,0 +1,205 @@
+"""SURVEY section 8(f) rows -- xxccStandard, CQT chroma / cqcc, SpectrogramObj front door -- on the CPU:
+the numpy oracle against the committed golden fixture and against oracle/_ref, and the host-side tables /
+parameter rules of libaudioflux_b200 against both.  (The CUDA parity tests are in test_gpu_parity.py.)"""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+import audioflux_b200 as af
+from conftest import noise, tones, rel_max
+from oracle import af_oracle as O
+
+S, ST, N, D = (af.SpectralFilterBankScaleType, af.SpectralFilterBankStyleType,
+               af.SpectralFilterBankNormalType, af.SpectralDataType)
+E, CN = af.CepstralEnergyType, af.ChromaDataNormalType
+TOL = 1e-4
+
+
+# ---------------- oracle vs golden (always runs) ----------------
+@pytest.mark.parametrize("name,et,order", [("rep", 0, 9), ("app", 1, 5), ("ign", 2, 3)])
+def test_oracle_xxcc_standard_golden(golden, name, et, order):
+    g, c1 = golden("next_rows.npz"), golden("c1_mel_mfcc.npz")
+    coe, d1, d2 = O.xxcc_standard(c1["mel"][:24], g["energy"], 13, order, et)
+    for got, key in ((coe, "coe"), (d1, "d1"), (d2, "d2")):
+        want = g[f"std_{name}_{key}"]
+        assert got.shape == want.shape
+        assert rel_max(got, want) < TOL
+
+
+def test_oracle_chroma_cqcc_golden(golden):
+    g, c = golden("next_rows.npz"), golden("cqt_84.npz")
+    assert rel_max(O.cqt_chroma(c["re"], c["im"], 12, O.DATA_POWER, O.CHROMA_NORM_MAX), g["chroma_max"]) < TOL
+    assert rel_max(O.cqt_chroma(c["re"], c["im"], 12, O.DATA_MAG, O.CHROMA_NORM_P2), g["chroma_p2"]) < TOL
+    p = (c["re"].astype(np.float64) ** 2 + c["im"].astype(np.float64) ** 2).astype(np.float32)
+    assert rel_max(O.xxcc(p, 20), g["cqcc"]) < TOL
+
+
+def _phase_mask(re_like_spec):
+    """Bins whose phase is well conditioned: the reference's phase is atan2f(im, max(re, 1e-16)), so wherever
+    re < 0 it degenerates to sign(im)*pi/2 and a bin with |im| at rounding-noise level flips sign freely."""
+    return re_like_spec > 1e-7 * re_like_spec.max()
+
+
+def test_oracle_spectrogram_golden(golden):
+    g = golden("next_rows.npz")
+    x = g["xsp"]
+    lin, ph = O.spectrogram(x, sr=48000, low=100., high=8000., radix2_exp=10, hop=256, want_phase=True)
+    assert lin.shape == g["lin"].shape == (20, 170)
+    assert rel_max(lin, g["lin"]) < TOL
+    m = _phase_mask(g["lin"])
+    assert m.mean() > 0.8
+    assert np.abs(ph - g["lin_phase"])[m].max() < 5e-3
+    p = O.spectrogram_params(0, 48000, 100., 8000., 12, 10, O.SCALE_LINEAR)
+    fre, bins = O.spectrogram_linear_bands(48000, 10, p["low_idx"], p["num"])
+    assert np.array_equal(bins, g["lin_bin"]) and np.array_equal(fre, g["lin_fre"])
+    mel = O.spectrogram(x, 64, 48000, radix2_exp=10, hop=256, data_type=O.DATA_MAG, scale=O.SCALE_MEL, norm_value=0.5)
+    assert rel_max(mel, g["mel_mag"]) < TOL
+    assert rel_max(O.xxcc(g["mel_mag"], 13), g["mel_cc"]) < TOL
+
+
+# ---------------- host tables of the product (no GPU needed) ----------------
+@pytest.mark.parametrize("num,bpo,fmin", [(12, 12, 32.703196), (12, 24, 32.703196), (12, 36, 55.0), (6, 12, 32.703196),
+                                           (24, 24, 65.4), (12, 12, 440.0), (12, 12, 46.25), (12, 12, 61.74)])
+def test_chroma_bank(product_lib, num, bpo, fmin):
+    length = 7 * bpo
+    got = np.zeros((num, length), np.float32)
+    assert product_lib.afb200_chromaCqtFilterBank(num, length, bpo, C.c_float(fmin), got.ctypes.data) == 0
+    assert np.array_equal(got, O.chroma_cqt_bank(num, length, bpo, fmin))
+    assert got.sum() == length                                  # every CQT bin lands in exactly one class
+
+
+def test_chroma_bank_vs_reference(ref_lib):
+    for num, bpo, fmin in [(12, 12, 32.703196), (12, 24, 32.703196), (12, 36, 55.0), (24, 24, 65.4), (12, 12, 440.0),
+                           (12, 12, 46.25), (12, 12, 61.74), (4, 12, 100.0)]:
+        length = 7 * bpo
+        want = np.zeros((num, length), np.float32)
+        ref_lib.chroma_cqtFilterBank(num, length, bpo, C.byref(C.c_float(fmin)), want.ctypes.data)
+        assert np.array_equal(want, O.chroma_cqt_bank(num, length, bpo, fmin)), (num, bpo, fmin)
+
+
+def test_chroma_bank_rejects_bad_division(product_lib):
+    got = np.zeros((5, 84), np.float32)
+    assert product_lib.afb200_chromaCqtFilterBank(5, 84, 12, C.c_float(32.7), got.ctypes.data) != 0
+
+
+SPEC_CASES = [
+    dict(num=0, samplate=48000, low_fre=100., high_fre=8000., radix2_exp=10, slide_length=256),
+    dict(num=0, samplate=32000, radix2_exp=11),
+    dict(num=0, samplate=16000, low_fre=7000., high_fre=300., radix2_exp=9),            # high < low -> full band
+    dict(num=128, samplate=48000, radix2_exp=11, slide_length=512, filter_bank_type=S.MEL),
+    dict(num=64, samplate=32000, radix2_exp=10, filter_bank_type=S.BARK, style_type=ST.ETSI, normal_type=N.AREA),
+    dict(num=40, samplate=16000, radix2_exp=10, filter_bank_type=S.ERB, low_fre=50., high_fre=7000.),
+    dict(num=84, samplate=32000, radix2_exp=12, filter_bank_type=S.OCTAVE),
+    dict(num=48, samplate=32000, radix2_exp=12, filter_bank_type=S.OCTAVE, bin_per_octave=24, low_fre=65.4),
+    dict(num=64, samplate=48000, radix2_exp=11, filter_bank_type=S.LINSPACE, low_fre=1000., high_fre=20000.),
+    dict(num=64, samplate=48000, radix2_exp=11, filter_bank_type=S.LOG, low_fre=32.703196, high_fre=19000.),
+]
+
+
+@pytest.mark.parametrize("kw", SPEC_CASES)
+def test_spectrogram_new_tables_vs_oracle(product_lib, kw):
+    s = af.Spectrogram(**kw)
+    scale = af.enum_value(kw.get("filter_bank_type", S.LINEAR))
+    p = O.spectrogram_params(kw["num"], kw["samplate"], kw.get("low_fre"), kw.get("high_fre"),
+                             kw.get("bin_per_octave", 12), kw["radix2_exp"], scale)
+    assert s.num == p["num"] == s.get_bin_band_length()
+    n = 1 << kw["radix2_exp"]
+    hop = kw.get("slide_length", n // 4)
+    assert s.cal_time_length(10 * n) == (10 * n - n) // hop + 1
+    if scale == 0:
+        fre, bins = O.spectrogram_linear_bands(kw["samplate"], kw["radix2_exp"], p["low_idx"], p["num"])
+        assert np.array_equal(s.get_bin_band_arr(), bins) and np.array_equal(s.get_fre_band_arr(), fre)
+    else:
+        _, fre, bins = O.auditory_filterbank(p["num"], n, kw["samplate"], scale,
+                                             af.enum_value(kw.get("style_type", ST.SLANEY)),
+                                             af.enum_value(kw.get("normal_type", N.NONE)), float(p["low"]), float(p["high"]),
+                                             p["bpo"])
+        assert np.array_equal(s.get_bin_band_arr(), bins)
+        np.testing.assert_allclose(s.get_fre_band_arr(), fre, rtol=2e-6, atol=1e-3)
+
+
+@pytest.mark.parametrize("kw", SPEC_CASES)
+def test_spectrogram_new_tables_vs_reference(product_lib, ref_lib, kw):
+    a, b = af.Spectrogram(**kw), af.Spectrogram(_lib=ref_lib, **kw)
+    assert a.num == b.num
+    assert np.array_equal(a.get_bin_band_arr(), b.get_bin_band_arr())
+    np.testing.assert_allclose(a.get_fre_band_arr(), b.get_fre_band_arr(), rtol=2e-6, atol=1e-3)
+    assert a.cal_time_length(50000) == b.cal_time_length(50000)
+
+
+def test_spectrogram_new_status_codes(product_lib):
+    from audioflux_b200.capi import opt_int
+    obj = C.c_void_p()
+    none = [None] * 12
+    a = list(none); a[4] = opt_int(31)
+    assert product_lib.spectrogramObj_new(C.byref(obj), 128, *a) == -100                 # radix2Exp
+    a = list(none); a[9] = opt_int(2)
+    assert product_lib.spectrogramObj_new(C.byref(obj), 1, *a) == -1                     # num < 2 (mel)
+    assert product_lib.spectrogramObj_new(C.byref(obj), 5000, *a) == -1                  # num > n/2+1
+    a = list(none); a[9] = opt_int(7)
+    assert product_lib.spectrogramObj_new(C.byref(obj), 12, *a) == -2                    # Chroma family: loud
+    assert b"not supported" in product_lib.afb200_lastError()
+    a = list(none); a[7] = opt_int(1)
+    assert product_lib.spectrogramObj_new(C.byref(obj), 12, *a) == -2                    # isContinue
+    a = list(none); a[9] = opt_int(5)
+    assert product_lib.spectrogramObj_new(C.byref(obj), 240, *a) == -1                   # Octave overflow
+    for ctor, args in (("spectrogramObj_newMel", (128, 48000, 11)), ("spectrogramObj_newBark", (64, 32000, 10)),
+                       ("spectrogramObj_newErb", (40, 16000, 10))):
+        assert getattr(product_lib, ctor)(C.byref(obj), *args, None) == 0
+        assert product_lib.spectrogramObj_getBandNum(obj) == args[0]
+        product_lib.spectrogramObj_free(obj)
+    assert product_lib.spectrogramObj_newLinear(C.byref(obj), 32000, 11, None) == 0
+    assert product_lib.spectrogramObj_getBandNum(obj) == 1025
+    product_lib.spectrogramObj_free(obj)
+
+
+# ---------------- oracle vs the reference itself ----------------
+@pytest.mark.parametrize("et,order,cc,rect", [(0, 9, 13, 0), (1, 9, 13, 0), (2, 9, 20, 0), (0, 5, 40, 1), (1, 3, 5, 0),
+                                               (0, 4, 13, 0)])
+def test_xxcc_standard_vs_reference(ref_lib, et, order, cc, rect):
+    rng = np.random.default_rng(7)
+    m = (rng.random((37, 64)) ** 4 * 10).astype(np.float32)
+    m[3, :5] = 0                                              # exercises the 1e-8 floor
+    e = (rng.random(37) * 3).astype(np.float32)
+    e[2] = 0
+    x = af.XXCC(64, _lib=ref_lib)
+    want = x.xxcc_standard_planes(m, e, cc, order, et, rect)
+    got = O.xxcc_standard(m, e, cc, order, et, rect)
+    for g, w in zip(got, want):
+        assert g.shape == w.shape and rel_max(g, w) < TOL
+
+
+@pytest.mark.parametrize("cn,dt,norm,bpo,num", [(12, 0, 1, 12, 84), (12, 1, 3, 12, 84), (12, 0, 0, 12, 84), (12, 0, 2, 12, 84),
+                                                 (12, 1, 4, 12, 84), (12, 0, 1, 24, 96), (24, 0, 1, 24, 96), (6, 1, 3, 12, 48)])
+def test_chroma_cqcc_vs_reference(ref_lib, cn, dt, norm, bpo, num):
+    x = tones(11, 9000, 32000)
+    c = af.CQT(num, 32000, bin_per_octave=bpo, _lib=ref_lib)
+    re, im = c.cqt_planes(x)
+    want = c.chroma_planes(re, im, cn, dt, norm)
+    got = O.cqt_chroma(re, im, cn, dt, norm, bpo)
+    assert rel_max(got, want) < TOL
+    p = (re * re + im * im).astype(np.float32)
+    assert rel_max(O.xxcc(p, 13), c.cqcc_planes(p, 13)) < TOL
+
+
+@pytest.mark.parametrize("kw", SPEC_CASES[:8])
+def test_spectrogram_vs_reference(ref_lib, kw):
+    x = tones(12, 30000, kw["samplate"])
+    for dt, nv in ((D.POWER, 1.0), (D.MAG, 1.0), (D.POWER, 0.7), (D.MAG, 1.5)):
+        s = af.Spectrogram(_lib=ref_lib, data_type=dt, **kw)
+        if nv != 1.0:
+            s.set_data_norm_value(nv)
+        scale = af.enum_value(kw.get("filter_bank_type", S.LINEAR))
+        want = s.spectrogram_planes(x, scale == 0)
+        got = O.spectrogram(x, kw["num"], kw["samplate"], kw.get("low_fre"), kw.get("high_fre"),
+                            kw.get("bin_per_octave", 12), kw["radix2_exp"], hop=kw.get("slide_length"),
+                            data_type=af.enum_value(dt), scale=scale,
+                            style=af.enum_value(kw.get("style_type", ST.SLANEY)),
+                            norm=af.enum_value(kw.get("normal_type", N.NONE)), norm_value=nv, want_phase=scale == 0)
+        if scale == 0:
+            assert rel_max(got[0], want[0]) < TOL
+            m = _phase_mask(want[0])
+            assert np.abs(got[1] - want[1])[m].max() < 5e-3
+        else:
+            assert rel_max(got, want) < TOL
