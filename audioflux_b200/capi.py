@@ -102,6 +102,12 @@ EXTENSION_API = {
     "bftObj_bftBatch": (C.c_int, [vp, vp, C.c_int, C.c_int, vp, vp, C.c_int, vp]),
     "bftObj_mfccBatch": (C.c_int, [vp, vp, C.c_int, C.c_int, C.c_int, C.c_int, vp, C.c_int, vp]),
     "bftObj_getFilterBankArr": (C.c_int, [vp, vp]),
+    "bftObj_mfccBatchScatter": (C.c_int, [vp, vp, C.c_int, C.c_int, C.c_int, C.c_int, vp, C.c_int, P(vp), vp]),
+    "afb200_peerAlloc": (C.c_int, [P(vp), C.c_size_t]),
+    "afb200_peerFree": (C.c_int, [vp]),
+    "afb200_ipcGetHandle": (C.c_int, [vp, vp]),
+    "afb200_ipcOpenHandle": (C.c_int, [vp, P(vp)]),
+    "afb200_ipcCloseHandle": (C.c_int, [vp]),
     "xxccObj_xxccBatch": (C.c_int, [vp, vp, C.c_int, C.c_int, C.c_int, vp, C.c_int, vp]),
     "cqtObj_cqtBatch": (C.c_int, [vp, vp, C.c_int, C.c_int, vp, vp, C.c_int, vp]),
     "cqtObj_getKernelBank": (C.c_int, [vp, vp, vp]),

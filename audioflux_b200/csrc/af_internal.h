@@ -155,7 +155,8 @@ int af_mfcc_plan_build(void **plan, int fftLength, int num, int ccNum, const flo
                        const float *bank, const AfBands *bands, const float *dct, int dataType);
 void af_mfcc_plan_free(void *plan);
 int af_launch_mfcc_fused(void *plan, const float *data, int dataLength, int batch, int timeLength,
-                         int slideLength, int rectifyType, float *out, void *stream);
+                         int slideLength, int rectifyType, float *out, int nPeer, float *const *peerOut,
+                         void *stream);
 
 int af_launch_decimate2(const float *in, int inLength, int inStride, int batch, const float *left32,
                         const float *right31, float *out, int outStride, void *stream);

@@ -296,7 +296,7 @@ int af_bft_phase(BFTObj b, const float *data, int dataLength, int batch, int low
 
 /* ---- fused / composed MFCC: bft(real mode) -> rectify -> ortho DCT-II -> first ccNum ---- */
 static int mfcc_compute(BFTObj b, const float *dData, int dataLength, int batch, int ccNum, int rectifyType,
-                        float *dOut, void *st) {
+                        float *dOut, int nPeer, float *const *peerOut, void *st) {
     const int T = bftObj_calTimeLength(b, dataLength);
     int rc;
     const int fusable = b->normValue == 1.0f && b->scaleType != SpectralFilterBankScale_Linear &&
@@ -313,8 +313,9 @@ static int mfcc_compute(BFTObj b, const float *dData, int dataLength, int batch,
             if (rc) return rc;
             b->mfccPlanCc = ccNum;
         }
-        return af_launch_mfcc_fused(b->mfccPlan, dData, dataLength, batch, T, b->slideLength, rectifyType, dOut, st);
+        return af_launch_mfcc_fused(b->mfccPlan, dData, dataLength, batch, T, b->slideLength, rectifyType, dOut, nPeer, peerOut, st);
     }
+    if (nPeer > 0) return af_fail(AF_ERR_UNSUPPORTED, "bftObj_mfccBatchScatter: only the fused fftLength=2048 path can store to peers");
     /* general composition (any fftLength / bank / alignment), still entirely on the device */
     if (!b->dctReady) {
         const int n = b->num;
@@ -349,15 +350,30 @@ int bftObj_mfccBatch(BFTObj b, const float *data, int dataLength, int batch, int
     void *st = stream ? stream : b->stream;
     if (memKind == AFB200_MEM_DEVICE) {
         st = stream;                      /* NULL = the CUDA default stream */
-        if ((rc = mfcc_compute(b, data, dataLength, batch, ccNum, rectifyType, out, st))) return rc;
+        if ((rc = mfcc_compute(b, data, dataLength, batch, ccNum, rectifyType, out, 0, NULL, st))) return rc;
         return AF_OK;                       /* asynchronous on the caller's stream */
     }
     const size_t inB = sizeof(float) * (size_t)batch * dataLength, outB = sizeof(float) * (size_t)batch * T * ccNum;
     if ((rc = af_devbuf_reserve(&b->dIn, inB)) || (rc = af_devbuf_reserve(&b->dOutRe, outB))) return rc;
     if ((rc = af_memcpy_h2d(b->dIn.ptr, data, inB, st))) return rc;
-    if ((rc = mfcc_compute(b, (const float *)b->dIn.ptr, dataLength, batch, ccNum, rectifyType, (float *)b->dOutRe.ptr, st))) return rc;
+    if ((rc = mfcc_compute(b, (const float *)b->dIn.ptr, dataLength, batch, ccNum, rectifyType, (float *)b->dOutRe.ptr, 0, NULL, st))) return rc;
     if ((rc = af_memcpy_d2h(out, b->dOutRe.ptr, outB, st))) return rc;
     return af_stream_sync(st);
+}
+
+/* MFCC + all-gather in one kernel: device pointers only.  `out` is this GPU's destination, peerOut[0..nPeer) are
+ * the same logical location inside other GPUs' buffers (mapped with afb200_ipcOpenHandle); every finished tile is
+ * stored to all of them from the kernel epilogue.  Asynchronous on `stream`; the caller fences across ranks. */
+int bftObj_mfccBatchScatter(BFTObj b, const float *data, int dataLength, int batch, int ccNum, int rectifyType,
+                            float *out, int nPeer, void **peerOut, void *stream) {
+    if (!b || !data || !out || dataLength <= 0 || batch <= 0 || nPeer < 0 || (nPeer > 0 && !peerOut))
+        return af_fail(AF_ERR_ARG, "bftObj_mfccBatchScatter: bad argument");
+    if (ccNum < 1 || ccNum > b->num) return af_fail(AF_ERR_ARG, "bftObj_mfccBatchScatter: ccNum=%d outside [1, %d]", ccNum, b->num);
+    af_clear_error();
+    int rc = bft_device(b);
+    if (rc) return rc;
+    if (bftObj_calTimeLength(b, dataLength) <= 0) return AF_OK;
+    return mfcc_compute(b, data, dataLength, batch, ccNum, rectifyType, out, nPeer, (float *const *)peerOut, stream);
 }
 
 void bftObj_free(BFTObj b) {

@@ -113,3 +113,33 @@ int af_sm_count(void) {
     if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, d) != cudaSuccess) return 0;
     return n;
 }
+
+/* ---- buffers that other processes (one per GPU) can map: the gathered result of the multi-GPU path ---- */
+int afb200_peerAlloc(void **devPtr, size_t bytes) {
+    if (!devPtr || bytes == 0) return af_fail(AF_ERR_ARG, "afb200_peerAlloc: bad argument");
+    int rc = af_device_ready();
+    if (rc) return rc;
+    *devPtr = NULL;
+    int e = cudaMalloc(devPtr, bytes);          /* plain cudaMalloc: exportable with cudaIpcGetMemHandle at offset 0 */
+    if (e != cudaSuccess) { *devPtr = NULL; return af_fail(AF_ERR_NOMEM, "cudaMalloc(%zu bytes): %s", bytes, cudaGetErrorString((cudaError_t)e)); }
+    return AF_OK;
+}
+int afb200_peerFree(void *devPtr) { return devPtr ? af_cuda_check(cudaFree(devPtr), "cudaFree") : AF_OK; }
+int afb200_ipcGetHandle(void *devPtr, void *handle64) {
+    if (!devPtr || !handle64) return af_fail(AF_ERR_ARG, "afb200_ipcGetHandle: bad argument");
+    cudaIpcMemHandle_t h;
+    int e = cudaIpcGetMemHandle(&h, devPtr);
+    if (e != cudaSuccess) return af_cuda_check(e, "cudaIpcGetMemHandle");
+    memcpy(handle64, &h, sizeof(h));
+    return AF_OK;
+}
+int afb200_ipcOpenHandle(const void *handle64, void **devPtr) {
+    if (!handle64 || !devPtr) return af_fail(AF_ERR_ARG, "afb200_ipcOpenHandle: bad argument");
+    int rc = af_device_ready();
+    if (rc) return rc;
+    cudaIpcMemHandle_t h;
+    memcpy(&h, handle64, sizeof(h));
+    *devPtr = NULL;
+    return af_cuda_check(cudaIpcOpenMemHandle(devPtr, h, cudaIpcMemLazyEnablePeerAccess), "cudaIpcOpenMemHandle");
+}
+int afb200_ipcCloseHandle(void *devPtr) { return devPtr ? af_cuda_check(cudaIpcCloseMemHandle(devPtr), "cudaIpcCloseMemHandle") : AF_OK; }

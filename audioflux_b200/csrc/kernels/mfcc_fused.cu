@@ -55,6 +55,7 @@ constexpr int kEpiWarps = AF_EPI_WARPS;   // DCT epilogue warps; tile `it` is se
 constexpr int kCtasPerSm = AF_CTAS_PER_SM;   // independent CTAs per SM drift apart, so their phases (LSU-heavy load /
                                              // transpose / bank vs FMA-heavy FFT) overlap instead of queueing on one pipe
 constexpr int kThreads = (kFrameWarps + 1 + kEpiWarps) * 32;   // + TMA producer warp + DCT epilogue warps
+constexpr int kMaxPeers = 15;      // extra destinations of the output tile (P2P stores to peer GPUs)
 constexpr int kLPitch = 132;        // log-mel tile row pitch (floats): 4g + t -> 32 distinct banks for mma A fragments
 constexpr int kLRows = kFrameWarps <= 8 ? 8 : 16;   // stored rows of the mma M=16 tile (rows beyond are zeros)
 constexpr int kStages = 2;
@@ -91,6 +92,10 @@ struct Params {
     int melGroups, melWFloats;
     int melGroupLen[4];
     int ccNum, rectify, dataType;
+    // fused all-gather: every finished tile is also stored at the same offset of up to kMaxPeers other buffers
+    // (peer GPUs' gathered arrays mapped over NVLink, opened with cudaIpcOpenMemHandle by the host side)
+    int nPeer;
+    float *peerOut[kMaxPeers];
 };
 
 // shared-memory carve-up (bytes), all 16-byte aligned
@@ -233,18 +238,22 @@ __global__ void __launch_bounds__(kThreads, kCtasPerSm) k_mfcc_fused(Params p) {
                 for (int i = 0; i < 4; i++) acc[n][i] += acx[n][i];
             __syncwarp();
             if (lane == 0) af_mbar_arrive(&lEmpty[buf]);           // tile consumed: frame warps may overwrite it
-            // C fragment: rows g and g+8, columns n*8 + 2t, +1
-            float *o = p.out + ((long long)clip * p.timeLength + f0) * p.ccNum;
+            // C fragment: rows g and g+8, columns n*8 + 2t, +1.  Destination 0 is this GPU's buffer, 1..nPeer the
+            // peers' (posted NVLink stores: the all-gather of the result rides on the epilogue, tile by tile)
+            const long long tileOff = ((long long)clip * p.timeLength + f0) * p.ccNum;
+            for (int d = 0; d <= p.nPeer; d++) {
+                float *o = (d == 0 ? p.out : p.peerOut[d - 1]) + tileOff;
 #pragma unroll
-            for (int n = 0; n < CT; n++) {
-                const int c = n * 8 + 2 * t;
-                if (g < nf) {
-                    if (c < p.ccNum) o[(long long)g * p.ccNum + c] = acc[n][0];
-                    if (c + 1 < p.ccNum) o[(long long)g * p.ccNum + c + 1] = acc[n][1];
-                }
-                if (g + 8 < nf) {
-                    if (c < p.ccNum) o[(long long)(g + 8) * p.ccNum + c] = acc[n][2];
-                    if (c + 1 < p.ccNum) o[(long long)(g + 8) * p.ccNum + c + 1] = acc[n][3];
+                for (int n = 0; n < CT; n++) {
+                    const int c = n * 8 + 2 * t;
+                    if (g < nf) {
+                        if (c < p.ccNum) o[(long long)g * p.ccNum + c] = acc[n][0];
+                        if (c + 1 < p.ccNum) o[(long long)g * p.ccNum + c + 1] = acc[n][1];
+                    }
+                    if (g + 8 < nf) {
+                        if (c < p.ccNum) o[(long long)(g + 8) * p.ccNum + c] = acc[n][2];
+                        if (c + 1 < p.ccNum) o[(long long)(g + 8) * p.ccNum + c + 1] = acc[n][3];
+                    }
                 }
             }
         }
@@ -518,7 +527,8 @@ extern "C" int af_mfcc_plan_build(void **planOut, int fftLength, int num, int cc
 }
 
 extern "C" int af_launch_mfcc_fused(void *plan, const float *data, int dataLength, int batch, int timeLength,
-                                    int slideLength, int rectifyType, float *out, void *stream) {
+                                    int slideLength, int rectifyType, float *out, int nPeer, float *const *peerOut,
+                                    void *stream) {
     Plan *pl = static_cast<Plan *>(plan);
     if (!pl) return af_fail(AF_ERR_ARG, "fused MFCC: no plan");
     if (batch <= 0 || timeLength <= 0) return AF_OK;
@@ -533,6 +543,9 @@ extern "C" int af_launch_mfcc_fused(void *plan, const float *data, int dataLengt
     p.melGroups = pl->melGroups; p.melWFloats = pl->melWFloats;
     for (int g = 0; g < 4; g++) p.melGroupLen[g] = pl->melGroupLen[g];
     p.ccNum = pl->ccNum; p.rectify = rectifyType; p.dataType = pl->dataType;
+    if (nPeer < 0 || nPeer > kMaxPeers || (nPeer > 0 && !peerOut)) return af_fail(AF_ERR_ARG, "fused MFCC: nPeer=%d outside [0, %d]", nPeer, kMaxPeers);
+    p.nPeer = nPeer;
+    for (int d = 0; d < nPeer; d++) p.peerOut[d] = peerOut[d];
 
     // frames per tile: as many as fit the shared-memory budget (<= kFrameWarps)
     const int budget = kCtasPerSm == 1 ? 227 * 1024 : (233472 - kCtasPerSm * 1024) / kCtasPerSm;

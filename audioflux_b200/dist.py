@@ -90,3 +90,105 @@ class OverlappedGather:
                 o.record_stream(self.comm)
         cur.wait_stream(self.comm)
         return self.gathered
+
+
+class _DevArray:
+    """Zero-copy view of a raw device pointer for torch.as_tensor (CUDA array interface v2)."""
+
+    def __init__(self, ptr, shape):
+        self.__cuda_array_interface__ = {"shape": tuple(shape), "typestr": "<f4", "data": (int(ptr), False),
+                                         "version": 2, "strides": None}
+
+
+class PeerScatter:
+    """MFCC + all-gather as ONE kernel (no NCCL on the data path).
+
+    Every rank owns a gathered array (world, B_local, T, cc) allocated by the library (`afb200_peerAlloc`) and
+    exported with `cudaIpcGetMemHandle`; the 64-byte handles travel once through `all_gather_object` and each rank
+    maps the other ranks' arrays (`afb200_ipcOpenHandle`, peer access over NVLink / NVSwitch).  A step then is a
+    single `bftObj_mfccBatchScatter` launch: the kernel's DCT epilogue stores each finished tile into slot `rank`
+    of its own array AND of every peer's array, so the exchange overlaps the transform tile by tile and costs no
+    SMs, no copy engines and no extra launches.  `fence()` orders all ranks' stores before anybody reads
+    (a 4-byte all-reduce on the current stream: a rank's contribution is stream-ordered after its kernel)."""
+
+    def __init__(self, bft, batch_local: int, data_length: int, cc_num: int, rectify_type=0, group=None):
+        import ctypes as C
+        import torch
+        import torch.distributed as dist
+        self.bft, self.group = bft, group
+        self.lib = bft._lib
+        self.world, self.rank = dist.get_world_size(group), dist.get_rank(group)
+        if self.world - 1 > 15:
+            raise ValueError("PeerScatter supports up to 16 ranks")
+        self.B, self.L, self.cc, self.rect = batch_local, data_length, cc_num, int(getattr(rectify_type, "value", rectify_type))
+        self.T = bft.cal_time_length(data_length)
+        self.block = batch_local * self.T * cc_num                      # floats per rank slot
+        nbytes = self.world * self.block * 4
+        self._ptr = C.c_void_p()
+        self._peers = []
+        # every rank takes part in every collective below even if a local step failed, so that a failure
+        # surfaces as the same exception on all ranks instead of a hang
+        err = None
+        handle = (C.c_ubyte * 64)()
+        if self.lib.afb200_peerAlloc(C.byref(self._ptr), nbytes) != 0:
+            err = "afb200_peerAlloc: " + self.lib.afb200_lastError().decode()
+            self._ptr = C.c_void_p()
+        elif self.lib.afb200_ipcGetHandle(self._ptr, handle) != 0:
+            err = "afb200_ipcGetHandle: " + self.lib.afb200_lastError().decode()
+        handles = [None] * self.world
+        dist.all_gather_object(handles, None if err else bytes(handle), group=group)
+        if err is None and all(h is not None for h in handles):
+            for r in range(self.world):
+                if r == self.rank:
+                    continue
+                p = C.c_void_p()
+                buf = (C.c_ubyte * 64).from_buffer_copy(handles[r])
+                if self.lib.afb200_ipcOpenHandle(buf, C.byref(p)) != 0:
+                    err = f"afb200_ipcOpenHandle(rank {r}): " + self.lib.afb200_lastError().decode()
+                    break
+                self._peers.append(p.value)
+        elif err is None:
+            err = "a peer rank could not export its buffer"
+        errs = [None] * self.world
+        dist.all_gather_object(errs, err, group=group)
+        if any(errs):
+            self.close()
+            raise RuntimeError("PeerScatter setup failed: " + "; ".join(f"rank {r}: {e}" for r, e in enumerate(errs) if e))
+        off = self.rank * self.block * 4
+        self._dst = C.c_void_p(self._ptr.value + off)
+        self._peer_arr = (C.c_void_p * max(1, len(self._peers)))(*[C.c_void_p(p + off) for p in self._peers])
+        self.gathered = torch.as_tensor(_DevArray(self._ptr.value, (self.world, batch_local, self.T, cc_num)),
+                                        device=torch.device("cuda", torch.cuda.current_device()))
+        self._flag = torch.zeros(1, dtype=torch.int32, device=self.gathered.device)
+        dist.barrier(group=group)                                        # every rank has mapped every buffer
+
+    def _check(self, rc, what):
+        if rc != 0:
+            raise RuntimeError(f"{what} failed ({rc}): {self.lib.afb200_lastError().decode()}")
+
+    def __call__(self, clips):
+        """clips: this rank's (B_local, L) CUDA tensor.  Launches the fused kernel on the current stream and returns
+        the gathered (world, B_local, T, cc) tensor; call `fence()` before reading other ranks' slots."""
+        import ctypes as C
+        import torch
+        if tuple(clips.shape) != (self.B, self.L) or not clips.is_cuda or clips.dtype != torch.float32 or not clips.is_contiguous():
+            raise ValueError("clips must be a contiguous float32 CUDA tensor of shape (B_local, L)")
+        stream = C.c_void_p(torch.cuda.current_stream().cuda_stream)
+        self._check(self.lib.bftObj_mfccBatchScatter(self.bft._obj, C.c_void_p(clips.data_ptr()), self.L, self.B, self.cc,
+                                                     self.rect, self._dst, len(self._peers), self._peer_arr, stream),
+                    "bftObj_mfccBatchScatter")
+        return self.gathered
+
+    def fence(self):
+        import torch.distributed as dist
+        if self.world > 1:
+            dist.all_reduce(self._flag, group=self.group)
+
+    def close(self):
+        for p in self._peers:
+            self.lib.afb200_ipcCloseHandle(p)
+        self._peers = []
+        self.gathered = None
+        if self._ptr is not None and self._ptr.value:
+            self.lib.afb200_peerFree(self._ptr)
+        self._ptr = None

@@ -8,8 +8,9 @@ One JSON line on stdout from rank 0.
 
 A "step" is one pass of the fused STFT->mel->log->DCT path over one synthetic batch:
   N=1 : BASELINE config 2 = 1024 clips x 5 s (983 MB of samples, larger than the 126 MB L2).
-  N>1 : the same 1024 clips PER GPU (weak scaling, config 5 at N=8) followed by the NCCL all-gather
-        of the (1024, 465, 40) result blocks, which is the path's only exchange step.
+  N>1 : the same 1024 clips PER GPU (weak scaling, config 5 at N=8) with the all-gather of the (1024, 465, 40)
+        result blocks -- the path's only exchange step -- fused into the kernel epilogue as NVLink P2P stores
+        (--gather peer, default) or done by NCCL on a side stream (--gather nccl).
 `value` is device-timed (CUDA events on the launching stream) with inputs resident in HBM;
 `e2e` goes through the public call with pinned HOST buffers, H2D and D2H inside the timed region.
 """
@@ -197,16 +198,34 @@ def run_b200_arm(args):
     bft = af.BFT(NMEL, RADIX, SR, slide_length=HOP, scale_type=S.MEL, data_type=D.POWER)
     g = torch.Generator(device=dev).manual_seed(1234 + 2 + rank)
     x = 0.1 * torch.randn((B, L), generator=g, device=dev, dtype=torch.float32)
-    # N > 1: the batch is cut into chunks; chunk k's NCCL all-gather runs on a side stream while chunk k+1 computes
-    overlap = None
+    # N > 1: the gather of the per-rank results.  Default "peer": ONE kernel per step, whose epilogue stores every
+    # finished tile into all ranks' gathered arrays over NVLink (audioflux_b200/dist.py:PeerScatter), then a 4-byte
+    # all-reduce as the cross-rank fence.  Fallback / comparison "nccl": chunked compute with chunk k's
+    # all_gather_into_tensor on a side stream while chunk k+1 computes (OverlappedGather).
+    overlap = scatter = None
+    gather_mode = "none"
     if world > 1:
-        from audioflux_b200.dist import OverlappedGather
-        overlap = OverlappedGather(chunks=args.gather_chunks)
+        from audioflux_b200.dist import OverlappedGather, PeerScatter
+        gather_mode = args.gather
+        if gather_mode == "peer":
+            try:
+                scatter = PeerScatter(bft, B, L, NCC)
+            except RuntimeError as e:
+                if rank == 0:
+                    print(f"[bench] peer scatter unavailable, using NCCL all-gather: {e}", file=sys.stderr)
+                gather_mode = "nccl"
+        if gather_mode == "nccl":
+            overlap = OverlappedGather(chunks=args.gather_chunks)
 
-    def step():
-        if world > 1:
-            return overlap(lambda c: bft.mfcc_batch(c, NCC), x)
-        return bft.mfcc_batch(x, NCC)
+    def step(inp=None):
+        inp = x if inp is None else inp
+        if scatter is not None:
+            out = scatter(inp)
+            scatter.fence()
+            return out
+        if overlap is not None:
+            return overlap(lambda c: bft.mfcc_batch(c, NCC), inp)
+        return bft.mfcc_batch(inp, NCC)
 
     # parity gate on this very configuration before any timing counts (clip 0 vs the numpy oracle)
     parity = None
@@ -225,6 +244,26 @@ def run_b200_arm(args):
     torch.cuda.synchronize()
     if dist:
         dist.barrier()
+    # gather gate (N > 1): rank 0 regenerates the LAST rank's seeded shard, transforms it locally and compares with
+    # what arrived in its gathered array -- bit for bit (results do not depend on which GPU computed them)
+    gather_ok = None
+    if world > 1 and rank == 0:
+        gl = torch.Generator(device=dev).manual_seed(1234 + 2 + (world - 1))
+        xl = 0.1 * torch.randn((B, L), generator=gl, device=dev, dtype=torch.float32)
+        want_l = bft.mfcc_batch(xl[:8], NCC)
+        res = step()
+        torch.cuda.synchronize()
+        got_l = res[world - 1][:8] if scatter is not None else res[0][(world - 1) * res[0].shape[0] // world:][:8]
+        gather_ok = bool(torch.equal(got_l, want_l))
+        del xl
+    elif world > 1:
+        step()
+        torch.cuda.synchronize()
+    if dist:
+        dist.barrier()
+    if gather_ok is False:
+        print(json.dumps({"error": "gather gate failed: the last rank's block did not arrive intact on rank 0"}))
+        return 1
 
     sampler = ClockSampler(local)
     if rank == 0:
@@ -269,13 +308,15 @@ def run_b200_arm(args):
 
     def e2e_step():
         xd.copy_(xh, non_blocking=True)
-        if world > 1:
-            outs = overlap(lambda c: bft.mfcc_batch(c, NCC), xd)
-            per = outs[0].shape[0] // world
-            for k, o in enumerate(outs):          # this rank's own rows of every gathered chunk -> host
+        res = step(xd)
+        if scatter is not None:                   # this rank's own slot of the gathered array -> host
+            oh.copy_(res[rank], non_blocking=True)
+        elif overlap is not None:
+            per = res[0].shape[0] // world
+            for k, o in enumerate(res):           # this rank's own rows of every gathered chunk -> host
                 oh[k * per:(k + 1) * per].copy_(o[rank * per:(rank + 1) * per], non_blocking=True)
         else:
-            oh.copy_(bft.mfcc_batch(xd, NCC), non_blocking=True)
+            oh.copy_(res, non_blocking=True)
 
     for _ in range(2):
         e2e_step()
@@ -294,6 +335,10 @@ def run_b200_arm(args):
         dist.all_reduce(te, op=dist.ReduceOp.MAX)
     e2e_value = world * B * T / (float(te.item()) / n_e2e * 1e-3)
 
+    if scatter is not None:
+        torch.cuda.synchronize()
+        dist.barrier()                 # nobody unmaps while a peer may still be storing
+        scatter.close()
     if rank != 0:
         if dist:
             dist.destroy_process_group()
@@ -313,7 +358,11 @@ def run_b200_arm(args):
                                "STFT(2048,hop 512,hann)->mel128(slaney)->log10->DCT MFCC(40), fused kernel",
                    "batch_per_gpu": B, "clip_samples": L, "frames_per_clip": T,
                    "l2": "inputs (983 MB per GPU) exceed the 126 MB L2; no explicit flush needed",
-                   "collective": f"nccl all_gather of (B,T,40) per step in {args.gather_chunks} chunks overlapped with compute" if world > 1 else "none",
+                   "collective": {"none": "none",
+                                  "peer": "fused: the kernel epilogue stores each tile into every rank's gathered (world,B,T,40) array "
+                                          "over NVLink P2P (cudaIpc-mapped), then a 4-byte NCCL all-reduce as the cross-rank fence",
+                                  "nccl": f"nccl all_gather of (B,T,40) per step in {args.gather_chunks} chunks overlapped with compute"}[gather_mode],
+                   "gather_gate_bitexact": gather_ok,
                    "parity_rel_err_clip0": parity},
         "clocks": clocks,
         "e2e": {"value": e2e_value, "unit": "frames/s", "h2d_bytes_per_step": B * L * 4, "d2h_bytes_per_step": B * T * NCC * 4,
@@ -344,7 +393,9 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--batch", type=int, default=BATCH_PER_GPU, help="clips per GPU (default: BASELINE config 2)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--gather-chunks", type=int, default=4, help="N>1: chunks per step for compute/all-gather overlap")
+    ap.add_argument("--gather-chunks", type=int, default=4, help="N>1, --gather nccl: chunks per step for compute/all-gather overlap")
+    ap.add_argument("--gather", choices=("peer", "nccl"), default="peer",
+                    help="N>1: 'peer' = all-gather fused into the kernel epilogue (NVLink P2P stores); 'nccl' = overlapped NCCL all-gather")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference_arm(args)

@@ -49,6 +49,18 @@ int spectrogramObj_spectrogramBatch(SpectrogramObj spectrogramObj, const float *
                                     float *spect, float *phase, int memKind, void *stream);
 int spectrogramObj_mfccBatch(SpectrogramObj spectrogramObj, const float *data, int dataLength, int batch, int ccNum,
                              int rectifyType, float *out, int memKind, void *stream);
+/* MFCC + all-gather as ONE kernel (multi-GPU, one process per GPU).  Device pointers only: `out` is this GPU's
+ * destination, peerOut[0..nPeer) (nPeer <= 15) the same logical location inside the other GPUs' gathered buffers,
+ * mapped with afb200_ipcOpenHandle.  The kernel epilogue stores every finished tile to all of them (NVLink P2P
+ * stores), so the exchange overlaps the transform tile by tile; the caller fences across ranks afterwards. */
+int bftObj_mfccBatchScatter(BFTObj bftObj, const float *data, int dataLength, int batch, int ccNum, int rectifyType,
+                            float *out, int nPeer, void **peerOut, void *stream);
+/* cudaMalloc'ed buffers other processes can map (cudaIpc*; handle = 64 opaque bytes) */
+int afb200_peerAlloc(void **devPtr, size_t bytes);
+int afb200_peerFree(void *devPtr);
+int afb200_ipcGetHandle(void *devPtr, void *handle64);
+int afb200_ipcOpenHandle(const void *handle64, void **devPtr);
+int afb200_ipcCloseHandle(void *devPtr);
 int bftObj_getFilterBankArr(BFTObj bftObj, float *bank /* num x (fftLength/2+1) host */);
 /* in: rows x num; out: rows x ccNum */
 int xxccObj_xxccBatch(XXCCObj xxccObj, const float *in, int rows, int ccNum, int rectifyType,
