@@ -187,8 +187,8 @@ def run_b200_arm(args):
         import torch.distributed as dist_
         dist = dist_
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
-            os.environ["NCCL_DEBUG"] = "WARN"          # keep stdout to the single JSON line ("NCCL version ..." goes there)
+        # stdout carries exactly one JSON line: NCCL's own log ("NCCL version ..." at any debug level) goes to a file
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/tmp/afb200_nccl_%h_%p.log")
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     dev = torch.device("cuda", local)
     lib = L_.get_lib()
