@@ -102,6 +102,7 @@ EXTENSION_API = {
     "bftObj_bftBatch": (C.c_int, [vp, vp, C.c_int, C.c_int, vp, vp, C.c_int, vp]),
     "bftObj_mfccBatch": (C.c_int, [vp, vp, C.c_int, C.c_int, C.c_int, C.c_int, vp, C.c_int, vp]),
     "bftObj_getFilterBankArr": (C.c_int, [vp, vp]),
+    "bftObj_mfccPlanMode": (C.c_int, [vp]),
     "bftObj_mfccBatchScatter": (C.c_int, [vp, vp, C.c_int, C.c_int, C.c_int, C.c_int, vp, C.c_int, P(vp), vp]),
     "afb200_peerAlloc": (C.c_int, [P(vp), C.c_size_t]),
     "afb200_peerFree": (C.c_int, [vp]),
@@ -123,6 +124,7 @@ EXTENSION_API = {
     "afb200_auditoryFilterBank": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
                                             C.c_float, C.c_float, C.c_int, vp, vp, vp]),
     "afb200_decimatorTaps": (C.c_int, [vp, vp]),
+    "afb200_mfccIntervalPlan": (C.c_int, [vp, C.c_int, vp, vp, vp, vp, vp, vp, vp, vp]),
     "afb200_chromaCqtFilterBank": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_float, vp]),
 }
 

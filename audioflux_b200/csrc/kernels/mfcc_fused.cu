@@ -62,6 +62,7 @@ constexpr int kStages = 2;
 constexpr int kMaxNum = 128;        // filters (padded)
 constexpr int kScratchFloats = 1152;            // per warp: 33x32 float transpose plane, later Ps[0..1024] + zero pad
 constexpr int kPsPad = 1152;        // Ps[0..1024], zeros up to kPsPad (padded band reads)
+constexpr int kTailMax = 512;       // bins above the last filter's peak (interval mode)
 
 struct Plan {                       // host-side descriptor of the device tables
     float *dWindowHalf;             // 2048, window * 0.5
@@ -74,6 +75,10 @@ struct Plan {                       // host-side descriptor of the device tables
     int melGroups;
     int melWFloats;
     int num, ccNum, ct, dataType;
+    // interval ("shared product") form of a triangular bank, see build_intervals()
+    int melMode;                    // 0: lane per filter over its whole support; 1: lane per interval
+    float *dMelAux;                 // [128 gains][kTailMax tail weights]
+    int tailStart, tailLen;
 };
 
 struct Params {
@@ -91,6 +96,8 @@ struct Params {
     int spanFloats;                 // floats per stage buffer
     int melGroups, melWFloats;
     int melGroupLen[4];
+    int melMode, num, tailStart, tailLen;
+    const float *melAux;
     int ccNum, rectify, dataType;
     // fused all-gather: every finished tile is also stored at the same offset of up to kMaxPeers other buffers
     // (peer GPUs' gathered arrays mapped over NVLink, opened with cudaIpcOpenMemHandle by the host side)
@@ -100,7 +107,7 @@ struct Params {
 
 // shared-memory carve-up (bytes), all 16-byte aligned
 struct Smem {
-    int spanOff, scratchOff, windowOff, tw1Off, tw2Off, melWOff, melStartOff, dctOff, lOff, barOff, total;
+    int spanOff, scratchOff, windowOff, tw1Off, tw2Off, melWOff, melStartOff, melAuxOff, dctOff, lOff, barOff, total;
 };
 
 __host__ __device__ inline Smem carve(int spanFloats, int melWFloats, int ct) {
@@ -112,6 +119,7 @@ __host__ __device__ inline Smem carve(int spanFloats, int melWFloats, int ct) {
     s.tw2Off = o;      o += 32 * 8;
     s.melWOff = o;     o += ((melWFloats * 4 + 15) / 16) * 16;
     s.melStartOff = o; o += kMaxNum * 4;
+    s.melAuxOff = o;   o += (kMaxNum + kTailMax) * 4;
     s.dctOff = o;      o += kMaxNum * (ct <= 5 ? 40 : 72) * 4;
     s.lOff = o;        o += 2 * kLRows * kLPitch * 4;
     s.barOff = o;      o += (2 * kStages + 4) * 8;
@@ -130,6 +138,7 @@ __global__ void __launch_bounds__(kThreads, kCtasPerSm) k_mfcc_fused(Params p) {
     float2 *sTw2 = reinterpret_cast<float2 *>(smem + L.tw2Off);
     float *sMelW = reinterpret_cast<float *>(smem + L.melWOff);
     int *sMelStart = reinterpret_cast<int *>(smem + L.melStartOff);
+    float *sMelAux = reinterpret_cast<float *>(smem + L.melAuxOff);     // interval mode: [128 gains][tail weights]
     float *sDct = reinterpret_cast<float *>(smem + L.dctOff);
     float *sL = reinterpret_cast<float *>(smem + L.lOff);                 // [2][kLRows][kLPitch] log-mel tiles
     uint64_t *fullBar = reinterpret_cast<uint64_t *>(smem + L.barOff);
@@ -146,6 +155,7 @@ __global__ void __launch_bounds__(kThreads, kCtasPerSm) k_mfcc_fused(Params p) {
     for (int i = threadIdx.x; i < 32; i += kThreads) sTw2[i] = p.tw2[i];
     for (int i = threadIdx.x; i < p.melWFloats; i += kThreads) sMelW[i] = p.melW[i];
     for (int i = threadIdx.x; i < kMaxNum; i += kThreads) sMelStart[i] = p.melStart[i];
+    for (int i = threadIdx.x; i < kMaxNum + kTailMax; i += kThreads) sMelAux[i] = p.melMode ? p.melAux[i] : 0.0f;
     for (int i = threadIdx.x; i < kMaxNum * kDctPitch; i += kThreads) sDct[i] = p.dct[i];
     for (int i = threadIdx.x; i < 2 * kLRows * kLPitch; i += kThreads) sL[i] = 0.0f;
     if (threadIdx.x == 0) {
@@ -366,6 +376,57 @@ __global__ void __launch_bounds__(kThreads, kCtasPerSm) k_mfcc_fused(Params p) {
 
         // ---- D: banded filter bank (lane = filter within group, bank-conflict-free starts) + rectify ----
         af_mbar_wait(&lEmpty[lbuf], ((uint32_t)(it >> 1) & 1u) ^ 1u);   // epilogue done with tile it-2
+        if (p.melMode) {
+            // Interval form of a triangular bank (two filters overlap on every bin and their weights there sum to the
+            // filters' gains: fall_m(k) = g_m (1 - r_{m+1}(k))).  Lane j owns interval j = the bins between the peaks
+            // of filters j-1 and j and accumulates A_j = sum r_j P and S_j = sum P ONCE; then
+            //     mel_m = g_m (A_m + (S_{m+1} - A_{m+1})),
+            // i.e. every bin is read and multiplied once instead of twice (half the shared-memory traffic of the
+            // filter-per-lane loop).  Padded slots carry r = 0 and are masked out of S by the (r > 0) test.
+            const float4 *wg4 = reinterpret_cast<const float4 *>(sMelW) + lane;
+            float A[4], U[4];
+#pragma unroll
+            for (int g = 0; g < 4; g++) {
+                A[g] = 0.0f; U[g] = 0.0f;
+                if (g >= p.melGroups) continue;
+                const int len4 = (AF_ABLATE & 1) ? 0 : p.melGroupLen[g] >> 2;
+                const float2 *ps2 = reinterpret_cast<const float2 *>(scratch + sMelStart[g * 32 + lane]);
+                float a0 = 0.0f, a1 = 0.0f, a2 = 0.0f, a3 = 0.0f, s0 = 0.0f, s1 = 0.0f, s2 = 0.0f, s3 = 0.0f;
+                float4 w = wg4[0];
+                float2 p0 = ps2[0], p1 = ps2[1];
+#pragma unroll 2
+                for (int i = 0; i < len4; i++) {
+                    const float4 wn = wg4[(i + 1) * 32];
+                    const float2 q0 = ps2[2 * i + 2], q1 = ps2[2 * i + 3];
+                    a0 = fmaf(p0.x, w.x, a0); s0 = fmaf(p0.x, w.x > 0.0f ? 1.0f : 0.0f, s0);
+                    a1 = fmaf(p0.y, w.y, a1); s1 = fmaf(p0.y, w.y > 0.0f ? 1.0f : 0.0f, s1);
+                    a2 = fmaf(p1.x, w.z, a2); s2 = fmaf(p1.x, w.z > 0.0f ? 1.0f : 0.0f, s2);
+                    a3 = fmaf(p1.y, w.w, a3); s3 = fmaf(p1.y, w.w > 0.0f ? 1.0f : 0.0f, s3);
+                    w = wn; p0 = q0; p1 = q1;
+                }
+                A[g] = (a0 + a1) + (a2 + a3);
+                U[g] = ((s0 + s1) + (s2 + s3)) - A[g];
+                wg4 += len4 * 32;
+            }
+            // tail interval (above the last filter's peak): its falling weights directly, one bin per lane
+            float ut = 0.0f;
+            for (int i = lane; i < p.tailLen; i += 32) ut = fmaf(scratch[p.tailStart + i], sMelAux[kMaxNum + i], ut);
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) ut += __shfl_xor_sync(0xffffffffu, ut, o);
+#pragma unroll
+            for (int g = 0; g < 4; g++) {
+                if (g >= p.melGroups) { lrow[g * 32 + lane] = 0.0f; continue; }
+                float un = __shfl_down_sync(0xffffffffu, U[g], 1);
+                const float nextFirst = __shfl_sync(0xffffffffu, U[g < 3 ? g + 1 : 3], 0);
+                if (lane == 31) un = nextFirst;
+                const int m = g * 32 + lane;
+                if (m + 1 == p.num) un = ut;
+                float v = m < p.num ? sMelAux[m] * (A[g] + un) : 0.0f;
+                if (p.rectify == CepstralRectify_CubicRoot) v = powf(v, 1.0f / 3.0f);
+                else v = __log2f(v < 1e-8f ? 1e-8f : v) * 0.30102999566398120f;
+                lrow[m] = m < p.num ? v : 0.0f;
+            }
+        } else
         {
             // weights: per group [len/4][32 lanes] float4 (LDS.128); P: two LDS.64 per 4 taps (starts are even and
             // spread over distinct 8-byte bank pairs per half-warp by the host planner)
@@ -405,7 +466,7 @@ __global__ void __launch_bounds__(kThreads, kCtasPerSm) k_mfcc_fused(Params p) {
 void free_plan(Plan *pl) {
     if (!pl) return;
     af_dev_free(pl->dWindowHalf); af_dev_free(pl->dTw1); af_dev_free(pl->dTw2);
-    af_dev_free(pl->dMelW); af_dev_free(pl->dMelStart); af_dev_free(pl->dDct);
+    af_dev_free(pl->dMelW); af_dev_free(pl->dMelStart); af_dev_free(pl->dDct); af_dev_free(pl->dMelAux);
     free(pl);
 }
 
@@ -416,31 +477,31 @@ void free_plan(Plan *pl) {
 // where the group's length budget allows, spreads the 16 starts of a half-warp over different 8-byte bank
 // pairs.  The budget is the longest filter of the group (+1 for parity) rounded up to 4 taps, so short groups
 // of adjacent filters accept a 2-way conflict instead of padding; longest filters are placed first.
-static int plan_mel(const AfBands *bands, int num, int *startShifted /* kMaxNum */, int *groupLen /* 4 */) {
+static int plan_rows(const int *rowStart, const int *rowLen, int num, int *startShifted /* kMaxNum */, int *groupLen /* 4 */) {
     int total = 0;
     for (int m = 0; m < kMaxNum; m++) startShifted[m] = 0;
     for (int g = 0; g < 4; g++) groupLen[g] = 0;
     for (int g = 0; g * 32 < num; g++) {
         int gmax = 0;
-        for (int m = g * 32; m < num && m < g * 32 + 32; m++) if (bands->len[m] > gmax) gmax = bands->len[m];
+        for (int m = g * 32; m < num && m < g * 32 + 32; m++) if (rowLen[m] > gmax) gmax = rowLen[m];
         const int cap = (gmax + 1 + 3) & ~3;
         int len = 0;
         for (int h = 0; h < 2; h++) {                         // half-warps: lanes 16h .. 16h+15
             int order[16], cnt = 0, used[16] = {0};
             for (int m = g * 32 + 16 * h; m < num && m < g * 32 + 16 * h + 16; m++) order[cnt++] = m;
             for (int i = 1; i < cnt; i++)
-                for (int j = i; j > 0 && bands->len[order[j]] > bands->len[order[j - 1]]; j--) { int t = order[j]; order[j] = order[j - 1]; order[j - 1] = t; }
+                for (int j = i; j > 0 && rowLen[order[j]] > rowLen[order[j - 1]]; j--) { int t = order[j]; order[j] = order[j - 1]; order[j - 1] = t; }
             for (int i = 0; i < cnt; i++) {
-                const int m = order[i], s0 = bands->start[m];
+                const int m = order[i], s0 = rowStart[m];
                 int best = -1, bestUsed = 1 << 30;
-                for (int d = s0 & 1; d < 34 && s0 - d >= 0 && bands->len[m] + d <= cap; d += 2) {
+                for (int d = s0 & 1; d < 34 && s0 - d >= 0 && rowLen[m] + d <= cap; d += 2) {
                     const int u = used[((s0 - d) >> 1) & 15];
                     if (u < bestUsed) { bestUsed = u; best = d; }
                 }
                 if (best < 0) best = (s0 & 1) && s0 > 0 ? 1 : 0;
                 used[((s0 - best) >> 1) & 15]++;
                 startShifted[m] = s0 - best;
-                if (bands->len[m] + best > len) len = bands->len[m] + best;
+                if (rowLen[m] + best > len) len = rowLen[m] + best;
             }
         }
         len = (len + 3) & ~3;
@@ -448,6 +509,92 @@ static int plan_mel(const AfBands *bands, int num, int *startShifted /* kMaxNum 
         total += len * 32;
     }
     return total + 4 * 32;                                    // one stage of padding for the pipelined prefetch
+}
+
+static int plan_mel(const AfBands *bands, int num, int *startShifted, int *groupLen) {
+    return plan_rows(bands->start, bands->len, num, startShifted, groupLen);
+}
+
+// ---- interval form of a triangular bank ---------------------------------------------------------------------
+// Accepts a bank in which (i) every bin is covered by at most two filters, consecutive ones, and (ii) where filters
+// m-1 and m overlap, bank[m-1][k] / g_{m-1} + bank[m][k] / g_m = 1 (g = per-filter gain of the normalisation; the
+// Slaney and ETSI triangles of auditory_filterBank.c:373-500 have this form by construction).  Then bin k belongs to
+// exactly one interval j(k) (between the peaks of filters j-1 and j) with rising weight r[k] = bank[j][k] / g_j, and
+//     mel_m = g_m ( sum_{I_m} r P  +  sum_{I_{m+1}} (1 - r) P ).
+// Interval `num` (above the last peak) keeps the last filter's own falling weights (tail).  Verified numerically
+// against the actual table with tolerance kTriTol; any violation -> the generic filter-per-lane path is used.
+constexpr float kTriTol = 2e-6f;
+struct Intervals {
+    int start[kMaxNum + 1], len[kMaxNum + 1];
+    float r[kNC + 1];
+    int owner[kNC + 1];             // interval of each bin, -1 = none
+    float tailW[kTailMax];
+    int tailStart, tailLen;
+};
+
+static bool build_intervals(const float *bank, const AfBands *bands, int num, const float *gain, Intervals *iv) {
+    const int width = kNC + 1;
+    if (num < 2 || num > kMaxNum) return false;
+    int peak[kMaxNum];
+    for (int m = 0; m < num; m++) {
+        peak[m] = -1;
+        if (!(gain[m] > 0.0f)) return false;
+        if (bands->len[m] <= 0) continue;                    // a triangle narrower than the bin spacing: no bins, mel = 0
+        int best = bands->start[m];
+        for (int k = bands->start[m]; k < bands->start[m] + bands->len[m]; k++)
+            if (bank[(size_t)m * width + k] > bank[(size_t)m * width + best]) best = k;
+        peak[m] = best;
+    }
+    for (int k = 0; k < width; k++) { iv->r[k] = 0.0f; iv->owner[k] = -1; }
+    int lo = 0;                                              // filters are ordered: first candidate cover of bin k
+    int prevOwner = -1;
+    for (int k = 0; k < width; k++) {
+        int cover[3], nc = 0;
+        while (lo < num && bands->start[lo] + bands->len[lo] <= k) lo++;
+        for (int m = lo; m < num && bands->start[m] <= k && nc < 3; m++)
+            if (k < bands->start[m] + bands->len[m] && bank[(size_t)m * width + k] != 0.0f) cover[nc++] = m;
+        if (nc == 0) continue;
+        if (nc > 2 || (nc == 2 && cover[1] != cover[0] + 1)) return false;
+        int j; float r;
+        if (nc == 2) {
+            const int a = cover[0];
+            j = a + 1;
+            r = bank[(size_t)j * width + k] / gain[j];
+            if (fabsf(bank[(size_t)a * width + k] / gain[a] - (1.0f - r)) > kTriTol) return false;
+        } else {
+            // a bin under one filter only: the filter's centre bin (weight = gain), or the outer flank of the first /
+            // last filter (an inner flank would be shared with the neighbouring filter)
+            const int m = cover[0];
+            const float w = bank[(size_t)m * width + k] / gain[m];
+            if (fabsf(1.0f - w) <= kTriTol) { j = m; r = 1.0f; }
+            else if (m == 0 && k <= peak[0]) { j = 0; r = w; }
+            else if (m == num - 1 && k >= peak[m]) { j = num; r = 1.0f - w; }
+            else return false;
+        }
+        if (!(r > 0.0f) && j < num) r = 1e-30f;
+        if (j < prevOwner) return false;                     // intervals must be runs of consecutive bins
+        prevOwner = j;
+        iv->owner[k] = j;
+        iv->r[k] = r;
+    }
+    for (int j = 0; j <= num; j++) { iv->start[j] = 0; iv->len[j] = 0; }
+    for (int k = 0; k < width; k++) {
+        const int j = iv->owner[k];
+        if (j < 0) continue;
+        if (iv->len[j] == 0) iv->start[j] = k;
+        iv->len[j] = k - iv->start[j] + 1;
+    }
+    iv->tailStart = iv->start[num]; iv->tailLen = iv->len[num];
+    if (iv->tailLen > kTailMax) return false;
+    for (int i = 0; i < kTailMax; i++) iv->tailW[i] = 0.0f;
+    for (int i = 0; i < iv->tailLen; i++) {
+        const int k = iv->tailStart + i;
+        iv->tailW[i] = iv->owner[k] == num ? bank[(size_t)(num - 1) * width + k] / gain[num - 1] : 0.0f;
+    }
+    // empty intervals read (and ignore) the bins where they would sit, keeping the lanes' starts monotone
+    int last = 0;
+    for (int j = 0; j < num; j++) { if (iv->len[j] == 0) iv->start[j] = last; else last = iv->start[j] + iv->len[j]; }
+    return true;
 }
 
 extern "C" int af_mfcc_fused_supported(int fftLength, int num, int ccNum, const AfBands *bands) {
@@ -459,10 +606,11 @@ extern "C" int af_mfcc_fused_supported(int fftLength, int num, int ccNum, const 
 }
 
 extern "C" void af_mfcc_plan_free(void *plan) { free_plan(static_cast<Plan *>(plan)); }
+extern "C" int af_mfcc_plan_mode(void *plan) { return plan ? static_cast<Plan *>(plan)->melMode : -1; }
 
 extern "C" int af_mfcc_plan_build(void **planOut, int fftLength, int num, int ccNum, const float *window,
                                   const float *bank, const AfBands *bands, const float *dct /* ccNum x num */,
-                                  int dataType) {
+                                  int dataType, const float *gain /* num per-filter normalisation gains, or NULL */) {
     *planOut = NULL;
     if (!af_mfcc_fused_supported(fftLength, num, ccNum, bands)) return af_fail(AF_ERR_UNSUPPORTED, "fused MFCC plan: unsupported configuration");
     Plan *pl = static_cast<Plan *>(calloc(1, sizeof(Plan)));
@@ -494,23 +642,65 @@ extern "C" int af_mfcc_plan_build(void **planOut, int fftLength, int num, int cc
     const int width = kNC + 1;
     pl->melGroups = (num + 31) / 32;
     int starts[kMaxNum];
-    const int total = plan_mel(bands, num, starts, pl->melGroupLen);
-    pl->melWFloats = total;
-    float *mw = static_cast<float *>(calloc((size_t)(total > 0 ? total : 1), sizeof(float)));
-    int off = 0;
-    for (int g = 0; g < pl->melGroups; g++) {
-        for (int l = 0; l < 32; l++) {
-            const int m = g * 32 + l;
-            if (m >= num) continue;
-            const int delta = bands->start[m] - starts[m];
-            for (int i = 0; i < bands->len[m]; i++)
-                mw[off + ((i + delta) >> 2) * 128 + l * 4 + ((i + delta) & 3)] = bank[(size_t)m * width + bands->start[m] + i];
+    Intervals *iv = static_cast<Intervals *>(malloc(sizeof(Intervals)));
+    const char *force = getenv("AFB200_MFCC_BANK_MODE");         // "0" forces the filter-per-lane loop (tests, A/B timing)
+    float ones[kMaxNum];
+    for (int m = 0; m < kMaxNum; m++) ones[m] = 1.0f;
+    pl->melMode = 0;
+    if (iv && !(force && force[0] == '0') && build_intervals(bank, bands, num, gain ? gain : ones, iv)) {
+        int glen[4];
+        const int tot = plan_rows(iv->start, iv->len, num, starts, glen);
+        bool fits = tot * 4 <= 24 * 1024;
+        for (int g = 0; g < 4; g++) if (glen[g] + 4 > kPsPad - (kNC + 1)) fits = false;
+        if (fits) {
+            pl->melMode = 1;
+            pl->melWFloats = tot;
+            for (int g = 0; g < 4; g++) pl->melGroupLen[g] = glen[g];
+            pl->tailStart = iv->tailStart; pl->tailLen = iv->tailLen;
         }
-        off += pl->melGroupLen[g] * 32;
     }
-    if (rc == AF_OK) rc = af_dev_upload(reinterpret_cast<void **>(&pl->dMelW), mw, sizeof(float) * (size_t)(total > 0 ? total : 1));
+    if (pl->melMode == 1) {
+        const int total = pl->melWFloats;
+        float *mw = static_cast<float *>(calloc((size_t)total, sizeof(float)));
+        int off = 0;
+        for (int g = 0; g < pl->melGroups; g++) {
+            for (int l = 0; l < 32; l++) {
+                const int j = g * 32 + l;
+                if (j >= num) continue;
+                const int delta = iv->start[j] - starts[j];
+                for (int i = 0; i < iv->len[j]; i++) {
+                    const int k = iv->start[j] + i;
+                    if (iv->owner[k] == j) mw[off + ((i + delta) >> 2) * 128 + l * 4 + ((i + delta) & 3)] = iv->r[k];
+                }
+            }
+            off += pl->melGroupLen[g] * 32;
+        }
+        float aux[kMaxNum + kTailMax];
+        for (int m = 0; m < kMaxNum; m++) aux[m] = m < num ? (gain ? gain[m] : 1.0f) : 0.0f;
+        for (int i = 0; i < kTailMax; i++) aux[kMaxNum + i] = iv->tailW[i];
+        if (rc == AF_OK) rc = af_dev_upload(reinterpret_cast<void **>(&pl->dMelW), mw, sizeof(float) * (size_t)total);
+        if (rc == AF_OK) rc = af_dev_upload(reinterpret_cast<void **>(&pl->dMelAux), aux, sizeof(aux));
+        free(mw);
+    } else {
+        const int total = plan_mel(bands, num, starts, pl->melGroupLen);
+        pl->melWFloats = total;
+        float *mw = static_cast<float *>(calloc((size_t)(total > 0 ? total : 1), sizeof(float)));
+        int off = 0;
+        for (int g = 0; g < pl->melGroups; g++) {
+            for (int l = 0; l < 32; l++) {
+                const int m = g * 32 + l;
+                if (m >= num) continue;
+                const int delta = bands->start[m] - starts[m];
+                for (int i = 0; i < bands->len[m]; i++)
+                    mw[off + ((i + delta) >> 2) * 128 + l * 4 + ((i + delta) & 3)] = bank[(size_t)m * width + bands->start[m] + i];
+            }
+            off += pl->melGroupLen[g] * 32;
+        }
+        if (rc == AF_OK) rc = af_dev_upload(reinterpret_cast<void **>(&pl->dMelW), mw, sizeof(float) * (size_t)(total > 0 ? total : 1));
+        free(mw);
+    }
+    free(iv);
     if (rc == AF_OK) rc = af_dev_upload(reinterpret_cast<void **>(&pl->dMelStart), starts, sizeof(int) * kMaxNum);
-    free(mw);
 
     // DCT table as the mma B operand: D^T[m][c] with row pitch 40 (72 for cc > 40): pitch % 32 == 8 makes the
     // (k0 + t, n0 + g) fragment reads hit 32 different banks; rows m >= num and columns c >= ccNum are zero
@@ -541,6 +731,7 @@ extern "C" int af_launch_mfcc_fused(void *plan, const float *data, int dataLengt
     p.melW = pl->dMelW; p.melStart = pl->dMelStart; p.dct = pl->dDct;
     p.dataStride = dataLength; p.batch = batch; p.timeLength = timeLength; p.hop = slideLength;
     p.melGroups = pl->melGroups; p.melWFloats = pl->melWFloats;
+    p.melMode = pl->melMode; p.num = pl->num; p.tailStart = pl->tailStart; p.tailLen = pl->tailLen; p.melAux = pl->dMelAux;
     for (int g = 0; g < 4; g++) p.melGroupLen[g] = pl->melGroupLen[g];
     p.ccNum = pl->ccNum; p.rectify = rectifyType; p.dataType = pl->dataType;
     if (nPeer < 0 || nPeer > kMaxPeers || (nPeer > 0 && !peerOut)) return af_fail(AF_ERR_ARG, "fused MFCC: nPeer=%d outside [0, %d]", nPeer, kMaxPeers);
@@ -580,4 +771,30 @@ extern "C" int af_launch_mfcc_fused(void *plan, const float *data, int dataLengt
 #undef AF_MFCC_LAUNCH
     AF_LAUNCH_CHECK("k_mfcc_fused");
     return AF_OK;
+}
+
+// Diagnostic / test hook (host only, no device needed): the interval form the planner derives from a bank.
+// Returns 1 when the bank has the triangular two-overlap structure (then owner/r/tail/starts/groupLen are filled), else 0.
+extern "C" int afb200_mfccIntervalPlan(const float *bank, int num, const float *gain, int *owner /* 1025 */,
+                                       float *r /* 1025 */, int *ivStart /* num+1 */, int *ivLen /* num+1 */,
+                                       float *tailW /* 512 */, int *groupLen /* 4 */, int *startShifted /* 128 */) {
+    if (!bank || num < 2 || num > kMaxNum) return 0;
+    AfBands bands;
+    if (af_bands_build(bank, num, kNC + 1, &bands)) return 0;
+    Intervals *iv = static_cast<Intervals *>(malloc(sizeof(Intervals)));
+    float ones[kMaxNum];
+    for (int m = 0; m < kMaxNum; m++) ones[m] = 1.0f;
+    int ok = iv && build_intervals(bank, &bands, num, gain ? gain : ones, iv) ? 1 : 0;
+    if (ok) {
+        for (int k = 0; k <= kNC; k++) { if (owner) owner[k] = iv->owner[k]; if (r) r[k] = iv->r[k]; }
+        for (int j = 0; j <= num; j++) { if (ivStart) ivStart[j] = iv->start[j]; if (ivLen) ivLen[j] = iv->len[j]; }
+        if (tailW) for (int i = 0; i < kTailMax; i++) tailW[i] = iv->tailW[i];
+        int st[kMaxNum], gl[4];
+        plan_rows(iv->start, iv->len, num, st, gl);
+        if (groupLen) for (int g = 0; g < 4; g++) groupLen[g] = gl[g];
+        if (startShifted) for (int m = 0; m < kMaxNum; m++) startShifted[m] = st[m];
+    }
+    free(iv);
+    af_bands_free(&bands);
+    return ok;
 }

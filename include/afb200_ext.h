@@ -61,6 +61,9 @@ int afb200_peerFree(void *devPtr);
 int afb200_ipcGetHandle(void *devPtr, void *handle64);
 int afb200_ipcOpenHandle(const void *handle64, void **devPtr);
 int afb200_ipcCloseHandle(void *devPtr);
+/* diagnostics: bank loop of the fused MFCC plan built by the last bftObj_mfccBatch call
+ * (1 interval / shared-product form of a triangular bank, 0 filter-per-lane, -1 no fused plan) */
+int bftObj_mfccPlanMode(BFTObj bftObj);
 int bftObj_getFilterBankArr(BFTObj bftObj, float *bank /* num x (fftLength/2+1) host */);
 /* in: rows x num; out: rows x ccNum */
 int xxccObj_xxccBatch(XXCCObj xxccObj, const float *in, int rows, int ccNum, int rectifyType,
@@ -93,6 +96,10 @@ int afb200_auditoryFilterBank(int num, int fftLength, int samplate, int scaleTyp
                               int normType, float lowFre, float highFre, int binPerOctave,
                               float *bank, float *freBandArr /* num */, int *binBandArr /* num */);
 int afb200_decimatorTaps(float *left32, float *right31);
+/* planner of the fused MFCC kernel's bank loop (host only): 1 when `bank` (num x 1025) has the triangular
+ * two-overlap structure and the interval form applies; fills the per-bin interval owner / rising weight etc. */
+int afb200_mfccIntervalPlan(const float *bank, int num, const float *gain, int *owner, float *r, int *ivStart,
+                            int *ivLen, float *tailW, int *groupLen, int *startShifted);
 /* chroma_cqtFilterBank (src/filterbank/chroma_filterBank.c:176-262): bank num x cqtLength */
 int afb200_chromaCqtFilterBank(int num, int cqtLength, int binPerOctave, float minFre, float *bank);
 

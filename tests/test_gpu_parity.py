@@ -201,6 +201,49 @@ def test_mfcc_fused_vs_oracle(torch_cuda, hop, cc, norm, dt, rect, L):
         assert rel_max(out[i], want) < TOL, (i, rel_max(out[i], want))
 
 
+@pytest.mark.parametrize("scale,style,norm,num,sr,dt", [(S.MEL, ST.SLANEY, N.NONE, 128, 48000, D.POWER),
+                                                         (S.MEL, ST.SLANEY, N.AREA, 128, 48000, D.POWER),
+                                                         (S.MEL, ST.SLANEY, N.BAND_WIDTH, 128, 48000, D.MAG),
+                                                         (S.BARK, ST.ETSI, N.AREA, 64, 48000, D.POWER),
+                                                         (S.ERB, ST.SLANEY, N.NONE, 128, 48000, D.POWER),
+                                                         (S.MEL, ST.ETSI, N.NONE, 128, 48000, D.POWER),
+                                                         (S.MEL, ST.HANN, N.NONE, 128, 48000, D.POWER),
+                                                         (S.MEL, ST.SLANEY, N.NONE, 40, 16000, D.POWER),
+                                                         (S.ERB, ST.ETSI, N.BAND_WIDTH, 77, 22050, D.MAG)])
+def test_mfcc_fused_bank_loop_modes(torch_cuda, product_lib, monkeypatch, scale, style, norm, num, sr, dt):
+    """The fused kernel has two bank loops: the interval ("shared product") form for triangular banks and the
+    filter-per-lane loop for any banded bank.  Both against the oracle, and against each other."""
+    torch = torch_cuda
+    x = np.stack([tones(31, 20480, sr), noise(32, 20480)])
+    xd = torch.from_numpy(x).cuda()
+    cc = min(20, num)
+    outs = {}
+    for mode in ("1", "0"):
+        monkeypatch.setenv("AFB200_MFCC_BANK_MODE", mode)
+        b = af.BFT(num, 11, sr, slide_length=512, scale_type=scale, style_type=style, normal_type=norm, data_type=dt)
+        outs[mode] = b.mfcc_batch(xd, cc).cpu().numpy()
+        assert product_lib.bftObj_mfccPlanMode(b._obj) == int(mode)         # every bank above has the structure
+    lo, hi, _, _ = O.bft_revise_range(num, 2048, sr, None, None, af.enum_value(scale), 12)
+    bank, _, _ = O.auditory_filterbank(num, 2048, sr, af.enum_value(scale), af.enum_value(style), af.enum_value(norm),
+                                       float(lo), float(hi), 12)
+    for i in range(2):
+        mel = O.bft(x[i], num, 11, sr, 512, scale=af.enum_value(scale), data_type=af.enum_value(dt), bank=bank)
+        want = O.xxcc(mel, cc)
+        assert rel_max(outs["1"][i], want) < TOL
+        assert rel_max(outs["0"][i], want) < TOL
+    assert rel_max(outs["1"], outs["0"]) < 2e-5
+
+
+def test_mfcc_fused_non_triangular_bank_uses_filter_loop(torch_cuda, product_lib):
+    torch = torch_cuda
+    x = noise(33, 20480)
+    b = af.BFT(128, 11, 48000, slide_length=512, scale_type=S.MEL, style_type=ST.RECT, data_type=D.POWER)
+    got = b.mfcc_batch(torch.from_numpy(x[None]).cuda(), 13).cpu().numpy()[0]
+    assert product_lib.bftObj_mfccPlanMode(b._obj) == 0
+    mel = O.bft(x, 128, 11, 48000, 512, scale=O.SCALE_MEL, style=O.STYLE_RECT)
+    assert rel_max(got, O.xxcc(mel, 13)) < TOL
+
+
 def test_mfcc_fused_equals_composed_path(torch_cuda):
     """fused kernel == bft_batch(result_type=1) -> xxcc_batch (general kernels), and other banks
     that fit the fused plan (bark / erb, ETSI) agree with the oracle too."""
