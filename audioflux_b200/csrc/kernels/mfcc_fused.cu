@@ -127,7 +127,7 @@ __host__ __device__ inline Smem carve(int spanFloats, int melWFloats, int ct) {
     return s;
 }
 
-template <int CT>
+template <int CT, int MODE>
 __global__ void __launch_bounds__(kThreads, kCtasPerSm) k_mfcc_fused(Params p) {
     extern __shared__ __align__(128) unsigned char smem[];
     const Smem L = carve(p.spanFloats, p.melWFloats, CT);
@@ -155,7 +155,7 @@ __global__ void __launch_bounds__(kThreads, kCtasPerSm) k_mfcc_fused(Params p) {
     for (int i = threadIdx.x; i < 32; i += kThreads) sTw2[i] = p.tw2[i];
     for (int i = threadIdx.x; i < p.melWFloats; i += kThreads) sMelW[i] = p.melW[i];
     for (int i = threadIdx.x; i < kMaxNum; i += kThreads) sMelStart[i] = p.melStart[i];
-    for (int i = threadIdx.x; i < kMaxNum + kTailMax; i += kThreads) sMelAux[i] = p.melMode ? p.melAux[i] : 0.0f;
+    for (int i = threadIdx.x; i < kMaxNum + kTailMax; i += kThreads) sMelAux[i] = MODE ? p.melAux[i] : 0.0f;
     for (int i = threadIdx.x; i < kMaxNum * kDctPitch; i += kThreads) sDct[i] = p.dct[i];
     for (int i = threadIdx.x; i < 2 * kLRows * kLPitch; i += kThreads) sL[i] = 0.0f;
     if (threadIdx.x == 0) {
@@ -376,7 +376,7 @@ __global__ void __launch_bounds__(kThreads, kCtasPerSm) k_mfcc_fused(Params p) {
 
         // ---- D: banded filter bank (lane = filter within group, bank-conflict-free starts) + rectify ----
         af_mbar_wait(&lEmpty[lbuf], ((uint32_t)(it >> 1) & 1u) ^ 1u);   // epilogue done with tile it-2
-        if (p.melMode) {
+        if (MODE) {
             // Interval form of a triangular bank (two filters overlap on every bin and their weights there sum to the
             // filters' gains: fall_m(k) = g_m (1 - r_{m+1}(k))).  Lane j owns interval j = the bins between the peaks
             // of filters j-1 and j and accumulates A_j = sum r_j P and S_j = sum P ONCE; then
@@ -398,10 +398,11 @@ __global__ void __launch_bounds__(kThreads, kCtasPerSm) k_mfcc_fused(Params p) {
                 for (int i = 0; i < len4; i++) {
                     const float4 wn = wg4[(i + 1) * 32];
                     const float2 q0 = ps2[2 * i + 2], q1 = ps2[2 * i + 3];
-                    a0 = fmaf(p0.x, w.x, a0); s0 = fmaf(p0.x, w.x > 0.0f ? 1.0f : 0.0f, s0);
-                    a1 = fmaf(p0.y, w.y, a1); s1 = fmaf(p0.y, w.y > 0.0f ? 1.0f : 0.0f, s1);
-                    a2 = fmaf(p1.x, w.z, a2); s2 = fmaf(p1.x, w.z > 0.0f ? 1.0f : 0.0f, s2);
-                    a3 = fmaf(p1.y, w.w, a3); s3 = fmaf(p1.y, w.w > 0.0f ? 1.0f : 0.0f, s3);
+                    a0 = fmaf(p0.x, w.x, a0); a1 = fmaf(p0.y, w.y, a1); a2 = fmaf(p1.x, w.z, a2); a3 = fmaf(p1.y, w.w, a3);
+                    if (!(AF_ABLATE & 32)) {
+                        s0 = fmaf(p0.x, w.x > 0.0f ? 1.0f : 0.0f, s0); s1 = fmaf(p0.y, w.y > 0.0f ? 1.0f : 0.0f, s1);
+                        s2 = fmaf(p1.x, w.z > 0.0f ? 1.0f : 0.0f, s2); s3 = fmaf(p1.y, w.w > 0.0f ? 1.0f : 0.0f, s3);
+                    }
                     w = wn; p0 = q0; p1 = q1;
                 }
                 A[g] = (a0 + a1) + (a2 + a3);
@@ -410,15 +411,19 @@ __global__ void __launch_bounds__(kThreads, kCtasPerSm) k_mfcc_fused(Params p) {
             }
             // tail interval (above the last filter's peak): its falling weights directly, one bin per lane
             float ut = 0.0f;
-            for (int i = lane; i < p.tailLen; i += 32) ut = fmaf(scratch[p.tailStart + i], sMelAux[kMaxNum + i], ut);
+            if (!(AF_ABLATE & 64)) for (int i = lane; i < p.tailLen; i += 32) ut = fmaf(scratch[p.tailStart + i], sMelAux[kMaxNum + i], ut);
+            if (!(AF_ABLATE & 64))
 #pragma unroll
-            for (int o = 16; o > 0; o >>= 1) ut += __shfl_xor_sync(0xffffffffu, ut, o);
+                for (int o = 16; o > 0; o >>= 1) ut += __shfl_xor_sync(0xffffffffu, ut, o);
 #pragma unroll
             for (int g = 0; g < 4; g++) {
                 if (g >= p.melGroups) { lrow[g * 32 + lane] = 0.0f; continue; }
-                float un = __shfl_down_sync(0xffffffffu, U[g], 1);
-                const float nextFirst = __shfl_sync(0xffffffffu, U[g < 3 ? g + 1 : 3], 0);
-                if (lane == 31) un = nextFirst;
+                float un = U[g];
+                if (!(AF_ABLATE & 64)) {
+                    un = __shfl_down_sync(0xffffffffu, U[g], 1);
+                    const float nextFirst = __shfl_sync(0xffffffffu, U[g < 3 ? g + 1 : 3], 0);
+                    if (lane == 31) un = nextFirst;
+                }
                 const int m = g * 32 + lane;
                 if (m + 1 == p.num) un = ut;
                 float v = m < p.num ? sMelAux[m] * (A[g] + un) : 0.0f;
@@ -643,11 +648,15 @@ extern "C" int af_mfcc_plan_build(void **planOut, int fftLength, int num, int cc
     pl->melGroups = (num + 31) / 32;
     int starts[kMaxNum];
     Intervals *iv = static_cast<Intervals *>(malloc(sizeof(Intervals)));
-    const char *force = getenv("AFB200_MFCC_BANK_MODE");         // "0" forces the filter-per-lane loop (tests, A/B timing)
+    // The interval loop is opt-in (AFB200_MFCC_BANK_MODE=1): it halves the bank loop's shared-memory traffic, but on
+    // B200 it measured SLOWER (2.01 ms vs 1.78 ms at config 2, profiles/r1_bankmode_ablation.txt): the kernel is bound by
+    // the latency of queued MIO operations per warp, and the interval form adds a serial tail (warp reduction of the
+    // last interval + neighbour exchange by shuffles, 0.29 ms) that outweighs the shorter loop (0.43 vs 0.49 ms).
+    const char *force = getenv("AFB200_MFCC_BANK_MODE");
     float ones[kMaxNum];
     for (int m = 0; m < kMaxNum; m++) ones[m] = 1.0f;
     pl->melMode = 0;
-    if (iv && !(force && force[0] == '0') && build_intervals(bank, bands, num, gain ? gain : ones, iv)) {
+    if (iv && force && force[0] == '1' && build_intervals(bank, bands, num, gain ? gain : ones, iv)) {
         int glen[4];
         const int tot = plan_rows(iv->start, iv->len, num, starts, glen);
         bool fits = tot * 4 <= 24 * 1024;
@@ -758,16 +767,18 @@ extern "C" int af_launch_mfcc_fused(void *plan, const float *data, int dataLengt
     long long grid = p.totalTiles < (long long)sms * kCtasPerSm ? p.totalTiles : (long long)sms * kCtasPerSm;
     cudaStream_t st = (cudaStream_t)stream;
     cudaError_t e = cudaSuccess;
-#define AF_MFCC_LAUNCH(CT_)                                                                              \
-    e = cudaFuncSetAttribute(k_mfcc_fused<CT_>, cudaFuncAttributeMaxDynamicSharedMemorySize, smemBytes);  \
-    if (e != cudaSuccess) return af_cuda_check(e, "cudaFuncSetAttribute(k_mfcc_fused)");                 \
-    k_mfcc_fused<CT_><<<(unsigned)grid, kThreads, smemBytes, st>>>(p)
+#define AF_MFCC_LAUNCH2(CT_, MODE_)                                                                               \
+    e = cudaFuncSetAttribute(k_mfcc_fused<CT_, MODE_>, cudaFuncAttributeMaxDynamicSharedMemorySize, smemBytes);  \
+    if (e != cudaSuccess) return af_cuda_check(e, "cudaFuncSetAttribute(k_mfcc_fused)");                          \
+    k_mfcc_fused<CT_, MODE_><<<(unsigned)grid, kThreads, smemBytes, st>>>(p)
+#define AF_MFCC_LAUNCH(CT_) if (pl->melMode) { AF_MFCC_LAUNCH2(CT_, 1); } else { AF_MFCC_LAUNCH2(CT_, 0); }
     switch (pl->ct) {
     case 2: AF_MFCC_LAUNCH(2); break;
     case 3: AF_MFCC_LAUNCH(3); break;
     case 5: AF_MFCC_LAUNCH(5); break;
     default: AF_MFCC_LAUNCH(8); break;
     }
+#undef AF_MFCC_LAUNCH2
 #undef AF_MFCC_LAUNCH
     AF_LAUNCH_CHECK("k_mfcc_fused");
     return AF_OK;
