@@ -106,7 +106,9 @@ typedef struct {
     int dataLength;       /* samples per clip */
     int timeLength;       /* frames per clip */
     int batch;
-    int padLeft;          /* zeros logically prepended (CQT centre padding) */
+    int padLeft;          /* samples logically prepended (CQT / STFT padding) */
+    int padMode;          /* PaddingMode_Constant (0) | Reflect | Wrap: content of the logical samples outside the clip */
+    float padValue1, padValue2;   /* constant mode: value left / right of the clip (0 for CQT) */
     int validLength;      /* samples of the clip actually used (dataLength minus dropped tail) */
     const float *window;  /* device, fftLength (NULL = rect) */
     const float *data;    /* device, batch x dataLength */

@@ -101,12 +101,15 @@ static int stft_frame_src(STFTObj s, int dataLength, int batch, AfFrameSrc *src)
     src->validLength = dataLength;
     src->window = s->useWindow ? s->dWindow : NULL;
     if (s->isPad) {
-        if (s->mode != PaddingMode_Constant || s->padValue1 != 0.0f || s->padValue2 != 0.0f)
-            return af_fail(AF_ERR_UNSUPPORTED, "STFT padding: only constant zero padding is supported (reflect/wrap/non-zero are not)");
-        /* the tail that does not fill a hop is dropped when more than one frame exists (stft_algorithm.c:813-826) */
+        /* the tail that does not fill a hop is dropped when more than one frame exists (stft_algorithm.c:813-826);
+         * then fftLength samples are added: n/2 + n/2 (Center), n left (Left) or n right (Right), holding a constant,
+         * the mirror image or the periodic extension of the kept samples (__stftObj_dealPadData, :583-694) */
         if (src->timeLength > 1) src->validLength = dataLength - dataLength % s->slideLength;
         src->padLeft = s->position == PaddingPosition_Center ? s->fftLength / 2
                      : s->position == PaddingPosition_Left ? s->fftLength : 0;
+        src->padMode = s->mode;
+        if (s->position == PaddingPosition_Center) { src->padValue1 = s->padValue1; src->padValue2 = s->padValue2; }
+        else src->padValue1 = src->padValue2 = (float)(int)s->padValue1;   /* __vpad_left1/right1 take an int (:641-652) */
     }
     return AF_OK;
 }

@@ -25,7 +25,7 @@
 //     per-filter start bins are shifted down (host planner) until the 32 lanes of a group read 32
 //     different banks -> conflict-free;
 //   * DCT-II is the one dense GEMM-shaped piece ([frames x 128] . [128 x cc]): the frame warps drop their
-//     log-mel rows into a double-buffered 16 x 128 shared tile and a dedicated epilogue warp contracts the
+//     log-mel rows into a multi-buffered (kLBufs) 16 x 128 shared tile and a dedicated epilogue warp contracts the
 //     whole tile on the tensor cores (mma.sync m16n8k8 TF32, 3xTF32 split so the result keeps fp32 accuracy)
 //     while the frame warps are already transforming the next tile.
 #include <math.h>
@@ -59,6 +59,11 @@ constexpr int kMaxPeers = 15;      // extra destinations of the output tile (P2P
 constexpr int kLPitch = 132;        // log-mel tile row pitch (floats): 4g + t -> 32 distinct banks for mma A fragments
 constexpr int kLRows = kFrameWarps <= 8 ? 8 : 16;   // stored rows of the mma M=16 tile (rows beyond are zeros)
 constexpr int kStages = 2;
+#ifndef AF_LBUFS
+#define AF_LBUFS 3
+#endif
+constexpr int kLBufs = AF_LBUFS;    // log-mel tiles in flight between the frame warps and the DCT epilogue (2 measured 4 % of
+                                    // frame-warp time waiting for the epilogue, profiles/r1_final_hotspots.txt)
 constexpr int kMaxNum = 128;        // filters (padded)
 constexpr int kScratchFloats = 1152;            // per warp: 33x32 float transpose plane, later Ps[0..1024] + zero pad
 constexpr int kPsPad = 1152;        // Ps[0..1024], zeros up to kPsPad (padded band reads)
@@ -121,8 +126,8 @@ __host__ __device__ inline Smem carve(int spanFloats, int melWFloats, int ct) {
     s.melStartOff = o; o += kMaxNum * 4;
     s.melAuxOff = o;   o += (kMaxNum + kTailMax) * 4;
     s.dctOff = o;      o += kMaxNum * (ct <= 5 ? 40 : 72) * 4;
-    s.lOff = o;        o += 2 * kLRows * kLPitch * 4;
-    s.barOff = o;      o += (2 * kStages + 4) * 8;
+    s.lOff = o;        o += kLBufs * kLRows * kLPitch * 4;
+    s.barOff = o;      o += (2 * kStages + 2 * kLBufs) * 8;
     s.total = o;
     return s;
 }
@@ -140,11 +145,11 @@ __global__ void __launch_bounds__(kThreads, kCtasPerSm) k_mfcc_fused(Params p) {
     int *sMelStart = reinterpret_cast<int *>(smem + L.melStartOff);
     float *sMelAux = reinterpret_cast<float *>(smem + L.melAuxOff);     // interval mode: [128 gains][tail weights]
     float *sDct = reinterpret_cast<float *>(smem + L.dctOff);
-    float *sL = reinterpret_cast<float *>(smem + L.lOff);                 // [2][kLRows][kLPitch] log-mel tiles
+    float *sL = reinterpret_cast<float *>(smem + L.lOff);                 // [kLBufs][kLRows][kLPitch] log-mel tiles
     uint64_t *fullBar = reinterpret_cast<uint64_t *>(smem + L.barOff);
     uint64_t *emptyBar = fullBar + kStages;
-    uint64_t *lFull = emptyBar + kStages;                                  // [2] frame warps -> epilogue
-    uint64_t *lEmpty = lFull + 2;                                          // [2] epilogue -> frame warps
+    uint64_t *lFull = emptyBar + kStages;                                  // [kLBufs] frame warps -> epilogue
+    uint64_t *lEmpty = lFull + kLBufs;                                     // [kLBufs] epilogue -> frame warps
     constexpr int kDctPitch = CT <= 5 ? 40 : 72;
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -157,10 +162,10 @@ __global__ void __launch_bounds__(kThreads, kCtasPerSm) k_mfcc_fused(Params p) {
     for (int i = threadIdx.x; i < kMaxNum; i += kThreads) sMelStart[i] = p.melStart[i];
     for (int i = threadIdx.x; i < kMaxNum + kTailMax; i += kThreads) sMelAux[i] = MODE ? p.melAux[i] : 0.0f;
     for (int i = threadIdx.x; i < kMaxNum * kDctPitch; i += kThreads) sDct[i] = p.dct[i];
-    for (int i = threadIdx.x; i < 2 * kLRows * kLPitch; i += kThreads) sL[i] = 0.0f;
+    for (int i = threadIdx.x; i < kLBufs * kLRows * kLPitch; i += kThreads) sL[i] = 0.0f;
     if (threadIdx.x == 0) {
         for (int s = 0; s < kStages; s++) { af_mbar_init(&fullBar[s], 1); af_mbar_init(&emptyBar[s], kFrameWarps); }
-        for (int s = 0; s < 2; s++) { af_mbar_init(&lFull[s], kFrameWarps); af_mbar_init(&lEmpty[s], 1); }
+        for (int s = 0; s < kLBufs; s++) { af_mbar_init(&lFull[s], kFrameWarps); af_mbar_init(&lEmpty[s], 1); }
         af_fence_barrier_init();
     }
     __syncthreads();
@@ -196,11 +201,11 @@ __global__ void __launch_bounds__(kThreads, kCtasPerSm) k_mfcc_fused(Params p) {
         int it = 0;
         for (long long tile = blockIdx.x; tile < p.totalTiles; tile += gridDim.x, ++it) {
             if (it % kEpiWarps != epi) continue;
-            const int buf = it & 1;
+            const int buf = it % kLBufs;
             const long long clip = tile / p.tilesPerClip;
             const int f0 = (int)(tile % p.tilesPerClip) * F;
             const int nf = min(F, p.timeLength - f0);
-            af_mbar_wait_sleepy(&lFull[buf], (uint32_t)(it >> 1) & 1u);
+            af_mbar_wait_sleepy(&lFull[buf], (uint32_t)(it / kLBufs) & 1u);
             const float *A = sL + (size_t)buf * kLRows * kLPitch;
             // two accumulator sets (hi*hi and the two cross terms) and term-major issue order: consecutive HMMAs
             // never touch the same accumulator, so the in-order warp is not serialised on the mma latency
@@ -297,12 +302,12 @@ __global__ void __launch_bounds__(kThreads, kCtasPerSm) k_mfcc_fused(Params p) {
         }
         __syncwarp();
         if (lane == 0) af_mbar_arrive(&emptyBar[stage]);     // span slot may be refilled
-        const int lbuf = it & 1;
+        const int lbuf = it % kLBufs;
         float *lrow = sL + ((size_t)lbuf * kLRows + warp) * kLPitch;
         if (!active) {
             // keep the log-mel tile protocol in step: one arrival per warp per tile, never before the
             // epilogue released this buffer (tile it-2), else an early arrival would complete the wrong phase
-            af_mbar_wait(&lEmpty[lbuf], ((uint32_t)(it >> 1) & 1u) ^ 1u);
+            af_mbar_wait(&lEmpty[lbuf], ((uint32_t)(it / kLBufs) & 1u) ^ 1u);
             if (lane == 0) af_mbar_arrive(&lFull[lbuf]);
             continue;
         }
@@ -375,7 +380,7 @@ __global__ void __launch_bounds__(kThreads, kCtasPerSm) k_mfcc_fused(Params p) {
         __syncwarp();
 
         // ---- D: banded filter bank (lane = filter within group, bank-conflict-free starts) + rectify ----
-        af_mbar_wait(&lEmpty[lbuf], ((uint32_t)(it >> 1) & 1u) ^ 1u);   // epilogue done with tile it-2
+        af_mbar_wait(&lEmpty[lbuf], ((uint32_t)(it / kLBufs) & 1u) ^ 1u);   // epilogue done with tile it-kLBufs
         if (MODE) {
             // Interval form of a triangular bank (two filters overlap on every bin and their weights there sum to the
             // filters' gains: fall_m(k) = g_m (1 - r_{m+1}(k))).  Lane j owns interval j = the bins between the peaks
@@ -441,7 +446,8 @@ __global__ void __launch_bounds__(kThreads, kCtasPerSm) k_mfcc_fused(Params p) {
                 const float2 *ps2 = reinterpret_cast<const float2 *>(scratch + sMelStart[g * 32 + lane]);
                 float acc0 = 0.0f, acc1 = 0.0f, acc2 = 0.0f, acc3 = 0.0f;
                 // software pipelined: the loads of stage i+1 are in flight while stage i is accumulated
-                // (the final prefetch over-reads one stage: the tables carry one stage of padding)
+                // (the final prefetch over-reads one stage: the tables carry the padding).  A two-stage-deep
+                // pipeline was measured slower (1.93 vs 1.78 ms: 128 registers, longer prologue per group).
                 float4 w = wg4[0];
                 float2 p0 = ps2[0], p1 = ps2[1];
 #pragma unroll 2
@@ -513,7 +519,7 @@ static int plan_rows(const int *rowStart, const int *rowLen, int num, int *start
         groupLen[g] = len;
         total += len * 32;
     }
-    return total + 4 * 32;                                    // one stage of padding for the pipelined prefetch
+    return total + 8 * 32;                                    // two stages of padding for the pipelined prefetch
 }
 
 static int plan_mel(const AfBands *bands, int num, int *startShifted, int *groupLen) {
@@ -606,7 +612,7 @@ extern "C" int af_mfcc_fused_supported(int fftLength, int num, int ccNum, const 
     if (fftLength != kN || num < 1 || num > kMaxNum || ccNum < 1 || ccNum > 64 || !bands) return 0;
     int starts[kMaxNum], groupLen[4];
     const int floats = plan_mel(bands, num, starts, groupLen);
-    for (int g = 0; g < 4; g++) if (groupLen[g] + 4 > kPsPad - (kNC + 1)) return 0;   // padded (and prefetched) reads stay inside the zero pad
+    for (int g = 0; g < 4; g++) if (groupLen[g] + 8 > kPsPad - (kNC + 1)) return 0;   // padded (and prefetched) reads stay inside the zero pad
     return floats * 4 <= 24 * 1024;                              // weight table budget in shared memory
 }
 
@@ -660,7 +666,7 @@ extern "C" int af_mfcc_plan_build(void **planOut, int fftLength, int num, int cc
         int glen[4];
         const int tot = plan_rows(iv->start, iv->len, num, starts, glen);
         bool fits = tot * 4 <= 24 * 1024;
-        for (int g = 0; g < 4; g++) if (glen[g] + 4 > kPsPad - (kNC + 1)) fits = false;
+        for (int g = 0; g < 4; g++) if (glen[g] + 8 > kPsPad - (kNC + 1)) fits = false;
         if (fits) {
             pl->melMode = 1;
             pl->melWFloats = tot;

@@ -21,6 +21,8 @@ struct StftParams {
     long long dataStride;   // floats between clips
     int n, nc, log2nc;
     int hop, timeLength, padLeft, validLength;
+    int padMode;            // PaddingMode_Constant | Reflect | Wrap for samples outside [0, validLength)
+    float padValue1, padValue2;   // constant mode: value left / right of the data
     int mode;
     float normValue;
 };
@@ -31,6 +33,21 @@ __device__ __forceinline__ float2 twiddle(int k, int m) {   // exp(-2 pi i k / m
     return make_float2(c, s);
 }
 
+// sample s of the logical (padded) signal of one clip: x[0:valid] with, outside, a constant (left / right value),
+// the mirror image without repeating the edge sample (period 2(valid-1), == __vpad_center2 of the reference,
+// src/vector/flux_vectorOp.c:654-723) or the periodic extension (__vpad_center3, :736-770).  Reflect / wrap of fewer
+// than two samples pad nothing (zeros), as in the reference.
+__device__ __forceinline__ float padded_sample(const StftParams &p, const float *x, int s) {
+    const int v = p.validLength;
+    if (s >= 0 && s < v) return x[s];
+    if (p.padMode == PaddingMode_Constant) return s < 0 ? p.padValue1 : p.padValue2;
+    if (v < 2) return 0.0f;
+    if (p.padMode == PaddingMode_Wrap) { int j = s % v; if (j < 0) j += v; return x[j]; }
+    const int period = 2 * (v - 1);
+    int j = s % period; if (j < 0) j += period;
+    return x[j < v ? j : period - j];
+}
+
 __global__ void k_stft_generic(StftParams p) {
     extern __shared__ float2 smem[];
     float2 *a = smem, *b = smem + p.nc;
@@ -39,12 +56,12 @@ __global__ void k_stft_generic(StftParams p) {
     const float *x = p.data + (long long)clip * p.dataStride;
     const int nc = p.nc, n = p.n;
 
-    // load + window, 2 real samples -> 1 complex point; logical signal = zeros(padLeft) ++ x[0:valid] ++ zeros
+    // load + window, 2 real samples -> 1 complex point; logical signal = pad(padLeft) ++ x[0:valid] ++ pad
     const int base = frame * p.hop - p.padLeft;
     for (int i = threadIdx.x; i < nc; i += blockDim.x) {
         int s0 = base + 2 * i, s1 = s0 + 1;
-        float v0 = (s0 >= 0 && s0 < p.validLength) ? x[s0] : 0.0f;
-        float v1 = (s1 >= 0 && s1 < p.validLength) ? x[s1] : 0.0f;
+        float v0 = padded_sample(p, x, s0);
+        float v1 = padded_sample(p, x, s1);
         if (p.window) { v0 *= p.window[2 * i]; v1 *= p.window[2 * i + 1]; }
         a[i] = make_float2(v0, v1);
     }
@@ -130,8 +147,8 @@ __global__ void k_stft_n2(StftParams p, long long frames) {
     const int clip = (int)(f / p.timeLength);
     const float *x = p.data + (long long)clip * p.dataStride;
     int s0 = frame * p.hop - p.padLeft;
-    float v0 = (s0 >= 0 && s0 < p.validLength) ? x[s0] : 0.0f;
-    float v1 = (s0 + 1 >= 0 && s0 + 1 < p.validLength) ? x[s0 + 1] : 0.0f;
+    float v0 = padded_sample(p, x, s0);
+    float v1 = padded_sample(p, x, s0 + 1);
     if (p.window) { v0 *= p.window[0]; v1 *= p.window[1]; }
     float X[2] = {v0 + v1, v0 - v1};
     for (int k = 0; k < 2; k++) {
@@ -161,6 +178,7 @@ extern "C" int af_launch_stft(const AfFrameSrc *src, int mode, float normValue, 
     p.log2nc = 0; while ((1 << p.log2nc) < p.nc) p.log2nc++;
     p.hop = src->slideLength; p.timeLength = src->timeLength; p.padLeft = src->padLeft;
     p.validLength = src->validLength; p.mode = mode; p.normValue = normValue;
+    p.padMode = src->padMode; p.padValue1 = src->padValue1; p.padValue2 = src->padValue2;
     cudaStream_t st = (cudaStream_t)stream;
     if (n == 2) {
         k_stft_n2<<<(unsigned)((frames + 255) / 256), 256, 0, st>>>(p, frames);

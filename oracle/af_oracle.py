@@ -140,18 +140,43 @@ def stft_time_length(L, n, hop, is_pad=False):
     return 0 if L <= 0 else L // hop + 1
 
 
-def stft(x, n, hop, window, is_pad=False):
+PAD_CENTER, PAD_RIGHT, PAD_LEFT = 0, 1, 2
+PAD_CONSTANT, PAD_REFLECT, PAD_WRAP = 0, 1, 2
+
+
+def stft_pad(x, n, hop, position=PAD_CENTER, mode=PAD_CONSTANT, value1=0.0, value2=0.0):
+    """`__stftObj_dealPadData` (stft_algorithm.c:583-694): drop the `L % hop` tail when more than one frame exists,
+    then add n samples: n/2 + n/2 (Center), n left (Left), n right (Right) -- a constant (Left/Right: the value is
+    passed as `int`, src/vector/flux_vectorOp.c:641-652), the mirror image (== numpy 'reflect', :654-723) or the
+    periodic extension (== numpy 'wrap', :736-770); reflect / wrap of fewer than two samples add zeros."""
+    x = np.asarray(x, dtype=np.float64)
+    L = x.shape[0]
+    T = stft_time_length(L, n, hop, True)
+    tail = (L % hop) if T > 1 else 0
+    v = x[:L - tail]
+    left, right = {PAD_CENTER: (n // 2, n - n // 2), PAD_LEFT: (n, 0), PAD_RIGHT: (0, n)}[position]
+    if mode == PAD_CONSTANT:
+        if position == PAD_CENTER:
+            c1, c2 = float(f32(value1)), float(f32(value2))
+        else:
+            c1 = c2 = float(int(value1))
+        return np.concatenate([np.full(left, c1), v, np.full(right, c2)])
+    if len(v) < 2:
+        return np.concatenate([np.zeros(left), v, np.zeros(right)])
+    # numpy's reflect / wrap iterate when the pad is longer than the data, exactly like the reference's index walk
+    return np.pad(v, (left, right), mode="reflect" if mode == PAD_REFLECT else "wrap")
+
+
+def stft(x, n, hop, window, is_pad=False, position=PAD_CENTER, mode=PAD_CONSTANT, value1=0.0, value2=0.0):
     """Full mirrored n-point spectrum per frame -> (re[T,n], im[T,n]).
 
-    is_pad=True restates the centre/constant-zero padding used by CQT
-    (stft_algorithm.c:601-694, 813-826): the `L % hop` tail is dropped when T>1,
-    then n/2 zeros are added on both sides."""
+    is_pad=True: frames are cut from the padded signal of `stft_pad` (default = the centre / constant-zero padding
+    CQT uses, stft_algorithm.c:601-694, 813-826)."""
     x = np.asarray(x, dtype=np.float64)
     L = x.shape[0]
     T = stft_time_length(L, n, hop, is_pad)
     if is_pad:
-        tail = (L % hop) if T > 1 else 0
-        x = np.concatenate([np.zeros(n // 2), x[:L - tail], np.zeros(n - n // 2)])
+        x = stft_pad(x, n, hop, position, mode, value1, value2)
     if T == 0:
         return np.zeros((0, n), f32), np.zeros((0, n), f32)
     idx = np.arange(T)[:, None] * hop + np.arange(n)[None, :]

@@ -191,3 +191,39 @@ def test_next_rows_against_reference_build(torch_cuda, ref_lib):
         for a, r in zip(af.XXCC(40).xxcc_standard_planes(m, e, 13, 9, et),
                         af.XXCC(40, _lib=ref_lib).xxcc_standard_planes(m, e, 13, 9, et)):
             assert rel_max(a, r) < TOL
+
+
+# ------------------------------------------------------------------ STFT padding modes (reflect / wrap / constant values)
+from test_next_rows_cpu import PAD_CASES  # noqa: E402
+
+
+@pytest.mark.parametrize("pos,mode,v1,v2,L,n,hop", PAD_CASES + [(0, 1, 0, 0, 1, 64, 16), (0, 2, 0, 0, 40, 256, 64)])
+def test_stft_padding_modes(torch_cuda, pos, mode, v1, v2, L, n, hop):
+    torch = torch_cuda
+    x = noise(61, L)
+    r = int(np.log2(n))
+    s = af.STFT(r, af.WindowType.HANN, hop)
+    s.enable_padding(True)
+    s.set_padding(pos, mode, v1, v2)
+    re, im = s.stft_planes(x)                                    # legacy entry: full mirrored planes
+    re2, im2 = O.stft(x, n, hop, O.fft_window(O.W_HANN, n), True, pos, mode, v1, v2)
+    assert re.shape == re2.shape
+    scale = max(np.abs(re2).max(), np.abs(im2).max(), 1e-30)
+    assert np.abs(re - re2).max() <= TOL * scale and np.abs(im - im2).max() <= TOL * scale
+    xb = np.stack([x, noise(62, L)])
+    bre, bim = s.stft_batch(torch.from_numpy(xb).cuda())        # batched device entry: half spectrum
+    assert np.abs(bre[0].cpu().numpy() - re2[:, :n // 2 + 1]).max() <= TOL * scale
+    assert np.abs(bim[0].cpu().numpy() - im2[:, :n // 2 + 1]).max() <= TOL * scale
+
+
+def test_stft_padding_against_reference_build(torch_cuda, ref_lib):
+    x = tones(63, 5000, 16000)
+    for pos in (0, 1, 2):
+        for mode in (0, 1, 2):
+            a, r = af.STFT(9, af.WindowType.HAMM, 128), af.STFT(9, af.WindowType.HAMM, 128, _lib=ref_lib)
+            for s in (a, r):
+                s.enable_padding(True)
+                s.set_padding(pos, mode, 1.25, -0.75)
+            (ar, ai), (rr, ri) = a.stft_planes(x), r.stft_planes(x)
+            scale = max(np.abs(rr).max(), np.abs(ri).max())
+            assert np.abs(ar - rr).max() <= TOL * scale and np.abs(ai - ri).max() <= TOL * scale

@@ -203,3 +203,22 @@ def test_spectrogram_vs_reference(ref_lib, kw):
             assert np.abs(got[1] - want[1])[m].max() < 5e-3
         else:
             assert rel_max(got, want) < TOL
+
+
+# ---------------- STFT padding modes: oracle vs the reference ----------------
+PAD_CASES = [(pos, mode, v1, v2, L, n, hop) for pos in (0, 1, 2) for mode in (0, 1, 2)
+             for (v1, v2, L, n, hop) in ((0.0, 0.0, 3000, 256, 64), (0.37, -1.6, 2500, 512, 100), (2.9, 0.5, 700, 1024, 256))]
+
+
+@pytest.mark.parametrize("pos,mode,v1,v2,L,n,hop", PAD_CASES + [(0, 1, 0, 0, 1, 64, 16), (0, 2, 0, 0, 40, 256, 64)])
+def test_stft_padding_modes_vs_reference(ref_lib, pos, mode, v1, v2, L, n, hop):
+    x = noise(61, L)
+    r = int(np.log2(n))
+    s = af.STFT(r, af.WindowType.HANN, hop, _lib=ref_lib)
+    s.enable_padding(True)
+    s.set_padding(pos, mode, v1, v2)
+    re, im = s.stft_planes(x)
+    re2, im2 = O.stft(x, n, hop, O.fft_window(O.W_HANN, n), True, pos, mode, v1, v2)
+    assert re.shape == re2.shape
+    scale = max(np.abs(re).max(), np.abs(im).max(), 1e-30)
+    assert np.abs(re - re2).max() <= TOL * scale and np.abs(im - im2).max() <= TOL * scale
