@@ -25,6 +25,18 @@ import time
 import numpy as np
 
 ROOT = os.path.dirname(os.path.realpath(__file__))
+_REAL_STDOUT = None
+
+
+def emit(obj):
+    """The one JSON line of the contract, on the process's original stdout."""
+    text = json.dumps(obj) + "\n"
+    if _REAL_STDOUT is None:
+        sys.stdout.write(text)
+        sys.stdout.flush()
+    else:
+        os.write(_REAL_STDOUT, text.encode())
+
 if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
 
@@ -151,7 +163,7 @@ def run_reference_arm(args):
     for _ in range(max(1, min(args.steps, 3))):
         r = cpu_reference_rate(per, cores)
         if r is None:
-            print(json.dumps({"impl": "reference", "unavailable": "oracle/_ref/libaudioflux_ref.so not built"}))
+            emit({"impl": "reference", "unavailable": "oracle/_ref/libaudioflux_ref.so not built"})
             return 0
         vals.append(r["frames_per_s"])
     v = float(np.median(vals))
@@ -168,7 +180,7 @@ def run_reference_arm(args):
         "e2e": {"value": v, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0, "wall_s": time.perf_counter() - t_all,
     }
-    print(json.dumps(line))
+    emit(line)
     return 0
 
 
@@ -187,8 +199,12 @@ def run_b200_arm(args):
         import torch.distributed as dist_
         dist = dist_
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        # stdout carries exactly one JSON line: NCCL's own log ("NCCL version ..." at any debug level) goes to a file
-        os.environ.setdefault("NCCL_DEBUG_FILE", "/tmp/afb200_nccl_%h_%p.log")
+        # stdout carries exactly one JSON line, but NCCL prints "NCCL version ..." there when the box sets NCCL_DEBUG:
+        # from here on file descriptor 1 is stderr, and the JSON line is written to the saved real stdout (emit())
+        global _REAL_STDOUT
+        sys.stdout.flush()
+        _REAL_STDOUT = os.dup(1)
+        os.dup2(2, 1)
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     dev = torch.device("cuda", local)
     lib = L_.get_lib()
@@ -236,7 +252,7 @@ def run_b200_arm(args):
         want = O.mfcc(x[0].cpu().numpy(), SR, RADIX, HOP, NMEL, NCC)
         parity = float(np.abs(out[0].cpu().numpy() - want).max() / np.abs(want).max())
         if not parity < 1e-4:
-            print(json.dumps({"error": f"parity gate failed: rel err {parity}"}))
+            emit({"error": f"parity gate failed: rel err {parity}"})
             return 1
 
     for _ in range(max(args.warmup, 3)):
@@ -262,7 +278,7 @@ def run_b200_arm(args):
     if dist:
         dist.barrier()
     if gather_ok is False:
-        print(json.dumps({"error": "gather gate failed: the last rank's block did not arrive intact on rank 0"}))
+        emit({"error": "gather gate failed: the last rank's block did not arrive intact on rank 0"})
         return 1
 
     sampler = ClockSampler(local)
@@ -379,7 +395,7 @@ def run_b200_arm(args):
         line["cpu_baseline"] = {"value": cpu["frames_per_s"], "unit": "frames/s", "cores": cores, "kind": "reference",
                                 "sample": f"{cores} processes x {max(2, int(os.environ.get('AFB200_CPU_CLIPS_PER_WORKER', '4')))} clips, "
                                           "oracle/_ref (gcc -O3, built-in radix-2 FFT + naive dot)"}
-    print(json.dumps(line))
+    emit(line)
     if dist:
         dist.destroy_process_group()
     return 0
