@@ -31,6 +31,7 @@ REFERENCE_API = {
     "stftObj_calTimeLength": (C.c_int, [vp, C.c_int]),
     "stftObj_calDataLength": (C.c_int, [vp, C.c_int]),
     "stftObj_stft": (None, [vp, vp, C.c_int, vp, vp]),
+    "stftObj_istft": (None, [vp, vp, vp, C.c_int, C.c_int, vp]),
     "stftObj_free": (None, [vp]),
     # ---- BFT
     "bftObj_new": (C.c_int, [P(vp), C.c_int, C.c_int, c_int_p, c_float_p, c_float_p, c_int_p,
@@ -66,6 +67,8 @@ REFERENCE_API = {
     "cwtObj_getFreBandArr": (vp, [vp]),
     "cwtObj_getBinBandArr": (vp, [vp]),
     "cwtObj_cwt": (None, [vp, vp, vp, vp]),
+    "cwtObj_enableDet": (None, [vp, C.c_int]),
+    "cwtObj_cwtDet": (None, [vp, vp, vp, vp]),
     "cwtObj_free": (None, [vp]),
     # ---- Spectrogram (front door; src/spectrogram_algorithm.h:40-119)
     "spectrogramObj_new": (C.c_int, [P(vp), C.c_int, c_int_p, c_float_p, c_float_p, c_int_p, c_int_p, c_int_p,
@@ -99,6 +102,7 @@ EXTENSION_API = {
     "afb200_kernelLaunchCount": (C.c_longlong, []),
     "afb200_deviceSynchronize": (C.c_int, []),
     "stftObj_stftBatch": (C.c_int, [vp, vp, C.c_int, C.c_int, vp, vp, C.c_int, vp]),
+    "stftObj_istftBatch": (C.c_int, [vp, vp, vp, C.c_int, C.c_int, C.c_int, C.c_int, vp, C.c_int, vp]),
     "bftObj_bftBatch": (C.c_int, [vp, vp, C.c_int, C.c_int, vp, vp, C.c_int, vp]),
     "bftObj_mfccBatch": (C.c_int, [vp, vp, C.c_int, C.c_int, C.c_int, C.c_int, vp, C.c_int, vp]),
     "bftObj_getFilterBankArr": (C.c_int, [vp, vp]),
@@ -119,6 +123,7 @@ EXTENSION_API = {
     "spectrogramObj_spectrogramBatch": (C.c_int, [vp, vp, C.c_int, C.c_int, vp, vp, C.c_int, vp]),
     "spectrogramObj_mfccBatch": (C.c_int, [vp, vp, C.c_int, C.c_int, C.c_int, C.c_int, vp, C.c_int, vp]),
     "cwtObj_cwtBatch": (C.c_int, [vp, vp, C.c_int, vp, vp, C.c_int, vp]),
+    "cwtObj_cwtDetBatch": (C.c_int, [vp, vp, C.c_int, vp, vp, C.c_int, vp]),
     "cwtObj_getFilterBankArr": (C.c_int, [vp, vp]),
     "afb200_window": (C.c_int, [C.c_int, C.c_int, vp]),
     "afb200_auditoryFilterBank": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,

@@ -120,6 +120,11 @@ enum { AF_STFT_FULL = 0, AF_STFT_HALF = 1, AF_STFT_POWER = 2, AF_STFT_MAG = 3, A
  * SQUARE: (re,im) <- X^2 complex square, T x (n/2+1). */
 int af_launch_stft(const AfFrameSrc *src, int mode, float normValue, float *outRe, float *outIm, void *stream);
 
+/* inverse STFT: planes [batch*T][width] (width = n or n/2+1) -> data[batch][(T-1)*hop+n] (accumulating, then
+ * divided by the window sum); frames = scratch batch*T*n floats; window NULL = rect */
+int af_launch_istft(const float *re, const float *im, int width, int fftLength, int slideLength, int timeLength,
+                    int batch, const float *window, int methodType, float *frames, float *data, void *stream);
+
 typedef struct {
     int num, width;               /* width = fftLength/2+1 */
     const float *dense;           /* device num x width */
@@ -175,8 +180,10 @@ typedef struct {
     int log2n, num, batch, padLength, dataLength;
     AfWavelet wavelet;
     const float *scaleArr;   /* device, num */
+    int det;                 /* 1: multiply the bank by j*omega (cwtObj_cwtDet) */
 } AfCwtArgs;
 size_t af_cwt_workspace_bytes(const AfCwtArgs *a);
+/* data == NULL: skip the forward transform and reuse the spectra a previous call left in `workspace` */
 int af_launch_cwt(const AfCwtArgs *a, const float *data, void *workspace, float *outRe, float *outIm, void *stream);
 int af_launch_cwt_bank_table(const AfCwtArgs *a, float *bank /* device num x n */, void *stream);
 

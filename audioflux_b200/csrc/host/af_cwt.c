@@ -19,6 +19,8 @@ struct OpaqueCWT {
     void *stream;
     float *dScale;
     AfDevBuf dIn, dWork, dOutRe, dOutIm;
+    int detEnabled;                /* cwtObj_enableDet */
+    int haveSpec;                  /* dWork starts with the spectrum of the last single-clip call */
 };
 
 int cwtObj_new(CWTObj *out, int num, int radix2Exp, int *samplate, float *lowFre, float *highFre,
@@ -79,16 +81,17 @@ static int cwt_device(CWTObj c) {
     return AF_OK;
 }
 
-static void cwt_args(CWTObj c, int batch, AfCwtArgs *a) {
+static void cwt_args(CWTObj c, int batch, int det, AfCwtArgs *a) {
     memset(a, 0, sizeof(*a));
+    a->det = det;
     a->log2n = c->log2fft; a->num = c->num; a->batch = batch; a->padLength = c->padLength;
     a->dataLength = c->dataLength; a->wavelet = c->wavelet; a->scaleArr = c->dScale;
 }
 
 /* dData [batch x N] -> planes [batch x num x N]; the batch is cut into chunks that fit the workspace */
-static int cwt_compute(CWTObj c, const float *dData, int batch, float *dRe, float *dIm, void *st) {
+static int cwt_compute(CWTObj c, const float *dData, int batch, int det, float *dRe, float *dIm, void *st) {
     AfCwtArgs a;
-    cwt_args(c, 1, &a);
+    cwt_args(c, 1, det, &a);
     const size_t perClip = af_cwt_workspace_bytes(&a);
     size_t budget = af_dev_free_bytes() / 3 + c->dWork.bytes;
     if (budget > ((size_t)24 << 30)) budget = (size_t)24 << 30;
@@ -101,29 +104,40 @@ static int cwt_compute(CWTObj c, const float *dData, int batch, float *dRe, floa
     const size_t outClip = (size_t)c->num * c->dataLength;
     for (int c0 = 0; c0 < batch; c0 += chunk) {
         const int nb = batch - c0 < chunk ? batch - c0 : chunk;
-        cwt_args(c, nb, &a);
-        if ((rc = af_launch_cwt(&a, dData + (size_t)c0 * c->dataLength, c->dWork.ptr, dRe + (size_t)c0 * outClip,
+        cwt_args(c, nb, det, &a);
+        if ((rc = af_launch_cwt(&a, dData ? dData + (size_t)c0 * c->dataLength : NULL, c->dWork.ptr, dRe + (size_t)c0 * outClip,
                                 dIm + (size_t)c0 * outClip, st))) return rc;
     }
+    c->haveSpec = batch == 1;       /* the workspace now starts with this clip's spectrum (cwtObj_cwtDet(NULL) reuses it) */
     return AF_OK;
 }
 
-int cwtObj_cwtBatch(CWTObj c, const float *data, int batch, float *mReal4, float *mImag4, int memKind, void *stream) {
-    if (!c || !data || !mReal4 || !mImag4 || batch <= 0) return af_fail(AF_ERR_ARG, "cwtObj_cwtBatch: bad argument");
+static int cwt_batch(CWTObj c, const float *data, int batch, int det, float *mReal4, float *mImag4, int memKind,
+                     void *stream, const char *who) {
+    if (!c || !mReal4 || !mImag4 || batch <= 0) return af_fail(AF_ERR_ARG, "%s: bad argument", who);
     af_clear_error();
     int rc = cwt_device(c);
     if (rc) return rc;
     void *st = stream ? stream : c->stream;
+    if (!data) {                        /* cwtObj_cwtDet(obj, NULL, ...): the spectrum of the last single-clip call */
+        if (batch != 1 || !c->haveSpec) return af_fail(AF_ERR_ARG, "%s: no data and no spectrum of a previous single-clip call", who);
+        if (memKind == AFB200_MEM_DEVICE) return cwt_compute(c, NULL, 1, det, mReal4, mImag4, stream);
+        const size_t outB = sizeof(float) * (size_t)c->num * c->dataLength;
+        if ((rc = af_devbuf_reserve(&c->dOutRe, outB)) || (rc = af_devbuf_reserve(&c->dOutIm, outB))) return rc;
+        if ((rc = cwt_compute(c, NULL, 1, det, (float *)c->dOutRe.ptr, (float *)c->dOutIm.ptr, st))) return rc;
+        if ((rc = af_memcpy_d2h(mReal4, c->dOutRe.ptr, outB, st)) || (rc = af_memcpy_d2h(mImag4, c->dOutIm.ptr, outB, st))) return rc;
+        return af_stream_sync(st);
+    }
     if (memKind == AFB200_MEM_DEVICE) {
         st = stream;
-        return cwt_compute(c, data, batch, mReal4, mImag4, st);
+        return cwt_compute(c, data, batch, det, mReal4, mImag4, st);
     }
     /* host pointers: stream clip by clip so the device footprint stays one clip's planes */
     const size_t inB = sizeof(float) * (size_t)c->dataLength, outB = sizeof(float) * (size_t)c->num * c->dataLength;
     if ((rc = af_devbuf_reserve(&c->dIn, inB)) || (rc = af_devbuf_reserve(&c->dOutRe, outB)) || (rc = af_devbuf_reserve(&c->dOutIm, outB))) return rc;
     for (int b = 0; b < batch; b++) {
         if ((rc = af_memcpy_h2d(c->dIn.ptr, data + (size_t)b * c->dataLength, inB, st))) return rc;
-        if ((rc = cwt_compute(c, (const float *)c->dIn.ptr, 1, (float *)c->dOutRe.ptr, (float *)c->dOutIm.ptr, st))) return rc;
+        if ((rc = cwt_compute(c, (const float *)c->dIn.ptr, 1, det, (float *)c->dOutRe.ptr, (float *)c->dOutIm.ptr, st))) return rc;
         if ((rc = af_memcpy_d2h(mReal4 + (size_t)b * c->num * c->dataLength, c->dOutRe.ptr, outB, st)) ||
             (rc = af_memcpy_d2h(mImag4 + (size_t)b * c->num * c->dataLength, c->dOutIm.ptr, outB, st))) return rc;
         if ((rc = af_stream_sync(st))) return rc;
@@ -131,9 +145,27 @@ int cwtObj_cwtBatch(CWTObj c, const float *data, int batch, float *mReal4, float
     return AF_OK;
 }
 
+int cwtObj_cwtBatch(CWTObj c, const float *data, int batch, float *mReal4, float *mImag4, int memKind, void *stream) {
+    if (!data) return af_fail(AF_ERR_ARG, "cwtObj_cwtBatch: bad argument");
+    return cwt_batch(c, data, batch, 0, mReal4, mImag4, memKind, stream, "cwtObj_cwtBatch");
+}
+
 void cwtObj_cwt(CWTObj c, float *dataArr, float *mRealArr4, float *mImageArr4) {
     if (!c || !dataArr) return;
     cwtObj_cwtBatch(c, dataArr, 1, mRealArr4, mImageArr4, AFB200_MEM_HOST, NULL);
+}
+
+/* ---- derivative transform: bank * j*omega (cwt_algorithm.c:352-358, 485-528); feeds synchrosqueezing ---- */
+void cwtObj_enableDet(CWTObj c, int flag) { if (c && flag) c->detEnabled = 1; }   /* never switched off again, as :494-496 */
+
+int cwtObj_cwtDetBatch(CWTObj c, const float *data, int batch, float *mReal4, float *mImag4, int memKind, void *stream) {
+    if (c && !c->detEnabled) return af_fail(AF_ERR_ARG, "cwtObj_cwtDetBatch: call cwtObj_enableDet(obj, 1) first");
+    return cwt_batch(c, data, batch, 1, mReal4, mImag4, memKind, stream, "cwtObj_cwtDetBatch");
+}
+
+void cwtObj_cwtDet(CWTObj c, float *dataArr, float *mRealArr4, float *mImageArr4) {
+    if (!c || !c->detEnabled) return;                 /* silent without enableDet, like :355 */
+    cwtObj_cwtDetBatch(c, dataArr, 1, mRealArr4, mImageArr4, AFB200_MEM_HOST, NULL);
 }
 
 int cwtObj_getFilterBankArr(CWTObj c, float *bank) {

@@ -19,7 +19,7 @@ struct OpaqueSTFT {
     int devReady, windowDirty;
     void *stream;
     float *dWindow;
-    AfDevBuf dIn, dRe, dIm;
+    AfDevBuf dIn, dRe, dIm, dFrames;
 };
 
 int stftObj_new(STFTObj *out, int radix2Exp, WindowType *windowType, int *slideLength, int *isContinue) {
@@ -158,9 +158,44 @@ int stftObj_stftBatch(STFTObj s, const float *data, int dataLength, int batch, f
     return af_stream_sync(st);
 }
 
+/* ---- inverse: planes [batch x T x width] -> data [batch x ((T-1)*hop + n)]  (stft_algorithm.c:304-409) ----
+ * width = fftLength (full mirrored planes, the reference layout) or fftLength/2+1 (what stftObj_stftBatch produces).
+ * As in the reference the frames are ADDED to what `data` holds before the division by the window sum, so the
+ * caller passes a zeroed buffer. */
+int stftObj_istftBatch(STFTObj s, const float *mReal, const float *mImag, int timeLength, int batch, int specWidth,
+                       int methodType, float *data, int memKind, void *stream) {
+    if (!s || !mReal || !mImag || !data || timeLength <= 0 || batch <= 0) return af_fail(AF_ERR_ARG, "stftObj_istftBatch: bad argument");
+    if (specWidth != s->fftLength && specWidth != s->fftLength / 2 + 1)
+        return af_fail(AF_ERR_ARG, "stftObj_istftBatch: specWidth=%d must be fftLength or fftLength/2+1", specWidth);
+    af_clear_error();
+    int rc = stft_device(s);
+    if (rc) return rc;
+    const int n = s->fftLength, dataLength = (timeLength - 1) * s->slideLength + n;
+    const size_t plane = sizeof(float) * (size_t)batch * timeLength * specWidth;
+    const size_t frameB = sizeof(float) * (size_t)batch * timeLength * n, dataB = sizeof(float) * (size_t)batch * dataLength;
+    if ((rc = af_devbuf_reserve(&s->dFrames, frameB))) return rc;
+    const float *win = s->useWindow ? s->dWindow : NULL;
+    if (memKind == AFB200_MEM_DEVICE)
+        return af_launch_istft(mReal, mImag, specWidth, n, s->slideLength, timeLength, batch, win, methodType,
+                               (float *)s->dFrames.ptr, data, stream);
+    void *st = stream ? stream : s->stream;
+    if ((rc = af_devbuf_reserve(&s->dRe, plane)) || (rc = af_devbuf_reserve(&s->dIm, plane)) || (rc = af_devbuf_reserve(&s->dIn, dataB))) return rc;
+    if ((rc = af_memcpy_h2d(s->dRe.ptr, mReal, plane, st)) || (rc = af_memcpy_h2d(s->dIm.ptr, mImag, plane, st)) ||
+        (rc = af_memcpy_h2d(s->dIn.ptr, data, dataB, st))) return rc;
+    if ((rc = af_launch_istft((const float *)s->dRe.ptr, (const float *)s->dIm.ptr, specWidth, n, s->slideLength, timeLength,
+                              batch, win, methodType, (float *)s->dFrames.ptr, (float *)s->dIn.ptr, st))) return rc;
+    if ((rc = af_memcpy_d2h(data, s->dIn.ptr, dataB, st))) return rc;
+    return af_stream_sync(st);
+}
+
+void stftObj_istft(STFTObj s, float *mRealArr, float *mImageArr, int timeLength, int methodType, float *dataArr) {
+    if (!s || !mRealArr || !mImageArr || !dataArr || timeLength <= 0) return;
+    stftObj_istftBatch(s, mRealArr, mImageArr, timeLength, 1, s->fftLength, methodType, dataArr, AFB200_MEM_HOST, NULL);
+}
+
 void stftObj_free(STFTObj s) {
     if (!s) return;
-    af_devbuf_free(&s->dIn); af_devbuf_free(&s->dRe); af_devbuf_free(&s->dIm);
+    af_devbuf_free(&s->dIn); af_devbuf_free(&s->dRe); af_devbuf_free(&s->dIm); af_devbuf_free(&s->dFrames);
     af_dev_free(s->dWindow);
     af_stream_destroy(s->stream);
     free(s->window);

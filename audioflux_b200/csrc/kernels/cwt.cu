@@ -118,6 +118,7 @@ struct CwtParams {
     float2 *work;             // items x N           (inter-leg buffer; items = batch or batch*num)
     float *outRe, *outIm;     // batch x num x dataLength
     const float *scaleArr;    // num
+    int det;                  // 1: bank * omega * j (cwtObj_cwtDet, src/cwt_algorithm.c:485-528, 426-437)
     int log2N, log2N1, log2N2, N, N1, N2;
     int dataLength, padLength, num, batch;
     int wType; float g, b, factor;
@@ -131,6 +132,20 @@ __device__ __forceinline__ float load_padded(const CwtParams &p, const float *x,
     if (j < 0) j = -j - 1;
     else if (j >= p.dataLength) j = 2 * p.dataLength - 1 - j;
     return x[j];
+}
+
+// wavelet(s*omega_k) * X[k]  (cwtObj_cwt) or  j * omega_k * wavelet(s*omega_k) * X[k]  (cwtObj_cwtDet: the reference
+// multiplies the bank by wArr[k] = 2 pi k / N in float and then forms (-bd * im, bd * re), src/cwt_algorithm.c:426-437,
+// 500-512).  omega_k = 2 pi k / N for k <= N/2, negative above, where every wavelet family is zero.
+__device__ __forceinline__ float2 bank_times_spec(const CwtParams &p, float s, int k, float2 x) {
+    float wv = 0.0f, omega = 0.0f;
+    if (k <= p.N / 2) {
+        omega = (float)((double)k * 2.0 * M_PI / (double)p.N);
+        wv = wavelet_eval(p.wType, p.g, p.b, p.factor, s * omega);
+    }
+    if (!p.det) return make_float2(wv * x.x, wv * x.y);
+    const float bd = wv * omega;
+    return make_float2(-(bd * x.y), bd * x.x);
 }
 
 // MODE 0: forward, input = real clip (padded) ; MODE 1: inverse, input = wavelet(s*omega_k) * spec[k]
@@ -158,14 +173,7 @@ __global__ void k_cwt_cols(CwtParams p) {
         if (MODE == 0) {
             v = make_float2(load_padded(p, p.data + (size_t)clip * p.dataLength, k), 0.0f);
         } else {
-            // omega_k = 2 pi k / N for k <= N/2, negative above (every family is 0 there)
-            float wv = 0.0f;
-            if (k <= p.N / 2) {
-                const float omega = (float)((double)k * 2.0 * M_PI / (double)p.N);
-                wv = wavelet_eval(p.wType, p.g, p.b, p.factor, s * omega);
-            }
-            const float2 x = p.spec[(size_t)clip * p.N + k];
-            v = make_float2(wv * x.x, wv * x.y);
+            v = bank_times_spec(p, s, k, p.spec[(size_t)clip * p.N + k]);
         }
         a[(size_t)c * pitch + i] = v;
     }
@@ -292,10 +300,8 @@ __global__ void __launch_bounds__(kWCols * 32) k_cwt_cols_w(CwtParams p) {
         if (MODE == 0) {
             v = c_pack(load_padded(p, p.data + (size_t)clip * p.dataLength, k), 0.0f);
         } else {
-            float wv = 0.0f;
-            if (k <= p.N / 2) wv = wavelet_eval(p.wType, p.g, p.b, p.factor, s * (float)((double)k * 2.0 * M_PI / (double)p.N));
-            const float2 x = p.spec[(size_t)clip * p.N + k];
-            v = c_pack(wv * x.x, -(wv * x.y));                                 // conj: inverse transform via forward DFT
+            const float2 y = bank_times_spec(p, s, k, p.spec[(size_t)clip * p.N + k]);
+            v = c_pack(y.x, -y.y);                                             // conj: inverse transform via forward DFT
         }
         tile[(size_t)c * kWColPitch + i] = v;
     }
@@ -428,6 +434,7 @@ void fill_params(const AfCwtArgs *a, CwtParams *p) {
     p->N1 = 1 << p->log2N1; p->N2 = 1 << p->log2N2;
     p->dataLength = a->dataLength; p->padLength = a->padLength; p->num = a->num; p->batch = a->batch;
     p->scaleArr = a->scaleArr;
+    p->det = a->det;
     p->itemBase = 0;
     p->wType = a->wavelet.waveletType; p->g = a->wavelet.gamma; p->b = a->wavelet.beta; p->factor = (float)a->wavelet.factor;
     const size_t budget = (size_t)(getenv("AFB200_CWT_LEG_KB") ? atoi(getenv("AFB200_CWT_LEG_KB")) : 72) * 1024;   // per-CTA leg buffers: small enough for 2-3 CTAs per SM so load / FFT / store phases of different CTAs overlap
@@ -470,10 +477,12 @@ extern "C" int af_launch_cwt(const AfCwtArgs *a, const float *data, void *worksp
         if ((rc = set_smem(k_cwt_cols_w<0>, smC, "smem k_cwt_cols_w<0>")) || (rc = set_smem(k_cwt_cols_w<1>, smC, "smem k_cwt_cols_w<1>")) ||
             (rc = set_smem(k_cwt_rows_w<0>, smR, "smem k_cwt_rows_w<0>")) || (rc = set_smem(k_cwt_rows_w<1>, smR, "smem k_cwt_rows_w<1>"))) return rc;
         const unsigned cb = (unsigned)(p.N2 / kWCols), rb = (unsigned)(p.N1 / kWRows), items = (unsigned)(a->batch * a->num);
-        k_cwt_cols_w<0><<<dim3((unsigned)a->batch, cb), kWCols * 32, smC, st>>>(p);
-        AF_LAUNCH_CHECK("k_cwt_cols_w<0>");
-        k_cwt_rows_w<0><<<dim3((unsigned)a->batch, rb), kWRows * 16, smR, st>>>(p);
-        AF_LAUNCH_CHECK("k_cwt_rows_w<0>");
+        if (data) {                                        // NULL: reuse the spectra already in the workspace
+            k_cwt_cols_w<0><<<dim3((unsigned)a->batch, cb), kWCols * 32, smC, st>>>(p);
+            AF_LAUNCH_CHECK("k_cwt_cols_w<0>");
+            k_cwt_rows_w<0><<<dim3((unsigned)a->batch, rb), kWRows * 16, smR, st>>>(p);
+            AF_LAUNCH_CHECK("k_cwt_rows_w<0>");
+        }
         // optional: alternate the two legs over groups of (clip, scale) items (AFB200_CWT_GROUP) so that a group's
         // inter-leg buffer is still in L2 when read back.  Measured on B200: slower than one launch pair for the
         // whole chunk (launch tails cost more than the HBM round trip saves), so the default is a single group.
@@ -498,11 +507,13 @@ extern "C" int af_launch_cwt(const AfCwtArgs *a, const float *data, void *worksp
     const unsigned colBlocks = (unsigned)((p.N2 + p.cols - 1) / p.cols);
     const unsigned rowBlocks = (unsigned)((p.N1 + p.rows - 1) / p.rows);
     // forward transform of every clip
-    k_cwt_cols<0><<<dim3((unsigned)a->batch, colBlocks), threads, smemC, st>>>(p);
-    AF_LAUNCH_CHECK("k_cwt_cols<0>");
-    if (p.N2 > 1) {
-        k_cwt_rows<0><<<dim3((unsigned)a->batch, rowBlocks), threads, smemR, st>>>(p);
-        AF_LAUNCH_CHECK("k_cwt_rows<0>");
+    if (data) {                                            // NULL: reuse the spectra already in the workspace
+        k_cwt_cols<0><<<dim3((unsigned)a->batch, colBlocks), threads, smemC, st>>>(p);
+        AF_LAUNCH_CHECK("k_cwt_cols<0>");
+        if (p.N2 > 1) {
+            k_cwt_rows<0><<<dim3((unsigned)a->batch, rowBlocks), threads, smemR, st>>>(p);
+            AF_LAUNCH_CHECK("k_cwt_rows<0>");
+        }
     }
     // per (clip, scale): wavelet * spectrum -> inverse transform -> planes
     const unsigned items = (unsigned)(a->batch * a->num);

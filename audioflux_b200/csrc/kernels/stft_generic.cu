@@ -11,6 +11,7 @@
 // fused kernel (mfcc_fused.cu).
 #include <math.h>
 #include "common.cuh"
+#include "stockham.cuh"
 
 namespace {
 
@@ -27,11 +28,6 @@ struct StftParams {
     float normValue;
 };
 
-__device__ __forceinline__ float2 twiddle(int k, int m) {   // exp(-2 pi i k / m)
-    float s, c;
-    sincospif(-2.0f * (float)k / (float)m, &s, &c);
-    return make_float2(c, s);
-}
 
 // sample s of the logical (padded) signal of one clip: x[0:valid] with, outside, a constant (left / right value),
 // the mirror image without repeating the edge sample (period 2(valid-1), == __vpad_center2 of the reference,
@@ -67,44 +63,7 @@ __global__ void k_stft_generic(StftParams p) {
     }
     __syncthreads();
 
-    // Stockham autosort passes: P = product of radices already applied
-    int P = 1, rem = p.log2nc;
-    while (rem >= 2) {
-        const int t = nc >> 2;
-        for (int i = threadIdx.x; i < t; i += blockDim.x) {
-            const int k = i & (P - 1);
-            float2 u0 = a[i], u1 = a[i + t], u2 = a[i + 2 * t], u3 = a[i + 3 * t];
-            if (k) {
-                float2 w1 = twiddle(k, 4 * P);
-                float2 w2 = af_cmul(w1, w1), w3 = af_cmul(w2, w1);
-                u1 = af_cmul(u1, w1); u2 = af_cmul(u2, w2); u3 = af_cmul(u3, w3);
-            }
-            float2 s02 = make_float2(u0.x + u2.x, u0.y + u2.y), d02 = make_float2(u0.x - u2.x, u0.y - u2.y);
-            float2 s13 = make_float2(u1.x + u3.x, u1.y + u3.y);
-            float2 d13 = make_float2(u1.y - u3.y, -(u1.x - u3.x));          // (u1-u3) * (-i)
-            const int j = ((i - k) << 2) + k;
-            b[j] = make_float2(s02.x + s13.x, s02.y + s13.y);
-            b[j + P] = make_float2(d02.x + d13.x, d02.y + d13.y);
-            b[j + 2 * P] = make_float2(s02.x - s13.x, s02.y - s13.y);
-            b[j + 3 * P] = make_float2(d02.x - d13.x, d02.y - d13.y);
-        }
-        __syncthreads();
-        float2 *tmp = a; a = b; b = tmp;
-        P <<= 2; rem -= 2;
-    }
-    if (rem == 1) {
-        const int t = nc >> 1;
-        for (int i = threadIdx.x; i < t; i += blockDim.x) {
-            const int k = i & (P - 1);
-            float2 u0 = a[i], u1 = a[i + t];
-            if (k) u1 = af_cmul(u1, twiddle(k, 2 * P));
-            const int j = ((i - k) << 1) + k;
-            b[j] = make_float2(u0.x + u1.x, u0.y + u1.y);
-            b[j + P] = make_float2(u0.x - u1.x, u0.y - u1.y);
-        }
-        __syncthreads();
-        float2 *tmp = a; a = b; b = tmp;
-    }
+    a = af_stockham(a, b, nc, p.log2nc);      // forward complex FFT of the nc packed points (stockham.cuh)
 
     // real-FFT post-pass: X[k] = E[k] + W_n^k O[k], k = 0..nc
     const int width = nc + 1;
@@ -113,7 +72,7 @@ __global__ void k_stft_generic(StftParams p) {
         float2 zk = a[k == nc ? 0 : k], zp = a[k == 0 ? 0 : nc - k];
         float er = 0.5f * (zk.x + zp.x), ei = 0.5f * (zk.y - zp.y);
         float orr = 0.5f * (zk.y + zp.y), oi = -0.5f * (zk.x - zp.x);
-        float2 w = twiddle(k, n);
+        float2 w = af_twiddle(k, n);
         float xr = er + (w.x * orr - w.y * oi), xi = ei + (w.x * oi + w.y * orr);
         if (k == 0 || k == nc) xi = 0.0f;
         switch (p.mode) {

@@ -77,6 +77,35 @@ class CWT(Base):
             outs.append((re + 1j * im)[::-1])
         return np.ascontiguousarray(np.stack(outs).reshape(*lead, self.num, N))
 
+    def enable_det(self, flag=True):
+        self._lib.cwtObj_enableDet(self._obj, int(flag))
+
+    def cwt_det_planes(self, data_arr=None):
+        """Raw C layout of the derivative transform (cwtObj_cwtDet): (re, im) each [num, N].  data_arr=None reuses the
+        spectrum of the preceding cwt / cwt_det call on this object."""
+        re = np.zeros((self.num, self.fft_length), np.float32)
+        im = np.zeros((self.num, self.fft_length), np.float32)
+        if data_arr is None:
+            self._lib.cwtObj_cwtDet(self._obj, None, np_ptr(re), np_ptr(im))
+        else:
+            x = as_f32(data_arr)
+            if x.shape[-1] != self.fft_length:
+                raise ValueError(f"data length must be 2**radix2_exp = {self.fft_length}")
+            self._lib.cwtObj_cwtDet(self._obj, np_ptr(x), np_ptr(re), np_ptr(im))
+        return re, im
+
+    def cwt_det_batch(self, data):
+        """Additive: data [B, N] (numpy host | torch cuda) -> (re, im) each [B, num, N] of the derivative transform."""
+        fn = self._require_ext("cwtObj_cwtDetBatch")
+        x2, lead, kind, ptr, stream, alloc = split_batch(data)
+        B, N = x2.shape
+        if N != self.fft_length:
+            raise ValueError(f"data length must be 2**radix2_exp = {self.fft_length}")
+        re = alloc(B, self.num, N)
+        im = alloc(B, self.num, N)
+        check(fn(self._obj, ptr(x2), B, ptr(re), ptr(im), kind, stream), "cwtObj_cwtDetBatch")
+        return re.reshape(*lead, self.num, N), im.reshape(*lead, self.num, N)
+
     def cwt_batch(self, data):
         """Additive: data [B, N] (numpy host | torch cuda) -> (re, im) each [B, num, N] (C row order)."""
         fn = self._require_ext("cwtObj_cwtBatch")

@@ -85,6 +85,49 @@ class STFT(Base):
         check(fn(self._obj, ptr(x2), L, B, ptr(re), ptr(im), kind, stream), "stftObj_stftBatch")
         return re.reshape(*lead, T, -1), im.reshape(*lead, T, -1)
 
+    def cal_data_length(self, time_length):
+        return self._lib.stftObj_calDataLength(self._obj, int(time_length))
+
+    def istft_planes(self, re, im, method_type=0):
+        """Raw C layout: planes [T, fft_length] (full mirrored spectrum) -> data [(T-1)*slide + fft_length]."""
+        re, im = as_f32(re), as_f32(im)
+        out = np.zeros(self.cal_data_length(re.shape[0]), np.float32)
+        self._lib.stftObj_istft(self._obj, np_ptr(re), np_ptr(im), re.shape[0], int(method_type), np_ptr(out))
+        return out
+
+    def istft(self, m_data_arr, method_type=0):
+        """complex [..., fft_length//2+1, T] -> [..., data_length] like the reference wrapper (stft.py:302-361):
+        method_type 0 'weight', 1 'overlap-add'."""
+        z = np.asarray(m_data_arr)
+        if not np.iscomplexobj(z):
+            raise ValueError("m_data_arr must be of type np.complex")
+        if z.ndim < 2:
+            raise ValueError("m_data_arr's dimensions must be greater than 1")
+        mirror = np.conj(z[..., ::-1, :][..., 1:-1, :])
+        full = np.swapaxes(np.concatenate([z, mirror], axis=-2), -1, -2)          # [..., T, fft_length]
+        lead = full.shape[:-2]
+        f2 = full.reshape((-1,) + full.shape[-2:])
+        outs = [self.istft_planes(f2[i].real, f2[i].imag, method_type) for i in range(f2.shape[0])]
+        return np.stack(outs).reshape(*lead, -1)
+
+    def istft_batch(self, re, im, method_type=0):
+        """Additive: planes [B, T, W] with W = fft_length//2+1 (as stft_batch returns them) or fft_length
+        (numpy host | torch cuda) -> data [B, (T-1)*slide + fft_length]."""
+        fn = self._require_ext("stftObj_istftBatch")
+        r2, lead, kind, ptr, stream, alloc = split_batch(re)
+        i2 = split_batch(im)[0]
+        if len(lead) < 1:
+            raise ValueError("planes must be [..., T, W]")
+        T, W = lead[-1], r2.shape[-1]
+        B = r2.shape[0] // T
+        out = alloc(B, self.cal_data_length(T))
+        if kind == 0:
+            out[...] = 0
+        else:
+            out.zero_()
+        check(fn(self._obj, ptr(r2), ptr(i2), T, B, W, int(method_type), ptr(out), kind, stream), "stftObj_istftBatch")
+        return out.reshape(*lead[:-1], -1)
+
     def __del__(self):
         if getattr(self, "_is_created", False):
             self._lib.stftObj_free(self._obj)

@@ -19,6 +19,10 @@ float *cwtObj_getFreBandArr(CWTObj cwtObj);                       /* :336-339 */
 int *cwtObj_getBinBandArr(CWTObj cwtObj);                         /* :341-344 */
 /* :346-350.  dataArr: exactly 2^radix2Exp samples; outputs num x 2^radix2Exp, row 0 = highest band. */
 void cwtObj_cwt(CWTObj cwtObj, float *dataArr, float *mRealArr4, float *mImageArr4);
+/* :485-528 / :352-358.  Derivative transform W' = IFFT(j * omega * wavelet * X) for synchrosqueezing.  enableDet(1)
+ * must be called once; dataArr may be NULL to reuse the spectrum of the preceding single-clip cwtObj_cwt / cwtDet. */
+void cwtObj_enableDet(CWTObj cwtObj, int flag);
+void cwtObj_cwtDet(CWTObj cwtObj, float *dataArr, float *mRealArr4, float *mImageArr4);
 void cwtObj_free(CWTObj cwtObj);
 
 #ifdef __cplusplus

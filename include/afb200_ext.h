@@ -37,6 +37,10 @@ int afb200_deviceSynchronize(void);
 /* data: batch x dataLength; out planes: batch x T x (fftLength/2+1) */
 int stftObj_stftBatch(STFTObj stftObj, const float *data, int dataLength, int batch,
                       float *mReal, float *mImag, int memKind, void *stream);
+/* inverse: planes batch x T x specWidth (specWidth = fftLength, or fftLength/2+1 = the layout stftObj_stftBatch
+ * writes) -> data batch x ((T-1)*slide + fftLength), pre-zeroed by the caller */
+int stftObj_istftBatch(STFTObj stftObj, const float *mReal, const float *mImag, int timeLength, int batch,
+                       int specWidth, int methodType, float *data, int memKind, void *stream);
 /* out: batch x T x num (mImag3 may be NULL when resultType=1) */
 int bftObj_bftBatch(BFTObj bftObj, const float *data, int dataLength, int batch,
                     float *mReal3, float *mImag3, int memKind, void *stream);
@@ -85,6 +89,9 @@ int cqtObj_getKernelBank(CQTObj cqtObj, float *kr, float *ki /* binPerOctave x (
 /* data: batch x 2^radix2Exp; out planes: batch x num x 2^radix2Exp */
 int cwtObj_cwtBatch(CWTObj cwtObj, const float *data, int batch, float *mReal4, float *mImag4,
                     int memKind, void *stream);
+/* derivative transform (after cwtObj_enableDet); data may be NULL with batch = 1 to reuse the last spectrum */
+int cwtObj_cwtDetBatch(CWTObj cwtObj, const float *data, int batch, float *mReal4, float *mImag4,
+                       int memKind, void *stream);
 int cwtObj_getFilterBankArr(CWTObj cwtObj, float *bank /* num x fftLength host */);
 
 /* setup-time table builders, exported for parity tests against the reference's

@@ -24,6 +24,11 @@ int stftObj_calTimeLength(STFTObj stftObj, int dataLength);                    /
 int stftObj_calDataLength(STFTObj stftObj, int timeLength);                    /* :289-301 */
 /* :264-287.  mRealArr/mImageArr: timeLength x fftLength, full mirrored spectrum. */
 void stftObj_stft(STFTObj stftObj, float *dataArr, int dataLength, float *mRealArr, float *mImageArr);
+/* :304-409.  mRealArr/mImageArr: timeLength x fftLength (full spectrum); dataArr: (timeLength-1)*slide + fftLength
+ * samples, pre-zeroed by the caller (frames are added to its content, then divided by the window sum).
+ * methodType 0 'weight' (synthesis window w, normaliser sum w^2), else 'overlap-add' (normaliser sum w).
+ * fftLength <= 8192. */
+void stftObj_istft(STFTObj stftObj, float *mRealArr, float *mImageArr, int timeLength, int methodType, float *dataArr);
 void stftObj_free(STFTObj stftObj);                                            /* :411-467, NULL-safe */
 void stftObj_debug(STFTObj stftObj);                                           /* :837-849 */
 

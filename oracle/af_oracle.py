@@ -185,6 +185,25 @@ def stft(x, n, hop, window, is_pad=False, position=PAD_CENTER, mode=PAD_CONSTANT
     return X.real.astype(f32), X.imag.astype(f32)
 
 
+def istft(re, im, n, hop, window, method_type=0, initial=None):
+    """`stftObj_istft` (stft_algorithm.c:304-409): full-spectrum planes (T, n) -> data ((T-1)*hop + n).
+    method_type 0 'weight': frames * w, normaliser sum w^2; else 'overlap-add': frames, normaliser sum w;
+    normaliser < 1e-6 -> 1.  `initial` = what the caller's buffer held (the reference adds onto it)."""
+    X = np.asarray(re, dtype=np.float64) + 1j * np.asarray(im, dtype=np.float64)
+    T = X.shape[0]
+    w = np.asarray(window, dtype=np.float64)
+    y = np.fft.ifft(X, axis=1).real
+    e = 1 if method_type == 0 else 0
+    L = (T - 1) * hop + n
+    out = np.zeros(L) if initial is None else np.asarray(initial, dtype=np.float64).copy()
+    norm = np.zeros(L)
+    for t in range(T):
+        out[t * hop:t * hop + n] += y[t] * w ** e
+        norm[t * hop:t * hop + n] += w ** (e + 1)
+    norm[norm < 1e-6] = 1.0
+    return (out / norm).astype(f32)
+
+
 # ---------------------------------------------------------------------------
 # auditory scales  (src/filterbank/auditory_filterBank.c:1023-1190) -- float32 semantics
 # ---------------------------------------------------------------------------
@@ -675,8 +694,10 @@ def cwt_filterbank(num, n, sr, wavelet=WAVE_MORLET, scale=SCALE_OCTAVE, low=None
 
 
 def cwt(x, num=84, radix2_exp=12, sr=32000, wavelet=WAVE_MORLET, scale=SCALE_OCTAVE, low=None,
-        high=None, bpo=12, gamma=None, beta=None, is_pad=False, bank=None):
-    """`cwtObj_cwt` (cwt_algorithm.c:346-350, 361-483) -> (re, im) [num, N]; row 0 = highest band."""
+        high=None, bpo=12, gamma=None, beta=None, is_pad=False, bank=None, det=False):
+    """`cwtObj_cwt` (cwt_algorithm.c:346-350, 361-483) -> (re, im) [num, N]; row 0 = highest band.
+    det=True: `cwtObj_cwtDet` (:352-358, 485-528): the bank is multiplied by omega_k (float32: 2 pi k / L for k <= L/2,
+    mirrored negative above) and by j before the inverse transform."""
     N = 1 << radix2_exp
     x = np.asarray(x, dtype=np.float64)[:N]
     pad = 0
@@ -687,7 +708,14 @@ def cwt(x, num=84, radix2_exp=12, sr=32000, wavelet=WAVE_MORLET, scale=SCALE_OCT
     if pad:
         x = np.concatenate([x[:pad][::-1], x, x[N - pad:][::-1]])
     X = np.fft.fft(x)
-    y = np.fft.ifft(bank.astype(np.float64) * X[None, :], axis=1)
+    B = bank.astype(np.float64)
+    if det:
+        Lf = B.shape[1]
+        w = np.zeros(Lf, f32)
+        w[:Lf // 2 + 1] = (np.arange(Lf // 2 + 1) * 2 * math.pi / Lf).astype(f32)
+        w[Lf // 2 + 1:] = -w[Lf // 2 - 1:0:-1][:Lf - Lf // 2 - 1]
+        B = (bank * w[None, :]).astype(f32).astype(np.float64) * 1j
+    y = np.fft.ifft(B * X[None, :], axis=1)
     if pad:
         y = y[:, pad:pad + N]
     return y.real.astype(f32), y.imag.astype(f32)

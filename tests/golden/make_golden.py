@@ -99,7 +99,11 @@ def main():
     sm.set_data_norm_value(0.5)
     msp = sm.spectrogram_planes(xsp)
     mcc = sm.mfcc(np.ascontiguousarray(msp.T), 13).T
-    np.savez_compressed(os.path.join(HERE, "next_rows.npz"), energy=energy[:24], chroma_max=chroma_max,
+    wd = af.CWT(12, 10, 48000, wavelet_type=af.WaveletContinueType.MORLET, is_padding=False, _lib=ref)
+    wd.enable_det(True)
+    xdet = noise(7, 1024)
+    det_re, det_im = wd.cwt_det_planes(xdet)
+    np.savez_compressed(os.path.join(HERE, "next_rows.npz"), xdet=xdet, det_re=det_re, det_im=det_im, energy=energy[:24], chroma_max=chroma_max,
                         chroma_p2=chroma_p2, cqcc=cqcc, xsp=xsp, lin=lin, lin_phase=lin_phase,
                         lin_fre=sl.get_fre_band_arr(), lin_bin=sl.get_bin_band_arr(), mel_mag=msp, mel_cc=mcc,
                         mel_fre=sm.get_fre_band_arr(), **std)

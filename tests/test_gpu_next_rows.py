@@ -227,3 +227,95 @@ def test_stft_padding_against_reference_build(torch_cuda, ref_lib):
             (ar, ai), (rr, ri) = a.stft_planes(x), r.stft_planes(x)
             scale = max(np.abs(rr).max(), np.abs(ri).max())
             assert np.abs(ar - rr).max() <= TOL * scale and np.abs(ai - ri).max() <= TOL * scale
+
+
+# ------------------------------------------------------------------ cwtObj_cwtDet
+def test_cwt_det_golden_legacy(cuda_device, golden):
+    g = golden("next_rows.npz")
+    w = af.CWT(12, 10, 48000, wavelet_type=af.WaveletContinueType.MORLET, is_padding=False)
+    re0, im0 = w.cwt_det_planes(g["xdet"])
+    assert not re0.any() and not im0.any()                        # silent no-op before enableDet, like the reference
+    w.enable_det(True)
+    re, im = w.cwt_det_planes(g["xdet"])
+    scale = max(np.abs(g["det_re"]).max(), np.abs(g["det_im"]).max())
+    assert np.abs(re - g["det_re"]).max() <= TOL * scale and np.abs(im - g["det_im"]).max() <= TOL * scale
+    w.cwt_planes(g["xdet"])
+    re2, im2 = w.cwt_det_planes(None)                             # dataArr = NULL: spectrum of the preceding call
+    assert np.array_equal(re2, re) and np.array_equal(im2, im)
+
+
+@pytest.mark.parametrize("wav,pad,r", [(1, False, 12), (0, False, 12), (3, True, 11), (2, False, 10), (4, False, 13), (1, False, 14)])
+def test_cwt_det_batch_vs_oracle(torch_cuda, wav, pad, r):
+    torch = torch_cuda
+    x = np.stack([noise(71, 1 << r), tones(72, 1 << r, 48000)])
+    w = af.CWT(24, r, 48000, wavelet_type=wav, is_padding=pad)
+    w.enable_det(True)
+    re, im = w.cwt_det_batch(torch.from_numpy(x).cuda())
+    for b in range(2):
+        r2, i2 = O.cwt(x[b], 24, r, 48000, wav, O.SCALE_OCTAVE, low=32.703196, is_pad=pad, det=True)
+        scale = max(np.abs(r2).max(), np.abs(i2).max())
+        assert np.abs(re[b].cpu().numpy() - r2).max() <= TOL * scale
+        assert np.abs(im[b].cpu().numpy() - i2).max() <= TOL * scale
+
+
+def test_cwt_det_2pow19_fast_path(torch_cuda):
+    """config-4 length: the warp-level FFT legs with the derivative bank; checked on 3 rows against the oracle."""
+    torch = torch_cuda
+    x = noise(73, 1 << 19)
+    w = af.CWT(84, 19, 48000, wavelet_type=af.WaveletContinueType.MORLET, is_padding=False)
+    w.enable_det(True)
+    re, im = w.cwt_det_batch(torch.from_numpy(x[None]).cuda())
+    r2, i2 = O.cwt(x, 84, 19, 48000, O.WAVE_MORLET, O.SCALE_OCTAVE, low=32.703196, det=True)
+    for row in (0, 41, 83):
+        scale = max(np.abs(r2[row]).max(), np.abs(i2[row]).max())
+        assert np.abs(re[0, row].cpu().numpy() - r2[row]).max() <= TOL * scale
+        assert np.abs(im[0, row].cpu().numpy() - i2[row]).max() <= TOL * scale
+
+
+def test_cwt_det_requires_enable(cuda_device, product_lib):
+    w = af.CWT(12, 10, 48000)
+    x = noise(1, 1024)
+    with pytest.raises(af.lib.AfB200Error):
+        w.cwt_det_batch(x[None])
+
+
+# ------------------------------------------------------------------ stftObj_istft
+from test_next_rows_cpu import ISTFT_CASES, istft_conditioned  # noqa: E402
+
+
+@pytest.mark.parametrize("r,hop,wt,method", ISTFT_CASES + [(13, 2048, 1, 0)])
+def test_istft(torch_cuda, r, hop, wt, method):
+    torch = torch_cuda
+    n = 1 << r
+    x = np.stack([noise(81, 20 * hop + n), tones(82, 20 * hop + n, 16000)])
+    s = af.STFT(r, wt, hop)
+    re, im = s.stft_planes(x[0])                                  # full mirrored planes of the CUDA forward path
+    got = s.istft_planes(re, im, method)                          # legacy entry, host pointers
+    want = O.istft(re, im, n, hop, O.fft_window(wt, n), method)
+    ok = istft_conditioned(n, hop, re.shape[0], O.fft_window(wt, n), method)
+    assert got.shape == want.shape and np.abs(got - want)[ok].max() <= TOL * np.abs(want).max()
+    assert np.abs(got - want).max() <= 1e-2 * np.abs(want).max()
+    # batched device entry on the half-spectrum planes stft_batch produces: round trip on the GPU
+    xd = torch.from_numpy(x).cuda()
+    bre, bim = s.stft_batch(xd)
+    y = s.istft_batch(bre, bim, method)
+    assert tuple(y.shape) == (2, want.shape[0])
+    assert np.abs(y[0].cpu().numpy() - want)[ok].max() <= TOL * np.abs(want).max()
+    if hop <= n // 2 and wt in (1, 2):
+        assert (y[:, n:-n] - xd[:, n:y.shape[1] - n]).abs().max().item() < 1e-4
+    # the reference adds onto the caller's buffer before normalising
+    init = noise(83, want.shape[0])
+    buf = init.copy()
+    af.lib.get_lib().stftObj_istft(s._obj, re.ctypes.data, im.ctypes.data, re.shape[0], method, buf.ctypes.data)
+    want2 = O.istft(re, im, n, hop, O.fft_window(wt, n), method, initial=init)
+    assert np.abs(buf - want2)[ok].max() <= TOL * np.abs(want2).max()
+
+
+def test_istft_against_reference_build(torch_cuda, ref_lib):
+    x = tones(84, 6000, 16000)
+    for wt, method in ((1, 0), (2, 1), (0, 0)):
+        a, r = af.STFT(9, wt, 128), af.STFT(9, wt, 128, _lib=ref_lib)
+        re, im = r.stft_planes(x)
+        ya, yr = a.istft_planes(re, im, method), r.istft_planes(re, im, method)
+        ok = istft_conditioned(512, 128, re.shape[0], O.fft_window(wt, 512), method)
+        assert np.abs(ya - yr)[ok].max() <= TOL * np.abs(yr).max()

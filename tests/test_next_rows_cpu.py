@@ -222,3 +222,57 @@ def test_stft_padding_modes_vs_reference(ref_lib, pos, mode, v1, v2, L, n, hop):
     assert re.shape == re2.shape
     scale = max(np.abs(re).max(), np.abs(im).max(), 1e-30)
     assert np.abs(re - re2).max() <= TOL * scale and np.abs(im - im2).max() <= TOL * scale
+
+
+# ---------------- cwtObj_cwtDet: oracle vs golden and vs the reference ----------------
+def test_oracle_cwt_det_golden(golden):
+    g = golden("next_rows.npz")
+    re, im = O.cwt(g["xdet"], 12, 10, 48000, O.WAVE_MORLET, O.SCALE_OCTAVE, low=32.703196, det=True)
+    scale = max(np.abs(g["det_re"]).max(), np.abs(g["det_im"]).max())
+    assert np.abs(re - g["det_re"]).max() <= TOL * scale and np.abs(im - g["det_im"]).max() <= TOL * scale
+
+
+@pytest.mark.parametrize("wav,pad,r", [(1, False, 12), (0, False, 12), (3, True, 11), (2, False, 10), (4, False, 12), (5, True, 10)])
+def test_cwt_det_vs_reference(ref_lib, wav, pad, r):
+    x = noise(71, 1 << r)
+    w = af.CWT(36, r, 48000, wavelet_type=wav, is_padding=pad, _lib=ref_lib)
+    w.enable_det(True)
+    w.cwt_planes(x)
+    re, im = w.cwt_det_planes(None)                              # reuses the spectrum of the cwt call
+    re1, im1 = w.cwt_det_planes(x)
+    assert np.array_equal(re, re1) and np.array_equal(im, im1)
+    r2, i2 = O.cwt(x, 36, r, 48000, wav, O.SCALE_OCTAVE, low=32.703196, is_pad=pad, det=True)
+    scale = max(np.abs(re).max(), np.abs(im).max())
+    assert np.abs(re - r2).max() <= TOL * scale and np.abs(im - i2).max() <= TOL * scale
+
+
+# ---------------- stftObj_istft: oracle vs the reference ----------------
+def istft_conditioned(n, hop, T, window, method):
+    """Samples whose window-sum normaliser is not tiny: elsewhere the division amplifies float32 rounding of the
+    frames (the reference divides by sums down to 1e-6), so only a loose bound makes sense there."""
+    w = np.asarray(window, dtype=np.float64) ** (2 if method == 0 else 1)
+    norm = np.zeros((T - 1) * hop + n)
+    for t in range(T):
+        norm[t * hop:t * hop + n] += w
+    return norm > 1e-2
+
+
+ISTFT_CASES = [(9, 128, 1, 0), (9, 128, 1, 1), (10, 256, 2, 0), (8, 64, 0, 0), (8, 256, 1, 1), (11, 512, 4, 0), (6, 100, 1, 0)]
+
+
+@pytest.mark.parametrize("r,hop,wt,method", ISTFT_CASES)
+def test_istft_vs_reference(ref_lib, r, hop, wt, method):
+    n = 1 << r
+    x = noise(81, 20 * hop + n)
+    s = af.STFT(r, wt, hop, _lib=ref_lib)
+    re, im = s.stft_planes(x)
+    got = s.istft_planes(re, im, method)
+    want = O.istft(re, im, n, hop, O.fft_window(wt, n), method)
+    assert got.shape == want.shape
+    ok = istft_conditioned(n, hop, re.shape[0], O.fft_window(wt, n), method)
+    assert np.abs(got - want)[ok].max() <= TOL * np.abs(want).max() and np.abs(got - want).max() <= 1e-2 * np.abs(want).max()
+    if hop <= n // 2 and wt in (1, 2):                   # enough overlap: the round trip reproduces the interior
+        assert np.abs(got[n:-n] - x[n:len(got) - n]).max() < 1e-4
+    # reference-layout front door (complex [n/2+1, T] in)
+    z = (re + 1j * im).T[:n // 2 + 1]
+    assert np.abs(s.istft(z, method) - want)[ok].max() <= TOL * np.abs(want).max()
