@@ -10,6 +10,7 @@ from .bft import BFT  # noqa: F401
 from .xxcc import XXCC  # noqa: F401
 from .cqt import CQT  # noqa: F401
 from .cwt import CWT  # noqa: F401
+from .pwt import PWT  # noqa: F401
 from .spectrogram import Spectrogram, MelSpectrogram, BarkSpectrogram, ErbSpectrogram  # noqa: F401
 from . import lib  # noqa: F401
 

@@ -70,6 +70,15 @@ REFERENCE_API = {
     "cwtObj_enableDet": (None, [vp, C.c_int]),
     "cwtObj_cwtDet": (None, [vp, vp, vp, vp]),
     "cwtObj_free": (None, [vp]),
+    # ---- PWT (src/pwt_algorithm.h:16-31)
+    "pwtObj_new": (C.c_int, [P(vp), C.c_int, C.c_int, c_int_p, c_float_p, c_float_p, c_int_p, c_int_p, c_int_p,
+                             c_int_p, c_int_p]),
+    "pwtObj_getFreBandArr": (vp, [vp]),
+    "pwtObj_getBinBandArr": (vp, [vp]),
+    "pwtObj_pwt": (None, [vp, vp, vp, vp]),
+    "pwtObj_enableDet": (None, [vp, C.c_int]),
+    "pwtObj_pwtDet": (None, [vp, vp, vp, vp]),
+    "pwtObj_free": (None, [vp]),
     # ---- Spectrogram (front door; src/spectrogram_algorithm.h:40-119)
     "spectrogramObj_new": (C.c_int, [P(vp), C.c_int, c_int_p, c_float_p, c_float_p, c_int_p, c_int_p, c_int_p,
                                      c_int_p, c_int_p, c_int_p, c_int_p, c_int_p, c_int_p]),
@@ -125,6 +134,9 @@ EXTENSION_API = {
     "cwtObj_cwtBatch": (C.c_int, [vp, vp, C.c_int, vp, vp, C.c_int, vp]),
     "cwtObj_cwtDetBatch": (C.c_int, [vp, vp, C.c_int, vp, vp, C.c_int, vp]),
     "cwtObj_getFilterBankArr": (C.c_int, [vp, vp]),
+    "pwtObj_pwtBatch": (C.c_int, [vp, vp, C.c_int, vp, vp, C.c_int, vp]),
+    "pwtObj_pwtDetBatch": (C.c_int, [vp, vp, C.c_int, vp, vp, C.c_int, vp]),
+    "pwtObj_getFilterBankArr": (C.c_int, [vp, vp]),
     "afb200_window": (C.c_int, [C.c_int, C.c_int, vp]),
     "afb200_auditoryFilterBank": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
                                             C.c_float, C.c_float, C.c_int, vp, vp, vp]),

@@ -181,6 +181,8 @@ typedef struct {
     AfWavelet wavelet;
     const float *scaleArr;   /* device, num */
     int det;                 /* 1: multiply the bank by j*omega (cwtObj_cwtDet) */
+    const float *bankTable;  /* device, num x bankWidth: tabulated bank (PWT) instead of the closed-form wavelet */
+    int bankWidth;
 } AfCwtArgs;
 size_t af_cwt_workspace_bytes(const AfCwtArgs *a);
 /* data == NULL: skip the forward transform and reuse the spectra a previous call left in `workspace` */

@@ -6,6 +6,7 @@
 #include <stdlib.h>
 #include <string.h>
 #include "../af_internal.h"
+#include "../../../include/afb200_pwt.h"
 
 struct OpaqueCWT {
     int num, radix2Exp, dataLength, padLength, fftLength, log2fft, samplate, binPerOctave;
@@ -19,6 +20,8 @@ struct OpaqueCWT {
     void *stream;
     float *dScale;
     AfDevBuf dIn, dWork, dOutRe, dOutIm;
+    float *bankHost, *dBank;       /* PWT: auditory bank num x (fftLength/2+1) instead of a wavelet family */
+    int bankWidth;
     int detEnabled;                /* cwtObj_enableDet */
     int haveSpec;                  /* dWork starts with the spectrum of the last single-clip call */
 };
@@ -77,6 +80,7 @@ static int cwt_device(CWTObj c) {
     if (c->devReady) return AF_OK;
     if ((rc = af_stream_create(&c->stream))) return rc;
     if ((rc = af_dev_upload((void **)&c->dScale, c->scaleArr, sizeof(float) * (size_t)c->num))) return rc;
+    if (c->bankHost && (rc = af_dev_upload((void **)&c->dBank, c->bankHost, sizeof(float) * (size_t)c->num * c->bankWidth))) return rc;
     c->devReady = 1;
     return AF_OK;
 }
@@ -86,6 +90,7 @@ static void cwt_args(CWTObj c, int batch, int det, AfCwtArgs *a) {
     a->det = det;
     a->log2n = c->log2fft; a->num = c->num; a->batch = batch; a->padLength = c->padLength;
     a->dataLength = c->dataLength; a->wavelet = c->wavelet; a->scaleArr = c->dScale;
+    a->bankTable = c->dBank; a->bankWidth = c->bankWidth;
 }
 
 /* dData [batch x N] -> planes [batch x num x N]; the batch is cut into chunks that fit the workspace */
@@ -175,6 +180,7 @@ int cwtObj_getFilterBankArr(CWTObj c, float *bank) {
     for (int i = 0; i < c->num; i++)
         for (int k = 0; k < n; k++) {
             float v = 0.0f;
+            if (c->bankHost) { bank[(size_t)i * n + k] = k < c->bankWidth ? c->bankHost[(size_t)i * c->bankWidth + k] : 0.0f; continue; }
             if (k <= n / 2) { float omega = (float)((double)k * 2.0 * M_PI / (double)n); v = af_wavelet_eval(&c->wavelet, c->scaleArr[i] * omega); }
             bank[(size_t)i * n + k] = v;
         }
@@ -184,8 +190,93 @@ int cwtObj_getFilterBankArr(CWTObj c, float *bank) {
 void cwtObj_free(CWTObj c) {
     if (!c) return;
     af_devbuf_free(&c->dIn); af_devbuf_free(&c->dWork); af_devbuf_free(&c->dOutRe); af_devbuf_free(&c->dOutIm);
-    af_dev_free(c->dScale);
+    af_dev_free(c->dScale); af_dev_free(c->dBank);
+    free(c->bankHost);
     af_stream_destroy(c->stream);
     free(c->freBandArr); free(c->binBandArr); free(c->scaleArr);
     free(c);
+}
+
+/* ================= PWT: pseudo wavelet transform (src/pwt_algorithm.h:16-31, src/pwt_algorithm.c:63-348) =================
+ * Same FFT -> bank x spectrum -> IFFT structure as the CWT with the auditory filter bank of the BFT path
+ * (auditory_filterBank with isPseudo = 1: rows of fftLength entries, zero above fftLength/2) instead of an analytic
+ * wavelet, so the object is a CWT core whose kernels read the bank from a table. */
+struct OpaquePWT { struct OpaqueCWT c; };
+
+int pwtObj_new(PWTObj *out, int num, int radix2Exp, int *samplate, float *lowFre, float *highFre, int *binPerOctave,
+               SpectralFilterBankScaleType *scaleType, SpectralFilterBankStyleType *styleType,
+               SpectralFilterBankNormalType *normalType, int *isPadding) {
+    if (!out) return -1;
+    *out = NULL;
+    if (radix2Exp < 1 || radix2Exp > 30) { printf("radix2Exp is error!\n"); return -100; }
+    int sr = 32000;
+    if (samplate && *samplate > 0 && *samplate <= 196000) sr = *samplate;
+    SpectralFilterBankScaleType scale = scaleType ? *scaleType : SpectralFilterBankScale_Octave;
+    if (scale > SpectralFilterBankScale_Log) { printf("scaleType is error!\n"); return 1; }
+    int bpo = 12;
+    if (binPerOctave && *binPerOctave >= 4 && *binPerOctave <= 48) bpo = *binPerOctave;
+    const int N = 1 << radix2Exp;
+    AfRange range;
+    if (af_revise_range(num, N, sr, lowFre, highFre, scale, bpo, &range)) {
+        printf(scale == SpectralFilterBankScale_Linear ? "scale linear: lowFre and num is large, overflow error\n"
+                                                        : "scale log: lowFre and num is large, overflow error!\n");
+        return -1;
+    }
+    if (num < 2 || num > N / 2 + 1) { printf("num is error!\n"); return -1; }
+    int pad = 0;
+    if (isPadding && *isPadding) pad = N <= 1e5 ? N / 2 : (int)ceilf(log2f((float)N));
+    const int fftLength = N + 2 * pad;
+    if (fftLength & (fftLength - 1)) {
+        af_fail(AF_ERR_UNSUPPORTED, "pwtObj_new: isPadding with 2^%d samples gives a non power-of-two length %d "
+                "(the reference falls back to an O(N^2) dense DFT there); use isPadding=0", radix2Exp, fftLength);
+        return -2;
+    }
+    PWTObj p = (PWTObj)calloc(1, sizeof(struct OpaquePWT));
+    if (!p) return -1;
+    CWTObj c = &p->c;
+    c->num = num; c->radix2Exp = radix2Exp; c->dataLength = N; c->padLength = pad; c->fftLength = fftLength;
+    c->log2fft = radix2Exp + (pad ? 1 : 0);
+    c->samplate = sr; c->binPerOctave = bpo; c->lowFre = range.low; c->highFre = range.high; c->scaleType = scale;
+    c->bankWidth = fftLength / 2 + 1;
+    c->bankHost = (float *)calloc((size_t)num * c->bankWidth, sizeof(float));
+    c->freBandArr = (float *)calloc((size_t)num + 2, sizeof(float));
+    c->binBandArr = (int *)calloc((size_t)num + 2, sizeof(int));
+    c->scaleArr = (float *)calloc((size_t)num, sizeof(float));
+    if (!c->bankHost || !c->freBandArr || !c->binBandArr || !c->scaleArr) { pwtObj_free(p); return -1; }
+    if (af_auditory_filterbank(num, fftLength, sr, scale, styleType ? (int)*styleType : SpectralFilterBankStyle_Slaney,
+                               normalType ? (int)*normalType : SpectralFilterBankNormal_None, c->lowFre, c->highFre, bpo,
+                               c->bankHost, c->freBandArr, c->binBandArr)) { pwtObj_free(p); return -2; }
+    *out = p;
+    return 0;
+}
+
+float *pwtObj_getFreBandArr(PWTObj p) { return p ? p->c.freBandArr : NULL; }
+int *pwtObj_getBinBandArr(PWTObj p) { return p ? p->c.binBandArr : NULL; }
+void pwtObj_enableDet(PWTObj p, int flag) { if (p) cwtObj_enableDet(&p->c, flag); }
+int pwtObj_pwtBatch(PWTObj p, const float *data, int batch, float *mReal3, float *mImag3, int memKind, void *stream) {
+    if (!p || !data) return af_fail(AF_ERR_ARG, "pwtObj_pwtBatch: bad argument");
+    return cwt_batch(&p->c, data, batch, 0, mReal3, mImag3, memKind, stream, "pwtObj_pwtBatch");
+}
+int pwtObj_pwtDetBatch(PWTObj p, const float *data, int batch, float *mReal3, float *mImag3, int memKind, void *stream) {
+    if (!p) return af_fail(AF_ERR_ARG, "pwtObj_pwtDetBatch: bad argument");
+    if (!p->c.detEnabled) return af_fail(AF_ERR_ARG, "pwtObj_pwtDetBatch: call pwtObj_enableDet(obj, 1) first");
+    return cwt_batch(&p->c, data, batch, 1, mReal3, mImag3, memKind, stream, "pwtObj_pwtDetBatch");
+}
+void pwtObj_pwt(PWTObj p, float *dataArr, float *mRealArr3, float *mImageArr3) {
+    if (!p || !dataArr) return;
+    pwtObj_pwtBatch(p, dataArr, 1, mRealArr3, mImageArr3, AFB200_MEM_HOST, NULL);
+}
+void pwtObj_pwtDet(PWTObj p, float *dataArr, float *mRealArr3, float *mImageArr3) {
+    if (!p || !p->c.detEnabled) return;
+    pwtObj_pwtDetBatch(p, dataArr, 1, mRealArr3, mImageArr3, AFB200_MEM_HOST, NULL);
+}
+int pwtObj_getFilterBankArr(PWTObj p, float *bank) { return p ? cwtObj_getFilterBankArr(&p->c, bank) : af_fail(AF_ERR_ARG, "pwtObj_getFilterBankArr: bad argument"); }
+void pwtObj_free(PWTObj p) {
+    if (!p) return;
+    CWTObj c = &p->c;
+    af_devbuf_free(&c->dIn); af_devbuf_free(&c->dWork); af_devbuf_free(&c->dOutRe); af_devbuf_free(&c->dOutIm);
+    af_dev_free(c->dScale); af_dev_free(c->dBank);
+    af_stream_destroy(c->stream);
+    free(c->bankHost); free(c->freBandArr); free(c->binBandArr); free(c->scaleArr);
+    free(p);
 }

@@ -119,6 +119,8 @@ struct CwtParams {
     float *outRe, *outIm;     // batch x num x dataLength
     const float *scaleArr;    // num
     int det;                  // 1: bank * omega * j (cwtObj_cwtDet, src/cwt_algorithm.c:485-528, 426-437)
+    const float *bankTable;   // PWT: tabulated bank rows [num][bankWidth] over bins 0..bankWidth-1 instead of a wavelet
+    int bankWidth;
     int log2N, log2N1, log2N2, N, N1, N2;
     int dataLength, padLength, num, batch;
     int wType; float g, b, factor;
@@ -137,11 +139,12 @@ __device__ __forceinline__ float load_padded(const CwtParams &p, const float *x,
 // wavelet(s*omega_k) * X[k]  (cwtObj_cwt) or  j * omega_k * wavelet(s*omega_k) * X[k]  (cwtObj_cwtDet: the reference
 // multiplies the bank by wArr[k] = 2 pi k / N in float and then forms (-bd * im, bd * re), src/cwt_algorithm.c:426-437,
 // 500-512).  omega_k = 2 pi k / N for k <= N/2, negative above, where every wavelet family is zero.
-__device__ __forceinline__ float2 bank_times_spec(const CwtParams &p, float s, int k, float2 x) {
+__device__ __forceinline__ float2 bank_times_spec(const CwtParams &p, float s, int sIdx, int k, float2 x) {
     float wv = 0.0f, omega = 0.0f;
     if (k <= p.N / 2) {
         omega = (float)((double)k * 2.0 * M_PI / (double)p.N);
-        wv = wavelet_eval(p.wType, p.g, p.b, p.factor, s * omega);
+        if (p.bankTable) wv = k < p.bankWidth ? p.bankTable[(size_t)sIdx * p.bankWidth + k] : 0.0f;   // pwtObj_pwt
+        else wv = wavelet_eval(p.wType, p.g, p.b, p.factor, s * omega);
     }
     if (!p.det) return make_float2(wv * x.x, wv * x.y);
     const float bd = wv * omega;
@@ -173,7 +176,7 @@ __global__ void k_cwt_cols(CwtParams p) {
         if (MODE == 0) {
             v = make_float2(load_padded(p, p.data + (size_t)clip * p.dataLength, k), 0.0f);
         } else {
-            v = bank_times_spec(p, s, k, p.spec[(size_t)clip * p.N + k]);
+            v = bank_times_spec(p, s, sIdx, k, p.spec[(size_t)clip * p.N + k]);
         }
         a[(size_t)c * pitch + i] = v;
     }
@@ -300,7 +303,7 @@ __global__ void __launch_bounds__(kWCols * 32) k_cwt_cols_w(CwtParams p) {
         if (MODE == 0) {
             v = c_pack(load_padded(p, p.data + (size_t)clip * p.dataLength, k), 0.0f);
         } else {
-            const float2 y = bank_times_spec(p, s, k, p.spec[(size_t)clip * p.N + k]);
+            const float2 y = bank_times_spec(p, s, item % p.num, k, p.spec[(size_t)clip * p.N + k]);
             v = c_pack(y.x, -y.y);                                             // conj: inverse transform via forward DFT
         }
         tile[(size_t)c * kWColPitch + i] = v;
@@ -435,6 +438,7 @@ void fill_params(const AfCwtArgs *a, CwtParams *p) {
     p->dataLength = a->dataLength; p->padLength = a->padLength; p->num = a->num; p->batch = a->batch;
     p->scaleArr = a->scaleArr;
     p->det = a->det;
+    p->bankTable = a->bankTable; p->bankWidth = a->bankWidth;
     p->itemBase = 0;
     p->wType = a->wavelet.waveletType; p->g = a->wavelet.gamma; p->b = a->wavelet.beta; p->factor = (float)a->wavelet.factor;
     const size_t budget = (size_t)(getenv("AFB200_CWT_LEG_KB") ? atoi(getenv("AFB200_CWT_LEG_KB")) : 72) * 1024;   // per-CTA leg buffers: small enough for 2-3 CTAs per SM so load / FFT / store phases of different CTAs overlap

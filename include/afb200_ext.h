@@ -19,6 +19,7 @@
 #include "afb200_cqt.h"
 #include "afb200_cwt.h"
 #include "afb200_spectrogram.h"
+#include "afb200_pwt.h"
 #ifdef __cplusplus
 extern "C" {
 #endif
@@ -93,6 +94,10 @@ int cwtObj_cwtBatch(CWTObj cwtObj, const float *data, int batch, float *mReal4, 
 int cwtObj_cwtDetBatch(CWTObj cwtObj, const float *data, int batch, float *mReal4, float *mImag4,
                        int memKind, void *stream);
 int cwtObj_getFilterBankArr(CWTObj cwtObj, float *bank /* num x fftLength host */);
+/* PWT: data batch x 2^radix2Exp -> planes batch x num x 2^radix2Exp */
+int pwtObj_pwtBatch(PWTObj pwtObj, const float *data, int batch, float *mReal3, float *mImag3, int memKind, void *stream);
+int pwtObj_pwtDetBatch(PWTObj pwtObj, const float *data, int batch, float *mReal3, float *mImag3, int memKind, void *stream);
+int pwtObj_getFilterBankArr(PWTObj pwtObj, float *bank /* num x fftLength host */);
 
 /* setup-time table builders, exported for parity tests against the reference's
  * window_calFFTWindow (src/dsp/flux_window.c:890-940), auditory_filterBank

@@ -877,3 +877,21 @@ def spectrogram_linear_bands(sr, radix2_exp, low_idx, num):
     n = 1 << radix2_exp
     grid = _linspace_f32(f32(0), f32(sr / 2.0), n // 2 + 1)
     return grid[low_idx:low_idx + num].copy(), np.arange(low_idx, low_idx + num, dtype=np.int32)
+
+
+def pwt(x, num=84, radix2_exp=12, sr=32000, low=None, high=None, bpo=12, scale=SCALE_OCTAVE, style=STYLE_SLANEY,
+        norm=NORM_NONE, is_pad=False, det=False):
+    """`pwtObj_pwt` / `pwtObj_pwtDet` (src/pwt_algorithm.c:63-348, 392-520): the CWT structure with the auditory bank of
+    `auditory_filterBank(isPseudo=1)` (rows of fftLength entries, zero above fftLength/2) built for the PADDED length.
+    Range rules = `bft_revise_range` with the unpadded length (:135-195)."""
+    N = 1 << radix2_exp
+    lo, hi, _, _ = bft_revise_range(num, N, sr, low, high, scale, bpo)
+    pad = 0
+    if is_pad:
+        pad = N // 2 if N <= 1e5 else int(math.ceil(math.log2(N)))
+    Lf = N + 2 * pad
+    half, fre, bins = auditory_filterbank(num, Lf, sr, scale, style, norm, float(lo), float(hi), bpo)
+    bank = np.zeros((num, Lf), f32)
+    bank[:, :Lf // 2 + 1] = half
+    re, im = cwt(x, num, radix2_exp, sr, is_pad=is_pad, bank=bank, det=det)
+    return re, im, fre, bins

@@ -319,3 +319,39 @@ def test_istft_against_reference_build(torch_cuda, ref_lib):
         ya, yr = a.istft_planes(re, im, method), r.istft_planes(re, im, method)
         ok = istft_conditioned(512, 128, re.shape[0], O.fft_window(wt, 512), method)
         assert np.abs(ya - yr)[ok].max() <= TOL * np.abs(yr).max()
+
+
+# ------------------------------------------------------------------ PWT
+from test_next_rows_cpu import PWT_CASES, _pwt_oracle  # noqa: E402
+
+
+@pytest.mark.parametrize("kw", PWT_CASES)
+def test_pwt_vs_oracle(torch_cuda, kw):
+    torch = torch_cuda
+    r = 12
+    x = np.stack([noise(91, 1 << r), tones(92, 1 << r, kw["samplate"])])
+    p = af.PWT(radix2_exp=r, **kw)
+    re, im = p.pwt_planes(x[0])                                   # legacy entry
+    r2, i2, fre, bins = _pwt_oracle(x[0], kw, r)
+    scale = max(np.abs(r2).max(), np.abs(i2).max())
+    assert np.abs(re - r2).max() <= TOL * scale and np.abs(im - i2).max() <= TOL * scale
+    assert np.array_equal(p.get_bin_band_arr(), bins)
+    bre, bim = p.pwt_batch(torch.from_numpy(x).cuda())            # batched device entry
+    assert np.array_equal(bre[0].cpu().numpy(), re) and np.array_equal(bim[0].cpu().numpy(), im)
+    r3, i3, _, _ = _pwt_oracle(x[1], kw, r)
+    s3 = max(np.abs(r3).max(), np.abs(i3).max())
+    assert np.abs(bre[1].cpu().numpy() - r3).max() <= TOL * s3 and np.abs(bim[1].cpu().numpy() - i3).max() <= TOL * s3
+    p.enable_det(True)
+    p.pwt_planes(x[0])                                            # single-clip call: its spectrum stays in the workspace
+    dr, di = p.pwt_det_planes(None)
+    d2, e2, _, _ = _pwt_oracle(x[0], kw, r, det=True)
+    sd = max(np.abs(d2).max(), np.abs(e2).max())
+    assert np.abs(dr - d2).max() <= TOL * sd and np.abs(di - e2).max() <= TOL * sd
+
+
+def test_pwt_long_clip_and_reference_build(torch_cuda, ref_lib):
+    x = tones(93, 1 << 14, 32000)
+    a, r = af.PWT(84, 14, 32000, is_padding=False), af.PWT(84, 14, 32000, is_padding=False, _lib=ref_lib)
+    (ar, ai), (rr, ri) = a.pwt_planes(x), r.pwt_planes(x)
+    scale = max(np.abs(rr).max(), np.abs(ri).max())
+    assert np.abs(ar - rr).max() <= TOL * scale and np.abs(ai - ri).max() <= TOL * scale

@@ -276,3 +276,50 @@ def test_istft_vs_reference(ref_lib, r, hop, wt, method):
     # reference-layout front door (complex [n/2+1, T] in)
     z = (re + 1j * im).T[:n // 2 + 1]
     assert np.abs(s.istft(z, method) - want)[ok].max() <= TOL * np.abs(want).max()
+
+
+# ---------------- PWT: tables and oracle vs the reference ----------------
+PWT_CASES = [dict(num=84, samplate=32000, is_padding=False), dict(num=84, samplate=32000, is_padding=True),
+             dict(num=40, samplate=16000, scale_type=2, is_padding=False, normal_type=1),
+             dict(num=64, samplate=48000, scale_type=3, style_type=1, is_padding=True),
+             dict(num=48, samplate=32000, scale_type=5, bin_per_octave=24, low_fre=65.4, is_padding=False),
+             dict(num=32, samplate=22050, scale_type=4, style_type=2, is_padding=False)]
+
+
+def _pwt_oracle(x, kw, r, det=False):
+    return O.pwt(x, kw["num"], r, kw["samplate"], low=kw.get("low_fre"), bpo=kw.get("bin_per_octave", 12),
+                 scale=kw.get("scale_type", 5), style=kw.get("style_type", 0), norm=kw.get("normal_type", 0),
+                 is_pad=kw["is_padding"], det=det)
+
+
+@pytest.mark.parametrize("kw", PWT_CASES[:5])
+def test_pwt_vs_reference(ref_lib, product_lib, kw):
+    x = noise(91, 4096)
+    w, p = af.PWT(radix2_exp=12, _lib=ref_lib, **kw), af.PWT(radix2_exp=12, **kw)
+    assert np.array_equal(w.get_bin_band_arr(), p.get_bin_band_arr())             # product tables == reference tables
+    np.testing.assert_allclose(p.get_fre_band_arr(), w.get_fre_band_arr(), rtol=2e-6, atol=1e-3)
+    re, im = w.pwt_planes(x)
+    r2, i2, fre, bins = _pwt_oracle(x, kw, 12)
+    scale = max(np.abs(re).max(), np.abs(im).max())
+    assert np.abs(re - r2).max() <= TOL * scale and np.abs(im - i2).max() <= TOL * scale
+    assert np.array_equal(bins, w.get_bin_band_arr())
+    w.enable_det(True)
+    dr, di = w.pwt_det_planes(None)
+    d2, e2, _, _ = _pwt_oracle(x, kw, 12, det=True)
+    sd = max(np.abs(dr).max(), np.abs(di).max())
+    assert np.abs(dr - d2).max() <= TOL * sd and np.abs(di - e2).max() <= TOL * sd
+
+
+def test_pwt_new_status_codes(product_lib):
+    obj = C.c_void_p()
+    none = [None] * 8
+    assert product_lib.pwtObj_new(C.byref(obj), 84, 31, *none) == -100
+    assert product_lib.pwtObj_new(C.byref(obj), 1, 12, *none) == -1
+    assert product_lib.pwtObj_new(C.byref(obj), 400, 12, *none) == -1                   # octave overflow
+    from audioflux_b200.capi import opt_int
+    a = list(none); a[4] = opt_int(9)
+    assert product_lib.pwtObj_new(C.byref(obj), 84, 12, *a) == 1                        # scale > Log
+    a = list(none); a[7] = opt_int(1)
+    assert product_lib.pwtObj_new(C.byref(obj), 84, 19, *a) == -2                       # padding -> non power of two
+    assert product_lib.pwtObj_new(C.byref(obj), 84, 12, *none) == 0
+    product_lib.pwtObj_free(obj)
