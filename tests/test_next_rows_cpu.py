@@ -283,7 +283,7 @@ PWT_CASES = [dict(num=84, samplate=32000, is_padding=False), dict(num=84, sampla
              dict(num=40, samplate=16000, scale_type=2, is_padding=False, normal_type=1),
              dict(num=64, samplate=48000, scale_type=3, style_type=1, is_padding=True),
              dict(num=48, samplate=32000, scale_type=5, bin_per_octave=24, low_fre=65.4, is_padding=False),
-             dict(num=32, samplate=22050, scale_type=4, style_type=2, is_padding=False)]
+             dict(num=32, samplate=22050, scale_type=4, style_type=5, normal_type=2, is_padding=False)]
 
 
 def _pwt_oracle(x, kw, r, det=False):
