@@ -119,6 +119,7 @@ struct CwtParams {
     float *outRe, *outIm;     // batch x num x dataLength
     const float *scaleArr;    // num
     int det;                  // 1: bank * omega * j (cwtObj_cwtDet, src/cwt_algorithm.c:485-528, 426-437)
+    float omegaHi, omegaLo;   // 2 pi / N = omegaHi + omegaLo
     const float *bankTable;   // PWT: tabulated bank rows [num][bankWidth] over bins 0..bankWidth-1 instead of a wavelet
     int bankWidth;
     int log2N, log2N1, log2N2, N, N1, N2;
@@ -142,7 +143,9 @@ __device__ __forceinline__ float load_padded(const CwtParams &p, const float *x,
 __device__ __forceinline__ float2 bank_times_spec(const CwtParams &p, float s, int sIdx, int k, float2 x) {
     float wv = 0.0f, omega = 0.0f;
     if (k <= p.N / 2) {
-        omega = (float)((double)k * 2.0 * M_PI / (double)p.N);
+        // omega_k = float(2 pi k / N) as the reference tabulates it (double product, rounded once): k * (hi + lo) with
+        // hi + lo = 2 pi / N split into two floats gives the same value without FP64 instructions (1/64 rate here)
+        omega = fmaf((float)k, p.omegaHi, (float)k * p.omegaLo);
         if (p.bankTable) wv = k < p.bankWidth ? p.bankTable[(size_t)sIdx * p.bankWidth + k] : 0.0f;   // pwtObj_pwt
         else wv = wavelet_eval(p.wType, p.g, p.b, p.factor, s * omega);
     }
@@ -260,6 +263,14 @@ constexpr int kWCols = 8;             // columns (= warps) per CTA in the column
 constexpr int kWColPitch = 1056;      // c64 per column slot: 1024 points + room for the 33 x 32 float transpose plane
 constexpr int kWRows = 16;            // rows per CTA in the rows kernel (2 per warp)
 constexpr int kWRowPitch = 520;       // c64 per row slot
+// Both tiles are filled / drained by threads that walk ACROSS slots (8 columns or 16 rows per index) while the FFT
+// warps walk ALONG one slot.  The slot pitches are multiples of 16 c64 (the float transpose planes inside a slot
+// rely on it), so the across-walk would hit one 8-byte bank pair 8 times; XOR-ing the low index bits with the slot
+// number makes it conflict-free and leaves the along-walk (16 consecutive entries of one slot) a permutation of the
+// same 128 bytes.  (ncu before: 66 % / 59 % of the shared wavefronts of the two kernels were conflict replays; the
+// kernels are latency-bound though, so this bought only 1.4 %.)
+__device__ __forceinline__ int wcol_idx(int c, int i) { return c * kWColPitch + (i ^ (2 * c)); }
+__device__ __forceinline__ int wrow_idx(int r, int k) { return r * kWRowPitch + (k ^ (r & 15)); }
 
 // 32 x 32 complex transpose of a warp's register tile through a 33-padded float plane (real, then imaginary)
 __device__ __forceinline__ void warp_transpose32(c64 (&z)[32], float *plane, int lane, const c64 *srcBr /* values at AF_BR5 */) {
@@ -287,6 +298,7 @@ __global__ void __launch_bounds__(kWCols * 32) k_cwt_cols_w(CwtParams p) {
     c64 *tile = reinterpret_cast<c64 *>(smemRaw);                              // [kWCols][kWColPitch]
     float2 *tw1 = reinterpret_cast<float2 *>(tile + (size_t)kWCols * kWColPitch);   // [32 ka][32 n1] W_1024^(n1 ka)
     float2 *tf = tw1 + 1024;                                                   // [N2] W_N^j (fine inter-leg twiddle)
+    float2 *t1k = tf + p.N2;                                                   // [1024] W_1024^j (coarse inter-leg twiddle)
     const int N2 = p.N2;
     const int item = p.itemBase + blockIdx.x;
     const int clip = MODE == 0 ? item : item / p.num;
@@ -296,6 +308,7 @@ __global__ void __launch_bounds__(kWCols * 32) k_cwt_cols_w(CwtParams p) {
 
     for (int j = threadIdx.x; j < 1024; j += blockDim.x) tw1[j] = cw((j >> 5) * (j & 31), 1024, -1.0f);
     for (int j = threadIdx.x; j < N2; j += blockDim.x) tf[j] = cw(j, p.N, -1.0f);
+    for (int j = threadIdx.x; j < 1024; j += blockDim.x) t1k[j] = cw(j, 1024, -1.0f);
     for (int e = threadIdx.x; e < 1024 * kWCols; e += blockDim.x) {
         const int i = e / kWCols, c = e - i * kWCols;
         const int k = i * N2 + col0 + c;
@@ -303,10 +316,11 @@ __global__ void __launch_bounds__(kWCols * 32) k_cwt_cols_w(CwtParams p) {
         if (MODE == 0) {
             v = c_pack(load_padded(p, p.data + (size_t)clip * p.dataLength, k), 0.0f);
         } else {
-            const float2 y = bank_times_spec(p, s, item % p.num, k, p.spec[(size_t)clip * p.N + k]);
+            // every wavelet family / bank is zero above N/2: do not fetch that half of the spectrum at all
+            const float2 y = k <= p.N / 2 ? bank_times_spec(p, s, item % p.num, k, p.spec[(size_t)clip * p.N + k]) : make_float2(0.0f, 0.0f);
             v = c_pack(y.x, -y.y);                                             // conj: inverse transform via forward DFT
         }
-        tile[(size_t)c * kWColPitch + i] = v;
+        tile[wcol_idx(c, i)] = v;
     }
     __syncthreads();
 
@@ -314,7 +328,7 @@ __global__ void __launch_bounds__(kWCols * 32) k_cwt_cols_w(CwtParams p) {
         c64 *colp = tile + (size_t)warp * kWColPitch;
         c64 z[32], y[32];
 #pragma unroll
-        for (int j = 0; j < 32; j++) z[j] = colp[lane + 32 * j];
+        for (int j = 0; j < 32; j++) z[j] = tile[wcol_idx(warp, lane + 32 * j)];
         __syncwarp();
         af_fft32(z);
 #pragma unroll
@@ -329,9 +343,9 @@ __global__ void __launch_bounds__(kWCols * 32) k_cwt_cols_w(CwtParams p) {
             if (N2 > 1) {
                 const int prod = col * k1;                                     // W_N^prod = W_1024^(prod / N2) * W_N^(prod % N2)
                 const int hi = prod >> p.log2N2;
-                v = c_mul(v, c_mul(c_from(cw(hi, 1024, -1.0f)), c_from(tf[prod & (N2 - 1)])));
+                v = c_mul(v, c_mul(c_from(t1k[hi & 1023]), c_from(tf[prod & (N2 - 1)])));
             }
-            colp[k1] = v;
+            tile[wcol_idx(warp, k1)] = v;
         }
     }
     __syncthreads();
@@ -339,7 +353,7 @@ __global__ void __launch_bounds__(kWCols * 32) k_cwt_cols_w(CwtParams p) {
     for (int e = threadIdx.x; e < 1024 * kWCols; e += blockDim.x) {
         const int k1 = e / kWCols, c = e - k1 * kWCols;
         float re, im;
-        c_unpack(tile[(size_t)c * kWColPitch + k1], re, im);
+        c_unpack(tile[wcol_idx(c, k1)], re, im);
         wk[(size_t)k1 * N2 + col0 + c] = make_float2(re, im);
     }
 }
@@ -390,9 +404,8 @@ __global__ void __launch_bounds__(kWRows * 16) k_cwt_rows_w(CwtParams p) {
         __syncwarp();
         af_fft16(u0);                                                          // X[k = q + 32 kb] at AF_BR4(kb)
         af_fft16(u1);                                                          // X[k = q + 16 + 32 kb]
-        c64 *rowp = tile + (size_t)r * kWRowPitch;
 #pragma unroll
-        for (int kb = 0; kb < 16; kb++) { rowp[q + 32 * kb] = u0[AF_BR4(kb)]; rowp[q + 16 + 32 * kb] = u1[AF_BR4(kb)]; }
+        for (int kb = 0; kb < 16; kb++) { tile[wrow_idx(r, q + 32 * kb)] = u0[AF_BR4(kb)]; tile[wrow_idx(r, q + 16 + 32 * kb)] = u1[AF_BR4(kb)]; }
     }
     __syncthreads();
     // result element (row k1, k2) is sequence index k1 + N1 * k2
@@ -401,7 +414,7 @@ __global__ void __launch_bounds__(kWRows * 16) k_cwt_rows_w(CwtParams p) {
         for (int e = threadIdx.x; e < kWRows * 512; e += blockDim.x) {
             const int k2 = e / kWRows, rr = e - k2 * kWRows;
             float re, im;
-            c_unpack(tile[(size_t)rr * kWRowPitch + k2], re, im);
+            c_unpack(tile[wrow_idx(rr, k2)], re, im);
             sp[(size_t)k2 * N1 + row0 + rr] = make_float2(re, im);
         }
     } else {
@@ -412,7 +425,7 @@ __global__ void __launch_bounds__(kWRows * 16) k_cwt_rows_w(CwtParams p) {
             const long long n = (long long)k2 * N1 + row0 + rr - p.padLength;
             if (n < 0 || n >= p.dataLength) continue;
             float re, im;
-            c_unpack(tile[(size_t)rr * kWRowPitch + k2], re, im);
+            c_unpack(tile[wrow_idx(rr, k2)], re, im);
             oRe[n] = re * inv; oIm[n] = -im * inv;                             // conj back
         }
     }
@@ -438,6 +451,7 @@ void fill_params(const AfCwtArgs *a, CwtParams *p) {
     p->dataLength = a->dataLength; p->padLength = a->padLength; p->num = a->num; p->batch = a->batch;
     p->scaleArr = a->scaleArr;
     p->det = a->det;
+    { const double w = 2.0 * M_PI / (double)p->N; p->omegaHi = (float)w; p->omegaLo = (float)(w - (double)p->omegaHi); }
     p->bankTable = a->bankTable; p->bankWidth = a->bankWidth;
     p->itemBase = 0;
     p->wType = a->wavelet.waveletType; p->g = a->wavelet.gamma; p->b = a->wavelet.beta; p->factor = (float)a->wavelet.factor;
@@ -476,7 +490,7 @@ extern "C" int af_launch_cwt(const AfCwtArgs *a, const float *data, void *worksp
     int rc;
     if (p.log2N1 == 10 && p.log2N2 == 9 && !getenv("AFB200_CWT_GENERIC")) {
         // warp-level transforms (see k_cwt_cols_w / k_cwt_rows_w)
-        const size_t smC = sizeof(c64) * (size_t)kWCols * kWColPitch + sizeof(float2) * (1024 + p.N2);
+        const size_t smC = sizeof(c64) * (size_t)kWCols * kWColPitch + sizeof(float2) * (1024 + p.N2 + 1024);
         const size_t smR = sizeof(c64) * (size_t)kWRows * kWRowPitch + sizeof(float2) * 512;
         if ((rc = set_smem(k_cwt_cols_w<0>, smC, "smem k_cwt_cols_w<0>")) || (rc = set_smem(k_cwt_cols_w<1>, smC, "smem k_cwt_cols_w<1>")) ||
             (rc = set_smem(k_cwt_rows_w<0>, smR, "smem k_cwt_rows_w<0>")) || (rc = set_smem(k_cwt_rows_w<1>, smR, "smem k_cwt_rows_w<1>"))) return rc;
