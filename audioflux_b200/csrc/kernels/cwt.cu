@@ -420,13 +420,22 @@ __global__ void __launch_bounds__(kWRows * 16) k_cwt_rows_w(CwtParams p) {
     } else {
         const float inv = 1.0f / (float)p.N;
         float *oRe = p.outRe + (size_t)item * p.dataLength, *oIm = p.outIm + (size_t)item * p.dataLength;
-        for (int e = threadIdx.x; e < kWRows * 512; e += blockDim.x) {
-            const int k2 = e / kWRows, rr = e - k2 * kWRows;
-            const long long n = (long long)k2 * N1 + row0 + rr - p.padLength;
-            if (n < 0 || n >= p.dataLength) continue;
-            float re, im;
-            c_unpack(tile[wrow_idx(rr, k2)], re, im);
-            oRe[n] = re * inv; oIm[n] = -im * inv;                             // conj back
+        // thread -> (row rr, columns k2 = k20 + 16 it): 16 consecutive output samples per half-warp and plane.
+        // Shared-memory reads of 4 iterations are issued ahead of their stores.
+        const int rr = threadIdx.x & (kWRows - 1), k20 = threadIdx.x / kWRows;
+#pragma unroll 1
+        for (int it0 = 0; it0 < 512 / 16; it0 += 4) {
+            c64 v[4];
+#pragma unroll
+            for (int u = 0; u < 4; u++) v[u] = tile[wrow_idx(rr, k20 + 16 * (it0 + u))];
+#pragma unroll
+            for (int u = 0; u < 4; u++) {
+                const long long n = (long long)(k20 + 16 * (it0 + u)) * N1 + row0 + rr - p.padLength;
+                if (n < 0 || n >= p.dataLength) continue;
+                float re, im;
+                c_unpack(v[u], re, im);
+                oRe[n] = re * inv; oIm[n] = -im * inv;                         // conj back
+            }
         }
     }
 }
