@@ -385,7 +385,11 @@ def run_b200_arm(args):
                 "steps": n_e2e},
         "gpu_launches": int(launches),
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peaks["hbm_gbs"], "unit": "GB/s",
-                     "frac": achieved / peaks["hbm_gbs"], "traffic": None, "peak_kind": peak_kind,
+                     "frac": achieved / peaks["hbm_gbs"],
+                     # dram__bytes_read.sum + dram__bytes_write.sum of ONE launch of this kernel at this configuration from the
+                     # committed ncu --set full capture (profiles/r1_final_mfcc_fused_ncu_summary.txt): 981.77 + 72.74 MB
+                     "traffic": (981766144 + 72740864) if (B == 1024 and L == 240000) else None,
+                     "traffic_source": "profiles/r1_final_mfcc_fused_ncu_summary.txt", "peak_kind": peak_kind,
                      "kernel": "k_mfcc_fused<5>", "kernel_ms": kernel_ms, "algorithmic_bytes_per_launch": B * BYTES_PER_CLIP,
                      "frame_read_model_frac": (B * T * BYTES_PER_FRAME_READ_MODEL / (kernel_ms * 1e-3) / 1e9) / peaks["hbm_gbs"],
                      "fp32_tflops": B * T * FLOP_PER_FRAME / (kernel_ms * 1e-3) / 1e12},
