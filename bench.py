@@ -62,15 +62,30 @@ def measured_peaks():
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons sampled every 200 ms during the timed region."""
+    """SM clock and throttle reasons polled every ~5 ms through NVML (nvidia-smi every 200 ms as a fallback) in a side
+    thread; `mark()` brackets the timed region and the reported median / reasons come from the samples inside it."""
     Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
          "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
          "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+    BITS = {"sw_power_cap": 0x4, "hw_slowdown": 0x8, "sw_thermal_slowdown": 0x20, "hw_thermal_slowdown": 0x40}
 
     def __init__(self, index=0):
-        self.index, self.rows, self.proc = index, [], None
+        self.index, self.rows, self.proc, self.nvml = index, [], None, None
+        self.t0 = self.t1 = None
+        self.stop_flag = False
 
     def start(self):
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nvml = pynvml
+            self.handle = pynvml.nvmlDeviceGetHandleByIndex(self.index)
+            self.max_mhz = float(pynvml.nvmlDeviceGetMaxClockInfo(self.handle, pynvml.NVML_CLOCK_SM))
+            self.thread = threading.Thread(target=self._poll, daemon=True)
+            self.thread.start()
+            return
+        except Exception:
+            self.nvml = None
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
                                           "-lms", "200", "-i", str(self.index)], stdout=subprocess.PIPE, text=True)
@@ -79,31 +94,57 @@ class ClockSampler:
         except Exception:
             self.proc = None
 
+    def mark(self, begin):
+        if begin:
+            self.t0 = time.perf_counter()
+        else:
+            self.t1 = time.perf_counter()
+
+    def _poll(self):
+        n = self.nvml
+        while not self.stop_flag:
+            try:
+                mhz = float(n.nvmlDeviceGetClockInfo(self.handle, n.NVML_CLOCK_SM))
+                try:
+                    mask = int(n.nvmlDeviceGetCurrentClocksEventReasons(self.handle))
+                except Exception:
+                    mask = int(n.nvmlDeviceGetCurrentClocksThrottleReasons(self.handle))
+                self.rows.append((time.perf_counter(), mhz, self.max_mhz, mask))
+            except Exception:
+                pass
+            time.sleep(0.004)
+
     def _read(self):
         for line in self.proc.stdout:
-            self.rows.append([c.strip() for c in line.split(",")])
-
-    def stop(self):
-        if not self.proc:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        time.sleep(0.25)
-        self.proc.terminate()
-        try:
-            self.proc.wait(timeout=2)
-        except Exception:
-            self.proc.kill()
-        sm, mx, reasons = [], [], set()
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for r in self.rows:
+            r = [c.strip() for c in line.split(",")]
             try:
-                sm.append(float(r[1])); mx.append(float(r[2]))
-                for n, v in zip(names, r[5:9]):
-                    if v.lower().startswith("active"):
-                        reasons.add(n)
+                mask = sum(bit for (name, bit), v in zip((("hw_slowdown", 0x8), ("hw_thermal_slowdown", 0x40),
+                                                           ("sw_thermal_slowdown", 0x20), ("sw_power_cap", 0x4)), r[5:9])
+                           if v.lower().startswith("active"))
+                self.rows.append((time.perf_counter(), float(r[1]), float(r[2]), mask))
             except Exception:
                 continue
-        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "samples": len(sm), "reasons": sorted(reasons)}
+
+    def stop(self):
+        if self.nvml is None and not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        if self.nvml is not None:
+            self.stop_flag = True
+            self.thread.join(timeout=1)
+        else:
+            time.sleep(0.25)
+            self.proc.terminate()
+            try:
+                self.proc.wait(timeout=2)
+            except Exception:
+                self.proc.kill()
+        inside = [r for r in self.rows if self.t0 is not None and self.t1 is not None and self.t0 <= r[0] <= self.t1]
+        use = inside if inside else self.rows
+        reasons = sorted(name for name, bit in self.BITS.items() if any(r[3] & bit for r in use))
+        return {"sm_mhz": float(np.median([r[1] for r in use])) if use else None,
+                "sm_max_mhz": max(r[2] for r in use) if use else None,
+                "samples": len(use), "samples_in_timed_region": len(inside), "samples_total": len(self.rows),
+                "source": "nvml" if self.nvml is not None else "nvidia-smi", "reasons": reasons}
 
 
 # --------------------------------------------------------------------------- reference / CPU arm
@@ -255,6 +296,9 @@ def run_b200_arm(args):
             emit({"error": f"parity gate failed: rel err {parity}"})
             return 1
 
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
     for _ in range(max(args.warmup, 3)):
         step()
     torch.cuda.synchronize()
@@ -281,18 +325,17 @@ def run_b200_arm(args):
         emit({"error": "gather gate failed: the last rank's block did not arrive intact on rank 0"})
         return 1
 
-    sampler = ClockSampler(local)
-    if rank == 0:
-        sampler.start()
     launches0 = lib.afb200_kernelLaunchCount()
     ev = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps + 1)]
     kern_ms = []
     torch.cuda.synchronize()
+    sampler.mark(True)
     ev[0].record()
     for i in range(args.steps):
         step()
         ev[i + 1].record()
     torch.cuda.synchronize()
+    sampler.mark(False)
     if dist:
         dist.barrier()
     launches = lib.afb200_kernelLaunchCount() - launches0
