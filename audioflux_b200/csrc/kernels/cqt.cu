@@ -88,10 +88,25 @@ __global__ void k_cqt_octave(OctParams p) {
     // stage the tile's span of the zero-padded signal, polyphase-major
     const int span = (p.TT - 1) * h + N;
     const long long m0 = (long long)t0 * h - N / 2;          // signal index of padded position t0*h
-    for (int i = threadIdx.x; i < span; i += blockDim.x) {
-        const long long m = m0 + i;
-        const float v = (m >= 0 && m < p.validLength) ? sig[m] : 0.0f;
-        xs[(i % h) * p.rowLen + i / h] = v;
+    // (4 independent loads in flight per thread: at the top octave the staging moves 3x more data per MAC than
+    //  lower down and was load-latency bound, 28 % of that launch's stall samples; hop is a power of two in every
+    //  default configuration, then the polyphase split is a shift and a mask)
+    const int hShift = (h & (h - 1)) == 0 ? __ffs(h) - 1 : -1;
+    for (int i0 = threadIdx.x; i0 < span; i0 += 4 * blockDim.x) {
+        float v[4];
+#pragma unroll
+        for (int u = 0; u < 4; u++) {
+            const int i = i0 + u * blockDim.x;
+            const long long m = m0 + i;
+            v[u] = (i < span && m >= 0 && m < p.validLength) ? sig[m] : 0.0f;
+        }
+#pragma unroll
+        for (int u = 0; u < 4; u++) {
+            const int i = i0 + u * blockDim.x;
+            if (i >= span) continue;
+            const int r = hShift >= 0 ? (i & (h - 1)) : i % h, a = hShift >= 0 ? (i >> hShift) : i / h;
+            xs[r * p.rowLen + a] = v[u];
+        }
     }
 
     const int quarter = p.TT / kFT;
@@ -117,16 +132,19 @@ __global__ void k_cqt_octave(OctParams p) {
             }
             __syncthreads();
             const float2 *kb = sk + (size_t)(jg * kBT) * p.nChunk - n0;
-            for (int r = 0; r < h; r++) {
-                const float *row = xs + r * p.rowLen + tl;
-                int a = n0 > r ? (n0 - r + h - 1) / h : 0;
-                if (a < aLo) a = aLo;
-                const int nEnd = min(n1, aHi * h + r);
+            // taps n of this chunk and of this thread's segment, in ascending n: tap n = a*h + r reads polyphase row r at
+            // column a.  One flat loop with (r, a) advanced incrementally: no per-phase set-up (a division and ~50
+            // instructions per phase, which dominated at the top octaves where a phase holds only N/hop = 4 taps).
+            const int nBeg = max(n0, aLo * h), nEnd = min(n1, aHi * h);
+            if (nBeg < nEnd) {
+                int a = hShift >= 0 ? (nBeg >> hShift) : nBeg / h;
+                int r = nBeg - a * h;
+                const float *row = xs + r * p.rowLen + tl + a;
 #pragma unroll 2
-                for (int n = a * h + r; n < nEnd; a++, n += h) {
+                for (int n = nBeg; n < nEnd; n++) {
                     float x[kFT];
 #pragma unroll
-                    for (int f = 0; f < kFT; f++) x[f] = row[a + f * quarter];
+                    for (int f = 0; f < kFT; f++) x[f] = row[f * quarter];
 #pragma unroll
                     for (int u = 0; u < kBT; u++) {
                         const float2 c = kb[(size_t)u * p.nChunk + n];
@@ -136,6 +154,8 @@ __global__ void k_cqt_octave(OctParams p) {
                             ai[f][u] = fmaf(x[f], c.y, ai[f][u]);
                         }
                     }
+                    row += p.rowLen;
+                    if (++r == h) { r = 0; row -= (long long)h * p.rowLen - 1; }
                 }
             }
         }
