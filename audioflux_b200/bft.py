@@ -112,14 +112,19 @@ class BFT(Base):
         re = re.reshape(*lead, T, self.num)
         return re if result_type else (re, im.reshape(*lead, T, self.num))
 
-    def mfcc_batch(self, data, cc_num=13, rectify_type=CepstralRectifyType.LOG):
+    def mfcc_batch(self, data, cc_num=13, rectify_type=CepstralRectifyType.LOG, out=None):
         """Fused STFT -> |.|^2 (or |.|) -> bank -> log10/cbrt -> DCT-II(ortho) -> first cc_num.
-        data [B, L] -> [B, T, cc_num].  Equals bft(result_type=1) followed by XXCC.xxcc."""
+        data [B, L] -> [B, T, cc_num].  Equals bft(result_type=1) followed by XXCC.xxcc.
+        Host arrays go through the library's chunked copy-in / transform / copy-out pipeline; pass page-locked arrays
+        (and a page-locked `out`) to run it at PCIe speed."""
         fn = self._require_ext("bftObj_mfccBatch")
         x2, lead, kind, ptr, stream, alloc = split_batch(data)
         B, L = x2.shape
         T = self.cal_time_length(L)
-        out = alloc(B, T, cc_num)
+        if out is None:
+            out = alloc(B, T, cc_num)
+        elif tuple(out.shape) != (B, T, cc_num) or not (out.flags["C_CONTIGUOUS"] if hasattr(out, "flags") else out.is_contiguous()):
+            raise ValueError(f"out must be a contiguous float32 array of shape {(B, T, cc_num)}")
         check(fn(self._obj, ptr(x2), L, B, cc_num, enum_value(rectify_type), ptr(out), kind, stream),
               "bftObj_mfccBatch")
         return out.reshape(*lead, T, cc_num)

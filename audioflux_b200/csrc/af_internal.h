@@ -37,6 +37,10 @@ void af_dev_free(void *dptr);
 int af_stream_create(void **stream);
 void af_stream_destroy(void *stream);
 int af_stream_sync(void *stream);
+int af_event_create(void **ev);
+void af_event_destroy(void *ev);
+int af_event_record(void *ev, void *stream);
+int af_stream_wait_event(void *stream, void *ev);
 int af_memcpy_h2d(void *dst, const void *src, size_t bytes, void *stream);
 int af_memcpy_d2h(void *dst, const void *src, size_t bytes, void *stream);
 int af_memset_d(void *dst, int v, size_t bytes, void *stream);

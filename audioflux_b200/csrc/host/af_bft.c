@@ -34,6 +34,10 @@ struct OpaqueBFT {
     void *mfccPlan;
     int mfccPlanCc;
     float *dDctT; int dctReady;          /* general path: transposed DCT [num][num] */
+    /* host-pointer MFCC pipeline: two chunk slots, copy-in / compute / copy-out streams */
+    void *inStream, *outStream, *evIn[2], *evDone[2], *evOut[2];
+    AfDevBuf dChunkIn[2], dChunkOut[2];
+    int pipeReady;
 };
 
 int bftObj_new(BFTObj *out, int num, int radix2Exp, int *samplate, float *lowFre, float *highFre,
@@ -364,6 +368,48 @@ static int mfcc_compute(BFTObj b, const float *dData, int dataLength, int batch,
     return af_launch_xxcc((const float *)b->dOutIm.ptr, batch * T, b->num, ccNum, rectifyType, b->dDctT, dOut, st);
 }
 
+/* Host pointers: the batch is cut into chunks that flow through two device slots on three streams -- copy-in of chunk
+ * k+1 (PCIe H2D), transform of chunk k, copy-out of chunk k-1 (PCIe D2H, the other direction) all overlap, so with
+ * page-locked caller buffers the call runs at the speed of the input transfer and needs only 2 chunks of device
+ * memory instead of the whole batch (pageable buffers work too, the driver then stages them synchronously). */
+static int mfcc_host_pipeline(BFTObj b, const float *data, int dataLength, int batch, int T, int ccNum, int rectifyType,
+                              float *out, void *st) {
+    int rc;
+    if (!b->pipeReady) {
+        if ((rc = af_stream_create(&b->inStream)) || (rc = af_stream_create(&b->outStream))) return rc;
+        for (int s = 0; s < 2; s++)
+            if ((rc = af_event_create(&b->evIn[s])) || (rc = af_event_create(&b->evDone[s])) || (rc = af_event_create(&b->evOut[s]))) return rc;
+        b->pipeReady = 1;
+    }
+    /* chunk: about 64 MB of samples, a multiple of 16 clips, at least 1 */
+    long long per = ((long long)64 << 20) / ((long long)dataLength * 4);
+    if (per >= 16) per -= per % 16;
+    if (per < 1) per = 1;
+    if (per > batch) per = batch;
+    const int chunk = (int)per;
+    const size_t inB = sizeof(float) * (size_t)chunk * dataLength, outB = sizeof(float) * (size_t)chunk * T * ccNum;
+    for (int s = 0; s < 2; s++)
+        if ((rc = af_devbuf_reserve(&b->dChunkIn[s], inB)) || (rc = af_devbuf_reserve(&b->dChunkOut[s], outB))) return rc;
+    int k = 0;
+    for (int c0 = 0; c0 < batch; c0 += chunk, k++) {
+        const int nb = batch - c0 < chunk ? batch - c0 : chunk, s = k & 1;
+        if (k >= 2) {                                   /* slot reuse: its previous transform and read-back are over */
+            if ((rc = af_stream_wait_event(b->inStream, b->evDone[s]))) return rc;
+            if ((rc = af_stream_wait_event(st, b->evOut[s]))) return rc;
+        }
+        if ((rc = af_memcpy_h2d(b->dChunkIn[s].ptr, data + (size_t)c0 * dataLength, sizeof(float) * (size_t)nb * dataLength, b->inStream))) return rc;
+        if ((rc = af_event_record(b->evIn[s], b->inStream))) return rc;
+        if ((rc = af_stream_wait_event(st, b->evIn[s]))) return rc;
+        if ((rc = mfcc_compute(b, (const float *)b->dChunkIn[s].ptr, dataLength, nb, ccNum, rectifyType, (float *)b->dChunkOut[s].ptr, 0, NULL, st))) return rc;
+        if ((rc = af_event_record(b->evDone[s], st))) return rc;
+        if ((rc = af_stream_wait_event(b->outStream, b->evDone[s]))) return rc;
+        if ((rc = af_memcpy_d2h(out + (size_t)c0 * T * ccNum, b->dChunkOut[s].ptr, sizeof(float) * (size_t)nb * T * ccNum, b->outStream))) return rc;
+        if ((rc = af_event_record(b->evOut[s], b->outStream))) return rc;
+    }
+    if ((rc = af_stream_sync(b->inStream)) || (rc = af_stream_sync(st))) return rc;
+    return af_stream_sync(b->outStream);
+}
+
 int bftObj_mfccBatch(BFTObj b, const float *data, int dataLength, int batch, int ccNum, int rectifyType,
                      float *out, int memKind, void *stream) {
     if (!b || !data || !out || dataLength <= 0 || batch <= 0) return af_fail(AF_ERR_ARG, "bftObj_mfccBatch: bad argument");
@@ -379,12 +425,7 @@ int bftObj_mfccBatch(BFTObj b, const float *data, int dataLength, int batch, int
         if ((rc = mfcc_compute(b, data, dataLength, batch, ccNum, rectifyType, out, 0, NULL, st))) return rc;
         return AF_OK;                       /* asynchronous on the caller's stream */
     }
-    const size_t inB = sizeof(float) * (size_t)batch * dataLength, outB = sizeof(float) * (size_t)batch * T * ccNum;
-    if ((rc = af_devbuf_reserve(&b->dIn, inB)) || (rc = af_devbuf_reserve(&b->dOutRe, outB))) return rc;
-    if ((rc = af_memcpy_h2d(b->dIn.ptr, data, inB, st))) return rc;
-    if ((rc = mfcc_compute(b, (const float *)b->dIn.ptr, dataLength, batch, ccNum, rectifyType, (float *)b->dOutRe.ptr, 0, NULL, st))) return rc;
-    if ((rc = af_memcpy_d2h(out, b->dOutRe.ptr, outB, st))) return rc;
-    return af_stream_sync(st);
+    return mfcc_host_pipeline(b, data, dataLength, batch, T, ccNum, rectifyType, out, st);
 }
 
 /* MFCC + all-gather in one kernel: device pointers only.  `out` is this GPU's destination, peerOut[0..nPeer) are
@@ -409,7 +450,11 @@ void bftObj_free(BFTObj b) {
     af_devbuf_free(&b->dOutRe); af_devbuf_free(&b->dOutIm);
     af_dev_free(b->dWindow); af_dev_free(b->dBank); af_dev_free(b->dPacked);
     af_dev_free(b->dStart); af_dev_free(b->dLen); af_dev_free(b->dOff); af_dev_free(b->dDctT);
-    af_stream_destroy(b->stream);
+    af_stream_destroy(b->stream); af_stream_destroy(b->inStream); af_stream_destroy(b->outStream);
+    for (int s = 0; s < 2; s++) {
+        af_event_destroy(b->evIn[s]); af_event_destroy(b->evDone[s]); af_event_destroy(b->evOut[s]);
+        af_devbuf_free(&b->dChunkIn[s]); af_devbuf_free(&b->dChunkOut[s]);
+    }
     af_bands_free(&b->bands);
     free(b->window); free(b->bank); free(b->freBandArr); free(b->binBandArr);
     free(b);

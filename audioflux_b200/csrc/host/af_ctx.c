@@ -114,6 +114,18 @@ int af_sm_count(void) {
     return n;
 }
 
+/* ---- events: ordering between the copy / compute / read-back streams of the host-pointer pipelines ---- */
+int af_event_create(void **ev) {
+    cudaEvent_t e;
+    int rc = cudaEventCreateWithFlags(&e, cudaEventDisableTiming);
+    if (rc != cudaSuccess) { *ev = NULL; return af_cuda_check(rc, "cudaEventCreate"); }
+    *ev = (void *)e;
+    return AF_OK;
+}
+void af_event_destroy(void *ev) { if (ev) cudaEventDestroy((cudaEvent_t)ev); }
+int af_event_record(void *ev, void *stream) { return af_cuda_check(cudaEventRecord((cudaEvent_t)ev, (cudaStream_t)stream), "cudaEventRecord"); }
+int af_stream_wait_event(void *stream, void *ev) { return af_cuda_check(cudaStreamWaitEvent((cudaStream_t)stream, (cudaEvent_t)ev, 0), "cudaStreamWaitEvent"); }
+
 /* ---- buffers that other processes (one per GPU) can map: the gathered result of the multi-GPU path ---- */
 int afb200_peerAlloc(void **devPtr, size_t bytes) {
     if (!devPtr || bytes == 0) return af_fail(AF_ERR_ARG, "afb200_peerAlloc: bad argument");

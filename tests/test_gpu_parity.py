@@ -245,6 +245,27 @@ def test_mfcc_fused_non_triangular_bank_uses_filter_loop(torch_cuda, product_lib
     assert rel_max(got, O.xxcc(mel, 13)) < TOL
 
 
+def test_mfcc_host_pointer_pipeline(torch_cuda):
+    """Host-pointer entry: the batch flows through the library's chunked copy-in / transform / copy-out pipeline
+    (3 chunks here, the last one partial); pageable and page-locked buffers, result bit-identical to the device entry."""
+    torch = torch_cuda
+    B, L = 150, 240000
+    xh = torch.empty((B, L), dtype=torch.float32).pin_memory()
+    g = torch.Generator().manual_seed(5)
+    xh.copy_(0.1 * torch.randn((B, L), generator=g))
+    b = mel_bft()
+    want = b.mfcc_batch(xh.cuda(), 40).cpu().numpy()
+    got_pageable = b.mfcc_batch(xh.numpy().copy(), 40)
+    assert np.array_equal(got_pageable, want)
+    oh = torch.empty((B, b.cal_time_length(L), 40), dtype=torch.float32).pin_memory()
+    for _ in range(2):                                            # second call reuses the slots
+        oh.zero_()
+        ret = b.mfcc_batch(xh.numpy(), 40, out=oh.numpy())
+        assert ret.ctypes.data == oh.numpy().ctypes.data and np.array_equal(oh.numpy(), want)
+    small = b.mfcc_batch(xh.numpy()[:3], 40)                       # fewer clips than one chunk
+    assert np.array_equal(small, want[:3])
+
+
 def test_mfcc_fused_equals_composed_path(torch_cuda):
     """fused kernel == bft_batch(result_type=1) -> xxcc_batch (general kernels), and other banks
     that fit the fused plan (bark / erb, ETSI) agree with the oracle too."""
