@@ -156,7 +156,8 @@ class PeerScatter:
             raise RuntimeError("PeerScatter setup failed: " + "; ".join(f"rank {r}: {e}" for r, e in enumerate(errs) if e))
         off = self.rank * self.block * 4
         self._dst = C.c_void_p(self._ptr.value + off)
-        self._peer_arr = (C.c_void_p * max(1, len(self._peers)))(*[C.c_void_p(p + off) for p in self._peers])
+        self._peer_base = [p + off for p in self._peers]                 # slot `rank` inside every peer's array
+        self._peer_arr = (C.c_void_p * max(1, len(self._peers)))(*[C.c_void_p(p) for p in self._peer_base])
         self.gathered = torch.as_tensor(_DevArray(self._ptr.value, (self.world, batch_local, self.T, cc_num)),
                                         device=torch.device("cuda", torch.cuda.current_device()))
         self._flag = torch.zeros(1, dtype=torch.int32, device=self.gathered.device)
@@ -166,16 +167,23 @@ class PeerScatter:
         if rc != 0:
             raise RuntimeError(f"{what} failed ({rc}): {self.lib.afb200_lastError().decode()}")
 
-    def __call__(self, clips):
-        """clips: this rank's (B_local, L) CUDA tensor.  Launches the fused kernel on the current stream and returns
-        the gathered (world, B_local, T, cc) tensor; call `fence()` before reading other ranks' slots."""
+    def __call__(self, clips, clip_offset=0):
+        """clips: this rank's (B_local, L) CUDA tensor -- or a chunk (nb, L) of it that starts at clip `clip_offset`
+        (callers that stream their shard in from the host launch chunk by chunk).  Launches the fused kernel on the
+        current stream and returns the gathered (world, B_local, T, cc) tensor; call `fence()` before reading other
+        ranks' slots."""
         import ctypes as C
         import torch
-        if tuple(clips.shape) != (self.B, self.L) or not clips.is_cuda or clips.dtype != torch.float32 or not clips.is_contiguous():
-            raise ValueError("clips must be a contiguous float32 CUDA tensor of shape (B_local, L)")
+        nb = clips.shape[0]
+        if clips.dim() != 2 or clips.shape[1] != self.L or clip_offset < 0 or clip_offset + nb > self.B or \
+                not clips.is_cuda or clips.dtype != torch.float32 or not clips.is_contiguous():
+            raise ValueError("clips must be a contiguous float32 CUDA tensor (nb, L) with clip_offset + nb <= B_local")
         stream = C.c_void_p(torch.cuda.current_stream().cuda_stream)
-        self._check(self.lib.bftObj_mfccBatchScatter(self.bft._obj, C.c_void_p(clips.data_ptr()), self.L, self.B, self.cc,
-                                                     self.rect, self._dst, len(self._peers), self._peer_arr, stream),
+        off = clip_offset * self.T * self.cc * 4
+        dst = C.c_void_p(self._dst.value + off)
+        peers = (C.c_void_p * max(1, len(self._peers)))(*[C.c_void_p(p + off) for p in self._peer_base]) if off else self._peer_arr
+        self._check(self.lib.bftObj_mfccBatchScatter(self.bft._obj, C.c_void_p(clips.data_ptr()), self.L, nb, self.cc,
+                                                     self.rect, dst, len(self._peers), peers, stream),
                     "bftObj_mfccBatchScatter")
         return self.gathered
 

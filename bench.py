@@ -366,6 +366,8 @@ def run_b200_arm(args):
     xd = torch.empty_like(x)
 
     xh_np, oh_np = xh.numpy(), oh.numpy()           # views of the page-locked buffers for the C-ABI host-pointer call
+    h2d_stream = torch.cuda.Stream()
+    h2d_done = [torch.cuda.Event() for _ in range(8)]
 
     def e2e_step():
         if world == 1:
@@ -373,14 +375,31 @@ def run_b200_arm(args):
             # pipelines copy-in / transform / copy-out over chunks and returns when `oh` is complete
             bft.mfcc_batch(xh_np, NCC, out=oh_np)
             return
-        xd.copy_(xh, non_blocking=True)
+        if scatter is not None:
+            # stream the shard in chunk by chunk: copy-in of chunk k+1 on a side stream overlaps the fused transform +
+            # scatter of chunk k; then the cross-rank fence and this rank's own slot of the gathered array -> host
+            cur = torch.cuda.current_stream()
+            nchunk = 8
+            per = (B + nchunk - 1) // nchunk
+            for k in range(nchunk):
+                lo, hi = k * per, min(B, (k + 1) * per)
+                if lo >= hi:
+                    break
+                with torch.cuda.stream(h2d_stream):
+                    if k == 0:
+                        h2d_stream.wait_stream(cur)                  # xd is free again (previous step's kernels done)
+                    xd[lo:hi].copy_(xh[lo:hi], non_blocking=True)
+                    h2d_done[k].record(h2d_stream)
+                cur.wait_event(h2d_done[k])
+                scatter(xd[lo:hi], clip_offset=lo)
+            scatter.fence()
+            oh.copy_(scatter.gathered[rank], non_blocking=True)
+            return
+        xd.copy_(xh, non_blocking=True)            # --gather nccl: copy-in, chunked compute + overlapped all-gather
         res = step(xd)
-        if scatter is not None:                   # this rank's own slot of the gathered array -> host
-            oh.copy_(res[rank], non_blocking=True)
-        else:
-            per = res[0].shape[0] // world
-            for k, o in enumerate(res):           # this rank's own rows of every gathered chunk -> host
-                oh[k * per:(k + 1) * per].copy_(o[rank * per:(rank + 1) * per], non_blocking=True)
+        per = res[0].shape[0] // world
+        for k, o in enumerate(res):                # this rank's own rows of every gathered chunk -> host
+            oh[k * per:(k + 1) * per].copy_(o[rank * per:(rank + 1) * per], non_blocking=True)
 
     for _ in range(2):
         e2e_step()

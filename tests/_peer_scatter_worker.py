@@ -41,6 +41,16 @@ def main():
         for r in range(world):
             want = bft.mfcc_batch(shard(r, B, L, dev), CC)
             assert torch.equal(out[r], want), f"rank {rank}: slot {r} differs (rep {rep})"
+    # chunked launches (a shard streamed in from the host): same result
+    sc.gathered.zero_()
+    torch.cuda.synchronize()
+    dist.barrier()
+    for lo in range(0, B, 7):
+        sc(x[lo:lo + 7].contiguous(), clip_offset=lo)
+    sc.fence()
+    torch.cuda.synchronize()
+    for r in range(world):
+        assert torch.equal(sc.gathered[r], bft.mfcc_batch(shard(r, B, L, dev), CC)), f"rank {rank}: chunked slot {r} differs"
     torch.cuda.synchronize()
     dist.barrier()
     sc.close()
