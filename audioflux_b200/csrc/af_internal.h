@@ -45,6 +45,21 @@ int af_memcpy_h2d(void *dst, const void *src, size_t bytes, void *stream);
 int af_memcpy_d2h(void *dst, const void *src, size_t bytes, void *stream);
 int af_memset_d(void *dst, int v, size_t bytes, void *stream);
 size_t af_dev_free_bytes(void);
+
+/* Host-pointer batches: items flow through two device slots on three streams -- copy-in of chunk k+1, the transform
+ * of chunk k and copy-out of chunk k-1 overlap (H2D and D2H are opposite PCIe directions).  With page-locked caller
+ * buffers a call runs at the speed of the larger transfer and needs two chunks of device memory instead of the
+ * batch; pageable buffers work too (the driver stages them synchronously). */
+typedef struct {
+    int ready;
+    void *inStream, *outStream, *evIn[2], *evDone[2], *evOut[2];
+    AfDevBuf in[2], out0[2], out1[2];
+} AfPipe;
+/* transform of `nb` items already on the device: dIn -> dOut0 (and dOut1 when the entry point has two planes) */
+typedef int (*AfChunkFn)(void *obj, const float *dIn, int nb, float *dOut0, float *dOut1, void *stream);
+int af_pipe_run(AfPipe *pipe, AfChunkFn fn, void *obj, const float *hIn, size_t inFloatsPerItem, int batch,
+                float *hOut0, float *hOut1, size_t outFloatsPerItem, void *computeStream);
+void af_pipe_free(AfPipe *pipe);
 int af_sm_count(void);
 
 /* ---------------- setup-time tables (host/af_window.c, af_filterbank.c, ...) ---------------- */

@@ -34,11 +34,12 @@ struct OpaqueBFT {
     void *mfccPlan;
     int mfccPlanCc;
     float *dDctT; int dctReady;          /* general path: transposed DCT [num][num] */
-    /* host-pointer MFCC pipeline: two chunk slots, copy-in / compute / copy-out streams */
-    void *inStream, *outStream, *evIn[2], *evDone[2], *evOut[2];
-    AfDevBuf dChunkIn[2], dChunkOut[2];
-    int pipeReady;
+    AfPipe pipe;                         /* host-pointer batches: chunked copy-in / transform / copy-out */
+    int pipeLength, pipeCc, pipeRectify; /* arguments of the call the pipe is currently serving */
 };
+
+static int bft_chunk(void *obj, const float *dIn, int nb, float *dOut0, float *dOut1, void *st);
+static int mfcc_chunk(void *obj, const float *dIn, int nb, float *dOut0, float *dOut1, void *st);
 
 int bftObj_new(BFTObj *out, int num, int radix2Exp, int *samplate, float *lowFre, float *highFre,
                int *binPerOctave, WindowType *windowType, int *slideLength,
@@ -241,15 +242,9 @@ int bftObj_bftBatch(BFTObj b, const float *data, int dataLength, int batch, floa
         if ((rc = bft_compute(b, data, dataLength, batch, mReal3, needIm ? mImag3 : NULL, st))) return rc;
         return AF_OK;                       /* asynchronous on the caller's stream */
     }
-    const size_t inB = sizeof(float) * (size_t)batch * dataLength, outB = sizeof(float) * (size_t)batch * T * b->num;
-    if ((rc = af_devbuf_reserve(&b->dIn, inB)) || (rc = af_devbuf_reserve(&b->dOutRe, outB))) return rc;
-    if (needIm && (rc = af_devbuf_reserve(&b->dOutIm, outB))) return rc;
-    if ((rc = af_memcpy_h2d(b->dIn.ptr, data, inB, st))) return rc;
-    if ((rc = bft_compute(b, (const float *)b->dIn.ptr, dataLength, batch, (float *)b->dOutRe.ptr,
-                          needIm ? (float *)b->dOutIm.ptr : NULL, st))) return rc;
-    if ((rc = af_memcpy_d2h(mReal3, b->dOutRe.ptr, outB, st))) return rc;
-    if (needIm && (rc = af_memcpy_d2h(mImag3, b->dOutIm.ptr, outB, st))) return rc;
-    return af_stream_sync(st);
+    b->pipeLength = dataLength;
+    return af_pipe_run(&b->pipe, bft_chunk, b, data, (size_t)dataLength, batch, mReal3, needIm ? mImag3 : NULL,
+                       (size_t)T * b->num, st);
 }
 
 void bftObj_bft(BFTObj b, float *dataArr, int dataLength, float *mRealArr3, float *mImageArr3) {
@@ -368,46 +363,14 @@ static int mfcc_compute(BFTObj b, const float *dData, int dataLength, int batch,
     return af_launch_xxcc((const float *)b->dOutIm.ptr, batch * T, b->num, ccNum, rectifyType, b->dDctT, dOut, st);
 }
 
-/* Host pointers: the batch is cut into chunks that flow through two device slots on three streams -- copy-in of chunk
- * k+1 (PCIe H2D), transform of chunk k, copy-out of chunk k-1 (PCIe D2H, the other direction) all overlap, so with
- * page-locked caller buffers the call runs at the speed of the input transfer and needs only 2 chunks of device
- * memory instead of the whole batch (pageable buffers work too, the driver then stages them synchronously). */
-static int mfcc_host_pipeline(BFTObj b, const float *data, int dataLength, int batch, int T, int ccNum, int rectifyType,
-                              float *out, void *st) {
-    int rc;
-    if (!b->pipeReady) {
-        if ((rc = af_stream_create(&b->inStream)) || (rc = af_stream_create(&b->outStream))) return rc;
-        for (int s = 0; s < 2; s++)
-            if ((rc = af_event_create(&b->evIn[s])) || (rc = af_event_create(&b->evDone[s])) || (rc = af_event_create(&b->evOut[s]))) return rc;
-        b->pipeReady = 1;
-    }
-    /* chunk: about 64 MB of samples, a multiple of 16 clips, at least 1 */
-    long long per = ((long long)64 << 20) / ((long long)dataLength * 4);
-    if (per >= 16) per -= per % 16;
-    if (per < 1) per = 1;
-    if (per > batch) per = batch;
-    const int chunk = (int)per;
-    const size_t inB = sizeof(float) * (size_t)chunk * dataLength, outB = sizeof(float) * (size_t)chunk * T * ccNum;
-    for (int s = 0; s < 2; s++)
-        if ((rc = af_devbuf_reserve(&b->dChunkIn[s], inB)) || (rc = af_devbuf_reserve(&b->dChunkOut[s], outB))) return rc;
-    int k = 0;
-    for (int c0 = 0; c0 < batch; c0 += chunk, k++) {
-        const int nb = batch - c0 < chunk ? batch - c0 : chunk, s = k & 1;
-        if (k >= 2) {                                   /* slot reuse: its previous transform and read-back are over */
-            if ((rc = af_stream_wait_event(b->inStream, b->evDone[s]))) return rc;
-            if ((rc = af_stream_wait_event(st, b->evOut[s]))) return rc;
-        }
-        if ((rc = af_memcpy_h2d(b->dChunkIn[s].ptr, data + (size_t)c0 * dataLength, sizeof(float) * (size_t)nb * dataLength, b->inStream))) return rc;
-        if ((rc = af_event_record(b->evIn[s], b->inStream))) return rc;
-        if ((rc = af_stream_wait_event(st, b->evIn[s]))) return rc;
-        if ((rc = mfcc_compute(b, (const float *)b->dChunkIn[s].ptr, dataLength, nb, ccNum, rectifyType, (float *)b->dChunkOut[s].ptr, 0, NULL, st))) return rc;
-        if ((rc = af_event_record(b->evDone[s], st))) return rc;
-        if ((rc = af_stream_wait_event(b->outStream, b->evDone[s]))) return rc;
-        if ((rc = af_memcpy_d2h(out + (size_t)c0 * T * ccNum, b->dChunkOut[s].ptr, sizeof(float) * (size_t)nb * T * ccNum, b->outStream))) return rc;
-        if ((rc = af_event_record(b->evOut[s], b->outStream))) return rc;
-    }
-    if ((rc = af_stream_sync(b->inStream)) || (rc = af_stream_sync(st))) return rc;
-    return af_stream_sync(b->outStream);
+static int mfcc_chunk(void *obj, const float *dIn, int nb, float *dOut0, float *dOut1, void *st) {
+    BFTObj b = (BFTObj)obj;
+    (void)dOut1;
+    return mfcc_compute(b, dIn, b->pipeLength, nb, b->pipeCc, b->pipeRectify, dOut0, 0, NULL, st);
+}
+static int bft_chunk(void *obj, const float *dIn, int nb, float *dOut0, float *dOut1, void *st) {
+    BFTObj b = (BFTObj)obj;
+    return bft_compute(b, dIn, b->pipeLength, nb, dOut0, dOut1, st);
 }
 
 int bftObj_mfccBatch(BFTObj b, const float *data, int dataLength, int batch, int ccNum, int rectifyType,
@@ -425,7 +388,8 @@ int bftObj_mfccBatch(BFTObj b, const float *data, int dataLength, int batch, int
         if ((rc = mfcc_compute(b, data, dataLength, batch, ccNum, rectifyType, out, 0, NULL, st))) return rc;
         return AF_OK;                       /* asynchronous on the caller's stream */
     }
-    return mfcc_host_pipeline(b, data, dataLength, batch, T, ccNum, rectifyType, out, st);
+    b->pipeLength = dataLength; b->pipeCc = ccNum; b->pipeRectify = rectifyType;
+    return af_pipe_run(&b->pipe, mfcc_chunk, b, data, (size_t)dataLength, batch, out, NULL, (size_t)T * ccNum, st);
 }
 
 /* MFCC + all-gather in one kernel: device pointers only.  `out` is this GPU's destination, peerOut[0..nPeer) are
@@ -450,11 +414,8 @@ void bftObj_free(BFTObj b) {
     af_devbuf_free(&b->dOutRe); af_devbuf_free(&b->dOutIm);
     af_dev_free(b->dWindow); af_dev_free(b->dBank); af_dev_free(b->dPacked);
     af_dev_free(b->dStart); af_dev_free(b->dLen); af_dev_free(b->dOff); af_dev_free(b->dDctT);
-    af_stream_destroy(b->stream); af_stream_destroy(b->inStream); af_stream_destroy(b->outStream);
-    for (int s = 0; s < 2; s++) {
-        af_event_destroy(b->evIn[s]); af_event_destroy(b->evDone[s]); af_event_destroy(b->evOut[s]);
-        af_devbuf_free(&b->dChunkIn[s]); af_devbuf_free(&b->dChunkOut[s]);
-    }
+    af_stream_destroy(b->stream);
+    af_pipe_free(&b->pipe);
     af_bands_free(&b->bands);
     free(b->window); free(b->bank); free(b->freBandArr); free(b->binBandArr);
     free(b);

@@ -24,6 +24,8 @@ struct OpaqueCQT {
     int chromaNum;
     float *dChromaBank, *dDctT;
     AfDevBuf dPostA, dPostB, dPostOut;
+    AfPipe pipe;                   /* host-pointer batches: chunked copy-in / transform / copy-out */
+    int pipeLength;
 };
 
 int cqtObj_newWith(CQTObj *out, int num, int *samplate, float *minFre, int *binPerOctave, float *factor,
@@ -144,6 +146,11 @@ static int cqt_compute(CQTObj c, const float *dData, int dataLength, int batch, 
     return AF_OK;
 }
 
+static int cqt_chunk(void *obj, const float *dIn, int nb, float *dOut0, float *dOut1, void *st) {
+    CQTObj c = (CQTObj)obj;
+    return cqt_compute(c, dIn, c->pipeLength, nb, dOut0, dOut1, st);
+}
+
 int cqtObj_cqtBatch(CQTObj c, const float *data, int dataLength, int batch, float *mReal3, float *mImag3,
                     int memKind, void *stream) {
     if (!c || !data || !mReal3 || !mImag3 || dataLength <= 0 || batch <= 0) return af_fail(AF_ERR_ARG, "cqtObj_cqtBatch: bad argument");
@@ -156,12 +163,8 @@ int cqtObj_cqtBatch(CQTObj c, const float *data, int dataLength, int batch, floa
         st = stream;
         return cqt_compute(c, data, dataLength, batch, mReal3, mImag3, st);
     }
-    const size_t inB = sizeof(float) * (size_t)batch * dataLength, outB = sizeof(float) * (size_t)batch * T * c->num;
-    if ((rc = af_devbuf_reserve(&c->dIn, inB)) || (rc = af_devbuf_reserve(&c->dOutRe, outB)) || (rc = af_devbuf_reserve(&c->dOutIm, outB))) return rc;
-    if ((rc = af_memcpy_h2d(c->dIn.ptr, data, inB, st))) return rc;
-    if ((rc = cqt_compute(c, (const float *)c->dIn.ptr, dataLength, batch, (float *)c->dOutRe.ptr, (float *)c->dOutIm.ptr, st))) return rc;
-    if ((rc = af_memcpy_d2h(mReal3, c->dOutRe.ptr, outB, st)) || (rc = af_memcpy_d2h(mImag3, c->dOutIm.ptr, outB, st))) return rc;
-    return af_stream_sync(st);
+    c->pipeLength = dataLength;
+    return af_pipe_run(&c->pipe, cqt_chunk, c, data, (size_t)dataLength, batch, mReal3, mImag3, (size_t)T * c->num, st);
 }
 
 void cqtObj_cqt(CQTObj c, float *dataArr, int dataLength, float *mRealArr3, float *mImageArr3) {
@@ -264,6 +267,7 @@ void cqtObj_free(CQTObj c) {
     af_devbuf_free(&c->dIn); af_devbuf_free(&c->dSigA); af_devbuf_free(&c->dSigB);
     af_devbuf_free(&c->dOutRe); af_devbuf_free(&c->dOutIm);
     af_devbuf_free(&c->dPostA); af_devbuf_free(&c->dPostB); af_devbuf_free(&c->dPostOut);
+    af_pipe_free(&c->pipe);
     af_dev_free(c->dChromaBank); af_dev_free(c->dDctT);
     af_dev_free(c->dKappa2); af_dev_free(c->dLeft); af_dev_free(c->dRight); af_dev_free(c->dScale);
     af_stream_destroy(c->stream);

@@ -126,6 +126,54 @@ void af_event_destroy(void *ev) { if (ev) cudaEventDestroy((cudaEvent_t)ev); }
 int af_event_record(void *ev, void *stream) { return af_cuda_check(cudaEventRecord((cudaEvent_t)ev, (cudaStream_t)stream), "cudaEventRecord"); }
 int af_stream_wait_event(void *stream, void *ev) { return af_cuda_check(cudaStreamWaitEvent((cudaStream_t)stream, (cudaEvent_t)ev, 0), "cudaStreamWaitEvent"); }
 
+int af_pipe_run(AfPipe *pp, AfChunkFn fn, void *obj, const float *hIn, size_t inPer, int batch,
+                float *hOut0, float *hOut1, size_t outPer, void *st) {
+    int rc;
+    if (!pp->ready) {
+        if ((rc = af_stream_create(&pp->inStream)) || (rc = af_stream_create(&pp->outStream))) return rc;
+        for (int s = 0; s < 2; s++)
+            if ((rc = af_event_create(&pp->evIn[s])) || (rc = af_event_create(&pp->evDone[s])) || (rc = af_event_create(&pp->evOut[s]))) return rc;
+        pp->ready = 1;
+    }
+    /* chunk: about 64 MB of the larger side, a multiple of 16 items when possible, at least 1 */
+    const size_t big = inPer > outPer * (hOut1 ? 2 : 1) ? inPer : outPer * (hOut1 ? 2 : 1);
+    long long per = ((long long)64 << 20) / (long long)(big * sizeof(float) > 0 ? big * sizeof(float) : 1);
+    if (per >= 16) per -= per % 16;
+    if (per < 1) per = 1;
+    if (per > batch) per = batch;
+    const int chunk = (int)per;
+    for (int s = 0; s < 2; s++) {
+        if ((rc = af_devbuf_reserve(&pp->in[s], sizeof(float) * inPer * chunk)) ||
+            (rc = af_devbuf_reserve(&pp->out0[s], sizeof(float) * outPer * chunk))) return rc;
+        if (hOut1 && (rc = af_devbuf_reserve(&pp->out1[s], sizeof(float) * outPer * chunk))) return rc;
+    }
+    int k = 0;
+    for (int c0 = 0; c0 < batch; c0 += chunk, k++) {
+        const int nb = batch - c0 < chunk ? batch - c0 : chunk, s = k & 1;
+        if (k >= 2) {                                   /* slot reuse: its previous transform and read-back are over */
+            if ((rc = af_stream_wait_event(pp->inStream, pp->evDone[s])) || (rc = af_stream_wait_event(st, pp->evOut[s]))) return rc;
+        }
+        if ((rc = af_memcpy_h2d(pp->in[s].ptr, hIn + (size_t)c0 * inPer, sizeof(float) * inPer * nb, pp->inStream))) return rc;
+        if ((rc = af_event_record(pp->evIn[s], pp->inStream)) || (rc = af_stream_wait_event(st, pp->evIn[s]))) return rc;
+        if ((rc = fn(obj, (const float *)pp->in[s].ptr, nb, (float *)pp->out0[s].ptr, hOut1 ? (float *)pp->out1[s].ptr : NULL, st))) return rc;
+        if ((rc = af_event_record(pp->evDone[s], st)) || (rc = af_stream_wait_event(pp->outStream, pp->evDone[s]))) return rc;
+        if ((rc = af_memcpy_d2h(hOut0 + (size_t)c0 * outPer, pp->out0[s].ptr, sizeof(float) * outPer * nb, pp->outStream))) return rc;
+        if (hOut1 && (rc = af_memcpy_d2h(hOut1 + (size_t)c0 * outPer, pp->out1[s].ptr, sizeof(float) * outPer * nb, pp->outStream))) return rc;
+        if ((rc = af_event_record(pp->evOut[s], pp->outStream))) return rc;
+    }
+    if ((rc = af_stream_sync(pp->inStream)) || (rc = af_stream_sync(st))) return rc;
+    return af_stream_sync(pp->outStream);
+}
+
+void af_pipe_free(AfPipe *pp) {
+    af_stream_destroy(pp->inStream); af_stream_destroy(pp->outStream);
+    for (int s = 0; s < 2; s++) {
+        af_event_destroy(pp->evIn[s]); af_event_destroy(pp->evDone[s]); af_event_destroy(pp->evOut[s]);
+        af_devbuf_free(&pp->in[s]); af_devbuf_free(&pp->out0[s]); af_devbuf_free(&pp->out1[s]);
+    }
+    memset(pp, 0, sizeof(*pp));
+}
+
 /* ---- buffers that other processes (one per GPU) can map: the gathered result of the multi-GPU path ---- */
 int afb200_peerAlloc(void **devPtr, size_t bytes) {
     if (!devPtr || bytes == 0) return af_fail(AF_ERR_ARG, "afb200_peerAlloc: bad argument");

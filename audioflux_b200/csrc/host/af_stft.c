@@ -20,6 +20,8 @@ struct OpaqueSTFT {
     void *stream;
     float *dWindow;
     AfDevBuf dIn, dRe, dIm, dFrames;
+    AfPipe pipe;                   /* host-pointer batches: chunked copy-in / transform / copy-out */
+    int pipeLength;
 };
 
 int stftObj_new(STFTObj *out, int radix2Exp, WindowType *windowType, int *slideLength, int *isContinue) {
@@ -131,6 +133,15 @@ void stftObj_stft(STFTObj s, float *dataArr, int dataLength, float *mRealArr, fl
     af_stream_sync(s->stream);
 }
 
+static int stft_chunk(void *obj, const float *dIn, int nb, float *dOut0, float *dOut1, void *st) {
+    STFTObj s = (STFTObj)obj;
+    AfFrameSrc src;
+    int rc = stft_frame_src(s, s->pipeLength, nb, &src);
+    if (rc) return rc;
+    src.data = dIn;
+    return af_launch_stft(&src, AF_STFT_HALF, 1.0f, dOut0, dOut1, st);
+}
+
 int stftObj_stftBatch(STFTObj s, const float *data, int dataLength, int batch, float *mReal, float *mImag,
                       int memKind, void *stream) {
     if (!s || !data || !mReal || !mImag || dataLength <= 0 || batch <= 0) return af_fail(AF_ERR_ARG, "stftObj_stftBatch: bad argument");
@@ -140,8 +151,6 @@ int stftObj_stftBatch(STFTObj s, const float *data, int dataLength, int batch, f
     AfFrameSrc src;
     if ((rc = stft_frame_src(s, dataLength, batch, &src))) return rc;
     if (src.timeLength <= 0) return AF_OK;
-    const size_t inBytes = sizeof(float) * (size_t)batch * dataLength;
-    const size_t plane = sizeof(float) * (size_t)batch * src.timeLength * (s->fftLength / 2 + 1);
     void *st = stream ? stream : s->stream;
     if (memKind == AFB200_MEM_DEVICE) {
         st = stream;                      /* NULL = the CUDA default stream */
@@ -149,13 +158,9 @@ int stftObj_stftBatch(STFTObj s, const float *data, int dataLength, int batch, f
         if ((rc = af_launch_stft(&src, AF_STFT_HALF, 1.0f, mReal, mImag, st))) return rc;
         return AF_OK;                       /* asynchronous on the caller's stream */
     }
-    if ((rc = af_devbuf_reserve(&s->dIn, inBytes)) || (rc = af_devbuf_reserve(&s->dRe, plane)) ||
-        (rc = af_devbuf_reserve(&s->dIm, plane))) return rc;
-    if ((rc = af_memcpy_h2d(s->dIn.ptr, data, inBytes, st))) return rc;
-    src.data = (const float *)s->dIn.ptr;
-    if ((rc = af_launch_stft(&src, AF_STFT_HALF, 1.0f, (float *)s->dRe.ptr, (float *)s->dIm.ptr, st))) return rc;
-    if ((rc = af_memcpy_d2h(mReal, s->dRe.ptr, plane, st)) || (rc = af_memcpy_d2h(mImag, s->dIm.ptr, plane, st))) return rc;
-    return af_stream_sync(st);
+    s->pipeLength = dataLength;
+    return af_pipe_run(&s->pipe, stft_chunk, s, data, (size_t)dataLength, batch, mReal, mImag,
+                       (size_t)src.timeLength * (s->fftLength / 2 + 1), st);
 }
 
 /* ---- inverse: planes [batch x T x width] -> data [batch x ((T-1)*hop + n)]  (stft_algorithm.c:304-409) ----
@@ -196,6 +201,7 @@ void stftObj_istft(STFTObj s, float *mRealArr, float *mImageArr, int timeLength,
 void stftObj_free(STFTObj s) {
     if (!s) return;
     af_devbuf_free(&s->dIn); af_devbuf_free(&s->dRe); af_devbuf_free(&s->dIm); af_devbuf_free(&s->dFrames);
+    af_pipe_free(&s->pipe);
     af_dev_free(s->dWindow);
     af_stream_destroy(s->stream);
     free(s->window);

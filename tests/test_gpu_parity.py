@@ -266,6 +266,28 @@ def test_mfcc_host_pointer_pipeline(torch_cuda):
     assert np.array_equal(small, want[:3])
 
 
+def test_host_pointer_pipelines_bft_cqt_stft(torch_cuda):
+    """Every batched host-pointer entry point runs the same chunked 3-stream pipeline (af_pipe_run): several chunks,
+    the last one partial, results bit-identical to the device-pointer entry."""
+    torch = torch_cuda
+    g = torch.Generator().manual_seed(6)
+    x = (0.1 * torch.randn((100, 240000), generator=g)).numpy()
+    xd = torch.from_numpy(x).cuda()
+    b = mel_bft()
+    assert np.array_equal(b.bft_batch(x), b.bft_batch(xd).cpu().numpy())                  # 64 + 36 clips
+    hr, hi = b.bft_batch(x[:70], 0)                                                        # complex mode: two planes
+    dr, di = b.bft_batch(xd[:70], 0)
+    assert np.array_equal(hr, dr.cpu().numpy()) and np.array_equal(hi, di.cpu().numpy())
+    c = af.CQT(84, 48000)
+    hre, him = c.cqt_batch(x)
+    dre, dim = c.cqt_batch(xd)
+    assert np.array_equal(hre, dre.cpu().numpy()) and np.array_equal(him, dim.cpu().numpy())   # 48 + 48 + 4 clips
+    s = af.STFT(11, W.HANN, 512)
+    hre, him = s.stft_batch(x[:40])
+    dre, dim = s.stft_batch(xd[:40])
+    assert np.array_equal(hre, dre.cpu().numpy()) and np.array_equal(him, dim.cpu().numpy())   # 16 + 16 + 8 clips
+
+
 def test_mfcc_fused_equals_composed_path(torch_cuda):
     """fused kernel == bft_batch(result_type=1) -> xxcc_batch (general kernels), and other banks
     that fit the fused plan (bark / erb, ETSI) agree with the oracle too."""
