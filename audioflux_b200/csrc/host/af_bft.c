@@ -33,6 +33,7 @@ struct OpaqueBFT {
     /* fused MFCC plan cache */
     void *mfccPlan;
     int mfccPlanCc;
+    void *melPlan;                       /* same fused kernel stopped after the bank (real-mode bftObj_bft at n = 2048) */
     float *dDctT; int dctReady;          /* general path: transposed DCT [num][num] */
     AfPipe pipe;                         /* host-pointer batches: chunked copy-in / transform / copy-out */
     int pipeLength, pipeCc, pipeRectify; /* arguments of the call the pipe is currently serving */
@@ -179,6 +180,22 @@ static int bft_compute(BFTObj b, const float *dData, int dataLength, int batch, 
     const int T = bftObj_calTimeLength(b, dataLength);
     const int width = b->fftLength / 2 + 1;
     if (T <= 0) return AF_OK;
+    /* real mode at fftLength 2048 with a banded bank: the fused TMA-fed kernel of the MFCC path, stopped after the
+     * filter bank (one launch, no spectrum round trip through HBM: 3.3x the general composition below) */
+    if (b->resultType && b->normValue == 1.0f && b->scaleType != SpectralFilterBankScale_Linear && b->bankDev.banded &&
+        af_mfcc_fused_supported(b->fftLength, b->num, 1, &b->bands) && b->slideLength % 4 == 0 && dataLength % 4 == 0 &&
+        ((size_t)dData & 15) == 0 && !getenv("AFB200_BFT_GENERAL")) {
+        int rc = AF_OK;
+        if (!b->melPlan) {
+            float *dct = (float *)calloc((size_t)b->num, sizeof(float));      /* unused by this mode */
+            if (!dct) return AF_ERR_NOMEM;
+            rc = af_mfcc_plan_build(&b->melPlan, b->fftLength, b->num, 1, b->window, b->bank, &b->bands, dct, b->dataType, NULL);
+            free(dct);
+            if (rc) return rc;
+        }
+        if (af_mfcc_plan_mode(b->melPlan) == 0)
+            return af_launch_mel_fused(b->melPlan, dData, dataLength, batch, T, b->slideLength, dRe, st);
+    }
     const int linear = b->scaleType == SpectralFilterBankScale_Linear;
     const int count = b->highIndex - b->lowIndex + 1 < b->num ? b->highIndex - b->lowIndex + 1 : b->num;
     /* the spectrum workspace is bounded: process the batch in chunks of clips */
@@ -409,7 +426,7 @@ int bftObj_mfccBatchScatter(BFTObj b, const float *data, int dataLength, int bat
 
 void bftObj_free(BFTObj b) {
     if (!b) return;
-    af_mfcc_plan_free(b->mfccPlan);
+    af_mfcc_plan_free(b->mfccPlan); af_mfcc_plan_free(b->melPlan);
     af_devbuf_free(&b->dIn); af_devbuf_free(&b->dSpecRe); af_devbuf_free(&b->dSpecIm);
     af_devbuf_free(&b->dOutRe); af_devbuf_free(&b->dOutIm);
     af_dev_free(b->dWindow); af_dev_free(b->dBank); af_dev_free(b->dPacked);

@@ -104,6 +104,7 @@ struct Params {
     int melMode, num, tailStart, tailLen;
     const float *melAux;
     int ccNum, rectify, dataType;
+    int rawMel;                     // 1: stop after the bank: out[frame][num] = bank . |X|^2 (bftObj_bft real mode), no log / DCT
     // fused all-gather: every finished tile is also stored at the same offset of up to kMaxPeers other buffers
     // (peer GPUs' gathered arrays mapped over NVLink, opened with cudaIpcOpenMemHandle by the host side)
     int nPeer;
@@ -196,6 +197,7 @@ __global__ void __launch_bounds__(kThreads, kCtasPerSm) k_mfcc_fused(Params p) {
         // ================= epilogue: DCT-II of a whole tile on the tensor cores =================
         // out[16 x 8*CT] = L[16 x 128] . D^T[128 x 8*CT], mma.sync.m16n8k8 TF32 with the 3xTF32 split
         // (x = hi + lo, hi = tf32(x), lo = tf32(x - hi);  lo*hi + hi*lo + hi*hi) -> fp32-level accuracy.
+        if (p.rawMel) return;                                  // filter-bank output only: no cepstral epilogue
         const int g = lane >> 2, t = lane & 3;
         const int epi = warp - (kFrameWarps + 1);
         int it = 0;
@@ -304,6 +306,8 @@ __global__ void __launch_bounds__(kThreads, kCtasPerSm) k_mfcc_fused(Params p) {
         if (lane == 0) af_mbar_arrive(&emptyBar[stage]);     // span slot may be refilled
         const int lbuf = it % kLBufs;
         float *lrow = sL + ((size_t)lbuf * kLRows + warp) * kLPitch;
+        float *melRow = p.out + ((tile / p.tilesPerClip) * p.timeLength + f0 + warp) * (long long)p.num;   // rawMel destination
+        if (!active && p.rawMel) continue;
         if (!active) {
             // keep the log-mel tile protocol in step: one arrival per warp per tile, never before the
             // epilogue released this buffer (tile it-2), else an early arrival would complete the wrong phase
@@ -380,7 +384,7 @@ __global__ void __launch_bounds__(kThreads, kCtasPerSm) k_mfcc_fused(Params p) {
         __syncwarp();
 
         // ---- D: banded filter bank (lane = filter within group, bank-conflict-free starts) + rectify ----
-        af_mbar_wait(&lEmpty[lbuf], ((uint32_t)(it / kLBufs) & 1u) ^ 1u);   // epilogue done with tile it-kLBufs
+        if (!p.rawMel) af_mbar_wait(&lEmpty[lbuf], ((uint32_t)(it / kLBufs) & 1u) ^ 1u);   // epilogue done with tile it-kLBufs
         if (MODE) {
             // Interval form of a triangular bank (two filters overlap on every bin and their weights there sum to the
             // filters' gains: fall_m(k) = g_m (1 - r_{m+1}(k))).  Lane j owns interval j = the bins between the peaks
@@ -461,15 +465,20 @@ __global__ void __launch_bounds__(kThreads, kCtasPerSm) k_mfcc_fused(Params p) {
                     w = wn; p0 = q0; p1 = q1;
                 }
                 float v = (acc0 + acc1) + (acc2 + acc3);
+                if (p.rawMel) {                                  // coalesced: one 128-byte row segment per group
+                    if (g * 32 + lane < p.num) melRow[g * 32 + lane] = v;
+                    wg4 += len4 * 32;
+                    continue;
+                }
                 if (p.rectify == CepstralRectify_CubicRoot) v = powf(v, 1.0f / 3.0f);
                 else v = __log2f(v < 1e-8f ? 1e-8f : v) * 0.30102999566398120f;   // log10 via MUFU.LG2
                 lrow[g * 32 + lane] = v;
                 wg4 += len4 * 32;
             }
-            for (int g = p.melGroups; g < 4; g++) lrow[g * 32 + lane] = 0.0f;
+            if (!p.rawMel) for (int g = p.melGroups; g < 4; g++) lrow[g * 32 + lane] = 0.0f;
         }
         __syncwarp();
-        if (lane == 0) af_mbar_arrive(&lFull[lbuf]);           // row ready for the tensor-core DCT epilogue
+        if (!p.rawMel && lane == 0) af_mbar_arrive(&lFull[lbuf]);           // row ready for the tensor-core DCT epilogue
 
     }
 }
@@ -731,9 +740,8 @@ extern "C" int af_mfcc_plan_build(void **planOut, int fftLength, int num, int cc
     return AF_OK;
 }
 
-extern "C" int af_launch_mfcc_fused(void *plan, const float *data, int dataLength, int batch, int timeLength,
-                                    int slideLength, int rectifyType, float *out, int nPeer, float *const *peerOut,
-                                    void *stream) {
+static int launch_fused(void *plan, const float *data, int dataLength, int batch, int timeLength, int slideLength,
+                        int rectifyType, float *out, int nPeer, float *const *peerOut, int rawMel, void *stream) {
     Plan *pl = static_cast<Plan *>(plan);
     if (!pl) return af_fail(AF_ERR_ARG, "fused MFCC: no plan");
     if (batch <= 0 || timeLength <= 0) return AF_OK;
@@ -749,6 +757,8 @@ extern "C" int af_launch_mfcc_fused(void *plan, const float *data, int dataLengt
     p.melMode = pl->melMode; p.num = pl->num; p.tailStart = pl->tailStart; p.tailLen = pl->tailLen; p.melAux = pl->dMelAux;
     for (int g = 0; g < 4; g++) p.melGroupLen[g] = pl->melGroupLen[g];
     p.ccNum = pl->ccNum; p.rectify = rectifyType; p.dataType = pl->dataType;
+    p.rawMel = rawMel;
+    if (rawMel && pl->melMode) return af_fail(AF_ERR_UNSUPPORTED, "fused filter-bank output needs the filter-per-lane plan");
     if (nPeer < 0 || nPeer > kMaxPeers || (nPeer > 0 && !peerOut)) return af_fail(AF_ERR_ARG, "fused MFCC: nPeer=%d outside [0, %d]", nPeer, kMaxPeers);
     p.nPeer = nPeer;
     for (int d = 0; d < nPeer; d++) p.peerOut[d] = peerOut[d];
@@ -788,6 +798,18 @@ extern "C" int af_launch_mfcc_fused(void *plan, const float *data, int dataLengt
 #undef AF_MFCC_LAUNCH
     AF_LAUNCH_CHECK("k_mfcc_fused");
     return AF_OK;
+}
+
+extern "C" int af_launch_mfcc_fused(void *plan, const float *data, int dataLength, int batch, int timeLength,
+                                    int slideLength, int rectifyType, float *out, int nPeer, float *const *peerOut,
+                                    void *stream) {
+    return launch_fused(plan, data, dataLength, batch, timeLength, slideLength, rectifyType, out, nPeer, peerOut, 0, stream);
+}
+
+// same kernel stopped after the filter bank: out[batch][T][num] = bank . |X|^2 (or |X|), i.e. bftObj_bft in real mode
+extern "C" int af_launch_mel_fused(void *plan, const float *data, int dataLength, int batch, int timeLength,
+                                   int slideLength, float *out, void *stream) {
+    return launch_fused(plan, data, dataLength, batch, timeLength, slideLength, 0, out, 0, NULL, 1, stream);
 }
 
 // Diagnostic / test hook (host only, no device needed): the interval form the planner derives from a bank.

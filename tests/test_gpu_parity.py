@@ -288,6 +288,35 @@ def test_host_pointer_pipelines_bft_cqt_stft(torch_cuda):
     assert np.array_equal(hre, dre.cpu().numpy()) and np.array_equal(him, dim.cpu().numpy())   # 16 + 16 + 8 clips
 
 
+@pytest.mark.parametrize("scale,style,norm,dt,num", [(S.MEL, ST.SLANEY, N.NONE, D.POWER, 128), (S.MEL, ST.SLANEY, N.AREA, D.MAG, 128),
+                                                      (S.BARK, ST.SLANEY, N.BAND_WIDTH, D.POWER, 128), (S.ERB, ST.ETSI, N.NONE, D.MAG, 96)])
+def test_bft_real_mode_fused_bank_output(torch_cuda, product_lib, monkeypatch, scale, style, norm, dt, num):
+    """Real-mode BFT at fftLength 2048 = the fused kernel stopped after the filter bank (ONE launch); against the
+    oracle and against the general STFT -> bank composition (AFB200_BFT_GENERAL=1)."""
+    torch = torch_cuda
+    x = np.stack([tones(41, 30720, 48000), noise(42, 30720)])
+    xd = torch.from_numpy(x).cuda()
+    b = af.BFT(num, 11, 48000, slide_length=512, scale_type=scale, style_type=style, normal_type=norm, data_type=dt)
+    n0 = product_lib.afb200_kernelLaunchCount()
+    got = b.bft_batch(xd).cpu().numpy()
+    assert product_lib.afb200_kernelLaunchCount() - n0 == 1
+    monkeypatch.setenv("AFB200_BFT_GENERAL", "1")
+    n0 = product_lib.afb200_kernelLaunchCount()
+    general = b.bft_batch(xd).cpu().numpy()
+    assert product_lib.afb200_kernelLaunchCount() - n0 == 2                      # STFT + bank
+    monkeypatch.delenv("AFB200_BFT_GENERAL")
+    for i in range(2):
+        want = O.bft(x[i], num, 11, 48000, 512, scale=af.enum_value(scale), style=af.enum_value(style),
+                     norm=af.enum_value(norm), data_type=af.enum_value(dt))
+        assert rel_max(got[i], want) < TOL and rel_max(general[i], want) < TOL
+    assert rel_max(got, general) < 2e-5
+    # a norm value other than 1 keeps the general composition (pow before / after the bank)
+    b.set_data_norm_value(0.5)
+    n0 = product_lib.afb200_kernelLaunchCount()
+    b.bft_batch(xd)
+    assert product_lib.afb200_kernelLaunchCount() - n0 == 2
+
+
 def test_mfcc_fused_equals_composed_path(torch_cuda):
     """fused kernel == bft_batch(result_type=1) -> xxcc_batch (general kernels), and other banks
     that fit the fused plan (bark / erb, ETSI) agree with the oracle too."""
