@@ -14,7 +14,8 @@ namespace {
 
 // spec planes [rows][width] with width = n (full spectrum) or n/2+1 (half: the rest is the Hermitian mirror)
 __global__ void k_istft_frames(const float *__restrict__ re, const float *__restrict__ im, int width, int n, int log2n,
-                               const float *__restrict__ window, int weightMode, float *__restrict__ frames) {
+                               const float *__restrict__ window, int weightMode, float *__restrict__ frames,
+                               const float2 *__restrict__ tw) {
     extern __shared__ float2 smem[];
     float2 *a = smem, *b = smem + n;
     const long long row = blockIdx.x;
@@ -26,7 +27,7 @@ __global__ void k_istft_frames(const float *__restrict__ re, const float *__rest
         a[k] = make_float2(xr, -xi);                 // conj in; the conj out only flips the unused imaginary part
     }
     __syncthreads();
-    a = af_stockham(a, b, n, log2n);
+    a = af_stockham(a, b, n, log2n, tw);
     const float inv = 1.0f / (float)n;
     float *f = frames + row * n;
     for (int j = threadIdx.x; j < n; j += blockDim.x) {
@@ -75,7 +76,7 @@ extern "C" int af_launch_istft(const float *re, const float *im, int width, int 
     int threads = fftLength / 4; if (threads < 32) threads = 32; if (threads > 1024) threads = 1024;
     cudaStream_t st = (cudaStream_t)stream;
     k_istft_frames<<<(unsigned)((long long)batch * timeLength), threads, smem, st>>>(re, im, width, fftLength, log2n, window,
-                                                                                    weightMode, frames);
+                                                                                    weightMode, frames, af_twiddle_table(log2n));
     AF_LAUNCH_CHECK("k_istft_frames");
     const int dataLength = (timeLength - 1) * slideLength + fftLength;
     const long long total = (long long)batch * dataLength;

@@ -26,6 +26,7 @@ struct StftParams {
     float padValue1, padValue2;   // constant mode: value left / right of the data
     int mode;
     float normValue;
+    const float2 *tw;       // twiddle tables of af_twiddle_table(log2nc), or null
 };
 
 
@@ -63,7 +64,7 @@ __global__ void k_stft_generic(StftParams p) {
     }
     __syncthreads();
 
-    a = af_stockham(a, b, nc, p.log2nc);      // forward complex FFT of the nc packed points (stockham.cuh)
+    a = af_stockham(a, b, nc, p.log2nc, p.tw);      // forward complex FFT of the nc packed points (stockham.cuh)
 
     // real-FFT post-pass: X[k] = E[k] + W_n^k O[k], k = 0..nc
     const int width = nc + 1;
@@ -72,7 +73,7 @@ __global__ void k_stft_generic(StftParams p) {
         float2 zk = a[k == nc ? 0 : k], zp = a[k == 0 ? 0 : nc - k];
         float er = 0.5f * (zk.x + zp.x), ei = 0.5f * (zk.y - zp.y);
         float orr = 0.5f * (zk.y + zp.y), oi = -0.5f * (zk.x - zp.x);
-        float2 w = af_twiddle(k, n);
+        float2 w = p.tw ? __ldg(p.tw + nc + k) : af_twiddle(k, n);     // exp(-2 pi i k / n), second half of the table
         float xr = er + (w.x * orr - w.y * oi), xi = ei + (w.x * oi + w.y * orr);
         if (k == 0 || k == nc) xi = 0.0f;
         switch (p.mode) {
@@ -138,6 +139,7 @@ extern "C" int af_launch_stft(const AfFrameSrc *src, int mode, float normValue, 
     p.hop = src->slideLength; p.timeLength = src->timeLength; p.padLeft = src->padLeft;
     p.validLength = src->validLength; p.mode = mode; p.normValue = normValue;
     p.padMode = src->padMode; p.padValue1 = src->padValue1; p.padValue2 = src->padValue2;
+    p.tw = n >= 4 ? af_twiddle_table(p.log2nc) : nullptr;
     cudaStream_t st = (cudaStream_t)stream;
     if (n == 2) {
         k_stft_n2<<<(unsigned)((frames + 255) / 256), 256, 0, st>>>(p, frames);
@@ -153,4 +155,31 @@ extern "C" int af_launch_stft(const AfFrameSrc *src, int mode, float normValue, 
     k_stft_generic<<<(unsigned)frames, threads, smem, st>>>(p);
     AF_LAUNCH_CHECK("k_stft_generic");
     return AF_OK;
+}
+
+// ---- twiddle tables shared by the Stockham kernels (STFT general path, ISTFT) ----
+#include <mutex>
+#include <vector>
+const float2 *af_twiddle_table(int log2n) {
+    static std::mutex mu;
+    static float2 *cache[64][32];
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64 || log2n < 1 || log2n > 24) return nullptr;
+    std::lock_guard<std::mutex> lock(mu);
+    if (cache[dev][log2n]) return cache[dev][log2n];
+    const size_t n = (size_t)1 << log2n;
+    std::vector<float2> h(2 * n + 1);
+    for (size_t j = 0; j < n; j++) {
+        const double a = -2.0 * M_PI * (double)j / (double)n;
+        h[j] = make_float2((float)cos(a), (float)sin(a));
+    }
+    for (size_t j = 0; j <= n; j++) {
+        const double a = -2.0 * M_PI * (double)j / (double)(2 * n);
+        h[n + j] = make_float2((float)cos(a), (float)sin(a));
+    }
+    float2 *d = nullptr;
+    if (cudaMalloc(&d, sizeof(float2) * h.size()) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+    if (cudaMemcpy(d, h.data(), sizeof(float2) * h.size(), cudaMemcpyHostToDevice) != cudaSuccess) { cudaGetLastError(); cudaFree(d); return nullptr; }
+    cache[dev][log2n] = d;
+    return d;
 }
