@@ -213,8 +213,12 @@ def run_reference_arm(args):
         "metric": "mfcc_frames_per_s", "value": v, "unit": "frames/s", "impl": "reference", "n_gpus": args.gpus,
         "steps": len(vals), "warmup": args.warmup, "ms_per_step": 1e3 * frames_step / v, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": "MFCC(40) of 5 s 48 kHz clips, n_fft=2048 hop=512 mel=128 via bftObj_bft(resultType=1)+xxccObj_xxcc",
-                   "sample": f"{per} clips x {cores} worker processes per step"},
+        # the B200 arm's workload (same clips, same transform); each reference step is a bounded sample of it
+        "config": {"workload": f"BASELINE config {'2' if args.gpus == 1 else '5-shaped'}: batch={args.batch} x 5 s 48 kHz clips per GPU, "
+                               "STFT(2048,hop 512,hann)->mel128(slaney)->log10->DCT MFCC(40)",
+                   "batch_per_gpu": args.batch, "clip_samples": L, "frames_per_clip": T,
+                   "implementation": "reference CPU path: bftObj_bft(resultType=1) + xxccObj_xxcc of oracle/_ref (unmodified reference sources)",
+                   "sample": f"{per} clips x {cores} worker processes per step ({per * cores} of the {args.batch} clips)"},
         "cpu_baseline": {"value": v, "unit": "frames/s", "cores": cores, "kind": "reference",
                          "sample": f"{per * cores} clips ({frames_step} frames) per step, {cores} processes x 1 object; "
                                    "reference built with gcc -O3, built-in radix-2 FFT + naive dot (no FFTW/MKL/BLAS in the image)"},
