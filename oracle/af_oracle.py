@@ -312,15 +312,120 @@ def band_edges(num, n_fft, sr, low, high, scale, ref, is_edge, slaney_bins):
     return fre, bins
 
 
+
+# ---------------------------------------------------------------------------
+# gammatone bank (src/filterbank/auditory_filterBank.c:509-591, coefficients :691-924, response
+# src/dsp/filterDesign_freqz.c:8-118): magnitude response of Slaney's four cascaded biquads at the FFT bins.
+# The lowest bands are numerically degenerate (the gain and the biquad responses lose most float32 digits to
+# cancellation) and the reference's values there are what a float32 evaluation in ITS order with ITS libm produces:
+# numpy's own float32 cos/sin/exp differ from glibc's in the last bit and move six of 64 rows by up to 3e-4.  So this
+# restatement is float32 operation by operation and takes cosf / sinf / expf / powf from the C library (ctypes); given the
+# reference's centre frequencies it reproduces the reference bank bit for bit, and within 5e-6 of a row's maximum from
+# its own centre frequencies (tests/test_golden.py, tests/test_oracle_vs_ref.py).
+# ---------------------------------------------------------------------------
+import ctypes as _C
+import ctypes.util as _Cu
+
+_libm = _C.CDLL(_Cu.find_library("m") or "libm.so.6")
+for _n in ("cosf", "sinf", "expf", "powf"):
+    _fn = getattr(_libm, _n)
+    _fn.restype = _C.c_float
+    _fn.argtypes = [_C.c_float] * (2 if _n == "powf" else 1)
+
+
+class libm:                                   # float32 in, float32 out, glibc rounding
+    cosf = staticmethod(lambda x: _libm.cosf(float(x)))
+    sinf = staticmethod(lambda x: _libm.sinf(float(x)))
+    expf = staticmethod(lambda x: _libm.expf(float(x)))
+    powf = staticmethod(lambda x, y: _libm.powf(float(x), float(y)))
+
+
+cosf = lambda x: f32(libm.cosf(x))            # noqa: E731
+sinf = lambda x: f32(libm.sinf(x))            # noqa: E731
+expf = lambda x: f32(libm.expf(x))            # noqa: E731
+sqrtf = lambda x: f32(np.sqrt(f32(x)))        # noqa: E731
+
+
+def gammatone_bank(num, n_fft, sr, norm, fre):
+    width=n_fft//2+1
+    t=f32(1.0/sr)
+    p15=f32(libm.powf(2.0,1.5))
+    pv=sqrtf(f32(3)+p15); nv=sqrtf(f32(3)-p15)
+    wEnd=f32(2*math.pi); wStep=f32(f32(f32(wEnd-f32(wEnd/f32(n_fft)))-f32(0))/f32(n_fft-1))
+    w=(f32(0)+np.arange(width).astype(f32)*wStep).astype(f32)
+    # per-bin trig with libm for exactness
+    if True:
+        c1=np.array([libm.cosf(float(-x)) for x in w],f32); s1=np.array([libm.sinf(float(-x)) for x in w],f32)
+        w2=(-w*f32(2)).astype(f32)
+        c2=np.array([libm.cosf(float(x)) for x in w2],f32); s2=np.array([libm.sinf(float(x)) for x in w2],f32)
+    bank=np.zeros((num,width),f32)
+    for i in range(num):
+        cf=f32(fre[i])
+        bw=f32((float(cf)/9.26449+24.7)*2*math.pi*1.019)
+        arg=f32(float(f32(cf*f32(2)))*math.pi*float(t))
+        v=f32(-t*expf(f32(-t*bw)))
+        cs,sn=cosf(arg),sinf(arg)
+        a4=f32(4*math.pi*float(t)*float(cf))
+        c2r,c2i=cosf(a4),sinf(a4)
+        e1=expf(f32(-bw*t))
+        a2=2*math.pi*float(t)*float(cf)
+        gr=f32(float(f32(f32(f32(2)*t)*e1))*math.cos(a2)); gi=f32(float(f32(f32(f32(2)*t)*e1))*math.sin(a2))
+        den1=f32(f32(f32(-2)*cs)/expf(f32(bw*t))); den2=expf(f32(f32(f32(-2)*t)*bw))
+        k=[f32(cs+f32(pv*sn)),f32(cs-f32(pv*sn)),f32(cs+f32(nv*sn)),f32(cs-f32(nv*sn))]
+        num1=[f32(v*kk) for kk in k]
+        mags=[]
+        for s in range(4):
+            re=f32(f32(f32(f32(-2)*t)*c2r)+f32(gr*k[s])); im=f32(f32(f32(f32(-2)*t)*c2i)+f32(gi*k[s]))
+            mags.append(sqrtf(f32(f32(re*re)+f32(im*im))))
+        e2=expf(f32(f32(f32(2)*t)*bw)); e3=expf(f32(t*bw))
+        r5=f32(f32(f32(f32(-2)/e2)-f32(f32(2)*c2r))+f32(f32(f32(2)*f32(f32(1)+c2r))/e3))
+        i5=f32(f32(f32(-2)*c2i)+f32(f32(f32(2)*c2i)/e3))
+        q=f32(f32(r5*r5)+f32(i5*i5))
+        gain=f32(f32(f32(f32(mags[0]*mags[1])*mags[2])*mags[3])/f32(q*q))
+        sec=[]
+        for s in range(4):
+            b0=f32(t/gain) if s==0 else t
+            b1=f32(num1[0]/gain) if s==0 else num1[s]
+            b2=f32(f32(0)/gain) if s==0 else f32(0)
+            sec.append((b0,b1,b2,f32(1),den1,den2))
+        def poly(c0,c1_,c2_):
+            re=np.zeros(width,f32); im=np.zeros(width,f32)
+            re=(re+ (np.ones(width,f32)*c0).astype(f32)).astype(f32)   # cos(0)*c0 ; sin(-0)*c0=0 (-0*c0)
+            im=(im+ (np.zeros(width,f32)*c0).astype(f32)).astype(f32)
+            re=(re+(c1*c1_).astype(f32)).astype(f32); im=(im+(s1*c1_).astype(f32)).astype(f32)
+            re=(re+(c2*c2_).astype(f32)).astype(f32); im=(im+(s2*c2_).astype(f32)).astype(f32)
+            return re,im
+        def cdiv(a,b):
+            d=(b[0]*b[0]).astype(f32)+(b[1]*b[1]).astype(f32); d=d.astype(f32)
+            return (((a[0]*b[0]).astype(f32)+(a[1]*b[1]).astype(f32)).astype(f32)/d).astype(f32), (((a[1]*b[0]).astype(f32)-(a[0]*b[1]).astype(f32)).astype(f32)/d).astype(f32)
+        def cmul(a,b):
+            return ((a[0]*b[0]).astype(f32)-(a[1]*b[1]).astype(f32)).astype(f32), ((a[0]*b[1]).astype(f32)+(a[1]*b[0]).astype(f32)).astype(f32)
+        h=cdiv(poly(*sec[0][:3]),poly(*sec[0][3:]))
+        for s in range(1,4): h=cmul(h,cdiv(poly(*sec[s][:3]),poly(*sec[s][3:])))
+        row=np.sqrt(((h[0]*h[0]).astype(f32)+(h[1]*h[1]).astype(f32)).astype(f32)).astype(f32)
+        if norm in (1,2):
+            if norm==1:
+                inner=f32(0)
+                for j in range(1,width-1): inner=f32(inner+row[j])
+                wt=f32(row[0]+row[width-1]); wt=f32(wt+f32(inner*f32(2)))
+            else:
+                wt=f32(1.019*24.7*(0.00437*float(fre[i])+1)); wt=f32(wt/f32(2))
+            row=np.where(row!=0,(row/wt).astype(f32),row)
+        row[1:width-1]=(row[1:width-1]*f32(2)).astype(f32)
+        bank[i]=row
+    return bank
+
 def auditory_filterbank(num, n_fft, sr, scale=SCALE_MEL, style=STYLE_SLANEY, norm=NORM_NONE,
                         low=0.0, high=None, bpo=12):
-    """`auditory_filterBank` (auditory_filterBank.c:56-207) for Slaney / ETSI / window styles.
+    """`auditory_filterBank` (auditory_filterBank.c:56-207) for the Slaney / ETSI / window styles and gammatone.
 
     Returns (bank[num, n_fft/2+1] float32, fre_band[num], bin_band[num])."""
     if high is None:
         high = sr / 2.0
-    if style == STYLE_GAMMATONE:
-        raise NotImplementedError("gammatone banks are checked against oracle/_ref only")
+    if style == STYLE_GAMMATONE:                   # the num points are the centre frequencies themselves (isEdge = 1)
+        lo_g, hi_g, ref_g = revise_edges(num, low, high, scale, n_fft, sr, bpo, is_edge=True)
+        fre_g, bins_g = band_edges(num, n_fft, sr, lo_g, hi_g, scale, ref_g, True, False)
+        return gammatone_bank(num, n_fft, sr, norm, fre_g), fre_g.astype(f32), bins_g
     m = n_fft // 2 + 1
     low, high, ref = revise_edges(num, low, high, scale, n_fft, sr, bpo, is_edge=False)
     fre, bins = band_edges(num, n_fft, sr, low, high, scale, ref, False, style == STYLE_SLANEY)

@@ -62,11 +62,16 @@ def test_cwt(golden):
     assert rel_max(re, g["re"]) < TOL and rel_max(im, g["im"]) < TOL
 
 
-def test_gammatone_with_reference_bank(golden):
-    """The float32-faithful gammatone builder lives in the product library (the reference's values in the lowest
-    bands are float32 rounding artefacts); the oracle takes the bank from the fixture."""
+def test_gammatone_bank_and_path(golden):
+    """The oracle's gammatone bank is a float32, libm-faithful restatement (the reference's values in the lowest bands are
+    float32 rounding artefacts): bit-identical to the reference given its centre frequencies, within 2e-5 of a row's
+    maximum from the oracle's own; then the BFT / cepstrum path with it."""
     g = golden("erb_gammatone.npz")
-    m = O.bft(g["x"], 64, 10, 32000, 256, O.W_HANN, O.SCALE_ERB, O.STYLE_GAMMATONE, O.NORM_NONE, O.DATA_POWER,
-              result_type=1, bank=g["bank"])
+    assert np.array_equal(O.gammatone_bank(64, 1024, 32000, O.NORM_NONE, g["fre_band"]), g["bank"])
+    bank, fre, bins = O.auditory_filterbank(64, 1024, 32000, O.SCALE_ERB, O.STYLE_GAMMATONE, O.NORM_NONE, 0.0, 16000.0)
+    assert np.array_equal(bins, g["bin_band"])
+    np.testing.assert_allclose(fre, g["fre_band"], rtol=2e-6)
+    assert (np.abs(bank - g["bank"]).max(axis=1) <= 2e-5 * g["bank"].max(axis=1)).all()
+    m = O.bft(g["x"], 64, 10, 32000, 256, O.W_HANN, O.SCALE_ERB, O.STYLE_GAMMATONE, O.NORM_NONE, O.DATA_POWER, result_type=1)
     assert rel_max(m, g["mel"]) < TOL
     assert rel_max(O.xxcc(g["mel"], 13), g["cc"]) < TOL

@@ -129,3 +129,21 @@ def test_cwt(ref_lib, r, wav, scale, pad):
     re, im = w.cwt_planes(x)
     re2, im2 = O.cwt(x, w.num, r, 48000, wav, scale, low=kw.get("low_fre", 32.703196 if scale in (5, 6) else None), is_pad=pad)
     assert rel_max(re2, re) < 1e-5 and rel_max(im2, im) < 1e-5
+
+
+@pytest.mark.parametrize("num,n,sr,scale,norm", [(64, 1024, 32000, 4, 0), (64, 1024, 32000, 4, 1), (40, 2048, 16000, 2, 2),
+                                                  (128, 2048, 48000, 4, 0), (32, 512, 22050, 3, 1), (24, 1024, 44100, 1, 0)])
+def test_gammatone_bank(ref_lib, num, n, sr, scale, norm):
+    lo, hi = (100.0, sr / 2 - 100.0) if scale == 1 else (0.0, sr / 2)
+    b = np.zeros((num + 4, n // 2 + 1), np.float32)
+    f = np.zeros(num + 2, np.float32)
+    bi = np.zeros(num + 2, np.int32)
+    ref_lib.auditory_filterBank(num, n, sr, 0, scale, 2, norm, C.c_float(lo), C.c_float(hi), 12, b.ctypes.data, f.ctypes.data,
+                                bi.ctypes.data)
+    ob, of, obi = O.auditory_filterbank(num, n, sr, scale, O.STYLE_GAMMATONE, norm, lo, hi)
+    assert np.array_equal(obi, bi[:num])
+    np.testing.assert_allclose(of, f[:num], rtol=2e-6, atol=1e-3)
+    assert (np.abs(ob - b[:num]).max(axis=1) <= 2e-5 * np.maximum(b[:num].max(axis=1), 1e-30)).all()
+    # given the reference's own centre frequencies the restatement is bit-exact (area norm: up to its summation order)
+    exact = O.gammatone_bank(num, n, sr, norm, f[:num])
+    assert (np.abs(exact - b[:num]).max(axis=1) <= (1e-5 if norm == 1 else 0.0) * np.maximum(b[:num].max(axis=1), 1e-30)).all()
