@@ -86,6 +86,10 @@ REFERENCE_API = {
     "spectrogramObj_newMel": (C.c_int, [P(vp), C.c_int, C.c_int, C.c_int, c_int_p]),
     "spectrogramObj_newBark": (C.c_int, [P(vp), C.c_int, C.c_int, C.c_int, c_int_p]),
     "spectrogramObj_newErb": (C.c_int, [P(vp), C.c_int, C.c_int, C.c_int, c_int_p]),
+    "spectrogramObj_newChroma": (C.c_int, [P(vp), C.c_int, C.c_int, c_int_p]),
+    "spectrogramObj_newDeep": (C.c_int, [P(vp), C.c_int, C.c_int, C.c_int, c_int_p]),
+    "spectrogramObj_newDeepChroma": (C.c_int, [P(vp), C.c_int, C.c_int, c_int_p]),
+    "spectrogramObj_enableDebug": (None, [vp, C.c_int]),
     "spectrogramObj_setDataNormValue": (None, [vp, C.c_float]),
     "spectrogramObj_calTimeLength": (C.c_int, [vp, C.c_int]),
     "spectrogramObj_getFreBandArr": (vp, [vp]),

@@ -120,6 +120,27 @@ int spectrogramObj_newErb(SpectrogramObj *o, int num, int samplate, int radix2Ex
     return new_scale(o, num, samplate, radix2Exp, isContinue, SpectralFilterBankScale_Erb);
 }
 
+/* constructors of the scale families outside the path: exported so that a caller resolving them gets a loud refusal
+ * (status -2 + afb200_lastError) instead of a missing symbol */
+static int refuse_family(SpectrogramObj *o, const char *what) {
+    if (o) *o = NULL;
+    af_fail(AF_ERR_UNSUPPORTED, "%s: the Chroma / Deep spectrogram families are not part of libaudioflux_b200", what);
+    return -2;
+}
+int spectrogramObj_newChroma(SpectrogramObj *o, int samplate, int radix2Exp, int *isContinue) {
+    (void)samplate; (void)radix2Exp; (void)isContinue;
+    return refuse_family(o, "spectrogramObj_newChroma");
+}
+int spectrogramObj_newDeep(SpectrogramObj *o, int num, int samplate, int radix2Exp, int *isContinue) {
+    (void)num; (void)samplate; (void)radix2Exp; (void)isContinue;
+    return refuse_family(o, "spectrogramObj_newDeep");
+}
+int spectrogramObj_newDeepChroma(SpectrogramObj *o, int samplate, int radix2Exp, int *isContinue) {
+    (void)samplate; (void)radix2Exp; (void)isContinue;
+    return refuse_family(o, "spectrogramObj_newDeepChroma");
+}
+void spectrogramObj_enableDebug(SpectrogramObj s, int flag) { (void)s; (void)flag; }   /* the reference only prints */
+
 void spectrogramObj_setDataNormValue(SpectrogramObj s, float v) { if (s) bftObj_setDataNormValue(s->core, v); }
 int spectrogramObj_calTimeLength(SpectrogramObj s, int dataLength) { return s ? bftObj_calTimeLength(s->core, dataLength) : 0; }
 float *spectrogramObj_getFreBandArr(SpectrogramObj s) { return s ? s->freBandArr : NULL; }

@@ -26,6 +26,11 @@ int spectrogramObj_newLinear(SpectrogramObj *spectrogramObj, int samplate, int r
 int spectrogramObj_newMel(SpectrogramObj *spectrogramObj, int num, int samplate, int radix2Exp, int *isContinue);  /* :205-222 */
 int spectrogramObj_newBark(SpectrogramObj *spectrogramObj, int num, int samplate, int radix2Exp, int *isContinue); /* :224-242 */
 int spectrogramObj_newErb(SpectrogramObj *spectrogramObj, int num, int samplate, int radix2Exp, int *isContinue);  /* :244-262 */
+/* :264-324.  Chroma / Deep families: refused loudly (-2), exported so the symbols resolve */
+int spectrogramObj_newChroma(SpectrogramObj *spectrogramObj, int samplate, int radix2Exp, int *isContinue);
+int spectrogramObj_newDeep(SpectrogramObj *spectrogramObj, int num, int samplate, int radix2Exp, int *isContinue);
+int spectrogramObj_newDeepChroma(SpectrogramObj *spectrogramObj, int samplate, int radix2Exp, int *isContinue);
+void spectrogramObj_enableDebug(SpectrogramObj spectrogramObj, int flag);                    /* :3171, no-op */
 void spectrogramObj_setDataNormValue(SpectrogramObj spectrogramObj, float normValue);       /* :841-846 */
 int spectrogramObj_calTimeLength(SpectrogramObj spectrogramObj, int dataLength);            /* :848-853 */
 float *spectrogramObj_getFreBandArr(SpectrogramObj spectrogramObj);                         /* :3176, borrowed */

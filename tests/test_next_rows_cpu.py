@@ -149,6 +149,10 @@ def test_spectrogram_new_status_codes(product_lib):
         assert getattr(product_lib, ctor)(C.byref(obj), *args, None) == 0
         assert product_lib.spectrogramObj_getBandNum(obj) == args[0]
         product_lib.spectrogramObj_free(obj)
+    assert product_lib.spectrogramObj_newChroma(C.byref(obj), 32000, 12, None) == -2 and not obj.value
+    assert product_lib.spectrogramObj_newDeep(C.byref(obj), 84, 32000, 12, None) == -2
+    assert product_lib.spectrogramObj_newDeepChroma(C.byref(obj), 32000, 12, None) == -2
+    assert b"Chroma / Deep" in product_lib.afb200_lastError()
     assert product_lib.spectrogramObj_newLinear(C.byref(obj), 32000, 11, None) == 0
     assert product_lib.spectrogramObj_getBandNum(obj) == 1025
     product_lib.spectrogramObj_free(obj)
