@@ -188,6 +188,16 @@ int af_launch_mfcc_fused(void *plan, const float *data, int dataLength, int batc
                          int slideLength, int rectifyType, float *out, int nPeer, float *const *peerOut,
                          void *stream);
 
+/* second-generation fused kernel (kernels/mfcc_fused2.cu): banks in which at most two consecutive filters overlap */
+int af_mfcc2_supported(int fftLength, int num, int ccNum, const float *bank /* num x (fftLength/2+1) */);
+int af_mfcc2_plan_build(void **plan, int fftLength, int num, int ccNum, const float *window, const float *bank,
+                        const float *dct, int dataType);
+void af_mfcc2_plan_free(void *plan);
+int af_launch_mfcc2(void *plan, const float *data, int dataLength, int batch, int timeLength, int slideLength,
+                    int rectifyType, float *out, int nPeer, float *const *peerOut, void *stream);
+int af_launch_mel2(void *plan, const float *data, int dataLength, int batch, int timeLength, int slideLength,
+                   float *out, void *stream);
+
 int af_launch_decimate2(const float *in, int inLength, int inStride, int batch, const float *left32,
                         const float *right31, float *out, int outStride, void *stream);
 /* out[b][t][colOff + j] (row stride num) = scale[j] * sum_n xpad[t*hop + n] * kappa[j][n];

@@ -34,6 +34,8 @@ struct OpaqueBFT {
     void *mfccPlan;
     int mfccPlanCc;
     void *melPlan;                       /* same fused kernel stopped after the bank (real-mode bftObj_bft at n = 2048) */
+    void *mfccPlan2, *melPlan2;          /* second-generation fused kernel (kernels/mfcc_fused2.cu), preferred when the bank qualifies */
+    int mfccPlan2Cc, v2State;            /* v2State: 0 unknown, 1 usable, -1 not (bank structure / AFB200_MFCC_KERNEL=v1) */
     float *dDctT; int dctReady;          /* general path: transposed DCT [num][num] */
     AfPipe pipe;                         /* host-pointer batches: chunked copy-in / transform / copy-out */
     int pipeLength, pipeCc, pipeRectify; /* arguments of the call the pipe is currently serving */
@@ -140,6 +142,15 @@ int bftObj_getFilterBankArr(BFTObj b, float *bank) {
     return AF_OK;
 }
 
+/* the v2 fused kernel needs fftLength 2048 and a bank whose bins are covered by at most two consecutive filters */
+static int bft_v2_usable(BFTObj b, int ccNum) {
+    if (b->v2State == 0) {
+        const char *k = getenv("AFB200_MFCC_KERNEL");
+        b->v2State = (k && !strcmp(k, "v1")) ? -1 : (af_mfcc2_supported(b->fftLength, b->num, 1, b->bank) ? 1 : -1);
+    }
+    return b->v2State > 0 && ccNum >= 1 && ccNum <= 64;
+}
+
 static int bft_device(BFTObj b) {
     int rc = af_device_ready();
     if (rc) return rc;
@@ -186,6 +197,16 @@ static int bft_compute(BFTObj b, const float *dData, int dataLength, int batch, 
         af_mfcc_fused_supported(b->fftLength, b->num, 1, &b->bands) && b->slideLength % 4 == 0 && dataLength % 4 == 0 &&
         ((size_t)dData & 15) == 0 && !getenv("AFB200_BFT_GENERAL")) {
         int rc = AF_OK;
+        if (bft_v2_usable(b, 1)) {
+            if (!b->melPlan2) {
+                float *dct = (float *)calloc((size_t)b->num, sizeof(float));      /* unused by this mode */
+                if (!dct) return AF_ERR_NOMEM;
+                rc = af_mfcc2_plan_build(&b->melPlan2, b->fftLength, b->num, 1, b->window, b->bank, dct, b->dataType);
+                free(dct);
+                if (rc) return rc;
+            }
+            return af_launch_mel2(b->melPlan2, dData, dataLength, batch, T, b->slideLength, dRe, st);
+        }
         if (!b->melPlan) {
             float *dct = (float *)calloc((size_t)b->num, sizeof(float));      /* unused by this mode */
             if (!dct) return AF_ERR_NOMEM;
@@ -319,6 +340,19 @@ static int mfcc_compute(BFTObj b, const float *dData, int dataLength, int batch,
     const int fusable = b->normValue == 1.0f && b->scaleType != SpectralFilterBankScale_Linear &&
                         b->bankDev.banded && af_mfcc_fused_supported(b->fftLength, b->num, ccNum, &b->bands) &&
                         b->slideLength % 4 == 0 && dataLength % 4 == 0 && ((size_t)dData & 15) == 0;
+    if (fusable && bft_v2_usable(b, ccNum)) {
+        if (!b->mfccPlan2 || b->mfccPlan2Cc != ccNum) {
+            af_mfcc2_plan_free(b->mfccPlan2); b->mfccPlan2 = NULL;
+            float *dct = (float *)malloc(sizeof(float) * (size_t)ccNum * b->num);
+            if (!dct) return AF_ERR_NOMEM;
+            af_dct2_matrix(b->num, ccNum, dct);
+            rc = af_mfcc2_plan_build(&b->mfccPlan2, b->fftLength, b->num, ccNum, b->window, b->bank, dct, b->dataType);
+            free(dct);
+            if (rc) return rc;
+            b->mfccPlan2Cc = ccNum;
+        }
+        return af_launch_mfcc2(b->mfccPlan2, dData, dataLength, batch, T, b->slideLength, rectifyType, dOut, nPeer, peerOut, st);
+    }
     if (fusable) {
         if (!b->mfccPlan || b->mfccPlanCc != ccNum) {
             af_mfcc_plan_free(b->mfccPlan); b->mfccPlan = NULL;
@@ -427,6 +461,7 @@ int bftObj_mfccBatchScatter(BFTObj b, const float *data, int dataLength, int bat
 void bftObj_free(BFTObj b) {
     if (!b) return;
     af_mfcc_plan_free(b->mfccPlan); af_mfcc_plan_free(b->melPlan);
+    af_mfcc2_plan_free(b->mfccPlan2); af_mfcc2_plan_free(b->melPlan2);
     af_devbuf_free(&b->dIn); af_devbuf_free(&b->dSpecRe); af_devbuf_free(&b->dSpecIm);
     af_devbuf_free(&b->dOutRe); af_devbuf_free(&b->dOutIm);
     af_dev_free(b->dWindow); af_dev_free(b->dBank); af_dev_free(b->dPacked);

@@ -1,0 +1,704 @@
+// mfcc_fused2.cu -- second-generation fused framed-STFT(2048) -> |X|^2 / |X| -> banded filter bank -> log10 / cbrt
+// -> ortho DCT-II -> first ccNum coefficients.  One persistent kernel, samples read from HBM once (1-D TMA bulk copies
+// through an mbarrier ring), results leave as whole tiles (TMA bulk stores, also to peer GPUs).
+//
+// Replaces, for fftLength = 2048, the same reference chain as mfcc_fused.cu (v1):
+//   stftObj_stft (src/stft_algorithm.c:696-715, 790-801) -> __mccut (src/reassign_algorithm.c:600-604)
+//   -> __mcsquare / sqrtf (src/bft_algorithm.c:489-497) -> __mdot1 (:515-518, src/vector/flux_vector.c:55-86)
+//   -> log10f clamp / powf(1/3) (src/feature/xxcc_algorithm.c:124-140) -> fftObj_dct (:142-149) -> cut (:151-155)
+//
+// What changed against v1 (profiles/r1_final_hotspots.txt: bank loop 28 %, post-pass shuffles 15 % of frame-warp time):
+//  * the real 2048-point FFT is split as 64 (real, in registers) x 32 (complex, in registers): lane n2 transforms the
+//    64 real samples x[32 n1 + n2] (packed complex 32-point DFT + an IN-LANE post-pass, compile-time twiddles), the
+//    columns k1 = 1..31 are twiddled, transposed through shared memory and transformed again; lane k1 then holds the
+//    bins k1 + 64 k2 and (by Hermitian symmetry) 2048 - (k1 + 64 k2): all 1025 bins without any cross-lane exchange
+//    (v1: 32 shuffles + a second twiddle pass per frame);
+//  * the two "half" columns k1 = 0 and k1 = 32 (real-valued after stage 1) are collected for the whole tile and
+//    transformed by the TMA producer warp, one lane per (frame, column): 1/13 of a frame's work instead of a
+//    divergent second pass in every frame warp;
+//  * the filter bank is applied per TILE by the helper warps, not per frame by the frame warps: the power spectra of
+//    the tile's frames sit in shared memory as [bin pair][frame], lane = frame, and every bin pair is multiplied
+//    ONCE for the two filters that overlap on it (interval form: rising slope of filter i, falling slope of filter
+//    i-1, the reference's own float weights, no re-normalisation) with packed FFMA2; the weights are warp-uniform and
+//    come from the kernel parameter block (constant bank, no shared-memory traffic);
+//  * the 13 x cc result tile is staged in shared memory and leaves as one TMA bulk store per destination (this GPU and,
+//    for the fused all-gather, every peer GPU): full lines over NVLink instead of 32-bit stores.
+#include <math.h>
+#include <stdlib.h>
+#include <string.h>
+#include "common.cuh"
+#include "fft32_gen.cuh"
+
+namespace {
+
+constexpr int kN = 2048;
+constexpr int kBins = 1025;
+constexpr int kPairs = 513;         // bin pairs of the power-spectrum tile
+#ifndef AF2_FRAME_WARPS
+#define AF2_FRAME_WARPS 13
+#endif
+#ifndef AF2_EPI_WARPS
+#define AF2_EPI_WARPS 2
+#endif
+#ifndef AF2_ABLATE
+#define AF2_ABLATE 0                // diagnostic timing builds: 1 no bank, 4 no FFTs, 8 no transposes, 16 no loads
+#endif
+constexpr int kFW = AF2_FRAME_WARPS;            // frame warps = max frames per tile (<= 16: one mma M tile)
+constexpr int kEW = AF2_EPI_WARPS;              // bank + DCT warps
+constexpr int kThreads = (kFW + 1 + kEW) * 32;  // + producer / special-column warp
+constexpr int kMaxPeers = 15;
+constexpr int kMaxNum = 128;
+constexpr int kLPitch = 132;        // log-mel tile row pitch (floats): 4g + t -> 32 distinct banks for mma A fragments
+constexpr int kMaxTab = 1408;       // bank table entries (one float4 per bin pair of an interval) in the parameter block
+constexpr int kSpecPitch = 17;      // c64 slots per n2 row of the special-column buffer (odd -> conflict-free both ways)
+constexpr int kScratchFloats = 33 * 32;
+
+struct Plan {
+    float2 *dWinPairs;              // [32 m][32 lane]  0.5 * (w[64 m + lane], w[64 m + 32 + lane])
+    float2 *dTw;                    // [17][32]  W_2048^(lane * ka), ka = 0..15; row 16: W_2048^(16 lane)
+    float *dDct;                    // [128 m][dctPitch]
+    int num, ccNum, ct, dataType;
+    int ivFirst[kEW + 1];
+    unsigned ivDesc[kMaxNum + 2];   // (first bin pair << 16) | table offset, entry num+1 = end sentinel
+    int tabLen;
+    float4 *tab;                    // host copy of the bank table
+};
+
+struct Params {
+    const float *data;
+    float *out;
+    const float2 *winPairs, *tw;
+    const float *dct;
+    long long dataStride, totalTiles;
+    int batch, timeLength, hop, framesPerTile, tilesPerClip, spanFloats, stages;
+    int num, ccNum, rectify, dataType, rawMel, pitchPairs, bulkStore, dctPitch;
+    int nPeer;
+    float *peerOut[kMaxPeers];
+    int offSpan, offScratch, offP, offWin, offTw, offSpec, offDct, offL, offStage, offBar, stageBytes;
+    int ivFirst[kEW + 1];
+    unsigned ivDesc[kMaxNum + 2];
+    float4 bankW[kMaxTab];
+};
+static_assert(sizeof(Params) < 32000, "kernel parameter block must stay below the 32 KB limit");
+
+__device__ __forceinline__ void named_bar_sync(int id, int threads) {
+    asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(threads) : "memory");
+}
+__device__ __forceinline__ void fence_proxy_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void bulk_store(void *dstGmem, const void *srcSmem, uint32_t bytes) {
+    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;"
+                 ::"l"(dstGmem), "r"(af_smem_u32(srcSmem)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait_read0() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait0() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+
+__device__ __forceinline__ float rectify_value(float v, int rectify) {
+    if (rectify == CepstralRectify_CubicRoot) return powf(v, 1.0f / 3.0f);
+    return __log2f(v < 1e-8f ? 1e-8f : v) * 0.30102999566398120f;      // log10 via MUFU.LG2
+}
+
+template <int CT>
+__global__ void __launch_bounds__(kThreads, 1) k_mfcc_fused2(const __grid_constant__ Params p) {
+    extern __shared__ __align__(128) unsigned char smem[];
+    float *span = reinterpret_cast<float *>(smem + p.offSpan);
+    float *scratchAll = reinterpret_cast<float *>(smem + p.offScratch);
+    float *sP = reinterpret_cast<float *>(smem + p.offP);                 // [kPairs][pitchPairs][2]
+    float2 *sWin = reinterpret_cast<float2 *>(smem + p.offWin);
+    float2 *sTw = reinterpret_cast<float2 *>(smem + p.offTw);
+    c64 *sSpec = reinterpret_cast<c64 *>(smem + p.offSpec);               // [2][32 n2][kSpecPitch]
+    float *sDct = reinterpret_cast<float *>(smem + p.offDct);
+    float *sL = reinterpret_cast<float *>(smem + p.offL);                 // [16][kLPitch]
+    float *sStage = reinterpret_cast<float *>(smem + p.offStage);         // result tile(s), dense rows
+    uint64_t *fullBar = reinterpret_cast<uint64_t *>(smem + p.offBar);    // [2] TMA landed
+    uint64_t *emptyBar = fullBar + 2;                                     // [2] frame warps took their samples
+    uint64_t *specFull = fullBar + 4;                                     // [2] special columns of a tile stored
+    uint64_t *pFull = fullBar + 6;                                        // power-spectrum tile complete
+    uint64_t *pEmpty = fullBar + 7;                                       // bank done with it
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int pitch = p.pitchPairs;
+
+    // ---- one-time: tables -> shared, zero the tiles (pad slots are multiplied by zero weights), barriers ----
+    for (int i = threadIdx.x; i < 32 * 32; i += kThreads) sWin[i] = p.winPairs[i];
+    for (int i = threadIdx.x; i < 17 * 32; i += kThreads) sTw[i] = p.tw[i];
+    for (int i = threadIdx.x; i < kFW * kScratchFloats; i += kThreads) scratchAll[i] = 0.0f;
+    for (int i = threadIdx.x; i < kPairs * pitch * 2; i += kThreads) sP[i] = 0.0f;
+    for (int i = threadIdx.x; i < 2 * 32 * kSpecPitch; i += kThreads) sSpec[i] = 0ull;
+    if (!p.rawMel) {
+        for (int i = threadIdx.x; i < kMaxNum * p.dctPitch; i += kThreads) sDct[i] = p.dct[i];
+        for (int i = threadIdx.x; i < 16 * kLPitch; i += kThreads) sL[i] = 0.0f;
+    }
+    for (int i = threadIdx.x; i < p.stageBytes / 4; i += kThreads) sStage[i] = 0.0f;
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < 2; s++) {
+            af_mbar_init(&fullBar[s], 1);
+            af_mbar_init(&emptyBar[s], kFW);
+            af_mbar_init(&specFull[s], kFW);
+        }
+        af_mbar_init(pFull, kFW + 1);
+        af_mbar_init(pEmpty, kEW);
+        af_fence_barrier_init();
+    }
+    __syncthreads();
+
+    const int F = p.framesPerTile;
+
+    if (warp == kFW) {
+        // ================= producer (TMA) + special columns k1 = 0 / 32 of every frame of the tile =================
+        const int S = p.stages;
+        auto issue = [&](long long tile, int stage) {
+            const long long clip = tile / p.tilesPerClip;
+            const int f0 = (int)(tile % p.tilesPerClip) * F;
+            const int nf = min(F, p.timeLength - f0);
+            const uint32_t bytes = (uint32_t)(((nf - 1) * p.hop + kN) * 4);
+            af_mbar_arrive_expect_tx(&fullBar[stage], bytes);
+            af_tma_load_1d(span + (size_t)stage * p.spanFloats, p.data + clip * p.dataStride + (long long)f0 * p.hop, bytes,
+                           &fullBar[stage]);
+        };
+        if (lane == 0)
+            for (int s = 0; s < S; s++) {
+                const long long tile = blockIdx.x + (long long)s * gridDim.x;
+                if (tile < p.totalTiles) issue(tile, s);
+            }
+        const int f = lane & 15, kind = lane >> 4;              // lane = (frame, column kind)
+        int it = 0;
+        for (long long tile = blockIdx.x; tile < p.totalTiles; tile += gridDim.x, ++it) {
+            const int stage = it % S;
+            if (lane == 0) {
+                af_mbar_wait_sleepy(&emptyBar[stage], (uint32_t)(it / S) & 1u);       // tile `it` taken: refill the slot
+                const long long next = tile + (long long)S * gridDim.x;
+                if (next < p.totalTiles) issue(next, stage);
+            }
+            __syncwarp();
+            const int f0 = (int)(tile % p.tilesPerClip) * F;
+            const int nf = min(F, p.timeLength - f0);
+            const int sb = it & 1;
+            af_mbar_wait_sleepy(&specFull[sb], (uint32_t)(it >> 1) & 1u);
+            // a[n2] = R_n2[0], b[n2] = R_n2[32] (both real).  kind 0: X[64 k2] = DFT32(a)[k2], k2 = 0..16;
+            // kind 1: X[32 + 64 k2] = DFT32(b[n2] W_64^n2)[k2], k2 = 0..15
+            c64 u[32];
+            const c64 *sp = sSpec + (size_t)sb * 32 * kSpecPitch + min(f, nf - 1);
+#pragma unroll
+            for (int n2 = 0; n2 < 32; n2++) {
+                float a, b;
+                c_unpack(sp[n2 * kSpecPitch], a, b);
+                const float v = kind ? b : a;
+                u[n2] = kind ? af_mul_w64(c_pack(v, 0.0f), n2 & 15) : c_pack(v, 0.0f);
+                if (n2 >= 16 && kind) u[n2] = c_mul_mi(u[n2]);                        // W_64^16 = -i
+            }
+            af_fft32(u);
+            af_mbar_wait_sleepy(pEmpty, ((uint32_t)it & 1u) ^ 1u);                   // bank done with the previous tile
+            if (f < nf) {
+                float *dst = sP + 2 * f + (kind ? 32 * pitch : 0);                    // bin 64 k2 + 32 kind -> pair 32 k2 + 16 kind
+#pragma unroll
+                for (int k2 = 0; k2 < 16; k2++) {
+                    float pw = c_norm2(u[AF_BR5(k2)]);
+                    if (p.dataType == SpectralData_Mag) pw = sqrtf(pw);
+                    dst[(size_t)k2 * 64 * pitch] = pw;
+                }
+                if (!kind) {
+                    float pw = c_norm2(u[AF_BR5(16)]);
+                    if (p.dataType == SpectralData_Mag) pw = sqrtf(pw);
+                    dst[(size_t)16 * 64 * pitch] = pw;                                // bin 1024
+                }
+            }
+            __syncwarp();
+            if (lane == 0) af_mbar_arrive(pFull);
+        }
+        return;
+    }
+
+    if (warp > kFW) {
+        // ================= helpers: interval-form bank over the tile, then the DCT on the tensor cores =================
+        const int e = warp - (kFW + 1);
+        const int g = lane >> 2, t = lane & 3;
+        const int i0 = p.ivFirst[e], i1 = p.ivFirst[e + 1];        // filters [i0, i1) = intervals i0 .. i1
+        const int rowFloats = p.rawMel ? p.num : p.ccNum;
+        constexpr int kNB = (CT + kEW - 1) / kEW;                  // n-blocks of the DCT per warp
+        int it = 0;
+        for (long long tile = blockIdx.x; tile < p.totalTiles; tile += gridDim.x, ++it) {
+            const long long clip = tile / p.tilesPerClip;
+            const int f0 = (int)(tile % p.tilesPerClip) * F;
+            const int nf = min(F, p.timeLength - f0);
+            float *stage = sStage + (p.rawMel ? (size_t)(it & 1) * (p.stageBytes / 8) : 0);
+        const int stagePitch = p.rawMel ? p.num + 4 : p.ccNum;      // raw filter-bank rows are padded (bank conflicts), cepstra dense
+            af_mbar_wait_sleepy(pFull, (uint32_t)it & 1u);
+            // ---- bank: lane = frame; per interval the rising weights of filter i and the falling weights of filter i-1
+            if (i1 > i0 && lane < 16 && !(AF2_ABLATE & 1)) {      // second half-warp idle: no shared-memory wavefronts for it
+                const int fr = min(lane, nf - 1);
+                const c64 *Pp = reinterpret_cast<const c64 *>(sP) + fr;
+                float prevR = 0.0f;
+                for (int i = i0; i <= i1; i++) {
+                    const unsigned d0 = p.ivDesc[i], d1 = p.ivDesc[i + 1];
+                    const int off1 = (int)(d1 & 0xffffu);
+                    int j = (int)(d0 & 0xffffu);
+                    const c64 *q = Pp + (size_t)(d0 >> 16) * pitch;
+                    c64 aR = 0ull, aF = 0ull, bR = 0ull, bF = 0ull;
+                    for (; j + 1 < off1; j += 2) {
+                        const float4 w0 = p.bankW[j], w1 = p.bankW[j + 1];
+                        const c64 v0 = q[0], v1 = q[pitch];
+                        q += 2 * pitch;
+                        aR = v_fma(v0, c_pack(w0.x, w0.y), aR);
+                        aF = v_fma(v0, c_pack(w0.z, w0.w), aF);
+                        bR = v_fma(v1, c_pack(w1.x, w1.y), bR);
+                        bF = v_fma(v1, c_pack(w1.z, w1.w), bF);
+                    }
+                    if (j < off1) {
+                        const float4 w0 = p.bankW[j];
+                        const c64 v0 = q[0];
+                        aR = v_fma(v0, c_pack(w0.x, w0.y), aR);
+                        aF = v_fma(v0, c_pack(w0.z, w0.w), aF);
+                    }
+                    float r0, r1, f0_, f1_;
+                    c_unpack(c_add(aR, bR), r0, r1);
+                    c_unpack(c_add(aF, bF), f0_, f1_);
+                    if (i > i0 && lane < nf) {
+                        const int m = i - 1;
+                        const float v = prevR + (f0_ + f1_);
+                        if (p.rawMel) stage[lane * stagePitch + m] = v;
+                        else sL[lane * kLPitch + m] = rectify_value(v, p.rectify);
+                    }
+                    prevR = r0 + r1;
+                }
+            }
+            __syncwarp();
+            if (lane == 0) af_mbar_arrive(pEmpty);                 // frame warps may overwrite the power tile
+            if (e == 0) bulk_wait_read0();                         // the previous tiles' bulk stores have read their staging
+            if (p.rawMel) fence_proxy_async_smem();
+            named_bar_sync(1, kEW * 32);                           // A: the whole log-mel tile is in shared memory
+            if (!p.rawMel) {
+                // out[16 x 8 CT] = L[16 x 128] . D^T[128 x 8 CT]: mma.sync m16n8k8 TF32, 3xTF32 split (hi by truncation,
+                // lo = x - hi exact), separate accumulators for hi*hi and the cross terms
+                float acc[kNB][4], acx[kNB][4];
+#pragma unroll
+                for (int n = 0; n < kNB; n++) {
+                    acc[n][0] = acc[n][1] = acc[n][2] = acc[n][3] = 0.0f;
+                    acx[n][0] = acx[n][1] = acx[n][2] = acx[n][3] = 0.0f;
+                }
+#define AF_MMA_TF32(ACC, A0, A1, A2, A3, B0, B1)                                                              \
+    asm("mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};" \
+        : "+f"(ACC[0]), "+f"(ACC[1]), "+f"(ACC[2]), "+f"(ACC[3])                                              \
+        : "r"(A0), "r"(A1), "r"(A2), "r"(A3), "r"(B0), "r"(B1))
+#pragma unroll 2
+                for (int k0 = 0; k0 < kMaxNum; k0 += 8) {
+                    const float af[4] = {sL[g * kLPitch + k0 + t], sL[(g + 8) * kLPitch + k0 + t],
+                                         sL[g * kLPitch + k0 + t + 4], sL[(g + 8) * kLPitch + k0 + t + 4]};
+                    uint32_t ah[4], al[4];
+#pragma unroll
+                    for (int i = 0; i < 4; i++) {
+                        ah[i] = __float_as_uint(af[i]) & 0xffffe000u;
+                        al[i] = __float_as_uint(af[i] - __uint_as_float(ah[i])) & 0xffffe000u;
+                    }
+#pragma unroll
+                    for (int n = 0; n < kNB; n++) {
+                        const int nb = e + n * kEW;
+                        if (nb < CT) {
+                            const float bf[2] = {sDct[(k0 + t) * p.dctPitch + nb * 8 + g], sDct[(k0 + t + 4) * p.dctPitch + nb * 8 + g]};
+                            uint32_t bh[2], bl[2];
+#pragma unroll
+                            for (int i = 0; i < 2; i++) {
+                                bh[i] = __float_as_uint(bf[i]) & 0xffffe000u;
+                                bl[i] = __float_as_uint(bf[i] - __uint_as_float(bh[i])) & 0xffffe000u;
+                            }
+                            AF_MMA_TF32(acx[n], al[0], al[1], al[2], al[3], bh[0], bh[1]);
+                            AF_MMA_TF32(acc[n], ah[0], ah[1], ah[2], ah[3], bh[0], bh[1]);
+                            AF_MMA_TF32(acx[n], ah[0], ah[1], ah[2], ah[3], bl[0], bl[1]);
+                        }
+                    }
+                }
+#undef AF_MMA_TF32
+                // C fragment: rows g and g+8, columns nb*8 + 2t, +1 -> dense staging tile [nf][ccNum]
+#pragma unroll
+                for (int n = 0; n < kNB; n++) {
+                    const int nb = e + n * kEW;
+                    if (nb >= CT) continue;
+                    const int c = nb * 8 + 2 * t;
+                    const float v0 = acc[n][0] + acx[n][0], v1 = acc[n][1] + acx[n][1];
+                    const float v2 = acc[n][2] + acx[n][2], v3 = acc[n][3] + acx[n][3];
+                    if (g < nf) {
+                        if (c < p.ccNum) stage[g * p.ccNum + c] = v0;
+                        if (c + 1 < p.ccNum) stage[g * p.ccNum + c + 1] = v1;
+                    }
+                    if (g + 8 < nf) {
+                        if (c < p.ccNum) stage[(g + 8) * p.ccNum + c] = v2;
+                        if (c + 1 < p.ccNum) stage[(g + 8) * p.ccNum + c + 1] = v3;
+                    }
+                }
+                fence_proxy_async_smem();
+                named_bar_sync(2, kEW * 32);                       // B: the result tile is staged
+            }
+            // ---- the tile leaves: destination 0 is this GPU's buffer, 1..nPeer the peers' gathered arrays (NVLink) ----
+            const long long tileOff = ((long long)clip * p.timeLength + f0) * rowFloats;
+            if (p.bulkStore) {
+                if (e == 0) {
+                    if (p.rawMel) {                                 // one row per lane (padded staging rows)
+                        if (lane < nf) bulk_store(p.out + tileOff + (long long)lane * rowFloats, stage + lane * stagePitch, (uint32_t)(rowFloats * 4));
+                    } else if (lane <= p.nPeer) {                   // one destination per lane, the whole tile at once
+                        float *o = (lane == 0 ? p.out : p.peerOut[lane - 1]) + tileOff;
+                        bulk_store(o, stage, (uint32_t)(nf * rowFloats * 4));
+                    }
+                    bulk_commit();
+                }
+            } else {
+                for (int d = 0; d <= p.nPeer; d++) {
+                    float *o = (d == 0 ? p.out : p.peerOut[d - 1]) + tileOff;
+                    for (int r = 0; r < nf; r++)
+                        for (int i = e * 32 + lane; i < rowFloats; i += kEW * 32) o[(long long)r * rowFloats + i] = stage[r * stagePitch + i];
+                }
+            }
+        }
+        if (e == 0) bulk_wait0();
+        return;
+    }
+
+    // ================= frame warps: warp w transforms frame f0 + w of every tile =================
+    float *scratch = scratchAll + (size_t)warp * kScratchFloats;
+    const c64 *sWinC = reinterpret_cast<const c64 *>(sWin);
+    const c64 *sTwC = reinterpret_cast<const c64 *>(sTw);
+    const c64 w16 = sTwC[16 * 32 + lane];                          // W_2048^(16 lane)
+    // power-tile addresses (floats): bin = lane + 64 k2 (k2 < 16) and 64 (32 - k2) - lane (k2 >= 16)
+    const int strideK2 = 64 * pitch;
+    const int offLo = (lane >> 1) * (2 * pitch) + 2 * warp + (lane & 1);
+    const int offHi = -((lane + 1) >> 1) * (2 * pitch) + 2 * warp + (lane & 1);
+
+    int it = 0;
+    for (long long tile = blockIdx.x; tile < p.totalTiles; tile += gridDim.x, ++it) {
+        const int stage = it % p.stages;
+        const int f0 = (int)(tile % p.tilesPerClip) * F;
+        const int nf = min(F, p.timeLength - f0);
+        const bool active = warp < nf;
+        const int sb = it & 1;
+
+        af_mbar_wait(&fullBar[stage], (uint32_t)(it / p.stages) & 1u);
+
+        c64 z[32];
+        if (active) {
+            // ---- A: x[32 n1 + lane], n1 = 0..63, times 0.5 w; packed z[m] = (s[2m], s[2m+1]) ----
+            const float *sp = span + (size_t)stage * p.spanFloats + warp * p.hop + lane;
+#pragma unroll
+            for (int m = 0; m < 32; m++)
+                z[m] = (AF2_ABLATE & 16) ? c_pack(1.0f + m, lane) : v_mul(c_pack(sp[64 * m], sp[64 * m + 32]), sWinC[m * 32 + lane]);
+        }
+        __syncwarp();
+        if (lane == 0) af_mbar_arrive(&emptyBar[stage]);           // span slot may be refilled
+        if (!active) {
+            // keep the tile protocols in step (one arrival per warp per tile and barrier)
+            if (lane == 0) af_mbar_arrive(&specFull[sb]);
+            af_mbar_wait(pEmpty, ((uint32_t)it & 1u) ^ 1u);
+            if (lane == 0) af_mbar_arrive(pFull);
+            continue;
+        }
+
+        // ---- B: 64-point real DFT of the lane's column: packed complex 32-point DFT + in-lane post-pass ----
+        if (!(AF2_ABLATE & 4)) af_fft32(z);                        // Z[k] at AF_BR5(k)
+#pragma unroll
+        for (int k = 1; k < 16; k++) {
+            const c64 zk = z[AF_BR5(k)], zc = c_conj(z[AF_BR5(32 - k)]);
+            const c64 ev = c_add(zk, zc);
+            const c64 od = af_mul_w64(c_mul_mi(c_sub(zk, zc)), k);  // -i W_64^k (Z[k] - conj Z[32-k])
+            z[AF_BR5(k)] = c_add(ev, od);                           // R[k]   (window carries the 1/2)
+            z[AF_BR5(32 - k)] = c_conj(c_sub(ev, od));              // R[32-k]
+        }
+        z[AF_BR5(16)] = v_mul(z[AF_BR5(16)], c_pack(2.0f, -2.0f)); // R[16] = 2 conj Z[16]
+        {
+            float zr, zi;
+            c_unpack(z[0], zr, zi);
+            z[0] = c_pack(2.0f * (zr + zi), 2.0f * (zr - zi));      // (R[0], R[32]), both real
+        }
+        sSpec[((size_t)sb * 32 + lane) * kSpecPitch + warp] = z[0];
+        __syncwarp();
+        if (lane == 0) af_mbar_arrive(&specFull[sb]);
+
+        // ---- C: columns k1 = 1..31 times W_2048^(lane k1), 32 x 32 transpose (real plane, then imaginary plane) ----
+        {
+            float yr[32], yi[32];
+#pragma unroll
+            for (int k1 = 1; k1 < 32; k1++) {
+                c64 y = z[AF_BR5(k1)];
+                if (k1 >= 16) y = c_mul(y, w16);
+                if (k1 & 15) y = c_mul(y, sTwC[(k1 & 15) * 32 + lane]);
+                c_unpack(y, yr[k1], yi[k1]);
+            }
+            if (!(AF2_ABLATE & 8)) {
+#pragma unroll
+                for (int k1 = 1; k1 < 32; k1++) scratch[k1 * 33 + lane] = yr[k1];
+                __syncwarp();
+#pragma unroll
+                for (int n2 = 0; n2 < 32; n2++) yr[n2] = scratch[lane * 33 + n2];
+                __syncwarp();
+#pragma unroll
+                for (int k1 = 1; k1 < 32; k1++) scratch[k1 * 33 + lane] = yi[k1];
+                __syncwarp();
+#pragma unroll
+                for (int n2 = 0; n2 < 32; n2++) z[n2] = c_pack(yr[n2], scratch[lane * 33 + n2]);
+                __syncwarp();
+            } else {
+                yr[0] = yi[0] = 0.0f;
+#pragma unroll
+                for (int n2 = 0; n2 < 32; n2++) z[n2] = c_pack(yr[n2], yi[n2]);
+            }
+        }
+        // ---- D: 32-point DFT over n2 in lane k1: bins k1 + 64 k2 and, mirrored, 64 (32 - k2) - k1 ----
+        if (!(AF2_ABLATE & 4)) af_fft32(z);
+        af_mbar_wait(pEmpty, ((uint32_t)it & 1u) ^ 1u);            // bank done with the previous tile's spectra
+        if (lane) {
+#pragma unroll
+            for (int k2 = 0; k2 < 32; k2++) {
+                float pw = c_norm2(z[AF_BR5(k2)]);
+                if (p.dataType == SpectralData_Mag) pw = sqrtf(pw);
+                if (k2 < 16) sP[offLo + k2 * strideK2] = pw;
+                else sP[offHi + (32 - k2) * strideK2] = pw;
+            }
+        }
+        __syncwarp();
+        if (lane == 0) af_mbar_arrive(pFull);
+    }
+}
+
+void free_plan(Plan *pl) {
+    if (!pl) return;
+    af_dev_free(pl->dWinPairs); af_dev_free(pl->dTw); af_dev_free(pl->dDct);
+    free(pl->tab);
+    free(pl);
+}
+
+// ---- interval form of a banded bank in which at most two consecutive filters overlap on any bin ------------------
+// Every bin k with a non-zero weight is given to ONE interval i in [0, num]: on interval i filter i contributes its
+// weight as "rise" and filter i-1 as "fall", so   mel_m = sum_{k in I_m} bank[m][k] P[k] + sum_{k in I_{m+1}} bank[m][k] P[k]
+// with the bank's own float weights (the same products as the direct form, each bin read once for both filters).
+struct Intervals {
+    int owner[kBins];               // interval of each bin, -1 = no filter covers it
+    int first[kMaxNum + 1], last[kMaxNum + 1];     // bin range of interval i (last < first: empty)
+};
+
+bool build_intervals2(const float *bank, int num, Intervals *iv) {
+    if (num < 1 || num > kMaxNum) return false;
+    int cur = 0;
+    for (int i = 0; i <= num; i++) { iv->first[i] = 1; iv->last[i] = 0; }
+    for (int k = 0; k < kBins; k++) {
+        int cover[3], nc = 0;
+        for (int m = 0; m < num && nc < 3; m++)
+            if (bank[(size_t)m * kBins + k] != 0.0f) cover[nc++] = m;
+        iv->owner[k] = -1;
+        if (nc == 0) continue;
+        if (nc > 2 || (nc == 2 && cover[1] != cover[0] + 1)) return false;
+        int i;
+        if (nc == 2) i = cover[1];
+        else i = cur <= cover[0] ? cover[0] : cover[0] + 1;
+        if (i < cur || i > cover[0] + 1) return false;             // intervals must be monotone runs of bins
+        cur = i;
+        iv->owner[k] = i;
+        if (iv->last[i] < iv->first[i]) iv->first[i] = k;
+        iv->last[i] = k;
+    }
+    return true;
+}
+
+// table: per interval the float4 (rise[2q], rise[2q+1], fall[2q], fall[2q+1]) of its bin pairs q; returns entries or -1
+int build_table(const float *bank, int num, const Intervals *iv, unsigned *desc /* num+2 */, float4 *tab /* kMaxTab */) {
+    int off = 0;
+    for (int i = 0; i <= num; i++) {
+        const bool empty = iv->last[i] < iv->first[i];
+        const int q0 = empty ? 0 : iv->first[i] >> 1, q1 = empty ? -1 : iv->last[i] >> 1;
+        desc[i] = ((unsigned)q0 << 16) | (unsigned)off;
+        for (int q = q0; q <= q1; q++) {
+            if (off >= kMaxTab) return -1;
+            float w[4] = {0, 0, 0, 0};
+            for (int h = 0; h < 2; h++) {
+                const int k = 2 * q + h;
+                if (k >= kBins || iv->owner[k] != i) continue;
+                if (i < num) w[h] = bank[(size_t)i * kBins + k];
+                if (i > 0) w[2 + h] = bank[(size_t)(i - 1) * kBins + k];
+            }
+            tab[off++] = make_float4(w[0], w[1], w[2], w[3]);
+        }
+    }
+    desc[num + 1] = (unsigned)off;
+    return off;
+}
+
+// filters [first[e], first[e+1]) per helper warp, balanced by (pairs + per-interval overhead) of the intervals it walks
+void split_filters(int num, const unsigned *desc, int *first /* kEW+1 */) {
+    double cost[kMaxNum + 1], total = 0;
+    for (int i = 0; i <= num; i++) { cost[i] = 5.0 + 2.0 * (double)((desc[i + 1] & 0xffffu) - (desc[i] & 0xffffu)); total += cost[i]; }
+    first[0] = 0;
+    double acc = 0;
+    int e = 1;
+    for (int m = 0; m < num && e < kEW; m++) {
+        acc += cost[m];
+        if (acc >= total * e / kEW) first[e++] = m + 1;
+    }
+    for (; e <= kEW; e++) first[e] = num;
+    first[kEW] = num;
+}
+
+}  // namespace
+
+extern "C" int af_mfcc2_supported(int fftLength, int num, int ccNum, const float *bank) {
+    if (fftLength != kN || num < 1 || num > kMaxNum || ccNum < 1 || ccNum > 64 || !bank) return 0;
+    Intervals *iv = static_cast<Intervals *>(malloc(sizeof(Intervals)));
+    float4 *tab = static_cast<float4 *>(malloc(sizeof(float4) * kMaxTab));
+    unsigned desc[kMaxNum + 2];
+    const int ok = iv && tab && build_intervals2(bank, num, iv) && build_table(bank, num, iv, desc, tab) >= 0;
+    free(iv); free(tab);
+    return ok;
+}
+
+extern "C" void af_mfcc2_plan_free(void *plan) { free_plan(static_cast<Plan *>(plan)); }
+
+extern "C" int af_mfcc2_plan_build(void **planOut, int fftLength, int num, int ccNum, const float *window,
+                                   const float *bank, const float *dct /* ccNum x num */, int dataType) {
+    *planOut = NULL;
+    if (!af_mfcc2_supported(fftLength, num, ccNum, bank)) return af_fail(AF_ERR_UNSUPPORTED, "fused MFCC v2 plan: unsupported configuration");
+    Plan *pl = static_cast<Plan *>(calloc(1, sizeof(Plan)));
+    if (!pl) return AF_ERR_NOMEM;
+    pl->num = num; pl->ccNum = ccNum; pl->dataType = dataType;
+    pl->ct = ccNum <= 16 ? 2 : ccNum <= 24 ? 3 : ccNum <= 40 ? 5 : 8;
+    int rc = AF_OK;
+
+    float2 *wp = static_cast<float2 *>(malloc(sizeof(float2) * 1024));
+    for (int m = 0; m < 32; m++)
+        for (int l = 0; l < 32; l++) wp[m * 32 + l] = make_float2(0.5f * window[64 * m + l], 0.5f * window[64 * m + 32 + l]);
+    rc = af_dev_upload(reinterpret_cast<void **>(&pl->dWinPairs), wp, sizeof(float2) * 1024);
+    for (int ka = 0; ka < 17; ka++)
+        for (int l = 0; l < 32; l++) {
+            const double a = -2.0 * M_PI * (double)((ka < 16 ? ka : 16) * l) / 2048.0;
+            wp[ka * 32 + l] = make_float2((float)cos(a), (float)sin(a));
+        }
+    if (rc == AF_OK) rc = af_dev_upload(reinterpret_cast<void **>(&pl->dTw), wp, sizeof(float2) * 17 * 32);
+    free(wp);
+
+    Intervals *iv = static_cast<Intervals *>(malloc(sizeof(Intervals)));
+    pl->tab = static_cast<float4 *>(malloc(sizeof(float4) * kMaxTab));
+    if (!iv || !pl->tab) { free(iv); free_plan(pl); return AF_ERR_NOMEM; }
+    build_intervals2(bank, num, iv);
+    pl->tabLen = build_table(bank, num, iv, pl->ivDesc, pl->tab);
+    split_filters(num, pl->ivDesc, pl->ivFirst);
+    free(iv);
+
+    // DCT table as the mma B operand: D^T[m][c], row pitch % 32 == 8 -> conflict-free fragment reads
+    const int pitch = pl->ct <= 5 ? 40 : 72;
+    float *dt = static_cast<float *>(calloc((size_t)kMaxNum * pitch, sizeof(float)));
+    for (int m = 0; m < num; m++)
+        for (int c = 0; c < ccNum; c++) dt[(size_t)m * pitch + c] = dct[(size_t)c * num + m];
+    if (rc == AF_OK) rc = af_dev_upload(reinterpret_cast<void **>(&pl->dDct), dt, sizeof(float) * (size_t)kMaxNum * pitch);
+    free(dt);
+    if (rc != AF_OK) { free_plan(pl); return rc; }
+    *planOut = pl;
+    return AF_OK;
+}
+
+static int launch_fused2(void *plan, const float *data, int dataLength, int batch, int timeLength, int slideLength,
+                         int rectifyType, float *out, int nPeer, float *const *peerOut, int rawMel, void *stream) {
+    Plan *pl = static_cast<Plan *>(plan);
+    if (!pl) return af_fail(AF_ERR_ARG, "fused MFCC v2: no plan");
+    if (batch <= 0 || timeLength <= 0) return AF_OK;
+    if (slideLength % 4 || dataLength % 4 || (reinterpret_cast<uintptr_t>(data) & 15))
+        return af_fail(AF_ERR_UNSUPPORTED, "fused MFCC needs 16-byte aligned clips and slideLength %% 4 == 0 (TMA bulk copy)");
+    if (nPeer < 0 || nPeer > kMaxPeers || (nPeer > 0 && !peerOut)) return af_fail(AF_ERR_ARG, "fused MFCC: nPeer=%d outside [0, %d]", nPeer, kMaxPeers);
+
+    Params *pp = static_cast<Params *>(malloc(sizeof(Params)));     // 24 KB: off the stack
+    if (!pp) return AF_ERR_NOMEM;
+    memset(pp, 0, sizeof(Params));
+    pp->data = data; pp->out = out; pp->winPairs = pl->dWinPairs; pp->tw = pl->dTw; pp->dct = pl->dDct;
+    pp->dataStride = dataLength; pp->batch = batch; pp->timeLength = timeLength; pp->hop = slideLength;
+    pp->num = pl->num; pp->ccNum = pl->ccNum; pp->rectify = rectifyType; pp->dataType = pl->dataType; pp->rawMel = rawMel;
+    pp->dctPitch = pl->ct <= 5 ? 40 : 72;
+    pp->nPeer = nPeer;
+    for (int d = 0; d < nPeer; d++) pp->peerOut[d] = peerOut[d];
+    for (int e = 0; e <= kEW; e++) pp->ivFirst[e] = pl->ivFirst[e];
+    memcpy(pp->ivDesc, pl->ivDesc, sizeof(pp->ivDesc));
+    memcpy(pp->bankW, pl->tab, sizeof(float4) * (size_t)pl->tabLen);
+    const int rowFloats = rawMel ? pl->num : pl->ccNum;
+    int bulk = rowFloats % 4 == 0 && (reinterpret_cast<uintptr_t>(out) & 15) == 0;
+    for (int d = 0; d < nPeer; d++) if (reinterpret_cast<uintptr_t>(peerOut[d]) & 15) bulk = 0;
+    const char *sv = getenv("AFB200_MFCC_STORE");
+    if (sv && !strcmp(sv, "plain")) bulk = 0;
+    pp->bulkStore = bulk;
+
+    // shared-memory carve-up: as many frames per tile as fit (<= kFW), two TMA stages when they fit, else one
+    const int budget = 227 * 1024;
+    int F = kFW < timeLength ? kFW : timeLength, stages = 2, total = 0;
+    for (;;) {
+        int o = 0;
+        const int spanFloats = (F - 1) * slideLength + kN;
+        const int pitchPairs = F | 1;
+        pp->offSpan = o;    o += stages * spanFloats * 4;
+        pp->offScratch = o; o += kFW * kScratchFloats * 4;
+        pp->offP = o;       o += kPairs * pitchPairs * 8;
+        pp->offWin = o;     o += 32 * 32 * 8;
+        pp->offTw = o;      o += 17 * 32 * 8;
+        pp->offSpec = o;    o += 2 * 32 * kSpecPitch * 8;
+        pp->offDct = o;     o += rawMel ? 0 : kMaxNum * pp->dctPitch * 4;
+        pp->offL = o;       o += rawMel ? 0 : 16 * kLPitch * 4;
+        pp->stageBytes = rawMel ? 2 * ((F * (pl->num + 4) * 4 + 15) & ~15) : ((F * pl->ccNum * 4 + 15) & ~15);
+        pp->offStage = o;   o += pp->stageBytes;
+        pp->offBar = o;     o += 8 * 8;
+        total = o;
+        pp->spanFloats = spanFloats; pp->pitchPairs = pitchPairs;
+        if (total <= budget) break;
+        if (stages == 2) { stages = 1; continue; }
+        stages = 2;
+        if (--F < 1) { free(pp); return af_fail(AF_ERR_UNSUPPORTED, "fused MFCC: slideLength %d too large for shared memory", slideLength); }
+    }
+    pp->framesPerTile = F; pp->stages = stages;
+    pp->tilesPerClip = (timeLength + F - 1) / F;
+    pp->totalTiles = (long long)pp->tilesPerClip * batch;
+
+    int sms = af_sm_count();
+    if (sms <= 0) sms = 148;
+    const long long grid = pp->totalTiles < (long long)sms ? pp->totalTiles : (long long)sms;
+    cudaStream_t st = (cudaStream_t)stream;
+    cudaError_t e = cudaSuccess;
+#define AF_MFCC2_LAUNCH(CT_)                                                                                      \
+    e = cudaFuncSetAttribute(k_mfcc_fused2<CT_>, cudaFuncAttributeMaxDynamicSharedMemorySize, total);            \
+    if (e == cudaSuccess) k_mfcc_fused2<CT_><<<(unsigned)grid, kThreads, total, st>>>(*pp)
+    switch (pl->ct) {
+    case 2: AF_MFCC2_LAUNCH(2); break;
+    case 3: AF_MFCC2_LAUNCH(3); break;
+    case 5: AF_MFCC2_LAUNCH(5); break;
+    default: AF_MFCC2_LAUNCH(8); break;
+    }
+#undef AF_MFCC2_LAUNCH
+    free(pp);
+    if (e != cudaSuccess) return af_cuda_check(e, "cudaFuncSetAttribute(k_mfcc_fused2)");
+    AF_LAUNCH_CHECK("k_mfcc_fused2");
+    return AF_OK;
+}
+
+extern "C" int af_launch_mfcc2(void *plan, const float *data, int dataLength, int batch, int timeLength, int slideLength,
+                               int rectifyType, float *out, int nPeer, float *const *peerOut, void *stream) {
+    return launch_fused2(plan, data, dataLength, batch, timeLength, slideLength, rectifyType, out, nPeer, peerOut, 0, stream);
+}
+
+// same kernel stopped after the filter bank: out[batch][T][num] = bank . |X|^2 (or |X|), i.e. bftObj_bft in real mode
+extern "C" int af_launch_mel2(void *plan, const float *data, int dataLength, int batch, int timeLength, int slideLength,
+                              float *out, void *stream) {
+    return launch_fused2(plan, data, dataLength, batch, timeLength, slideLength, 0, out, 0, NULL, 1, stream);
+}
+
+// Diagnostic / test hook (host only): the interval form the planner derives from a bank [num][1025].
+// Returns the number of table entries (>= 0) or -1 when the bank does not have the two-overlap structure.
+extern "C" int afb200_mfccBankPlan2(const float *bank, int num, int *owner /* 1025 */, unsigned *desc /* num+2 */,
+                                    float *table /* 4 * 1408 */, int *first /* helper warps + 1 */, int *helperWarps) {
+    if (!bank || num < 1 || num > kMaxNum) return -1;
+    Intervals *iv = static_cast<Intervals *>(malloc(sizeof(Intervals)));
+    float4 *tab = static_cast<float4 *>(malloc(sizeof(float4) * kMaxTab));
+    unsigned d[kMaxNum + 2];
+    int n = -1;
+    if (iv && tab && build_intervals2(bank, num, iv)) {
+        n = build_table(bank, num, iv, d, tab);
+        if (n >= 0) {
+            if (owner) memcpy(owner, iv->owner, sizeof(int) * kBins);
+            if (desc) memcpy(desc, d, sizeof(unsigned) * (size_t)(num + 2));
+            if (table) memcpy(table, tab, sizeof(float4) * (size_t)n);
+            int f[kEW + 1];
+            split_filters(num, d, f);
+            if (first) memcpy(first, f, sizeof(f));
+            if (helperWarps) *helperWarps = kEW;
+        }
+    }
+    free(iv); free(tab);
+    return n;
+}

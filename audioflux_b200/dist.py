@@ -109,9 +109,16 @@ class PeerScatter:
     single `bftObj_mfccBatchScatter` launch: the kernel's DCT epilogue stores each finished tile into slot `rank`
     of its own array AND of every peer's array, so the exchange overlaps the transform tile by tile and costs no
     SMs, no copy engines and no extra launches.  `fence()` orders all ranks' stores before anybody reads
-    (a 4-byte all-reduce on the current stream: a rank's contribution is stream-ordered after its kernel)."""
+    (a 4-byte all-reduce on the current stream: a rank's contribution is stream-ordered after its kernel).
 
-    def __init__(self, bft, batch_local: int, data_length: int, cc_num: int, rectify_type=0, group=None):
+    Write-after-read: the gathered array is double buffered (`slots=2`).  Step k writes slot k % 2 and `fence()` closes
+    the step; the kernels of step k+1 write the OTHER slot, so a rank may still be reading step k's result while its
+    peers are already storing step k+1.  Slot k % 2 is rewritten by step k+2, which a rank launches only after its
+    own fence of step k+1 has completed, i.e. after EVERY rank's stream has reached that fence: reads of step k that
+    were enqueued (on the fencing stream) before the next fence are therefore always finished in time.  A consumer
+    that reads on another stream, or later than that, must make the fencing stream wait for it first."""
+
+    def __init__(self, bft, batch_local: int, data_length: int, cc_num: int, rectify_type=0, group=None, slots: int = 2):
         import ctypes as C
         import torch
         import torch.distributed as dist
@@ -122,8 +129,10 @@ class PeerScatter:
             raise ValueError("PeerScatter supports up to 16 ranks")
         self.B, self.L, self.cc, self.rect = batch_local, data_length, cc_num, int(getattr(rectify_type, "value", rectify_type))
         self.T = bft.cal_time_length(data_length)
-        self.block = batch_local * self.T * cc_num                      # floats per rank slot
-        nbytes = self.world * self.block * 4
+        self.block = batch_local * self.T * cc_num                      # floats per rank block
+        self.slots, self._slot, self._open = max(1, int(slots)), 0, False
+        self.slot_bytes = self.world * self.block * 4                   # one gathered array
+        nbytes = self.slots * self.slot_bytes
         self._ptr = C.c_void_p()
         self._peers = []
         # every rank takes part in every collective below even if a local step failed, so that a failure
@@ -154,13 +163,12 @@ class PeerScatter:
         if any(errs):
             self.close()
             raise RuntimeError("PeerScatter setup failed: " + "; ".join(f"rank {r}: {e}" for r, e in enumerate(errs) if e))
-        off = self.rank * self.block * 4
-        self._dst = C.c_void_p(self._ptr.value + off)
-        self._peer_base = [p + off for p in self._peers]                 # slot `rank` inside every peer's array
-        self._peer_arr = (C.c_void_p * max(1, len(self._peers)))(*[C.c_void_p(p) for p in self._peer_base])
-        self.gathered = torch.as_tensor(_DevArray(self._ptr.value, (self.world, batch_local, self.T, cc_num)),
-                                        device=torch.device("cuda", torch.cuda.current_device()))
-        self._flag = torch.zeros(1, dtype=torch.int32, device=self.gathered.device)
+        self._rank_off = self.rank * self.block * 4                      # block `rank` inside every gathered array
+        dev = torch.device("cuda", torch.cuda.current_device())
+        self._gathered = [torch.as_tensor(_DevArray(self._ptr.value + k * self.slot_bytes, (self.world, batch_local, self.T, cc_num)),
+                                          device=dev) for k in range(self.slots)]
+        self.gathered = self._gathered[0]                                # the array of the step last launched
+        self._flag = torch.zeros(1, dtype=torch.int32, device=dev)
         dist.barrier(group=group)                                        # every rank has mapped every buffer
 
     def _check(self, rc, what):
@@ -179,24 +187,32 @@ class PeerScatter:
                 not clips.is_cuda or clips.dtype != torch.float32 or not clips.is_contiguous():
             raise ValueError("clips must be a contiguous float32 CUDA tensor (nb, L) with clip_offset + nb <= B_local")
         stream = C.c_void_p(torch.cuda.current_stream().cuda_stream)
-        off = clip_offset * self.T * self.cc * 4
-        dst = C.c_void_p(self._dst.value + off)
-        peers = (C.c_void_p * max(1, len(self._peers)))(*[C.c_void_p(p + off) for p in self._peer_base]) if off else self._peer_arr
+        self._open = True                                                # launches until the next fence() belong to this step / slot
+        off = self._slot * self.slot_bytes + self._rank_off + clip_offset * self.T * self.cc * 4
+        dst = C.c_void_p(self._ptr.value + off)
+        peers = (C.c_void_p * max(1, len(self._peers)))(*[C.c_void_p(p + off) for p in self._peers])
+        self.gathered = self._gathered[self._slot]
         self._check(self.lib.bftObj_mfccBatchScatter(self.bft._obj, C.c_void_p(clips.data_ptr()), self.L, nb, self.cc,
                                                      self.rect, dst, len(self._peers), peers, stream),
                     "bftObj_mfccBatchScatter")
         return self.gathered
 
     def fence(self):
+        """Closes the step: after it (stream order) every rank's stores of this step are complete and visible; the next
+        `__call__` starts the next step in the other slot."""
         import torch.distributed as dist
         if self.world > 1:
             dist.all_reduce(self._flag, group=self.group)
+        if self._open:
+            self._slot = (self._slot + 1) % self.slots
+            self._open = False
 
     def close(self):
         for p in self._peers:
             self.lib.afb200_ipcCloseHandle(p)
         self._peers = []
         self.gathered = None
+        self._gathered = []
         if self._ptr is not None and self._ptr.value:
             self.lib.afb200_peerFree(self._ptr)
         self._ptr = None

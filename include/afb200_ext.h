@@ -112,6 +112,12 @@ int afb200_decimatorTaps(float *left32, float *right31);
  * two-overlap structure and the interval form applies; fills the per-bin interval owner / rising weight etc. */
 int afb200_mfccIntervalPlan(const float *bank, int num, const float *gain, int *owner, float *r, int *ivStart,
                             int *ivLen, float *tailW, int *groupLen, int *startShifted);
+/* planner of the second-generation fused kernel (kernels/mfcc_fused2.cu, host only): every bin of `bank` (num x 1025)
+ * is given to one interval i in [0, num] on which filter i "rises" and filter i-1 "falls" (the bank's own weights);
+ * returns the number of float4 table entries (rise[2q], rise[2q+1], fall[2q], fall[2q+1]) or -1 when some bin is
+ * covered by more than two, or by non-consecutive, filters.  desc[i] = (first bin pair << 16) | table offset. */
+int afb200_mfccBankPlan2(const float *bank, int num, int *owner /* 1025 */, unsigned *desc /* num + 2 */,
+                         float *table /* 4 x 1408 */, int *first /* helper warps + 1 */, int *helperWarps);
 /* chroma_cqtFilterBank (src/filterbank/chroma_filterBank.c:176-262): bank num x cqtLength */
 int afb200_chromaCqtFilterBank(int num, int cqtLength, int binPerOctave, float minFre, float *bank);
 

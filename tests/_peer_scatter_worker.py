@@ -31,8 +31,9 @@ def main():
     bft = af.BFT(128, 11, 48000, slide_length=512, scale_type=S.MEL, data_type=D.POWER)
     x = shard(rank, B, L, dev)
     sc = PeerScatter(bft, B, L, CC)
-    for rep in range(3):                                   # repeated steps reuse the mapped buffers
-        sc.gathered.zero_()
+    for rep in range(3):                                   # repeated steps reuse the mapped buffers (alternating slots)
+        for arr in sc._gathered:
+            arr.zero_()
         torch.cuda.synchronize()
         dist.barrier()
         out = sc(x)
@@ -41,8 +42,28 @@ def main():
         for r in range(world):
             want = bft.mfcc_batch(shard(r, B, L, dev), CC)
             assert torch.equal(out[r], want), f"rank {rank}: slot {r} differs (rep {rep})"
+    # write-after-read: consecutive steps with NO host synchronisation in between.  Step k's gathered array
+    # must still hold step k's blocks after step k+1 has been launched and fenced (double-buffered slots), and the
+    # third step reuses the first slot.
+    x2 = shard(rank + 50, B, L, dev)
+    a = sc(x)
+    sc.fence()
+    a_copy_later = torch.empty_like(a)
+    b = sc(x2)                                             # peers may already be storing step k+1 ...
+    a_copy_later.copy_(a)                                  # ... while this rank still reads step k (same stream, before the next fence)
+    sc.fence()
+    c = sc(x)
+    sc.fence()
+    torch.cuda.synchronize()
+    assert a.data_ptr() != b.data_ptr() and c.data_ptr() == a.data_ptr()
+    for r in range(world):
+        assert torch.equal(a_copy_later[r], bft.mfcc_batch(shard(r, B, L, dev), CC)), f"rank {rank}: step k block {r} was overwritten"
+        assert torch.equal(b[r], bft.mfcc_batch(shard(r + 50, B, L, dev), CC)), f"rank {rank}: step k+1 block {r} differs"
+        assert torch.equal(c[r], bft.mfcc_batch(shard(r, B, L, dev), CC)), f"rank {rank}: step k+2 block {r} differs"
+    dist.barrier()
     # chunked launches (a shard streamed in from the host): same result
-    sc.gathered.zero_()
+    for arr in sc._gathered:
+        arr.zero_()
     torch.cuda.synchronize()
     dist.barrier()
     for lo in range(0, B, 7):

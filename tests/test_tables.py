@@ -228,3 +228,76 @@ def test_mfcc_interval_plan_rejects_other_banks(product_lib):
     bad[40, np.nonzero(tri[40])[0][0]] *= 1.01                      # one weight off by 1 %: structure check must fail
     assert _interval_plan(product_lib, bad)[0] == 0
     assert _interval_plan(product_lib, tri, np.full(128, 2.0, np.float32))[0] == 0    # wrong gains
+
+
+# ---- planner of the second-generation fused kernel (kernels/mfcc_fused2.cu): per-tile interval form with the bank's own weights ----
+def _bank_plan2(lib, bank):
+    num = bank.shape[0]
+    bank = np.ascontiguousarray(bank, np.float32)
+    owner = np.zeros(1025, np.int32)
+    desc = np.zeros(num + 2, np.uint32)
+    table = np.zeros((1408, 4), np.float32)
+    first = np.zeros(9, np.int32)
+    hw = np.zeros(1, np.int32)
+    n = lib.afb200_mfccBankPlan2(bank.ctypes.data, num, owner.ctypes.data, desc.ctypes.data, table.ctypes.data,
+                                 first.ctypes.data, hw.ctypes.data)
+    return n, owner, desc, table, first[:hw[0] + 1]
+
+
+def _plan2_mel(num, P, plan):
+    """the helper warps' loop (mfcc_fused2.cu, bank phase) in float64: filters [first[e], first[e+1]) per warp"""
+    n, owner, desc, table, first = plan
+    Pp = np.concatenate([P, [0.0]])
+    mel = np.full(num, np.nan)
+    for e in range(len(first) - 1):
+        i0, i1 = int(first[e]), int(first[e + 1])
+        if i1 <= i0:
+            continue
+        prev = 0.0
+        for i in range(i0, i1 + 1):
+            q, j0, j1 = int(desc[i] >> 16), int(desc[i] & 0xffff), int(desc[i + 1] & 0xffff)
+            R = Fl = 0.0
+            for j in range(j0, j1):
+                w = table[j].astype(np.float64)
+                k = 2 * (q + j - j0)
+                R += Pp[k] * w[0] + Pp[k + 1] * w[1]
+                Fl += Pp[k] * w[2] + Pp[k + 1] * w[3]
+            if i > i0:
+                mel[i - 1] = prev + Fl
+            prev = R
+    return mel
+
+
+@pytest.mark.parametrize("scale,style,norm,num,sr", [(2, 0, 0, 128, 48000), (2, 0, 1, 128, 48000), (2, 0, 2, 128, 48000),
+                                                      (3, 1, 1, 64, 48000), (4, 0, 0, 128, 48000), (3, 0, 0, 128, 32000),
+                                                      (2, 1, 0, 128, 48000), (2, 0, 0, 40, 16000), (2, 5, 0, 128, 48000),
+                                                      (3, 0, 1, 100, 44100), (4, 1, 2, 77, 22050), (2, 0, 0, 1, 48000),
+                                                      (2, 0, 0, 3, 8000)])
+def test_mfcc_bank_plan2_reproduces_the_bank(product_lib, scale, style, norm, num, sr):
+    lo, hi, _, _ = O.bft_revise_range(num, 2048, sr, None, None, scale, 12)
+    bank, _, _ = O.auditory_filterbank(num, 2048, sr, scale, style, norm, float(lo), float(hi), 12)
+    plan = _bank_plan2(product_lib, bank)
+    n, owner, desc, table, first = plan
+    assert 0 <= n <= 1408
+    assert (np.diff(owner[owner >= 0]) >= 0).all()                 # intervals are runs of consecutive bins
+    assert first[0] == 0 and first[-1] == num and (np.diff(first) >= 0).all()
+    B = bank.astype(np.float64)
+    rng = np.random.default_rng(0)
+    for _ in range(2):
+        P = rng.random(1025) ** 8 * 100
+        want = B @ P
+        got = _plan2_mel(num, P, plan)
+        assert np.abs(got - want).max() <= 1e-12 * max(np.abs(want).max(), 1e-300)
+    eye = np.eye(1025)
+    got = np.stack([_plan2_mel(num, eye[k], plan) for k in range(0, 1025, 7)], axis=1)      # = the bank's own float weights
+    assert np.array_equal(got, B[:, 0:1025:7])
+
+
+def test_mfcc_bank_plan2_rejects_other_banks(product_lib):
+    rnd = np.random.default_rng(1).random((16, 1025)).astype(np.float32)               # dense
+    assert _bank_plan2(product_lib, rnd)[0] == -1
+    tri, _, _ = O.auditory_filterbank(128, 2048, 48000, 2, 0, 0, 0.0, 24000.0, 12)
+    assert _bank_plan2(product_lib, tri)[0] > 0
+    bad = tri.copy()
+    bad[10, 900] = 0.5                                              # a third filter on a high bin
+    assert _bank_plan2(product_lib, bad)[0] == -1
