@@ -101,6 +101,8 @@ static int cwt_compute(CWTObj c, const float *dData, int batch, int det, float *
     size_t budget = af_dev_free_bytes() / 3 + c->dWork.bytes;
     if (budget > ((size_t)24 << 30)) budget = (size_t)24 << 30;
     int chunk = (int)(budget / perClip);
+    const char *force = getenv("AFB200_CWT_CHUNK");       /* test hook: clips per workspace chunk */
+    if (force && atoi(force) > 0 && atoi(force) < chunk) chunk = atoi(force);
     if (chunk < 1) chunk = 1;
     if (chunk > batch) chunk = batch;
     while ((long long)chunk * c->num > 0x7fffffffLL / 2) chunk /= 2;
