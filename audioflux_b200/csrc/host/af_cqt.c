@@ -16,6 +16,8 @@ struct OpaqueCQT {
     /* device (lazy) */
     int devReady;
     void *stream;
+    float *dBfrag;                               /* tensor-core octave kernel: pre-split kernel fragments */
+    unsigned char *dBimg;                        /* tcgen05 octave kernel: pre-swizzled shared-memory images of the kernels */
     float *dKappa2, *dLeft, *dRight, *dScale;    /* dScale: octaveNum x bpo, rebuilt when isScale flips */
     int scaleDirty;
     AfDevBuf dIn, dSigA, dSigB, dOutRe, dOutIm;
@@ -91,6 +93,24 @@ static int cqt_device(CQTObj c) {
     if (!c->devReady) {
         if ((rc = af_stream_create(&c->stream))) return rc;
         if ((rc = af_dev_upload((void **)&c->dKappa2, c->kappa2, sizeof(float) * 2 * (size_t)c->binPerOctave * c->fftLength))) return rc;
+        if (c->binPerOctave == 12 && c->fftLength % 64 == 0) {
+            const size_t nf = (size_t)(c->fftLength / 8) * 96 * 4;
+            float *bf = (float *)malloc(sizeof(float) * nf);
+            if (!bf) return AF_ERR_NOMEM;
+            af_cqt_tc_fragments(c->kappa2, c->fftLength, bf);
+            rc = af_dev_upload((void **)&c->dBfrag, bf, sizeof(float) * nf);
+            free(bf);
+            if (rc) return rc;
+        }
+        if (c->binPerOctave == 12 && c->fftLength % 128 == 0 && c->fftLength >= 256) {
+            const size_t nb = (size_t)(c->fftLength / 128) * 32768;
+            unsigned char *img = (unsigned char *)malloc(nb);
+            if (!img) return AF_ERR_NOMEM;
+            af_cqt_umma_bimage(c->kappa2, c->fftLength, img);
+            rc = af_dev_upload((void **)&c->dBimg, img, nb);
+            free(img);
+            if (rc) return rc;
+        }
         if ((rc = af_dev_upload((void **)&c->dLeft, c->left32, sizeof(float) * 32))) return rc;
         if ((rc = af_dev_upload((void **)&c->dRight, c->right31, sizeof(float) * 32))) return rc;
         c->devReady = 1;
@@ -139,6 +159,18 @@ static int cqt_compute(CQTObj c, const float *dData, int dataLength, int batch, 
         /* padded STFT semantics: drop the tail that does not fill a hop when more than one frame exists */
         const int frames = len / hop + 1;
         const int valid = frames > 1 ? len - len % hop : len;
+        const char *kq = getenv("AFB200_CQT_KERNEL");
+        /* tcgen05 (default where the hop allows it) > mma.sync 3xTF32 > FP32 loop; AFB200_CQT_KERNEL = mma | fp32 forces the older ones */
+        if (c->dBimg && af_cqt_umma_supported(c->fftLength, hop, c->binPerOctave) && !kq) {
+            if ((rc = af_launch_cqt_octave_umma(sig, stride, batch, valid, c->fftLength, hop, T, c->dBimg,
+                                                c->dScale + (size_t)k * c->binPerOctave, c->num, o * c->binPerOctave, dRe, dIm, st))) return rc;
+            continue;
+        }
+        if (c->dBfrag && af_cqt_tc_supported(c->fftLength, hop, c->binPerOctave) && !(kq && !strcmp(kq, "fp32"))) {
+            if ((rc = af_launch_cqt_octave_tc(sig, stride, batch, valid, c->fftLength, hop, T, c->dBfrag,
+                                              c->dScale + (size_t)k * c->binPerOctave, c->num, o * c->binPerOctave, dRe, dIm, st))) return rc;
+            continue;
+        }
         if ((rc = af_launch_cqt_octave(sig, len, stride, batch, valid, c->fftLength, hop, T, c->binPerOctave,
                                        c->dKappa2, c->dScale + (size_t)k * c->binPerOctave, c->num,
                                        o * c->binPerOctave, dRe, dIm, st))) return rc;
@@ -269,6 +301,7 @@ void cqtObj_free(CQTObj c) {
     af_devbuf_free(&c->dPostA); af_devbuf_free(&c->dPostB); af_devbuf_free(&c->dPostOut);
     af_pipe_free(&c->pipe);
     af_dev_free(c->dChromaBank); af_dev_free(c->dDctT);
+    af_dev_free(c->dBfrag); af_dev_free(c->dBimg);
     af_dev_free(c->dKappa2); af_dev_free(c->dLeft); af_dev_free(c->dRight); af_dev_free(c->dScale);
     af_stream_destroy(c->stream);
     af_cqt_bank_free(&c->bank);

@@ -12,6 +12,7 @@
 // The signal tile is staged polyphase-major (xs[r][u] = x[hop*u + r]) so that the 32 lanes of a warp
 // (32 consecutive frames) read consecutive words for every (r, a) step whatever the hop is.
 #include <math.h>
+#include <string.h>
 #include "common.cuh"
 
 namespace {
@@ -199,6 +200,127 @@ __global__ void k_cqt_octave(OctParams p) {
     }
 }
 
+
+// ---- tensor-core octave kernel ---------------------------------------------------------------------------------
+// One octave is a GEMM  out[T x 24] = A[T x N] . B[N x 24]  with a Hankel A operand, A[t][n] = xpad[t*hop + n]
+// (never materialised: the mma A fragments are read straight from the staged signal tile) and B = the 12 time-domain
+// kernels kappa_b as interleaved (re, im) columns.  mma.sync.m16n8k8 TF32 with the 3xTF32 split (x = hi + lo, hi by
+// truncation, lo = x - hi exact; hi*hi + lo*hi + hi*lo) keeps fp32-level accuracy (measured against the oracle in
+// tests/test_gpu_parity.py); the kappa fragments arrive pre-split from a host-built table, chunk by chunk.
+//   * signal tile: polyphase-major xs[r][u] = x[hop*u + r] with row pitch == 8 (mod 32) for hop >= 8 -> the fragment
+//     element (frame g, tap t4) sits in bank 8*t4 + g: conflict-free; plain linear for hop <= 4 (4g + t4, or equal
+//     addresses for hop 2: broadcast);
+//   * warp w owns kTcMT m-tiles (16 frames each); per k-step it reads 3 LDS.128 of B fragments (shared by its m-tiles)
+//     and, per m-tile, 4 LDS.32 + 8 ALU (split) + 9 HMMA: ~140 MAC per issued instruction (FP32 loop: ~26).
+constexpr int kTcMT = 2;                          // m-tiles (16 frames) per warp
+constexpr int kTcKC = 16;                         // k-steps (8 taps) of kernel fragments resident in shared memory at a time
+
+struct OctTcParams {
+    const float *sig; long long sigStride; int validLength;
+    int N, hop, hs, T;
+    const float4 *bfrag;          // [N/8 k-steps][3 n-tiles][32 lanes] (hi0, hi1, lo0, lo1)
+    const float *scale;           // [12]
+    float *outRe, *outIm; long long outStride; int num, colOff;
+    int TT, rowLen, warps;
+};
+
+__global__ void k_cqt_octave_tc(OctTcParams p) {
+    extern __shared__ __align__(16) unsigned char smemRaw[];
+    float4 *sB = reinterpret_cast<float4 *>(smemRaw);                        // [kTcKC][3][32]
+    float *xs = reinterpret_cast<float *>(smemRaw + sizeof(float4) * kTcKC * 96);
+    const int clip = blockIdx.y;
+    const int t0 = blockIdx.x * p.TT;
+    const float *sig = p.sig + (long long)clip * p.sigStride;
+    const int h = p.hop, N = p.N, hs = p.hs;
+    const bool poly = h >= 8;
+
+    // stage the tile's span of the zero-padded signal
+    const int span = (p.TT - 1) * h + N;
+    const long long m0 = (long long)t0 * h - N / 2;
+    for (int i0 = threadIdx.x; i0 < span; i0 += 4 * blockDim.x) {
+        float v[4];
+#pragma unroll
+        for (int u = 0; u < 4; u++) {
+            const int i = i0 + u * blockDim.x;
+            const long long m = m0 + i;
+            v[u] = (i < span && m >= 0 && m < p.validLength) ? sig[m] : 0.0f;
+        }
+#pragma unroll
+        for (int u = 0; u < 4; u++) {
+            const int i = i0 + u * blockDim.x;
+            if (i >= span) continue;
+            xs[poly ? (i & (h - 1)) * p.rowLen + (i >> hs) : i] = v[u];
+        }
+    }
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int g = lane >> 2, t4 = lane & 3;
+    float acc[kTcMT][3][4];
+#pragma unroll
+    for (int m = 0; m < kTcMT; m++)
+#pragma unroll
+        for (int n = 0; n < 3; n++) acc[m][n][0] = acc[m][n][1] = acc[m][n][2] = acc[m][n][3] = 0.0f;
+    const int tb = warp * (16 * kTcMT);                                     // first frame (within the tile) of this warp
+    const int rowStep = poly ? 8 : 8 * h;                                   // address step from frame g to frame g + 8
+    const int colStep = poly ? 4 * p.rowLen : 4;                            // address step from tap t4 to tap t4 + 4
+
+#define AF_MMA_TF32(ACC, A0, A1, A2, A3, B0, B1)                                                              \
+    asm("mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};" \
+        : "+f"(ACC[0]), "+f"(ACC[1]), "+f"(ACC[2]), "+f"(ACC[3])                                              \
+        : "r"(A0), "r"(A1), "r"(A2), "r"(A3), "r"(B0), "r"(B1))
+
+    const int kSteps = N >> 3;
+    for (int kc = 0; kc < kSteps; kc += kTcKC) {
+        __syncthreads();                                                    // signal staged / previous chunk consumed
+        const int nk = min(kTcKC, kSteps - kc);
+        for (int i = threadIdx.x; i < nk * 96; i += blockDim.x) sB[i] = p.bfrag[(size_t)kc * 96 + i];
+        __syncthreads();
+#pragma unroll 2
+        for (int ks = 0; ks < nk; ks++) {
+            const int n0 = (kc + ks) << 3;
+            const float4 b0 = sB[(ks * 3 + 0) * 32 + lane], b1 = sB[(ks * 3 + 1) * 32 + lane], b2 = sB[(ks * 3 + 2) * 32 + lane];
+            const int base = poly ? ((n0 & (h - 1)) + t4) * p.rowLen + (n0 >> hs) + tb + g : (tb + g) * h + n0 + t4;
+#pragma unroll
+            for (int m = 0; m < kTcMT; m++) {
+                const float *a = xs + base + m * (poly ? 16 : 16 * h);
+                const float af[4] = {a[0], a[rowStep], a[colStep], a[colStep + rowStep]};
+                uint32_t ah[4], al[4];
+#pragma unroll
+                for (int i = 0; i < 4; i++) {
+                    ah[i] = __float_as_uint(af[i]) & 0xffffe000u;
+                    al[i] = __float_as_uint(af[i] - __uint_as_float(ah[i]));
+                }
+                AF_MMA_TF32(acc[m][0], al[0], al[1], al[2], al[3], __float_as_uint(b0.x), __float_as_uint(b0.y));
+                AF_MMA_TF32(acc[m][1], al[0], al[1], al[2], al[3], __float_as_uint(b1.x), __float_as_uint(b1.y));
+                AF_MMA_TF32(acc[m][2], al[0], al[1], al[2], al[3], __float_as_uint(b2.x), __float_as_uint(b2.y));
+                AF_MMA_TF32(acc[m][0], ah[0], ah[1], ah[2], ah[3], __float_as_uint(b0.z), __float_as_uint(b0.w));
+                AF_MMA_TF32(acc[m][1], ah[0], ah[1], ah[2], ah[3], __float_as_uint(b1.z), __float_as_uint(b1.w));
+                AF_MMA_TF32(acc[m][2], ah[0], ah[1], ah[2], ah[3], __float_as_uint(b2.z), __float_as_uint(b2.w));
+                AF_MMA_TF32(acc[m][0], ah[0], ah[1], ah[2], ah[3], __float_as_uint(b0.x), __float_as_uint(b0.y));
+                AF_MMA_TF32(acc[m][1], ah[0], ah[1], ah[2], ah[3], __float_as_uint(b1.x), __float_as_uint(b1.y));
+                AF_MMA_TF32(acc[m][2], ah[0], ah[1], ah[2], ah[3], __float_as_uint(b2.x), __float_as_uint(b2.y));
+            }
+        }
+    }
+#undef AF_MMA_TF32
+    // C fragment: rows g / g + 8 = frames, columns 2 t4, 2 t4 + 1 = (re, im) of bin 4 nt + t4
+#pragma unroll
+    for (int m = 0; m < kTcMT; m++)
+#pragma unroll
+        for (int n = 0; n < 3; n++) {
+            const int j = 4 * n + t4;
+            const float s = p.scale[j];
+#pragma unroll
+            for (int hf = 0; hf < 2; hf++) {
+                const int t = t0 + tb + 16 * m + g + 8 * hf;
+                if (t >= p.T) continue;
+                const long long o = (long long)clip * p.outStride + (long long)t * p.num + p.colOff + j;
+                p.outRe[o] = acc[m][n][2 * hf] * s;
+                p.outIm[o] = acc[m][n][2 * hf + 1] * s;
+            }
+        }
+}
+
 }  // namespace
 
 extern "C" int af_launch_decimate2(const float *in, int inLength, int inStride, int batch, const float *left32,
@@ -265,5 +387,72 @@ extern "C" int af_launch_cqt_octave(const float *sig, int sigLength, int sigStri
     dim3 grid((unsigned)((timeLength + TT - 1) / TT), (unsigned)batch);
     k_cqt_octave<<<grid, (TT / kFT) * kJG * p.segs, smem, (cudaStream_t)stream>>>(p);
     AF_LAUNCH_CHECK("k_cqt_octave");
+    return AF_OK;
+}
+
+// Host side of the tensor-core octave kernel: the B-fragment table [N/8][3][32] float4 of the 12 kernels
+// (column 2 b = Re kappa_b, 2 b + 1 = Im kappa_b), pre-split into TF32 hi (truncated) and lo (= x - hi) parts.
+extern "C" void af_cqt_tc_fragments(const float *kappa2 /* [12][N] (re, im) */, int N, float *out /* N/8 * 96 * 4 */) {
+    for (int ks = 0; ks < N / 8; ks++)
+        for (int nt = 0; nt < 3; nt++)
+            for (int lane = 0; lane < 32; lane++) {
+                const int g = lane >> 2, t4 = lane & 3;
+                const int col = nt * 8 + g, b = col >> 1, part = col & 1;
+                float v[2], hi[2], lo[2];
+                for (int i = 0; i < 2; i++) {
+                    v[i] = kappa2[((size_t)b * N + ks * 8 + t4 + 4 * i) * 2 + part];
+                    uint32_t u;
+                    memcpy(&u, &v[i], 4);
+                    u &= 0xffffe000u;
+                    memcpy(&hi[i], &u, 4);
+                    lo[i] = v[i] - hi[i];
+                }
+                float *o = out + (((size_t)ks * 3 + nt) * 32 + lane) * 4;
+                o[0] = hi[0]; o[1] = hi[1]; o[2] = lo[0]; o[3] = lo[1];
+            }
+}
+
+// tile geometry of the tensor-core kernel: 8 warps x 2 m-tiles = 256 frames when the signal tile fits ~100 KB (two CTAs
+// per SM), else fewer warps; returns the dynamic shared-memory bytes, 0 when even one warp does not fit
+static size_t cqt_tc_geometry(int fftLength, int hop, int *warpsOut, int *ttOut, int *rowLenOut) {
+    const size_t bBytes = sizeof(float4) * kTcKC * 96;
+    for (int warps = 8; warps >= 1; warps /= 2) {
+        const int TT = warps * 16 * kTcMT;
+        int rowLen = TT + fftLength / hop + 1;
+        rowLen = ((rowLen + 31) / 32) * 32 + 8;                      // == 8 (mod 32): conflict-free fragment reads
+        const size_t sigFloats = hop >= 8 ? (size_t)hop * rowLen : (size_t)(TT - 1) * hop + fftLength;
+        const size_t smem = bBytes + sizeof(float) * sigFloats;
+        if (smem <= (size_t)100 * 1024 || (warps == 1 && smem <= (size_t)227 * 1024)) {
+            *warpsOut = warps; *ttOut = TT; *rowLenOut = rowLen;
+            return smem;
+        }
+    }
+    return 0;
+}
+
+extern "C" int af_cqt_tc_supported(int fftLength, int hop, int bpo) {
+    int w, tt, rl;
+    return bpo == 12 && fftLength >= 64 && fftLength % 64 == 0 && hop >= 2 && (hop & (hop - 1)) == 0 &&
+           cqt_tc_geometry(fftLength, hop, &w, &tt, &rl) > 0;
+}
+
+extern "C" int af_launch_cqt_octave_tc(const float *sig, int sigStride, int batch, int validLength, int fftLength, int hop,
+                                       int timeLength, const float *bfrag, const float *scale, int num, int colOff,
+                                       float *outRe, float *outIm, void *stream) {
+    if (batch <= 0 || timeLength <= 0) return AF_OK;
+    if (!af_cqt_tc_supported(fftLength, hop, 12)) return af_fail(AF_ERR_UNSUPPORTED, "cqt octave (tensor core): fftLength %d hop %d", fftLength, hop);
+    if (batch > 65535) return af_fail(AF_ERR_ARG, "cqt octave: batch %d > 65535 per launch", batch);
+    OctTcParams p;
+    p.sig = sig; p.sigStride = sigStride; p.validLength = validLength;
+    p.N = fftLength; p.hop = hop; p.T = timeLength;
+    p.hs = 0; while ((1 << p.hs) < hop) p.hs++;
+    p.bfrag = reinterpret_cast<const float4 *>(bfrag); p.scale = scale;
+    p.outRe = outRe; p.outIm = outIm; p.outStride = (long long)timeLength * num; p.num = num; p.colOff = colOff;
+    const size_t smem = cqt_tc_geometry(fftLength, hop, &p.warps, &p.TT, &p.rowLen);
+    cudaError_t e = cudaFuncSetAttribute(k_cqt_octave_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return af_cuda_check(e, "cudaFuncSetAttribute(k_cqt_octave_tc)");
+    dim3 grid((unsigned)((timeLength + p.TT - 1) / p.TT), (unsigned)batch);
+    k_cqt_octave_tc<<<grid, p.warps * 32, smem, (cudaStream_t)stream>>>(p);
+    AF_LAUNCH_CHECK("k_cqt_octave_tc");
     return AF_OK;
 }

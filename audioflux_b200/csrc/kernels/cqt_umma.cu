@@ -1,0 +1,280 @@
+// cqt_umma.cu -- one CQT octave on the 5th-generation tensor cores (tcgen05.mma, accumulators in TMEM).
+//
+// Same restatement as cqt.cu (reference: src/cqt_algorithm.c:951-1048, the per-octave STFT + sparse spectral dot,
+// rewritten as the strided correlation out[t][b] = sum_n xpad[t*hop + n] kappa_b[n]):
+//     D[128 frames x 32] = A[128 x 512] . B[512 x 32],   A[t][n] = xpad[(t0 + t) hop + n]  (a Hankel matrix),
+//     B = the 12 time-domain kernels as interleaved (re, im) columns (24 used).
+// The Hankel operand is NEVER materialised: the staged signal itself is the UMMA A operand.  In the canonical K-major
+// shared-memory layouts the 8 rows of a core-matrix group sit 16 / 32 / 64 / 128 bytes apart (no swizzle / 32B / 64B /
+// 128B swizzle); a signal stored linearly has "rows" hop*4 bytes apart, so
+//     hop  4 -> SWIZZLE_NONE  (row pitch 16 B; LBO = 16 B, SBO = 128 B),
+//     hop  8 -> SWIZZLE_32B   (row pitch 32 B, SBO = 256 B),   hop 16 -> SWIZZLE_64B (64 B, SBO = 512 B),
+//     hop 32 -> SWIZZLE_128B  (128 B, SBO = 1024 B),
+//     hop 64 / 128 -> 2 / 4 phase planes of 128-byte rows (plane phi holds rows P u + phi), SWIZZLE_128B each,
+// and the next K atom of the Hankel matrix is simply the SAME buffer one row further down (start address + row pitch,
+// descriptor base_offset = row index mod 8).  The swizzle is an XOR on absolute shared-memory address bits, so the
+// signal is stored through the same XOR and every shifted view reads it back consistently.
+// fp32 accuracy with TF32 tensor cores: x = hi + lo (hi = top 19 bits, lo = x - hi exact); hi*hi + lo*hi + hi*lo, three
+// MMAs per 8 taps, the kernels pre-split on the host.  One elected thread issues 192 MMAs per 128-frame tile;
+// the other threads stage the next signal tile / run the epilogue of the co-resident CTA.
+#include <math.h>
+#include <string.h>
+#include "common.cuh"
+
+namespace {
+
+constexpr int kUmmaM = 128;          // frames per tile (TMEM lanes)
+constexpr int kUmmaN = 32;           // accumulator columns (24 used: 12 bins x (re, im))
+constexpr int kUmmaChunkK = 128;     // taps per kernel chunk in shared memory
+constexpr int kUmmaBBytes = kUmmaN * kUmmaChunkK * 4;      // one part (hi or lo) of one chunk: 16 KB
+
+struct UmmaParams {
+    const float *sig; long long sigStride; int validLength;
+    int N, hop, T;
+    const unsigned char *bimg;     // [N / 128 chunks][2 parts (hi, lo)][16 KB] pre-swizzled shared-memory images of B
+    const float *scale;            // [12]
+    float *outRe, *outIm; long long outStride; int num, colOff;
+    int mode;                      // 0: hop 4 (no swizzle), 1: hop 8 (32B), 2: hop 16 (64B), 3: hop 32 * planes (128B)
+    int planes, rowsPerPlane, sigBytes;   // mode 3: phase planes and rows (128 B each) per plane; bytes of one signal copy
+};
+
+__device__ __forceinline__ uint64_t umma_desc(uint32_t smemAddr, uint32_t lboBytes, uint32_t sboBytes, uint32_t layout, uint32_t baseOff) {
+    uint64_t d = 0;
+    d |= (uint64_t)((smemAddr >> 4) & 0x3fffu);
+    d |= (uint64_t)((lboBytes >> 4) & 0x3fffu) << 16;
+    d |= (uint64_t)((sboBytes >> 4) & 0x3fffu) << 32;
+    d |= (uint64_t)1 << 46;                      // descriptor version (sm_100)
+    d |= (uint64_t)(baseOff & 7u) << 49;
+    d |= (uint64_t)(layout & 7u) << 61;
+    return d;
+}
+
+__device__ __forceinline__ void umma_tf32(uint32_t tmemD, uint64_t descA, uint64_t descB, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(tmemD), "l"(descA), "l"(descB), "r"(idesc), "r"(accumulate) : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint64_t *bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(af_smem_u32(bar)) : "memory");
+}
+
+// byte offset of sample s (floats from the tile start) inside one signal copy
+__device__ __forceinline__ uint32_t sig_offset(const UmmaParams &p, int s) {
+    if (p.mode == 0) return (uint32_t)s * 4u;
+    uint32_t a;
+    if (p.mode == 3) {
+        const int row = s >> 5, kk = s & 31;                       // 128-byte rows of 32 samples
+        const int phi = row % p.planes, u = row / p.planes;
+        a = (uint32_t)(phi * p.rowsPerPlane + u) * 128u + (uint32_t)kk * 4u;
+        return a ^ (((a >> 7) & 7u) << 4);                          // 128B swizzle: bits [4,7) ^= bits [7,10)
+    }
+    a = (uint32_t)s * 4u;
+    if (p.mode == 2) return a ^ (((a >> 7) & 3u) << 4);             // 64B swizzle: bits [4,6) ^= bits [7,9)
+    return a ^ (((a >> 7) & 1u) << 4);                              // 32B swizzle: bit 4 ^= bit 7
+}
+
+__global__ void __launch_bounds__(128) k_cqt_octave_umma(UmmaParams p) {
+    extern __shared__ __align__(1024) unsigned char smem[];
+    // [B buffers: 2 x (hi 16 KB, lo 16 KB)] [signal hi copy] [signal lo copy] [barriers] [tmem address]
+    unsigned char *sB = smem;
+    unsigned char *sHi = smem + 2 * 2 * kUmmaBBytes;
+    unsigned char *sLo = sHi + p.sigBytes;
+    uint64_t *bars = reinterpret_cast<uint64_t *>(sLo + p.sigBytes);
+    uint64_t *bFull = bars, *bEmpty = bars + 2, *accFull = bars + 4;
+    uint32_t *tmemSlot = reinterpret_cast<uint32_t *>(bars + 6);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int clip = blockIdx.y, t0 = blockIdx.x * kUmmaM;
+    const int h = p.hop, N = p.N;
+    const int chunks = N / kUmmaChunkK;
+
+    if (threadIdx.x == 0) {
+        for (int i = 0; i < 2; i++) { af_mbar_init(&bFull[i], 1); af_mbar_init(&bEmpty[i], 1); }
+        af_mbar_init(accFull, 1);
+        af_fence_barrier_init();
+    }
+    if (warp == 0) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(af_smem_u32(tmemSlot)), "n"(32) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {                                         // first two kernel chunks are on their way while the signal is staged
+        for (int c = 0; c < 2 && c < chunks; c++) {
+            af_mbar_arrive_expect_tx(&bFull[c], 2 * kUmmaBBytes);
+            af_tma_load_1d(sB + c * 2 * kUmmaBBytes, p.bimg + (size_t)c * 2 * kUmmaBBytes, 2 * kUmmaBBytes, &bFull[c]);
+        }
+    }
+
+    // ---- stage the tile's span of the zero-padded signal: hi / lo copies through the layout's swizzle ----
+    {
+        const float *sig = p.sig + (long long)clip * p.sigStride;
+        const int span = (kUmmaM - 1) * h + N;
+        const long long m0 = (long long)t0 * h - N / 2;
+        const int total = p.sigBytes / 4;                          // whole copy (tail beyond the span = zeros)
+        for (int i0 = threadIdx.x; i0 < total; i0 += 4 * 128) {
+            float v[4];
+#pragma unroll
+            for (int u = 0; u < 4; u++) {
+                const int i = i0 + u * 128;
+                const long long m = m0 + i;
+                v[u] = (i < span && m >= 0 && m < p.validLength) ? sig[m] : 0.0f;
+            }
+#pragma unroll
+            for (int u = 0; u < 4; u++) {
+                const int i = i0 + u * 128;
+                if (i >= total) continue;
+                const uint32_t off = sig_offset(p, i);
+                const float hi = __uint_as_float(__float_as_uint(v[u]) & 0xffffe000u);
+                *reinterpret_cast<float *>(sHi + off) = hi;
+                *reinterpret_cast<float *>(sLo + off) = v[u] - hi;
+            }
+        }
+    }
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");     // generic-proxy writes -> visible to the tensor core (async proxy)
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const uint32_t tmemD = *tmemSlot;
+
+    if (threadIdx.x == 0) {
+        // ---- the MMA issuer: D += A_hi B_hi + A_lo B_hi + A_hi B_lo for every 8 taps ----
+        constexpr uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(kUmmaN >> 3) << 17) | ((uint32_t)(kUmmaM >> 4) << 24);
+        const uint32_t aHi = af_smem_u32(sHi), aLo = af_smem_u32(sLo);
+        uint32_t layoutA, sboA, lboA;
+        if (p.mode == 0) { layoutA = 0; sboA = 128; lboA = 16; }
+        else if (p.mode == 1) { layoutA = 6; sboA = 256; lboA = 0; }
+        else if (p.mode == 2) { layoutA = 4; sboA = 512; lboA = 0; }
+        else { layoutA = 2; sboA = 1024; lboA = 0; }
+        uint32_t acc = 0;
+        for (int c = 0; c < chunks; c++) {
+            const int buf = c & 1;
+            af_mbar_wait(&bFull[buf], (uint32_t)(c >> 1) & 1u);
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            const uint32_t bBase = af_smem_u32(sB + buf * 2 * kUmmaBBytes);
+#pragma unroll 1
+            for (int ks = 0; ks < kUmmaChunkK / 8; ks++) {
+                const int n0 = c * kUmmaChunkK + ks * 8;            // first tap of this K step
+                // A: Hankel view of the signal copy at tap offset n0
+                uint32_t offA, baseOffA = 0;
+                if (p.mode == 0) offA = (uint32_t)n0 * 4u;
+                else if (p.mode == 3) {
+                    const int j = n0 >> 5, q = (n0 >> 3) & 3;      // 128-byte atom index along K, 32-byte step inside it
+                    const int phi = j % p.planes, dr = j / p.planes;
+                    offA = (uint32_t)(phi * p.rowsPerPlane + dr) * 128u + (uint32_t)q * 32u;
+                    baseOffA = (uint32_t)dr & 7u;
+                } else {
+                    offA = (uint32_t)n0 * 4u;                      // atom row = n0 * 4 / rowPitch rows down, (n0 * 4) % rowPitch inside
+                    baseOffA = (offA >> 7) & 7u;
+                }
+                const uint64_t dAhi = umma_desc(aHi + offA, lboA, sboA, layoutA, baseOffA);
+                const uint64_t dAlo = umma_desc(aLo + offA, lboA, sboA, layoutA, baseOffA);
+                // B: K-major 128B-swizzled [32 n][128 k] image: K atom (32 taps) = 4096 B, 32-byte step inside
+                const uint32_t offB = (uint32_t)(ks >> 2) * 4096u + (uint32_t)(ks & 3) * 32u;
+                const uint64_t dBhi = umma_desc(bBase + offB, 0, 1024, 2, 0);
+                const uint64_t dBlo = umma_desc(bBase + kUmmaBBytes + offB, 0, 1024, 2, 0);
+                umma_tf32(tmemD, dAlo, dBhi, idesc, acc); acc = 1;
+                umma_tf32(tmemD, dAhi, dBlo, idesc, 1);
+                umma_tf32(tmemD, dAhi, dBhi, idesc, 1);
+            }
+            if (c + 2 < chunks) {                                   // refill this buffer once its MMAs have read it
+                umma_commit(&bEmpty[buf]);
+                af_mbar_wait(&bEmpty[buf], (uint32_t)(c >> 1) & 1u);
+                af_mbar_arrive_expect_tx(&bFull[buf], 2 * kUmmaBBytes);
+                af_tma_load_1d(sB + buf * 2 * kUmmaBBytes, p.bimg + (size_t)(c + 2) * 2 * kUmmaBBytes, 2 * kUmmaBBytes, &bFull[buf]);
+            }
+        }
+        umma_commit(accFull);                                        // arrives when every MMA above has completed
+    }
+    __syncwarp();
+
+    // ---- epilogue: TMEM lane = frame, 24 columns = (re, im) of the 12 bins ----
+    af_mbar_wait(accFull, 0);
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    uint32_t r[32];
+    const uint32_t taddr = tmemD + ((uint32_t)(warp * 32) << 16);
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+          "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
+          "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
+          "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+        : "r"(taddr));
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+    const int t = t0 + warp * 32 + lane;
+    if (t < p.T) {
+        const long long o = (long long)clip * p.outStride + (long long)t * p.num + p.colOff;
+#pragma unroll
+        for (int j = 0; j < 12; j++) {
+            const float s = p.scale[j];
+            p.outRe[o + j] = __uint_as_float(r[2 * j]) * s;
+            p.outIm[o + j] = __uint_as_float(r[2 * j + 1]) * s;
+        }
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    if (warp == 0)
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmemD), "n"(32) : "memory");
+}
+
+}  // namespace
+
+// Pre-swizzled shared-memory images of the B operand: per 128-tap chunk, hi part then lo part, each [32 n][128 k] K-major
+// with the 128-byte swizzle (K atom of 32 taps = 4096 B = 4 groups of 8 rows x 128 B).
+extern "C" void af_cqt_umma_bimage(const float *kappa2 /* [12][N] (re, im) */, int N, unsigned char *out /* N/128 * 32 KB */) {
+    memset(out, 0, (size_t)(N / kUmmaChunkK) * 2 * kUmmaBBytes);
+    for (int c = 0; c < N / kUmmaChunkK; c++)
+        for (int n = 0; n < 24; n++)
+            for (int k = 0; k < kUmmaChunkK; k++) {
+                const int b = n >> 1, part = n & 1;
+                const float v = kappa2[((size_t)b * N + c * kUmmaChunkK + k) * 2 + part];
+                uint32_t u;
+                memcpy(&u, &v, 4);
+                u &= 0xffffe000u;
+                float hi;
+                memcpy(&hi, &u, 4);
+                const float lo = v - hi;
+                const int ka = k >> 5, kk = k & 31, g = n >> 3, r = n & 7;
+                const size_t off = (size_t)ka * 4096 + (size_t)g * 1024 + (size_t)r * 128 + (size_t)(((kk >> 2) ^ r) * 16) + (size_t)(kk & 3) * 4;
+                memcpy(out + ((size_t)c * 2 + 0) * kUmmaBBytes + off, &hi, 4);
+                memcpy(out + ((size_t)c * 2 + 1) * kUmmaBBytes + off, &lo, 4);
+            }
+}
+
+extern "C" int af_cqt_umma_supported(int fftLength, int hop, int bpo) {
+    return bpo == 12 && fftLength % kUmmaChunkK == 0 && fftLength >= 2 * kUmmaChunkK &&
+           (hop == 4 || hop == 8 || hop == 16 || hop == 32 || hop == 64 || hop == 128);
+}
+
+extern "C" int af_launch_cqt_octave_umma(const float *sig, int sigStride, int batch, int validLength, int fftLength, int hop,
+                                         int timeLength, const unsigned char *bimg, const float *scale, int num, int colOff,
+                                         float *outRe, float *outIm, void *stream) {
+    if (batch <= 0 || timeLength <= 0) return AF_OK;
+    if (!af_cqt_umma_supported(fftLength, hop, 12)) return af_fail(AF_ERR_UNSUPPORTED, "cqt octave (tcgen05): fftLength %d hop %d", fftLength, hop);
+    if (batch > 65535) return af_fail(AF_ERR_ARG, "cqt octave: batch %d > 65535 per launch", batch);
+    UmmaParams p;
+    p.sig = sig; p.sigStride = sigStride; p.validLength = validLength;
+    p.N = fftLength; p.hop = hop; p.T = timeLength;
+    p.bimg = bimg; p.scale = scale;
+    p.outRe = outRe; p.outIm = outIm; p.outStride = (long long)timeLength * num; p.num = num; p.colOff = colOff;
+    p.mode = hop == 4 ? 0 : hop == 8 ? 1 : hop == 16 ? 2 : 3;
+    p.planes = hop >= 32 ? hop / 32 : 1;
+    const int span = (kUmmaM - 1) * hop + fftLength;               // samples a tile touches
+    if (p.mode == 3) {
+        p.rowsPerPlane = ((kUmmaM + fftLength / 32 / p.planes + 1 + 7) / 8) * 8;   // rows u = t + j / planes, padded to whole 8-row groups
+        p.sigBytes = p.planes * p.rowsPerPlane * 128;
+    } else {
+        p.rowsPerPlane = 0;
+        p.sigBytes = ((span * 4 + 8 * 128 + 1023) / 1024) * 1024;    // the last core-matrix groups read a little past the span
+    }
+    const size_t smem = (size_t)2 * 2 * kUmmaBBytes + 2 * (size_t)p.sigBytes + 64;
+    if (smem > (size_t)227 * 1024) return af_fail(AF_ERR_UNSUPPORTED, "cqt octave (tcgen05): tile exceeds shared memory");
+    cudaError_t e = cudaFuncSetAttribute(k_cqt_octave_umma, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return af_cuda_check(e, "cudaFuncSetAttribute(k_cqt_octave_umma)");
+    dim3 grid((unsigned)((timeLength + kUmmaM - 1) / kUmmaM), (unsigned)batch);
+    k_cqt_octave_umma<<<grid, 128, smem, (cudaStream_t)stream>>>(p);
+    AF_LAUNCH_CHECK("k_cqt_octave_umma");
+    return AF_OK;
+}

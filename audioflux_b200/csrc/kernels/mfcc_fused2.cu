@@ -37,19 +37,25 @@ constexpr int kPairs = 513;         // bin pairs of the power-spectrum tile
 #ifndef AF2_FRAME_WARPS
 #define AF2_FRAME_WARPS 13
 #endif
-#ifndef AF2_EPI_WARPS
-#define AF2_EPI_WARPS 2
+#ifndef AF2_BANK_WARPS
+#define AF2_BANK_WARPS 3
+#endif
+#ifndef AF2_DCT_WARPS
+#define AF2_DCT_WARPS 3
 #endif
 #ifndef AF2_ABLATE
 #define AF2_ABLATE 0                // diagnostic timing builds: 1 no bank, 4 no FFTs, 8 no transposes, 16 no loads
 #endif
 constexpr int kFW = AF2_FRAME_WARPS;            // frame warps = max frames per tile (<= 16: one mma M tile)
-constexpr int kEW = AF2_EPI_WARPS;              // bank + DCT warps
-constexpr int kThreads = (kFW + 1 + kEW) * 32;  // + producer / special-column warp
+constexpr int kBW = AF2_BANK_WARPS;             // filter-bank warps (one interval per lane)
+constexpr int kDW = AF2_DCT_WARPS;              // DCT (tensor-core) + store warps, one tile behind the bank warps
+constexpr int kEW = kBW;                        // (planner: helper lanes that walk intervals)
+constexpr int kThreads = (kFW + 1 + kBW + kDW) * 32;  // + producer / special-column warp: 20 warps at <= 96 registers
 constexpr int kMaxPeers = 15;
 constexpr int kMaxNum = 128;
 constexpr int kLPitch = 132;        // log-mel tile row pitch (floats): 4g + t -> 32 distinct banks for mma A fragments
 constexpr int kMaxTab = 1408;       // bank table entries (one float4 per bin pair of an interval) in the parameter block
+constexpr int kMaxPass = (kMaxNum + 1 + kEW * 32 - 1) / (kEW * 32);   // bank passes: one interval per helper lane and pass
 constexpr int kSpecPitch = 17;      // c64 slots per n2 row of the special-column buffer (odd -> conflict-free both ways)
 constexpr int kScratchFloats = 33 * 32;
 
@@ -58,10 +64,14 @@ struct Plan {
     float2 *dTw;                    // [17][32]  W_2048^(lane * ka), ka = 0..15; row 16: W_2048^(16 lane)
     float *dDct;                    // [128 m][dctPitch]
     int num, ccNum, ct, dataType;
-    int ivFirst[kEW + 1];
-    unsigned ivDesc[kMaxNum + 2];   // (first bin pair << 16) | table offset, entry num+1 = end sentinel
+    unsigned ivDesc[kMaxNum + 4];   // (first bin pair << 16) | table offset; entries num+1.. = end sentinels
+    int nPass, passLen[kMaxPass];   // bank passes and the longest interval (bin pairs) of each
+    unsigned short assign[kMaxPass * kEW * 32];   // interval of helper lane (pass, warp * 32 + lane), 0xffff = none
     int tabLen;
     float4 *tab;                    // host copy of the bank table
+    float4 *dTab;                   // device copy, staged into shared memory by every CTA
+    unsigned *dDesc;
+    unsigned short *dAssign;
 };
 
 struct Params {
@@ -74,12 +84,13 @@ struct Params {
     int num, ccNum, rectify, dataType, rawMel, pitchPairs, bulkStore, dctPitch;
     int nPeer;
     float *peerOut[kMaxPeers];
-    int offSpan, offScratch, offP, offWin, offTw, offSpec, offDct, offL, offStage, offBar, stageBytes;
-    int ivFirst[kEW + 1];
-    unsigned ivDesc[kMaxNum + 2];
-    float4 bankW[kMaxTab];
+    int offSpan, offScratch, offP, offWin, offTw, offSpec, offDct, offL, offG, offStage, offBar, offTab, offDesc, offAssign, stageBytes;   // offL: two log-mel tiles
+    int nPass, passLen[kMaxPass];
+    const unsigned short *assign;
+    int tabLen;
+    const float4 *bankTab;          // [tabLen] (rise[2q], rise[2q+1], fall[2q], fall[2q+1]) per bin pair of an interval
+    const unsigned *ivDesc;         // [kMaxNum + 4]
 };
-static_assert(sizeof(Params) < 32000, "kernel parameter block must stay below the 32 KB limit");
 
 __device__ __forceinline__ void named_bar_sync(int id, int threads) {
     asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(threads) : "memory");
@@ -115,6 +126,12 @@ __global__ void __launch_bounds__(kThreads, 1) k_mfcc_fused2(const __grid_consta
     uint64_t *specFull = fullBar + 4;                                     // [2] special columns of a tile stored
     uint64_t *pFull = fullBar + 6;                                        // power-spectrum tile complete
     uint64_t *pEmpty = fullBar + 7;                                       // bank done with it
+    uint64_t *lFull = fullBar + 8;                                        // [2] log-mel tile written by the bank warps
+    uint64_t *lEmpty = fullBar + 10;                                      // [2] ... consumed by the DCT warps
+    float4 *sTab = reinterpret_cast<float4 *>(smem + p.offTab);           // interval-form bank weights
+    unsigned *sDesc = reinterpret_cast<unsigned *>(smem + p.offDesc);
+    unsigned short *sAssign = reinterpret_cast<unsigned short *>(smem + p.offAssign);
+    float *sG = reinterpret_cast<float *>(smem + p.offG);                 // [16][kLPitch] falling-slope sums Fl_i (sL holds R_i)
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int pitch = p.pitchPairs;
@@ -122,13 +139,16 @@ __global__ void __launch_bounds__(kThreads, 1) k_mfcc_fused2(const __grid_consta
     // ---- one-time: tables -> shared, zero the tiles (pad slots are multiplied by zero weights), barriers ----
     for (int i = threadIdx.x; i < 32 * 32; i += kThreads) sWin[i] = p.winPairs[i];
     for (int i = threadIdx.x; i < 17 * 32; i += kThreads) sTw[i] = p.tw[i];
+    for (int i = threadIdx.x; i < p.tabLen; i += kThreads) sTab[i] = p.bankTab[i];
+    for (int i = threadIdx.x; i < kMaxNum + 4; i += kThreads) sDesc[i] = p.ivDesc[i];
+    for (int i = threadIdx.x; i < kMaxPass * kEW * 32; i += kThreads) sAssign[i] = p.assign[i];
+    for (int i = threadIdx.x; i < 16 * kLPitch; i += kThreads) sG[i] = 0.0f;
     for (int i = threadIdx.x; i < kFW * kScratchFloats; i += kThreads) scratchAll[i] = 0.0f;
     for (int i = threadIdx.x; i < kPairs * pitch * 2; i += kThreads) sP[i] = 0.0f;
     for (int i = threadIdx.x; i < 2 * 32 * kSpecPitch; i += kThreads) sSpec[i] = 0ull;
-    if (!p.rawMel) {
+    for (int i = threadIdx.x; i < 2 * 16 * kLPitch; i += kThreads) sL[i] = 0.0f;
+    if (!p.rawMel)
         for (int i = threadIdx.x; i < kMaxNum * p.dctPitch; i += kThreads) sDct[i] = p.dct[i];
-        for (int i = threadIdx.x; i < 16 * kLPitch; i += kThreads) sL[i] = 0.0f;
-    }
     for (int i = threadIdx.x; i < p.stageBytes / 4; i += kThreads) sStage[i] = 0.0f;
     if (threadIdx.x == 0) {
         for (int s = 0; s < 2; s++) {
@@ -137,7 +157,8 @@ __global__ void __launch_bounds__(kThreads, 1) k_mfcc_fused2(const __grid_consta
             af_mbar_init(&specFull[s], kFW);
         }
         af_mbar_init(pFull, kFW + 1);
-        af_mbar_init(pEmpty, kEW);
+        af_mbar_init(pEmpty, kBW);
+        for (int s = 0; s < 2; s++) { af_mbar_init(&lFull[s], kBW); af_mbar_init(&lEmpty[s], kDW); }
         af_fence_barrier_init();
     }
     __syncthreads();
@@ -166,7 +187,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_mfcc_fused2(const __grid_consta
         for (long long tile = blockIdx.x; tile < p.totalTiles; tile += gridDim.x, ++it) {
             const int stage = it % S;
             if (lane == 0) {
-                af_mbar_wait_sleepy(&emptyBar[stage], (uint32_t)(it / S) & 1u);       // tile `it` taken: refill the slot
+                af_mbar_wait(&emptyBar[stage], (uint32_t)(it / S) & 1u);       // tile `it` taken: refill the slot
                 const long long next = tile + (long long)S * gridDim.x;
                 if (next < p.totalTiles) issue(next, stage);
             }
@@ -174,7 +195,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_mfcc_fused2(const __grid_consta
             const int f0 = (int)(tile % p.tilesPerClip) * F;
             const int nf = min(F, p.timeLength - f0);
             const int sb = it & 1;
-            af_mbar_wait_sleepy(&specFull[sb], (uint32_t)(it >> 1) & 1u);
+            af_mbar_wait(&specFull[sb], (uint32_t)(it >> 1) & 1u);
             // a[n2] = R_n2[0], b[n2] = R_n2[32] (both real).  kind 0: X[64 k2] = DFT32(a)[k2], k2 = 0..16;
             // kind 1: X[32 + 64 k2] = DFT32(b[n2] W_64^n2)[k2], k2 = 0..15
             c64 u[32];
@@ -188,7 +209,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_mfcc_fused2(const __grid_consta
                 if (n2 >= 16 && kind) u[n2] = c_mul_mi(u[n2]);                        // W_64^16 = -i
             }
             af_fft32(u);
-            af_mbar_wait_sleepy(pEmpty, ((uint32_t)it & 1u) ^ 1u);                   // bank done with the previous tile
+            af_mbar_wait(pEmpty, ((uint32_t)it & 1u) ^ 1u);                   // bank done with the previous tile
             if (f < nf) {
                 float *dst = sP + 2 * f + (kind ? 32 * pitch : 0);                    // bin 64 k2 + 32 kind -> pair 32 k2 + 16 kind
 #pragma unroll
@@ -209,146 +230,196 @@ __global__ void __launch_bounds__(kThreads, 1) k_mfcc_fused2(const __grid_consta
         return;
     }
 
-    if (warp > kFW) {
-        // ================= helpers: interval-form bank over the tile, then the DCT on the tensor cores =================
+    if (warp > kFW && warp <= kFW + kBW) {
+        // ================= bank warps: interval-form filter bank over the whole tile =================
         const int e = warp - (kFW + 1);
-        const int g = lane >> 2, t = lane & 3;
-        const int i0 = p.ivFirst[e], i1 = p.ivFirst[e + 1];        // filters [i0, i1) = intervals i0 .. i1
-        const int rowFloats = p.rawMel ? p.num : p.ccNum;
-        constexpr int kNB = (CT + kEW - 1) / kEW;                  // n-blocks of the DCT per warp
+        const int rowFloats = p.num;
         int it = 0;
         for (long long tile = blockIdx.x; tile < p.totalTiles; tile += gridDim.x, ++it) {
             const long long clip = tile / p.tilesPerClip;
             const int f0 = (int)(tile % p.tilesPerClip) * F;
             const int nf = min(F, p.timeLength - f0);
-            float *stage = sStage + (p.rawMel ? (size_t)(it & 1) * (p.stageBytes / 8) : 0);
-        const int stagePitch = p.rawMel ? p.num + 4 : p.ccNum;      // raw filter-bank rows are padded (bank conflicts), cepstra dense
-            af_mbar_wait_sleepy(pFull, (uint32_t)it & 1u);
-            // ---- bank: lane = frame; per interval the rising weights of filter i and the falling weights of filter i-1
-            if (i1 > i0 && lane < 16 && !(AF2_ABLATE & 1)) {      // second half-warp idle: no shared-memory wavefronts for it
-                const int fr = min(lane, nf - 1);
-                const c64 *Pp = reinterpret_cast<const c64 *>(sP) + fr;
-                float prevR = 0.0f;
-                for (int i = i0; i <= i1; i++) {
-                    const unsigned d0 = p.ivDesc[i], d1 = p.ivDesc[i + 1];
-                    const int off1 = (int)(d1 & 0xffffu);
-                    int j = (int)(d0 & 0xffffu);
-                    const c64 *q = Pp + (size_t)(d0 >> 16) * pitch;
-                    c64 aR = 0ull, aF = 0ull, bR = 0ull, bF = 0ull;
-                    for (; j + 1 < off1; j += 2) {
-                        const float4 w0 = p.bankW[j], w1 = p.bankW[j + 1];
-                        const c64 v0 = q[0], v1 = q[pitch];
-                        q += 2 * pitch;
-                        aR = v_fma(v0, c_pack(w0.x, w0.y), aR);
-                        aF = v_fma(v0, c_pack(w0.z, w0.w), aF);
-                        bR = v_fma(v1, c_pack(w1.x, w1.y), bR);
-                        bF = v_fma(v1, c_pack(w1.z, w1.w), bF);
+            const int lbuf = it & 1;
+            float *L = sL + (size_t)lbuf * 16 * kLPitch;
+            float *stage = sStage + (size_t)lbuf * (p.stageBytes / 8);   // (filter-bank output mode: two staging tiles)
+            const int stagePitch = p.num + 4;                              // padded rows (bank conflicts)
+            af_mbar_wait(pFull, (uint32_t)it & 1u);
+            if (!p.rawMel) af_mbar_wait(&lEmpty[lbuf], ((uint32_t)(it >> 1) & 1u) ^ 1u);    // DCT done with tile it - 2
+            // ---- phase 1: ONE INTERVAL PER LANE, all frames of the tile in registers.  Pass after pass (longest
+            // intervals first, host-planned so that the 16 lanes of a half-warp start in different 8-byte bank pairs) a lane
+            // walks the bin pairs of its interval: one LDS.128 of weights (rise of filter i, fall of filter i-1) and, per
+            // frame, one LDS.64 of the power pair + two FFMA2: kFW independent accumulator chains per lane.
+            if (!(AF2_ABLATE & 1)) {
+                for (int ps = 0; ps < p.nPass; ps++) {
+                    const unsigned iv = sAssign[(ps * kBW + e) * 32 + lane];
+                    const bool have = iv != 0xffffu;
+                    const unsigned d0 = sDesc[have ? iv : 0], d1 = sDesc[have ? iv + 1 : 0];
+                    const int len = have ? (int)(d1 & 0xffffu) - (int)(d0 & 0xffffu) : 0;
+                    const float4 *wt = sTab + (d0 & 0xffffu);
+                    const c64 *q = reinterpret_cast<const c64 *>(sP) + (size_t)(d0 >> 16) * pitch;
+                    c64 aR[kFW], aF[kFW];
+#pragma unroll
+                    for (int f = 0; f < kFW; f++) { aR[f] = 0ull; aF[f] = 0ull; }
+                    const int maxLen = p.passLen[ps];
+                    for (int j = 0; j < maxLen; j++) {
+                        if (j < len) {
+                            const float4 w = wt[j];
+                            const c64 wr = c_pack(w.x, w.y), wf = c_pack(w.z, w.w);
+#pragma unroll
+                            for (int f = 0; f < kFW; f++) {
+                                const c64 v = q[f];
+                                aR[f] = v_fma(v, wr, aR[f]);
+                                aF[f] = v_fma(v, wf, aF[f]);
+                            }
+                            q += pitch;
+                        }
                     }
-                    if (j < off1) {
-                        const float4 w0 = p.bankW[j];
-                        const c64 v0 = q[0];
-                        aR = v_fma(v0, c_pack(w0.x, w0.y), aR);
-                        aF = v_fma(v0, c_pack(w0.z, w0.w), aF);
+                    if (have) {
+#pragma unroll
+                        for (int f = 0; f < kFW; f++) {
+                            float r0, r1, f0_, f1_;
+                            c_unpack(aR[f], r0, r1);
+                            c_unpack(aF[f], f0_, f1_);
+                            L[f * kLPitch + iv] = r0 + r1;             // R_i: rising part of filter i (zero for i = num)
+                            sG[f * kLPitch + iv] = f0_ + f1_;          // Fl_i: falling part of filter i - 1
+                        }
                     }
-                    float r0, r1, f0_, f1_;
-                    c_unpack(c_add(aR, bR), r0, r1);
-                    c_unpack(c_add(aF, bF), f0_, f1_);
-                    if (i > i0 && lane < nf) {
-                        const int m = i - 1;
-                        const float v = prevR + (f0_ + f1_);
-                        if (p.rawMel) stage[lane * stagePitch + m] = v;
-                        else sL[lane * kLPitch + m] = rectify_value(v, p.rectify);
-                    }
-                    prevR = r0 + r1;
                 }
             }
             __syncwarp();
             if (lane == 0) af_mbar_arrive(pEmpty);                 // frame warps may overwrite the power tile
-            if (e == 0) bulk_wait_read0();                         // the previous tiles' bulk stores have read their staging
-            if (p.rawMel) fence_proxy_async_smem();
-            named_bar_sync(1, kEW * 32);                           // A: the whole log-mel tile is in shared memory
-            if (!p.rawMel) {
-                // out[16 x 8 CT] = L[16 x 128] . D^T[128 x 8 CT]: mma.sync m16n8k8 TF32, 3xTF32 split (hi by truncation,
-                // lo = x - hi exact), separate accumulators for hi*hi and the cross terms
-                float acc[kNB][4], acx[kNB][4];
+            if (p.rawMel && e == 0) bulk_wait_read0();             // the store of tile it - 2 has read this staging tile
+            named_bar_sync(3, kBW * 32);                           // every R_i / Fl_i of the tile is in shared memory
+            // ---- phase 2: mel_m = R_m + Fl_{m+1}, rectified in place (cepstra) or staged as the result row (filter bank) ----
+            if (!(AF2_ABLATE & 1)) {
+                for (int m = e * 32 + lane; m < p.num; m += kBW * 32) {
 #pragma unroll
-                for (int n = 0; n < kNB; n++) {
-                    acc[n][0] = acc[n][1] = acc[n][2] = acc[n][3] = 0.0f;
-                    acx[n][0] = acx[n][1] = acx[n][2] = acx[n][3] = 0.0f;
+                    for (int f = 0; f < kFW; f++) {
+                        const float v = L[f * kLPitch + m] + sG[f * kLPitch + m + 1];
+                        if (p.rawMel) { if (f < nf) stage[f * stagePitch + m] = v; }
+                        else L[f * kLPitch + m] = rectify_value(v, p.rectify);
+                    }
                 }
+            }
+            if (!p.rawMel) {
+                __syncwarp();
+                if (lane == 0) af_mbar_arrive(&lFull[lbuf]);       // the DCT warps take the tile from here
+                named_bar_sync(1, kBW * 32);                       // sG is free for the next tile's phase 1
+                continue;
+            }
+            fence_proxy_async_smem();
+            named_bar_sync(1, kBW * 32);                           // the result rows are staged (and sG is free again)
+            const long long tileOff = ((long long)clip * p.timeLength + f0) * rowFloats;
+            if (p.bulkStore) {
+                if (e == 0) {                                       // one row per lane (padded staging rows)
+                    if (lane < nf) bulk_store(p.out + tileOff + (long long)lane * rowFloats, stage + lane * stagePitch, (uint32_t)(rowFloats * 4));
+                    bulk_commit();
+                }
+            } else {
+                for (int r = 0; r < nf; r++)
+                    for (int i = e * 32 + lane; i < rowFloats; i += kBW * 32) p.out[tileOff + (long long)r * rowFloats + i] = stage[r * stagePitch + i];
+            }
+        }
+        if (e == 0) bulk_wait0();
+        return;
+    }
+
+    if (warp > kFW + kBW) {
+        // ================= DCT warps: ortho DCT-II of the log-mel tile on the tensor cores, then the tile leaves =================
+        if (p.rawMel) return;
+        const int d = warp - (kFW + 1 + kBW);
+        const int g = lane >> 2, t = lane & 3;
+        constexpr int kNB = (CT + kDW - 1) / kDW;                  // n-blocks of the DCT per warp
+        float *stage = sStage;
+        int it = 0;
+        for (long long tile = blockIdx.x; tile < p.totalTiles; tile += gridDim.x, ++it) {
+            const long long clip = tile / p.tilesPerClip;
+            const int f0 = (int)(tile % p.tilesPerClip) * F;
+            const int nf = min(F, p.timeLength - f0);
+            const int lbuf = it & 1;
+            const float *L = sL + (size_t)lbuf * 16 * kLPitch;
+            af_mbar_wait(&lFull[lbuf], (uint32_t)(it >> 1) & 1u);
+            // out[16 x 8 CT] = L[16 x 128] . D^T[128 x 8 CT]: mma.sync m16n8k8 TF32, 3xTF32 split (hi by truncation,
+            // lo = x - hi exact), separate accumulators for hi*hi and the cross terms
+            float acc[kNB][4], acx[kNB][4];
+#pragma unroll
+            for (int n = 0; n < kNB; n++) {
+                acc[n][0] = acc[n][1] = acc[n][2] = acc[n][3] = 0.0f;
+                acx[n][0] = acx[n][1] = acx[n][2] = acx[n][3] = 0.0f;
+            }
 #define AF_MMA_TF32(ACC, A0, A1, A2, A3, B0, B1)                                                              \
     asm("mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};" \
         : "+f"(ACC[0]), "+f"(ACC[1]), "+f"(ACC[2]), "+f"(ACC[3])                                              \
         : "r"(A0), "r"(A1), "r"(A2), "r"(A3), "r"(B0), "r"(B1))
 #pragma unroll 2
-                for (int k0 = 0; k0 < kMaxNum; k0 += 8) {
-                    const float af[4] = {sL[g * kLPitch + k0 + t], sL[(g + 8) * kLPitch + k0 + t],
-                                         sL[g * kLPitch + k0 + t + 4], sL[(g + 8) * kLPitch + k0 + t + 4]};
-                    uint32_t ah[4], al[4];
+            for (int k0 = 0; k0 < kMaxNum; k0 += 8) {
+                const float af[4] = {L[g * kLPitch + k0 + t], L[(g + 8) * kLPitch + k0 + t],
+                                     L[g * kLPitch + k0 + t + 4], L[(g + 8) * kLPitch + k0 + t + 4]};
+                uint32_t ah[4], al[4];
 #pragma unroll
-                    for (int i = 0; i < 4; i++) {
-                        ah[i] = __float_as_uint(af[i]) & 0xffffe000u;
-                        al[i] = __float_as_uint(af[i] - __uint_as_float(ah[i])) & 0xffffe000u;
-                    }
-#pragma unroll
-                    for (int n = 0; n < kNB; n++) {
-                        const int nb = e + n * kEW;
-                        if (nb < CT) {
-                            const float bf[2] = {sDct[(k0 + t) * p.dctPitch + nb * 8 + g], sDct[(k0 + t + 4) * p.dctPitch + nb * 8 + g]};
-                            uint32_t bh[2], bl[2];
-#pragma unroll
-                            for (int i = 0; i < 2; i++) {
-                                bh[i] = __float_as_uint(bf[i]) & 0xffffe000u;
-                                bl[i] = __float_as_uint(bf[i] - __uint_as_float(bh[i])) & 0xffffe000u;
-                            }
-                            AF_MMA_TF32(acx[n], al[0], al[1], al[2], al[3], bh[0], bh[1]);
-                            AF_MMA_TF32(acc[n], ah[0], ah[1], ah[2], ah[3], bh[0], bh[1]);
-                            AF_MMA_TF32(acx[n], ah[0], ah[1], ah[2], ah[3], bl[0], bl[1]);
-                        }
-                    }
+                for (int i = 0; i < 4; i++) {
+                    ah[i] = __float_as_uint(af[i]) & 0xffffe000u;
+                    al[i] = __float_as_uint(af[i] - __uint_as_float(ah[i])) & 0xffffe000u;
                 }
-#undef AF_MMA_TF32
-                // C fragment: rows g and g+8, columns nb*8 + 2t, +1 -> dense staging tile [nf][ccNum]
 #pragma unroll
                 for (int n = 0; n < kNB; n++) {
-                    const int nb = e + n * kEW;
-                    if (nb >= CT) continue;
-                    const int c = nb * 8 + 2 * t;
-                    const float v0 = acc[n][0] + acx[n][0], v1 = acc[n][1] + acx[n][1];
-                    const float v2 = acc[n][2] + acx[n][2], v3 = acc[n][3] + acx[n][3];
-                    if (g < nf) {
-                        if (c < p.ccNum) stage[g * p.ccNum + c] = v0;
-                        if (c + 1 < p.ccNum) stage[g * p.ccNum + c + 1] = v1;
-                    }
-                    if (g + 8 < nf) {
-                        if (c < p.ccNum) stage[(g + 8) * p.ccNum + c] = v2;
-                        if (c + 1 < p.ccNum) stage[(g + 8) * p.ccNum + c + 1] = v3;
+                    const int nb = d + n * kDW;
+                    if (nb < CT) {
+                        const float bf[2] = {sDct[(k0 + t) * p.dctPitch + nb * 8 + g], sDct[(k0 + t + 4) * p.dctPitch + nb * 8 + g]};
+                        uint32_t bh[2], bl[2];
+#pragma unroll
+                        for (int i = 0; i < 2; i++) {
+                            bh[i] = __float_as_uint(bf[i]) & 0xffffe000u;
+                            bl[i] = __float_as_uint(bf[i] - __uint_as_float(bh[i])) & 0xffffe000u;
+                        }
+                        AF_MMA_TF32(acx[n], al[0], al[1], al[2], al[3], bh[0], bh[1]);
+                        AF_MMA_TF32(acc[n], ah[0], ah[1], ah[2], ah[3], bh[0], bh[1]);
+                        AF_MMA_TF32(acx[n], ah[0], ah[1], ah[2], ah[3], bl[0], bl[1]);
                     }
                 }
-                fence_proxy_async_smem();
-                named_bar_sync(2, kEW * 32);                       // B: the result tile is staged
             }
+#undef AF_MMA_TF32
+            __syncwarp();
+            if (lane == 0) af_mbar_arrive(&lEmpty[lbuf]);          // the bank warps may refill this log-mel tile
+            if (d == 0) bulk_wait_read0();                         // the previous tile's bulk stores have read the staging tile
+            named_bar_sync(2, kDW * 32);
+            // C fragment: rows g and g+8, columns nb*8 + 2t, +1 -> dense staging tile [nf][ccNum]
+#pragma unroll
+            for (int n = 0; n < kNB; n++) {
+                const int nb = d + n * kDW;
+                if (nb >= CT) continue;
+                const int c = nb * 8 + 2 * t;
+                const float v0 = acc[n][0] + acx[n][0], v1 = acc[n][1] + acx[n][1];
+                const float v2 = acc[n][2] + acx[n][2], v3 = acc[n][3] + acx[n][3];
+                if (g < nf) {
+                    if (c < p.ccNum) stage[g * p.ccNum + c] = v0;
+                    if (c + 1 < p.ccNum) stage[g * p.ccNum + c + 1] = v1;
+                }
+                if (g + 8 < nf) {
+                    if (c < p.ccNum) stage[(g + 8) * p.ccNum + c] = v2;
+                    if (c + 1 < p.ccNum) stage[(g + 8) * p.ccNum + c + 1] = v3;
+                }
+            }
+            fence_proxy_async_smem();
+            named_bar_sync(4, kDW * 32);                           // the result tile is staged
             // ---- the tile leaves: destination 0 is this GPU's buffer, 1..nPeer the peers' gathered arrays (NVLink) ----
-            const long long tileOff = ((long long)clip * p.timeLength + f0) * rowFloats;
+            const long long tileOff = ((long long)clip * p.timeLength + f0) * p.ccNum;
             if (p.bulkStore) {
-                if (e == 0) {
-                    if (p.rawMel) {                                 // one row per lane (padded staging rows)
-                        if (lane < nf) bulk_store(p.out + tileOff + (long long)lane * rowFloats, stage + lane * stagePitch, (uint32_t)(rowFloats * 4));
-                    } else if (lane <= p.nPeer) {                   // one destination per lane, the whole tile at once
-                        float *o = (lane == 0 ? p.out : p.peerOut[lane - 1]) + tileOff;
-                        bulk_store(o, stage, (uint32_t)(nf * rowFloats * 4));
-                    }
+                if (d == 0 && lane <= p.nPeer) {                   // one destination per lane, the whole tile at once
+                    float *o = (lane == 0 ? p.out : p.peerOut[lane - 1]) + tileOff;
+                    bulk_store(o, stage, (uint32_t)(nf * p.ccNum * 4));
                     bulk_commit();
                 }
             } else {
-                for (int d = 0; d <= p.nPeer; d++) {
-                    float *o = (d == 0 ? p.out : p.peerOut[d - 1]) + tileOff;
-                    for (int r = 0; r < nf; r++)
-                        for (int i = e * 32 + lane; i < rowFloats; i += kEW * 32) o[(long long)r * rowFloats + i] = stage[r * stagePitch + i];
+                const int n = nf * p.ccNum;
+                for (int dst = 0; dst <= p.nPeer; dst++) {
+                    float *o = (dst == 0 ? p.out : p.peerOut[dst - 1]) + tileOff;
+                    for (int i = d * 32 + lane; i < n; i += kDW * 32) o[i] = stage[i];
                 }
+                named_bar_sync(2, kDW * 32);                       // staging tile read before the next tile's fragments land
             }
         }
-        if (e == 0) bulk_wait0();
+        if (d == 0) bulk_wait0();
         return;
     }
 
@@ -441,14 +512,22 @@ __global__ void __launch_bounds__(kThreads, 1) k_mfcc_fused2(const __grid_consta
         }
         // ---- D: 32-point DFT over n2 in lane k1: bins k1 + 64 k2 and, mirrored, 64 (32 - k2) - k1 ----
         if (!(AF2_ABLATE & 4)) af_fft32(z);
-        af_mbar_wait(pEmpty, ((uint32_t)it & 1u) ^ 1u);            // bank done with the previous tile's spectra
+        af_mbar_wait(pEmpty, ((uint32_t)it & 1u) ^ 1u);     // bank done with the previous tile's spectra
         if (lane) {
+            if (p.dataType == SpectralData_Mag) {                  // (uniform branch: no sqrt sequence in the power path)
 #pragma unroll
-            for (int k2 = 0; k2 < 32; k2++) {
-                float pw = c_norm2(z[AF_BR5(k2)]);
-                if (p.dataType == SpectralData_Mag) pw = sqrtf(pw);
-                if (k2 < 16) sP[offLo + k2 * strideK2] = pw;
-                else sP[offHi + (32 - k2) * strideK2] = pw;
+                for (int k2 = 0; k2 < 32; k2++) {
+                    const float pw = sqrtf(c_norm2(z[AF_BR5(k2)]));
+                    if (k2 < 16) sP[offLo + k2 * strideK2] = pw;
+                    else sP[offHi + (32 - k2) * strideK2] = pw;
+                }
+            } else {
+#pragma unroll
+                for (int k2 = 0; k2 < 32; k2++) {
+                    const float pw = c_norm2(z[AF_BR5(k2)]);
+                    if (k2 < 16) sP[offLo + k2 * strideK2] = pw;
+                    else sP[offHi + (32 - k2) * strideK2] = pw;
+                }
             }
         }
         __syncwarp();
@@ -458,7 +537,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_mfcc_fused2(const __grid_consta
 
 void free_plan(Plan *pl) {
     if (!pl) return;
-    af_dev_free(pl->dWinPairs); af_dev_free(pl->dTw); af_dev_free(pl->dDct);
+    af_dev_free(pl->dWinPairs); af_dev_free(pl->dTw); af_dev_free(pl->dDct); af_dev_free(pl->dTab); af_dev_free(pl->dDesc); af_dev_free(pl->dAssign);
     free(pl->tab);
     free(pl);
 }
@@ -475,6 +554,8 @@ struct Intervals {
 bool build_intervals2(const float *bank, int num, Intervals *iv) {
     if (num < 1 || num > kMaxNum) return false;
     int cur = 0;
+    int peak[kMaxNum];
+    for (int m = 0; m < num; m++) peak[m] = -1;
     for (int i = 0; i <= num; i++) { iv->first[i] = 1; iv->last[i] = 0; }
     for (int k = 0; k < kBins; k++) {
         int cover[3], nc = 0;
@@ -485,7 +566,18 @@ bool build_intervals2(const float *bank, int num, Intervals *iv) {
         if (nc > 2 || (nc == 2 && cover[1] != cover[0] + 1)) return false;
         int i;
         if (nc == 2) i = cover[1];
-        else i = cur <= cover[0] ? cover[0] : cover[0] + 1;
+        else {
+            // one filter only: its rising side (interval m) up to its peak, its falling side (interval m + 1) after it --
+            // keeps the two outer slopes of the bank in intervals of their own instead of one double-length interval
+            const int m = cover[0];
+            if (peak[m] < 0) {
+                int best = k;
+                for (int kk = k; kk < kBins && bank[(size_t)m * kBins + kk] != 0.0f; kk++)
+                    if (bank[(size_t)m * kBins + kk] > bank[(size_t)m * kBins + best]) best = kk;
+                peak[m] = best;
+            }
+            i = (cur <= m && k <= peak[m]) ? m : m + 1;
+        }
         if (i < cur || i > cover[0] + 1) return false;             // intervals must be monotone runs of bins
         cur = i;
         iv->owner[k] = i;
@@ -518,19 +610,42 @@ int build_table(const float *bank, int num, const Intervals *iv, unsigned *desc 
     return off;
 }
 
-// filters [first[e], first[e+1]) per helper warp, balanced by (pairs + per-interval overhead) of the intervals it walks
-void split_filters(int num, const unsigned *desc, int *first /* kEW+1 */) {
-    double cost[kMaxNum + 1], total = 0;
-    for (int i = 0; i <= num; i++) { cost[i] = 5.0 + 2.0 * (double)((desc[i + 1] & 0xffffu) - (desc[i] & 0xffffu)); total += cost[i]; }
-    first[0] = 0;
-    double acc = 0;
-    int e = 1;
-    for (int m = 0; m < num && e < kEW; m++) {
-        acc += cost[m];
-        if (acc >= total * e / kEW) first[e++] = m + 1;
+// One interval per helper lane and pass: intervals sorted by length (bin pairs), the longest kEW*32 form pass 0, the
+// next ones pass 1, ...; inside a pass the intervals are dealt to half-warps (16 lanes) such that their first bin
+// pairs differ mod 16 where possible: with the odd tile pitch the 16 lanes then read 16 different 8-byte bank pairs
+// for every frame and every step of the walk (conflict-free LDS.64).
+int plan_passes(int num, const unsigned *desc, unsigned short *assign /* kMaxPass * kEW * 32 */, int *passLen /* kMaxPass */) {
+    const int W = kEW * 32, n = num + 1;
+    int order[kMaxNum + 1], len[kMaxNum + 1];
+    for (int i = 0; i < n; i++) { order[i] = i; len[i] = (int)(desc[i + 1] & 0xffffu) - (int)(desc[i] & 0xffffu); }
+    for (int a = 1; a < n; a++)                                      // insertion sort, longest first, stable
+        for (int b = a; b > 0 && len[order[b]] > len[order[b - 1]]; b--) { const int t = order[b]; order[b] = order[b - 1]; order[b - 1] = t; }
+    for (int i = 0; i < kMaxPass * W; i++) assign[i] = 0xffffu;
+    for (int ps = 0; ps < kMaxPass; ps++) passLen[ps] = 0;
+    int nPass = 0;
+    for (int base = 0; base < n; base += W, nPass++) {
+        const int cnt = n - base < W ? n - base : W;
+        passLen[nPass] = len[order[base]];
+        unsigned short *row = assign + (size_t)nPass * W;
+        int used[2 * kEW][16], fill[2 * kEW];
+        memset(used, 0, sizeof(used)); memset(fill, 0, sizeof(fill));
+        int later[kMaxNum + 1], nLater = 0;
+        for (int c = 0; c < cnt; c++) {                              // first round: a half-warp whose residue slot is free
+            const int iv = order[base + c], r = (int)(desc[iv] >> 16) & 15;
+            int best = -1;
+            for (int h = 0; h < 2 * kEW; h++)
+                if (fill[h] < 16 && !used[h][r] && (best < 0 || fill[h] < fill[best])) best = h;
+            if (best < 0) { later[nLater++] = iv; continue; }
+            used[best][r] = 1;
+            row[best * 16 + fill[best]++] = (unsigned short)iv;
+        }
+        for (int c = 0; c < nLater; c++) {                           // the rest: wherever there is room (a 2-way conflict)
+            int best = -1;
+            for (int h = 0; h < 2 * kEW; h++) if (fill[h] < 16 && (best < 0 || fill[h] < fill[best])) best = h;
+            row[best * 16 + fill[best]++] = (unsigned short)later[c];
+        }
     }
-    for (; e <= kEW; e++) first[e] = num;
-    first[kEW] = num;
+    return nPass;
 }
 
 }  // namespace
@@ -539,7 +654,7 @@ extern "C" int af_mfcc2_supported(int fftLength, int num, int ccNum, const float
     if (fftLength != kN || num < 1 || num > kMaxNum || ccNum < 1 || ccNum > 64 || !bank) return 0;
     Intervals *iv = static_cast<Intervals *>(malloc(sizeof(Intervals)));
     float4 *tab = static_cast<float4 *>(malloc(sizeof(float4) * kMaxTab));
-    unsigned desc[kMaxNum + 2];
+    unsigned desc[kMaxNum + 4];
     const int ok = iv && tab && build_intervals2(bank, num, iv) && build_table(bank, num, iv, desc, tab) >= 0;
     free(iv); free(tab);
     return ok;
@@ -574,8 +689,12 @@ extern "C" int af_mfcc2_plan_build(void **planOut, int fftLength, int num, int c
     if (!iv || !pl->tab) { free(iv); free_plan(pl); return AF_ERR_NOMEM; }
     build_intervals2(bank, num, iv);
     pl->tabLen = build_table(bank, num, iv, pl->ivDesc, pl->tab);
-    split_filters(num, pl->ivDesc, pl->ivFirst);
     free(iv);
+    for (int i = num + 2; i < kMaxNum + 4; i++) pl->ivDesc[i] = pl->ivDesc[num + 1];
+    pl->nPass = plan_passes(num, pl->ivDesc, pl->assign, pl->passLen);
+    if (rc == AF_OK) rc = af_dev_upload(reinterpret_cast<void **>(&pl->dAssign), pl->assign, sizeof(pl->assign));
+    if (rc == AF_OK) rc = af_dev_upload(reinterpret_cast<void **>(&pl->dTab), pl->tab, sizeof(float4) * (size_t)(pl->tabLen > 0 ? pl->tabLen : 1));
+    if (rc == AF_OK) rc = af_dev_upload(reinterpret_cast<void **>(&pl->dDesc), pl->ivDesc, sizeof(pl->ivDesc));
 
     // DCT table as the mma B operand: D^T[m][c], row pitch % 32 == 8 -> conflict-free fragment reads
     const int pitch = pl->ct <= 5 ? 40 : 72;
@@ -607,9 +726,9 @@ static int launch_fused2(void *plan, const float *data, int dataLength, int batc
     pp->dctPitch = pl->ct <= 5 ? 40 : 72;
     pp->nPeer = nPeer;
     for (int d = 0; d < nPeer; d++) pp->peerOut[d] = peerOut[d];
-    for (int e = 0; e <= kEW; e++) pp->ivFirst[e] = pl->ivFirst[e];
-    memcpy(pp->ivDesc, pl->ivDesc, sizeof(pp->ivDesc));
-    memcpy(pp->bankW, pl->tab, sizeof(float4) * (size_t)pl->tabLen);
+    pp->nPass = pl->nPass; pp->assign = pl->dAssign;
+    for (int i = 0; i < kMaxPass; i++) pp->passLen[i] = pl->passLen[i];
+    pp->bankTab = pl->dTab; pp->ivDesc = pl->dDesc; pp->tabLen = pl->tabLen;
     const int rowFloats = rawMel ? pl->num : pl->ccNum;
     int bulk = rowFloats % 4 == 0 && (reinterpret_cast<uintptr_t>(out) & 15) == 0;
     for (int d = 0; d < nPeer; d++) if (reinterpret_cast<uintptr_t>(peerOut[d]) & 15) bulk = 0;
@@ -623,18 +742,22 @@ static int launch_fused2(void *plan, const float *data, int dataLength, int batc
     for (;;) {
         int o = 0;
         const int spanFloats = (F - 1) * slideLength + kN;
-        const int pitchPairs = F | 1;
+        const int pitchPairs = kFW | 1;                          // odd: conflict-free column walks; always kFW frames wide (bank phase)
         pp->offSpan = o;    o += stages * spanFloats * 4;
         pp->offScratch = o; o += kFW * kScratchFloats * 4;
-        pp->offP = o;       o += kPairs * pitchPairs * 8;
+        pp->offP = o;       o += (kPairs * pitchPairs * 8 + 15) & ~15;
         pp->offWin = o;     o += 32 * 32 * 8;
         pp->offTw = o;      o += 17 * 32 * 8;
         pp->offSpec = o;    o += 2 * 32 * kSpecPitch * 8;
         pp->offDct = o;     o += rawMel ? 0 : kMaxNum * pp->dctPitch * 4;
-        pp->offL = o;       o += rawMel ? 0 : 16 * kLPitch * 4;
+        pp->offL = o;       o += 2 * 16 * kLPitch * 4;
+        pp->offG = o;       o += 16 * kLPitch * 4;
         pp->stageBytes = rawMel ? 2 * ((F * (pl->num + 4) * 4 + 15) & ~15) : ((F * pl->ccNum * 4 + 15) & ~15);
         pp->offStage = o;   o += pp->stageBytes;
-        pp->offBar = o;     o += 8 * 8;
+        pp->offBar = o;     o += 12 * 8;
+        pp->offTab = o;     o += pl->tabLen * 16;
+        pp->offDesc = o;    o += (kMaxNum + 4) * 4;
+        pp->offAssign = o;  o += (kMaxPass * kEW * 32 * 2 + 15) & ~15;
         total = o;
         pp->spanFloats = spanFloats; pp->pitchPairs = pitchPairs;
         if (total <= budget) break;
@@ -678,14 +801,16 @@ extern "C" int af_launch_mel2(void *plan, const float *data, int dataLength, int
     return launch_fused2(plan, data, dataLength, batch, timeLength, slideLength, 0, out, 0, NULL, 1, stream);
 }
 
-// Diagnostic / test hook (host only): the interval form the planner derives from a bank [num][1025].
-// Returns the number of table entries (>= 0) or -1 when the bank does not have the two-overlap structure.
+// Diagnostic / test hook (host only): the interval form the planner derives from a bank [num][1025] and the lane
+// assignment of the bank passes.  Returns the number of table entries (>= 0) or -1 when the bank does not have the
+// two-overlap structure.  assign: [passes][helper lanes] interval per lane (0xffff = none), info = {passes, helper lanes,
+// passLen[0..passes)}.
 extern "C" int afb200_mfccBankPlan2(const float *bank, int num, int *owner /* 1025 */, unsigned *desc /* num+2 */,
-                                    float *table /* 4 * 1408 */, int *first /* helper warps + 1 */, int *helperWarps) {
+                                    float *table /* 4 * 1408 */, unsigned short *assign /* 8 * 128 */, int *info /* 16 */) {
     if (!bank || num < 1 || num > kMaxNum) return -1;
     Intervals *iv = static_cast<Intervals *>(malloc(sizeof(Intervals)));
     float4 *tab = static_cast<float4 *>(malloc(sizeof(float4) * kMaxTab));
-    unsigned d[kMaxNum + 2];
+    unsigned d[kMaxNum + 4];
     int n = -1;
     if (iv && tab && build_intervals2(bank, num, iv)) {
         n = build_table(bank, num, iv, d, tab);
@@ -693,10 +818,11 @@ extern "C" int afb200_mfccBankPlan2(const float *bank, int num, int *owner /* 10
             if (owner) memcpy(owner, iv->owner, sizeof(int) * kBins);
             if (desc) memcpy(desc, d, sizeof(unsigned) * (size_t)(num + 2));
             if (table) memcpy(table, tab, sizeof(float4) * (size_t)n);
-            int f[kEW + 1];
-            split_filters(num, d, f);
-            if (first) memcpy(first, f, sizeof(f));
-            if (helperWarps) *helperWarps = kEW;
+            unsigned short as[kMaxPass * kEW * 32];
+            int pl[kMaxPass];
+            const int np = plan_passes(num, d, as, pl);
+            if (assign) memcpy(assign, as, sizeof(unsigned short) * (size_t)np * kEW * 32);
+            if (info) { info[0] = np; info[1] = kEW * 32; for (int i = 0; i < np; i++) info[2 + i] = pl[i]; }
         }
     }
     free(iv); free(tab);

@@ -117,7 +117,8 @@ int afb200_mfccIntervalPlan(const float *bank, int num, const float *gain, int *
  * returns the number of float4 table entries (rise[2q], rise[2q+1], fall[2q], fall[2q+1]) or -1 when some bin is
  * covered by more than two, or by non-consecutive, filters.  desc[i] = (first bin pair << 16) | table offset. */
 int afb200_mfccBankPlan2(const float *bank, int num, int *owner /* 1025 */, unsigned *desc /* num + 2 */,
-                         float *table /* 4 x 1408 */, int *first /* helper warps + 1 */, int *helperWarps);
+                         float *table /* 4 x 1408 */, unsigned short *assign /* passes x helper lanes: interval of each lane,
+                         0xffff = none */, int *info /* passes, helper lanes, longest interval of each pass */);
 /* chroma_cqtFilterBank (src/filterbank/chroma_filterBank.c:176-262): bank num x cqtLength */
 int afb200_chromaCqtFilterBank(int num, int cqtLength, int binPerOctave, float minFre, float *bank);
 

@@ -33,7 +33,7 @@ def test_cqt_config3_full_batch_device(cuda_device):
         r1, i1 = c.cqt_batch(x[i:i + 1].contiguous())
         torch.cuda.synchronize()
         assert torch.equal(re[i], r1[0]) and torch.equal(im[i], i1[0]), f"clip {i} of the full batch differs from the single-clip result"
-    wr, wi = O.cqt(x[1023].cpu().numpy(), 84, 48000)
+    wr, wi = O.cqt(x[1023].cpu().numpy(), 84, 48000, norm=O.NORM_AREA)
     got = re[1023].cpu().numpy() + 1j * im[1023].cpu().numpy()
     assert float(np.abs(got - (wr + 1j * wi)).max() / np.abs(wr + 1j * wi).max()) < TOL
 
@@ -51,7 +51,7 @@ def test_cqt_host_pipeline_chunk_boundaries(cuda_device):
     for i in idx:
         r1, i1 = c.cqt_planes(x[i])
         assert np.array_equal(re[i], r1) and np.array_equal(im[i], i1), f"clip {i} (chunk size {per}) differs from the single-clip call"
-    wr, wi = O.cqt(x[idx[2]], 84, 48000)
+    wr, wi = O.cqt(x[idx[2]], 84, 48000, norm=O.NORM_AREA)
     assert rel_max(re[idx[2]], wr) < TOL and rel_max(im[idx[2]], wi) < TOL
 
 

@@ -237,35 +237,33 @@ def _bank_plan2(lib, bank):
     owner = np.zeros(1025, np.int32)
     desc = np.zeros(num + 2, np.uint32)
     table = np.zeros((1408, 4), np.float32)
-    first = np.zeros(9, np.int32)
-    hw = np.zeros(1, np.int32)
+    assign = np.zeros(8 * 128, np.uint16)
+    info = np.zeros(16, np.int32)
     n = lib.afb200_mfccBankPlan2(bank.ctypes.data, num, owner.ctypes.data, desc.ctypes.data, table.ctypes.data,
-                                 first.ctypes.data, hw.ctypes.data)
-    return n, owner, desc, table, first[:hw[0] + 1]
+                                 assign.ctypes.data, info.ctypes.data)
+    passes, lanes = int(info[0]), int(info[1])
+    return n, owner, desc, table, assign[:passes * lanes].reshape(passes, lanes) if n >= 0 else None, info[2:2 + passes]
 
 
 def _plan2_mel(num, P, plan):
-    """the helper warps' loop (mfcc_fused2.cu, bank phase) in float64: filters [first[e], first[e+1]) per warp"""
-    n, owner, desc, table, first = plan
+    """the helper warps' two bank phases (mfcc_fused2.cu) in float64: R_i / Fl_i per interval, mel_m = R_m + Fl_{m+1}"""
+    n, owner, desc, table, assign, pass_len = plan
     Pp = np.concatenate([P, [0.0]])
-    mel = np.full(num, np.nan)
-    for e in range(len(first) - 1):
-        i0, i1 = int(first[e]), int(first[e + 1])
-        if i1 <= i0:
-            continue
-        prev = 0.0
-        for i in range(i0, i1 + 1):
-            q, j0, j1 = int(desc[i] >> 16), int(desc[i] & 0xffff), int(desc[i + 1] & 0xffff)
-            R = Fl = 0.0
+    R = np.zeros(num + 2)
+    Fl = np.zeros(num + 2)
+    for ps in range(assign.shape[0]):
+        for iv in assign[ps]:
+            if iv == 0xffff:
+                continue
+            iv = int(iv)
+            q, j0, j1 = int(desc[iv] >> 16), int(desc[iv] & 0xffff), int(desc[iv + 1] & 0xffff)
+            assert j1 - j0 <= pass_len[ps]
             for j in range(j0, j1):
                 w = table[j].astype(np.float64)
                 k = 2 * (q + j - j0)
-                R += Pp[k] * w[0] + Pp[k + 1] * w[1]
-                Fl += Pp[k] * w[2] + Pp[k + 1] * w[3]
-            if i > i0:
-                mel[i - 1] = prev + Fl
-            prev = R
-    return mel
+                R[iv] += Pp[k] * w[0] + Pp[k + 1] * w[1]
+                Fl[iv] += Pp[k] * w[2] + Pp[k + 1] * w[3]
+    return R[:num] + Fl[1:num + 1]
 
 
 @pytest.mark.parametrize("scale,style,norm,num,sr", [(2, 0, 0, 128, 48000), (2, 0, 1, 128, 48000), (2, 0, 2, 128, 48000),
@@ -277,10 +275,18 @@ def test_mfcc_bank_plan2_reproduces_the_bank(product_lib, scale, style, norm, nu
     lo, hi, _, _ = O.bft_revise_range(num, 2048, sr, None, None, scale, 12)
     bank, _, _ = O.auditory_filterbank(num, 2048, sr, scale, style, norm, float(lo), float(hi), 12)
     plan = _bank_plan2(product_lib, bank)
-    n, owner, desc, table, first = plan
+    n, owner, desc, table, assign, pass_len = plan
     assert 0 <= n <= 1408
     assert (np.diff(owner[owner >= 0]) >= 0).all()                 # intervals are runs of consecutive bins
-    assert first[0] == 0 and first[-1] == num and (np.diff(first) >= 0).all()
+    got_iv = np.sort(assign[assign != 0xffff])
+    assert np.array_equal(got_iv, np.arange(num + 1))              # every interval 0..num is walked by exactly one lane
+    assert (np.diff(pass_len) <= 0).all()                          # longest intervals first
+    if num == 128 and scale == 2:                                  # the headline bank: half-warps start in distinct bank pairs
+        for ps in range(assign.shape[0]):
+            for h in range(assign.shape[1] // 16):
+                ivs = [int(v) for v in assign[ps, 16 * h:16 * h + 16] if v != 0xffff]
+                res = [(int(desc[v]) >> 16) & 15 for v in ivs]
+                assert len(res) - len(set(res)) <= 4
     B = bank.astype(np.float64)
     rng = np.random.default_rng(0)
     for _ in range(2):
