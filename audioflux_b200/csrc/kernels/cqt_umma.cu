@@ -18,6 +18,7 @@
 // MMAs per 8 taps, the kernels pre-split on the host.  One elected thread issues 192 MMAs per 128-frame tile;
 // the other threads stage the next signal tile / run the epilogue of the co-resident CTA.
 #include <math.h>
+#include <stdlib.h>
 #include <string.h>
 #include "common.cuh"
 
@@ -36,6 +37,7 @@ struct UmmaParams {
     float *outRe, *outIm; long long outStride; int num, colOff;
     int mode;                      // 0: hop 4 (no swizzle), 1: hop 8 (32B), 2: hop 16 (64B), 3: hop 32 * planes (128B)
     int planes, rowsPerPlane, sigBytes;   // mode 3: phase planes and rows (128 B each) per plane; bytes of one signal copy
+    int boMode;                    // descriptor base_offset of row-shifted views: 0 = none (absolute-address swizzle), 1 = +rows, 2 = -rows
 };
 
 __device__ __forceinline__ uint64_t umma_desc(uint32_t smemAddr, uint32_t lboBytes, uint32_t sboBytes, uint32_t layout, uint32_t baseOff) {
@@ -167,6 +169,7 @@ __global__ void __launch_bounds__(128) k_cqt_octave_umma(UmmaParams p) {
                     offA = (uint32_t)n0 * 4u;                      // atom row = n0 * 4 / rowPitch rows down, (n0 * 4) % rowPitch inside
                     baseOffA = (offA >> 7) & 7u;
                 }
+                baseOffA = p.boMode == 0 ? 0u : p.boMode == 1 ? baseOffA : ((8u - baseOffA) & 7u);
                 const uint64_t dAhi = umma_desc(aHi + offA, lboA, sboA, layoutA, baseOffA);
                 const uint64_t dAlo = umma_desc(aLo + offA, lboA, sboA, layoutA, baseOffA);
                 // B: K-major 128B-swizzled [32 n][128 k] image: K atom (32 taps) = 4096 B, 32-byte step inside
@@ -261,6 +264,7 @@ extern "C" int af_launch_cqt_octave_umma(const float *sig, int sigStride, int ba
     p.outRe = outRe; p.outIm = outIm; p.outStride = (long long)timeLength * num; p.num = num; p.colOff = colOff;
     p.mode = hop == 4 ? 0 : hop == 8 ? 1 : hop == 16 ? 2 : 3;
     p.planes = hop >= 32 ? hop / 32 : 1;
+    { const char *bo = getenv("AFB200_UMMA_BO"); p.boMode = bo ? atoi(bo) : 0; }
     const int span = (kUmmaM - 1) * hop + fftLength;               // samples a tile touches
     if (p.mode == 3) {
         p.rowsPerPlane = ((kUmmaM + fftLength / 32 / p.planes + 1 + 7) / 8) * 8;   // rows u = t + j / planes, padded to whole 8-row groups

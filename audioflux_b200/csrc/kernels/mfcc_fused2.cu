@@ -44,7 +44,7 @@ constexpr int kPairs = 513;         // bin pairs of the power-spectrum tile
 #define AF2_DCT_WARPS 3
 #endif
 #ifndef AF2_ABLATE
-#define AF2_ABLATE 0                // diagnostic timing builds: 1 no bank, 4 no FFTs, 8 no transposes, 16 no loads
+#define AF2_ABLATE 0                // diagnostic timing builds: 1 no bank, 2 no DCT, 4 no FFTs, 8 no transposes, 16 no loads
 #endif
 constexpr int kFW = AF2_FRAME_WARPS;            // frame warps = max frames per tile (<= 16: one mma M tile)
 constexpr int kBW = AF2_BANK_WARPS;             // filter-bank warps (one interval per lane)
@@ -352,7 +352,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_mfcc_fused2(const __grid_consta
         : "+f"(ACC[0]), "+f"(ACC[1]), "+f"(ACC[2]), "+f"(ACC[3])                                              \
         : "r"(A0), "r"(A1), "r"(A2), "r"(A3), "r"(B0), "r"(B1))
 #pragma unroll 2
-            for (int k0 = 0; k0 < kMaxNum; k0 += 8) {
+            for (int k0 = 0; k0 < ((AF2_ABLATE & 2) ? 8 : kMaxNum); k0 += 8) {
                 const float af[4] = {L[g * kLPitch + k0 + t], L[(g + 8) * kLPitch + k0 + t],
                                      L[g * kLPitch + k0 + t + 4], L[(g + 8) * kLPitch + k0 + t + 4]};
                 uint32_t ah[4], al[4];

@@ -1000,3 +1000,112 @@ def pwt(x, num=84, radix2_exp=12, sr=32000, low=None, high=None, bpo=12, scale=S
     bank[:, :Lf // 2 + 1] = half
     re, im = cwt(x, num, radix2_exp, sr, is_pad=is_pad, bank=bank, det=det)
     return re, im, fre, bins
+
+
+# ---------------------------------------------------------------------------
+# Synchrosqueezing: WSST (src/wsst_algorithm.c:64-352) and Synsq (src/synsq_algorithm.c:38-300)
+# ---------------------------------------------------------------------------
+def _complex_div(ar, ai, br, bi):
+    """__complexDiv (src/vector/flux_complex.c): (ar + i ai) / (br + i bi), float32 arithmetic"""
+    ar, ai, br, bi = (np.asarray(v, dtype=f32) for v in (ar, ai, br, bi))
+    with np.errstate(divide="ignore", invalid="ignore"):
+        den = (br * br + bi * bi).astype(f32)
+        re = ((ar * br + ai * bi).astype(f32) / den).astype(f32)
+        im = ((ai * br - ar * bi).astype(f32) / den).astype(f32)
+    return re, im
+
+
+def squeeze_index(inst_fre, fre_arr, sr, scale, num):
+    """row index of an instantaneous frequency (cycles / sample): wsst_algorithm.c:268-296, synsq_algorithm.c:167-193.
+    Octave / Log: round((log2|f| - log2 fmin) num / (log2 fmax - log2 fmin)); Linear / Linspace: round(|f - fmin| num /
+    (fmax - fmin)); Mel / Bark / Erb: nearest band (`__arr_roundIndex`, -1 outside).  int conversion of NaN / inf as C
+    does it on x86 (INT_MIN)."""
+    f = np.asarray(inst_fre, dtype=f32)
+    fre = np.asarray(fre_arr, dtype=f32)
+    with np.errstate(divide="ignore", invalid="ignore", over="ignore"):
+        if scale in (SCALE_OCTAVE, SCALE_LOG):
+            fmin, fmax = f32(fre[0] / f32(sr)), f32(fre[num - 1] / f32(sr))
+            v = np.round(((np.log2(np.abs(f)).astype(f32) - np.log2(fmin)) * f32(num) / (np.log2(fmax) - np.log2(fmin))).astype(f32))
+        elif scale in (SCALE_LINEAR, SCALE_LINSPACE):
+            fmin, fmax = f32(fre[0] / f32(sr)), f32(fre[num - 1] / f32(sr))
+            v = np.round((np.abs(f - fmin) * f32(num) / (fmax - fmin)).astype(f32))
+        else:
+            arr = (fre / f32(sr)).astype(f32)
+            a = np.abs(f)
+            idx = np.full(f.shape, -1, dtype=np.int64)
+            j = np.searchsorted(arr, a, side="right") - 1          # arr[j] <= a < arr[j + 1]
+            ok = (j >= 0) & (j < num - 1)
+            jj = np.clip(j, 0, num - 2)
+            left, right = a - arr[jj], arr[jj + 1] - a
+            idx[ok] = np.where(left < right, jj, jj + 1)[ok]
+            return idx
+    out = np.full(f.shape, np.iinfo(np.int32).min, dtype=np.int64)
+    fin = np.isfinite(v) & (np.abs(v) < 2 ** 31)
+    out[fin] = v[fin].astype(np.int64)
+    return out
+
+
+def squeeze_scatter(re, im, idx, thresh):
+    """out[idx[i, j], j] += W[i, j] for rows i in ascending order where 0 <= idx < num and |W|^2 > thresh^2
+    (wsst_algorithm.c:318-341): float32 accumulation in the reference's order"""
+    num, n = re.shape
+    o_re = np.zeros((num, n), dtype=f32)
+    o_im = np.zeros((num, n), dtype=f32)
+    cols = np.arange(n)
+    t2 = f32(thresh) * f32(thresh)
+    for i in range(num):
+        v1, v2 = re[i].astype(f32), im[i].astype(f32)
+        ok = (idx[i] >= 0) & (idx[i] < num) & ((v1 * v1 + v2 * v2).astype(f32) > t2)
+        r = idx[i][ok]
+        o_re[r, cols[ok]] += v1[ok]
+        o_im[r, cols[ok]] += v2[ok]
+    return o_re, o_im
+
+
+def wsst(x, num=84, radix2_exp=12, sr=32000, wavelet=WAVE_MORLET, scale=SCALE_OCTAVE, low=None, high=None, bpo=12,
+         gamma=None, beta=None, thresh=0.001, is_pad=False, cwt_planes=None):
+    """`wsstObj_wsst` (order 1) -> (re, im, cwt_re, cwt_im), each [num, N] in the reference's row order.
+    cwt_planes = (W_re, W_im, dW_re, dW_im) overrides the transforms (used to test the squeezing alone)."""
+    if cwt_planes is None:
+        w_re, w_im = cwt(x, num, radix2_exp, sr, wavelet, scale, low, high, bpo, gamma, beta, is_pad)
+        d_re, d_im = cwt(x, num, radix2_exp, sr, wavelet, scale, low, high, bpo, gamma, beta, is_pad, det=True)
+    else:
+        w_re, w_im, d_re, d_im = cwt_planes
+    _, fre = cwt_filterbank(num, 1 << radix2_exp, sr, wavelet, scale, low, high, bpo, gamma, beta, 0)
+    _, ph = _complex_div(d_re, d_im, w_re, w_im)
+    ph = (ph / f32(2 * math.pi)).astype(f32)
+    idx = squeeze_index(ph, fre, sr, scale, num)
+    o_re, o_im = squeeze_scatter(w_re, w_im, idx, thresh)
+    return o_re, o_im, w_re, w_im
+
+
+def unwrap_rows(p):
+    """`__vunwrap` in place along the last axis (src/vector/flux_vector.c:1792-1830): float32 storage, the correction
+    t * 2 pi evaluated in double as the C expression does"""
+    p = np.array(p, dtype=f32)
+    two_pi = 2 * math.pi
+    for r in range(p.shape[0]):
+        a = p[r]
+        for i in range(1, a.shape[0]):
+            sub = float(f32(abs(f32(a[i] - a[i - 1]))))
+            if sub >= math.pi:
+                t = int(math.floor(float(f32(sub / two_pi))))        # floorf(double) -> the argument is rounded to float
+                mod = float(f32(sub - t * two_pi))
+                if mod > math.pi:
+                    t += 1
+                a[i] = f32(float(a[i]) - t * two_pi) if a[i] > a[i - 1] else f32(float(a[i]) + t * two_pi)
+    return p
+
+
+def synsq(fre_arr, re, im, sr=32000, scale=SCALE_OCTAVE, thresh=0.001):
+    """`synsqObj_synsq` (order 1): phase = atan2f(re, im) (the reference's argument order), unwrap along time, first
+    difference (last column repeated), / 2 pi, index, scatter -> (re, im) [num, N]"""
+    re, im = np.asarray(re, dtype=f32), np.asarray(im, dtype=f32)
+    num, n = re.shape
+    ph = unwrap_rows(np.arctan2(re, im).astype(f32))
+    d = np.zeros_like(ph)
+    d[:, 1:] = (ph[:, 1:] - ph[:, :-1]).astype(f32)
+    d[:, n - 1] = d[:, n - 2]
+    d = (d / f32(2 * math.pi)).astype(f32)
+    idx = squeeze_index(d, fre_arr, sr, scale, num)
+    return squeeze_scatter(re, im, idx, thresh)
