@@ -11,6 +11,7 @@ from .xxcc import XXCC  # noqa: F401
 from .cqt import CQT  # noqa: F401
 from .cwt import CWT  # noqa: F401
 from .pwt import PWT  # noqa: F401
+from .wsst import WSST, Synsq  # noqa: F401
 from .spectrogram import Spectrogram, MelSpectrogram, BarkSpectrogram, ErbSpectrogram  # noqa: F401
 from . import lib  # noqa: F401
 

@@ -79,6 +79,17 @@ REFERENCE_API = {
     "pwtObj_enableDet": (None, [vp, C.c_int]),
     "pwtObj_pwtDet": (None, [vp, vp, vp, vp]),
     "pwtObj_free": (None, [vp]),
+    # synchrosqueezing (src/wsst_algorithm.h, src/synsq_algorithm.h)
+    "wsstObj_new": (C.c_int, [P(vp), C.c_int, C.c_int, c_int_p, c_float_p, c_float_p, c_int_p, c_int_p, c_int_p,
+                              c_float_p, c_float_p, c_float_p, c_int_p]),
+    "wsstObj_getFreBandArr": (vp, [vp]),
+    "wsstObj_getBinBandArr": (vp, [vp]),
+    "wsstObj_setOrder": (None, [vp, C.c_int]),
+    "wsstObj_wsst": (None, [vp, vp, vp, vp, vp, vp]),
+    "wsstObj_free": (None, [vp]),
+    "synsqObj_new": (C.c_int, [P(vp), C.c_int, C.c_int, c_int_p, c_int_p, c_float_p]),
+    "synsqObj_synsq": (None, [vp, vp, C.c_int, vp, vp, vp, vp]),
+    "synsqObj_free": (None, [vp]),
     # ---- Spectrogram (front door; src/spectrogram_algorithm.h:40-119)
     "spectrogramObj_new": (C.c_int, [P(vp), C.c_int, c_int_p, c_float_p, c_float_p, c_int_p, c_int_p, c_int_p,
                                      c_int_p, c_int_p, c_int_p, c_int_p, c_int_p, c_int_p]),
@@ -141,6 +152,8 @@ EXTENSION_API = {
     "pwtObj_pwtBatch": (C.c_int, [vp, vp, C.c_int, vp, vp, C.c_int, vp]),
     "pwtObj_pwtDetBatch": (C.c_int, [vp, vp, C.c_int, vp, vp, C.c_int, vp]),
     "pwtObj_getFilterBankArr": (C.c_int, [vp, vp]),
+    "wsstObj_wsstDevice": (C.c_int, [vp, vp, vp, vp, vp, vp, vp]),
+    "synsqObj_synsqDevice": (C.c_int, [vp, vp, C.c_int, vp, vp, vp, vp, vp]),
     "afb200_window": (C.c_int, [C.c_int, C.c_int, vp]),
     "afb200_auditoryFilterBank": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
                                             C.c_float, C.c_float, C.c_int, vp, vp, vp]),

@@ -245,6 +245,14 @@ int af_bft_phase(BFTObj b, const float *data, int dataLength, int batch, int low
                  int memKind, void *stream);
 int af_launch_phase(const float *re, const float *im, int rows, int width, int lo, int count, float *out, void *stream);
 
+/* synchrosqueezing (kernels/squeeze.cu): row index of the instantaneous frequency, row scatter */
+int af_launch_wsst_index(const float *wr, const float *wi, const float *dr, const float *di, int num, int n, int scaleType,
+                         float fre0, float freLast, int samplate, const float *dNorm, int *idx, void *stream);
+int af_launch_synsq_index(const float *re, const float *im, int num, int n, int scaleType, float fre0, float freLast,
+                          int samplate, const float *dNorm, int *idx, void *stream);
+int af_launch_squeeze_scatter(const float *re, const float *im, const int *idx, int num, int n, float thresh,
+                              float *outRe, float *outIm, void *stream);
+
 void af_count_launch(int n);
 
 #ifdef __cplusplus

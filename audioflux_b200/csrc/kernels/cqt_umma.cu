@@ -28,6 +28,7 @@ constexpr int kUmmaM = 128;          // frames per tile (TMEM lanes)
 constexpr int kUmmaN = 32;           // accumulator columns (24 used: 12 bins x (re, im))
 constexpr int kUmmaChunkK = 128;     // taps per kernel chunk in shared memory
 constexpr int kUmmaBBytes = kUmmaN * kUmmaChunkK * 4;      // one part (hi or lo) of one chunk: 16 KB
+constexpr int kUmmaThreads = 256;    // 8 warps stage the signal; warp 0 lane 0 issues the MMAs; warps 0-3 run the epilogue
 
 struct UmmaParams {
     const float *sig; long long sigStride; int validLength;
@@ -35,7 +36,8 @@ struct UmmaParams {
     const unsigned char *bimg;     // [N / 128 chunks][2 parts (hi, lo)][16 KB] pre-swizzled shared-memory images of B
     const float *scale;            // [12]
     float *outRe, *outIm; long long outStride; int num, colOff;
-    int mode;                      // 0: hop 4 (no swizzle), 1: hop 8 (32B), 2: hop 16 (64B), 3: hop 32 * planes (128B)
+    int mode;                      // 0: hop 4 (no swizzle), 1: hop 8 (32B), 2: hop 16 (64B), 3: hop 32 * planes (128B),
+                                   // 4: hop 2 = two hop-4 problems (even / odd frames; the odd one reads a copy shifted by 2 samples)
     int planes, rowsPerPlane, sigBytes;   // mode 3: phase planes and rows (128 B each) per plane; bytes of one signal copy
     int boMode;                    // descriptor base_offset of row-shifted views: 0 = none (absolute-address swizzle), 1 = +rows, 2 = -rows
 };
@@ -63,7 +65,7 @@ __device__ __forceinline__ void umma_commit(uint64_t *bar) {
 
 // byte offset of sample s (floats from the tile start) inside one signal copy
 __device__ __forceinline__ uint32_t sig_offset(const UmmaParams &p, int s) {
-    if (p.mode == 0) return (uint32_t)s * 4u;
+    if (p.mode == 0 || p.mode == 4) return (uint32_t)s * 4u;
     uint32_t a;
     if (p.mode == 3) {
         const int row = s >> 5, kk = s & 31;                       // 128-byte rows of 32 samples
@@ -76,7 +78,7 @@ __device__ __forceinline__ uint32_t sig_offset(const UmmaParams &p, int s) {
     return a ^ (((a >> 7) & 1u) << 4);                              // 32B swizzle: bit 4 ^= bit 7
 }
 
-__global__ void __launch_bounds__(128) k_cqt_octave_umma(UmmaParams p) {
+__global__ void __launch_bounds__(kUmmaThreads) k_cqt_octave_umma(UmmaParams p) {
     extern __shared__ __align__(1024) unsigned char smem[];
     // [B buffers: 2 x (hi 16 KB, lo 16 KB)] [signal hi copy] [signal lo copy] [barriers] [tmem address]
     unsigned char *sB = smem;
@@ -87,9 +89,12 @@ __global__ void __launch_bounds__(128) k_cqt_octave_umma(UmmaParams p) {
     uint32_t *tmemSlot = reinterpret_cast<uint32_t *>(bars + 6);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int clip = blockIdx.y, t0 = blockIdx.x * kUmmaM;
+    const int par2 = p.mode == 4 ? 2 : 1;                           // frame parities per tile (hop 2: even and odd frames)
+    const int clip = blockIdx.y, t0 = blockIdx.x * kUmmaM * par2;
     const int h = p.hop, N = p.N;
     const int chunks = N / kUmmaChunkK;
+    // hop 2: [hi copy 0][hi copy 1 (shifted by 2 samples)] [lo copy 0][lo copy 1]
+    const int copyBytes = p.mode == 4 ? p.sigBytes / 2 : p.sigBytes;
 
     if (threadIdx.x == 0) {
         for (int i = 0; i < 2; i++) { af_mbar_init(&bFull[i], 1); af_mbar_init(&bEmpty[i], 1); }
@@ -97,7 +102,7 @@ __global__ void __launch_bounds__(128) k_cqt_octave_umma(UmmaParams p) {
         af_fence_barrier_init();
     }
     if (warp == 0) {
-        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(af_smem_u32(tmemSlot)), "n"(32) : "memory");
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(af_smem_u32(tmemSlot)), "n"(64) : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
     __syncthreads();
@@ -108,28 +113,36 @@ __global__ void __launch_bounds__(128) k_cqt_octave_umma(UmmaParams p) {
         }
     }
 
-    // ---- stage the tile's span of the zero-padded signal: hi / lo copies through the layout's swizzle ----
+    // ---- stage the tile's span of the zero-padded signal: hi / lo copies through the layout's swizzle.  Four samples at
+    // a time: they share a 16-byte chunk, and every swizzle permutes whole 16-byte chunks (LDG.128 -> 2 STS.128) ----
     {
         const float *sig = p.sig + (long long)clip * p.sigStride;
-        const int span = (kUmmaM - 1) * h + N;
         const long long m0 = (long long)t0 * h - N / 2;
-        const int total = p.sigBytes / 4;                          // whole copy (tail beyond the span = zeros)
-        for (int i0 = threadIdx.x; i0 < total; i0 += 4 * 128) {
-            float v[4];
+        const int total = copyBytes / 4;                            // whole copy (tail beyond the span = zeros)
+        const bool vec = ((p.sigStride & 3) == 0) && ((reinterpret_cast<uintptr_t>(p.sig) & 15) == 0) && ((m0 & 3) == 0);
+        for (int cp = 0; cp < par2; cp++) {
+            const long long mc = m0 + 2 * cp;                       // copy 1 of hop 2: the signal advanced by 2 samples
+            unsigned char *dHi = sHi + cp * copyBytes, *dLo = sLo + cp * copyBytes;
+            for (int i = threadIdx.x * 4; i < total; i += 4 * kUmmaThreads) {
+                float v[4];
+                const long long m = mc + i;
+                if (vec && cp == 0 && m >= 0 && m + 3 < p.validLength) {
+                    const float4 q = *reinterpret_cast<const float4 *>(sig + m);
+                    v[0] = q.x; v[1] = q.y; v[2] = q.z; v[3] = q.w;
+                } else {
 #pragma unroll
-            for (int u = 0; u < 4; u++) {
-                const int i = i0 + u * 128;
-                const long long m = m0 + i;
-                v[u] = (i < span && m >= 0 && m < p.validLength) ? sig[m] : 0.0f;
-            }
+                    for (int u = 0; u < 4; u++) v[u] = (m + u >= 0 && m + u < p.validLength) ? sig[m + u] : 0.0f;
+                }
+                float4 hi4, lo4;
+                float *hp = reinterpret_cast<float *>(&hi4), *lp = reinterpret_cast<float *>(&lo4);
 #pragma unroll
-            for (int u = 0; u < 4; u++) {
-                const int i = i0 + u * 128;
-                if (i >= total) continue;
-                const uint32_t off = sig_offset(p, i);
-                const float hi = __uint_as_float(__float_as_uint(v[u]) & 0xffffe000u);
-                *reinterpret_cast<float *>(sHi + off) = hi;
-                *reinterpret_cast<float *>(sLo + off) = v[u] - hi;
+                for (int u = 0; u < 4; u++) {
+                    hp[u] = __uint_as_float(__float_as_uint(v[u]) & 0xffffe000u);
+                    lp[u] = v[u] - hp[u];
+                }
+                const uint32_t off = sig_offset(p, i);               // multiple of 16
+                *reinterpret_cast<float4 *>(dHi + off) = hi4;
+                *reinterpret_cast<float4 *>(dLo + off) = lo4;
             }
         }
     }
@@ -144,7 +157,7 @@ __global__ void __launch_bounds__(128) k_cqt_octave_umma(UmmaParams p) {
         constexpr uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(kUmmaN >> 3) << 17) | ((uint32_t)(kUmmaM >> 4) << 24);
         const uint32_t aHi = af_smem_u32(sHi), aLo = af_smem_u32(sLo);
         uint32_t layoutA, sboA, lboA;
-        if (p.mode == 0) { layoutA = 0; sboA = 128; lboA = 16; }
+        if (p.mode == 0 || p.mode == 4) { layoutA = 0; sboA = 128; lboA = 16; }
         else if (p.mode == 1) { layoutA = 6; sboA = 256; lboA = 0; }
         else if (p.mode == 2) { layoutA = 4; sboA = 512; lboA = 0; }
         else { layoutA = 2; sboA = 1024; lboA = 0; }
@@ -157,28 +170,28 @@ __global__ void __launch_bounds__(128) k_cqt_octave_umma(UmmaParams p) {
 #pragma unroll 1
             for (int ks = 0; ks < kUmmaChunkK / 8; ks++) {
                 const int n0 = c * kUmmaChunkK + ks * 8;            // first tap of this K step
-                // A: Hankel view of the signal copy at tap offset n0
-                uint32_t offA, baseOffA = 0;
-                if (p.mode == 0) offA = (uint32_t)n0 * 4u;
-                else if (p.mode == 3) {
+                // A: Hankel view of the signal copy at tap offset n0.  The swizzle is an XOR on absolute address bits, so a
+                // view that starts some rows further down needs no descriptor base offset (verified on B200: base_offset 0).
+                uint32_t offA;
+                if (p.mode == 3) {
                     const int j = n0 >> 5, q = (n0 >> 3) & 3;      // 128-byte atom index along K, 32-byte step inside it
-                    const int phi = j % p.planes, dr = j / p.planes;
-                    offA = (uint32_t)(phi * p.rowsPerPlane + dr) * 128u + (uint32_t)q * 32u;
-                    baseOffA = (uint32_t)dr & 7u;
+                    offA = (uint32_t)((j % p.planes) * p.rowsPerPlane + j / p.planes) * 128u + (uint32_t)q * 32u;
                 } else {
-                    offA = (uint32_t)n0 * 4u;                      // atom row = n0 * 4 / rowPitch rows down, (n0 * 4) % rowPitch inside
-                    baseOffA = (offA >> 7) & 7u;
+                    offA = (uint32_t)n0 * 4u;
                 }
-                baseOffA = p.boMode == 0 ? 0u : p.boMode == 1 ? baseOffA : ((8u - baseOffA) & 7u);
-                const uint64_t dAhi = umma_desc(aHi + offA, lboA, sboA, layoutA, baseOffA);
-                const uint64_t dAlo = umma_desc(aLo + offA, lboA, sboA, layoutA, baseOffA);
                 // B: K-major 128B-swizzled [32 n][128 k] image: K atom (32 taps) = 4096 B, 32-byte step inside
                 const uint32_t offB = (uint32_t)(ks >> 2) * 4096u + (uint32_t)(ks & 3) * 32u;
                 const uint64_t dBhi = umma_desc(bBase + offB, 0, 1024, 2, 0);
                 const uint64_t dBlo = umma_desc(bBase + kUmmaBBytes + offB, 0, 1024, 2, 0);
-                umma_tf32(tmemD, dAlo, dBhi, idesc, acc); acc = 1;
-                umma_tf32(tmemD, dAhi, dBlo, idesc, 1);
-                umma_tf32(tmemD, dAhi, dBhi, idesc, 1);
+                for (int cp = 0; cp < par2; cp++) {
+                    const uint64_t dAhi = umma_desc(aHi + cp * copyBytes + offA, lboA, sboA, layoutA, 0);
+                    const uint64_t dAlo = umma_desc(aLo + cp * copyBytes + offA, lboA, sboA, layoutA, 0);
+                    const uint32_t d = tmemD + (uint32_t)cp * kUmmaN;
+                    umma_tf32(d, dAlo, dBhi, idesc, acc);
+                    umma_tf32(d, dAhi, dBlo, idesc, 1);
+                    umma_tf32(d, dAhi, dBhi, idesc, 1);
+                }
+                acc = 1;
             }
             if (c + 2 < chunks) {                                   // refill this buffer once its MMAs have read it
                 umma_commit(&bEmpty[buf]);
@@ -191,35 +204,39 @@ __global__ void __launch_bounds__(128) k_cqt_octave_umma(UmmaParams p) {
     }
     __syncwarp();
 
-    // ---- epilogue: TMEM lane = frame, 24 columns = (re, im) of the 12 bins ----
-    af_mbar_wait(accFull, 0);
-    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-    uint32_t r[32];
-    const uint32_t taddr = tmemD + ((uint32_t)(warp * 32) << 16);
-    asm volatile(
-        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
-        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
-        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
-        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
-          "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
-          "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
-          "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
-        : "r"(taddr));
-    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-    const int t = t0 + warp * 32 + lane;
-    if (t < p.T) {
-        const long long o = (long long)clip * p.outStride + (long long)t * p.num + p.colOff;
+    // ---- epilogue (warps 0-3): TMEM lane = frame (of one parity), 24 columns = (re, im) of the 12 bins ----
+    if (warp < 4) {
+        af_mbar_wait(accFull, 0);
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        for (int cp = 0; cp < par2; cp++) {
+            uint32_t r[32];
+            const uint32_t taddr = tmemD + ((uint32_t)(warp * 32) << 16) + (uint32_t)cp * kUmmaN;
+            asm volatile(
+                "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+                "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+                "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+                : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+                  "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
+                  "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
+                  "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+                : "r"(taddr));
+            asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+            const int t = t0 + (warp * 32 + lane) * par2 + cp;
+            if (t < p.T) {
+                const long long o = (long long)clip * p.outStride + (long long)t * p.num + p.colOff;
 #pragma unroll
-        for (int j = 0; j < 12; j++) {
-            const float s = p.scale[j];
-            p.outRe[o + j] = __uint_as_float(r[2 * j]) * s;
-            p.outIm[o + j] = __uint_as_float(r[2 * j + 1]) * s;
+                for (int j = 0; j < 12; j++) {
+                    const float s = p.scale[j];
+                    p.outRe[o + j] = __uint_as_float(r[2 * j]) * s;
+                    p.outIm[o + j] = __uint_as_float(r[2 * j + 1]) * s;
+                }
+            }
         }
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
     if (warp == 0)
-        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmemD), "n"(32) : "memory");
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmemD), "n"(64) : "memory");
 }
 
 }  // namespace
@@ -246,9 +263,29 @@ extern "C" void af_cqt_umma_bimage(const float *kappa2 /* [12][N] (re, im) */, i
             }
 }
 
+// tile geometry: mode, phase planes, bytes of the staged signal (all copies of one precision) and the dynamic shared memory
+static size_t cqt_umma_geometry(int fftLength, int hop, int *mode, int *planes, int *rowsPerPlane, int *sigBytes) {
+    *mode = hop == 2 ? 4 : hop == 4 ? 0 : hop == 8 ? 1 : hop == 16 ? 2 : 3;
+    *planes = hop >= 32 ? hop / 32 : 1;
+    *rowsPerPlane = 0;
+    if (*mode == 3) {
+        *rowsPerPlane = ((kUmmaM + fftLength / 32 / *planes + 1 + 7) / 8) * 8;     // rows u = t + j / planes, whole 8-row groups
+        *sigBytes = *planes * *rowsPerPlane * 128;
+    } else if (*mode == 4) {
+        const int span = (kUmmaM - 1) * 4 + fftLength;                                // each parity is a hop-4 problem
+        *sigBytes = 2 * (((span * 4 + 1023) / 1024) * 1024);                          // two copies (shift 0 / 2 samples)
+    } else {
+        const int span = (kUmmaM - 1) * hop + fftLength;
+        *sigBytes = ((span * 4 + 1023) / 1024) * 1024;
+    }
+    return (size_t)2 * 2 * kUmmaBBytes + 2 * (size_t)*sigBytes + 64;
+}
+
 extern "C" int af_cqt_umma_supported(int fftLength, int hop, int bpo) {
-    return bpo == 12 && fftLength % kUmmaChunkK == 0 && fftLength >= 2 * kUmmaChunkK &&
-           (hop == 4 || hop == 8 || hop == 16 || hop == 32 || hop == 64 || hop == 128);
+    if (bpo != 12 || fftLength % kUmmaChunkK != 0 || fftLength < 2 * kUmmaChunkK) return 0;
+    if (!(hop == 2 || hop == 4 || hop == 8 || hop == 16 || hop == 32 || hop == 64 || hop == 128)) return 0;
+    int mode, planes, rpp, sb;
+    return cqt_umma_geometry(fftLength, hop, &mode, &planes, &rpp, &sb) <= (size_t)227 * 1024;
 }
 
 extern "C" int af_launch_cqt_octave_umma(const float *sig, int sigStride, int batch, int validLength, int fftLength, int hop,
@@ -262,23 +299,13 @@ extern "C" int af_launch_cqt_octave_umma(const float *sig, int sigStride, int ba
     p.N = fftLength; p.hop = hop; p.T = timeLength;
     p.bimg = bimg; p.scale = scale;
     p.outRe = outRe; p.outIm = outIm; p.outStride = (long long)timeLength * num; p.num = num; p.colOff = colOff;
-    p.mode = hop == 4 ? 0 : hop == 8 ? 1 : hop == 16 ? 2 : 3;
-    p.planes = hop >= 32 ? hop / 32 : 1;
     { const char *bo = getenv("AFB200_UMMA_BO"); p.boMode = bo ? atoi(bo) : 0; }
-    const int span = (kUmmaM - 1) * hop + fftLength;               // samples a tile touches
-    if (p.mode == 3) {
-        p.rowsPerPlane = ((kUmmaM + fftLength / 32 / p.planes + 1 + 7) / 8) * 8;   // rows u = t + j / planes, padded to whole 8-row groups
-        p.sigBytes = p.planes * p.rowsPerPlane * 128;
-    } else {
-        p.rowsPerPlane = 0;
-        p.sigBytes = ((span * 4 + 8 * 128 + 1023) / 1024) * 1024;    // the last core-matrix groups read a little past the span
-    }
-    const size_t smem = (size_t)2 * 2 * kUmmaBBytes + 2 * (size_t)p.sigBytes + 64;
-    if (smem > (size_t)227 * 1024) return af_fail(AF_ERR_UNSUPPORTED, "cqt octave (tcgen05): tile exceeds shared memory");
+    const size_t smem = cqt_umma_geometry(fftLength, hop, &p.mode, &p.planes, &p.rowsPerPlane, &p.sigBytes);
     cudaError_t e = cudaFuncSetAttribute(k_cqt_octave_umma, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return af_cuda_check(e, "cudaFuncSetAttribute(k_cqt_octave_umma)");
-    dim3 grid((unsigned)((timeLength + kUmmaM - 1) / kUmmaM), (unsigned)batch);
-    k_cqt_octave_umma<<<grid, 128, smem, (cudaStream_t)stream>>>(p);
+    const int framesPerTile = kUmmaM * (p.mode == 4 ? 2 : 1);
+    dim3 grid((unsigned)((timeLength + framesPerTile - 1) / framesPerTile), (unsigned)batch);
+    k_cqt_octave_umma<<<grid, kUmmaThreads, smem, (cudaStream_t)stream>>>(p);
     AF_LAUNCH_CHECK("k_cqt_octave_umma");
     return AF_OK;
 }

@@ -68,6 +68,7 @@ constexpr int kMaxNum = 128;        // filters (padded)
 constexpr int kScratchFloats = 1152;            // per warp: 33x32 float transpose plane, later Ps[0..1024] + zero pad
 constexpr int kPsPad = 1152;        // Ps[0..1024], zeros up to kPsPad (padded band reads)
 constexpr int kTailMax = 512;       // bins above the last filter's peak (interval mode)
+constexpr int kStageBytes = 16 * 64 * 4;   // result tile of one epilogue warp (<= 16 frames x 64 coefficients), source of the bulk stores
 
 struct Plan {                       // host-side descriptor of the device tables
     float *dWindowHalf;             // 2048, window * 0.5
@@ -105,6 +106,7 @@ struct Params {
     const float *melAux;
     int ccNum, rectify, dataType;
     int rawMel;                     // 1: stop after the bank: out[frame][num] = bank . |X|^2 (bftObj_bft real mode), no log / DCT
+    int bulkStore;                  // 1: the result tile leaves as one TMA bulk store per destination (16-byte aligned rows)
     // fused all-gather: every finished tile is also stored at the same offset of up to kMaxPeers other buffers
     // (peer GPUs' gathered arrays mapped over NVLink, opened with cudaIpcOpenMemHandle by the host side)
     int nPeer;
@@ -113,7 +115,7 @@ struct Params {
 
 // shared-memory carve-up (bytes), all 16-byte aligned
 struct Smem {
-    int spanOff, scratchOff, windowOff, tw1Off, tw2Off, melWOff, melStartOff, melAuxOff, dctOff, lOff, barOff, total;
+    int spanOff, scratchOff, windowOff, tw1Off, tw2Off, melWOff, melStartOff, melAuxOff, dctOff, lOff, stageOff, barOff, total;
 };
 
 __host__ __device__ inline Smem carve(int spanFloats, int melWFloats, int ct) {
@@ -128,6 +130,7 @@ __host__ __device__ inline Smem carve(int spanFloats, int melWFloats, int ct) {
     s.melAuxOff = o;   o += (kMaxNum + kTailMax) * 4;
     s.dctOff = o;      o += kMaxNum * (ct <= 5 ? 40 : 72) * 4;
     s.lOff = o;        o += kLBufs * kLRows * kLPitch * 4;
+    s.stageOff = o;    o += kEpiWarps * kStageBytes;
     s.barOff = o;      o += (2 * kStages + 2 * kLBufs) * 8;
     s.total = o;
     return s;
@@ -256,24 +259,53 @@ __global__ void __launch_bounds__(kThreads, kCtasPerSm) k_mfcc_fused(Params p) {
             __syncwarp();
             if (lane == 0) af_mbar_arrive(&lEmpty[buf]);           // tile consumed: frame warps may overwrite it
             // C fragment: rows g and g+8, columns n*8 + 2t, +1.  Destination 0 is this GPU's buffer, 1..nPeer the
-            // peers' (posted NVLink stores: the all-gather of the result rides on the epilogue, tile by tile)
+            // peers' (the all-gather of the result rides on the epilogue, tile by tile).  The tile is a contiguous run of
+            // nf * ccNum floats in every destination: it is staged in shared memory and leaves as ONE TMA bulk store per
+            // destination (full lines over NVLink; r1 wrote 32-bit scalars, 0.85 scaling efficiency at 8 GPUs).
             const long long tileOff = ((long long)clip * p.timeLength + f0) * p.ccNum;
-            for (int d = 0; d <= p.nPeer; d++) {
-                float *o = (d == 0 ? p.out : p.peerOut[d - 1]) + tileOff;
+            if (p.bulkStore) {
+                float *stage = reinterpret_cast<float *>(smem + L.stageOff + epi * kStageBytes);
+                asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");       // this warp's previous stores have read the staging tile
+                __syncwarp();
 #pragma unroll
                 for (int n = 0; n < CT; n++) {
                     const int c = n * 8 + 2 * t;
                     if (g < nf) {
-                        if (c < p.ccNum) o[(long long)g * p.ccNum + c] = acc[n][0];
-                        if (c + 1 < p.ccNum) o[(long long)g * p.ccNum + c + 1] = acc[n][1];
+                        if (c < p.ccNum) stage[g * p.ccNum + c] = acc[n][0];
+                        if (c + 1 < p.ccNum) stage[g * p.ccNum + c + 1] = acc[n][1];
                     }
                     if (g + 8 < nf) {
-                        if (c < p.ccNum) o[(long long)(g + 8) * p.ccNum + c] = acc[n][2];
-                        if (c + 1 < p.ccNum) o[(long long)(g + 8) * p.ccNum + c + 1] = acc[n][3];
+                        if (c < p.ccNum) stage[(g + 8) * p.ccNum + c] = acc[n][2];
+                        if (c + 1 < p.ccNum) stage[(g + 8) * p.ccNum + c + 1] = acc[n][3];
+                    }
+                }
+                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                __syncwarp();
+                if (lane <= p.nPeer) {
+                    float *o = (lane == 0 ? p.out : p.peerOut[lane - 1]) + tileOff;
+                    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;"
+                                 ::"l"(o), "r"(af_smem_u32(stage)), "r"((uint32_t)(nf * p.ccNum * 4)) : "memory");
+                    asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+                }
+            } else {
+                for (int d = 0; d <= p.nPeer; d++) {
+                    float *o = (d == 0 ? p.out : p.peerOut[d - 1]) + tileOff;
+#pragma unroll
+                    for (int n = 0; n < CT; n++) {
+                        const int c = n * 8 + 2 * t;
+                        if (g < nf) {
+                            if (c < p.ccNum) o[(long long)g * p.ccNum + c] = acc[n][0];
+                            if (c + 1 < p.ccNum) o[(long long)g * p.ccNum + c + 1] = acc[n][1];
+                        }
+                        if (g + 8 < nf) {
+                            if (c < p.ccNum) o[(long long)(g + 8) * p.ccNum + c] = acc[n][2];
+                            if (c + 1 < p.ccNum) o[(long long)(g + 8) * p.ccNum + c + 1] = acc[n][3];
+                        }
                     }
                 }
             }
         }
+        if (p.bulkStore) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
         return;
     }
 
@@ -762,6 +794,13 @@ static int launch_fused(void *plan, const float *data, int dataLength, int batch
     if (nPeer < 0 || nPeer > kMaxPeers || (nPeer > 0 && !peerOut)) return af_fail(AF_ERR_ARG, "fused MFCC: nPeer=%d outside [0, %d]", nPeer, kMaxPeers);
     p.nPeer = nPeer;
     for (int d = 0; d < nPeer; d++) p.peerOut[d] = peerOut[d];
+    {   // one bulk store per destination needs 16-byte aligned tiles: ccNum % 4 == 0 and aligned bases
+        int bulk = !rawMel && pl->ccNum % 4 == 0 && (reinterpret_cast<uintptr_t>(out) & 15) == 0;
+        for (int d = 0; d < nPeer; d++) if (reinterpret_cast<uintptr_t>(peerOut[d]) & 15) bulk = 0;
+        const char *sv = getenv("AFB200_MFCC_STORE");
+        if (sv && !strcmp(sv, "plain")) bulk = 0;
+        p.bulkStore = bulk;
+    }
 
     // frames per tile: as many as fit the shared-memory budget (<= kFrameWarps)
     const int budget = kCtasPerSm == 1 ? 227 * 1024 : (233472 - kCtasPerSm * 1024) / kCtasPerSm;

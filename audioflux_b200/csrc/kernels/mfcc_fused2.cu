@@ -38,10 +38,10 @@ constexpr int kPairs = 513;         // bin pairs of the power-spectrum tile
 #define AF2_FRAME_WARPS 13
 #endif
 #ifndef AF2_BANK_WARPS
-#define AF2_BANK_WARPS 3
+#define AF2_BANK_WARPS 4
 #endif
 #ifndef AF2_DCT_WARPS
-#define AF2_DCT_WARPS 3
+#define AF2_DCT_WARPS 2
 #endif
 #ifndef AF2_ABLATE
 #define AF2_ABLATE 0                // diagnostic timing builds: 1 no bank, 2 no DCT, 4 no FFTs, 8 no transposes, 16 no loads

@@ -327,3 +327,48 @@ def test_pwt_new_status_codes(product_lib):
     assert product_lib.pwtObj_new(C.byref(obj), 84, 19, *a) == -2                       # padding -> non power of two
     assert product_lib.pwtObj_new(C.byref(obj), 84, 12, *none) == 0
     product_lib.pwtObj_free(obj)
+
+
+# ---- synchrosqueezing: the numpy restatement (oracle wsst / synsq) pinned to the reference build -------------------------
+def _sq_signal(n, sr, seed):
+    t = np.arange(n) / sr
+    rng = np.random.default_rng(seed)
+    return (0.5 * np.sin(2 * np.pi * (300 + 2000 * t) * t) + 0.2 * np.sin(2 * np.pi * 2500 * t) + 0.01 * rng.standard_normal(n)).astype(np.float32)
+
+
+def _sq_agree(a, b):
+    cols = (np.abs(a - b) > 1e-5 * np.abs(b).max()).any(axis=0)
+    return 1.0 - cols.mean(), float(np.linalg.norm(a - b) / np.linalg.norm(b))
+
+
+@pytest.mark.parametrize("is_pad,scale,wavelet", [(False, O.SCALE_OCTAVE, O.WAVE_MORLET), (True, O.SCALE_OCTAVE, O.WAVE_MORLET),
+                                                   (False, O.SCALE_LINEAR, O.WAVE_MORSE), (False, O.SCALE_MEL, O.WAVE_BUMP)])
+def test_oracle_wsst_matches_the_reference_build(ref_lib, is_pad, scale, wavelet):
+    """row indices are integer outcomes of float32 log2f / divide: a few cells per thousand land one row apart between numpy
+    and glibc; the bar is statistical (>= 99 % of time columns identical, Frobenius error <= 5e-3)"""
+    import audioflux_b200 as af
+    sr, num, radix = 32000, 84, 12
+    x = _sq_signal(1 << radix, sr, 1)
+    w = af.WSST(num, radix, sr, wavelet_type=af.WaveletContinueType(wavelet), scale_type=af.SpectralFilterBankScaleType(scale),
+                is_padding=is_pad, _lib=ref_lib)
+    re, im, cr, ci = w.wsst_planes(x)
+    o_re, o_im, w_re, w_im = O.wsst(x, num, radix, sr, wavelet=wavelet, scale=scale, is_pad=is_pad, low=w.low_fre, high=w.high_fre)
+    assert rel_max(w_re, cr) < 1e-4 and rel_max(w_im, ci) < 1e-4
+    for got, want in ((o_re, re), (o_im, im)):
+        same, fro = _sq_agree(got, want)
+        assert same >= 0.99 and fro <= 5e-3, (same, fro)
+
+
+@pytest.mark.parametrize("scale", [O.SCALE_OCTAVE, O.SCALE_LINEAR, O.SCALE_BARK])
+def test_oracle_synsq_matches_the_reference_build(ref_lib, scale):
+    import audioflux_b200 as af
+    sr, num, radix = 32000, 84, 12
+    x = _sq_signal(1 << radix, sr, 2)
+    w_re, w_im = O.cwt(x, num, radix, sr, wavelet=O.WAVE_MORLET, scale=scale, is_pad=False)
+    _, fre = O.cwt_filterbank(num, 1 << radix, sr, O.WAVE_MORLET, scale, None, None, 12, None, None, 0)
+    fre = np.ascontiguousarray(fre, np.float32)
+    want = af.Synsq(num, radix, sr, _lib=ref_lib).synsq_planes(fre, af.SpectralFilterBankScaleType(scale), w_re, w_im)
+    got = O.synsq(fre, w_re, w_im, sr, scale)
+    for g, w in zip(got, want):
+        same, fro = _sq_agree(g, w)
+        assert same >= 0.99 and fro <= 1e-2, (same, fro)
