@@ -96,17 +96,20 @@ static void cwt_args(CWTObj c, int batch, int det, AfCwtArgs *a) {
 /* dData [batch x N] -> planes [batch x num x N]; the batch is cut into chunks that fit the workspace */
 static int cwt_compute(CWTObj c, const float *dData, int batch, int det, float *dRe, float *dIm, void *st) {
     AfCwtArgs a;
-    cwt_args(c, 1, det, &a);
-    const size_t perClip = af_cwt_workspace_bytes(&a);
     size_t budget = af_dev_free_bytes() / 3 + c->dWork.bytes;
     if (budget > ((size_t)24 << 30)) budget = (size_t)24 << 30;
-    int chunk = (int)(budget / perClip);
+    /* largest chunk whose workspace (spectra + inter-leg buffer, or the fused path's fixed ring) fits the budget */
+    int chunk = batch;
     const char *force = getenv("AFB200_CWT_CHUNK");       /* test hook: clips per workspace chunk */
     if (force && atoi(force) > 0 && atoi(force) < chunk) chunk = atoi(force);
-    if (chunk < 1) chunk = 1;
-    if (chunk > batch) chunk = batch;
+    for (;;) {
+        cwt_args(c, chunk, det, &a);
+        if (af_cwt_workspace_bytes(&a) <= budget || chunk == 1) break;
+        chunk = (chunk + 1) / 2;
+    }
     while ((long long)chunk * c->num > 0x7fffffffLL / 2) chunk /= 2;
-    int rc = af_devbuf_reserve(&c->dWork, perClip * (size_t)chunk);
+    cwt_args(c, chunk, det, &a);
+    int rc = af_devbuf_reserve(&c->dWork, af_cwt_workspace_bytes(&a));
     if (rc) return rc;
     const size_t outClip = (size_t)c->num * c->dataLength;
     for (int c0 = 0; c0 < batch; c0 += chunk) {

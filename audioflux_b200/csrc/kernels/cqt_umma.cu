@@ -123,26 +123,41 @@ __global__ void __launch_bounds__(kUmmaThreads) k_cqt_octave_umma(UmmaParams p) 
         for (int cp = 0; cp < par2; cp++) {
             const long long mc = m0 + 2 * cp;                       // copy 1 of hop 2: the signal advanced by 2 samples
             unsigned char *dHi = sHi + cp * copyBytes, *dLo = sLo + cp * copyBytes;
-            for (int i = threadIdx.x * 4; i < total; i += 4 * kUmmaThreads) {
-                float v[4];
-                const long long m = mc + i;
-                if (vec && cp == 0 && m >= 0 && m + 3 < p.validLength) {
-                    const float4 q = *reinterpret_cast<const float4 *>(sig + m);
-                    v[0] = q.x; v[1] = q.y; v[2] = q.z; v[3] = q.w;
-                } else {
+            // kLd float4 loads are in flight per thread before the first one is consumed: the tile of the top octaves is
+            // 17 k samples and the loads were the whole critical path (ncu r2: the first use of a loaded value held 25 % of
+            // the samples of the hop-128 launch)
+            constexpr int kLd = 8;
+            for (int i0 = threadIdx.x * 4; i0 < total; i0 += 4 * kUmmaThreads * kLd) {
+                float4 q[kLd];
 #pragma unroll
-                    for (int u = 0; u < 4; u++) v[u] = (m + u >= 0 && m + u < p.validLength) ? sig[m + u] : 0.0f;
-                }
-                float4 hi4, lo4;
-                float *hp = reinterpret_cast<float *>(&hi4), *lp = reinterpret_cast<float *>(&lo4);
+                for (int b = 0; b < kLd; b++) {
+                    const int i = i0 + b * 4 * kUmmaThreads;
+                    const long long m = mc + i;
+                    q[b] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+                    if (i >= total) continue;
+                    if (vec && cp == 0 && m >= 0 && m + 3 < p.validLength) q[b] = *reinterpret_cast<const float4 *>(sig + m);
+                    else {
+                        float *v = reinterpret_cast<float *>(&q[b]);
 #pragma unroll
-                for (int u = 0; u < 4; u++) {
-                    hp[u] = __uint_as_float(__float_as_uint(v[u]) & 0xffffe000u);
-                    lp[u] = v[u] - hp[u];
+                        for (int u = 0; u < 4; u++) v[u] = (m + u >= 0 && m + u < p.validLength) ? sig[m + u] : 0.0f;
+                    }
                 }
-                const uint32_t off = sig_offset(p, i);               // multiple of 16
-                *reinterpret_cast<float4 *>(dHi + off) = hi4;
-                *reinterpret_cast<float4 *>(dLo + off) = lo4;
+#pragma unroll
+                for (int b = 0; b < kLd; b++) {
+                    const int i = i0 + b * 4 * kUmmaThreads;
+                    if (i >= total) continue;
+                    const float *v = reinterpret_cast<const float *>(&q[b]);
+                    float4 hi4, lo4;
+                    float *hp = reinterpret_cast<float *>(&hi4), *lp = reinterpret_cast<float *>(&lo4);
+#pragma unroll
+                    for (int u = 0; u < 4; u++) {
+                        hp[u] = __uint_as_float(__float_as_uint(v[u]) & 0xffffe000u);
+                        lp[u] = v[u] - hp[u];
+                    }
+                    const uint32_t off = sig_offset(p, i);           // multiple of 16
+                    *reinterpret_cast<float4 *>(dHi + off) = hi4;
+                    *reinterpret_cast<float4 *>(dLo + off) = lo4;
+                }
             }
         }
     }

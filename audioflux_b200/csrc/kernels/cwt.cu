@@ -293,23 +293,23 @@ __device__ __forceinline__ void warp_transpose32(c64 (&z)[32], float *plane, int
     __syncwarp();
 }
 
+// twiddle tables of the columns leg: [32 ka][32 n1] W_1024^(n1 ka), [N2] W_N^j, [1024] W_1024^j
+__device__ void cwt_cols_w_tables(const CwtParams &p, float2 *tw1) {
+    float2 *tf = tw1 + 1024, *t1k = tf + p.N2;
+    for (int j = threadIdx.x; j < 1024; j += blockDim.x) tw1[j] = cw((j >> 5) * (j & 31), 1024, -1.0f);
+    for (int j = threadIdx.x; j < p.N2; j += blockDim.x) tf[j] = cw(j, p.N, -1.0f);
+    for (int j = threadIdx.x; j < 1024; j += blockDim.x) t1k[j] = cw(j, 1024, -1.0f);
+}
+
+// one unit of the columns leg: kWCols adjacent columns of item `item`, result into wk (the item's inter-leg buffer)
 template <int MODE>
-__global__ void __launch_bounds__(kWCols * 32) k_cwt_cols_w(CwtParams p) {
-    extern __shared__ __align__(16) unsigned char smemRaw[];
-    c64 *tile = reinterpret_cast<c64 *>(smemRaw);                              // [kWCols][kWColPitch]
-    float2 *tw1 = reinterpret_cast<float2 *>(tile + (size_t)kWCols * kWColPitch);   // [32 ka][32 n1] W_1024^(n1 ka)
-    float2 *tf = tw1 + 1024;                                                   // [N2] W_N^j (fine inter-leg twiddle)
-    float2 *t1k = tf + p.N2;                                                   // [1024] W_1024^j (coarse inter-leg twiddle)
+__device__ void cwt_cols_w_unit(const CwtParams &p, c64 *tile, const float2 *tw1, int item, int by, float2 *wk) {
+    const float2 *tf = tw1 + 1024, *t1k = tf + p.N2;
     const int N2 = p.N2;
-    const int item = p.itemBase + blockIdx.x;
     const int clip = MODE == 0 ? item : item / p.num;
-    const int col0 = blockIdx.y * kWCols;
+    const int col0 = by * kWCols;
     const float s = MODE == 1 ? p.scaleArr[item % p.num] : 0.0f;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-
-    for (int j = threadIdx.x; j < 1024; j += blockDim.x) tw1[j] = cw((j >> 5) * (j & 31), 1024, -1.0f);
-    for (int j = threadIdx.x; j < N2; j += blockDim.x) tf[j] = cw(j, p.N, -1.0f);
-    for (int j = threadIdx.x; j < 1024; j += blockDim.x) t1k[j] = cw(j, 1024, -1.0f);
     for (int e = threadIdx.x; e < 1024 * kWCols; e += blockDim.x) {
         const int i = e / kWCols, c = e - i * kWCols;
         const int k = i * N2 + col0 + c;
@@ -350,7 +350,6 @@ __global__ void __launch_bounds__(kWCols * 32) k_cwt_cols_w(CwtParams p) {
         }
     }
     __syncthreads();
-    float2 *wk = p.work + (size_t)item * p.N;
     for (int e = threadIdx.x; e < 1024 * kWCols; e += blockDim.x) {
         const int k1 = e / kWCols, c = e - k1 * kWCols;
         float re, im;
@@ -360,25 +359,34 @@ __global__ void __launch_bounds__(kWCols * 32) k_cwt_cols_w(CwtParams p) {
 }
 
 template <int MODE>
-__global__ void __launch_bounds__(kWRows * 16) k_cwt_rows_w(CwtParams p) {
+__global__ void __launch_bounds__(kWCols * 32) k_cwt_cols_w(CwtParams p) {
     extern __shared__ __align__(16) unsigned char smemRaw[];
-    c64 *tile = reinterpret_cast<c64 *>(smemRaw);                              // [kWRows][kWRowPitch]
-    float2 *tw = reinterpret_cast<float2 *>(tile + (size_t)kWRows * kWRowPitch);   // [32 ka][16 q] W_512^(q ka)
-    const int N1 = p.N1;
+    c64 *tile = reinterpret_cast<c64 *>(smemRaw);                              // [kWCols][kWColPitch]
+    float2 *tw1 = reinterpret_cast<float2 *>(tile + (size_t)kWCols * kWColPitch);
+    cwt_cols_w_tables(p, tw1);
     const int item = p.itemBase + blockIdx.x;
+    cwt_cols_w_unit<MODE>(p, tile, tw1, item, blockIdx.y, p.work + (size_t)item * p.N);
+}
+
+__device__ void cwt_rows_w_tables(float2 *tw) {                               // [32 ka][16 q] W_512^(q ka)
+    for (int j = threadIdx.x; j < 512; j += blockDim.x) tw[j] = cw((j >> 4) * (j & 15), 512, -1.0f);
+}
+
+// one unit of the rows leg: kWRows adjacent rows of item `item`, read from wk (the item's inter-leg buffer)
+template <int MODE>
+__device__ void cwt_rows_w_unit(const CwtParams &p, c64 *tile, const float2 *tw, int item, int by, const float2 *wk) {
+    const int N1 = p.N1;
     const int clip = MODE == 0 ? item : item / p.num;
-    const int row0 = blockIdx.y * kWRows;
+    const int row0 = by * kWRows;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int h = lane >> 4, q = lane & 15;
-    for (int j = threadIdx.x; j < 512; j += blockDim.x) tw[j] = cw((j >> 4) * (j & 15), 512, -1.0f);
-    __syncthreads();
 
     {   // each half-warp transforms one row of 512 points as 16 x 32: element n = q + 16 j
         const int r = 2 * warp + h;
-        const float2 *src = p.work + (size_t)item * p.N + (size_t)(row0 + r) * 512;
+        const float2 *src = wk + (size_t)(row0 + r) * 512;
         c64 z[32];
 #pragma unroll
-        for (int j = 0; j < 32; j++) z[j] = c_from(src[q + 16 * j]);
+        for (int j = 0; j < 32; j++) z[j] = c_from(__ldcg(&src[q + 16 * j]));     // L2 only: the ring slot was written by other SMs
         af_fft32(z);                                                           // over j -> Y[q][ka] at AF_BR5(ka)
         float *plane = reinterpret_cast<float *>(tile + (size_t)r * kWRowPitch);   // 1040 floats >= 32 x 17
         float yr[32], yi[32];
@@ -441,6 +449,95 @@ __global__ void __launch_bounds__(kWRows * 16) k_cwt_rows_w(CwtParams p) {
     }
 }
 
+template <int MODE>
+__global__ void __launch_bounds__(kWRows * 16) k_cwt_rows_w(CwtParams p) {
+    extern __shared__ __align__(16) unsigned char smemRaw[];
+    c64 *tile = reinterpret_cast<c64 *>(smemRaw);                              // [kWRows][kWRowPitch]
+    float2 *tw = reinterpret_cast<float2 *>(tile + (size_t)kWRows * kWRowPitch);
+    cwt_rows_w_tables(tw);
+    __syncthreads();
+    const int item = p.itemBase + blockIdx.x;
+    cwt_rows_w_unit<MODE>(p, tile, tw, item, blockIdx.y, p.work + (size_t)item * p.N);
+}
+
+// ============================================================================================
+// Both inverse legs in ONE persistent kernel (N = 2^19 fast path).  The inter-leg buffer of an item (4 MB) used to be
+// written by a columns launch over ALL items of the chunk and read back by a rows launch: 352 MB per clip to HBM and
+// back (ncu r1: 1036 MB of DRAM traffic per clip for 354 MB of results).  Here the (clip, scale) items are taken in
+// groups of `groupItems`; a group's inter-leg data lives in one slot of a small ring (kRing slots, tens of MB: it stays
+// in the 126 MB L2), the rows units of group g are queued right behind the columns units of group g + 1, and a slot is
+// rewritten -- in L2, before its dirty lines are ever evicted -- as soon as the rows units of its previous group are
+// done.  CTAs claim units from one global counter; two per-group counters carry the dependencies (columns done -> rows
+// may start; rows done -> the slot may be reused).  Unit order guarantees progress: whatever a unit waits for was
+// claimed earlier by a resident CTA.
+// ============================================================================================
+constexpr int kRing = 3;
+struct FusedParams {
+    CwtParams p;
+    int items, groupItems, groups, cb, rb;      // items = batch * num; cb / rb = column / row units per item
+    unsigned *counters;                         // [0] next unit, [1 + g] columns done of group g, [1 + groups + g] rows done
+};
+
+__device__ __forceinline__ unsigned ld_acquire(const unsigned *p) {
+    unsigned v;
+    asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+
+__global__ void __launch_bounds__(256, 2) k_cwt_fused_w(FusedParams f) {
+    extern __shared__ __align__(16) unsigned char smemRaw[];
+    const CwtParams &p = f.p;
+    c64 *tile = reinterpret_cast<c64 *>(smemRaw);                              // max(cols tile, rows tile)
+    float2 *tw1 = reinterpret_cast<float2 *>(tile + (size_t)kWCols * kWColPitch);   // columns tables (1024 + N2 + 1024)
+    float2 *twr = tw1 + 2048 + p.N2;                                           // rows table (512)
+    __shared__ unsigned sUnit;
+    cwt_cols_w_tables(p, tw1);
+    cwt_rows_w_tables(twr);
+    __syncthreads();
+    const unsigned colsPerGroup = (unsigned)f.groupItems * f.cb, rowsPerGroup = (unsigned)f.groupItems * f.rb;
+    // unit sequence: cols(0) | cols(1) rows(0) | cols(2) rows(1) | ... | rows(groups - 1); the last group may be short
+    const unsigned span = colsPerGroup + rowsPerGroup;
+    const unsigned total = (unsigned)f.groups * span;
+    for (;;) {
+        __syncthreads();                                                        // previous unit's tile fully consumed
+        if (threadIdx.x == 0) sUnit = atomicAdd(&f.counters[0], 1u);
+        __syncthreads();
+        const unsigned u = sUnit;
+        if (u >= total) break;
+        bool isRows;
+        unsigned g, r;
+        if (u < colsPerGroup) { isRows = false; g = 0; r = u; }
+        else {
+            const unsigned v = u - colsPerGroup, blk = v / span, w = v - blk * span;
+            if (blk + 1 < (unsigned)f.groups) { if (w < colsPerGroup) { isRows = false; g = blk + 1; r = w; } else { isRows = true; g = blk; r = w - colsPerGroup; } }
+            else { isRows = true; g = blk; r = w; if (w >= rowsPerGroup) continue; }      // tail: only rows(groups - 1)
+        }
+        const int perItem = isRows ? f.rb : f.cb;
+        const int li = (int)(r / perItem), by = (int)(r % perItem);
+        const int item = (int)g * f.groupItems + li;
+        const int itemsInGroup = min(f.groupItems, f.items - (int)g * f.groupItems);
+        float2 *wk = p.work + ((size_t)(g % kRing) * f.groupItems + li) * p.N;
+        if (li < itemsInGroup) {
+            if (threadIdx.x == 0) {
+                if (isRows) {                                                   // every columns unit of this group has landed
+                    const unsigned need = (unsigned)itemsInGroup * f.cb;
+                    while (ld_acquire(&f.counters[1 + g]) < need) __nanosleep(200);
+                } else if (g >= kRing) {                                        // the slot's previous group has been read out
+                    const int prevItems = min(f.groupItems, f.items - (int)(g - kRing) * f.groupItems);
+                    const unsigned need = (unsigned)prevItems * f.rb;
+                    while (ld_acquire(&f.counters[1 + f.groups + (g - kRing)]) < need) __nanosleep(200);
+                }
+            }
+            __syncthreads();
+            if (isRows) cwt_rows_w_unit<1>(p, tile, twr, item, by, wk);
+            else cwt_cols_w_unit<1>(p, tile, tw1, item, by, wk);
+            __threadfence();                                                    // this CTA's global writes before the release below
+            __syncthreads();
+            if (threadIdx.x == 0) atomicAdd(&f.counters[1 + (isRows ? f.groups : 0) + g], 1u);
+        }
+    }
+}
+
 __global__ void k_cwt_bank_table(CwtParams p, float *bank) {
     const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= (long long)p.num * p.N) return;
@@ -481,10 +578,23 @@ int set_smem(K kernel, size_t bytes, const char *name) {
 
 }  // namespace
 
-// workspace = forward spectrum (batch x N float2) + inter-leg buffer (batch x num x N float2 when N > 4096)
+// fast path (N = 2^19): persistent fused inverse legs over a small ring of inter-leg slots
+static int cwt_fused_enabled(const AfCwtArgs *a) {
+    const char *e = getenv("AFB200_CWT_FUSED");
+    return a->log2n == 19 && !getenv("AFB200_CWT_GENERIC") && !(e && e[0] == '0');
+}
+static int cwt_group_items(void) {
+    const char *e = getenv("AFB200_CWT_GROUP");
+    const int g = e ? atoi(e) : 0;
+    return g > 0 && g <= 64 ? g : 6;                     // 3 slots x 6 items x 4 MB = 72 MB of the 126 MB L2
+}
+
+// workspace = forward spectrum (batch x N float2) + inter-leg buffer: batch x num x N float2 when N > 4096, or -- fused
+// fast path -- a ring of kRing x groupItems item slots plus the unit counters
 extern "C" size_t af_cwt_workspace_bytes(const AfCwtArgs *a) {
     const size_t N = (size_t)1 << a->log2n;
     size_t bytes = sizeof(float2) * N * (size_t)a->batch;
+    if (cwt_fused_enabled(a)) return bytes + sizeof(float2) * N * (size_t)kRing * cwt_group_items() + 65536;
     if (a->log2n > 12) bytes += sizeof(float2) * N * (size_t)a->batch * a->num;
     return bytes;
 }
@@ -511,17 +621,29 @@ extern "C" int af_launch_cwt(const AfCwtArgs *a, const float *data, void *worksp
             k_cwt_rows_w<0><<<dim3((unsigned)a->batch, rb), kWRows * 16, smR, st>>>(p);
             AF_LAUNCH_CHECK("k_cwt_rows_w<0>");
         }
-        // optional: alternate the two legs over groups of (clip, scale) items (AFB200_CWT_GROUP) so that a group's
-        // inter-leg buffer is still in L2 when read back.  Measured on B200: slower than one launch pair for the
-        // whole chunk (launch tails cost more than the HBM round trip saves), so the default is a single group.
-        const unsigned group = getenv("AFB200_CWT_GROUP") && atoi(getenv("AFB200_CWT_GROUP")) > 0 ? (unsigned)atoi(getenv("AFB200_CWT_GROUP")) : items;
-        for (unsigned i0 = 0; i0 < items; i0 += group) {
-            const unsigned n = items - i0 < group ? items - i0 : group;
+        if (cwt_fused_enabled(a)) {
+            FusedParams f;
+            f.p = p;
+            f.items = (int)items; f.groupItems = cwt_group_items(); f.groups = (f.items + f.groupItems - 1) / f.groupItems;
+            f.cb = (int)cb; f.rb = (int)rb;
+            f.counters = reinterpret_cast<unsigned *>(p.work + (size_t)p.N * kRing * f.groupItems);
+            if ((size_t)(1 + 2 * f.groups) * sizeof(unsigned) > 65536) return af_fail(AF_ERR_UNSUPPORTED, "CWT: %d item groups exceed the counter block", f.groups);
+            cudaError_t e = cudaMemsetAsync(f.counters, 0, (size_t)(1 + 2 * f.groups) * sizeof(unsigned), st);
+            if (e != cudaSuccess) return af_cuda_check(e, "cudaMemsetAsync(cwt counters)");
+            const size_t smF = sizeof(c64) * (size_t)kWCols * kWColPitch + sizeof(float2) * (2048 + p.N2 + 512);
+            if ((rc = set_smem(k_cwt_fused_w, smF, "smem k_cwt_fused_w"))) return rc;
+            int sms = af_sm_count();
+            if (sms <= 0) sms = 148;
+            k_cwt_fused_w<<<(unsigned)(2 * sms), 256, smF, st>>>(f);
+            AF_LAUNCH_CHECK("k_cwt_fused_w");
+            return AF_OK;
+        }
+        for (unsigned i0 = 0; i0 < items; i0 += items) {
             CwtParams q = p;
             q.itemBase = (int)i0;
-            k_cwt_cols_w<1><<<dim3(n, cb), kWCols * 32, smC, st>>>(q);
+            k_cwt_cols_w<1><<<dim3(items, cb), kWCols * 32, smC, st>>>(q);
             AF_LAUNCH_CHECK("k_cwt_cols_w<1>");
-            k_cwt_rows_w<1><<<dim3(n, rb), kWRows * 16, smR, st>>>(q);
+            k_cwt_rows_w<1><<<dim3(items, rb), kWRows * 16, smR, st>>>(q);
             AF_LAUNCH_CHECK("k_cwt_rows_w<1>");
         }
         return AF_OK;
