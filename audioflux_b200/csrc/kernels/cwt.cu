@@ -594,7 +594,12 @@ static int cwt_group_items(void) {
 extern "C" size_t af_cwt_workspace_bytes(const AfCwtArgs *a) {
     const size_t N = (size_t)1 << a->log2n;
     size_t bytes = sizeof(float2) * N * (size_t)a->batch;
-    if (cwt_fused_enabled(a)) return bytes + sizeof(float2) * N * (size_t)kRing * cwt_group_items() + 65536;
+    if (cwt_fused_enabled(a)) {
+        // the forward transform of the chunk uses one inter-leg slot per clip, the fused inverse the ring
+        size_t slots = (size_t)kRing * cwt_group_items();
+        if ((size_t)a->batch > slots) slots = (size_t)a->batch;
+        return bytes + sizeof(float2) * N * slots + 65536;
+    }
     if (a->log2n > 12) bytes += sizeof(float2) * N * (size_t)a->batch * a->num;
     return bytes;
 }
@@ -626,7 +631,11 @@ extern "C" int af_launch_cwt(const AfCwtArgs *a, const float *data, void *worksp
             f.p = p;
             f.items = (int)items; f.groupItems = cwt_group_items(); f.groups = (f.items + f.groupItems - 1) / f.groupItems;
             f.cb = (int)cb; f.rb = (int)rb;
-            f.counters = reinterpret_cast<unsigned *>(p.work + (size_t)p.N * kRing * f.groupItems);
+            {
+                size_t slots = (size_t)kRing * f.groupItems;
+                if ((size_t)a->batch > slots) slots = (size_t)a->batch;
+                f.counters = reinterpret_cast<unsigned *>(p.work + (size_t)p.N * slots);
+            }
             if ((size_t)(1 + 2 * f.groups) * sizeof(unsigned) > 65536) return af_fail(AF_ERR_UNSUPPORTED, "CWT: %d item groups exceed the counter block", f.groups);
             cudaError_t e = cudaMemsetAsync(f.counters, 0, (size_t)(1 + 2 * f.groups) * sizeof(unsigned), st);
             if (e != cudaSuccess) return af_cuda_check(e, "cudaMemsetAsync(cwt counters)");
