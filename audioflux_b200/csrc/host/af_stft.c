@@ -22,18 +22,21 @@ struct OpaqueSTFT {
     AfDevBuf dIn, dRe, dIm, dFrames;
     AfPipe pipe;                   /* host-pointer batches: chunked copy-in / transform / copy-out */
     int pipeLength;
+    /* streaming (isContinue, stft_algorithm.c:474-599): the samples that did not complete a hop are carried to the next call */
+    int isContinue;
+    float *tail;                   /* host, fftLength + slideLength floats */
+    int tailLength;                /* may be negative when slideLength > fftLength: samples of the next call to skip */
+    float *cur; size_t curCap;     /* host staging: tail + new samples */
+    int timeLength;                /* frames of the last stftObj_stft call */
 };
 
 int stftObj_new(STFTObj *out, int radix2Exp, WindowType *windowType, int *slideLength, int *isContinue) {
     if (!out) return -1;
     *out = NULL;
     if (radix2Exp < 1 || radix2Exp > 30) return -100;
-    if (isContinue && *isContinue) {
-        af_fail(AF_ERR_UNSUPPORTED, "stftObj_new: isContinue=1 (streaming) is not supported by libaudioflux_b200");
-        return -2;
-    }
     STFTObj s = (STFTObj)calloc(1, sizeof(struct OpaqueSTFT));
     if (!s) return -1;
+    s->isContinue = isContinue ? *isContinue != 0 : 0;
     s->radix2Exp = radix2Exp;
     s->fftLength = 1 << radix2Exp;
     s->windowType = windowType ? *windowType : Window_Rect;
@@ -52,10 +55,7 @@ int stftObj_new(STFTObj *out, int radix2Exp, WindowType *windowType, int *slideL
 
 void stftObj_setSlideLength(STFTObj s, int slideLength) { if (s && slideLength > 0) s->slideLength = slideLength; }
 void stftObj_enablePadding(STFTObj s, int flag) { if (s) s->isPad = flag; }
-void stftObj_enableContinue(STFTObj s, int flag) {
-    (void)s;
-    if (flag) af_fail(AF_ERR_UNSUPPORTED, "stftObj_enableContinue: streaming mode is not supported by libaudioflux_b200");
-}
+void stftObj_enableContinue(STFTObj s, int flag) { if (s) { s->isContinue = flag != 0; } }
 void stftObj_setPadding(STFTObj s, PaddingPositionType *position, PaddingModeType *mode, float *v1, float *v2) {
     if (!s || !s->isPad) return;          /* like the reference: only honoured once padding is enabled */
     if (position) s->position = *position;
@@ -70,10 +70,14 @@ void stftObj_useWindowDataArr(STFTObj s, float *w) {
 }
 float *stftObj_getWindowDataArr(STFTObj s) { return s ? s->window : NULL; }
 
-int stftObj_calTimeLength(STFTObj s, int dataLength) {
-    if (!s) return 0;
+static int time_length(const struct OpaqueSTFT *s, int dataLength) {
     if (!s->isPad) return dataLength < s->fftLength ? 0 : (dataLength - s->fftLength) / s->slideLength + 1;
     return dataLength <= 0 ? 0 : dataLength / s->slideLength + 1;
+}
+int stftObj_calTimeLength(STFTObj s, int dataLength) {
+    if (!s) return 0;
+    if (!s->isPad && s->isContinue) dataLength += s->tailLength;         /* stft_algorithm.c:242-245 */
+    return time_length(s, dataLength);
 }
 int stftObj_calDataLength(STFTObj s, int timeLength) { return s ? (timeLength - 1) * s->slideLength + s->fftLength : 0; }
 void stftObj_debug(STFTObj s) {
@@ -99,7 +103,7 @@ static int stft_frame_src(STFTObj s, int dataLength, int batch, AfFrameSrc *src)
     memset(src, 0, sizeof(*src));
     src->fftLength = s->fftLength; src->slideLength = s->slideLength;
     src->dataLength = dataLength; src->batch = batch;
-    src->timeLength = stftObj_calTimeLength(s, dataLength);
+    src->timeLength = time_length(s, dataLength);
     src->validLength = dataLength;
     src->window = s->useWindow ? s->dWindow : NULL;
     if (s->isPad) {
@@ -116,17 +120,61 @@ static int stft_frame_src(STFTObj s, int dataLength, int batch, AfFrameSrc *src)
     return AF_OK;
 }
 
+/* streaming bookkeeping of __stftObj_dealData (stft_algorithm.c:474-599, non-padding mode): returns the samples to
+ * transform (tail of the previous calls + the new ones) in *cur / *curLength, or 0 when they do not fill a frame yet */
+static int stft_continue_assemble(STFTObj s, const float *data, int dataLength, const float **cur, int *curLength) {
+    const int n = s->fftLength, hop = s->slideLength;
+    if (!s->tail) {
+        s->tail = (float *)calloc((size_t)n + (size_t)hop + 1, sizeof(float));
+        if (!s->tail) return 0;
+    }
+    const int total = s->tailLength + dataLength;
+    if (total < n) {                                          /* not a frame yet: keep everything */
+        if (s->tailLength >= 0) memcpy(s->tail + s->tailLength, data, sizeof(float) * (size_t)dataLength);
+        else if (dataLength + s->tailLength > 0) memcpy(s->tail, data - s->tailLength, sizeof(float) * (size_t)(dataLength + s->tailLength));
+        s->tailLength = total;
+        s->timeLength = 0;
+        return 0;
+    }
+    const int tailLen = (total - n) % hop + (n - hop);      /* __calTimeAndTailLen */
+    if ((size_t)total + (size_t)n > s->curCap) {
+        free(s->cur);
+        s->curCap = (size_t)total + (size_t)n;
+        s->cur = (float *)malloc(sizeof(float) * s->curCap);
+        if (!s->cur) { s->curCap = 0; return 0; }
+    }
+    int len = 0;
+    if (s->tailLength < 0) {
+        len = dataLength + s->tailLength;
+        memcpy(s->cur, data - s->tailLength, sizeof(float) * (size_t)len);
+    } else {
+        if (s->tailLength > 0) memcpy(s->cur, s->tail, sizeof(float) * (size_t)s->tailLength);
+        memcpy(s->cur + s->tailLength, data, sizeof(float) * (size_t)dataLength);
+        len = s->tailLength + dataLength;
+    }
+    if (tailLen > 0) memcpy(s->tail, s->cur + (len - tailLen), sizeof(float) * (size_t)tailLen);
+    s->tailLength = tailLen;
+    *cur = s->cur; *curLength = len;
+    return 1;
+}
+
 void stftObj_stft(STFTObj s, float *dataArr, int dataLength, float *mRealArr, float *mImageArr) {
     if (!s || !dataArr || dataLength <= 0 || !mRealArr || !mImageArr) return;
     af_clear_error();
+    const float *x = dataArr;
+    int len = dataLength;
+    if (s->isContinue && !s->isPad) {
+        if (!stft_continue_assemble(s, dataArr, dataLength, &x, &len)) return;
+    }
     if (stft_device(s)) return;
     AfFrameSrc src;
-    if (stft_frame_src(s, dataLength, 1, &src)) return;
+    if (stft_frame_src(s, len, 1, &src)) return;
+    s->timeLength = src.timeLength;
     if (src.timeLength <= 0) return;
     size_t plane = sizeof(float) * (size_t)src.timeLength * s->fftLength;
-    if (af_devbuf_reserve(&s->dIn, sizeof(float) * (size_t)dataLength) || af_devbuf_reserve(&s->dRe, plane) ||
+    if (af_devbuf_reserve(&s->dIn, sizeof(float) * (size_t)len) || af_devbuf_reserve(&s->dRe, plane) ||
         af_devbuf_reserve(&s->dIm, plane)) return;
-    if (af_memcpy_h2d(s->dIn.ptr, dataArr, sizeof(float) * (size_t)dataLength, s->stream)) return;
+    if (af_memcpy_h2d(s->dIn.ptr, x, sizeof(float) * (size_t)len, s->stream)) return;
     src.data = (const float *)s->dIn.ptr;
     if (af_launch_stft(&src, AF_STFT_FULL, 1.0f, (float *)s->dRe.ptr, (float *)s->dIm.ptr, s->stream)) return;
     if (af_memcpy_d2h(mRealArr, s->dRe.ptr, plane, s->stream) || af_memcpy_d2h(mImageArr, s->dIm.ptr, plane, s->stream)) return;
@@ -204,6 +252,6 @@ void stftObj_free(STFTObj s) {
     af_pipe_free(&s->pipe);
     af_dev_free(s->dWindow);
     af_stream_destroy(s->stream);
-    free(s->window);
+    free(s->window); free(s->tail); free(s->cur);
     free(s);
 }

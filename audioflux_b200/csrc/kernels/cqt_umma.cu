@@ -254,6 +254,247 @@ __global__ void __launch_bounds__(kUmmaThreads) k_cqt_octave_umma(UmmaParams p) 
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmemD), "n"(64) : "memory");
 }
 
+
+// ============================================================================================
+// Persistent, warp-specialised version: one CTA per SM loops over tiles; three groups of warps run as a pipeline
+// connected by mbarriers, so the staging of tile k+1, the MMAs of tile k and the epilogue of tile k-1 overlap:
+//   warps 0-3  epilogue : accFull[a] -> tcgen05.ld (TMEM lane = frame) -> accEmpty[a] -> 16-byte stores
+//   warp  4    issuer   : sigFull[s], accEmpty[a] -> 192 tcgen05.mma (x2 for hop 2) -> tcgen05.commit -> sigEmpty[s], accFull[a]
+//   warps 5-11 stagers  : sigEmpty[s] -> signal tile (hi / lo, swizzled) -> fence.proxy.async -> sigFull[s]
+// The kernels (B, 128 KB hi + lo) stay RESIDENT in shared memory when the signal tiles leave room (hop <= 32: loaded once
+// per CTA by TMA); for hop 64 / 128 they are streamed per tile through the two 32 KB slots as in k_cqt_octave_umma.
+// Two accumulators in TMEM (four for hop 2) let the tensor core start tile k+1 while tile k is being read out.
+// ============================================================================================
+constexpr int kPEpiWarps = 4, kPStageWarps = 7;
+constexpr int kPThreads = (kPEpiWarps + 1 + kPStageWarps) * 32;
+
+struct UmmaPParams {
+    UmmaParams u;
+    int tilesPerClip, stages, bResident;
+    long long totalTiles;
+};
+
+__global__ void __launch_bounds__(kPThreads, 1) k_cqt_octave_umma_p(UmmaPParams pp) {
+    extern __shared__ __align__(1024) unsigned char smem[];
+    const UmmaParams &p = pp.u;
+    const int chunks = p.N / kUmmaChunkK;
+    const int bBytes = pp.bResident ? chunks * 2 * kUmmaBBytes : 2 * 2 * kUmmaBBytes;
+    unsigned char *sB = smem;
+    unsigned char *sSig = smem + bBytes;                              // [stage][hi | lo][sigBytes]
+    uint64_t *bars = reinterpret_cast<uint64_t *>(sSig + (size_t)pp.stages * 2 * p.sigBytes);
+    uint64_t *sigFull = bars, *sigEmpty = bars + 2, *accFull = bars + 4, *accEmpty = bars + 6, *bFull = bars + 8, *bEmpty = bars + 10;
+    uint32_t *tmemSlot = reinterpret_cast<uint32_t *>(bars + 12);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int par2 = p.mode == 4 ? 2 : 1;
+    const int framesPerTile = kUmmaM * par2;
+    const int h = p.hop, N = p.N;
+    const int copyBytes = p.mode == 4 ? p.sigBytes / 2 : p.sigBytes;
+
+    if (threadIdx.x == 0) {
+        for (int i = 0; i < 2; i++) {
+            af_mbar_init(&sigFull[i], kPStageWarps); af_mbar_init(&sigEmpty[i], 1);
+            af_mbar_init(&accFull[i], 1); af_mbar_init(&accEmpty[i], kPEpiWarps);
+            af_mbar_init(&bFull[i], 1); af_mbar_init(&bEmpty[i], 1);
+        }
+        af_fence_barrier_init();
+    }
+    if (warp == 0) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(af_smem_u32(tmemSlot)), "n"(128) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const uint32_t tmemBase = *tmemSlot;
+
+    if (warp >= kPEpiWarps + 1) {
+        // ================= stagers =================
+        const int sw = warp - (kPEpiWarps + 1), nst = kPStageWarps * 32, tid = sw * 32 + lane;
+        int k = 0;
+        for (long long tile = blockIdx.x; tile < pp.totalTiles; tile += gridDim.x, ++k) {
+            const int s = k % pp.stages;
+            af_mbar_wait(&sigEmpty[s], (((uint32_t)(k / pp.stages)) & 1u) ^ 1u);
+            const int clip = (int)(tile / pp.tilesPerClip), t0 = (int)(tile % pp.tilesPerClip) * framesPerTile;
+            const float *sig = p.sig + (long long)clip * p.sigStride;
+            const long long m0 = (long long)t0 * h - N / 2;
+            const int total = copyBytes / 4;
+            const bool vec = ((p.sigStride & 3) == 0) && ((reinterpret_cast<uintptr_t>(p.sig) & 15) == 0) && ((m0 & 3) == 0);
+            unsigned char *sHi = sSig + (size_t)s * 2 * p.sigBytes, *sLo = sHi + p.sigBytes;
+            for (int cp = 0; cp < par2; cp++) {
+                const long long mc = m0 + 2 * cp;
+                unsigned char *dHi = sHi + cp * copyBytes, *dLo = sLo + cp * copyBytes;
+                constexpr int kLd = 8;
+                for (int i0 = tid * 4; i0 < total; i0 += 4 * nst * kLd) {
+                    float4 q[kLd];
+#pragma unroll
+                    for (int b = 0; b < kLd; b++) {
+                        const int i = i0 + b * 4 * nst;
+                        const long long m = mc + i;
+                        q[b] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+                        if (i >= total) continue;
+                        if (vec && cp == 0 && m >= 0 && m + 3 < p.validLength) q[b] = *reinterpret_cast<const float4 *>(sig + m);
+                        else {
+                            float *v = reinterpret_cast<float *>(&q[b]);
+#pragma unroll
+                            for (int u = 0; u < 4; u++) v[u] = (m + u >= 0 && m + u < p.validLength) ? sig[m + u] : 0.0f;
+                        }
+                    }
+#pragma unroll
+                    for (int b = 0; b < kLd; b++) {
+                        const int i = i0 + b * 4 * nst;
+                        if (i >= total) continue;
+                        const float *v = reinterpret_cast<const float *>(&q[b]);
+                        float4 hi4, lo4;
+                        float *hp = reinterpret_cast<float *>(&hi4), *lp = reinterpret_cast<float *>(&lo4);
+#pragma unroll
+                        for (int u = 0; u < 4; u++) {
+                            hp[u] = __uint_as_float(__float_as_uint(v[u]) & 0xffffe000u);
+                            lp[u] = v[u] - hp[u];
+                        }
+                        const uint32_t off = sig_offset(p, i);
+                        *reinterpret_cast<float4 *>(dHi + off) = hi4;
+                        *reinterpret_cast<float4 *>(dLo + off) = lo4;
+                    }
+                }
+            }
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            __syncwarp();
+            if (lane == 0) af_mbar_arrive(&sigFull[s]);
+        }
+    } else if (warp == kPEpiWarps) {
+        // ================= MMA issuer (+ kernel loads) =================
+        if (lane == 0) {
+            constexpr uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(kUmmaN >> 3) << 17) | ((uint32_t)(kUmmaM >> 4) << 24);
+            uint32_t layoutA, sboA, lboA;
+            if (p.mode == 0 || p.mode == 4) { layoutA = 0; sboA = 128; lboA = 16; }
+            else if (p.mode == 1) { layoutA = 6; sboA = 256; lboA = 0; }
+            else if (p.mode == 2) { layoutA = 4; sboA = 512; lboA = 0; }
+            else { layoutA = 2; sboA = 1024; lboA = 0; }
+            long long bLoads = 0, bUses = 0;                          // streamed mode: chunk loads issued / consumed so far
+            if (pp.bResident) {
+                af_mbar_arrive_expect_tx(&bFull[0], (uint32_t)(chunks * 2 * kUmmaBBytes));
+                for (int c = 0; c < chunks; c++)
+                    af_tma_load_1d(sB + (size_t)c * 2 * kUmmaBBytes, p.bimg + (size_t)c * 2 * kUmmaBBytes, 2 * kUmmaBBytes, &bFull[0]);
+                af_mbar_wait(&bFull[0], 0);
+            } else {
+                for (; bLoads < 2; bLoads++) {
+                    af_mbar_arrive_expect_tx(&bFull[bLoads], 2 * kUmmaBBytes);
+                    af_tma_load_1d(sB + bLoads * 2 * kUmmaBBytes, p.bimg + (size_t)(bLoads % chunks) * 2 * kUmmaBBytes, 2 * kUmmaBBytes, &bFull[bLoads]);
+                }
+            }
+            const long long myTiles = (pp.totalTiles - blockIdx.x + gridDim.x - 1) / gridDim.x;
+            int k = 0;
+            for (long long tile = blockIdx.x; tile < pp.totalTiles; tile += gridDim.x, ++k) {
+                const int s = k % pp.stages, a = k & 1;
+                af_mbar_wait(&sigFull[s], ((uint32_t)(k / pp.stages)) & 1u);
+                af_mbar_wait(&accEmpty[a], (((uint32_t)(k >> 1)) & 1u) ^ 1u);
+                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                const uint32_t aHi = af_smem_u32(sSig + (size_t)s * 2 * p.sigBytes), aLo = aHi + (uint32_t)p.sigBytes;
+                const uint32_t tmemD = tmemBase + (uint32_t)a * (kUmmaN * par2);
+                uint32_t acc = 0;
+                for (int c = 0; c < chunks; c++) {
+                    uint32_t bBase;
+                    int slot = 0;
+                    if (pp.bResident) bBase = af_smem_u32(sB + (size_t)c * 2 * kUmmaBBytes);
+                    else {
+                        slot = (int)(bUses & 1);
+                        af_mbar_wait(&bFull[slot], (uint32_t)(bUses >> 1) & 1u);
+                        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                        bBase = af_smem_u32(sB + slot * 2 * kUmmaBBytes);
+                    }
+#pragma unroll 1
+                    for (int ks = 0; ks < kUmmaChunkK / 8; ks++) {
+                        const int n0 = c * kUmmaChunkK + ks * 8;
+                        uint32_t offA;
+                        if (p.mode == 3) {
+                            const int j = n0 >> 5, q = (n0 >> 3) & 3;
+                            offA = (uint32_t)((j % p.planes) * p.rowsPerPlane + j / p.planes) * 128u + (uint32_t)q * 32u;
+                        } else offA = (uint32_t)n0 * 4u;
+                        const uint32_t offB = (uint32_t)(ks >> 2) * 4096u + (uint32_t)(ks & 3) * 32u;
+                        const uint64_t dBhi = umma_desc(bBase + offB, 0, 1024, 2, 0);
+                        const uint64_t dBlo = umma_desc(bBase + kUmmaBBytes + offB, 0, 1024, 2, 0);
+                        for (int cp = 0; cp < par2; cp++) {
+                            const uint64_t dAhi = umma_desc(aHi + cp * copyBytes + offA, lboA, sboA, layoutA, 0);
+                            const uint64_t dAlo = umma_desc(aLo + cp * copyBytes + offA, lboA, sboA, layoutA, 0);
+                            const uint32_t d = tmemD + (uint32_t)cp * kUmmaN;
+                            umma_tf32(d, dAlo, dBhi, idesc, acc);
+                            umma_tf32(d, dAhi, dBlo, idesc, 1);
+                            umma_tf32(d, dAhi, dBhi, idesc, 1);
+                        }
+                        acc = 1;
+                    }
+                    if (!pp.bResident) {
+                        bUses++;
+                        // refill this slot with the chunk two uses ahead (the stream of chunks is periodic over the tiles)
+                        if (bLoads < myTiles * chunks) {
+                            umma_commit(&bEmpty[slot]);
+                            af_mbar_wait(&bEmpty[slot], (uint32_t)((bUses - 1) >> 1) & 1u);
+                            af_mbar_arrive_expect_tx(&bFull[slot], 2 * kUmmaBBytes);
+                            af_tma_load_1d(sB + slot * 2 * kUmmaBBytes, p.bimg + (size_t)(bLoads % chunks) * 2 * kUmmaBBytes, 2 * kUmmaBBytes, &bFull[slot]);
+                            bLoads++;
+                        }
+                    }
+                }
+                umma_commit(&sigEmpty[s]);                             // the tile's MMAs have read the signal stage
+                umma_commit(&accFull[a]);                              // ... and the accumulator is complete
+            }
+        }
+    } else {
+        // ================= epilogue =================
+        int k = 0;
+        for (long long tile = blockIdx.x; tile < pp.totalTiles; tile += gridDim.x, ++k) {
+            const int a = k & 1;
+            const int clip = (int)(tile / pp.tilesPerClip), t0 = (int)(tile % pp.tilesPerClip) * framesPerTile;
+            af_mbar_wait(&accFull[a], ((uint32_t)(k >> 1)) & 1u);
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            uint32_t r[2][32];
+            for (int cp = 0; cp < par2; cp++) {
+                const uint32_t taddr = tmemBase + ((uint32_t)(warp * 32) << 16) + (uint32_t)a * (kUmmaN * par2) + (uint32_t)cp * kUmmaN;
+                asm volatile(
+                    "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+                    "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+                    "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+                    : "=r"(r[cp][0]), "=r"(r[cp][1]), "=r"(r[cp][2]), "=r"(r[cp][3]), "=r"(r[cp][4]), "=r"(r[cp][5]), "=r"(r[cp][6]), "=r"(r[cp][7]),
+                      "=r"(r[cp][8]), "=r"(r[cp][9]), "=r"(r[cp][10]), "=r"(r[cp][11]), "=r"(r[cp][12]), "=r"(r[cp][13]), "=r"(r[cp][14]), "=r"(r[cp][15]),
+                      "=r"(r[cp][16]), "=r"(r[cp][17]), "=r"(r[cp][18]), "=r"(r[cp][19]), "=r"(r[cp][20]), "=r"(r[cp][21]), "=r"(r[cp][22]), "=r"(r[cp][23]),
+                      "=r"(r[cp][24]), "=r"(r[cp][25]), "=r"(r[cp][26]), "=r"(r[cp][27]), "=r"(r[cp][28]), "=r"(r[cp][29]), "=r"(r[cp][30]), "=r"(r[cp][31])
+                    : "r"(taddr));
+            }
+            asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+            asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+            __syncwarp();
+            if (lane == 0) af_mbar_arrive(&accEmpty[a]);               // the tensor core may overwrite this accumulator
+            for (int cp = 0; cp < par2; cp++) {
+                const int t = t0 + (warp * 32 + lane) * par2 + cp;
+                if (t >= p.T) continue;
+                const long long o = (long long)clip * p.outStride + (long long)t * p.num + p.colOff;
+                float re[12], im[12];
+#pragma unroll
+                for (int j = 0; j < 12; j++) {
+                    const float sc = p.scale[j];
+                    re[j] = __uint_as_float(r[cp][2 * j]) * sc;
+                    im[j] = __uint_as_float(r[cp][2 * j + 1]) * sc;
+                }
+                if (((o & 3) == 0) && ((reinterpret_cast<uintptr_t>(p.outRe) & 15) == 0) && ((reinterpret_cast<uintptr_t>(p.outIm) & 15) == 0)) {
+#pragma unroll
+                    for (int v = 0; v < 3; v++) {
+                        *reinterpret_cast<float4 *>(p.outRe + o + 4 * v) = make_float4(re[4 * v], re[4 * v + 1], re[4 * v + 2], re[4 * v + 3]);
+                        *reinterpret_cast<float4 *>(p.outIm + o + 4 * v) = make_float4(im[4 * v], im[4 * v + 1], im[4 * v + 2], im[4 * v + 3]);
+                    }
+                } else {
+#pragma unroll
+                    for (int j = 0; j < 12; j++) { p.outRe[o + j] = re[j]; p.outIm[o + j] = im[j]; }
+                }
+            }
+        }
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    if (warp == 0)
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmemBase), "n"(128) : "memory");
+}
+
 }  // namespace
 
 // Pre-swizzled shared-memory images of the B operand: per 128-tap chunk, hi part then lo part, each [32 n][128 k] K-major
@@ -319,6 +560,31 @@ extern "C" int af_launch_cqt_octave_umma(const float *sig, int sigStride, int ba
     cudaError_t e = cudaFuncSetAttribute(k_cqt_octave_umma, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return af_cuda_check(e, "cudaFuncSetAttribute(k_cqt_octave_umma)");
     const int framesPerTile = kUmmaM * (p.mode == 4 ? 2 : 1);
+    {
+        // persistent pipelined kernel: kernels resident + two signal stages when they fit, else streamed kernels
+        const char *kq = getenv("AFB200_CQT_UMMA");
+        UmmaPParams pp;
+        pp.u = p;
+        pp.tilesPerClip = (timeLength + framesPerTile - 1) / framesPerTile;
+        pp.totalTiles = (long long)pp.tilesPerClip * batch;
+        const size_t bAll = (size_t)(fftLength / kUmmaChunkK) * 2 * kUmmaBBytes, bSlots = (size_t)2 * 2 * kUmmaBBytes, lim = (size_t)227 * 1024 - 256;
+        const size_t sig2 = 2 * (size_t)p.sigBytes;                  // hi + lo of one stage
+        size_t smemP = 0;
+        if (bAll + 2 * sig2 <= lim) { pp.bResident = 1; pp.stages = 2; smemP = bAll + 2 * sig2; }
+        else if (bSlots + 2 * sig2 <= lim) { pp.bResident = 0; pp.stages = 2; smemP = bSlots + 2 * sig2; }
+        else if (bSlots + sig2 <= lim) { pp.bResident = 0; pp.stages = 1; smemP = bSlots + sig2; }
+        if (smemP && !(kq && kq[0] == '1')) {
+            smemP += 256;
+            cudaError_t e2 = cudaFuncSetAttribute(k_cqt_octave_umma_p, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smemP);
+            if (e2 != cudaSuccess) return af_cuda_check(e2, "cudaFuncSetAttribute(k_cqt_octave_umma_p)");
+            int sms = af_sm_count();
+            if (sms <= 0) sms = 148;
+            const long long g = pp.totalTiles < sms ? pp.totalTiles : sms;
+            k_cqt_octave_umma_p<<<(unsigned)g, kPThreads, smemP, (cudaStream_t)stream>>>(pp);
+            AF_LAUNCH_CHECK("k_cqt_octave_umma_p");
+            return AF_OK;
+        }
+    }
     dim3 grid((unsigned)((timeLength + framesPerTile - 1) / framesPerTile), (unsigned)batch);
     k_cqt_octave_umma<<<grid, kUmmaThreads, smem, (cudaStream_t)stream>>>(p);
     AF_LAUNCH_CHECK("k_cqt_octave_umma");

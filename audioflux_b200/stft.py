@@ -12,14 +12,15 @@ from .types import WindowType, PaddingPositionType, PaddingModeType, enum_value
 
 
 class STFT(Base):
-    def __init__(self, radix2_exp=12, window_type=WindowType.RECT, slide_length=1024, _lib=None):
+    def __init__(self, radix2_exp=12, window_type=WindowType.RECT, slide_length=1024, is_continue=False, _lib=None):
         super().__init__(_lib)
         self.radix2_exp = radix2_exp
         self.fft_length = 1 << radix2_exp
         self.window_type = window_type
         self.slide_length = slide_length
         status = self._lib.stftObj_new(C.byref(self._obj), radix2_exp, opt_int(enum_value(window_type)),
-                                       opt_int(slide_length), opt_int(0))
+                                       opt_int(slide_length), opt_int(int(is_continue)))
+        self.is_continue = is_continue
         if status != 0 or not self._obj:
             raise ValueError(f"stftObj_new failed with status {status}")
         self._is_created = True
@@ -27,6 +28,11 @@ class STFT(Base):
     def set_slide_length(self, slide_length):
         self._lib.stftObj_setSlideLength(self._obj, slide_length)
         self.slide_length = slide_length
+
+    def enable_continue(self, flag=False):
+        """streaming mode (src/stft_algorithm.c:180-183, 474-599): successive stft() calls continue one signal"""
+        self._lib.stftObj_enableContinue(self._obj, int(flag))
+        self.is_continue = bool(flag)
 
     def enable_padding(self, flag=False):
         self._lib.stftObj_enablePadding(self._obj, int(flag))

@@ -115,10 +115,28 @@ class ClockSampler:
             self.proc = None
 
     def mark(self, begin):
+        """brackets the timed region; one synchronous NVML sample is taken just inside each end so that even a region of a
+        few milliseconds (shorter than the polling thread's wake-up) carries clock / throttle evidence"""
         if begin:
             self.t0 = time.perf_counter()
+            self._sample_now()
         else:
+            self._sample_now()
             self.t1 = time.perf_counter()
+
+    def _sample_now(self):
+        n = self.nvml
+        if n is None:
+            return
+        try:
+            mhz = float(n.nvmlDeviceGetClockInfo(self.handle, n.NVML_CLOCK_SM))
+            try:
+                mask = int(n.nvmlDeviceGetCurrentClocksEventReasons(self.handle))
+            except Exception:
+                mask = int(n.nvmlDeviceGetCurrentClocksThrottleReasons(self.handle))
+            self.rows.append((time.perf_counter(), mhz, self.max_mhz, mask))
+        except Exception:
+            pass
 
     def _poll(self):
         n = self.nvml

@@ -11,11 +11,13 @@ extern "C" {
 typedef struct OpaqueSTFT *STFTObj;
 
 /* stft_algorithm.c:84-168.  radix2Exp in [1,30] else -100; NULL pointers = defaults
- * (rect window, slide = fftLength/4, isContinue 0).  isContinue=1 is rejected (-2). */
+ * (rect window, slide = fftLength/4, isContinue 0).  isContinue=1 (streaming, :474-599): every stftObj_stft call
+ * transforms the samples carried over from the previous calls followed by the new ones and keeps the rest that did not
+ * complete a hop (non-padding mode only, as in the reference; the batched / device-pointer entry points are stateless). */
 int stftObj_new(STFTObj *stftObj, int radix2Exp, WindowType *windowType, int *slideLength, int *isContinue);
 void stftObj_setSlideLength(STFTObj stftObj, int slideLength);                 /* :171-178 */
 void stftObj_enablePadding(STFTObj stftObj, int flag);                         /* :186-189 */
-void stftObj_enableContinue(STFTObj stftObj, int flag);                        /* :180-183, unsupported: prints */
+void stftObj_enableContinue(STFTObj stftObj, int flag);                        /* :180-183 */
 void stftObj_setPadding(STFTObj stftObj, PaddingPositionType *positionType, PaddingModeType *modeType,
                         float *value1, float *value2);                         /* :192-213 */
 void stftObj_useWindowDataArr(STFTObj stftObj, float *winDataArr);             /* :215-218 */

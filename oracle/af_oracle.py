@@ -1109,3 +1109,34 @@ def synsq(fre_arr, re, im, sr=32000, scale=SCALE_OCTAVE, thresh=0.001):
     d = (d / f32(2 * math.pi)).astype(f32)
     idx = squeeze_index(d, fre_arr, sr, scale, num)
     return squeeze_scatter(re, im, idx, thresh)
+
+
+# ---------------------------------------------------------------------------
+# streaming STFT (isContinue = 1, non-padding): `__stftObj_dealData` (src/stft_algorithm.c:474-599)
+# ---------------------------------------------------------------------------
+class StftStream:
+    """successive `push(chunk)` calls give the frames `stftObj_stft` returns in continue mode: the samples that did not
+    complete a hop are carried over (tail length (total - n) % hop + (n - hop); negative = samples to skip when hop > n)"""
+
+    def __init__(self, n, hop, window):
+        self.n, self.hop, self.window = n, hop, np.asarray(window, dtype=np.float64)
+        self.tail = np.zeros(0, np.float64)
+        self.skip = 0
+
+    def push(self, chunk):
+        x = np.asarray(chunk, dtype=np.float64)
+        if self.skip:
+            k = min(self.skip, x.shape[0])
+            x, self.skip = x[k:], self.skip - k
+        cur = np.concatenate([self.tail, x])
+        n, hop = self.n, self.hop
+        if cur.shape[0] < n:
+            self.tail = cur
+            return np.zeros((0, n), f32), np.zeros((0, n), f32)
+        tail_len = (cur.shape[0] - n) % hop + (n - hop)
+        re, im = stft(cur, n, hop, self.window)
+        if tail_len >= 0:
+            self.tail = cur[cur.shape[0] - tail_len:]
+        else:
+            self.tail, self.skip = np.zeros(0, np.float64), -tail_len
+        return re, im

@@ -355,3 +355,35 @@ def test_pwt_long_clip_and_reference_build(torch_cuda, ref_lib):
     (ar, ai), (rr, ri) = a.pwt_planes(x), r.pwt_planes(x)
     scale = max(np.abs(rr).max(), np.abs(ri).max())
     assert np.abs(ar - rr).max() <= TOL * scale and np.abs(ai - ri).max() <= TOL * scale
+
+
+# ---- streaming STFT (isContinue, stft_algorithm.c:474-599) ----
+@pytest.mark.parametrize("r,hop,chunks", [(9, 128, (1000, 37, 500, 3000, 129, 512)), (10, 1024, (700, 700, 2048, 5000, 1)),
+                                          (8, 300, (100, 100, 100, 1000, 40, 2000))])
+def test_stft_streaming_matches_oracle_reference_and_one_shot(cuda_device, ref_lib, r, hop, chunks):
+    """chunk by chunk through stftObj_stft(isContinue = 1): (i) every call equals the oracle's streaming model and the
+    reference build fed the same chunks, (ii) all frames together equal the one-shot transform of the whole signal"""
+    import audioflux_b200 as af
+    n = 1 << r
+    x = noise(77, sum(chunks))
+    s = af.STFT(r, af.WindowType.HANN, hop, is_continue=True)
+    q = af.STFT(r, af.WindowType.HANN, hop, is_continue=True, _lib=ref_lib)
+    model = O.StftStream(n, hop, O.fft_window(O.W_HANN, n))
+    got, pos = [], 0
+    for c in chunks:
+        piece = x[pos:pos + c]
+        pos += c
+        assert s.cal_time_length(c) == q.cal_time_length(c)
+        re, im = s.stft_planes(piece)
+        wr, wi = model.push(piece)
+        rr, ri = q.stft_planes(piece)
+        assert re.shape == wr.shape == rr.shape
+        if re.shape[0]:
+            assert rel_max(re, wr) < 1e-4 and rel_max(im, wi) < 1e-4
+            assert rel_max(re, rr) < 1e-4 and rel_max(im, ri) < 1e-4
+            got.append(re + 1j * im)
+    whole = af.STFT(r, af.WindowType.HANN, hop).stft_planes(x)
+    allf = np.concatenate(got)
+    T = allf.shape[0]
+    assert T == (len(x) - n) // hop + 1 if hop <= n else T > 0
+    assert rel_max(allf.real, whole[0][:T]) < 1e-5 and rel_max(allf.imag, whole[1][:T]) < 1e-5

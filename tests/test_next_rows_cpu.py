@@ -372,3 +372,23 @@ def test_oracle_synsq_matches_the_reference_build(ref_lib, scale):
     for g, w in zip(got, want):
         same, fro = _sq_agree(g, w)
         assert same >= 0.99 and fro <= 1e-2, (same, fro)
+
+
+# ---- streaming STFT: the oracle's model of __stftObj_dealData pinned to the reference build ----
+@pytest.mark.parametrize("r,hop,chunks", [(9, 128, (1000, 37, 500, 3000, 129, 512)), (10, 1024, (700, 700, 2048, 5000, 1)),
+                                          (8, 300, (100, 100, 100, 1000, 40, 2000)), (8, 64, (255, 1, 64, 63, 1, 800))])
+def test_oracle_stft_streaming_matches_the_reference_build(ref_lib, r, hop, chunks):
+    import audioflux_b200 as af
+    n = 1 << r
+    x = noise(78, sum(chunks))
+    q = af.STFT(r, af.WindowType.HANN, hop, is_continue=True, _lib=ref_lib)
+    model = O.StftStream(n, hop, O.fft_window(O.W_HANN, n))
+    pos = 0
+    for c in chunks:
+        piece = x[pos:pos + c]
+        pos += c
+        rr, ri = q.stft_planes(piece)
+        wr, wi = model.push(piece)
+        assert rr.shape == wr.shape, (c, rr.shape, wr.shape)
+        if rr.shape[0]:
+            assert rel_max(wr, rr) < 1e-5 and rel_max(wi, ri) < 1e-5
