@@ -18,7 +18,7 @@ C1_HZ = 32.703196
 class CQT(Base):
     def __init__(self, num=84, samplate=32000, low_fre=C1_HZ, bin_per_octave=12, factor=1., beta=0.,
                  thresh=0.01, window_type=WindowType.HANN, slide_length=None,
-                 normal_type=SpectralFilterBankNormalType.AREA, is_scale=True, _lib=None):
+                 normal_type=SpectralFilterBankNormalType.AREA, is_scale=True, is_continue=False, _lib=None):
         super().__init__(_lib)
         if low_fre < 27.5:
             raise ValueError("low_fre must be >= 27.5")
@@ -29,7 +29,8 @@ class CQT(Base):
         status = self._lib.cqtObj_newWith(
             C.byref(self._obj), num, opt_int(samplate), opt_float(low_fre), opt_int(bin_per_octave),
             opt_float(factor), opt_float(beta), opt_float(thresh), opt_int(enum_value(window_type)),
-            opt_int(slide_length), opt_int(0), opt_int(enum_value(normal_type)), opt_int(int(is_scale)))
+            opt_int(slide_length), opt_int(int(is_continue)), opt_int(enum_value(normal_type)), opt_int(int(is_scale)))
+        self.is_continue = is_continue
         if status != 0 or not self._obj:
             raise ValueError(f"cqtObj_newWith failed with status {status}")
         self._is_created = True

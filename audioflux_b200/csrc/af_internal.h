@@ -203,7 +203,7 @@ int af_launch_decimate2(const float *in, int inLength, int inStride, int batch, 
 /* out[b][t][colOff + j] (row stride num) = scale[j] * sum_n xpad[t*hop + n] * kappa[j][n];
  * kappa2 = interleaved (re, im) pairs [bpo][fftLength] */
 int af_launch_cqt_octave(const float *sig, int sigLength, int sigStride, int batch, int validLength,
-                         int fftLength, int hop, int timeLength, int bpo, const float *kappa2,
+                         int fftLength, int hop, int padLeft, int timeLength, int bpo, const float *kappa2,
                          const float *scale, int num, int colOff,
                          float *outRe, float *outIm, void *stream);
 
@@ -211,14 +211,14 @@ int af_launch_cqt_octave(const float *sig, int sigLength, int sigStride, int bat
 int af_cqt_tc_supported(int fftLength, int hop, int bpo);
 void af_cqt_tc_fragments(const float *kappa2, int fftLength, float *out /* fftLength/8 * 96 * 4 floats */);
 int af_launch_cqt_octave_tc(const float *sig, int sigStride, int batch, int validLength, int fftLength, int hop,
-                            int timeLength, const float *bfrag, const float *scale, int num, int colOff,
+                            int padLeft, int timeLength, const float *bfrag, const float *scale, int num, int colOff,
                             float *outRe, float *outIm, void *stream);
 
 /* tcgen05 octave kernel (kernels/cqt_umma.cu): the staged signal itself is the Hankel A operand; hops 4 .. 128 */
 int af_cqt_umma_supported(int fftLength, int hop, int bpo);
 void af_cqt_umma_bimage(const float *kappa2, int fftLength, unsigned char *out /* fftLength/128 * 32768 bytes */);
 int af_launch_cqt_octave_umma(const float *sig, int sigStride, int batch, int validLength, int fftLength, int hop,
-                              int timeLength, const unsigned char *bimg, const float *scale, int num, int colOff,
+                              int padLeft, int timeLength, const unsigned char *bimg, const float *scale, int num, int colOff,
                               float *outRe, float *outIm, void *stream);
 
 typedef struct {

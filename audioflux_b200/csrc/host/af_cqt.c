@@ -28,6 +28,10 @@ struct OpaqueCQT {
     AfDevBuf dPostA, dPostB, dPostOut;
     AfPipe pipe;                   /* host-pointer batches: chunked copy-in / transform / copy-out */
     int pipeLength;
+    /* streaming (isContinue, cqt_algorithm.c:346-456): full-rate samples that did not complete a hop wait for the next call */
+    int isContinue;
+    float *tail; int tailLength;   /* host; tailLength < 0: samples of the next call to skip (slide > fftLength) */
+    float *cur; size_t curCap;
 };
 
 int cqtObj_newWith(CQTObj *out, int num, int *samplate, float *minFre, int *binPerOctave, float *factor,
@@ -46,11 +50,11 @@ int cqtObj_newWith(CQTObj *out, int num, int *samplate, float *minFre, int *binP
     if (beta && *beta > 0) bet = *beta;
     if (thresh && *thresh > 0) thr = *thresh;
     if (bet != 0) { af_fail(AF_ERR_UNSUPPORTED, "cqtObj_newWith: beta != 0 (VQT) is not supported"); return -2; }
-    if (isContinue && *isContinue) { af_fail(AF_ERR_UNSUPPORTED, "cqtObj_newWith: isContinue=1 (streaming) is not supported"); return -2; }
     CQTObj c = (CQTObj)calloc(1, sizeof(struct OpaqueCQT));
     if (!c) return -1;
     c->num = num; c->samplate = sr; c->binPerOctave = bpo; c->octaveNum = num / bpo; c->minFre = fmin;
     c->isScale = isScale ? *isScale : 1;
+    c->isContinue = isContinue ? *isContinue != 0 : 0;
     if (af_cqt_bank_build(&c->bank, num, sr, fmin, bpo, fac, bet, thr, windowType ? (int)*windowType : Window_Hann,
                           normalType ? (int)*normalType : SpectralFilterBankNormal_None)) { cqtObj_free(c); return -1; }
     c->fftLength = c->bank.fftLength;
@@ -75,7 +79,17 @@ int cqtObj_new(CQTObj *out, int num, int samplate, float minFre, int *isContinue
     return cqtObj_newWith(out, num, &samplate, &minFre, NULL, NULL, NULL, NULL, NULL, NULL, isContinue, NULL, NULL);
 }
 
-int cqtObj_calTimeLength(CQTObj c, int dataLength) { return (!c || dataLength <= 0) ? 0 : dataLength / c->slideLength + 1; }
+/* cqt_algorithm.c:266-299: centre-padded frames, or -- streaming -- whole frames of (carried samples + new samples) */
+static int cqt_time_length(const struct OpaqueCQT *c, int dataLength, int isContinue) {
+    if (dataLength <= 0) return 0;
+    if (!isContinue) return dataLength / c->slideLength + 1;
+    return dataLength < c->fftLength ? 0 : (dataLength - c->fftLength) / c->slideLength + 1;
+}
+int cqtObj_calTimeLength(CQTObj c, int dataLength) {
+    if (!c) return 0;
+    if (c->isContinue) return dataLength + c->tailLength <= 0 ? 0 : cqt_time_length(c, dataLength + c->tailLength, 1);
+    return cqt_time_length(c, dataLength, 0);
+}
 int cqtObj_getFFTLength(CQTObj c) { return c ? c->fftLength : 0; }
 float *cqtObj_getFreBandArr(CQTObj c) { return c ? c->bank.freBandArr : NULL; }
 void cqtObj_setScale(CQTObj c, int flag) { if (c && c->isScale != flag) { c->isScale = flag; c->scaleDirty = 1; } }
@@ -139,8 +153,7 @@ static int cqt_device(CQTObj c) {
 }
 
 /* dData [batch x dataLength] -> planes [batch x T x num] */
-static int cqt_compute(CQTObj c, const float *dData, int dataLength, int batch, float *dRe, float *dIm, void *st) {
-    const int T = cqtObj_calTimeLength(c, dataLength);
+static int cqt_compute_ex(CQTObj c, const float *dData, int dataLength, int batch, int T, int padLeft, float *dRe, float *dIm, void *st) {
     if (T <= 0) return AF_OK;
     int rc;
     const size_t half = sizeof(float) * (size_t)batch * (dataLength / 2 + 1);
@@ -162,20 +175,25 @@ static int cqt_compute(CQTObj c, const float *dData, int dataLength, int batch, 
         const char *kq = getenv("AFB200_CQT_KERNEL");
         /* tcgen05 (default where the hop allows it) > mma.sync 3xTF32 > FP32 loop; AFB200_CQT_KERNEL = mma | fp32 forces the older ones */
         if (c->dBimg && af_cqt_umma_supported(c->fftLength, hop, c->binPerOctave) && !kq) {
-            if ((rc = af_launch_cqt_octave_umma(sig, stride, batch, valid, c->fftLength, hop, T, c->dBimg,
+            if ((rc = af_launch_cqt_octave_umma(sig, stride, batch, valid, c->fftLength, hop, padLeft, T, c->dBimg,
                                                 c->dScale + (size_t)k * c->binPerOctave, c->num, o * c->binPerOctave, dRe, dIm, st))) return rc;
             continue;
         }
         if (c->dBfrag && af_cqt_tc_supported(c->fftLength, hop, c->binPerOctave) && !(kq && !strcmp(kq, "fp32"))) {
-            if ((rc = af_launch_cqt_octave_tc(sig, stride, batch, valid, c->fftLength, hop, T, c->dBfrag,
+            if ((rc = af_launch_cqt_octave_tc(sig, stride, batch, valid, c->fftLength, hop, padLeft, T, c->dBfrag,
                                               c->dScale + (size_t)k * c->binPerOctave, c->num, o * c->binPerOctave, dRe, dIm, st))) return rc;
             continue;
         }
-        if ((rc = af_launch_cqt_octave(sig, len, stride, batch, valid, c->fftLength, hop, T, c->binPerOctave,
+        if ((rc = af_launch_cqt_octave(sig, len, stride, batch, valid, c->fftLength, hop, padLeft, T, c->binPerOctave,
                                        c->dKappa2, c->dScale + (size_t)k * c->binPerOctave, c->num,
                                        o * c->binPerOctave, dRe, dIm, st))) return rc;
     }
     return AF_OK;
+}
+
+/* batched / device entry points are stateless: centre padding, every clip on its own */
+static int cqt_compute(CQTObj c, const float *dData, int dataLength, int batch, float *dRe, float *dIm, void *st) {
+    return cqt_compute_ex(c, dData, dataLength, batch, cqt_time_length(c, dataLength, 0), c->fftLength / 2, dRe, dIm, st);
 }
 
 static int cqt_chunk(void *obj, const float *dIn, int nb, float *dOut0, float *dOut1, void *st) {
@@ -189,7 +207,7 @@ int cqtObj_cqtBatch(CQTObj c, const float *data, int dataLength, int batch, floa
     af_clear_error();
     int rc = cqt_device(c);
     if (rc) return rc;
-    const int T = cqtObj_calTimeLength(c, dataLength);
+    const int T = cqt_time_length(c, dataLength, 0);
     void *st = stream ? stream : c->stream;
     if (memKind == AFB200_MEM_DEVICE) {
         st = stream;
@@ -199,10 +217,67 @@ int cqtObj_cqtBatch(CQTObj c, const float *data, int dataLength, int batch, floa
     return af_pipe_run(&c->pipe, cqt_chunk, c, data, (size_t)dataLength, batch, mReal3, mImag3, (size_t)T * c->num, st);
 }
 
+/* streaming bookkeeping of _cqtObj_dealData (cqt_algorithm.c:346-456): 1 = *cur / *curLength hold tail + new samples */
+static int cqt_continue_assemble(CQTObj c, const float *data, int dataLength, const float **cur, int *curLength) {
+    const int n = c->fftLength, hop = c->slideLength;
+    if (!c->tail) {
+        c->tail = (float *)calloc((size_t)n + (size_t)hop + 1, sizeof(float));
+        if (!c->tail) return 0;
+    }
+    const int total = c->tailLength + dataLength;
+    if (total < n) {
+        if (c->tailLength >= 0) memcpy(c->tail + c->tailLength, data, sizeof(float) * (size_t)dataLength);
+        else if (dataLength + c->tailLength > 0) memcpy(c->tail, data - c->tailLength, sizeof(float) * (size_t)(dataLength + c->tailLength));
+        c->tailLength = total;
+        c->timeLength = 0;
+        return 0;
+    }
+    const int tailLen = (total - n) % hop + (n - hop);
+    if ((size_t)total + (size_t)n > c->curCap) {
+        free(c->cur);
+        c->curCap = (size_t)total + (size_t)n;
+        c->cur = (float *)malloc(sizeof(float) * c->curCap);
+        if (!c->cur) { c->curCap = 0; return 0; }
+    }
+    int len;
+    if (c->tailLength < 0) {
+        len = dataLength + c->tailLength;
+        memcpy(c->cur, data - c->tailLength, sizeof(float) * (size_t)len);
+    } else {
+        if (c->tailLength > 0) memcpy(c->cur, c->tail, sizeof(float) * (size_t)c->tailLength);
+        memcpy(c->cur + c->tailLength, data, sizeof(float) * (size_t)dataLength);
+        len = c->tailLength + dataLength;
+    }
+    if (tailLen > 0) memcpy(c->tail, c->cur + (len - tailLen), sizeof(float) * (size_t)tailLen);
+    c->tailLength = tailLen;
+    *cur = c->cur; *curLength = len;
+    return 1;
+}
+
 void cqtObj_cqt(CQTObj c, float *dataArr, int dataLength, float *mRealArr3, float *mImageArr3) {
     if (!c || !dataArr || dataLength <= 0) return;
-    c->timeLength = cqtObj_calTimeLength(c, dataLength);
-    cqtObj_cqtBatch(c, dataArr, dataLength, 1, mRealArr3, mImageArr3, AFB200_MEM_HOST, NULL);
+    if (!c->isContinue) {
+        c->timeLength = cqt_time_length(c, dataLength, 0);
+        cqtObj_cqtBatch(c, dataArr, dataLength, 1, mRealArr3, mImageArr3, AFB200_MEM_HOST, NULL);
+        return;
+    }
+    /* streaming: carried samples + new samples, frames start at t * slide (right zero padding, cqt_algorithm.c:1317-1319) */
+    const float *x = NULL;
+    int len = 0;
+    if (!mRealArr3 || !mImageArr3) return;
+    if (!cqt_continue_assemble(c, dataArr, dataLength, &x, &len)) return;
+    af_clear_error();
+    if (cqt_device(c)) return;
+    const int T = cqt_time_length(c, len, 1);
+    c->timeLength = T;
+    if (T <= 0) return;
+    const size_t inB = sizeof(float) * (size_t)len, outB = sizeof(float) * (size_t)T * c->num;
+    void *st = c->stream;
+    if (af_devbuf_reserve(&c->dIn, inB) || af_devbuf_reserve(&c->dOutRe, outB) || af_devbuf_reserve(&c->dOutIm, outB)) return;
+    if (af_memcpy_h2d(c->dIn.ptr, x, inB, st)) return;
+    if (cqt_compute_ex(c, (const float *)c->dIn.ptr, len, 1, T, 0, (float *)c->dOutRe.ptr, (float *)c->dOutIm.ptr, st)) return;
+    if (af_memcpy_d2h(mRealArr3, c->dOutRe.ptr, outB, st) || af_memcpy_d2h(mImageArr3, c->dOutIm.ptr, outB, st)) return;
+    af_stream_sync(st);
 }
 
 /* ---- chroma: rows x num CQT planes -> rows x chromaNum (cqt_algorithm.c:484-600) ---- */
@@ -305,6 +380,6 @@ void cqtObj_free(CQTObj c) {
     af_dev_free(c->dKappa2); af_dev_free(c->dLeft); af_dev_free(c->dRight); af_dev_free(c->dScale);
     af_stream_destroy(c->stream);
     af_cqt_bank_free(&c->bank);
-    free(c->kappa2);
+    free(c->kappa2); free(c->tail); free(c->cur);
     free(c);
 }

@@ -64,6 +64,7 @@ struct OctParams {
     const float2 *kappa;          // [bpo][N] (re, im)
     const float *scale;           // [bpo]
     float *outRe, *outIm; long long outStride; int num, colOff;
+    int padLeft;                  // zero samples logically in front of the clip: N/2 (centre padding) or 0 (streaming: right padding)
     int TT;                       // frames per CTA (multiple of kFT)
     int rowLen;                   // polyphase row pitch (floats)
     int rowsA;                    // ceil(N / hop)
@@ -88,7 +89,7 @@ __global__ void k_cqt_octave(OctParams p) {
 
     // stage the tile's span of the zero-padded signal, polyphase-major
     const int span = (p.TT - 1) * h + N;
-    const long long m0 = (long long)t0 * h - N / 2;          // signal index of padded position t0*h
+    const long long m0 = (long long)t0 * h - p.padLeft;      // signal index of padded position t0*h
     // (4 independent loads in flight per thread: at the top octave the staging moves 3x more data per MAC than
     //  lower down and was load-latency bound, 28 % of that launch's stall samples; hop is a power of two in every
     //  default configuration, then the polyphase split is a shift and a mask)
@@ -221,7 +222,7 @@ struct OctTcParams {
     const float4 *bfrag;          // [N/8 k-steps][3 n-tiles][32 lanes] (hi0, hi1, lo0, lo1)
     const float *scale;           // [12]
     float *outRe, *outIm; long long outStride; int num, colOff;
-    int TT, rowLen, warps;
+    int TT, rowLen, warps, padLeft;
 };
 
 __global__ void k_cqt_octave_tc(OctTcParams p) {
@@ -236,7 +237,7 @@ __global__ void k_cqt_octave_tc(OctTcParams p) {
 
     // stage the tile's span of the zero-padded signal
     const int span = (p.TT - 1) * h + N;
-    const long long m0 = (long long)t0 * h - N / 2;
+    const long long m0 = (long long)t0 * h - p.padLeft;
     for (int i0 = threadIdx.x; i0 < span; i0 += 4 * blockDim.x) {
         float v[4];
 #pragma unroll
@@ -346,7 +347,7 @@ extern "C" int af_launch_decimate2(const float *in, int inLength, int inStride, 
 }
 
 extern "C" int af_launch_cqt_octave(const float *sig, int sigLength, int sigStride, int batch, int validLength,
-                                    int fftLength, int hop, int timeLength, int bpo, const float *kappa2,
+                                    int fftLength, int hop, int padLeft, int timeLength, int bpo, const float *kappa2,
                                     const float *scale, int num, int colOff,
                                     float *outRe, float *outIm, void *stream) {
     if (batch <= 0 || timeLength <= 0) return AF_OK;
@@ -354,7 +355,7 @@ extern "C" int af_launch_cqt_octave(const float *sig, int sigLength, int sigStri
     if (batch > 65535) return af_fail(AF_ERR_ARG, "cqt octave: batch %d > 65535 per launch", batch);
     OctParams p;
     p.sig = sig; p.sigStride = sigStride; p.sigLength = sigLength; p.validLength = validLength;
-    p.N = fftLength; p.hop = hop; p.T = timeLength; p.bpo = bpo;
+    p.N = fftLength; p.hop = hop; p.T = timeLength; p.bpo = bpo; p.padLeft = padLeft;
     p.kappa = reinterpret_cast<const float2 *>(kappa2); p.scale = scale;
     p.outRe = outRe; p.outIm = outIm; p.outStride = (long long)timeLength * num; p.num = num; p.colOff = colOff;
     p.rowsA = (fftLength + hop - 1) / hop;
@@ -437,14 +438,14 @@ extern "C" int af_cqt_tc_supported(int fftLength, int hop, int bpo) {
 }
 
 extern "C" int af_launch_cqt_octave_tc(const float *sig, int sigStride, int batch, int validLength, int fftLength, int hop,
-                                       int timeLength, const float *bfrag, const float *scale, int num, int colOff,
+                                       int padLeft, int timeLength, const float *bfrag, const float *scale, int num, int colOff,
                                        float *outRe, float *outIm, void *stream) {
     if (batch <= 0 || timeLength <= 0) return AF_OK;
     if (!af_cqt_tc_supported(fftLength, hop, 12)) return af_fail(AF_ERR_UNSUPPORTED, "cqt octave (tensor core): fftLength %d hop %d", fftLength, hop);
     if (batch > 65535) return af_fail(AF_ERR_ARG, "cqt octave: batch %d > 65535 per launch", batch);
     OctTcParams p;
     p.sig = sig; p.sigStride = sigStride; p.validLength = validLength;
-    p.N = fftLength; p.hop = hop; p.T = timeLength;
+    p.N = fftLength; p.hop = hop; p.T = timeLength; p.padLeft = padLeft;
     p.hs = 0; while ((1 << p.hs) < hop) p.hs++;
     p.bfrag = reinterpret_cast<const float4 *>(bfrag); p.scale = scale;
     p.outRe = outRe; p.outIm = outIm; p.outStride = (long long)timeLength * num; p.num = num; p.colOff = colOff;

@@ -27,19 +27,18 @@ namespace {
 constexpr int kUmmaM = 128;          // frames per tile (TMEM lanes)
 constexpr int kUmmaN = 32;           // accumulator columns (24 used: 12 bins x (re, im))
 constexpr int kUmmaChunkK = 128;     // taps per kernel chunk in shared memory
-constexpr int kUmmaBBytes = kUmmaN * kUmmaChunkK * 4;      // one part (hi or lo) of one chunk: 16 KB
-constexpr int kUmmaThreads = 256;    // 8 warps stage the signal; warp 0 lane 0 issues the MMAs; warps 0-3 run the epilogue
+constexpr int kUmmaBBytes = kUmmaN * kUmmaChunkK * 4;      // one part (hi or lo) of one chunk: 16 KB (a chunk image holds both: 32 KB,
+                                                            // per 32-tap K atom 64 rows x 128 B: rows 0-31 = hi, 32-63 = lo)
 
 struct UmmaParams {
     const float *sig; long long sigStride; int validLength;
-    int N, hop, T;
+    int N, hop, T, padLeft;       // padLeft: N/2 (centre padding) or 0 (streaming)
     const unsigned char *bimg;     // [N / 128 chunks][2 parts (hi, lo)][16 KB] pre-swizzled shared-memory images of B
     const float *scale;            // [12]
     float *outRe, *outIm; long long outStride; int num, colOff;
     int mode;                      // 0: hop 4 (no swizzle), 1: hop 8 (32B), 2: hop 16 (64B), 3: hop 32 * planes (128B),
                                    // 4: hop 2 = two hop-4 problems (even / odd frames; the odd one reads a copy shifted by 2 samples)
     int planes, rowsPerPlane, sigBytes;   // mode 3: phase planes and rows (128 B each) per plane; bytes of one signal copy
-    int boMode;                    // descriptor base_offset of row-shifted views: 0 = none (absolute-address swizzle), 1 = +rows, 2 = -rows
 };
 
 __device__ __forceinline__ uint64_t umma_desc(uint32_t smemAddr, uint32_t lboBytes, uint32_t sboBytes, uint32_t layout, uint32_t baseOff) {
@@ -78,183 +77,6 @@ __device__ __forceinline__ uint32_t sig_offset(const UmmaParams &p, int s) {
     return a ^ (((a >> 7) & 1u) << 4);                              // 32B swizzle: bit 4 ^= bit 7
 }
 
-__global__ void __launch_bounds__(kUmmaThreads) k_cqt_octave_umma(UmmaParams p) {
-    extern __shared__ __align__(1024) unsigned char smem[];
-    // [B buffers: 2 x (hi 16 KB, lo 16 KB)] [signal hi copy] [signal lo copy] [barriers] [tmem address]
-    unsigned char *sB = smem;
-    unsigned char *sHi = smem + 2 * 2 * kUmmaBBytes;
-    unsigned char *sLo = sHi + p.sigBytes;
-    uint64_t *bars = reinterpret_cast<uint64_t *>(sLo + p.sigBytes);
-    uint64_t *bFull = bars, *bEmpty = bars + 2, *accFull = bars + 4;
-    uint32_t *tmemSlot = reinterpret_cast<uint32_t *>(bars + 6);
-
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int par2 = p.mode == 4 ? 2 : 1;                           // frame parities per tile (hop 2: even and odd frames)
-    const int clip = blockIdx.y, t0 = blockIdx.x * kUmmaM * par2;
-    const int h = p.hop, N = p.N;
-    const int chunks = N / kUmmaChunkK;
-    // hop 2: [hi copy 0][hi copy 1 (shifted by 2 samples)] [lo copy 0][lo copy 1]
-    const int copyBytes = p.mode == 4 ? p.sigBytes / 2 : p.sigBytes;
-
-    if (threadIdx.x == 0) {
-        for (int i = 0; i < 2; i++) { af_mbar_init(&bFull[i], 1); af_mbar_init(&bEmpty[i], 1); }
-        af_mbar_init(accFull, 1);
-        af_fence_barrier_init();
-    }
-    if (warp == 0) {
-        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(af_smem_u32(tmemSlot)), "n"(64) : "memory");
-        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
-    }
-    __syncthreads();
-    if (threadIdx.x == 0) {                                         // first two kernel chunks are on their way while the signal is staged
-        for (int c = 0; c < 2 && c < chunks; c++) {
-            af_mbar_arrive_expect_tx(&bFull[c], 2 * kUmmaBBytes);
-            af_tma_load_1d(sB + c * 2 * kUmmaBBytes, p.bimg + (size_t)c * 2 * kUmmaBBytes, 2 * kUmmaBBytes, &bFull[c]);
-        }
-    }
-
-    // ---- stage the tile's span of the zero-padded signal: hi / lo copies through the layout's swizzle.  Four samples at
-    // a time: they share a 16-byte chunk, and every swizzle permutes whole 16-byte chunks (LDG.128 -> 2 STS.128) ----
-    {
-        const float *sig = p.sig + (long long)clip * p.sigStride;
-        const long long m0 = (long long)t0 * h - N / 2;
-        const int total = copyBytes / 4;                            // whole copy (tail beyond the span = zeros)
-        const bool vec = ((p.sigStride & 3) == 0) && ((reinterpret_cast<uintptr_t>(p.sig) & 15) == 0) && ((m0 & 3) == 0);
-        for (int cp = 0; cp < par2; cp++) {
-            const long long mc = m0 + 2 * cp;                       // copy 1 of hop 2: the signal advanced by 2 samples
-            unsigned char *dHi = sHi + cp * copyBytes, *dLo = sLo + cp * copyBytes;
-            // kLd float4 loads are in flight per thread before the first one is consumed: the tile of the top octaves is
-            // 17 k samples and the loads were the whole critical path (ncu r2: the first use of a loaded value held 25 % of
-            // the samples of the hop-128 launch)
-            constexpr int kLd = 8;
-            for (int i0 = threadIdx.x * 4; i0 < total; i0 += 4 * kUmmaThreads * kLd) {
-                float4 q[kLd];
-#pragma unroll
-                for (int b = 0; b < kLd; b++) {
-                    const int i = i0 + b * 4 * kUmmaThreads;
-                    const long long m = mc + i;
-                    q[b] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
-                    if (i >= total) continue;
-                    if (vec && cp == 0 && m >= 0 && m + 3 < p.validLength) q[b] = *reinterpret_cast<const float4 *>(sig + m);
-                    else {
-                        float *v = reinterpret_cast<float *>(&q[b]);
-#pragma unroll
-                        for (int u = 0; u < 4; u++) v[u] = (m + u >= 0 && m + u < p.validLength) ? sig[m + u] : 0.0f;
-                    }
-                }
-#pragma unroll
-                for (int b = 0; b < kLd; b++) {
-                    const int i = i0 + b * 4 * kUmmaThreads;
-                    if (i >= total) continue;
-                    const float *v = reinterpret_cast<const float *>(&q[b]);
-                    float4 hi4, lo4;
-                    float *hp = reinterpret_cast<float *>(&hi4), *lp = reinterpret_cast<float *>(&lo4);
-#pragma unroll
-                    for (int u = 0; u < 4; u++) {
-                        hp[u] = __uint_as_float(__float_as_uint(v[u]) & 0xffffe000u);
-                        lp[u] = v[u] - hp[u];
-                    }
-                    const uint32_t off = sig_offset(p, i);           // multiple of 16
-                    *reinterpret_cast<float4 *>(dHi + off) = hi4;
-                    *reinterpret_cast<float4 *>(dLo + off) = lo4;
-                }
-            }
-        }
-    }
-    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");     // generic-proxy writes -> visible to the tensor core (async proxy)
-    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-    __syncthreads();
-    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-    const uint32_t tmemD = *tmemSlot;
-
-    if (threadIdx.x == 0) {
-        // ---- the MMA issuer: D += A_hi B_hi + A_lo B_hi + A_hi B_lo for every 8 taps ----
-        constexpr uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(kUmmaN >> 3) << 17) | ((uint32_t)(kUmmaM >> 4) << 24);
-        const uint32_t aHi = af_smem_u32(sHi), aLo = af_smem_u32(sLo);
-        uint32_t layoutA, sboA, lboA;
-        if (p.mode == 0 || p.mode == 4) { layoutA = 0; sboA = 128; lboA = 16; }
-        else if (p.mode == 1) { layoutA = 6; sboA = 256; lboA = 0; }
-        else if (p.mode == 2) { layoutA = 4; sboA = 512; lboA = 0; }
-        else { layoutA = 2; sboA = 1024; lboA = 0; }
-        uint32_t acc = 0;
-        for (int c = 0; c < chunks; c++) {
-            const int buf = c & 1;
-            af_mbar_wait(&bFull[buf], (uint32_t)(c >> 1) & 1u);
-            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-            const uint32_t bBase = af_smem_u32(sB + buf * 2 * kUmmaBBytes);
-#pragma unroll 1
-            for (int ks = 0; ks < kUmmaChunkK / 8; ks++) {
-                const int n0 = c * kUmmaChunkK + ks * 8;            // first tap of this K step
-                // A: Hankel view of the signal copy at tap offset n0.  The swizzle is an XOR on absolute address bits, so a
-                // view that starts some rows further down needs no descriptor base offset (verified on B200: base_offset 0).
-                uint32_t offA;
-                if (p.mode == 3) {
-                    const int j = n0 >> 5, q = (n0 >> 3) & 3;      // 128-byte atom index along K, 32-byte step inside it
-                    offA = (uint32_t)((j % p.planes) * p.rowsPerPlane + j / p.planes) * 128u + (uint32_t)q * 32u;
-                } else {
-                    offA = (uint32_t)n0 * 4u;
-                }
-                // B: K-major 128B-swizzled [32 n][128 k] image: K atom (32 taps) = 4096 B, 32-byte step inside
-                const uint32_t offB = (uint32_t)(ks >> 2) * 4096u + (uint32_t)(ks & 3) * 32u;
-                const uint64_t dBhi = umma_desc(bBase + offB, 0, 1024, 2, 0);
-                const uint64_t dBlo = umma_desc(bBase + kUmmaBBytes + offB, 0, 1024, 2, 0);
-                for (int cp = 0; cp < par2; cp++) {
-                    const uint64_t dAhi = umma_desc(aHi + cp * copyBytes + offA, lboA, sboA, layoutA, 0);
-                    const uint64_t dAlo = umma_desc(aLo + cp * copyBytes + offA, lboA, sboA, layoutA, 0);
-                    const uint32_t d = tmemD + (uint32_t)cp * kUmmaN;
-                    umma_tf32(d, dAlo, dBhi, idesc, acc);
-                    umma_tf32(d, dAhi, dBlo, idesc, 1);
-                    umma_tf32(d, dAhi, dBhi, idesc, 1);
-                }
-                acc = 1;
-            }
-            if (c + 2 < chunks) {                                   // refill this buffer once its MMAs have read it
-                umma_commit(&bEmpty[buf]);
-                af_mbar_wait(&bEmpty[buf], (uint32_t)(c >> 1) & 1u);
-                af_mbar_arrive_expect_tx(&bFull[buf], 2 * kUmmaBBytes);
-                af_tma_load_1d(sB + buf * 2 * kUmmaBBytes, p.bimg + (size_t)(c + 2) * 2 * kUmmaBBytes, 2 * kUmmaBBytes, &bFull[buf]);
-            }
-        }
-        umma_commit(accFull);                                        // arrives when every MMA above has completed
-    }
-    __syncwarp();
-
-    // ---- epilogue (warps 0-3): TMEM lane = frame (of one parity), 24 columns = (re, im) of the 12 bins ----
-    if (warp < 4) {
-        af_mbar_wait(accFull, 0);
-        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-        for (int cp = 0; cp < par2; cp++) {
-            uint32_t r[32];
-            const uint32_t taddr = tmemD + ((uint32_t)(warp * 32) << 16) + (uint32_t)cp * kUmmaN;
-            asm volatile(
-                "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
-                "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
-                "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
-                : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
-                  "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
-                  "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
-                  "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
-                : "r"(taddr));
-            asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-            const int t = t0 + (warp * 32 + lane) * par2 + cp;
-            if (t < p.T) {
-                const long long o = (long long)clip * p.outStride + (long long)t * p.num + p.colOff;
-#pragma unroll
-                for (int j = 0; j < 12; j++) {
-                    const float s = p.scale[j];
-                    p.outRe[o + j] = __uint_as_float(r[2 * j]) * s;
-                    p.outIm[o + j] = __uint_as_float(r[2 * j + 1]) * s;
-                }
-            }
-        }
-    }
-    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-    __syncthreads();
-    if (warp == 0)
-        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmemD), "n"(64) : "memory");
-}
-
-
 // ============================================================================================
 // Persistent, warp-specialised version: one CTA per SM loops over tiles; three groups of warps run as a pipeline
 // connected by mbarriers, so the staging of tile k+1, the MMAs of tile k and the epilogue of tile k-1 overlap:
@@ -265,7 +87,17 @@ __global__ void __launch_bounds__(kUmmaThreads) k_cqt_octave_umma(UmmaParams p) 
 // per CTA by TMA); for hop 64 / 128 they are streamed per tile through the two 32 KB slots as in k_cqt_octave_umma.
 // Two accumulators in TMEM (four for hop 2) let the tensor core start tile k+1 while tile k is being read out.
 // ============================================================================================
+#define AF_TMEM_LD32(R, TADDR)                                                                                         \
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x32.b32 "                                                              \
+                 "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "                               \
+                 "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"               \
+                 : "=r"(R[0]), "=r"(R[1]), "=r"(R[2]), "=r"(R[3]), "=r"(R[4]), "=r"(R[5]), "=r"(R[6]), "=r"(R[7]),       \
+                   "=r"(R[8]), "=r"(R[9]), "=r"(R[10]), "=r"(R[11]), "=r"(R[12]), "=r"(R[13]), "=r"(R[14]), "=r"(R[15]), \
+                   "=r"(R[16]), "=r"(R[17]), "=r"(R[18]), "=r"(R[19]), "=r"(R[20]), "=r"(R[21]), "=r"(R[22]), "=r"(R[23]), \
+                   "=r"(R[24]), "=r"(R[25]), "=r"(R[26]), "=r"(R[27]), "=r"(R[28]), "=r"(R[29]), "=r"(R[30]), "=r"(R[31]) \
+                 : "r"(TADDR))
 constexpr int kPEpiWarps = 4, kPStageWarps = 7;
+constexpr int kUmmaAccCols = 64;    // TMEM columns of one accumulator: 0-31 = hi.hi + lo.hi, 32-63 = hi.lo (summed in the epilogue)
 constexpr int kPThreads = (kPEpiWarps + 1 + kPStageWarps) * 32;
 
 struct UmmaPParams {
@@ -288,7 +120,7 @@ __global__ void __launch_bounds__(kPThreads, 1) k_cqt_octave_umma_p(UmmaPParams 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int par2 = p.mode == 4 ? 2 : 1;
     const int framesPerTile = kUmmaM * par2;
-    const int h = p.hop, N = p.N;
+    const int h = p.hop;
     const int copyBytes = p.mode == 4 ? p.sigBytes / 2 : p.sigBytes;
 
     if (threadIdx.x == 0) {
@@ -300,7 +132,7 @@ __global__ void __launch_bounds__(kPThreads, 1) k_cqt_octave_umma_p(UmmaPParams 
         af_fence_barrier_init();
     }
     if (warp == 0) {
-        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(af_smem_u32(tmemSlot)), "n"(128) : "memory");
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(af_smem_u32(tmemSlot)), "n"(256) : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -317,7 +149,7 @@ __global__ void __launch_bounds__(kPThreads, 1) k_cqt_octave_umma_p(UmmaPParams 
             af_mbar_wait(&sigEmpty[s], (((uint32_t)(k / pp.stages)) & 1u) ^ 1u);
             const int clip = (int)(tile / pp.tilesPerClip), t0 = (int)(tile % pp.tilesPerClip) * framesPerTile;
             const float *sig = p.sig + (long long)clip * p.sigStride;
-            const long long m0 = (long long)t0 * h - N / 2;
+            const long long m0 = (long long)t0 * h - p.padLeft;
             const int total = copyBytes / 4;
             const bool vec = ((p.sigStride & 3) == 0) && ((reinterpret_cast<uintptr_t>(p.sig) & 15) == 0) && ((m0 & 3) == 0);
             unsigned char *sHi = sSig + (size_t)s * 2 * p.sigBytes, *sLo = sHi + p.sigBytes;
@@ -365,12 +197,14 @@ __global__ void __launch_bounds__(kPThreads, 1) k_cqt_octave_umma_p(UmmaPParams 
     } else if (warp == kPEpiWarps) {
         // ================= MMA issuer (+ kernel loads) =================
         if (lane == 0) {
-            constexpr uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(kUmmaN >> 3) << 17) | ((uint32_t)(kUmmaM >> 4) << 24);
+            constexpr uint32_t idesc32 = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(32 >> 3) << 17) | ((uint32_t)(kUmmaM >> 4) << 24);
+            constexpr uint32_t idesc64 = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(64 >> 3) << 17) | ((uint32_t)(kUmmaM >> 4) << 24);
             uint32_t layoutA, sboA, lboA;
             if (p.mode == 0 || p.mode == 4) { layoutA = 0; sboA = 128; lboA = 16; }
             else if (p.mode == 1) { layoutA = 6; sboA = 256; lboA = 0; }
             else if (p.mode == 2) { layoutA = 4; sboA = 512; lboA = 0; }
             else { layoutA = 2; sboA = 1024; lboA = 0; }
+            const int lgP = 31 - __clz(p.planes);                     // planes is a power of two (hop / 32)
             long long bLoads = 0, bUses = 0;                          // streamed mode: chunk loads issued / consumed so far
             if (pp.bResident) {
                 af_mbar_arrive_expect_tx(&bFull[0], (uint32_t)(chunks * 2 * kUmmaBBytes));
@@ -390,8 +224,13 @@ __global__ void __launch_bounds__(kPThreads, 1) k_cqt_octave_umma_p(UmmaPParams 
                 af_mbar_wait(&sigFull[s], ((uint32_t)(k / pp.stages)) & 1u);
                 af_mbar_wait(&accEmpty[a], (((uint32_t)(k >> 1)) & 1u) ^ 1u);
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-                const uint32_t aHi = af_smem_u32(sSig + (size_t)s * 2 * p.sigBytes), aLo = aHi + (uint32_t)p.sigBytes;
-                const uint32_t tmemD = tmemBase + (uint32_t)a * (kUmmaN * par2);
+                // descriptors differ only in the 14-bit start-address field (16-byte units): one base per operand, the K
+                // steps just add to it -- the single issuing thread spends ~10 instructions per K step instead of ~80
+                const uint32_t aHi = af_smem_u32(sSig + (size_t)s * 2 * p.sigBytes);
+                const uint64_t dAhi0 = umma_desc(aHi, lboA, sboA, layoutA, 0);
+                const uint64_t dAlo0 = umma_desc(aHi + (uint32_t)p.sigBytes, lboA, sboA, layoutA, 0);
+                const uint32_t tmemD = tmemBase + (uint32_t)a * (kUmmaAccCols * par2);
+                const uint64_t cpStep = (uint64_t)(copyBytes >> 4);
                 uint32_t acc = 0;
                 for (int c = 0; c < chunks; c++) {
                     uint32_t bBase;
@@ -403,24 +242,22 @@ __global__ void __launch_bounds__(kPThreads, 1) k_cqt_octave_umma_p(UmmaPParams 
                         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
                         bBase = af_smem_u32(sB + slot * 2 * kUmmaBBytes);
                     }
-#pragma unroll 1
+                    const uint64_t dB0 = umma_desc(bBase, 0, 1024, 2, 0);
+#pragma unroll 4
                     for (int ks = 0; ks < kUmmaChunkK / 8; ks++) {
                         const int n0 = c * kUmmaChunkK + ks * 8;
-                        uint32_t offA;
+                        uint32_t offA;                              // bytes
                         if (p.mode == 3) {
-                            const int j = n0 >> 5, q = (n0 >> 3) & 3;
-                            offA = (uint32_t)((j % p.planes) * p.rowsPerPlane + j / p.planes) * 128u + (uint32_t)q * 32u;
+                            const int j = n0 >> 5;
+                            offA = (uint32_t)((j & (p.planes - 1)) * p.rowsPerPlane + (j >> lgP)) * 128u + (uint32_t)(ks & 3) * 32u;
                         } else offA = (uint32_t)n0 * 4u;
-                        const uint32_t offB = (uint32_t)(ks >> 2) * 4096u + (uint32_t)(ks & 3) * 32u;
-                        const uint64_t dBhi = umma_desc(bBase + offB, 0, 1024, 2, 0);
-                        const uint64_t dBlo = umma_desc(bBase + kUmmaBBytes + offB, 0, 1024, 2, 0);
+                        const uint64_t dB = dB0 + (uint64_t)((ks >> 2) * (8192 >> 4) + (ks & 3) * 2);
+                        uint64_t dAhi = dAhi0 + (uint64_t)(offA >> 4), dAlo = dAlo0 + (uint64_t)(offA >> 4);
                         for (int cp = 0; cp < par2; cp++) {
-                            const uint64_t dAhi = umma_desc(aHi + cp * copyBytes + offA, lboA, sboA, layoutA, 0);
-                            const uint64_t dAlo = umma_desc(aLo + cp * copyBytes + offA, lboA, sboA, layoutA, 0);
-                            const uint32_t d = tmemD + (uint32_t)cp * kUmmaN;
-                            umma_tf32(d, dAlo, dBhi, idesc, acc);
-                            umma_tf32(d, dAhi, dBlo, idesc, 1);
-                            umma_tf32(d, dAhi, dBhi, idesc, 1);
+                            const uint32_t d = tmemD + (uint32_t)cp * kUmmaAccCols;
+                            umma_tf32(d, dAhi, dB, idesc64, acc);     // [hi.hi | hi.lo] -> columns 0-31 | 32-63
+                            umma_tf32(d, dAlo, dB, idesc32, 1);       // lo.hi -> columns 0-31
+                            dAhi += cpStep; dAlo += cpStep;
                         }
                         acc = 1;
                     }
@@ -448,18 +285,11 @@ __global__ void __launch_bounds__(kPThreads, 1) k_cqt_octave_umma_p(UmmaPParams 
             const int clip = (int)(tile / pp.tilesPerClip), t0 = (int)(tile % pp.tilesPerClip) * framesPerTile;
             af_mbar_wait(&accFull[a], ((uint32_t)(k >> 1)) & 1u);
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-            uint32_t r[2][32];
+            uint32_t r[2][32], q[2][32];
             for (int cp = 0; cp < par2; cp++) {
-                const uint32_t taddr = tmemBase + ((uint32_t)(warp * 32) << 16) + (uint32_t)a * (kUmmaN * par2) + (uint32_t)cp * kUmmaN;
-                asm volatile(
-                    "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
-                    "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
-                    "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
-                    : "=r"(r[cp][0]), "=r"(r[cp][1]), "=r"(r[cp][2]), "=r"(r[cp][3]), "=r"(r[cp][4]), "=r"(r[cp][5]), "=r"(r[cp][6]), "=r"(r[cp][7]),
-                      "=r"(r[cp][8]), "=r"(r[cp][9]), "=r"(r[cp][10]), "=r"(r[cp][11]), "=r"(r[cp][12]), "=r"(r[cp][13]), "=r"(r[cp][14]), "=r"(r[cp][15]),
-                      "=r"(r[cp][16]), "=r"(r[cp][17]), "=r"(r[cp][18]), "=r"(r[cp][19]), "=r"(r[cp][20]), "=r"(r[cp][21]), "=r"(r[cp][22]), "=r"(r[cp][23]),
-                      "=r"(r[cp][24]), "=r"(r[cp][25]), "=r"(r[cp][26]), "=r"(r[cp][27]), "=r"(r[cp][28]), "=r"(r[cp][29]), "=r"(r[cp][30]), "=r"(r[cp][31])
-                    : "r"(taddr));
+                const uint32_t taddr = tmemBase + ((uint32_t)(warp * 32) << 16) + (uint32_t)a * (kUmmaAccCols * par2) + (uint32_t)cp * kUmmaAccCols;
+                AF_TMEM_LD32(r[cp], taddr);
+                AF_TMEM_LD32(q[cp], taddr + 32);
             }
             asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
             asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -473,8 +303,8 @@ __global__ void __launch_bounds__(kPThreads, 1) k_cqt_octave_umma_p(UmmaPParams 
 #pragma unroll
                 for (int j = 0; j < 12; j++) {
                     const float sc = p.scale[j];
-                    re[j] = __uint_as_float(r[cp][2 * j]) * sc;
-                    im[j] = __uint_as_float(r[cp][2 * j + 1]) * sc;
+                    re[j] = (__uint_as_float(r[cp][2 * j]) + __uint_as_float(q[cp][2 * j])) * sc;
+                    im[j] = (__uint_as_float(r[cp][2 * j + 1]) + __uint_as_float(q[cp][2 * j + 1])) * sc;
                 }
                 if (((o & 3) == 0) && ((reinterpret_cast<uintptr_t>(p.outRe) & 15) == 0) && ((reinterpret_cast<uintptr_t>(p.outIm) & 15) == 0)) {
 #pragma unroll
@@ -492,13 +322,15 @@ __global__ void __launch_bounds__(kPThreads, 1) k_cqt_octave_umma_p(UmmaPParams 
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
     if (warp == 0)
-        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmemBase), "n"(128) : "memory");
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmemBase), "n"(256) : "memory");
 }
 
 }  // namespace
 
-// Pre-swizzled shared-memory images of the B operand: per 128-tap chunk, hi part then lo part, each [32 n][128 k] K-major
-// with the 128-byte swizzle (K atom of 32 taps = 4096 B = 4 groups of 8 rows x 128 B).
+// Pre-swizzled shared-memory images of the B operand: per 128-tap chunk ONE K-major 128B-swizzled [64 rows][128 k] matrix
+// whose rows 0-31 are the TF32 hi parts of the 24 (+8 zero) columns and rows 32-63 the lo parts; a K atom (32 taps) is
+// 64 rows x 128 B = 8192 B (8 groups of 8 rows).  A_hi . [B_hi | B_lo] is then one N = 64 MMA (A fetched once for both
+// products) and A_lo . B_hi an N = 32 MMA on the first 32 rows of the same image.
 extern "C" void af_cqt_umma_bimage(const float *kappa2 /* [12][N] (re, im) */, int N, unsigned char *out /* N/128 * 32 KB */) {
     memset(out, 0, (size_t)(N / kUmmaChunkK) * 2 * kUmmaBBytes);
     for (int c = 0; c < N / kUmmaChunkK; c++)
@@ -512,10 +344,12 @@ extern "C" void af_cqt_umma_bimage(const float *kappa2 /* [12][N] (re, im) */, i
                 float hi;
                 memcpy(&hi, &u, 4);
                 const float lo = v - hi;
-                const int ka = k >> 5, kk = k & 31, g = n >> 3, r = n & 7;
-                const size_t off = (size_t)ka * 4096 + (size_t)g * 1024 + (size_t)r * 128 + (size_t)(((kk >> 2) ^ r) * 16) + (size_t)(kk & 3) * 4;
-                memcpy(out + ((size_t)c * 2 + 0) * kUmmaBBytes + off, &hi, 4);
-                memcpy(out + ((size_t)c * 2 + 1) * kUmmaBBytes + off, &lo, 4);
+                const int ka = k >> 5, kk = k & 31;
+                for (int half = 0; half < 2; half++) {
+                    const int row = n + 32 * half, g = row >> 3, r = row & 7;
+                    const size_t off = (size_t)ka * 8192 + (size_t)g * 1024 + (size_t)r * 128 + (size_t)(((kk >> 2) ^ r) * 16) + (size_t)(kk & 3) * 4;
+                    memcpy(out + (size_t)c * 2 * kUmmaBBytes + off, half ? &lo : &hi, 4);
+                }
             }
 }
 
@@ -541,28 +375,24 @@ extern "C" int af_cqt_umma_supported(int fftLength, int hop, int bpo) {
     if (bpo != 12 || fftLength % kUmmaChunkK != 0 || fftLength < 2 * kUmmaChunkK) return 0;
     if (!(hop == 2 || hop == 4 || hop == 8 || hop == 16 || hop == 32 || hop == 64 || hop == 128)) return 0;
     int mode, planes, rpp, sb;
-    return cqt_umma_geometry(fftLength, hop, &mode, &planes, &rpp, &sb) <= (size_t)227 * 1024;
+    return cqt_umma_geometry(fftLength, hop, &mode, &planes, &rpp, &sb) + 256 <= (size_t)227 * 1024;
 }
 
 extern "C" int af_launch_cqt_octave_umma(const float *sig, int sigStride, int batch, int validLength, int fftLength, int hop,
-                                         int timeLength, const unsigned char *bimg, const float *scale, int num, int colOff,
+                                         int padLeft, int timeLength, const unsigned char *bimg, const float *scale, int num, int colOff,
                                          float *outRe, float *outIm, void *stream) {
     if (batch <= 0 || timeLength <= 0) return AF_OK;
     if (!af_cqt_umma_supported(fftLength, hop, 12)) return af_fail(AF_ERR_UNSUPPORTED, "cqt octave (tcgen05): fftLength %d hop %d", fftLength, hop);
     if (batch > 65535) return af_fail(AF_ERR_ARG, "cqt octave: batch %d > 65535 per launch", batch);
     UmmaParams p;
     p.sig = sig; p.sigStride = sigStride; p.validLength = validLength;
-    p.N = fftLength; p.hop = hop; p.T = timeLength;
+    p.N = fftLength; p.hop = hop; p.T = timeLength; p.padLeft = padLeft;
     p.bimg = bimg; p.scale = scale;
     p.outRe = outRe; p.outIm = outIm; p.outStride = (long long)timeLength * num; p.num = num; p.colOff = colOff;
-    { const char *bo = getenv("AFB200_UMMA_BO"); p.boMode = bo ? atoi(bo) : 0; }
-    const size_t smem = cqt_umma_geometry(fftLength, hop, &p.mode, &p.planes, &p.rowsPerPlane, &p.sigBytes);
-    cudaError_t e = cudaFuncSetAttribute(k_cqt_octave_umma, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) return af_cuda_check(e, "cudaFuncSetAttribute(k_cqt_octave_umma)");
+    (void)cqt_umma_geometry(fftLength, hop, &p.mode, &p.planes, &p.rowsPerPlane, &p.sigBytes);
     const int framesPerTile = kUmmaM * (p.mode == 4 ? 2 : 1);
     {
         // persistent pipelined kernel: kernels resident + two signal stages when they fit, else streamed kernels
-        const char *kq = getenv("AFB200_CQT_UMMA");
         UmmaPParams pp;
         pp.u = p;
         pp.tilesPerClip = (timeLength + framesPerTile - 1) / framesPerTile;
@@ -573,7 +403,7 @@ extern "C" int af_launch_cqt_octave_umma(const float *sig, int sigStride, int ba
         if (bAll + 2 * sig2 <= lim) { pp.bResident = 1; pp.stages = 2; smemP = bAll + 2 * sig2; }
         else if (bSlots + 2 * sig2 <= lim) { pp.bResident = 0; pp.stages = 2; smemP = bSlots + 2 * sig2; }
         else if (bSlots + sig2 <= lim) { pp.bResident = 0; pp.stages = 1; smemP = bSlots + sig2; }
-        if (smemP && !(kq && kq[0] == '1')) {
+        if (smemP) {
             smemP += 256;
             cudaError_t e2 = cudaFuncSetAttribute(k_cqt_octave_umma_p, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smemP);
             if (e2 != cudaSuccess) return af_cuda_check(e2, "cudaFuncSetAttribute(k_cqt_octave_umma_p)");
@@ -585,8 +415,5 @@ extern "C" int af_launch_cqt_octave_umma(const float *sig, int sigStride, int ba
             return AF_OK;
         }
     }
-    dim3 grid((unsigned)((timeLength + framesPerTile - 1) / framesPerTile), (unsigned)batch);
-    k_cqt_octave_umma<<<grid, kUmmaThreads, smem, (cudaStream_t)stream>>>(p);
-    AF_LAUNCH_CHECK("k_cqt_octave_umma");
-    return AF_OK;
+    return af_fail(AF_ERR_UNSUPPORTED, "cqt octave (tcgen05): the tile does not fit shared memory");
 }

@@ -684,8 +684,10 @@ def cqt_kernel_bank(num, sr, min_fre=32.703196, bpo=12, factor=1.0, beta=0.0, th
 
 
 def cqt(x, num=84, sr=32000, min_fre=32.703196, bpo=12, factor=1.0, beta=0.0, thresh=0.01,
-        win_type=W_HANN, hop=None, norm=NORM_NONE, is_scale=True, bank=None):
-    """`cqtObj_cqt` non-continue mode (cqt_algorithm.c:463-478, 845-1061) -> (re, im) [T, num]."""
+        win_type=W_HANN, hop=None, norm=NORM_NONE, is_scale=True, bank=None, is_continue=False):
+    """`cqtObj_cqt` (cqt_algorithm.c:463-478, 845-1061) -> (re, im) [T, num].  is_continue: the streaming variant run on
+    the assembled samples -- frames start at t * hop (right zero padding, :1317-1319) and only the whole frames of the
+    full-rate signal count, T = (L - n) / hop + 1 (:923-928)."""
     if bank is None:
         bank = cqt_kernel_bank(num, sr, min_fre, bpo, factor, beta, thresh, win_type, norm)
     n, octs, slen = bank["fft_length"], bank["octs"], bank["slen"].astype(np.float64)
@@ -693,7 +695,7 @@ def cqt(x, num=84, sr=32000, min_fre=32.703196, bpo=12, factor=1.0, beta=0.0, th
     hop = n // 4 if hop is None or hop <= 0 else hop
     x = np.asarray(x, dtype=f32)
     L = x.shape[0]
-    T = L // hop + 1
+    T = L // hop + 1 if not is_continue else ((L - n) // hop + 1 if L >= n else 0)
     out = np.zeros((T, num), dtype=np.complex128)
     cur = x
     rect = np.ones(n)
@@ -702,7 +704,7 @@ def cqt(x, num=84, sr=32000, min_fre=32.703196, bpo=12, factor=1.0, beta=0.0, th
         if k > 0:
             cur = resample_down2(cur)
             hop //= 2
-        re, im = stft(cur, n, hop, rect, is_pad=True)
+        re, im = stft(cur, n, hop, rect, is_pad=True, position=PAD_RIGHT if is_continue else PAD_CENTER)
         S = (re[:, :n // 2 + 1].astype(np.float64) + 1j * im[:, :n // 2 + 1].astype(np.float64))
         Tn = min(T, S.shape[0])
         v = S[:Tn] @ K.T
@@ -1140,3 +1142,36 @@ class StftStream:
         else:
             self.tail, self.skip = np.zeros(0, np.float64), -tail_len
         return re, im
+
+
+class CqtStream:
+    """`cqtObj_cqt` with isContinue = 1 (`_cqtObj_dealData`, cqt_algorithm.c:346-456): full-rate samples that do not
+    complete a hop are carried to the next call; every call transforms the assembled samples on their own"""
+
+    def __init__(self, num=84, sr=32000, **kw):
+        self.num, self.sr, self.kw = num, sr, kw
+        self.bank = cqt_kernel_bank(num, sr, kw.get("min_fre", 32.703196), kw.get("bpo", 12), kw.get("factor", 1.0),
+                                    kw.get("beta", 0.0), kw.get("thresh", 0.01), kw.get("win_type", W_HANN), kw.get("norm", NORM_NONE))
+        self.n = self.bank["fft_length"]
+        self.hop = kw.get("hop") or self.n // 4
+        self.tail = np.zeros(0, f32)
+        self.skip = 0
+
+    def push(self, chunk):
+        x = np.asarray(chunk, dtype=f32)
+        if self.skip:
+            k = min(self.skip, x.shape[0])
+            x, self.skip = x[k:], self.skip - k
+        cur = np.concatenate([self.tail, x])
+        n, hop = self.n, self.hop
+        if cur.shape[0] < n:
+            self.tail = cur
+            return np.zeros((0, self.num), f32), np.zeros((0, self.num), f32)
+        tail_len = (cur.shape[0] - n) % hop + (n - hop)
+        out = cqt(cur, self.num, self.sr, bank=self.bank, hop=hop, is_scale=self.kw.get("is_scale", True),
+                  bpo=self.kw.get("bpo", 12), is_continue=True)
+        if tail_len >= 0:
+            self.tail = cur[cur.shape[0] - tail_len:]
+        else:
+            self.tail, self.skip = np.zeros(0, f32), -tail_len
+        return out

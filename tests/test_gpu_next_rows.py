@@ -387,3 +387,32 @@ def test_stft_streaming_matches_oracle_reference_and_one_shot(cuda_device, ref_l
     T = allf.shape[0]
     assert T == (len(x) - n) // hop + 1 if hop <= n else T > 0
     assert rel_max(allf.real, whole[0][:T]) < 1e-5 and rel_max(allf.imag, whole[1][:T]) < 1e-5
+
+
+# ---- streaming CQT (isContinue, cqt_algorithm.c:346-456, 923-928, 1317-1319) ----
+@pytest.mark.parametrize("chunks", [(3000, 2500, 5000, 1400), (4000, 4000, 2000), (3000, 100, 37, 3000)])
+def test_cqt_streaming_matches_oracle_and_reference(cuda_device, ref_lib, chunks):
+    """chunk by chunk through cqtObj_cqt(isContinue = 1) against the oracle's streaming model and -- where the reference
+    survives the chunk sequence (it corrupts its heap on chunks shorter than a frame) -- the reference build"""
+    import audioflux_b200 as af
+    sr = 32000
+    x = tones(3, sum(chunks), sr)
+    c = af.CQT(84, sr, is_continue=True)
+    use_ref = min(chunks) >= 512
+    q = af.CQT(84, sr, is_continue=True, _lib=ref_lib) if use_ref else None
+    model = O.CqtStream(84, sr, norm=O.NORM_AREA)
+    pos, total = 0, 0
+    for n in chunks:
+        piece = x[pos:pos + n]
+        pos += n
+        T = c.cal_time_length(n)
+        re, im = c.cqt_planes(piece)
+        wr, wi = model.push(piece)
+        assert re.shape[0] == wr.shape[0] == T
+        if T:
+            assert rel_max(re, wr) < 1e-4 and rel_max(im, wi) < 1e-4
+            if use_ref:
+                rr, ri = q.cqt_planes(piece)
+                assert rel_max(re, rr) < 1e-4 and rel_max(im, ri) < 1e-4
+        total += T
+    assert total > 0

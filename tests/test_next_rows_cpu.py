@@ -392,3 +392,21 @@ def test_oracle_stft_streaming_matches_the_reference_build(ref_lib, r, hop, chun
         assert rr.shape == wr.shape, (c, rr.shape, wr.shape)
         if rr.shape[0]:
             assert rel_max(wr, rr) < 1e-5 and rel_max(wi, ri) < 1e-5
+
+
+# ---- streaming CQT: the oracle's model of _cqtObj_dealData / right-padded frames pinned to the reference build ----
+@pytest.mark.parametrize("chunks", [(3000, 2500, 5000, 1400), (4000, 4000, 2000), (3000, 3000, 3000)])
+def test_oracle_cqt_streaming_matches_the_reference_build(ref_lib, chunks):
+    import audioflux_b200 as af
+    sr = 32000
+    x = tones(3, sum(chunks), sr)
+    q = af.CQT(84, sr, is_continue=True, _lib=ref_lib)
+    model = O.CqtStream(84, sr, norm=O.NORM_AREA)
+    pos = 0
+    for n in chunks:
+        piece = x[pos:pos + n]
+        pos += n
+        rr, ri = q.cqt_planes(piece)
+        wr, wi = model.push(piece)
+        assert rr.shape == wr.shape and rr.shape[0] > 0
+        assert rel_max(wr, rr) < 1e-5 and rel_max(wi, ri) < 1e-5
