@@ -14,47 +14,95 @@
 #include <math.h>
 #include <string.h>
 #include "common.cuh"
+#include "c64.cuh"
 
 namespace {
 
 constexpr int kDecThreads = 256;
-constexpr int kDecPer = 4;                       // outputs per thread (register sliding window)
+constexpr int kDecPer = 8;                       // outputs per thread (register sliding window)
 constexpr int kDecTile = kDecThreads * kDecPer;  // outputs per CTA
+constexpr int kDecSpan = 2 * kDecTile + 64;      // staged input samples per CTA
 __constant__ float c_decTaps[64];                // [0..31] left taps (x[2i-j]), [32..62] right taps (x[2i+1+j])
 
-// out[i] = (sum_{j<32} L[j] x[2i-j] + sum_{j<31} R[j] x[2i+1+j]) / sqrt(1/2), zero outside the clip.
-// Each thread keeps a 72-sample window in registers (18 LDS.128) and produces 4 outputs: 252 FMAs with
-// the taps as constant-bank operands, instead of one shared load per FMA.
-__global__ void __launch_bounds__(kDecThreads) k_decimate2(const float *__restrict__ in, int inLength, long long inStride,
-                                                           float *__restrict__ out, long long outStride) {
-    __shared__ __align__(16) float sx[2 * kDecTile + 72];
+// shared-memory slot of staged sample i: 4 pad floats after every 32 samples keep the 16-byte alignment and spread the
+// per-thread windows (64-byte stride) over all banks: the LDS.128 of a quarter-warp are conflict-free
+__device__ __forceinline__ int dec_slot(int i) { return i + 4 * (i >> 5); }
+
+// out[i] = (sum_{j<32} L[j] x[2i-j] + sum_{j<31} R[j] x[2i+1+j]) / sqrt(1/2), zero outside the clip: a 64-tap FIR
+// h[k] over the window x[2i-32+k] (h[0] = 0, h[32-j] = L[j], h[33+j] = R[j] = c_decTaps[32+j]).  Each thread keeps an 80-sample window in
+// registers (20 LDS.128) and produces 8 outputs; the taps are consumed as (even, odd) PAIRS against the aligned sample
+// pairs of the window with packed fp32x2 FMAs -- 32 FFMA2 per output, the two halves of the accumulator added at the end.
+__global__ void __launch_bounds__(kDecThreads, 2) k_decimate2(const float *__restrict__ in, int inLength, long long inStride,
+                                                              float *__restrict__ out, long long outStride) {
+    __shared__ __align__(16) float sx[kDecSpan + 4 * (kDecSpan / 32) + 8];
     const int outLength = inLength / 2;
     const int o0 = blockIdx.x * kDecTile;
     const float *x = in + (long long)blockIdx.y * inStride;
-    const int m0 = 2 * o0 - 31;                               // sx[i] = x[m0 + i]
-    for (int i = threadIdx.x; i < 2 * kDecTile + 72; i += kDecThreads) {
-        const int m = m0 + i;
-        sx[i] = (m >= 0 && m < inLength) ? x[m] : 0.0f;
+    const int m0 = 2 * o0 - 32;                               // staged sample i = x[m0 + i]
+    __shared__ __align__(16) float sh[64];                    // the FIR in window order
+    if (threadIdx.x < 64) {
+        const int k = threadIdx.x;
+        sh[k] = k == 0 ? 0.0f : (k <= 32 ? c_decTaps[32 - k] : c_decTaps[k - 1]);
+    }
+    const bool vec = ((inStride & 3) == 0) && ((reinterpret_cast<uintptr_t>(in) & 15) == 0);
+    if (vec && m0 >= 0 && m0 + kDecSpan <= inLength) {
+        constexpr int kV = kDecSpan / 4, kPer = (kV + kDecThreads - 1) / kDecThreads;
+        float4 q[kPer];
+#pragma unroll
+        for (int b = 0; b < kPer; b++) {
+            const int v = threadIdx.x + b * kDecThreads;
+            if (v < kV) q[b] = __ldg(reinterpret_cast<const float4 *>(x + m0) + v);
+        }
+#pragma unroll
+        for (int b = 0; b < kPer; b++) {
+            const int v = threadIdx.x + b * kDecThreads;
+            if (v < kV) *reinterpret_cast<float4 *>(sx + dec_slot(4 * v)) = q[b];
+        }
+    } else {
+        for (int i = threadIdx.x; i < kDecSpan; i += kDecThreads) {
+            const int m = m0 + i;
+            sx[dec_slot(i)] = (m >= 0 && m < inLength) ? x[m] : 0.0f;
+        }
     }
     __syncthreads();
-    float w[72];
-    const float4 *s4 = reinterpret_cast<const float4 *>(sx + 8 * threadIdx.x);
+    c64 w[kDecPer + 32];                                      // aligned sample pairs (x[2o0 - 32 + 2 (8 t + n)], next)
+    // slot of sample 16 t + 4 v = slot(16 t) + 4 v + 4 ((16 (t & 1) + 4 v) >> 5): two base pointers (the odd threads' second
+    // one is a pad further) and compile-time offsets -> LDS.128 with immediate offsets
+    const float *baseA = sx + dec_slot(2 * kDecPer * threadIdx.x), *baseB = baseA + 4 * (threadIdx.x & 1);
 #pragma unroll
-    for (int v = 0; v < 18; v++) {
-        const float4 q = s4[v];
-        w[4 * v] = q.x; w[4 * v + 1] = q.y; w[4 * v + 2] = q.z; w[4 * v + 3] = q.w;
+    for (int v = 0; v < (kDecPer + 32) / 2; v++) {
+        const float4 q = *reinterpret_cast<const float4 *>(((4 * v) & 31) >= 16 ? baseB + 4 * v + 4 * ((4 * v) >> 5) : baseA + 4 * v + 4 * ((4 * v) >> 5));
+        w[2 * v] = c_pack(q.x, q.y);
+        w[2 * v + 1] = c_pack(q.z, q.w);
+    }
+    c64 acc[kDecPer];
+#pragma unroll
+    for (int q = 0; q < kDecPer; q++) acc[q] = 0ull;
+#pragma unroll
+    for (int u = 0; u < 32; u++) {
+        const c64 h = reinterpret_cast<const c64 *>(sh)[u];   // (h[2u], h[2u+1]): vector registers, so the FFMA2 take no
+                                                              // uniform-register operands (those cost two UMOV each)
+#pragma unroll
+        for (int q = 0; q < kDecPer; q++) acc[q] = v_fma(h, w[q + u], acc[q]);
     }
     const float scale = 1.4142135623730951f;                  // 1 / sqrt(0.5)
+    float r[kDecPer];
 #pragma unroll
     for (int q = 0; q < kDecPer; q++) {
-        const int c = 31 + 2 * q;                             // w[c] = x[2 * o]
-        float acc = 0.0f;
+        float a, b;
+        c_unpack(acc[q], a, b);
+        r[q] = (a + b) * scale;
+    }
+    const int o = o0 + kDecPer * threadIdx.x;
+    float *dst = out + (long long)blockIdx.y * outStride + o;
+    if (o + kDecPer <= outLength && ((outStride & 3) == 0) && ((reinterpret_cast<uintptr_t>(out) & 15) == 0)) {
 #pragma unroll
-        for (int j = 0; j < 32; j++) acc = fmaf(c_decTaps[j], w[c - j], acc);
+        for (int v = 0; v < kDecPer / 4; v++)
+            reinterpret_cast<float4 *>(dst)[v] = make_float4(r[4 * v], r[4 * v + 1], r[4 * v + 2], r[4 * v + 3]);
+    } else {
 #pragma unroll
-        for (int j = 0; j < 31; j++) acc = fmaf(c_decTaps[32 + j], w[c + 1 + j], acc);
-        const int o = o0 + kDecPer * threadIdx.x + q;
-        if (o < outLength) out[(long long)blockIdx.y * outStride + o] = acc * scale;
+        for (int q = 0; q < kDecPer; q++)
+            if (o + q < outLength) dst[q] = r[q];
     }
 }
 

@@ -62,6 +62,12 @@ __device__ __forceinline__ void umma_commit(uint64_t *bar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(af_smem_u32(bar)) : "memory");
 }
 
+__device__ __forceinline__ bool elect_one() {
+    uint32_t pred;
+    asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.b32 %0, 1, 0, p;\n\t}" : "=r"(pred));
+    return pred != 0;
+}
+
 // byte offset of sample s (floats from the tile start) inside one signal copy
 __device__ __forceinline__ uint32_t sig_offset(const UmmaParams &p, int s) {
     if (p.mode == 0 || p.mode == 4) return (uint32_t)s * 4u;
@@ -96,9 +102,9 @@ __device__ __forceinline__ uint32_t sig_offset(const UmmaParams &p, int s) {
                    "=r"(R[16]), "=r"(R[17]), "=r"(R[18]), "=r"(R[19]), "=r"(R[20]), "=r"(R[21]), "=r"(R[22]), "=r"(R[23]), \
                    "=r"(R[24]), "=r"(R[25]), "=r"(R[26]), "=r"(R[27]), "=r"(R[28]), "=r"(R[29]), "=r"(R[30]), "=r"(R[31]) \
                  : "r"(TADDR))
-constexpr int kPEpiWarps = 4, kPStageWarps = 7;
+constexpr int kPEpiWarps = 4, kPIssueWarps = 2, kPStageWarps = 7;
 constexpr int kUmmaAccCols = 64;    // TMEM columns of one accumulator: 0-31 = hi.hi + lo.hi, 32-63 = hi.lo (summed in the epilogue)
-constexpr int kPThreads = (kPEpiWarps + 1 + kPStageWarps) * 32;
+constexpr int kPThreads = (kPEpiWarps + kPIssueWarps + kPStageWarps) * 32;
 
 struct UmmaPParams {
     UmmaParams u;
@@ -117,7 +123,7 @@ __global__ void __launch_bounds__(kPThreads, 1) k_cqt_octave_umma_p(UmmaPParams 
     uint64_t *sigFull = bars, *sigEmpty = bars + 2, *accFull = bars + 4, *accEmpty = bars + 6, *bFull = bars + 8, *bEmpty = bars + 10;
     uint32_t *tmemSlot = reinterpret_cast<uint32_t *>(bars + 12);
 
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;   // (uniform for the compiler)
     const int par2 = p.mode == 4 ? 2 : 1;
     const int framesPerTile = kUmmaM * par2;
     const int h = p.hop;
@@ -140,9 +146,9 @@ __global__ void __launch_bounds__(kPThreads, 1) k_cqt_octave_umma_p(UmmaPParams 
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     const uint32_t tmemBase = *tmemSlot;
 
-    if (warp >= kPEpiWarps + 1) {
+    if (warp >= kPEpiWarps + kPIssueWarps) {
         // ================= stagers =================
-        const int sw = warp - (kPEpiWarps + 1), nst = kPStageWarps * 32, tid = sw * 32 + lane;
+        const int sw = warp - (kPEpiWarps + kPIssueWarps), nst = kPStageWarps * 32, tid = sw * 32 + lane;
         int k = 0;
         for (long long tile = blockIdx.x; tile < pp.totalTiles; tile += gridDim.x, ++k) {
             const int s = k % pp.stages;
@@ -194,9 +200,16 @@ __global__ void __launch_bounds__(kPThreads, 1) k_cqt_octave_umma_p(UmmaPParams 
             __syncwarp();
             if (lane == 0) af_mbar_arrive(&sigFull[s]);
         }
-    } else if (warp == kPEpiWarps) {
-        // ================= MMA issuer (+ kernel loads) =================
-        if (lane == 0) {
+    } else if (warp >= kPEpiWarps) {
+        // ================= MMA issuers (+ kernel loads) =================
+        // The whole warp runs the loop on warp-uniform values (descriptors live in uniform registers); one elected lane
+        // issues the asynchronous operations.  With the kernels resident and two signal stages there are TWO issuer warps,
+        // each with its own stage and TMEM accumulator (tiles k = iw, iw + 2, ...): a single thread cannot feed the tensor
+        // pipe with N = 64 MMAs.
+        const int iw = warp - kPEpiWarps;
+        const int nIssue = (pp.bResident && pp.stages == 2) ? kPIssueWarps : 1;
+        const bool leader = elect_one();
+        if (iw < nIssue) {
             constexpr uint32_t idesc32 = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(32 >> 3) << 17) | ((uint32_t)(kUmmaM >> 4) << 24);
             constexpr uint32_t idesc64 = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(64 >> 3) << 17) | ((uint32_t)(kUmmaM >> 4) << 24);
             uint32_t layoutA, sboA, lboA;
@@ -205,76 +218,92 @@ __global__ void __launch_bounds__(kPThreads, 1) k_cqt_octave_umma_p(UmmaPParams 
             else if (p.mode == 2) { layoutA = 4; sboA = 512; lboA = 0; }
             else { layoutA = 2; sboA = 1024; lboA = 0; }
             const int lgP = 31 - __clz(p.planes);                     // planes is a power of two (hop / 32)
+            const int atoms = p.N / 32;                               // 32-tap K atoms (128 B of a signal row, 8 KB of a B chunk image)
             long long bLoads = 0, bUses = 0;                          // streamed mode: chunk loads issued / consumed so far
             if (pp.bResident) {
-                af_mbar_arrive_expect_tx(&bFull[0], (uint32_t)(chunks * 2 * kUmmaBBytes));
-                for (int c = 0; c < chunks; c++)
-                    af_tma_load_1d(sB + (size_t)c * 2 * kUmmaBBytes, p.bimg + (size_t)c * 2 * kUmmaBBytes, 2 * kUmmaBBytes, &bFull[0]);
+                if (iw == 0 && leader) {
+                    af_mbar_arrive_expect_tx(&bFull[0], (uint32_t)(chunks * 2 * kUmmaBBytes));
+                    for (int c = 0; c < chunks; c++)
+                        af_tma_load_1d(sB + (size_t)c * 2 * kUmmaBBytes, p.bimg + (size_t)c * 2 * kUmmaBBytes, 2 * kUmmaBBytes, &bFull[0]);
+                }
                 af_mbar_wait(&bFull[0], 0);
             } else {
-                for (; bLoads < 2; bLoads++) {
-                    af_mbar_arrive_expect_tx(&bFull[bLoads], 2 * kUmmaBBytes);
-                    af_tma_load_1d(sB + bLoads * 2 * kUmmaBBytes, p.bimg + (size_t)(bLoads % chunks) * 2 * kUmmaBBytes, 2 * kUmmaBBytes, &bFull[bLoads]);
-                }
+                for (; bLoads < 2; bLoads++)
+                    if (leader) {
+                        af_mbar_arrive_expect_tx(&bFull[bLoads], 2 * kUmmaBBytes);
+                        af_tma_load_1d(sB + bLoads * 2 * kUmmaBBytes, p.bimg + (size_t)(bLoads % chunks) * 2 * kUmmaBBytes, 2 * kUmmaBBytes, &bFull[bLoads]);
+                    }
             }
             const long long myTiles = (pp.totalTiles - blockIdx.x + gridDim.x - 1) / gridDim.x;
-            int k = 0;
-            for (long long tile = blockIdx.x; tile < pp.totalTiles; tile += gridDim.x, ++k) {
-                const int s = k % pp.stages, a = k & 1;
+            const long long totalUses = myTiles * chunks;
+            const uint32_t cpStep = (uint32_t)(copyBytes >> 4);
+            for (long long k = iw; k < myTiles; k += nIssue) {
+                const int s = (int)(k % pp.stages), a = (int)(k & 1);
                 af_mbar_wait(&sigFull[s], ((uint32_t)(k / pp.stages)) & 1u);
                 af_mbar_wait(&accEmpty[a], (((uint32_t)(k >> 1)) & 1u) ^ 1u);
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
                 // descriptors differ only in the 14-bit start-address field (16-byte units): one base per operand, the K
-                // steps just add to it -- the single issuing thread spends ~10 instructions per K step instead of ~80
+                // steps just add to it
                 const uint32_t aHi = af_smem_u32(sSig + (size_t)s * 2 * p.sigBytes);
                 const uint64_t dAhi0 = umma_desc(aHi, lboA, sboA, layoutA, 0);
                 const uint64_t dAlo0 = umma_desc(aHi + (uint32_t)p.sigBytes, lboA, sboA, layoutA, 0);
                 const uint32_t tmemD = tmemBase + (uint32_t)a * (kUmmaAccCols * par2);
-                const uint64_t cpStep = (uint64_t)(copyBytes >> 4);
                 uint32_t acc = 0;
-                for (int c = 0; c < chunks; c++) {
-                    uint32_t bBase;
+                uint64_t dB0 = 0;
+                for (int j = 0; j < atoms; j++) {
+                    const int c = j >> 2;
                     int slot = 0;
-                    if (pp.bResident) bBase = af_smem_u32(sB + (size_t)c * 2 * kUmmaBBytes);
-                    else {
-                        slot = (int)(bUses & 1);
-                        af_mbar_wait(&bFull[slot], (uint32_t)(bUses >> 1) & 1u);
-                        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-                        bBase = af_smem_u32(sB + slot * 2 * kUmmaBBytes);
-                    }
-                    const uint64_t dB0 = umma_desc(bBase, 0, 1024, 2, 0);
-#pragma unroll 4
-                    for (int ks = 0; ks < kUmmaChunkK / 8; ks++) {
-                        const int n0 = c * kUmmaChunkK + ks * 8;
-                        uint32_t offA;                              // bytes
-                        if (p.mode == 3) {
-                            const int j = n0 >> 5;
-                            offA = (uint32_t)((j & (p.planes - 1)) * p.rowsPerPlane + (j >> lgP)) * 128u + (uint32_t)(ks & 3) * 32u;
-                        } else offA = (uint32_t)n0 * 4u;
-                        const uint64_t dB = dB0 + (uint64_t)((ks >> 2) * (8192 >> 4) + (ks & 3) * 2);
-                        uint64_t dAhi = dAhi0 + (uint64_t)(offA >> 4), dAlo = dAlo0 + (uint64_t)(offA >> 4);
-                        for (int cp = 0; cp < par2; cp++) {
-                            const uint32_t d = tmemD + (uint32_t)cp * kUmmaAccCols;
-                            umma_tf32(d, dAhi, dB, idesc64, acc);     // [hi.hi | hi.lo] -> columns 0-31 | 32-63
-                            umma_tf32(d, dAlo, dB, idesc32, 1);       // lo.hi -> columns 0-31
-                            dAhi += cpStep; dAlo += cpStep;
+                    if ((j & 3) == 0) {
+                        uint32_t bBase;
+                        if (pp.bResident) bBase = af_smem_u32(sB + (size_t)c * 2 * kUmmaBBytes);
+                        else {
+                            slot = (int)(bUses & 1);
+                            af_mbar_wait(&bFull[slot], (uint32_t)(bUses >> 1) & 1u);
+                            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                            bBase = af_smem_u32(sB + slot * 2 * kUmmaBBytes);
                         }
-                        acc = 1;
+                        dB0 = umma_desc(bBase, 0, 1024, 2, 0);
                     }
-                    if (!pp.bResident) {
-                        bUses++;
-                        // refill this slot with the chunk two uses ahead (the stream of chunks is periodic over the tiles)
-                        if (bLoads < myTiles * chunks) {
-                            umma_commit(&bEmpty[slot]);
-                            af_mbar_wait(&bEmpty[slot], (uint32_t)((bUses - 1) >> 1) & 1u);
-                            af_mbar_arrive_expect_tx(&bFull[slot], 2 * kUmmaBBytes);
-                            af_tma_load_1d(sB + slot * 2 * kUmmaBBytes, p.bimg + (size_t)(bLoads % chunks) * 2 * kUmmaBBytes, 2 * kUmmaBBytes, &bFull[slot]);
+                    // A: Hankel view of the signal copy at tap 32 j (the swizzle is an XOR on absolute address bits: a view
+                    // that starts some rows further down needs no descriptor base offset)
+                    const uint32_t aOff = p.mode == 3 ? (uint32_t)((j & (p.planes - 1)) * p.rowsPerPlane + (j >> lgP)) * 8u : (uint32_t)j * 8u;
+                    const uint64_t dAh = dAhi0 + aOff, dAl = dAlo0 + aOff;
+                    const uint64_t dB = dB0 + (uint64_t)((j & 3) * (8192 >> 4));
+                    if (leader) {
+#pragma unroll
+                        for (int q = 0; q < 4; q++) {                  // 8-tap K steps inside the atom: +32 bytes each
+                            umma_tf32(tmemD, dAh + 2 * q, dB + 2 * q, idesc64, q == 0 ? acc : 1u);    // [hi.hi | hi.lo] -> columns 0-31 | 32-63
+                            umma_tf32(tmemD, dAl + 2 * q, dB + 2 * q, idesc32, 1);                     // lo.hi -> columns 0-31
+                            if (par2 == 2) {
+                                umma_tf32(tmemD + kUmmaAccCols, dAh + cpStep + 2 * q, dB + 2 * q, idesc64, q == 0 ? acc : 1u);
+                                umma_tf32(tmemD + kUmmaAccCols, dAl + cpStep + 2 * q, dB + 2 * q, idesc32, 1);
+                            }
+                        }
+                    }
+                    acc = 1;
+                    if (!pp.bResident && (j & 3) == 3) {
+                        // this chunk's MMAs are issued: its slot is refilled (with the chunk two uses ahead; the stream of
+                        // chunks is periodic over the tiles) once they have read it -- but the wait for that comes only after
+                        // the NEXT chunk's MMAs are in the pipe, so the tensor core does not drain
+                        slot = (int)(bUses & 1);
+                        if (leader) umma_commit(&bEmpty[slot]);
+                        if (bUses >= 1 && bLoads < totalUses) {
+                            const int ps = (int)((bUses - 1) & 1);       // previous use's slot
+                            af_mbar_wait(&bEmpty[ps], (uint32_t)((bUses - 1) >> 1) & 1u);
+                            if (leader) {
+                                af_mbar_arrive_expect_tx(&bFull[ps], 2 * kUmmaBBytes);
+                                af_tma_load_1d(sB + ps * 2 * kUmmaBBytes, p.bimg + (size_t)(bLoads % chunks) * 2 * kUmmaBBytes, 2 * kUmmaBBytes, &bFull[ps]);
+                            }
                             bLoads++;
                         }
+                        bUses++;
                     }
                 }
-                umma_commit(&sigEmpty[s]);                             // the tile's MMAs have read the signal stage
-                umma_commit(&accFull[a]);                              // ... and the accumulator is complete
+                if (leader) {
+                    umma_commit(&sigEmpty[s]);                         // the tile's MMAs have read the signal stage
+                    umma_commit(&accFull[a]);                          // ... and the accumulator is complete
+                }
+                __syncwarp();
             }
         }
     } else {
@@ -285,17 +314,17 @@ __global__ void __launch_bounds__(kPThreads, 1) k_cqt_octave_umma_p(UmmaPParams 
             const int clip = (int)(tile / pp.tilesPerClip), t0 = (int)(tile % pp.tilesPerClip) * framesPerTile;
             af_mbar_wait(&accFull[a], ((uint32_t)(k >> 1)) & 1u);
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-            uint32_t r[2][32], q[2][32];
             for (int cp = 0; cp < par2; cp++) {
+                uint32_t r[32], q[32];
                 const uint32_t taddr = tmemBase + ((uint32_t)(warp * 32) << 16) + (uint32_t)a * (kUmmaAccCols * par2) + (uint32_t)cp * kUmmaAccCols;
-                AF_TMEM_LD32(r[cp], taddr);
-                AF_TMEM_LD32(q[cp], taddr + 32);
-            }
-            asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-            asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-            __syncwarp();
-            if (lane == 0) af_mbar_arrive(&accEmpty[a]);               // the tensor core may overwrite this accumulator
-            for (int cp = 0; cp < par2; cp++) {
+                AF_TMEM_LD32(r, taddr);
+                AF_TMEM_LD32(q, taddr + 32);
+                asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+                if (cp == par2 - 1) {
+                    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+                    __syncwarp();
+                    if (lane == 0) af_mbar_arrive(&accEmpty[a]);       // the tensor core may overwrite this accumulator
+                }
                 const int t = t0 + (warp * 32 + lane) * par2 + cp;
                 if (t >= p.T) continue;
                 const long long o = (long long)clip * p.outStride + (long long)t * p.num + p.colOff;
@@ -303,8 +332,8 @@ __global__ void __launch_bounds__(kPThreads, 1) k_cqt_octave_umma_p(UmmaPParams 
 #pragma unroll
                 for (int j = 0; j < 12; j++) {
                     const float sc = p.scale[j];
-                    re[j] = (__uint_as_float(r[cp][2 * j]) + __uint_as_float(q[cp][2 * j])) * sc;
-                    im[j] = (__uint_as_float(r[cp][2 * j + 1]) + __uint_as_float(q[cp][2 * j + 1])) * sc;
+                    re[j] = (__uint_as_float(r[2 * j]) + __uint_as_float(q[2 * j])) * sc;
+                    im[j] = (__uint_as_float(r[2 * j + 1]) + __uint_as_float(q[2 * j + 1])) * sc;
                 }
                 if (((o & 3) == 0) && ((reinterpret_cast<uintptr_t>(p.outRe) & 15) == 0) && ((reinterpret_cast<uintptr_t>(p.outIm) & 15) == 0)) {
 #pragma unroll
