@@ -12,6 +12,7 @@ from .cqt import CQT  # noqa: F401
 from .cwt import CWT  # noqa: F401
 from .pwt import PWT  # noqa: F401
 from .wsst import WSST, Synsq  # noqa: F401
+from .reassign import Reassign  # noqa: F401
 from .spectrogram import Spectrogram, MelSpectrogram, BarkSpectrogram, ErbSpectrogram  # noqa: F401
 from . import lib  # noqa: F401
 

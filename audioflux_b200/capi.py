@@ -79,6 +79,13 @@ REFERENCE_API = {
     "pwtObj_enableDet": (None, [vp, C.c_int]),
     "pwtObj_pwtDet": (None, [vp, vp, vp, vp]),
     "pwtObj_free": (None, [vp]),
+    # reassignment (src/reassign_algorithm.h)
+    "reassignObj_new": (C.c_int, [P(vp), C.c_int, c_int_p, c_int_p, c_int_p, c_int_p, c_float_p, c_int_p, c_int_p]),
+    "reassignObj_calTimeLength": (C.c_int, [vp, C.c_int]),
+    "reassignObj_setResultType": (None, [vp, C.c_int]),
+    "reassignObj_setOrder": (None, [vp, C.c_int]),
+    "reassignObj_reassign": (None, [vp, vp, C.c_int, vp, vp, vp, vp]),
+    "reassignObj_free": (None, [vp]),
     # synchrosqueezing (src/wsst_algorithm.h, src/synsq_algorithm.h)
     "wsstObj_new": (C.c_int, [P(vp), C.c_int, C.c_int, c_int_p, c_float_p, c_float_p, c_int_p, c_int_p, c_int_p,
                               c_float_p, c_float_p, c_float_p, c_int_p]),
@@ -153,13 +160,14 @@ EXTENSION_API = {
     "pwtObj_pwtDetBatch": (C.c_int, [vp, vp, C.c_int, vp, vp, C.c_int, vp]),
     "pwtObj_getFilterBankArr": (C.c_int, [vp, vp]),
     "wsstObj_wsstDevice": (C.c_int, [vp, vp, vp, vp, vp, vp, vp]),
+    "reassignObj_reassignBatch": (C.c_int, [vp, vp, C.c_int, C.c_int, vp, vp, vp, vp, C.c_int, vp]),
     "synsqObj_synsqDevice": (C.c_int, [vp, vp, C.c_int, vp, vp, vp, vp, vp]),
     "afb200_window": (C.c_int, [C.c_int, C.c_int, vp]),
     "afb200_auditoryFilterBank": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
                                             C.c_float, C.c_float, C.c_int, vp, vp, vp]),
     "afb200_decimatorTaps": (C.c_int, [vp, vp]),
     "afb200_mfccIntervalPlan": (C.c_int, [vp, C.c_int, vp, vp, vp, vp, vp, vp, vp, vp]),
-    "afb200_mfccBankPlan2": (C.c_int, [vp, C.c_int, vp, vp, vp, vp, vp]),
+    "afb200_mfccBankPlan2": (C.c_int, [vp, C.c_int, vp, vp, vp, vp, vp, vp, vp]),
     "afb200_chromaCqtFilterBank": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_float, vp]),
 }
 

@@ -155,6 +155,8 @@ typedef struct {
 } AfBankDev;
 /* out[r][m] = sum_k in[r][k] * bank[m][k]  (rows = batch*T); optional out <- out^postPow */
 int af_launch_bank(const AfBankDev *bank, const float *in, int rows, float postPow, float *out, void *stream);
+/* in-place SQUARE / POWER / MAG of half-spectrum planes (modes of af_launch_stft) */
+int af_launch_spec_post(float *re, float *im, long long cells, int mode, float normValue, void *stream);
 int af_launch_copy_cols(const float *in, int rows, int width, int lo, int count, float *out, void *stream);
 /* rectify (0 log10 clamp 1e-8 | 1 cube root) then out[r][c] = sum_m D[c][m] * rect(in[r][m]) */
 int af_launch_xxcc(const float *in, int rows, int num, int ccNum, int rectifyType, const float *dct,
@@ -252,6 +254,17 @@ int af_launch_synsq_index(const float *re, const float *im, int num, int n, int 
                           int samplate, const float *dNorm, int *idx, void *stream);
 int af_launch_squeeze_scatter(const float *re, const float *im, const int *idx, int num, int n, float thresh,
                               float *outRe, float *outIm, void *stream);
+
+/* reassignment (kernels/reassign.cu): coordinates -> cell indices -> order-independent 64-bit fixed-point scatter.
+ * S_h / S_dh / S_th: half-spectrum planes [batch][T][n/2+1]; out planes are ADDED to (reassign_algorithm.c:374-381). */
+typedef struct {
+    int fftLength, slideLength, samplate, timeLength, batch;
+    int reType, order, resultType;
+    float thresh;
+} AfReassignArgs;
+int af_launch_reassign(const AfReassignArgs *a, const float *r1, const float *i1, const float *r2, const float *i2,
+                       const float *r3, const float *i3, int *tIdx, int *fIdx, unsigned *maxBits,
+                       unsigned long long *accRe, unsigned long long *accIm, float *outRe, float *outIm, void *stream);
 
 void af_count_launch(int n);
 

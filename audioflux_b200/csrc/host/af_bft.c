@@ -7,6 +7,7 @@
 #include <stdlib.h>
 #include <string.h>
 #include "../af_internal.h"
+#include "../../../include/afb200_reassign.h"
 
 struct OpaqueBFT {
     int num, radix2Exp, fftLength, slideLength, samplate, binPerOctave;
@@ -39,6 +40,7 @@ struct OpaqueBFT {
     float *dDctT; int dctReady;          /* general path: transposed DCT [num][num] */
     AfPipe pipe;                         /* host-pointer batches: chunked copy-in / transform / copy-out */
     int pipeLength, pipeCc, pipeRectify; /* arguments of the call the pipe is currently serving */
+    ReassignObj reassign;                /* isReassign = 1 (bft_algorithm.c:332-341): the bank is applied to the reassigned spectrum */
 };
 
 static int bft_chunk(void *obj, const float *dIn, int nb, float *dOut0, float *dOut1, void *st);
@@ -67,8 +69,8 @@ int bftObj_new(BFTObj *out, int num, int radix2Exp, int *samplate, float *lowFre
         return -1;
     }
     if (num < 2 || num > n / 2 + 1) { printf("num is error!\n"); return -1; }
-    if ((isReassign && *isReassign) || (isTemporal && *isTemporal)) {
-        af_fail(AF_ERR_UNSUPPORTED, "bftObj_new: isReassign / isTemporal are outside the accelerated path and not supported");
+    if (isTemporal && *isTemporal) {
+        af_fail(AF_ERR_UNSUPPORTED, "bftObj_new: isTemporal is outside the accelerated path and not supported");
         return -2;
     }
     AfBftSpec spec;
@@ -80,7 +82,15 @@ int bftObj_new(BFTObj *out, int num, int radix2Exp, int *samplate, float *lowFre
     spec.scaleType = scale;
     spec.styleType = styleType ? (int)*styleType : SpectralFilterBankStyle_Slaney;
     spec.normalType = normalType ? (int)*normalType : SpectralFilterBankNormal_None;
-    return af_bft_create(&spec, out);
+    int status = af_bft_create(&spec, out);
+    if (!status && isReassign && *isReassign) {
+        /* bft_algorithm.c:332-341: Reassign_All with the reassign object's own defaults (thresh 0.001, no padding) */
+        ReassignType reType = Reassign_All;
+        WindowType wt = (WindowType)spec.windowType;
+        status = reassignObj_new(&(*out)->reassign, r, &sr, &wt, &spec.slideLength, &reType, NULL, NULL, NULL);
+        if (status) { bftObj_free(*out); *out = NULL; }
+    }
+    return status;
 }
 
 /* tables of a BFT object from fully resolved parameters (shared with spectrogramObj_new, host/af_spectrogram.c) */
@@ -193,7 +203,7 @@ static int bft_compute(BFTObj b, const float *dData, int dataLength, int batch, 
     if (T <= 0) return AF_OK;
     /* real mode at fftLength 2048 with a banded bank: the fused TMA-fed kernel of the MFCC path, stopped after the
      * filter bank (one launch, no spectrum round trip through HBM: 3.3x the general composition below) */
-    if (b->resultType && b->normValue == 1.0f && b->scaleType != SpectralFilterBankScale_Linear && b->bankDev.banded &&
+    if (!b->reassign && b->resultType && b->normValue == 1.0f && b->scaleType != SpectralFilterBankScale_Linear && b->bankDev.banded &&
         af_mfcc_fused_supported(b->fftLength, b->num, 1, &b->bands) && b->slideLength % 4 == 0 && dataLength % 4 == 0 &&
         ((size_t)dData & 15) == 0 && !getenv("AFB200_BFT_GENERAL")) {
         int rc = AF_OK;
@@ -241,9 +251,19 @@ static int bft_compute(BFTObj b, const float *dData, int dataLength, int batch, 
         float *oRe = dRe + (size_t)c0 * T * b->num;
         float *oIm = dIm ? dIm + (size_t)c0 * T * b->num : NULL;
         float *sRe = (float *)b->dSpecRe.ptr, *sIm = (float *)b->dSpecIm.ptr;
+        if (b->reassign) {
+            /* reassigned half spectrum (added into zeroed planes), then the same square / power / magnitude step */
+            if ((rc = af_devbuf_reserve(&b->dSpecIm, perClip * chunk))) return rc;
+            sIm = (float *)b->dSpecIm.ptr;
+            if ((rc = af_memset_d(sRe, 0, perClip * nb, st)) || (rc = af_memset_d(sIm, 0, perClip * nb, st))) return rc;
+            if ((rc = reassignObj_reassignBatch(b->reassign, src.data, dataLength, nb, sRe, sIm, NULL, NULL, AFB200_MEM_DEVICE, st))) return rc;
+            const int mode = b->resultType ? (b->dataType == SpectralData_Mag ? AF_STFT_MAG : AF_STFT_POWER)
+                                           : (b->dataType == SpectralData_Power ? AF_STFT_SQUARE : AF_STFT_HALF);
+            if ((rc = af_launch_spec_post(sRe, sIm, (long long)rows * width, mode, b->normValue, st))) return rc;
+        }
         if (b->resultType) {                                  /* real: sum_k w |z|^2 (or |z|) */
             const int mode = b->dataType == SpectralData_Mag ? AF_STFT_MAG : AF_STFT_POWER;
-            if ((rc = af_launch_stft(&src, mode, b->normValue, sRe, NULL, st))) return rc;
+            if (!b->reassign && (rc = af_launch_stft(&src, mode, b->normValue, sRe, NULL, st))) return rc;
             const float post = (b->dataType == SpectralData_Mag) ? b->normValue : 1.0f;
             if (linear && post == 1.0f) {
                 if ((rc = af_launch_copy_cols(sRe, rows, width, b->lowIndex, count, oRe, st))) return rc;
@@ -252,7 +272,7 @@ static int bft_compute(BFTObj b, const float *dData, int dataLength, int batch, 
             }
         } else {                                              /* complex: sum_k w z^2 (or z) */
             const int mode = b->dataType == SpectralData_Power ? AF_STFT_SQUARE : AF_STFT_HALF;
-            if ((rc = af_launch_stft(&src, mode, 1.0f, sRe, sIm, st))) return rc;
+            if (!b->reassign && (rc = af_launch_stft(&src, mode, 1.0f, sRe, sIm, st))) return rc;
             if (linear) {
                 if ((rc = af_launch_copy_cols(sRe, rows, width, b->lowIndex, count, oRe, st))) return rc;
                 if (oIm && (rc = af_launch_copy_cols(sIm, rows, width, b->lowIndex, count, oIm, st))) return rc;
@@ -337,7 +357,7 @@ static int mfcc_compute(BFTObj b, const float *dData, int dataLength, int batch,
                         float *dOut, int nPeer, float *const *peerOut, void *st) {
     const int T = bftObj_calTimeLength(b, dataLength);
     int rc;
-    const int fusable = b->normValue == 1.0f && b->scaleType != SpectralFilterBankScale_Linear &&
+    const int fusable = !b->reassign && b->normValue == 1.0f && b->scaleType != SpectralFilterBankScale_Linear &&
                         b->bankDev.banded && af_mfcc_fused_supported(b->fftLength, b->num, ccNum, &b->bands) &&
                         b->slideLength % 4 == 0 && dataLength % 4 == 0 && ((size_t)dData & 15) == 0;
     if (fusable && bft_v2_usable(b, ccNum)) {
@@ -462,6 +482,7 @@ void bftObj_free(BFTObj b) {
     if (!b) return;
     af_mfcc_plan_free(b->mfccPlan); af_mfcc_plan_free(b->melPlan);
     af_mfcc2_plan_free(b->mfccPlan2); af_mfcc2_plan_free(b->melPlan2);
+    reassignObj_free(b->reassign);
     af_devbuf_free(&b->dIn); af_devbuf_free(&b->dSpecRe); af_devbuf_free(&b->dSpecIm);
     af_devbuf_free(&b->dOutRe); af_devbuf_free(&b->dOutIm);
     af_dev_free(b->dWindow); af_dev_free(b->dBank); af_dev_free(b->dPacked);

@@ -215,6 +215,19 @@ __global__ void k_phase(const float *__restrict__ re, const float *__restrict__ 
     out[i] = atan2f(im[r * width + k], a);
 }
 
+// spectrum planes -> what the bank consumes (bft_algorithm.c:456-497), in place: SQUARE (re, im) <- z^2; POWER re <- |z|^2
+// (optionally ^normValue); MAG re <- |z|.  Used after the reassignment scatter (the STFT kernel fuses this step itself).
+__global__ void k_spec_post(float *__restrict__ re, float *__restrict__ im, long long cells, int mode, float normValue) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= cells) return;
+    const float a = re[i], b = im[i];
+    if (mode == AF_STFT_SQUARE) { re[i] = a * a - b * b; im[i] = 2.0f * a * b; return; }
+    float v = a * a + b * b;
+    if (mode == AF_STFT_MAG) v = sqrtf(v);
+    else if (normValue != 1.0f) v = powf(v, normValue);
+    re[i] = v;
+}
+
 }  // namespace
 
 extern "C" int af_launch_bank(const AfBankDev *bank, const float *in, int rows, float postPow, float *out, void *stream) {
@@ -283,5 +296,12 @@ extern "C" int af_launch_phase(const float *re, const float *im, int rows, int w
     if (total <= 0) return AF_OK;
     k_phase<<<(unsigned)((total + 255) / 256), 256, 0, (cudaStream_t)stream>>>(re, im, rows, width, lo, count, out);
     AF_LAUNCH_CHECK("k_phase");
+    return AF_OK;
+}
+
+extern "C" int af_launch_spec_post(float *re, float *im, long long cells, int mode, float normValue, void *stream) {
+    if (cells <= 0 || mode == AF_STFT_HALF) return AF_OK;
+    k_spec_post<<<(unsigned)((cells + 255) / 256), 256, 0, (cudaStream_t)stream>>>(re, im, cells, mode, normValue);
+    AF_LAUNCH_CHECK("k_spec_post");
     return AF_OK;
 }

@@ -19,8 +19,10 @@
 //  * the filter bank is applied per TILE by the helper warps, not per frame by the frame warps: the power spectra of
 //    the tile's frames sit in shared memory as [bin pair][frame], lane = frame, and every bin pair is multiplied
 //    ONCE for the two filters that overlap on it (interval form: rising slope of filter i, falling slope of filter
-//    i-1, the reference's own float weights, no re-normalisation) with packed FFMA2; the weights are warp-uniform and
-//    come from the kernel parameter block (constant bank, no shared-memory traffic);
+//    i-1, the reference's own float weights, no re-normalisation) with packed FFMA2.  The intervals are cut into PIECES of
+//    at most Lmax bin pairs (host-planned, Lmax = 3 for the 128-band mel bank) so that the 128 helper lanes carry equal
+//    work (the longest interval is 15 pairs, the mean 4.5); a piece's partial sums go into a slot that ALIASES the power
+//    tile rows its pass has finished reading, and are added up per band in a fixed order (bit-stable);
 //  * the 13 x cc result tile is staged in shared memory and leaves as one TMA bulk store per destination (this GPU and,
 //    for the fused all-gather, every peer GPU): full lines over NVLink instead of 32-bit stores.
 #include <math.h>
@@ -55,7 +57,8 @@ constexpr int kMaxPeers = 15;
 constexpr int kMaxNum = 128;
 constexpr int kLPitch = 132;        // log-mel tile row pitch (floats): 4g + t -> 32 distinct banks for mma A fragments
 constexpr int kMaxTab = 1408;       // bank table entries (one float4 per bin pair of an interval) in the parameter block
-constexpr int kMaxPass = (kMaxNum + 1 + kEW * 32 - 1) / (kEW * 32);   // bank passes: one interval per helper lane and pass
+constexpr int kMaxPass = 2;         // bank passes: one piece per helper lane and pass
+constexpr int kMaxPieces = kMaxPass * kEW * 32;
 constexpr int kSpecPitch = 17;      // c64 slots per n2 row of the special-column buffer (odd -> conflict-free both ways)
 constexpr int kScratchFloats = 33 * 32;
 
@@ -65,13 +68,16 @@ struct Plan {
     float *dDct;                    // [128 m][dctPitch]
     int num, ccNum, ct, dataType;
     unsigned ivDesc[kMaxNum + 4];   // (first bin pair << 16) | table offset; entries num+1.. = end sentinels
-    int nPass, passLen[kMaxPass];   // bank passes and the longest interval (bin pairs) of each
-    unsigned short assign[kMaxPass * kEW * 32];   // interval of helper lane (pass, warp * 32 + lane), 0xffff = none
+    int nPass, passLen[kMaxPass];   // bank passes and the longest piece (bin pairs) of each
+    int nPieces, lmax, firstPass2;  // pieces 0 .. firstPass2-1 run in pass 0
+    unsigned pieceDesc[kMaxPieces];                  // (first bin pair << 20) | (pairs << 16) | table offset
+    unsigned short piecePrefix[kMaxNum + 4];         // first piece of interval i; [num + 1 ..] = nPieces
+    unsigned short assign[kMaxPass * kEW * 32];      // piece of helper lane (pass, warp * 32 + lane), 0xffff = none
     int tabLen;
     float4 *tab;                    // host copy of the bank table
     float4 *dTab;                   // device copy, staged into shared memory by every CTA
     unsigned *dDesc;
-    unsigned short *dAssign;
+    unsigned short *dAssign, *dPrefix;
 };
 
 struct Params {
@@ -84,12 +90,13 @@ struct Params {
     int num, ccNum, rectify, dataType, rawMel, pitchPairs, bulkStore, dctPitch;
     int nPeer;
     float *peerOut[kMaxPeers];
-    int offSpan, offScratch, offP, offWin, offTw, offSpec, offDct, offL, offG, offStage, offBar, offTab, offDesc, offAssign, stageBytes;   // offL: two log-mel tiles
+    int offSpan, offScratch, offP, offWin, offTw, offSpec, offDct, offL, offStage, offBar, offTab, offDesc, offAssign, offPrefix, stageBytes;   // offL: two log-mel tiles
     int nPass, passLen[kMaxPass];
     const unsigned short *assign;
     int tabLen;
     const float4 *bankTab;          // [tabLen] (rise[2q], rise[2q+1], fall[2q], fall[2q+1]) per bin pair of an interval
-    const unsigned *ivDesc;         // [kMaxNum + 4]
+    const unsigned *pieceDesc;      // [kMaxPieces]
+    const unsigned short *piecePrefix;   // [kMaxNum + 4]
 };
 
 __device__ __forceinline__ void named_bar_sync(int id, int threads) {
@@ -131,7 +138,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_mfcc_fused2(const __grid_consta
     float4 *sTab = reinterpret_cast<float4 *>(smem + p.offTab);           // interval-form bank weights
     unsigned *sDesc = reinterpret_cast<unsigned *>(smem + p.offDesc);
     unsigned short *sAssign = reinterpret_cast<unsigned short *>(smem + p.offAssign);
-    float *sG = reinterpret_cast<float *>(smem + p.offG);                 // [16][kLPitch] falling-slope sums Fl_i (sL holds R_i)
+    unsigned short *sPrefix = reinterpret_cast<unsigned short *>(smem + p.offPrefix);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int pitch = p.pitchPairs;
@@ -140,9 +147,9 @@ __global__ void __launch_bounds__(kThreads, 1) k_mfcc_fused2(const __grid_consta
     for (int i = threadIdx.x; i < 32 * 32; i += kThreads) sWin[i] = p.winPairs[i];
     for (int i = threadIdx.x; i < 17 * 32; i += kThreads) sTw[i] = p.tw[i];
     for (int i = threadIdx.x; i < p.tabLen; i += kThreads) sTab[i] = p.bankTab[i];
-    for (int i = threadIdx.x; i < kMaxNum + 4; i += kThreads) sDesc[i] = p.ivDesc[i];
+    for (int i = threadIdx.x; i < kMaxPieces; i += kThreads) sDesc[i] = p.pieceDesc[i];
+    for (int i = threadIdx.x; i < kMaxNum + 4; i += kThreads) sPrefix[i] = p.piecePrefix[i];
     for (int i = threadIdx.x; i < kMaxPass * kEW * 32; i += kThreads) sAssign[i] = p.assign[i];
-    for (int i = threadIdx.x; i < 16 * kLPitch; i += kThreads) sG[i] = 0.0f;
     for (int i = threadIdx.x; i < kFW * kScratchFloats; i += kThreads) scratchAll[i] = 0.0f;
     for (int i = threadIdx.x; i < kPairs * pitch * 2; i += kThreads) sP[i] = 0.0f;
     for (int i = threadIdx.x; i < 2 * 32 * kSpecPitch; i += kThreads) sSpec[i] = 0ull;
@@ -187,7 +194,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_mfcc_fused2(const __grid_consta
         for (long long tile = blockIdx.x; tile < p.totalTiles; tile += gridDim.x, ++it) {
             const int stage = it % S;
             if (lane == 0) {
-                af_mbar_wait(&emptyBar[stage], (uint32_t)(it / S) & 1u);       // tile `it` taken: refill the slot
+                af_mbar_wait_sleepy(&emptyBar[stage], (uint32_t)(it / S) & 1u);       // tile `it` taken: refill the slot
                 const long long next = tile + (long long)S * gridDim.x;
                 if (next < p.totalTiles) issue(next, stage);
             }
@@ -243,20 +250,22 @@ __global__ void __launch_bounds__(kThreads, 1) k_mfcc_fused2(const __grid_consta
             float *L = sL + (size_t)lbuf * 16 * kLPitch;
             float *stage = sStage + (size_t)lbuf * (p.stageBytes / 8);   // (filter-bank output mode: two staging tiles)
             const int stagePitch = p.num + 4;                              // padded rows (bank conflicts)
-            af_mbar_wait(pFull, (uint32_t)it & 1u);
+            af_mbar_wait_sleepy(pFull, (uint32_t)it & 1u);
             if (!p.rawMel) af_mbar_wait(&lEmpty[lbuf], ((uint32_t)(it >> 1) & 1u) ^ 1u);    // DCT done with tile it - 2
-            // ---- phase 1: ONE INTERVAL PER LANE, all frames of the tile in registers.  Pass after pass (longest
-            // intervals first, host-planned so that the 16 lanes of a half-warp start in different 8-byte bank pairs) a lane
-            // walks the bin pairs of its interval: one LDS.128 of weights (rise of filter i, fall of filter i-1) and, per
-            // frame, one LDS.64 of the power pair + two FFMA2: kFW independent accumulator chains per lane.
+            // ---- phase 1: ONE PIECE (<= Lmax bin pairs of one interval) PER LANE AND PASS, all frames of the tile in
+            // registers: one LDS.128 of weights (rise of filter i, fall of filter i-1) and, per frame, one LDS.64 of the
+            // power pair + two FFMA2 -- kFW independent accumulator chains per lane.  Pass 0 walks the low rows of the
+            // power tile, pass 1 the rest; once every helper warp is through a pass the rows it read are dead and take
+            // the pieces' partial sums S[piece][frame] = (rise part, fall part), piece index = row index.
+            c64 *sS = reinterpret_cast<c64 *>(sP);
             if (!(AF2_ABLATE & 1)) {
                 for (int ps = 0; ps < p.nPass; ps++) {
-                    const unsigned iv = sAssign[(ps * kBW + e) * 32 + lane];
-                    const bool have = iv != 0xffffu;
-                    const unsigned d0 = sDesc[have ? iv : 0], d1 = sDesc[have ? iv + 1 : 0];
-                    const int len = have ? (int)(d1 & 0xffffu) - (int)(d0 & 0xffffu) : 0;
+                    const unsigned piece = sAssign[(ps * kBW + e) * 32 + lane];
+                    const bool have = piece != 0xffffu;
+                    const unsigned d0 = sDesc[have ? piece : 0];
+                    const int len = have ? (int)((d0 >> 16) & 15u) : 0;
                     const float4 *wt = sTab + (d0 & 0xffffu);
-                    const c64 *q = reinterpret_cast<const c64 *>(sP) + (size_t)(d0 >> 16) * pitch;
+                    const c64 *q = reinterpret_cast<const c64 *>(sP) + (size_t)(d0 >> 20) * pitch;
                     c64 aR[kFW], aF[kFW];
 #pragma unroll
                     for (int f = 0; f < kFW; f++) { aR[f] = 0ull; aF[f] = 0ull; }
@@ -274,41 +283,44 @@ __global__ void __launch_bounds__(kThreads, 1) k_mfcc_fused2(const __grid_consta
                             q += pitch;
                         }
                     }
+                    named_bar_sync(3, kBW * 32);                   // every helper warp has read this pass's rows
                     if (have) {
 #pragma unroll
                         for (int f = 0; f < kFW; f++) {
                             float r0, r1, f0_, f1_;
                             c_unpack(aR[f], r0, r1);
                             c_unpack(aF[f], f0_, f1_);
-                            L[f * kLPitch + iv] = r0 + r1;             // R_i: rising part of filter i (zero for i = num)
-                            sG[f * kLPitch + iv] = f0_ + f1_;          // Fl_i: falling part of filter i - 1
+                            sS[(size_t)piece * pitch + f] = c_pack(r0 + r1, f0_ + f1_);
                         }
                     }
                 }
             }
-            __syncwarp();
-            if (lane == 0) af_mbar_arrive(pEmpty);                 // frame warps may overwrite the power tile
             if (p.rawMel && e == 0) bulk_wait_read0();             // the store of tile it - 2 has read this staging tile
-            named_bar_sync(3, kBW * 32);                           // every R_i / Fl_i of the tile is in shared memory
-            // ---- phase 2: mel_m = R_m + Fl_{m+1}, rectified in place (cepstra) or staged as the result row (filter bank) ----
+            named_bar_sync(1, kBW * 32);                           // every partial sum of the tile is in shared memory
+            // ---- phase 2: mel_m = sum of the rise parts of interval m + the fall parts of interval m + 1 (pieces in
+            // ascending order), rectified (cepstra) or staged as the result row (filter bank) ----
             if (!(AF2_ABLATE & 1)) {
                 for (int m = e * 32 + lane; m < p.num; m += kBW * 32) {
+                    const int a0 = sPrefix[m], a1 = sPrefix[m + 1], a2 = sPrefix[m + 2];
 #pragma unroll
                     for (int f = 0; f < kFW; f++) {
-                        const float v = L[f * kLPitch + m] + sG[f * kLPitch + m + 1];
+                        float v = 0.0f;
+                        for (int s = a0; s < a1; s++) v += c_re(sS[(size_t)s * pitch + f]);
+                        for (int s = a1; s < a2; s++) v += c_im(sS[(size_t)s * pitch + f]);
                         if (p.rawMel) { if (f < nf) stage[f * stagePitch + m] = v; }
                         else L[f * kLPitch + m] = rectify_value(v, p.rectify);
                     }
                 }
             }
+            __syncwarp();
+            if (lane == 0) af_mbar_arrive(pEmpty);                 // frame warps may overwrite the power tile (and the sums in it)
             if (!p.rawMel) {
                 __syncwarp();
                 if (lane == 0) af_mbar_arrive(&lFull[lbuf]);       // the DCT warps take the tile from here
-                named_bar_sync(1, kBW * 32);                       // sG is free for the next tile's phase 1
                 continue;
             }
             fence_proxy_async_smem();
-            named_bar_sync(1, kBW * 32);                           // the result rows are staged (and sG is free again)
+            named_bar_sync(3, kBW * 32);                           // the result rows are staged
             const long long tileOff = ((long long)clip * p.timeLength + f0) * rowFloats;
             if (p.bulkStore) {
                 if (e == 0) {                                       // one row per lane (padded staging rows)
@@ -338,7 +350,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_mfcc_fused2(const __grid_consta
             const int nf = min(F, p.timeLength - f0);
             const int lbuf = it & 1;
             const float *L = sL + (size_t)lbuf * 16 * kLPitch;
-            af_mbar_wait(&lFull[lbuf], (uint32_t)(it >> 1) & 1u);
+            af_mbar_wait_sleepy(&lFull[lbuf], (uint32_t)(it >> 1) & 1u);
             // out[16 x 8 CT] = L[16 x 128] . D^T[128 x 8 CT]: mma.sync m16n8k8 TF32, 3xTF32 split (hi by truncation,
             // lo = x - hi exact), separate accumulators for hi*hi and the cross terms
             float acc[kNB][4], acx[kNB][4];
@@ -537,7 +549,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_mfcc_fused2(const __grid_consta
 
 void free_plan(Plan *pl) {
     if (!pl) return;
-    af_dev_free(pl->dWinPairs); af_dev_free(pl->dTw); af_dev_free(pl->dDct); af_dev_free(pl->dTab); af_dev_free(pl->dDesc); af_dev_free(pl->dAssign);
+    af_dev_free(pl->dWinPairs); af_dev_free(pl->dTw); af_dev_free(pl->dDct); af_dev_free(pl->dTab); af_dev_free(pl->dDesc); af_dev_free(pl->dAssign); af_dev_free(pl->dPrefix);
     free(pl->tab);
     free(pl);
 }
@@ -610,42 +622,68 @@ int build_table(const float *bank, int num, const Intervals *iv, unsigned *desc 
     return off;
 }
 
-// One interval per helper lane and pass: intervals sorted by length (bin pairs), the longest kEW*32 form pass 0, the
-// next ones pass 1, ...; inside a pass the intervals are dealt to half-warps (16 lanes) such that their first bin
-// pairs differ mod 16 where possible: with the odd tile pitch the 16 lanes then read 16 different 8-byte bank pairs
-// for every frame and every step of the walk (conflict-free LDS.64).
-int plan_passes(int num, const unsigned *desc, unsigned short *assign /* kMaxPass * kEW * 32 */, int *passLen /* kMaxPass */) {
+// Pieces: every interval is cut into runs of at most lmax bin pairs (interval order = ascending rows of the power tile).
+// The first min(128, n) pieces form pass 0, the rest pass 1; a piece's partial sums are stored in row `piece index` of the
+// power tile once its pass is over, so pass 1 must not read rows below the number of pass-0 pieces.  lmax is the smallest
+// value for which the pieces fit two passes and that condition holds.  Inside a pass the pieces are dealt to half-warps
+// (16 lanes) such that their first rows differ mod 16 where possible: with the odd tile pitch the 16 lanes then read 16
+// different 8-byte bank pairs for every frame and every step of the walk (conflict-free LDS.64).
+// Returns the number of passes (1 or 2) or -1 when no lmax <= 15 works.
+struct PiecePlan {
+    int nPieces, lmax, firstPass2, nPass, passLen[kMaxPass];
+    unsigned pieceDesc[kMaxPieces];
+    unsigned short prefix[kMaxNum + 4];
+    unsigned short assign[kMaxPass * kEW * 32];
+};
+
+int plan_pieces(int num, const unsigned *desc /* num + 2 */, PiecePlan *pp) {
     const int W = kEW * 32, n = num + 1;
-    int order[kMaxNum + 1], len[kMaxNum + 1];
-    for (int i = 0; i < n; i++) { order[i] = i; len[i] = (int)(desc[i + 1] & 0xffffu) - (int)(desc[i] & 0xffffu); }
-    for (int a = 1; a < n; a++)                                      // insertion sort, longest first, stable
-        for (int b = a; b > 0 && len[order[b]] > len[order[b - 1]]; b--) { const int t = order[b]; order[b] = order[b - 1]; order[b - 1] = t; }
-    for (int i = 0; i < kMaxPass * W; i++) assign[i] = 0xffffu;
-    for (int ps = 0; ps < kMaxPass; ps++) passLen[ps] = 0;
-    int nPass = 0;
-    for (int base = 0; base < n; base += W, nPass++) {
-        const int cnt = n - base < W ? n - base : W;
-        passLen[nPass] = len[order[base]];
-        unsigned short *row = assign + (size_t)nPass * W;
-        int used[2 * kEW][16], fill[2 * kEW];
-        memset(used, 0, sizeof(used)); memset(fill, 0, sizeof(fill));
-        int later[kMaxNum + 1], nLater = 0;
-        for (int c = 0; c < cnt; c++) {                              // first round: a half-warp whose residue slot is free
-            const int iv = order[base + c], r = (int)(desc[iv] >> 16) & 15;
-            int best = -1;
-            for (int h = 0; h < 2 * kEW; h++)
-                if (fill[h] < 16 && !used[h][r] && (best < 0 || fill[h] < fill[best])) best = h;
-            if (best < 0) { later[nLater++] = iv; continue; }
-            used[best][r] = 1;
-            row[best * 16 + fill[best]++] = (unsigned short)iv;
+    for (int lmax = 1; lmax <= 15; lmax++) {
+        int cnt = 0;
+        bool fits = true;
+        for (int i = 0; i < n && fits; i++) {
+            const int off = (int)(desc[i] & 0xffffu), len = (int)(desc[i + 1] & 0xffffu) - off, q0 = (int)(desc[i] >> 16);
+            pp->prefix[i] = (unsigned short)cnt;
+            for (int j = 0; j < len; j += lmax) {
+                if (cnt >= kMaxPieces) { fits = false; break; }
+                const int l = len - j < lmax ? len - j : lmax;
+                pp->pieceDesc[cnt++] = ((unsigned)(q0 + j) << 20) | ((unsigned)l << 16) | (unsigned)(off + j);
+            }
         }
-        for (int c = 0; c < nLater; c++) {                           // the rest: wherever there is room (a 2-way conflict)
-            int best = -1;
-            for (int h = 0; h < 2 * kEW; h++) if (fill[h] < 16 && (best < 0 || fill[h] < fill[best])) best = h;
-            row[best * 16 + fill[best]++] = (unsigned short)later[c];
+        if (!fits) continue;
+        for (int i = n; i < kMaxNum + 4; i++) pp->prefix[i] = (unsigned short)cnt;
+        for (int i = cnt; i < kMaxPieces; i++) pp->pieceDesc[i] = 0;
+        const int n0 = cnt < W ? cnt : W;
+        if (cnt > n0 && (int)(pp->pieceDesc[n0] >> 20) < n0) continue;      // pass 1 would read a row that holds a pass-0 sum
+        if (cnt > kPairs) continue;                                          // (slots are rows of the power tile)
+        pp->nPieces = cnt; pp->lmax = lmax; pp->firstPass2 = n0; pp->nPass = cnt > n0 ? 2 : 1;
+        for (int i = 0; i < kMaxPass * W; i++) pp->assign[i] = 0xffffu;
+        for (int ps = 0; ps < kMaxPass; ps++) pp->passLen[ps] = 0;
+        for (int ps = 0; ps < pp->nPass; ps++) {
+            const int base = ps ? n0 : 0, m = ps ? cnt - n0 : n0;
+            unsigned short *row = pp->assign + (size_t)ps * W;
+            int used[2 * kEW][16], fill[2 * kEW];
+            memset(used, 0, sizeof(used)); memset(fill, 0, sizeof(fill));
+            int later[kMaxPieces], nLater = 0;
+            for (int c = 0; c < m; c++) {                                    // first round: a half-warp whose residue slot is free
+                const int pc = base + c, r = (int)(pp->pieceDesc[pc] >> 20) & 15, l = (int)(pp->pieceDesc[pc] >> 16) & 15;
+                if (l > pp->passLen[ps]) pp->passLen[ps] = l;
+                int best = -1;
+                for (int h = 0; h < 2 * kEW; h++)
+                    if (fill[h] < 16 && !used[h][r] && (best < 0 || fill[h] < fill[best])) best = h;
+                if (best < 0) { later[nLater++] = pc; continue; }
+                used[best][r] = 1;
+                row[best * 16 + fill[best]++] = (unsigned short)pc;
+            }
+            for (int c = 0; c < nLater; c++) {                               // the rest: wherever there is room (a 2-way conflict)
+                int best = -1;
+                for (int h = 0; h < 2 * kEW; h++) if (fill[h] < 16 && (best < 0 || fill[h] < fill[best])) best = h;
+                row[best * 16 + fill[best]++] = (unsigned short)later[c];
+            }
         }
+        return pp->nPass;
     }
-    return nPass;
+    return -1;
 }
 
 }  // namespace
@@ -655,8 +693,10 @@ extern "C" int af_mfcc2_supported(int fftLength, int num, int ccNum, const float
     Intervals *iv = static_cast<Intervals *>(malloc(sizeof(Intervals)));
     float4 *tab = static_cast<float4 *>(malloc(sizeof(float4) * kMaxTab));
     unsigned desc[kMaxNum + 4];
-    const int ok = iv && tab && build_intervals2(bank, num, iv) && build_table(bank, num, iv, desc, tab) >= 0;
-    free(iv); free(tab);
+    PiecePlan *pc = static_cast<PiecePlan *>(malloc(sizeof(PiecePlan)));
+    const int ok = iv && tab && pc && build_intervals2(bank, num, iv) && build_table(bank, num, iv, desc, tab) >= 0 &&
+                   plan_pieces(num, desc, pc) > 0;
+    free(iv); free(tab); free(pc);
     return ok;
 }
 
@@ -691,10 +731,20 @@ extern "C" int af_mfcc2_plan_build(void **planOut, int fftLength, int num, int c
     pl->tabLen = build_table(bank, num, iv, pl->ivDesc, pl->tab);
     free(iv);
     for (int i = num + 2; i < kMaxNum + 4; i++) pl->ivDesc[i] = pl->ivDesc[num + 1];
-    pl->nPass = plan_passes(num, pl->ivDesc, pl->assign, pl->passLen);
+    {
+        PiecePlan *pc = static_cast<PiecePlan *>(malloc(sizeof(PiecePlan)));
+        if (!pc || plan_pieces(num, pl->ivDesc, pc) <= 0) { free(pc); free_plan(pl); return af_fail(AF_ERR_UNSUPPORTED, "fused MFCC v2 plan: no piece plan"); }
+        pl->nPass = pc->nPass; pl->nPieces = pc->nPieces; pl->lmax = pc->lmax; pl->firstPass2 = pc->firstPass2;
+        memcpy(pl->passLen, pc->passLen, sizeof(pl->passLen));
+        memcpy(pl->pieceDesc, pc->pieceDesc, sizeof(pl->pieceDesc));
+        memcpy(pl->piecePrefix, pc->prefix, sizeof(pl->piecePrefix));
+        memcpy(pl->assign, pc->assign, sizeof(pl->assign));
+        free(pc);
+    }
     if (rc == AF_OK) rc = af_dev_upload(reinterpret_cast<void **>(&pl->dAssign), pl->assign, sizeof(pl->assign));
     if (rc == AF_OK) rc = af_dev_upload(reinterpret_cast<void **>(&pl->dTab), pl->tab, sizeof(float4) * (size_t)(pl->tabLen > 0 ? pl->tabLen : 1));
-    if (rc == AF_OK) rc = af_dev_upload(reinterpret_cast<void **>(&pl->dDesc), pl->ivDesc, sizeof(pl->ivDesc));
+    if (rc == AF_OK) rc = af_dev_upload(reinterpret_cast<void **>(&pl->dDesc), pl->pieceDesc, sizeof(pl->pieceDesc));
+    if (rc == AF_OK) rc = af_dev_upload(reinterpret_cast<void **>(&pl->dPrefix), pl->piecePrefix, sizeof(pl->piecePrefix));
 
     // DCT table as the mma B operand: D^T[m][c], row pitch % 32 == 8 -> conflict-free fragment reads
     const int pitch = pl->ct <= 5 ? 40 : 72;
@@ -728,7 +778,7 @@ static int launch_fused2(void *plan, const float *data, int dataLength, int batc
     for (int d = 0; d < nPeer; d++) pp->peerOut[d] = peerOut[d];
     pp->nPass = pl->nPass; pp->assign = pl->dAssign;
     for (int i = 0; i < kMaxPass; i++) pp->passLen[i] = pl->passLen[i];
-    pp->bankTab = pl->dTab; pp->ivDesc = pl->dDesc; pp->tabLen = pl->tabLen;
+    pp->bankTab = pl->dTab; pp->pieceDesc = pl->dDesc; pp->piecePrefix = pl->dPrefix; pp->tabLen = pl->tabLen;
     const int rowFloats = rawMel ? pl->num : pl->ccNum;
     int bulk = rowFloats % 4 == 0 && (reinterpret_cast<uintptr_t>(out) & 15) == 0;
     for (int d = 0; d < nPeer; d++) if (reinterpret_cast<uintptr_t>(peerOut[d]) & 15) bulk = 0;
@@ -751,13 +801,13 @@ static int launch_fused2(void *plan, const float *data, int dataLength, int batc
         pp->offSpec = o;    o += 2 * 32 * kSpecPitch * 8;
         pp->offDct = o;     o += rawMel ? 0 : kMaxNum * pp->dctPitch * 4;
         pp->offL = o;       o += 2 * 16 * kLPitch * 4;
-        pp->offG = o;       o += 16 * kLPitch * 4;
         pp->stageBytes = rawMel ? 2 * ((F * (pl->num + 4) * 4 + 15) & ~15) : ((F * pl->ccNum * 4 + 15) & ~15);
         pp->offStage = o;   o += pp->stageBytes;
         pp->offBar = o;     o += 12 * 8;
         pp->offTab = o;     o += pl->tabLen * 16;
-        pp->offDesc = o;    o += (kMaxNum + 4) * 4;
+        pp->offDesc = o;    o += kMaxPieces * 4;
         pp->offAssign = o;  o += (kMaxPass * kEW * 32 * 2 + 15) & ~15;
+        pp->offPrefix = o;  o += ((kMaxNum + 4) * 2 + 15) & ~15;
         total = o;
         pp->spanFloats = spanFloats; pp->pitchPairs = pitchPairs;
         if (total <= budget) break;
@@ -801,30 +851,37 @@ extern "C" int af_launch_mel2(void *plan, const float *data, int dataLength, int
     return launch_fused2(plan, data, dataLength, batch, timeLength, slideLength, 0, out, 0, NULL, 1, stream);
 }
 
-// Diagnostic / test hook (host only): the interval form the planner derives from a bank [num][1025] and the lane
-// assignment of the bank passes.  Returns the number of table entries (>= 0) or -1 when the bank does not have the
-// two-overlap structure.  assign: [passes][helper lanes] interval per lane (0xffff = none), info = {passes, helper lanes,
-// passLen[0..passes)}.
+// Diagnostic / test hook (host only): the interval form the planner derives from a bank [num][1025], its cut into pieces
+// and the lane assignment of the bank passes.  Returns the number of table entries (>= 0) or -1 when the bank does not
+// have the two-overlap structure / no piece plan exists.  desc: per interval (first bin pair << 16) | table offset;
+// pieceDesc [256]: (first bin pair << 20) | (pairs << 16) | table offset; prefix [num + 2]: first piece of interval i;
+// assign: [passes][helper lanes] piece per lane (0xffff = none); info = {passes, helper lanes, pieces, lmax, pieces of
+// pass 0, passLen[0..passes)}.
 extern "C" int afb200_mfccBankPlan2(const float *bank, int num, int *owner /* 1025 */, unsigned *desc /* num+2 */,
-                                    float *table /* 4 * 1408 */, unsigned short *assign /* 8 * 128 */, int *info /* 16 */) {
+                                    float *table /* 4 * 1408 */, unsigned *pieceDesc /* 256 */, unsigned short *prefix /* num+2 */,
+                                    unsigned short *assign /* 2 * 128 */, int *info /* 16 */) {
     if (!bank || num < 1 || num > kMaxNum) return -1;
     Intervals *iv = static_cast<Intervals *>(malloc(sizeof(Intervals)));
     float4 *tab = static_cast<float4 *>(malloc(sizeof(float4) * kMaxTab));
+    PiecePlan *pc = static_cast<PiecePlan *>(malloc(sizeof(PiecePlan)));
     unsigned d[kMaxNum + 4];
     int n = -1;
-    if (iv && tab && build_intervals2(bank, num, iv)) {
+    if (iv && tab && pc && build_intervals2(bank, num, iv)) {
         n = build_table(bank, num, iv, d, tab);
+        if (n >= 0 && plan_pieces(num, d, pc) <= 0) n = -1;
         if (n >= 0) {
             if (owner) memcpy(owner, iv->owner, sizeof(int) * kBins);
             if (desc) memcpy(desc, d, sizeof(unsigned) * (size_t)(num + 2));
             if (table) memcpy(table, tab, sizeof(float4) * (size_t)n);
-            unsigned short as[kMaxPass * kEW * 32];
-            int pl[kMaxPass];
-            const int np = plan_passes(num, d, as, pl);
-            if (assign) memcpy(assign, as, sizeof(unsigned short) * (size_t)np * kEW * 32);
-            if (info) { info[0] = np; info[1] = kEW * 32; for (int i = 0; i < np; i++) info[2 + i] = pl[i]; }
+            if (pieceDesc) memcpy(pieceDesc, pc->pieceDesc, sizeof(pc->pieceDesc));
+            if (prefix) memcpy(prefix, pc->prefix, sizeof(unsigned short) * (size_t)(num + 2));
+            if (assign) memcpy(assign, pc->assign, sizeof(unsigned short) * (size_t)pc->nPass * kEW * 32);
+            if (info) {
+                info[0] = pc->nPass; info[1] = kEW * 32; info[2] = pc->nPieces; info[3] = pc->lmax; info[4] = pc->firstPass2;
+                for (int i = 0; i < pc->nPass; i++) info[5 + i] = pc->passLen[i];
+            }
         }
     }
-    free(iv); free(tab);
+    free(iv); free(tab); free(pc);
     return n;
 }

@@ -86,6 +86,13 @@ class PaddingModeType(Enum):
     WRAP = 2
 
 
+class ReassignType(Enum):
+    ALL = 0
+    FRE = 1
+    TIME = 2
+    NONE = 3
+
+
 class WaveletContinueType(Enum):
     MORSE = 0
     MORLET = 1

@@ -10,7 +10,9 @@ extern "C" {
 typedef struct OpaqueBFT *BFTObj;
 
 /* bft_algorithm.c:87-276.  Returns 0 ok; -100 bad radix2Exp; 1 scale > Log; -1 bad num /
- * range overflow; -2 for isReassign / isTemporal (outside the hot path, rejected loudly). */
+ * range overflow; -2 for isTemporal (outside the hot path, rejected loudly).  isReassign = 1: the bank is applied to the
+ * reassigned spectrum (include/afb200_reassign.h, Reassign_All); every call starts from zeroed planes -- the reference
+ * keeps adding into its cached planes from the second call on (bft_algorithm.c:441-455), which is not reproduced. */
 int bftObj_new(BFTObj *bftObj, int num, int radix2Exp, int *samplate, float *lowFre, float *highFre,
                int *binPerOctave, WindowType *windowType, int *slideLength,
                SpectralFilterBankScaleType *filterScaleType, SpectralFilterBankStyleType *filterStyleType,

@@ -115,10 +115,14 @@ int afb200_mfccIntervalPlan(const float *bank, int num, const float *gain, int *
 /* planner of the second-generation fused kernel (kernels/mfcc_fused2.cu, host only): every bin of `bank` (num x 1025)
  * is given to one interval i in [0, num] on which filter i "rises" and filter i-1 "falls" (the bank's own weights);
  * returns the number of float4 table entries (rise[2q], rise[2q+1], fall[2q], fall[2q+1]) or -1 when some bin is
- * covered by more than two, or by non-consecutive, filters.  desc[i] = (first bin pair << 16) | table offset. */
+ * covered by more than two, or by non-consecutive, filters (or no piece plan exists).  desc[i] = (first bin pair << 16) |
+ * table offset.  The intervals are cut into pieces of at most lmax bin pairs, one per helper lane and pass:
+ * pieceDesc[p] = (first bin pair << 20) | (pairs << 16) | table offset, prefix[i] = first piece of interval i,
+ * assign = piece of each lane (0xffff = none), info = {passes, helper lanes, pieces, lmax, pieces of pass 0,
+ * longest piece of each pass}. */
 int afb200_mfccBankPlan2(const float *bank, int num, int *owner /* 1025 */, unsigned *desc /* num + 2 */,
-                         float *table /* 4 x 1408 */, unsigned short *assign /* passes x helper lanes: interval of each lane,
-                         0xffff = none */, int *info /* passes, helper lanes, longest interval of each pass */);
+                         float *table /* 4 x 1408 */, unsigned *pieceDesc /* 256 */, unsigned short *prefix /* num + 2 */,
+                         unsigned short *assign /* passes x helper lanes */, int *info /* 16 */);
 /* chroma_cqtFilterBank (src/filterbank/chroma_filterBank.c:176-262): bank num x cqtLength */
 int afb200_chromaCqtFilterBank(int num, int cqtLength, int binPerOctave, float minFre, float *bank);
 

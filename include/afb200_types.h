@@ -47,6 +47,9 @@ typedef enum { WaveletContinue_Morse = 0, WaveletContinue_Morlet, WaveletContinu
                WaveletContinue_Paul, WaveletContinue_DOG, WaveletContinue_Mexican,
                WaveletContinue_Hermit, WaveletContinue_Ricker } WaveletContinueType;
 
+/* src/reassign_algorithm.h:14-22 */
+typedef enum { Reassign_All = 0, Reassign_Fre, Reassign_Time, Reassign_None } ReassignType;
+
 #ifdef __cplusplus
 }
 #endif

@@ -1175,3 +1175,120 @@ class CqtStream:
         else:
             self.tail, self.skip = np.zeros(0, f32), -tail_len
         return out
+
+
+# ---------------------------------------------------------------------------
+# Reassignment (src/reassign_algorithm.c:83-186 constructor, :200-414 transform, :417-451 windows, :587-822 steps)
+# ---------------------------------------------------------------------------
+REASSIGN_ALL, REASSIGN_FRE, REASSIGN_TIME, REASSIGN_NONE = range(4)
+
+
+def reassign_windows(window):
+    """`_reassignObj_initWindowData` (reassign_algorithm.c:417-451): h, dh = central difference of the periodically
+    wrapped window (`__vgradient` of [w[n-1], w[0..n-1], w[0]], entries 1..n), th = n * w(n), n = -N/2 .. N/2-1."""
+    w = np.asarray(window, dtype=f32)
+    n = w.shape[0]
+    der = np.concatenate([w[-1:], w, w[:1]]).astype(f32)
+    dh = ((der[2:] - der[:-2]).astype(f32) / f32(2)).astype(f32)
+    th = (np.arange(-(n // 2), n // 2).astype(f32) * w).astype(f32)
+    return w, dh, th
+
+
+def _c_int_cast(v):
+    """(int) of a float as C does it on x86: NaN / inf / out of range -> INT_MIN"""
+    out = np.full(v.shape, np.iinfo(np.int32).min, dtype=np.int64)
+    fin = np.isfinite(v) & (np.abs(v) < 2 ** 31)
+    out[fin] = v[fin].astype(np.int64)
+    return out
+
+
+def _roundf(v):
+    """roundf: halves away from zero (numpy rounds halves to even)"""
+    v = np.asarray(v, dtype=f32)
+    return (np.sign(v) * np.floor(np.abs(v) + f32(0.5))).astype(f32)
+
+
+def reassign_coords(s1, s2, s3, n, sr, hop, re_type=REASSIGN_ALL, thresh=0.001):
+    """steps 3 + 4 (`_reassignObj_reassignTimeFre` :612-703, `_reassignObj_filterTimeFre` :709-822): reassigned
+    frequency / time of every cell [T, n/2+1] in float32, thresholded on |S_h|^2 >= thresh^2 and clipped."""
+    (r1, i1), W = s1, n // 2 + 1
+    T = r1.shape[0]
+    fre = _linspace_f32(0, sr / 2.0, W)
+    tarr = ((np.arange(T).astype(f32) * f32(hop)).astype(f32) / f32(sr)).astype(f32)
+    power = ((r1 * r1).astype(f32) + (i1 * i1).astype(f32)).astype(f32)
+    keep = power >= f32(thresh) * f32(thresh)
+    re_f = np.broadcast_to(fre[None, :], (T, W)).astype(f32).copy()
+    re_t = np.broadcast_to(tarr[:, None], (T, W)).astype(f32).copy()
+    fmax, tmax = fre[W - 1], tarr[T - 1]
+    with np.errstate(all="ignore"):
+        if re_type in (REASSIGN_FRE, REASSIGN_ALL):
+            _, qi = _complex_div(s2[0], s2[1], r1, i1)
+            v = ((qi * f32(-0.5 * sr / math.pi)).astype(f32) + fre[None, :]).astype(f32)     # __mmul_value takes a float
+            v = np.where(keep, v, re_f)
+            v = np.where(v < 0, f32(0), v)             # NaN compares false in both clips and survives, as in C
+            re_f = np.where(v > fmax, fmax, v).astype(f32)
+        if re_type in (REASSIGN_TIME, REASSIGN_ALL):
+            qr, _ = _complex_div(s3[0], s3[1], r1, i1)
+            v = ((qr * f32(1.0 / sr)).astype(f32) + tarr[:, None]).astype(f32)
+            v = np.where(keep, v, re_t)
+            v = np.where(v < 0, f32(0), v)
+            re_t = np.where(v > tmax, tmax, v).astype(f32)
+    return re_f, re_t, fre, tarr
+
+
+def reassign_indices(re_f, re_t, fre, tarr, n, order=1):
+    """`_reassignObj_rearrage` index part (:268-323): roundf of the affine maps, then order-1 further look-ups of the
+    frequency index along the row (the scratch keeps its previous content where the index leaves the row)."""
+    T, W = re_f.shape
+    fmin, fmax, tmin, tmax = fre[0], fre[W - 1], tarr[0], tarr[T - 1]
+    with np.errstate(all="ignore"):
+        ti = np.zeros((T, W), dtype=np.int64)
+        if T > 1:
+            ti = _c_int_cast(_roundf(((re_t - tmin).astype(f32) * f32(T - 1)).astype(f32) / f32(tmax - tmin)))
+        fi = _c_int_cast(_roundf(((re_f - fmin).astype(f32) * f32(n // 2)).astype(f32) / f32(fmax - fmin)))
+    if order > 1:
+        tmp = np.zeros((T, W), dtype=np.int64)
+        rows = np.arange(T)[:, None]
+        for _ in range(order - 1):
+            ok = (fi >= 0) & (fi < W)
+            look = fi[rows, np.clip(fi, 0, W - 1)]
+            tmp = np.where(ok, look, tmp)
+            fi = tmp.copy()
+    return ti, fi
+
+
+def reassign(x, radix2_exp=12, sr=32000, window_type=W_HANN, hop=None, re_type=REASSIGN_ALL, thresh=0.001,
+             is_pad=False, order=1, result_type=0, indices=False):
+    """`reassignObj_reassign` (reassign_algorithm.c:200-414) -> (re4, im4, re5, im5), planes [T, n/2+1]; the reference
+    ADDS into re4 / im4 (zero planes here), re5 / im5 = the plain half spectrum S_h.  float32 accumulation in the
+    reference's (frame, bin) order.  indices=True also returns (time index, frequency index)."""
+    n = 1 << radix2_exp
+    hop = hop if hop else n // 4
+    W = n // 2 + 1
+    h, dh, th = reassign_windows(fft_window(window_type, n))
+    s = []
+    for w in (h, dh, th):
+        r, i = stft(x, n, hop, w, is_pad=is_pad)
+        s.append((np.ascontiguousarray(r[:, :W]), np.ascontiguousarray(i[:, :W])))
+    T = s[0][0].shape[0]
+    if re_type == REASSIGN_NONE:
+        out = (s[0][0].copy(), s[0][1].copy(), None, None)
+        return out + (None, None) if indices else out
+    re_f, re_t, fre, tarr = reassign_coords(s[0], s[1], s[2], n, sr, hop, re_type, thresh)
+    ti, fi = reassign_indices(re_f, re_t, fre, tarr, n, order)
+    o_re = np.zeros((T, W), dtype=f32)
+    o_im = np.zeros((T, W), dtype=f32)
+    sign = np.where(np.arange(W) % 2 == 1, f32(-1), f32(1)).astype(f32)
+    v1 = (s[0][0] * sign[None, :]).astype(f32)
+    v2 = (s[0][1] * sign[None, :]).astype(f32)
+    ok = (ti >= 0) & (ti < T) & (fi >= 0) & (fi < W)
+    amp = np.sqrt((v1 * v1 + v2 * v2).astype(f32)).astype(f32)
+    for i in range(T):                                  # float32 += in source order (rows, then bins)
+        m = ok[i]
+        if result_type == 0:
+            np.add.at(o_re, (ti[i][m], fi[i][m]), v1[i][m])
+            np.add.at(o_im, (ti[i][m], fi[i][m]), v2[i][m])
+        else:
+            np.add.at(o_re, (ti[i][m], fi[i][m]), amp[i][m])
+    out = (o_re, o_im, s[0][0], s[0][1])
+    return out + (ti, fi) if indices else out

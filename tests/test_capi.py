@@ -19,7 +19,7 @@ def declared_symbols():
         src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
         for m in re.finditer(r"\b([A-Za-z_][A-Za-z0-9_]*)\s*\(", src):
             n = m.group(1)
-            if re.match(r"(stftObj_|bftObj_|xxccObj_|cqtObj_|cwtObj_|pwtObj_|wsstObj_|synsqObj_|spectrogramObj_|afb200_)", n):
+            if re.match(r"(stftObj_|bftObj_|xxccObj_|cqtObj_|cwtObj_|pwtObj_|wsstObj_|synsqObj_|reassignObj_|spectrogramObj_|afb200_)", n):
                 names.add(n)
     return names
 

@@ -80,7 +80,10 @@ def test_bft_new_status_codes(product_lib):
     a2 = list(args); a2[6] = opt_int(9)
     assert product_lib.bftObj_new(ctypes.byref(obj), 64, 11, *a2) == 1              # scale > Log
     a3 = list(args); a3[10] = opt_int(1)
-    assert product_lib.bftObj_new(ctypes.byref(obj), 64, 11, *a3) == -2             # isReassign: rejected loudly
+    assert product_lib.bftObj_new(ctypes.byref(obj), 64, 11, *a3) == 0              # isReassign: supported (bank over the reassigned spectrum)
+    product_lib.bftObj_free(obj)
+    a4 = list(args); a4[11] = opt_int(1)
+    assert product_lib.bftObj_new(ctypes.byref(obj), 64, 11, *a4) == -2             # isTemporal: rejected loudly
     assert product_lib.stftObj_new(ctypes.byref(obj), 0, None, None, None) == -100
     assert product_lib.xxccObj_new(ctypes.byref(obj), 1) == -1
     assert product_lib.cqtObj_newWith(ctypes.byref(obj), 84, None, None, opt_int(10), *([None] * 8)) == -1
@@ -237,33 +240,44 @@ def _bank_plan2(lib, bank):
     owner = np.zeros(1025, np.int32)
     desc = np.zeros(num + 2, np.uint32)
     table = np.zeros((1408, 4), np.float32)
-    assign = np.zeros(8 * 128, np.uint16)
+    piece = np.zeros(256, np.uint32)
+    prefix = np.zeros(num + 2, np.uint16)
+    assign = np.zeros(2 * 128, np.uint16)
     info = np.zeros(16, np.int32)
     n = lib.afb200_mfccBankPlan2(bank.ctypes.data, num, owner.ctypes.data, desc.ctypes.data, table.ctypes.data,
-                                 assign.ctypes.data, info.ctypes.data)
+                                 piece.ctypes.data, prefix.ctypes.data, assign.ctypes.data, info.ctypes.data)
     passes, lanes = int(info[0]), int(info[1])
-    return n, owner, desc, table, assign[:passes * lanes].reshape(passes, lanes) if n >= 0 else None, info[2:2 + passes]
+    plan = dict(n=n, owner=owner, desc=desc, table=table, piece=piece, prefix=prefix, pieces=int(info[2]), lmax=int(info[3]),
+                first_pass2=int(info[4]), pass_len=info[5:5 + passes].copy(),
+                assign=assign[:passes * lanes].reshape(passes, lanes) if n >= 0 else None)
+    return plan
 
 
 def _plan2_mel(num, P, plan):
-    """the helper warps' two bank phases (mfcc_fused2.cu) in float64: R_i / Fl_i per interval, mel_m = R_m + Fl_{m+1}"""
-    n, owner, desc, table, assign, pass_len = plan
+    """the helper warps' two bank phases (mfcc_fused2.cu) in float64: per piece the partial sums (rise, fall), then
+    mel_m = sum over the pieces of interval m of rise + sum over the pieces of interval m + 1 of fall"""
     Pp = np.concatenate([P, [0.0]])
-    R = np.zeros(num + 2)
-    Fl = np.zeros(num + 2)
-    for ps in range(assign.shape[0]):
-        for iv in assign[ps]:
-            if iv == 0xffff:
+    S = np.zeros((256, 2))
+    seen = np.zeros(256, bool)
+    for ps in range(plan["assign"].shape[0]):
+        for pc in plan["assign"][ps]:
+            if pc == 0xffff:
                 continue
-            iv = int(iv)
-            q, j0, j1 = int(desc[iv] >> 16), int(desc[iv] & 0xffff), int(desc[iv + 1] & 0xffff)
-            assert j1 - j0 <= pass_len[ps]
-            for j in range(j0, j1):
-                w = table[j].astype(np.float64)
-                k = 2 * (q + j - j0)
-                R[iv] += Pp[k] * w[0] + Pp[k + 1] * w[1]
-                Fl[iv] += Pp[k] * w[2] + Pp[k + 1] * w[3]
-    return R[:num] + Fl[1:num + 1]
+            d = int(plan["piece"][int(pc)])
+            row, ln, off = d >> 20, (d >> 16) & 15, d & 0xffff
+            assert 1 <= ln <= plan["pass_len"][ps] <= plan["lmax"] and not seen[pc]
+            assert (int(pc) < plan["first_pass2"]) == (ps == 0)
+            if ps == 1:
+                assert row >= plan["first_pass2"]          # pass 1 never reads a row that already holds a pass-0 sum
+            seen[pc] = True
+            for j in range(ln):
+                w = plan["table"][off + j].astype(np.float64)
+                k = 2 * (row + j)
+                S[pc, 0] += Pp[k] * w[0] + Pp[k + 1] * w[1]
+                S[pc, 1] += Pp[k] * w[2] + Pp[k + 1] * w[3]
+    assert seen[:plan["pieces"]].all() and not seen[plan["pieces"]:].any()
+    pre = plan["prefix"].astype(int)
+    return np.array([S[pre[m]:pre[m + 1], 0].sum() + S[pre[m + 1]:pre[m + 2], 1].sum() for m in range(num)])
 
 
 @pytest.mark.parametrize("scale,style,norm,num,sr", [(2, 0, 0, 128, 48000), (2, 0, 1, 128, 48000), (2, 0, 2, 128, 48000),
@@ -275,17 +289,24 @@ def test_mfcc_bank_plan2_reproduces_the_bank(product_lib, scale, style, norm, nu
     lo, hi, _, _ = O.bft_revise_range(num, 2048, sr, None, None, scale, 12)
     bank, _, _ = O.auditory_filterbank(num, 2048, sr, scale, style, norm, float(lo), float(hi), 12)
     plan = _bank_plan2(product_lib, bank)
-    n, owner, desc, table, assign, pass_len = plan
-    assert 0 <= n <= 1408
+    assert 0 <= plan["n"] <= 1408 and 1 <= plan["pieces"] <= 256
+    owner, desc = plan["owner"], plan["desc"]
     assert (np.diff(owner[owner >= 0]) >= 0).all()                 # intervals are runs of consecutive bins
-    got_iv = np.sort(assign[assign != 0xffff])
-    assert np.array_equal(got_iv, np.arange(num + 1))              # every interval 0..num is walked by exactly one lane
-    assert (np.diff(pass_len) <= 0).all()                          # longest intervals first
-    if num == 128 and scale == 2:                                  # the headline bank: half-warps start in distinct bank pairs
-        for ps in range(assign.shape[0]):
-            for h in range(assign.shape[1] // 16):
-                ivs = [int(v) for v in assign[ps, 16 * h:16 * h + 16] if v != 0xffff]
-                res = [(int(desc[v]) >> 16) & 15 for v in ivs]
+    # the pieces of an interval tile its table range in order
+    pre = plan["prefix"].astype(int)
+    for i in range(num + 1):
+        off, end, q0 = int(desc[i]) & 0xffff, int(desc[i + 1]) & 0xffff, int(desc[i]) >> 16
+        for pc in range(pre[i], pre[i + 1]):
+            d = int(plan["piece"][pc])
+            assert (d & 0xffff) == off and (d >> 20) == q0 + (off - (int(desc[i]) & 0xffff))
+            off += (d >> 16) & 15
+        assert off == end
+    if num == 128 and scale == 2:                                  # the headline bank: balanced, half-warps start in distinct bank pairs
+        assert plan["lmax"] <= 4 and plan["assign"].shape[0] == 2
+        for ps in range(plan["assign"].shape[0]):
+            for h in range(plan["assign"].shape[1] // 16):
+                pcs = [int(v) for v in plan["assign"][ps, 16 * h:16 * h + 16] if v != 0xffff]
+                res = [(int(plan["piece"][v]) >> 20) & 15 for v in pcs]
                 assert len(res) - len(set(res)) <= 4
     B = bank.astype(np.float64)
     rng = np.random.default_rng(0)
@@ -301,9 +322,9 @@ def test_mfcc_bank_plan2_reproduces_the_bank(product_lib, scale, style, norm, nu
 
 def test_mfcc_bank_plan2_rejects_other_banks(product_lib):
     rnd = np.random.default_rng(1).random((16, 1025)).astype(np.float32)               # dense
-    assert _bank_plan2(product_lib, rnd)[0] == -1
+    assert _bank_plan2(product_lib, rnd)["n"] == -1
     tri, _, _ = O.auditory_filterbank(128, 2048, 48000, 2, 0, 0, 0.0, 24000.0, 12)
-    assert _bank_plan2(product_lib, tri)[0] > 0
+    assert _bank_plan2(product_lib, tri)["n"] > 0
     bad = tri.copy()
     bad[10, 900] = 0.5                                              # a third filter on a high bin
-    assert _bank_plan2(product_lib, bad)[0] == -1
+    assert _bank_plan2(product_lib, bad)["n"] == -1

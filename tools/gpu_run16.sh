@@ -1,0 +1,8 @@
+set -x
+cd $GRAFT_REPO_ROOT
+mkdir -p gpurun_out
+timeout 1200 python -m pytest tests -m gpu -x -q > gpurun_out/r2b_pytest_gpu.log 2>&1; tail -15 gpurun_out/r2b_pytest_gpu.log
+timeout 300 python bench.py --steps 20 --warmup 3 --no-cpu-baseline --no-extra > gpurun_out/r2b_bench.json 2> gpurun_out/r2b_bench.err; cut -c1-330 gpurun_out/r2b_bench.json; tail -3 gpurun_out/r2b_bench.err
+timeout 300 ncu --set full --clock-control none --import-source on -k regex:k_mfcc_fused2 -s 2 -c 1 -f -o gpurun_out/r2b_mfcc2 python tools/mfcc_prof.py > /dev/null 2>&1
+python tools/ncu_summary.py gpurun_out/r2b_mfcc2.ncu-rep > gpurun_out/r2b_mfcc_fused2_ncu_summary.txt; cat gpurun_out/r2b_mfcc_fused2_ncu_summary.txt
+ncu -i gpurun_out/r2b_mfcc2.ncu-rep --page source --csv --print-source sass > gpurun_out/r2b_mfcc2_src.csv 2>/dev/null
