@@ -60,6 +60,8 @@ REFERENCE_API = {
     "cqtObj_cqt": (None, [vp, vp, C.c_int, vp, vp]),
     "cqtObj_chroma": (None, [vp, c_int_p, c_int_p, c_int_p, vp, vp, vp]),
     "cqtObj_cqcc": (None, [vp, vp, C.c_int, c_int_p, vp]),
+    "cqtObj_cqhc": (None, [vp, vp, C.c_int, vp]),
+    "cqtObj_deconv": (None, [vp, vp, vp, vp]),
     "cqtObj_free": (None, [vp]),
     # ---- CWT
     "cwtObj_new": (C.c_int, [P(vp), C.c_int, C.c_int, c_int_p, c_float_p, c_float_p, c_int_p,
@@ -149,6 +151,8 @@ EXTENSION_API = {
     "cqtObj_getKernelBank": (C.c_int, [vp, vp, vp]),
     "cqtObj_chromaBatch": (C.c_int, [vp, vp, vp, C.c_int, C.c_int, C.c_int, C.c_int, vp, C.c_int, vp]),
     "cqtObj_cqccBatch": (C.c_int, [vp, vp, C.c_int, C.c_int, C.c_int, vp, C.c_int, vp]),
+    "cqtObj_cqhcBatch": (C.c_int, [vp, vp, C.c_int, C.c_int, vp, C.c_int, vp]),
+    "cqtObj_deconvBatch": (C.c_int, [vp, vp, C.c_int, vp, vp, C.c_int, vp]),
     "xxccObj_xxccStandardBatch": (C.c_int, [vp, vp, vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
                                             vp, vp, vp, C.c_int, vp]),
     "spectrogramObj_spectrogramBatch": (C.c_int, [vp, vp, C.c_int, C.c_int, vp, vp, C.c_int, vp]),

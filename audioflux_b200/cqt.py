@@ -52,9 +52,9 @@ class CQT(Base):
         self._lib.cqtObj_setScale(self._obj, int(flag))
 
     def get_kernel_bank(self):
-        """Additive: (kr, ki) spectral kernels [bin_per_octave, fft_length//2+1]."""
+        """Additive: (kr, ki) spectral kernels [bin_per_octave (num when beta != 0: VQT), fft_length//2+1]."""
         fn = self._require_ext("cqtObj_getKernelBank")
-        kr = np.zeros((self.bin_per_octave, self.fft_length // 2 + 1), np.float32)
+        kr = np.zeros((self.num if self.beta else self.bin_per_octave, self.fft_length // 2 + 1), np.float32)
         ki = np.zeros_like(kr)
         check(fn(self._obj, np_ptr(kr), np_ptr(ki)), "cqtObj_getKernelBank")
         return kr, ki
@@ -142,6 +142,51 @@ class CQT(Base):
         check(fn(self._obj, ptr(x2), x2.shape[0], cc_num, enum_value(rectify_type), ptr(out), kind, stream),
               "cqtObj_cqccBatch")
         return out.reshape(*lead, cc_num)
+
+    def cqhc_planes(self, m_tn, hc_num=20):
+        """Raw C layout: [T, num] of the LAST cqt call -> [T, hc_num] (cqtObj_cqhc, src/cqt_algorithm.c:662-714)."""
+        m = as_f32(m_tn)
+        out = np.zeros((m.shape[0], hc_num), np.float32)
+        self._lib.cqtObj_cqhc(self._obj, np_ptr(m), int(hc_num), np_ptr(out))
+        return out
+
+    def cqhc(self, m_data_arr, hc_num=20):
+        """[num, T] power / magnitude (complex input: power) of the last cqt call -> [hc_num, T] as cqt.py:277-323."""
+        m = np.asarray(m_data_arr)
+        if np.iscomplexobj(m):
+            m = np.abs(m) ** 2
+        return swap_last2(self.cqhc_planes(np.swapaxes(as_f32(m), -1, -2), hc_num))
+
+    def deconv_planes(self, m_tn):
+        """Raw C layout: [T, num] of the LAST cqt call -> (timbre, pitch) each [T, num] (cqtObj_deconv, :716-781)."""
+        m = as_f32(m_tn)
+        tone, pitch = np.zeros_like(m), np.zeros_like(m)
+        self._lib.cqtObj_deconv(self._obj, np_ptr(m), np_ptr(tone), np_ptr(pitch))
+        return tone, pitch
+
+    def deconv(self, m_data_arr):
+        """[num, T] magnitude / power (complex input: magnitude) -> (tone, pitch) each [num, T] as cqt.py:325-375."""
+        m = np.asarray(m_data_arr)
+        if np.iscomplexobj(m):
+            m = np.abs(m)
+        tone, pitch = self.deconv_planes(np.swapaxes(as_f32(m), -1, -2))
+        return swap_last2(tone), swap_last2(pitch)
+
+    def cqhc_batch(self, m_tn, hc_num=20):
+        """Additive: [..., T, num] (numpy host | torch cuda) -> [..., T, hc_num]."""
+        fn = self._require_ext("cqtObj_cqhcBatch")
+        x2, lead, kind, ptr, stream, alloc = split_batch(m_tn)
+        out = alloc(x2.shape[0], hc_num)
+        check(fn(self._obj, ptr(x2), x2.shape[0], int(hc_num), ptr(out), kind, stream), "cqtObj_cqhcBatch")
+        return out.reshape(*lead, hc_num)
+
+    def deconv_batch(self, m_tn):
+        """Additive: [..., T, num] (numpy host | torch cuda) -> (timbre, pitch) each [..., T, num]."""
+        fn = self._require_ext("cqtObj_deconvBatch")
+        x2, lead, kind, ptr, stream, alloc = split_batch(m_tn)
+        tone, pitch = alloc(*x2.shape), alloc(*x2.shape)
+        check(fn(self._obj, ptr(x2), x2.shape[0], ptr(tone), ptr(pitch), kind, stream), "cqtObj_deconvBatch")
+        return tone.reshape(*lead, x2.shape[-1]), pitch.reshape(*lead, x2.shape[-1])
 
     def __del__(self):
         if getattr(self, "_is_created", False):

@@ -94,14 +94,15 @@ void af_decimator_taps(float *left32, float *right31);
 
 typedef struct {
     int num, binPerOctave, octaveNum, fftLength, samplate;
+    int vqt, rows;       /* beta != 0: one kernel row per bin (rows = num), else the top octave's rows shared (rows = bpo) */
     float *freBandArr;   /* num+2 */
     float *sLenArr;      /* num: sqrt(kernel length) */
-    float *kr, *ki;      /* binPerOctave x (fftLength/2+1) spectral kernels, thresholded */
+    float *kr, *ki;      /* rows x (fftLength/2+1) spectral kernels, thresholded */
 } AfCqtBank;
 int af_cqt_bank_build(AfCqtBank *b, int num, int samplate, float minFre, int binPerOctave, float factor,
                       float beta, float thresh, int windowType, int normType);
 void af_cqt_bank_free(AfCqtBank *b);
-/* time-domain kernels kappa[b][n] = sum_{k<=N/2} K[b][k] e^{-2 pi i k n/N}  -> 2 x bpo x N floats */
+/* time-domain kernels kappa[b][n] = sum_{k<=N/2} K[b][k] e^{-2 pi i k n/N}  -> 2 x rows x N floats */
 int af_cqt_time_kernels(const AfCqtBank *b, float *kappaRe, float *kappaIm);
 /* chroma folding matrix [num][cqtLength] of cqtObj_chroma; -1 when num does not divide binPerOctave */
 int af_chroma_cqt_bank(int num, int cqtLength, int binPerOctave, float minFre, float *bank);
@@ -230,6 +231,8 @@ typedef struct {
     int det;                 /* 1: multiply the bank by j*omega (cwtObj_cwtDet) */
     const float *bankTable;  /* device, num x bankWidth: tabulated bank (PWT) instead of the closed-form wavelet */
     int bankWidth;
+    int *support;            /* device, 3 x num ints: per bank row the bins [lo, hi) above 2^-28 of its peak (+ scratch); NULL = no pruning */
+    int *supportReady;       /* host flag of the owning object: 0 until the launcher has filled `support` */
 } AfCwtArgs;
 size_t af_cwt_workspace_bytes(const AfCwtArgs *a);
 /* data == NULL: skip the forward transform and reuse the spectra a previous call left in `workspace` */
@@ -265,6 +268,9 @@ typedef struct {
 int af_launch_reassign(const AfReassignArgs *a, const float *r1, const float *i1, const float *r2, const float *i2,
                        const float *r3, const float *i3, int *tIdx, int *fIdx, unsigned *maxBits,
                        unsigned long long *accRe, unsigned long long *accIm, float *outRe, float *outIm, void *stream);
+
+/* cepstral deconvolution of rows x num constant-Q magnitudes (kernels/deconv.cu): mode 0 cqhc, 1 deconv */
+int af_launch_cq_deconv(const float *in, int rows, int num, int mode, int hcNum, int bpo, float *out0, float *out1, void *stream);
 
 void af_count_launch(int n);
 

@@ -49,7 +49,6 @@ int cqtObj_newWith(CQTObj *out, int num, int *samplate, float *minFre, int *binP
     if (factor && *factor > 0) fac = *factor;
     if (beta && *beta > 0) bet = *beta;
     if (thresh && *thresh > 0) thr = *thresh;
-    if (bet != 0) { af_fail(AF_ERR_UNSUPPORTED, "cqtObj_newWith: beta != 0 (VQT) is not supported"); return -2; }
     CQTObj c = (CQTObj)calloc(1, sizeof(struct OpaqueCQT));
     if (!c) return -1;
     c->num = num; c->samplate = sr; c->binPerOctave = bpo; c->octaveNum = num / bpo; c->minFre = fmin;
@@ -64,10 +63,11 @@ int cqtObj_newWith(CQTObj *out, int num, int *samplate, float *minFre, int *binP
         cqtObj_free(c); return -1;
     }
     const int n = c->fftLength;
-    float *kr = (float *)malloc(sizeof(float) * (size_t)bpo * n), *ki = (float *)malloc(sizeof(float) * (size_t)bpo * n);
-    c->kappa2 = (float *)malloc(sizeof(float) * 2 * (size_t)bpo * n);
+    const size_t rows = (size_t)c->bank.rows;                     /* bpo, or num when beta != 0 (one kernel set per octave) */
+    float *kr = (float *)malloc(sizeof(float) * rows * n), *ki = (float *)malloc(sizeof(float) * rows * n);
+    c->kappa2 = (float *)malloc(sizeof(float) * 2 * rows * n);
     if (!kr || !ki || !c->kappa2 || af_cqt_time_kernels(&c->bank, kr, ki)) { free(kr); free(ki); cqtObj_free(c); return -1; }
-    for (size_t i = 0; i < (size_t)bpo * n; i++) { c->kappa2[2 * i] = kr[i]; c->kappa2[2 * i + 1] = ki[i]; }
+    for (size_t i = 0; i < rows * n; i++) { c->kappa2[2 * i] = kr[i]; c->kappa2[2 * i + 1] = ki[i]; }
     free(kr); free(ki);
     af_decimator_taps(c->left32, c->right31);
     c->scaleDirty = 1;
@@ -96,7 +96,7 @@ void cqtObj_setScale(CQTObj c, int flag) { if (c && c->isScale != flag) { c->isS
 
 int cqtObj_getKernelBank(CQTObj c, float *kr, float *ki) {
     if (!c || !kr || !ki) return af_fail(AF_ERR_ARG, "cqtObj_getKernelBank: bad argument");
-    size_t n = (size_t)c->binPerOctave * (c->fftLength / 2 + 1);
+    size_t n = (size_t)c->bank.rows * (c->fftLength / 2 + 1);
     memcpy(kr, c->bank.kr, sizeof(float) * n); memcpy(ki, c->bank.ki, sizeof(float) * n);
     return AF_OK;
 }
@@ -106,22 +106,25 @@ static int cqt_device(CQTObj c) {
     if (rc) return rc;
     if (!c->devReady) {
         if ((rc = af_stream_create(&c->stream))) return rc;
-        if ((rc = af_dev_upload((void **)&c->dKappa2, c->kappa2, sizeof(float) * 2 * (size_t)c->binPerOctave * c->fftLength))) return rc;
+        /* kernel sets: one (the top octave's, shared) or -- VQT -- one per octave, set o at offset o * bpo rows */
+        const int sets = c->bank.vqt ? c->octaveNum : 1;
+        const size_t setFloats = 2 * (size_t)c->binPerOctave * c->fftLength;
+        if ((rc = af_dev_upload((void **)&c->dKappa2, c->kappa2, sizeof(float) * setFloats * sets))) return rc;
         if (c->binPerOctave == 12 && c->fftLength % 64 == 0) {
             const size_t nf = (size_t)(c->fftLength / 8) * 96 * 4;
-            float *bf = (float *)malloc(sizeof(float) * nf);
+            float *bf = (float *)malloc(sizeof(float) * nf * sets);
             if (!bf) return AF_ERR_NOMEM;
-            af_cqt_tc_fragments(c->kappa2, c->fftLength, bf);
-            rc = af_dev_upload((void **)&c->dBfrag, bf, sizeof(float) * nf);
+            for (int s = 0; s < sets; s++) af_cqt_tc_fragments(c->kappa2 + setFloats * s, c->fftLength, bf + nf * s);
+            rc = af_dev_upload((void **)&c->dBfrag, bf, sizeof(float) * nf * sets);
             free(bf);
             if (rc) return rc;
         }
         if (c->binPerOctave == 12 && c->fftLength % 128 == 0 && c->fftLength >= 256) {
             const size_t nb = (size_t)(c->fftLength / 128) * 32768;
-            unsigned char *img = (unsigned char *)malloc(nb);
+            unsigned char *img = (unsigned char *)malloc(nb * sets);
             if (!img) return AF_ERR_NOMEM;
-            af_cqt_umma_bimage(c->kappa2, c->fftLength, img);
-            rc = af_dev_upload((void **)&c->dBimg, img, nb);
+            for (int s = 0; s < sets; s++) af_cqt_umma_bimage(c->kappa2 + setFloats * s, c->fftLength, img + nb * s);
+            rc = af_dev_upload((void **)&c->dBimg, img, nb * sets);
             free(img);
             if (rc) return rc;
         }
@@ -173,19 +176,24 @@ static int cqt_compute_ex(CQTObj c, const float *dData, int dataLength, int batc
         const int frames = len / hop + 1;
         const int valid = frames > 1 ? len - len % hop : len;
         const char *kq = getenv("AFB200_CQT_KERNEL");
+        /* kernel set of this octave: the shared top-octave set, or -- VQT -- the octave's own */
+        const size_t set = c->bank.vqt ? (size_t)o : 0;
+        const unsigned char *bimg = c->dBimg ? c->dBimg + set * (size_t)(c->fftLength / 128) * 32768 : NULL;
+        const float *bfrag = c->dBfrag ? c->dBfrag + set * (size_t)(c->fftLength / 8) * 96 * 4 : NULL;
+        const float *kappa = c->dKappa2 + set * 2 * (size_t)c->binPerOctave * c->fftLength;
         /* tcgen05 (default where the hop allows it) > mma.sync 3xTF32 > FP32 loop; AFB200_CQT_KERNEL = mma | fp32 forces the older ones */
         if (c->dBimg && af_cqt_umma_supported(c->fftLength, hop, c->binPerOctave) && !kq) {
-            if ((rc = af_launch_cqt_octave_umma(sig, stride, batch, valid, c->fftLength, hop, padLeft, T, c->dBimg,
+            if ((rc = af_launch_cqt_octave_umma(sig, stride, batch, valid, c->fftLength, hop, padLeft, T, bimg,
                                                 c->dScale + (size_t)k * c->binPerOctave, c->num, o * c->binPerOctave, dRe, dIm, st))) return rc;
             continue;
         }
         if (c->dBfrag && af_cqt_tc_supported(c->fftLength, hop, c->binPerOctave) && !(kq && !strcmp(kq, "fp32"))) {
-            if ((rc = af_launch_cqt_octave_tc(sig, stride, batch, valid, c->fftLength, hop, padLeft, T, c->dBfrag,
+            if ((rc = af_launch_cqt_octave_tc(sig, stride, batch, valid, c->fftLength, hop, padLeft, T, bfrag,
                                               c->dScale + (size_t)k * c->binPerOctave, c->num, o * c->binPerOctave, dRe, dIm, st))) return rc;
             continue;
         }
         if ((rc = af_launch_cqt_octave(sig, len, stride, batch, valid, c->fftLength, hop, padLeft, T, c->binPerOctave,
-                                       c->dKappa2, c->dScale + (size_t)k * c->binPerOctave, c->num,
+                                       kappa, c->dScale + (size_t)k * c->binPerOctave, c->num,
                                        o * c->binPerOctave, dRe, dIm, st))) return rc;
     }
     return AF_OK;
@@ -360,13 +368,42 @@ void cqtObj_cqcc(CQTObj c, float *mDataArr1, int ccNum, CepstralRectifyType *rec
                      mDataArr2, AFB200_MEM_HOST, NULL);
 }
 
+/* ---- cqhc / deconv: rows x num magnitudes (or powers) -> harmonic-index picks of the timbre sequence / timbre + pitch
+ * (cqt_algorithm.c:662-781).  mode 0: out0 [rows x hcNum]; mode 1: out0 = timbre, out1 = pitch [rows x num] ---- */
+static int cqt_deconv_batch(CQTObj c, const float *in, int rows, int mode, int hcNum, float *out0, float *out1, int memKind, void *stream) {
+    af_clear_error();
+    int rc = cqt_device(c);
+    if (rc) return rc;
+    if (rows <= 0) return AF_OK;
+    if (memKind == AFB200_MEM_DEVICE) return af_launch_cq_deconv(in, rows, c->num, mode, hcNum, c->binPerOctave, out0, out1, stream);
+    void *st = stream ? stream : c->stream;
+    const size_t inB = sizeof(float) * (size_t)rows * c->num, outB = sizeof(float) * (size_t)rows * (mode ? c->num : hcNum);
+    if ((rc = af_devbuf_reserve(&c->dPostA, inB)) || (rc = af_devbuf_reserve(&c->dPostOut, outB)) ||
+        (mode && (rc = af_devbuf_reserve(&c->dPostB, outB)))) return rc;
+    if ((rc = af_memcpy_h2d(c->dPostA.ptr, in, inB, st))) return rc;
+    if ((rc = af_launch_cq_deconv((const float *)c->dPostA.ptr, rows, c->num, mode, hcNum, c->binPerOctave, (float *)c->dPostOut.ptr,
+                                  mode ? (float *)c->dPostB.ptr : NULL, st))) return rc;
+    if ((rc = af_memcpy_d2h(out0, c->dPostOut.ptr, outB, st))) return rc;
+    if (mode && (rc = af_memcpy_d2h(out1, c->dPostB.ptr, outB, st))) return rc;
+    return af_stream_sync(st);
+}
+
+int cqtObj_cqhcBatch(CQTObj c, const float *in, int rows, int hcNum, float *out, int memKind, void *stream) {
+    if (!c || !in || !out || rows < 0 || hcNum < 1) return af_fail(AF_ERR_ARG, "cqtObj_cqhcBatch: bad argument");
+    return cqt_deconv_batch(c, in, rows, 0, hcNum, out, NULL, memKind, stream);
+}
+int cqtObj_deconvBatch(CQTObj c, const float *in, int rows, float *timbre, float *pitch, int memKind, void *stream) {
+    if (!c || !in || !timbre || !pitch || rows < 0) return af_fail(AF_ERR_ARG, "cqtObj_deconvBatch: bad argument");
+    return cqt_deconv_batch(c, in, rows, 1, 0, timbre, pitch, memKind, stream);
+}
+
 void cqtObj_cqhc(CQTObj c, float *mDataArr1, int hcNum, float *mDataArr2) {
-    (void)c; (void)mDataArr1; (void)hcNum; (void)mDataArr2;
-    af_fail(AF_ERR_UNSUPPORTED, "cqtObj_cqhc: cepstral deconvolution is not part of libaudioflux_b200");
+    if (!c || !mDataArr1 || !mDataArr2 || hcNum < 1 || c->timeLength <= 0) return;
+    cqtObj_cqhcBatch(c, mDataArr1, c->timeLength, hcNum, mDataArr2, AFB200_MEM_HOST, NULL);
 }
 void cqtObj_deconv(CQTObj c, float *mDataArr1, float *mDataArr2, float *mDataArr3) {
-    (void)c; (void)mDataArr1; (void)mDataArr2; (void)mDataArr3;
-    af_fail(AF_ERR_UNSUPPORTED, "cqtObj_deconv: cepstral deconvolution is not part of libaudioflux_b200");
+    if (!c || !mDataArr1 || !mDataArr2 || !mDataArr3 || c->timeLength <= 0) return;
+    cqtObj_deconvBatch(c, mDataArr1, c->timeLength, mDataArr2, mDataArr3, AFB200_MEM_HOST, NULL);
 }
 
 void cqtObj_free(CQTObj c) {

@@ -60,15 +60,24 @@ int af_cqt_bank_build(AfCqtBank *b, int num, int samplate, float minFre, int bpo
     b->fftLength = n;
     for (int i = 0; i < num; i++) b->sLenArr[i] = sqrtf(q * samplate / (b->freBandArr[i] + beta / alpha));
 
+    /* beta != 0 (VQT, cqt_algorithm.c:186-193, 1208-1246): no sharing of the top octave's kernels -- every octave gets its
+     * own `bpo` rows, built from its own float frequencies and the integer-halved sample rate, with the TOP octave's
+     * kernel lengths (cqt_filterBank.c:57-124) */
+    b->vqt = beta != 0;
+    b->rows = b->vqt ? num : bpo;
     const int width = n / 2 + 1;
-    b->kr = (float *)calloc((size_t)bpo * width, sizeof(float));
-    b->ki = (float *)calloc((size_t)bpo * width, sizeof(float));
+    b->kr = (float *)calloc((size_t)b->rows * width, sizeof(float));
+    b->ki = (float *)calloc((size_t)b->rows * width, sizeof(float));
     double *re = (double *)malloc(sizeof(double) * n), *im = (double *)malloc(sizeof(double) * n);
     float *win = (float *)malloc(sizeof(float) * (n + 1));
     if (!b->kr || !b->ki || !re || !im || !win) { free(re); free(im); free(win); return AF_ERR_NOMEM; }
     if (windowType == Window_Rect) windowType = Window_Hann;
     const float thresh2 = thresh * thresh;
+    int srOct = samplate;
+    for (int oct = octs - 1; oct >= (b->vqt ? 0 : octs - 1); oct--, srOct /= 2)
     for (int i = 0; i < bpo; i++) {
+        const float *fre = b->freBandArr + oct * bpo;
+        const size_t row = b->vqt ? (size_t)oct * bpo + i : (size_t)i;
         const float lenF = q * samplate / (top[i] + beta / alpha);
         int len = ceilf(lenF);
         if (len > n) len = n;
@@ -77,7 +86,7 @@ int af_cqt_bank_build(AfCqtBank *b, int num, int samplate, float minFre, int bpo
         const int st = (n - len) / 2;
         float area = 0;                                          /* float accumulation, like the reference */
         for (int j = 0; j < len; j++) {
-            float phase = 2 * M_PI * j * top[i] / samplate;     /* rounded to float like the reference */
+            float phase = 2 * M_PI * j * fre[i] / srOct;        /* rounded to float like the reference */
             float w = (normType == SpectralFilterBankNormal_None) ? lenF : 1.0f;
             float tr = cosf(phase) * win[j] / w, ti = sinf(phase) * win[j] / w;
             re[st + j] = tr; im[st + j] = ti;
@@ -87,8 +96,8 @@ int af_cqt_bank_build(AfCqtBank *b, int num, int samplate, float minFre, int bpo
         if (normType == SpectralFilterBankNormal_Area) div = area;
         else if (normType == SpectralFilterBankNormal_BandWidth) {
             /* neighbours in the full list; the slot after the last bin is 0 (as in the reference) */
-            int g = (octs - 1) * bpo + i;
-            float prev = g > 0 ? b->freBandArr[g - 1] : 0.0f;
+            int g = oct * bpo + i;
+            float prev = g > 0 ? b->freBandArr[g - 1] : 0.0f;     /* (the reference reads one float before its array there) */
             div = (b->freBandArr[g + 1] - prev) / 2;
         }
         const float rescale = lenF / n;
@@ -101,7 +110,7 @@ int af_cqt_bank_build(AfCqtBank *b, int num, int samplate, float minFre, int bpo
         fft_double(re, im, n);
         for (int k = 0; k < width; k++) {
             float vr = (float)re[k], vi = (float)im[k];
-            if (vr * vr + vi * vi > thresh2) { b->kr[(size_t)i * width + k] = vr; b->ki[(size_t)i * width + k] = vi; }
+            if (vr * vr + vi * vi > thresh2) { b->kr[row * width + k] = vr; b->ki[row * width + k] = vi; }
         }
     }
     free(re); free(im); free(win);
@@ -119,7 +128,7 @@ int af_cqt_time_kernels(const AfCqtBank *b, float *kappaRe, float *kappaIm) {
     const int n = b->fftLength, width = n / 2 + 1;
     double *re = (double *)malloc(sizeof(double) * n), *im = (double *)malloc(sizeof(double) * n);
     if (!re || !im) { free(re); free(im); return AF_ERR_NOMEM; }
-    for (int i = 0; i < b->binPerOctave; i++) {
+    for (int i = 0; i < b->rows; i++) {
         for (int k = 0; k < n; k++) {
             re[k] = k < width ? b->kr[(size_t)i * width + k] : 0.0;
             im[k] = k < width ? b->ki[(size_t)i * width + k] : 0.0;

@@ -24,6 +24,8 @@ struct OpaqueCWT {
     int bankWidth;
     int detEnabled;                /* cwtObj_enableDet */
     int haveSpec;                  /* dWork starts with the spectrum of the last single-clip call */
+    AfDevBuf dSupport;             /* fast path: per bank row the bins above 2^-28 of its peak (filled by the launcher) */
+    int supportReady;
 };
 
 int cwtObj_new(CWTObj *out, int num, int radix2Exp, int *samplate, float *lowFre, float *highFre,
@@ -81,6 +83,7 @@ static int cwt_device(CWTObj c) {
     if ((rc = af_stream_create(&c->stream))) return rc;
     if ((rc = af_dev_upload((void **)&c->dScale, c->scaleArr, sizeof(float) * (size_t)c->num))) return rc;
     if (c->bankHost && (rc = af_dev_upload((void **)&c->dBank, c->bankHost, sizeof(float) * (size_t)c->num * c->bankWidth))) return rc;
+    if ((rc = af_devbuf_reserve(&c->dSupport, sizeof(int) * 3 * (size_t)c->num))) return rc;
     c->devReady = 1;
     return AF_OK;
 }
@@ -91,6 +94,7 @@ static void cwt_args(CWTObj c, int batch, int det, AfCwtArgs *a) {
     a->log2n = c->log2fft; a->num = c->num; a->batch = batch; a->padLength = c->padLength;
     a->dataLength = c->dataLength; a->wavelet = c->wavelet; a->scaleArr = c->dScale;
     a->bankTable = c->dBank; a->bankWidth = c->bankWidth;
+    a->support = (int *)c->dSupport.ptr; a->supportReady = &c->supportReady;
 }
 
 /* dData [batch x N] -> planes [batch x num x N]; the batch is cut into chunks that fit the workspace */
@@ -196,6 +200,7 @@ void cwtObj_free(CWTObj c) {
     if (!c) return;
     af_devbuf_free(&c->dIn); af_devbuf_free(&c->dWork); af_devbuf_free(&c->dOutRe); af_devbuf_free(&c->dOutIm);
     af_dev_free(c->dScale); af_dev_free(c->dBank);
+    af_devbuf_free(&c->dSupport);
     free(c->bankHost);
     af_stream_destroy(c->stream);
     free(c->freBandArr); free(c->binBandArr); free(c->scaleArr);

@@ -127,6 +127,7 @@ struct CwtParams {
     int wType; float g, b, factor;
     int cols, rows;           // adjacent columns / rows per CTA (chosen so each leg fits shared memory)
     int itemBase;             // first (clip, scale) item of this launch (fast path processes items in groups)
+    const int *support;       // [lo: num | hi: num] bins [lo, hi) outside which the bank row is below 2^-28 of its peak (NULL: no pruning)
 };
 
 __device__ __forceinline__ float load_padded(const CwtParams &p, const float *x, int i) {
@@ -252,6 +253,29 @@ __global__ void k_cwt_rows(CwtParams p) {
     }
 }
 
+// ---- support of every bank row: bins [lo, hi) where psi_hat(s omega_k) exceeds 2^-28 of the row's peak.  Outside, the
+// fast path treats the row as zero (relative error <= 4e-9, far inside the 1e-4 tolerance): low scales touch a sliver of
+// the spectrum, and loading / evaluating the wavelet over all N/2 bins was 27 % of the fused kernel's time (ncu r2).
+__device__ __forceinline__ float bank_value(const CwtParams &p, int sIdx, int k) {
+    if (p.bankTable) return k < p.bankWidth ? fabsf(p.bankTable[(size_t)sIdx * p.bankWidth + k]) : 0.0f;
+    const float omega = fmaf((float)k, p.omegaHi, (float)k * p.omegaLo);
+    return fabsf(wavelet_eval(p.wType, p.g, p.b, p.factor, p.scaleArr[sIdx] * omega));
+}
+__global__ void k_cwt_support_peak(CwtParams p, unsigned *peakBits) {
+    const int sIdx = blockIdx.y, k = blockIdx.x * blockDim.x + threadIdx.x;
+    float v = k <= p.N / 2 ? bank_value(p, sIdx, k) : 0.0f;
+    if (!(v < INFINITY)) v = 0.0f;
+    unsigned m = __float_as_uint(v);
+    for (int o = 16; o; o >>= 1) m = max(m, __shfl_xor_sync(0xffffffffu, m, o));
+    if ((threadIdx.x & 31) == 0 && m) atomicMax(&peakBits[sIdx], m);
+}
+__global__ void k_cwt_support_range(CwtParams p, const unsigned *peakBits, int *support) {
+    const int sIdx = blockIdx.y, k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k > p.N / 2) return;
+    const float thr = __uint_as_float(peakBits[sIdx]) * 3.7252903e-9f;          // 2^-28
+    if (bank_value(p, sIdx, k) > thr) { atomicMin(&support[sIdx], k); atomicMax(&support[p.num + sIdx], k + 1); }
+}
+
 // ============================================================================================
 // Fast path for N = 2^19 (BASELINE config 4): N1 = 1024 columns leg, N2 = 512 rows leg, every
 // transform done by ONE WARP in registers (generated packed-fp32 32/16-point DFTs, warp-private
@@ -310,30 +334,58 @@ __device__ void cwt_cols_w_unit(const CwtParams &p, c64 *tile, const float2 *tw1
     const int col0 = by * kWCols;
     const float s = MODE == 1 ? p.scaleArr[item % p.num] : 0.0f;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    for (int e = threadIdx.x; e < 1024 * kWCols; e += blockDim.x) {
-        const int i = e / kWCols, c = e - i * kWCols;
-        const int k = i * N2 + col0 + c;
-        c64 v;
-        if (MODE == 0) {
-            v = c_pack(load_padded(p, p.data + (size_t)clip * p.dataLength, k), 0.0f);
-        } else {
-            // every wavelet family / bank is zero above N/2: do not fetch that half of the spectrum at all
-            const float2 y = k <= p.N / 2 ? bank_times_spec(p, s, item % p.num, k, p.spec[(size_t)clip * p.N + k]) : make_float2(0.0f, 0.0f);
-            v = c_pack(y.x, -y.y);                                             // conj: inverse transform via forward DFT
-        }
-        tile[wcol_idx(c, i)] = v;
+    // rows i of the column whose input can be non-zero (k = i N2 + column): everything for the forward transform, the
+    // bank row's support for the inverse
+    int iLo = 0, iHi = 1023, kLo = 0, kHi = p.N;
+    if (MODE == 1 && p.support) {
+        kLo = p.support[item % p.num]; kHi = p.support[p.num + item % p.num];
+        if (kHi <= kLo) { kLo = 0; kHi = 0; iLo = 0; iHi = -1; }
+        else { iLo = kLo >> p.log2N2; iHi = (kHi - 1) >> p.log2N2; }
     }
-    __syncthreads();
-
-    {   // warp `warp` transforms column `warp`: 1024 points as 32 x 32, element n = lane + 32 j
-        c64 *colp = tile + (size_t)warp * kWColPitch;
-        c64 z[32], y[32];
+    const bool single = MODE == 1 && p.support && iHi - iLo < 32;       // every lane of the 32 x 32 split sees at most ONE non-zero row
+    c64 *colp = tile + (size_t)warp * kWColPitch;
+    c64 y[32];
+    if (single) {
+        // row i = the member of [iLo, iHi] congruent to lane mod 32; stage 1 + its twiddle of a one-hot input collapse to
+        // y[ka] = v W_1024^(i ka): no tile fill, no first FFT
+        const int i = iLo + ((lane - iLo) & 31);
+        const int k = i * N2 + col0 + warp;
+        c64 v = 0ull;
+        if (i <= iHi && k >= kLo && k < kHi && k <= p.N / 2) {
+            const float2 t = bank_times_spec(p, s, item % p.num, k, p.spec[(size_t)clip * p.N + k]);
+            v = c_pack(t.x, -t.y);                                             // conj: inverse transform via forward DFT
+        }
 #pragma unroll
-        for (int j = 0; j < 32; j++) z[j] = tile[wcol_idx(warp, lane + 32 * j)];
+        for (int ka = 0; ka < 32; ka++) y[ka] = ka ? c_mul(v, c_from(t1k[(i * ka) & 1023])) : v;
+    } else {
+        const int e0 = iLo * kWCols, e1 = (iHi + 1) * kWCols;
+        for (int e = e0 + threadIdx.x; e < e1; e += blockDim.x) {
+            const int i = e / kWCols, c = e - i * kWCols;
+            const int k = i * N2 + col0 + c;
+            c64 v;
+            if (MODE == 0) {
+                v = c_pack(load_padded(p, p.data + (size_t)clip * p.dataLength, k), 0.0f);
+            } else {
+                // every wavelet family / bank is zero above N/2: do not fetch that half of the spectrum at all
+                const float2 t = (k <= p.N / 2 && k >= kLo && k < kHi) ? bank_times_spec(p, s, item % p.num, k, p.spec[(size_t)clip * p.N + k]) : make_float2(0.0f, 0.0f);
+                v = c_pack(t.x, -t.y);                                         // conj: inverse transform via forward DFT
+            }
+            tile[wcol_idx(c, i)] = v;
+        }
+        __syncthreads();
+        // warp `warp` transforms column `warp`: 1024 points as 32 x 32, element n = lane + 32 j (rows outside the support are zero)
+        c64 z[32];
+#pragma unroll
+        for (int j = 0; j < 32; j++) {
+            const int i = lane + 32 * j;
+            z[j] = (i >= iLo && i <= iHi) ? tile[wcol_idx(warp, i)] : 0ull;
+        }
         __syncwarp();
         af_fft32(z);
 #pragma unroll
         for (int ka = 0; ka < 32; ka++) y[ka] = ka ? c_mul(z[AF_BR5(ka)], c_from(tw1[ka * 32 + lane])) : z[AF_BR5(0)];
+    }
+    {
         warp_transpose32(y, reinterpret_cast<float *>(colp), lane, nullptr);
         af_fft32(y);                                                           // X[k1 = lane + 32 kb] at AF_BR5(kb)
         const int col = col0 + warp;
@@ -443,7 +495,8 @@ __device__ void cwt_rows_w_unit(const CwtParams &p, c64 *tile, const float2 *tw,
                 if (n < 0 || n >= p.dataLength) continue;
                 float re, im;
                 c_unpack(v[u], re, im);
-                oRe[n] = re * inv; oIm[n] = -im * inv;                         // conj back
+                __stcs(&oRe[n], re * inv); __stcs(&oIm[n], -im * inv);         // conj back; streaming (evict-first) stores: the
+                                                                               // 352 MB / clip of results must not push the ring out of L2
             }
         }
     }
@@ -558,6 +611,7 @@ void fill_params(const AfCwtArgs *a, CwtParams *p) {
     p->dataLength = a->dataLength; p->padLength = a->padLength; p->num = a->num; p->batch = a->batch;
     p->scaleArr = a->scaleArr;
     p->det = a->det;
+    p->support = NULL;
     { const double w = 2.0 * M_PI / (double)p->N; p->omegaHi = (float)w; p->omegaLo = (float)(w - (double)p->omegaHi); }
     p->bankTable = a->bankTable; p->bankWidth = a->bankWidth;
     p->itemBase = 0;
@@ -586,7 +640,7 @@ static int cwt_fused_enabled(const AfCwtArgs *a) {
 static int cwt_group_items(void) {
     const char *e = getenv("AFB200_CWT_GROUP");
     const int g = e ? atoi(e) : 0;
-    return g > 0 && g <= 64 ? g : 6;                     // 3 slots x 6 items x 4 MB = 72 MB of the 126 MB L2
+    return g > 0 && g <= 64 ? g : 4;                     // 3 slots x 4 items x 4 MB = 48 MB of the 126 MB L2 (sweep r2: 4 > 3 > 6 > 8 > 2)
 }
 
 // workspace = forward spectrum (batch x N float2) + inter-leg buffer: batch x num x N float2 when N > 4096, or -- fused
@@ -620,6 +674,21 @@ extern "C" int af_launch_cwt(const AfCwtArgs *a, const float *data, void *worksp
         if ((rc = set_smem(k_cwt_cols_w<0>, smC, "smem k_cwt_cols_w<0>")) || (rc = set_smem(k_cwt_cols_w<1>, smC, "smem k_cwt_cols_w<1>")) ||
             (rc = set_smem(k_cwt_rows_w<0>, smR, "smem k_cwt_rows_w<0>")) || (rc = set_smem(k_cwt_rows_w<1>, smR, "smem k_cwt_rows_w<1>"))) return rc;
         const unsigned cb = (unsigned)(p.N2 / kWCols), rb = (unsigned)(p.N1 / kWRows), items = (unsigned)(a->batch * a->num);
+        if (a->support && a->supportReady && !getenv("AFB200_CWT_NOPRUNE")) {
+            if (!*a->supportReady) {                       // once per object: peak and [lo, hi) of every bank row
+                cudaError_t e = cudaMemsetAsync(a->support, 0x7f, sizeof(int) * (size_t)a->num, st);
+                if (e == cudaSuccess) e = cudaMemsetAsync(a->support + a->num, 0, sizeof(int) * 2 * (size_t)a->num, st);
+                if (e != cudaSuccess) return af_cuda_check(e, "cudaMemsetAsync(cwt support)");
+                const dim3 g((unsigned)((p.N / 2 + 1 + 255) / 256), (unsigned)a->num);
+                unsigned *peak = reinterpret_cast<unsigned *>(a->support + 2 * a->num);
+                k_cwt_support_peak<<<g, 256, 0, st>>>(p, peak);
+                AF_LAUNCH_CHECK("k_cwt_support_peak");
+                k_cwt_support_range<<<g, 256, 0, st>>>(p, peak, a->support);
+                AF_LAUNCH_CHECK("k_cwt_support_range");
+                *a->supportReady = 1;
+            }
+            p.support = a->support;
+        }
         if (data) {                                        // NULL: reuse the spectra already in the workspace
             k_cwt_cols_w<0><<<dim3((unsigned)a->batch, cb), kWCols * 32, smC, st>>>(p);
             AF_LAUNCH_CHECK("k_cwt_cols_w<0>");
@@ -643,8 +712,39 @@ extern "C" int af_launch_cwt(const AfCwtArgs *a, const float *data, void *worksp
             if ((rc = set_smem(k_cwt_fused_w, smF, "smem k_cwt_fused_w"))) return rc;
             int sms = af_sm_count();
             if (sms <= 0) sms = 148;
+            // the ring is rewritten in place group after group: pin it in L2 (persisting access-policy window on this stream) so
+            // that its dirty lines are not written back to HBM between a group's column and row legs; the results themselves
+            // leave with streaming stores.  Best effort: any failure here just leaves the default policy.
+            const char *pe = getenv("AFB200_CWT_L2PERSIST");
+            const bool persist = !(pe && pe[0] == '0');
+            const size_t ringBytes = sizeof(float2) * (size_t)p.N * kRing * f.groupItems;
+            if (persist) {
+                static int limitSet = 0;
+                int dev = 0, maxPersist = 0, maxWindow = 0;
+                cudaGetDevice(&dev);
+                cudaDeviceGetAttribute(&maxPersist, cudaDevAttrMaxPersistingL2CacheSize, dev);
+                cudaDeviceGetAttribute(&maxWindow, cudaDevAttrMaxAccessPolicyWindowSize, dev);
+                if (maxPersist > 0 && maxWindow > 0) {
+                    if (!limitSet) { cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, (size_t)maxPersist); limitSet = 1; }
+                    cudaStreamAttrValue av;
+                    memset(&av, 0, sizeof(av));
+                    av.accessPolicyWindow.base_ptr = p.work;
+                    av.accessPolicyWindow.num_bytes = ringBytes < (size_t)maxWindow ? ringBytes : (size_t)maxWindow;
+                    av.accessPolicyWindow.hitRatio = ringBytes <= (size_t)maxPersist ? 1.0f : (float)((double)maxPersist / (double)ringBytes);
+                    av.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
+                    av.accessPolicyWindow.missProp = cudaAccessPropertyStreaming;
+                    cudaStreamSetAttribute(st, cudaStreamAttributeAccessPolicyWindow, &av);
+                    cudaGetLastError();
+                }
+            }
             k_cwt_fused_w<<<(unsigned)(2 * sms), 256, smF, st>>>(f);
             AF_LAUNCH_CHECK("k_cwt_fused_w");
+            if (persist) {
+                cudaStreamAttrValue av;
+                memset(&av, 0, sizeof(av));                          // num_bytes = 0: window off for whatever follows on this stream
+                cudaStreamSetAttribute(st, cudaStreamAttributeAccessPolicyWindow, &av);
+                cudaGetLastError();
+            }
             return AF_OK;
         }
         for (unsigned i0 = 0; i0 < items; i0 += items) {

@@ -57,8 +57,8 @@ constexpr int kMaxPeers = 15;
 constexpr int kMaxNum = 128;
 constexpr int kLPitch = 132;        // log-mel tile row pitch (floats): 4g + t -> 32 distinct banks for mma A fragments
 constexpr int kMaxTab = 1408;       // bank table entries (one float4 per bin pair of an interval) in the parameter block
-constexpr int kMaxPass = 2;         // bank passes: one piece per helper lane and pass
-constexpr int kMaxPieces = kMaxPass * kEW * 32;
+constexpr int kMaxPieces = 256;     // pieces the intervals may be cut into (slots = rows of the power tile)
+constexpr int kMaxPass = kMaxPieces / (kEW * 32);   // bank passes: one piece per helper lane and pass
 constexpr int kSpecPitch = 17;      // c64 slots per n2 row of the special-column buffer (odd -> conflict-free both ways)
 constexpr int kScratchFloats = 33 * 32;
 
@@ -85,7 +85,8 @@ struct Params {
     float *out;
     const float2 *winPairs, *tw;
     const float *dct;
-    long long dataStride, totalTiles;
+    long long dataStride;
+    unsigned totalTiles;            // (< 2^31: checked by the launcher) 32-bit tile arithmetic in the kernel
     int batch, timeLength, hop, framesPerTile, tilesPerClip, spanFloats, stages;
     int num, ccNum, rectify, dataType, rawMel, pitchPairs, bulkStore, dctPitch;
     int nPeer;
@@ -175,31 +176,31 @@ __global__ void __launch_bounds__(kThreads, 1) k_mfcc_fused2(const __grid_consta
     if (warp == kFW) {
         // ================= producer (TMA) + special columns k1 = 0 / 32 of every frame of the tile =================
         const int S = p.stages;
-        auto issue = [&](long long tile, int stage) {
-            const long long clip = tile / p.tilesPerClip;
-            const int f0 = (int)(tile % p.tilesPerClip) * F;
+        auto issue = [&](unsigned tile, int stage) {
+            const unsigned clip = tile / (unsigned)p.tilesPerClip;
+            const int f0 = (int)(tile - clip * (unsigned)p.tilesPerClip) * F;
             const int nf = min(F, p.timeLength - f0);
             const uint32_t bytes = (uint32_t)(((nf - 1) * p.hop + kN) * 4);
             af_mbar_arrive_expect_tx(&fullBar[stage], bytes);
-            af_tma_load_1d(span + (size_t)stage * p.spanFloats, p.data + clip * p.dataStride + (long long)f0 * p.hop, bytes,
+            af_tma_load_1d(span + (size_t)stage * p.spanFloats, p.data + (long long)clip * p.dataStride + (long long)f0 * p.hop, bytes,
                            &fullBar[stage]);
         };
         if (lane == 0)
             for (int s = 0; s < S; s++) {
-                const long long tile = blockIdx.x + (long long)s * gridDim.x;
+                const unsigned tile = blockIdx.x + (unsigned)s * gridDim.x;
                 if (tile < p.totalTiles) issue(tile, s);
             }
         const int f = lane & 15, kind = lane >> 4;              // lane = (frame, column kind)
         int it = 0;
-        for (long long tile = blockIdx.x; tile < p.totalTiles; tile += gridDim.x, ++it) {
+        for (unsigned tile = blockIdx.x; tile < p.totalTiles; tile += gridDim.x, ++it) {
             const int stage = it % S;
             if (lane == 0) {
                 af_mbar_wait_sleepy(&emptyBar[stage], (uint32_t)(it / S) & 1u);       // tile `it` taken: refill the slot
-                const long long next = tile + (long long)S * gridDim.x;
+                const unsigned next = tile + (unsigned)S * gridDim.x;
                 if (next < p.totalTiles) issue(next, stage);
             }
             __syncwarp();
-            const int f0 = (int)(tile % p.tilesPerClip) * F;
+            const int f0 = (int)(tile % (unsigned)p.tilesPerClip) * F;
             const int nf = min(F, p.timeLength - f0);
             const int sb = it & 1;
             af_mbar_wait(&specFull[sb], (uint32_t)(it >> 1) & 1u);
@@ -242,15 +243,15 @@ __global__ void __launch_bounds__(kThreads, 1) k_mfcc_fused2(const __grid_consta
         const int e = warp - (kFW + 1);
         const int rowFloats = p.num;
         int it = 0;
-        for (long long tile = blockIdx.x; tile < p.totalTiles; tile += gridDim.x, ++it) {
-            const long long clip = tile / p.tilesPerClip;
-            const int f0 = (int)(tile % p.tilesPerClip) * F;
+        for (unsigned tile = blockIdx.x; tile < p.totalTiles; tile += gridDim.x, ++it) {
+            const unsigned clip = tile / (unsigned)p.tilesPerClip;
+            const int f0 = (int)(tile - clip * (unsigned)p.tilesPerClip) * F;
             const int nf = min(F, p.timeLength - f0);
             const int lbuf = it & 1;
             float *L = sL + (size_t)lbuf * 16 * kLPitch;
             float *stage = sStage + (size_t)lbuf * (p.stageBytes / 8);   // (filter-bank output mode: two staging tiles)
             const int stagePitch = p.num + 4;                              // padded rows (bank conflicts)
-            af_mbar_wait_sleepy(pFull, (uint32_t)it & 1u);
+            af_mbar_wait(pFull, (uint32_t)it & 1u);
             if (!p.rawMel) af_mbar_wait(&lEmpty[lbuf], ((uint32_t)(it >> 1) & 1u) ^ 1u);    // DCT done with tile it - 2
             // ---- phase 1: ONE PIECE (<= Lmax bin pairs of one interval) PER LANE AND PASS, all frames of the tile in
             // registers: one LDS.128 of weights (rise of filter i, fall of filter i-1) and, per frame, one LDS.64 of the
@@ -299,21 +300,41 @@ __global__ void __launch_bounds__(kThreads, 1) k_mfcc_fused2(const __grid_consta
             named_bar_sync(1, kBW * 32);                           // every partial sum of the tile is in shared memory
             // ---- phase 2: mel_m = sum of the rise parts of interval m + the fall parts of interval m + 1 (pieces in
             // ascending order), rectified (cepstra) or staged as the result row (filter bank) ----
-            if (!(AF2_ABLATE & 1)) {
-                for (int m = e * 32 + lane; m < p.num; m += kBW * 32) {
-                    const int a0 = sPrefix[m], a1 = sPrefix[m + 1], a2 = sPrefix[m + 2];
+            // (kBW * 32 >= num: one band per helper lane; with fewer helper warps a lane takes kBands bands)
+            constexpr int kBands = (kMaxNum + kBW * 32 - 1) / (kBW * 32);
+            float v[kBands][kFW];
 #pragma unroll
-                    for (int f = 0; f < kFW; f++) {
-                        float v = 0.0f;
-                        for (int s = a0; s < a1; s++) v += c_re(sS[(size_t)s * pitch + f]);
-                        for (int s = a1; s < a2; s++) v += c_im(sS[(size_t)s * pitch + f]);
-                        if (p.rawMel) { if (f < nf) stage[f * stagePitch + m] = v; }
-                        else L[f * kLPitch + m] = rectify_value(v, p.rectify);
+            for (int b = 0; b < kBands; b++) {
+                const int m = (b * kBW + e) * 32 + lane;
+#pragma unroll
+                for (int f = 0; f < kFW; f++) v[b][f] = 0.0f;
+                if (!(AF2_ABLATE & 1) && m < p.num) {
+                    const int a0 = sPrefix[m], a1 = sPrefix[m + 1], a2 = sPrefix[m + 2];
+                    for (int s = a0; s < a1; s++) {
+                        const c64 *row = sS + (size_t)s * pitch;
+#pragma unroll
+                        for (int f = 0; f < kFW; f++) v[b][f] += c_re(row[f]);
+                    }
+                    for (int s = a1; s < a2; s++) {
+                        const c64 *row = sS + (size_t)s * pitch;
+#pragma unroll
+                        for (int f = 0; f < kFW; f++) v[b][f] += c_im(row[f]);
                     }
                 }
             }
             __syncwarp();
             if (lane == 0) af_mbar_arrive(pEmpty);                 // frame warps may overwrite the power tile (and the sums in it)
+#pragma unroll
+            for (int b = 0; b < kBands; b++) {
+                const int m = (b * kBW + e) * 32 + lane;
+                if (!(AF2_ABLATE & 1) && m < p.num) {
+#pragma unroll
+                    for (int f = 0; f < kFW; f++) {
+                        if (p.rawMel) { if (f < nf) stage[f * stagePitch + m] = v[b][f]; }
+                        else L[f * kLPitch + m] = rectify_value(v[b][f], p.rectify);
+                    }
+                }
+            }
             if (!p.rawMel) {
                 __syncwarp();
                 if (lane == 0) af_mbar_arrive(&lFull[lbuf]);       // the DCT warps take the tile from here
@@ -344,13 +365,13 @@ __global__ void __launch_bounds__(kThreads, 1) k_mfcc_fused2(const __grid_consta
         constexpr int kNB = (CT + kDW - 1) / kDW;                  // n-blocks of the DCT per warp
         float *stage = sStage;
         int it = 0;
-        for (long long tile = blockIdx.x; tile < p.totalTiles; tile += gridDim.x, ++it) {
-            const long long clip = tile / p.tilesPerClip;
-            const int f0 = (int)(tile % p.tilesPerClip) * F;
+        for (unsigned tile = blockIdx.x; tile < p.totalTiles; tile += gridDim.x, ++it) {
+            const unsigned clip = tile / (unsigned)p.tilesPerClip;
+            const int f0 = (int)(tile - clip * (unsigned)p.tilesPerClip) * F;
             const int nf = min(F, p.timeLength - f0);
             const int lbuf = it & 1;
             const float *L = sL + (size_t)lbuf * 16 * kLPitch;
-            af_mbar_wait_sleepy(&lFull[lbuf], (uint32_t)(it >> 1) & 1u);
+            af_mbar_wait(&lFull[lbuf], (uint32_t)(it >> 1) & 1u);
             // out[16 x 8 CT] = L[16 x 128] . D^T[128 x 8 CT]: mma.sync m16n8k8 TF32, 3xTF32 split (hi by truncation,
             // lo = x - hi exact), separate accumulators for hi*hi and the cross terms
             float acc[kNB][4], acx[kNB][4];
@@ -445,15 +466,20 @@ __global__ void __launch_bounds__(kThreads, 1) k_mfcc_fused2(const __grid_consta
     const int offLo = (lane >> 1) * (2 * pitch) + 2 * warp + (lane & 1);
     const int offHi = -((lane + 1) >> 1) * (2 * pitch) + 2 * warp + (lane & 1);
 
-    int it = 0;
-    for (long long tile = blockIdx.x; tile < p.totalTiles; tile += gridDim.x, ++it) {
-        const int stage = it % p.stages;
-        const int f0 = (int)(tile % p.tilesPerClip) * F;
+    int it = 0, stage = 0;
+    uint32_t stagePhase = 0;
+    // position of the tile inside its clip, advanced by gridDim.x tiles per iteration (no division in the loop)
+    unsigned tIn = blockIdx.x % (unsigned)p.tilesPerClip;
+    const unsigned tStep = gridDim.x % (unsigned)p.tilesPerClip;
+    for (unsigned tile = blockIdx.x; tile < p.totalTiles; tile += gridDim.x, ++it) {
+        const int f0 = (int)tIn * F;
+        tIn += tStep;
+        if (tIn >= (unsigned)p.tilesPerClip) tIn -= (unsigned)p.tilesPerClip;
         const int nf = min(F, p.timeLength - f0);
         const bool active = warp < nf;
         const int sb = it & 1;
 
-        af_mbar_wait(&fullBar[stage], (uint32_t)(it / p.stages) & 1u);
+        af_mbar_wait(&fullBar[stage], stagePhase);
 
         c64 z[32];
         if (active) {
@@ -465,6 +491,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_mfcc_fused2(const __grid_consta
         }
         __syncwarp();
         if (lane == 0) af_mbar_arrive(&emptyBar[stage]);           // span slot may be refilled
+        if (++stage == p.stages) { stage = 0; stagePhase ^= 1u; }
         if (!active) {
             // keep the tile protocols in step (one arrival per warp per tile and barrier)
             if (lane == 0) af_mbar_arrive(&specFull[sb]);
@@ -623,12 +650,12 @@ int build_table(const float *bank, int num, const Intervals *iv, unsigned *desc 
 }
 
 // Pieces: every interval is cut into runs of at most lmax bin pairs (interval order = ascending rows of the power tile).
-// The first min(128, n) pieces form pass 0, the rest pass 1; a piece's partial sums are stored in row `piece index` of the
-// power tile once its pass is over, so pass 1 must not read rows below the number of pass-0 pieces.  lmax is the smallest
-// value for which the pieces fit two passes and that condition holds.  Inside a pass the pieces are dealt to half-warps
+// Pass q takes pieces [q W, (q + 1) W), W = helper lanes; a piece's partial sums are stored in row `piece index` of the
+// power tile once its pass is over, so pass q must not read rows below q W.  lmax is the smallest value for which the
+// pieces fit the passes (at most kMaxPieces pieces) and that condition holds.  Inside a pass the pieces are dealt to half-warps
 // (16 lanes) such that their first rows differ mod 16 where possible: with the odd tile pitch the 16 lanes then read 16
 // different 8-byte bank pairs for every frame and every step of the walk (conflict-free LDS.64).
-// Returns the number of passes (1 or 2) or -1 when no lmax <= 15 works.
+// Returns the number of passes or -1 when no lmax <= 15 works.
 struct PiecePlan {
     int nPieces, lmax, firstPass2, nPass, passLen[kMaxPass];
     unsigned pieceDesc[kMaxPieces];
@@ -653,14 +680,17 @@ int plan_pieces(int num, const unsigned *desc /* num + 2 */, PiecePlan *pp) {
         if (!fits) continue;
         for (int i = n; i < kMaxNum + 4; i++) pp->prefix[i] = (unsigned short)cnt;
         for (int i = cnt; i < kMaxPieces; i++) pp->pieceDesc[i] = 0;
+        if (cnt > kPairs || cnt > kMaxPass * W) continue;                    // (slots are rows of the power tile)
+        const int nPass = (cnt + W - 1) / W;
+        bool ok = true;                                                      // pass q must not read a row that holds a sum of passes < q
+        for (int q = 1; q < nPass && ok; q++) ok = (int)(pp->pieceDesc[q * W] >> 20) >= q * W;
+        if (!ok) continue;
         const int n0 = cnt < W ? cnt : W;
-        if (cnt > n0 && (int)(pp->pieceDesc[n0] >> 20) < n0) continue;      // pass 1 would read a row that holds a pass-0 sum
-        if (cnt > kPairs) continue;                                          // (slots are rows of the power tile)
-        pp->nPieces = cnt; pp->lmax = lmax; pp->firstPass2 = n0; pp->nPass = cnt > n0 ? 2 : 1;
+        pp->nPieces = cnt; pp->lmax = lmax; pp->firstPass2 = n0; pp->nPass = nPass;
         for (int i = 0; i < kMaxPass * W; i++) pp->assign[i] = 0xffffu;
         for (int ps = 0; ps < kMaxPass; ps++) pp->passLen[ps] = 0;
         for (int ps = 0; ps < pp->nPass; ps++) {
-            const int base = ps ? n0 : 0, m = ps ? cnt - n0 : n0;
+            const int base = ps * W, m = cnt - base < W ? cnt - base : W;
             unsigned short *row = pp->assign + (size_t)ps * W;
             int used[2 * kEW][16], fill[2 * kEW];
             memset(used, 0, sizeof(used)); memset(fill, 0, sizeof(fill));
@@ -817,11 +847,12 @@ static int launch_fused2(void *plan, const float *data, int dataLength, int batc
     }
     pp->framesPerTile = F; pp->stages = stages;
     pp->tilesPerClip = (timeLength + F - 1) / F;
-    pp->totalTiles = (long long)pp->tilesPerClip * batch;
+    if ((long long)pp->tilesPerClip * batch >= (1ll << 31)) { free(pp); return af_fail(AF_ERR_UNSUPPORTED, "fused MFCC: more than 2^31 tiles in one launch"); }
+    pp->totalTiles = (unsigned)((long long)pp->tilesPerClip * batch);
 
     int sms = af_sm_count();
     if (sms <= 0) sms = 148;
-    const long long grid = pp->totalTiles < (long long)sms ? pp->totalTiles : (long long)sms;
+    const long long grid = (long long)pp->totalTiles < (long long)sms ? (long long)pp->totalTiles : (long long)sms;
     cudaStream_t st = (cudaStream_t)stream;
     cudaError_t e = cudaSuccess;
 #define AF_MFCC2_LAUNCH(CT_)                                                                                      \

@@ -1,5 +1,5 @@
 /* afb200_cqt.h -- constant-Q transform.  Replaces /root/reference/src/cqt_algorithm.h:14-62
- * (src/cqt_algorithm.c).  cqhc / deconv are exported but report "unsupported" (afb200_lastError). */
+ * (src/cqt_algorithm.c).   */
 #ifndef AFB200_CQT_H
 #define AFB200_CQT_H
 #include "afb200_types.h"
@@ -10,7 +10,7 @@ extern "C" {
 typedef struct OpaqueCQT *CQTObj;
 
 int cqtObj_new(CQTObj *cqtObj, int num, int samplate, float minFre, int *isContinue);  /* cqt_algorithm.c:110-120 */
-/* :123-247.  -1 if binPerOctave%12 or num%binPerOctave; -2 for isContinue=1 / beta!=0 (VQT). */
+/* :123-247.  -1 if binPerOctave%12 or num%binPerOctave.  beta != 0 (VQT): every octave gets its own kernel rows. */
 int cqtObj_newWith(CQTObj *cqtObj, int num, int *samplate, float *minFre, int *binPerOctave,
                    float *factor, float *beta, float *thresh, WindowType *windowType, int *slideLength,
                    int *isContinue, SpectralFilterBankNormalType *normalType, int *isScale);
@@ -26,8 +26,11 @@ void cqtObj_chroma(CQTObj cqtObj, int *chromaNum, SpectralDataType *dataType, Ch
                    float *mRealArr1, float *mImageArr1, float *mDataArr3);
 /* :602-660.  mDataArr1: timeLength x num (power or magnitude) -> mDataArr2: timeLength x ccNum. */
 void cqtObj_cqcc(CQTObj cqtObj, float *mDataArr1, int ccNum, CepstralRectifyType *rectifyType, float *mDataArr2);
-void cqtObj_cqhc(CQTObj cqtObj, float *mDataArr1, int hcNum, float *mDataArr2);              /* unsupported */
-void cqtObj_deconv(CQTObj cqtObj, float *mDataArr1, float *mDataArr2, float *mDataArr3);     /* unsupported */
+/* :662-714.  mDataArr1 [timeLength x num] magnitudes / powers of the last cqtObj_cqt call -> mDataArr2 [timeLength x hcNum]:
+ * the cepstral timbre sequence Re IFFT(|FFT(row)|) (length ceilPow2(2 num)) at round(binPerOctave log2(j + 1)). */
+void cqtObj_cqhc(CQTObj cqtObj, float *mDataArr1, int hcNum, float *mDataArr2);
+/* :716-781.  mDataArr2 = timbre (formant), mDataArr3 = pitch = Re IFFT(FFT(row) / |FFT(row)|), first num samples each. */
+void cqtObj_deconv(CQTObj cqtObj, float *mDataArr1, float *mDataArr2, float *mDataArr3);
 void cqtObj_free(CQTObj cqtObj);
 
 #ifdef __cplusplus

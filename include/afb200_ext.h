@@ -123,6 +123,10 @@ int afb200_mfccIntervalPlan(const float *bank, int num, const float *gain, int *
 int afb200_mfccBankPlan2(const float *bank, int num, int *owner /* 1025 */, unsigned *desc /* num + 2 */,
                          float *table /* 4 x 1408 */, unsigned *pieceDesc /* 256 */, unsigned short *prefix /* num + 2 */,
                          unsigned short *assign /* passes x helper lanes */, int *info /* 16 */);
+/* cepstral deconvolution of rows x num constant-Q magnitudes (cqtObj_cqhc / cqtObj_deconv for any number of rows) */
+int cqtObj_cqhcBatch(CQTObj cqtObj, const float *in, int rows, int hcNum, float *out /* rows x hcNum */, int memKind, void *stream);
+int cqtObj_deconvBatch(CQTObj cqtObj, const float *in, int rows, float *timbre, float *pitch /* rows x num each */,
+                       int memKind, void *stream);
 /* chroma_cqtFilterBank (src/filterbank/chroma_filterBank.c:176-262): bank num x cqtLength */
 int afb200_chromaCqtFilterBank(int num, int cqtLength, int binPerOctave, float minFre, float *bank);
 

@@ -641,9 +641,11 @@ def _ceil_pow2(v):
 
 def cqt_kernel_bank(num, sr, min_fre=32.703196, bpo=12, factor=1.0, beta=0.0, thresh=0.01,
                     win_type=W_HANN, norm=NORM_NONE):
-    """Top-octave spectral kernels (cqt_algorithm.c:1181-1265, cqt_filterBank.c:57-148, 253-336).
+    """Spectral kernels (cqt_algorithm.c:1181-1265, cqt_filterBank.c:57-148, 253-336): the top octave's `bpo` rows,
+    shared by all octaves -- or, beta != 0 (VQT, vFlag), `num` rows: every octave's rows from its own float
+    frequencies and the integer-halved sample rate, all with the TOP octave's kernel lengths.
 
-    Returns dict(fft_length, fre, slen(sqrt lengths), kr, ki) with kr/ki [bpo, n/2+1]."""
+    Returns dict(fft_length, fre, slen(sqrt lengths), kr, ki, vqt) with kr/ki [rows, n/2+1]."""
     octs = num // bpo
     fre = cqt_fre_arr(min_fre, num, bpo)
     top = fre[(octs - 1) * bpo:]
@@ -653,34 +655,41 @@ def cqt_kernel_bank(num, sr, min_fre=32.703196, bpo=12, factor=1.0, beta=0.0, th
     len_top = cqt_len_arr(top, sr, bpo, factor, beta)
     slen = np.sqrt(cqt_len_arr(fre, sr, bpo, factor, beta)).astype(f32)
     wt = win_type if win_type != W_RECT else W_HANN
-    kr = np.zeros((bpo, n // 2 + 1), dtype=f32)
-    ki = np.zeros((bpo, n // 2 + 1), dtype=f32)
-    for i in range(bpo):
-        ln = int(np.ceil(len_top[i]))
-        w = fft_window(wt, ln).astype(np.float64)
-        j = np.arange(ln, dtype=np.float64)
-        ph = 2 * np.pi * j * float(top[i]) / sr
-        weight = float(len_top[i]) if norm == NORM_NONE else 1.0
-        tr = np.cos(ph) * w / weight
-        ti = np.sin(ph) * w / weight
-        if norm == NORM_AREA:
-            s = np.sqrt(tr * tr + ti * ti).sum()
-            tr, ti = tr / s, ti / s
-        elif norm == NORM_BANDWIDTH:
-            full = np.concatenate([fre, [0.0, 0.0]])
-            k = (octs - 1) * bpo + i
-            bw = (float(full[k + 1]) - float(full[k - 1])) / 2
-            tr, ti = tr / bw, ti / bw
-        tr = tr * (float(len_top[i]) / n)
-        ti = ti * (float(len_top[i]) / n)
-        buf = np.zeros(n, dtype=np.complex128)
-        st = (n - ln) // 2
-        buf[st:st + ln] = tr + 1j * ti
-        K = np.fft.fft(buf)[:n // 2 + 1]
-        keep = (K.real.astype(f32).astype(np.float64) ** 2 + K.imag.astype(f32).astype(np.float64) ** 2) > float(f32(thresh) * f32(thresh))
-        kr[i] = np.where(keep, K.real, 0).astype(f32)
-        ki[i] = np.where(keep, K.imag, 0).astype(f32)
-    return dict(fft_length=n, fre=fre, slen=slen, kr=kr, ki=ki, octs=octs)
+    vqt = beta != 0
+    rows = num if vqt else bpo
+    kr = np.zeros((rows, n // 2 + 1), dtype=f32)
+    ki = np.zeros((rows, n // 2 + 1), dtype=f32)
+    full = np.concatenate([fre, [0.0, 0.0]])
+    sr_oct = int(sr)
+    for octv in range(octs - 1, (0 if vqt else octs - 1) - 1, -1):
+        for i in range(bpo):
+            f_bin = fre[octv * bpo + i]
+            ln = int(np.ceil(len_top[i]))
+            w = fft_window(wt, ln).astype(np.float64)
+            j = np.arange(ln, dtype=np.float64)
+            ph = 2 * np.pi * j * float(f_bin) / sr_oct
+            weight = float(len_top[i]) if norm == NORM_NONE else 1.0
+            tr = np.cos(ph) * w / weight
+            ti = np.sin(ph) * w / weight
+            if norm == NORM_AREA:
+                s = np.sqrt(tr * tr + ti * ti).sum()
+                tr, ti = tr / s, ti / s
+            elif norm == NORM_BANDWIDTH:
+                k = octv * bpo + i
+                bw = (float(full[k + 1]) - float(full[k - 1] if k > 0 else 0.0)) / 2
+                tr, ti = tr / bw, ti / bw
+            tr = tr * (float(len_top[i]) / n)
+            ti = ti * (float(len_top[i]) / n)
+            buf = np.zeros(n, dtype=np.complex128)
+            st = (n - ln) // 2
+            buf[st:st + ln] = tr + 1j * ti
+            K = np.fft.fft(buf)[:n // 2 + 1]
+            keep = (K.real.astype(f32).astype(np.float64) ** 2 + K.imag.astype(f32).astype(np.float64) ** 2) > float(f32(thresh) * f32(thresh))
+            row = octv * bpo + i if vqt else i
+            kr[row] = np.where(keep, K.real, 0).astype(f32)
+            ki[row] = np.where(keep, K.imag, 0).astype(f32)
+        sr_oct //= 2
+    return dict(fft_length=n, fre=fre, slen=slen, kr=kr, ki=ki, octs=octs, vqt=vqt)
 
 
 def cqt(x, num=84, sr=32000, min_fre=32.703196, bpo=12, factor=1.0, beta=0.0, thresh=0.01,
@@ -707,7 +716,8 @@ def cqt(x, num=84, sr=32000, min_fre=32.703196, bpo=12, factor=1.0, beta=0.0, th
         re, im = stft(cur, n, hop, rect, is_pad=True, position=PAD_RIGHT if is_continue else PAD_CENTER)
         S = (re[:, :n // 2 + 1].astype(np.float64) + 1j * im[:, :n // 2 + 1].astype(np.float64))
         Tn = min(T, S.shape[0])
-        v = S[:Tn] @ K.T
+        Ko = K[o * bpo:(o + 1) * bpo] if bank.get("vqt") else K
+        v = S[:Tn] @ Ko.T
         v = v * math.sqrt(float(1 << k)) if k > 0 else v
         if is_scale:
             v = v / slen[None, o * bpo:(o + 1) * bpo]
@@ -1292,3 +1302,30 @@ def reassign(x, radix2_exp=12, sr=32000, window_type=W_HANN, hop=None, re_type=R
             np.add.at(o_re, (ti[i][m], fi[i][m]), amp[i][m])
     out = (o_re, o_im, s[0][0], s[0][1])
     return out + (ti, fi) if indices else out
+
+
+# ---------------------------------------------------------------------------
+# cepstral deconvolution of constant-Q spectra: cqtObj_cqhc / cqtObj_deconv (src/cqt_algorithm.c:662-781)
+# ---------------------------------------------------------------------------
+def cq_deconv(m, bpo=12):
+    """m [T, num] magnitudes / powers -> (timbre, pitch), each [T, num]: rows zero-padded to L = ceilPow2(2 num);
+    timbre = Re IFFT(|FFT(row)|), pitch = Re IFFT(FFT(row) / max(|FFT(row)|, 1e-16))"""
+    m = np.asarray(m, dtype=np.float64)
+    T, num = m.shape
+    L = _ceil_pow2(2 * num)
+    X = np.fft.fft(np.concatenate([m, np.zeros((T, L - num))], axis=1), axis=1)
+    mag = np.abs(X).astype(f32).astype(np.float64)
+    timbre = np.fft.ifft(mag, axis=1).real
+    pitch = np.fft.ifft(X / np.maximum(mag, 1e-16), axis=1).real
+    return timbre[:, :num].astype(f32), pitch[:, :num].astype(f32)
+
+
+def cqhc(m, hc_num=20, bpo=12):
+    """`cqtObj_cqhc`: timbre[round(bpo log2(j + 1))], j < hc_num (index from float32 log2f / roundf)"""
+    m = np.asarray(m, dtype=np.float64)
+    T, num = m.shape
+    L = _ceil_pow2(2 * num)
+    X = np.fft.fft(np.concatenate([m, np.zeros((T, L - num))], axis=1), axis=1)
+    timbre = np.fft.ifft(np.abs(X).astype(f32).astype(np.float64), axis=1).real
+    idx = _roundf(f32(bpo) * np.log2(np.arange(1, hc_num + 1).astype(f32)).astype(f32)).astype(int)
+    return timbre[:, idx].astype(f32)

@@ -410,3 +410,14 @@ def test_oracle_cqt_streaming_matches_the_reference_build(ref_lib, chunks):
         wr, wi = model.push(piece)
         assert rr.shape == wr.shape and rr.shape[0] > 0
         assert rel_max(wr, rr) < 1e-5 and rel_max(wi, ri) < 1e-5
+
+
+@pytest.mark.parametrize("num,sr,beta,norm,bpo", [(84, 32000, 5.0, 0, 12), (48, 44100, 2.0, 1, 12), (72, 22050, 10.0, 2, 12),
+                                                   (48, 16000, 3.0, 0, 24)])
+def test_oracle_vqt_vs_reference_build(ref_lib, num, sr, beta, norm, bpo):
+    """VQT (beta != 0): the oracle's per-octave kernel rows against the reference build"""
+    import audioflux_b200 as af
+    x = (0.1 * np.random.default_rng(0).standard_normal(30000)).astype(np.float32)
+    z = af.CQT(num, sr, bin_per_octave=bpo, beta=beta, normal_type=af.SpectralFilterBankNormalType(norm), _lib=ref_lib).cqt(x)
+    re, im = O.cqt(x, num, sr, bpo=bpo, beta=beta, norm=norm)
+    assert rel_max(re.T, z.real) < 1e-5 and rel_max(im.T, z.imag) < 1e-5

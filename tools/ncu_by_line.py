@@ -2,13 +2,15 @@
 """Join an ncu SASS source page (ncu -i X.ncu-rep --page source --csv --print-source sass) with nvdisasm -gi -c line
 info of the same cubin: warp-stall samples, executed instructions and shared-memory wavefronts per OUTERMOST source
 line of the kernel's own .cu file.
-usage: ncu_by_line.py src.csv lines.txt <function substring> <file.cu> [units]"""
+usage: ncu_by_line.py src.csv lines.txt <function substring> <file.cu> [units] [source file] [deep]
+(deep: attribute to the DEEPEST inlined frame that lies in <file.cu> instead of the outermost line)"""
 import csv, re, sys, collections
 src_csv, lines_txt, fn, cu = sys.argv[1:5]
 units = float(sys.argv[5]) if len(sys.argv) > 5 else 476160.0
 # ---- nvdisasm: per instruction offset the outermost line in `cu`
 off2line = {}
-cur = None; infn = False; last_cu = None
+deep = len(sys.argv) > 7 and sys.argv[7] == "deep"
+cur = None; infn = False; last_cu = None; chain_first = None
 for ln in open(lines_txt):
     if ln.startswith(".text."):
         infn = fn in ln; continue
@@ -18,7 +20,12 @@ for ln in open(lines_txt):
         if m.group(1).endswith(cu) and "inlined at" not in ln: last_cu = int(m.group(2))
         elif m.group(1).endswith(cu): pass
         # outermost = the last "//## File" before the instruction without "inlined at"; track separately
-        if "inlined at" not in ln: cur = (m.group(1), int(m.group(2)))
+        if deep:
+            if chain_first is None and m.group(1).endswith(cu): chain_first = (m.group(1), int(m.group(2)))
+            if "inlined at" not in ln:
+                cur = chain_first if chain_first else (m.group(1), int(m.group(2)))
+                chain_first = None
+        elif "inlined at" not in ln: cur = (m.group(1), int(m.group(2)))
         continue
     m = re.match(r"\s+/\*([0-9a-f]+)\*/\s+\S", ln)
     if m and cur: off2line[int(m.group(1), 16)] = cur
