@@ -36,6 +36,7 @@ class BFT(Base):
         self.scale_type, self.style_type, self.normal_type = scale_type, style_type, normal_type
         self.data_type = data_type
         self.result_type = 0
+        self.is_reassign, self.is_temporal = is_reassign, is_temporal
         status = self._lib.bftObj_new(
             C.byref(self._obj), num, radix2_exp, opt_int(samplate), opt_float(low_fre),
             opt_float(high_fre), opt_int(bin_per_octave), opt_int(enum_value(window_type)),
@@ -81,6 +82,18 @@ class BFT(Base):
         im = np.zeros((T, self.num), np.float32)
         self._lib.bftObj_bft(self._obj, np_ptr(x), x.shape[-1], np_ptr(re), np_ptr(im))
         return re, im
+
+    def get_temporal_data(self, data_length):
+        """(energy, rms, zero-crossing rate) of the frames of the LAST `bft` call, each [T] (bft.py:391-417,
+        bftObj_getTemporalData); needs is_temporal=True."""
+        if not self.is_temporal:
+            raise ValueError("Please set the parameter is_temporal=True when creating the BFT object")
+        T = self.cal_time_length(data_length)
+        ptrs = [C.POINTER(C.c_float)() for _ in range(3)]
+        self._lib.bftObj_getTemporalData(self._obj, *[C.byref(q) for q in ptrs])
+        if not all(bool(q) for q in ptrs):
+            raise ValueError("Please call the `BFT.bft()` method before calling this method")
+        return tuple(np.ctypeslib.as_array(q, shape=(T,)).copy() for q in ptrs)
 
     def bft(self, data_arr, result_type=0):
         """-> [..., num, T] complex (result_type 0) or float32 (1), as bft.py:310-389."""

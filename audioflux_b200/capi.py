@@ -42,6 +42,7 @@ REFERENCE_API = {
     "bftObj_setResultType": (None, [vp, C.c_int]),
     "bftObj_setDataNormValue": (None, [vp, C.c_float]),
     "bftObj_bft": (None, [vp, vp, C.c_int, vp, vp]),
+    "bftObj_getTemporalData": (None, [vp, P(c_float_p), P(c_float_p), P(c_float_p)]),
     "bftObj_free": (None, [vp]),
     # ---- XXCC
     "xxccObj_new": (C.c_int, [P(vp), C.c_int]),

@@ -272,6 +272,10 @@ int af_launch_reassign(const AfReassignArgs *a, const float *r1, const float *i1
 /* cepstral deconvolution of rows x num constant-Q magnitudes (kernels/deconv.cu): mode 0 cqhc, 1 deconv */
 int af_launch_cq_deconv(const float *in, int rows, int num, int mode, int hcNum, int bpo, float *out0, float *out1, void *stream);
 
+/* energy / rms / zero-crossing rate of the windowed frames of ONE clip (src/temporal_algorithm.c:93-146); device arrays [T] */
+int af_launch_temporal(const float *data, int fftLength, int slideLength, int timeLength, const float *window,
+                       float *energy, float *rms, float *zcr, void *stream);
+
 void af_count_launch(int n);
 
 #ifdef __cplusplus

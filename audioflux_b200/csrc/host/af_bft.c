@@ -40,6 +40,9 @@ struct OpaqueBFT {
     float *dDctT; int dctReady;          /* general path: transposed DCT [num][num] */
     AfPipe pipe;                         /* host-pointer batches: chunked copy-in / transform / copy-out */
     int pipeLength, pipeCc, pipeRectify; /* arguments of the call the pipe is currently serving */
+    int isTemporal;                      /* bft_algorithm.c:376, 532-534: energy / rms / zcr of the frames of the last bftObj_bft call */
+    float *tempHost; int tempLength;     /* host: [energy | rms | zcr], tempLength frames each */
+    AfDevBuf dTemp;
     ReassignObj reassign;                /* isReassign = 1 (bft_algorithm.c:332-341): the bank is applied to the reassigned spectrum */
 };
 
@@ -69,10 +72,6 @@ int bftObj_new(BFTObj *out, int num, int radix2Exp, int *samplate, float *lowFre
         return -1;
     }
     if (num < 2 || num > n / 2 + 1) { printf("num is error!\n"); return -1; }
-    if (isTemporal && *isTemporal) {
-        af_fail(AF_ERR_UNSUPPORTED, "bftObj_new: isTemporal is outside the accelerated path and not supported");
-        return -2;
-    }
     AfBftSpec spec;
     spec.num = num; spec.radix2Exp = r; spec.samplate = sr; spec.binPerOctave = bpo;
     spec.lowFre = range.low; spec.highFre = range.high; spec.lowIndex = range.lowIndex; spec.highIndex = range.highIndex;
@@ -90,6 +89,7 @@ int bftObj_new(BFTObj *out, int num, int radix2Exp, int *samplate, float *lowFre
         status = reassignObj_new(&(*out)->reassign, r, &sr, &wt, &spec.slideLength, &reType, NULL, NULL, NULL);
         if (status) { bftObj_free(*out); *out = NULL; }
     }
+    if (!status && isTemporal && *isTemporal) (*out)->isTemporal = 1;
     return status;
 }
 
@@ -141,9 +141,12 @@ float *bftObj_getFreBandArr(BFTObj b) { return b ? b->freBandArr : NULL; }
 int *bftObj_getBinBandArr(BFTObj b) { return b ? b->binBandArr : NULL; }
 void bftObj_setResultType(BFTObj b, int type) { if (b) b->resultType = type; }
 void bftObj_setDataNormValue(BFTObj b, float v) { if (b && v > 0) b->normValue = v; }
+/* bft_algorithm.c:541-547: arrays [timeLength of the last bftObj_bft call], owned by the object; nothing without isTemporal */
 void bftObj_getTemporalData(BFTObj b, float **e, float **r, float **z) {
-    (void)b; (void)e; (void)r; (void)z;
-    af_fail(AF_ERR_UNSUPPORTED, "bftObj_getTemporalData: temporal features are not part of libaudioflux_b200");
+    if (!b || !b->isTemporal || !b->tempHost) return;
+    if (e) *e = b->tempHost;
+    if (r) *r = b->tempHost + b->tempLength;
+    if (z) *z = b->tempHost + 2 * (size_t)b->tempLength;
 }
 int bftObj_mfccPlanMode(BFTObj b) { return b ? af_mfcc_plan_mode(b->mfccPlan) : -1; }
 int bftObj_getFilterBankArr(BFTObj b, float *bank) {
@@ -305,9 +308,29 @@ int bftObj_bftBatch(BFTObj b, const float *data, int dataLength, int batch, floa
                        (size_t)T * b->num, st);
 }
 
+/* temporal descriptors of the clip's frames (isTemporal): one more small kernel on the object's stream */
+static int bft_temporal(BFTObj b, const float *dataArr, int dataLength) {
+    const int T = bftObj_calTimeLength(b, dataLength);
+    if (T <= 0) return AF_OK;
+    int rc;
+    if (T != b->tempLength) {
+        free(b->tempHost);
+        b->tempHost = (float *)calloc((size_t)3 * T, sizeof(float));
+        if (!b->tempHost) { b->tempLength = 0; return AF_ERR_NOMEM; }
+        b->tempLength = T;
+    }
+    if ((rc = af_devbuf_reserve(&b->dIn, sizeof(float) * (size_t)dataLength)) || (rc = af_devbuf_reserve(&b->dTemp, sizeof(float) * 3 * (size_t)T))) return rc;
+    float *d = (float *)b->dTemp.ptr;
+    if ((rc = af_memcpy_h2d(b->dIn.ptr, dataArr, sizeof(float) * (size_t)dataLength, b->stream))) return rc;
+    if ((rc = af_launch_temporal((const float *)b->dIn.ptr, b->fftLength, b->slideLength, T, b->dWindow, d, d + T, d + 2 * (size_t)T, b->stream))) return rc;
+    if ((rc = af_memcpy_d2h(b->tempHost, d, sizeof(float) * 3 * (size_t)T, b->stream))) return rc;
+    return af_stream_sync(b->stream);
+}
+
 void bftObj_bft(BFTObj b, float *dataArr, int dataLength, float *mRealArr3, float *mImageArr3) {
     if (!b || !dataArr || !mRealArr3) return;
-    bftObj_bftBatch(b, dataArr, dataLength, 1, mRealArr3, mImageArr3, AFB200_MEM_HOST, NULL);
+    if (bftObj_bftBatch(b, dataArr, dataLength, 1, mRealArr3, mImageArr3, AFB200_MEM_HOST, NULL)) return;
+    if (b->isTemporal) bft_temporal(b, dataArr, dataLength);
 }
 
 /* phase of the STFT bins lowIndex..highIndex as spectrogramObj_spectrogram reports it for the Linear scale
@@ -483,6 +506,7 @@ void bftObj_free(BFTObj b) {
     af_mfcc_plan_free(b->mfccPlan); af_mfcc_plan_free(b->melPlan);
     af_mfcc2_plan_free(b->mfccPlan2); af_mfcc2_plan_free(b->melPlan2);
     reassignObj_free(b->reassign);
+    free(b->tempHost); af_devbuf_free(&b->dTemp);
     af_devbuf_free(&b->dIn); af_devbuf_free(&b->dSpecRe); af_devbuf_free(&b->dSpecIm);
     af_devbuf_free(&b->dOutRe); af_devbuf_free(&b->dOutIm);
     af_dev_free(b->dWindow); af_dev_free(b->dBank); af_dev_free(b->dPacked);

@@ -228,6 +228,24 @@ __global__ void k_spec_post(float *__restrict__ re, float *__restrict__ im, long
     re[i] = v;
 }
 
+// temporal descriptors of the windowed frames (src/temporal_algorithm.c:93-146): energy sum v^2, rms sqrt(E / n) and the
+// zero-crossing rate #{v[i] v[i-1] < 0} / n, v = x . w.  One warp per frame.
+__global__ void __launch_bounds__(256) k_temporal(const float *__restrict__ data, int n, int hop, int T, const float *__restrict__ window,
+                                                  float *__restrict__ e, float *__restrict__ r, float *__restrict__ z) {
+    const int t = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+    if (t >= T) return;
+    const float *x = data + (size_t)t * hop;
+    float acc = 0.0f;
+    int cross = 0;
+    for (int i = lane; i < n; i += 32) {
+        const float v = x[i] * window[i];
+        acc += v * v;
+        if (i > 0 && v * (x[i - 1] * window[i - 1]) < 0.0f) cross++;
+    }
+    for (int o = 16; o; o >>= 1) { acc += __shfl_xor_sync(0xffffffffu, acc, o); cross += __shfl_xor_sync(0xffffffffu, cross, o); }
+    if (lane == 0) { e[t] = acc; r[t] = sqrtf(acc / (float)n); z[t] = (float)(1.0 * cross / n); }
+}
+
 }  // namespace
 
 extern "C" int af_launch_bank(const AfBankDev *bank, const float *in, int rows, float postPow, float *out, void *stream) {
@@ -303,5 +321,13 @@ extern "C" int af_launch_spec_post(float *re, float *im, long long cells, int mo
     if (cells <= 0 || mode == AF_STFT_HALF) return AF_OK;
     k_spec_post<<<(unsigned)((cells + 255) / 256), 256, 0, (cudaStream_t)stream>>>(re, im, cells, mode, normValue);
     AF_LAUNCH_CHECK("k_spec_post");
+    return AF_OK;
+}
+
+extern "C" int af_launch_temporal(const float *data, int fftLength, int slideLength, int timeLength, const float *window,
+                                  float *energy, float *rms, float *zcr, void *stream) {
+    if (timeLength <= 0) return AF_OK;
+    k_temporal<<<(unsigned)((timeLength + 7) / 8), 256, 0, (cudaStream_t)stream>>>(data, fftLength, slideLength, timeLength, window, energy, rms, zcr);
+    AF_LAUNCH_CHECK("k_temporal");
     return AF_OK;
 }

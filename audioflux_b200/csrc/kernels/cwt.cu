@@ -389,16 +389,22 @@ __device__ void cwt_cols_w_unit(const CwtParams &p, c64 *tile, const float2 *tw1
         warp_transpose32(y, reinterpret_cast<float *>(colp), lane, nullptr);
         af_fft32(y);                                                           // X[k1 = lane + 32 kb] at AF_BR5(kb)
         const int col = col0 + warp;
+        // inter-leg twiddle W_N^(col k1), k1 = lane + 32 kb: W_N^(col lane) . (W_N^(32 col))^kb.  Two table products per lane
+        // (W_N^j = W_1024^(j / N2) . W_N^(j % N2)) and a running product over kb in groups of 8, re-anchored at kb = 0, 8, 16, 24
+        // by exact table values: 10 table look-ups per lane instead of 64 (ncu r2: 10.4 % of the kernel sat on them), and at
+        // most 7 chained float products (relative error < 1e-6).
+        auto wN = [&](int j) { return c_mul(c_from(t1k[(j >> p.log2N2) & 1023]), c_from(tf[j & (N2 - 1)])); };
+        const c64 step = N2 > 1 ? wN((32 * col) & (p.N - 1)) : c_pack(1.0f, 0.0f);
 #pragma unroll
-        for (int kb = 0; kb < 32; kb++) {
-            const int k1 = lane + 32 * kb;
-            c64 v = y[AF_BR5(kb)];
-            if (N2 > 1) {
-                const int prod = col * k1;                                     // W_N^prod = W_1024^(prod / N2) * W_N^(prod % N2)
-                const int hi = prod >> p.log2N2;
-                v = c_mul(v, c_mul(c_from(t1k[hi & 1023]), c_from(tf[prod & (N2 - 1)])));
+        for (int g8 = 0; g8 < 4; g8++) {
+            c64 w = N2 > 1 ? wN((col * (lane + 256 * g8)) & (p.N - 1)) : c_pack(1.0f, 0.0f);
+#pragma unroll
+            for (int u = 0; u < 8; u++) {
+                const int kb = 8 * g8 + u, k1 = lane + 32 * kb;
+                c64 v = y[AF_BR5(kb)];
+                if (N2 > 1) { v = c_mul(v, w); if (u < 7) w = c_mul(w, step); }
+                tile[wcol_idx(warp, k1)] = v;
             }
-            tile[wcol_idx(warp, k1)] = v;
         }
     }
     __syncthreads();
@@ -584,9 +590,11 @@ __global__ void __launch_bounds__(256, 2) k_cwt_fused_w(FusedParams f) {
             __syncthreads();
             if (isRows) cwt_rows_w_unit<1>(p, tile, twr, item, by, wk);
             else cwt_cols_w_unit<1>(p, tile, tw1, item, by, wk);
-            __threadfence();                                                    // this CTA's global writes before the release below
-            __syncthreads();
-            if (threadIdx.x == 0) atomicAdd(&f.counters[1 + (isRows ? f.groups : 0) + g], 1u);
+            __syncthreads();                                                    // every thread's global writes of this unit are done ...
+            if (threadIdx.x == 0) {                                             // ... and ordered before the release below (the fence is
+                __threadfence();                                                // cumulative over the barrier: one per unit instead of 256)
+                atomicAdd(&f.counters[1 + (isRows ? f.groups : 0) + g], 1u);
+            }
         }
     }
 }
@@ -712,11 +720,12 @@ extern "C" int af_launch_cwt(const AfCwtArgs *a, const float *data, void *worksp
             if ((rc = set_smem(k_cwt_fused_w, smF, "smem k_cwt_fused_w"))) return rc;
             int sms = af_sm_count();
             if (sms <= 0) sms = 148;
-            // the ring is rewritten in place group after group: pin it in L2 (persisting access-policy window on this stream) so
-            // that its dirty lines are not written back to HBM between a group's column and row legs; the results themselves
-            // leave with streaming stores.  Best effort: any failure here just leaves the default policy.
+            // Optional (AFB200_CWT_L2PERSIST=1): pin the ring in L2 with a persisting access-policy window on this stream.  Measured
+            // (r2, 8 clips): DRAM writes drop from 415 to 348 MB / clip (= the compulsory 352 MB) but the kernel gets 10 % SLOWER
+            // (0.39 vs 0.354 ms / clip: the set-aside takes L2 away from the spectrum reads and the result stores), so the default is
+            // off: streaming result stores + a 48 MB ring already keep the traffic at 1.17x compulsory.
             const char *pe = getenv("AFB200_CWT_L2PERSIST");
-            const bool persist = !(pe && pe[0] == '0');
+            const bool persist = pe && pe[0] == '1';
             const size_t ringBytes = sizeof(float2) * (size_t)p.N * kRing * f.groupItems;
             if (persist) {
                 static int limitSet = 0;

@@ -10,7 +10,8 @@ extern "C" {
 typedef struct OpaqueBFT *BFTObj;
 
 /* bft_algorithm.c:87-276.  Returns 0 ok; -100 bad radix2Exp; 1 scale > Log; -1 bad num /
- * range overflow; -2 for isTemporal (outside the hot path, rejected loudly).  isReassign = 1: the bank is applied to the
+ * range overflow.  isTemporal = 1: bftObj_bft also computes energy / rms / zero-crossing rate of the windowed frames
+ * (src/temporal_algorithm.c:93-146), read with bftObj_getTemporalData.  isReassign = 1: the bank is applied to the
  * reassigned spectrum (include/afb200_reassign.h, Reassign_All); every call starts from zeroed planes -- the reference
  * keeps adding into its cached planes from the second call on (bft_algorithm.c:441-455), which is not reproduced. */
 int bftObj_new(BFTObj *bftObj, int num, int radix2Exp, int *samplate, float *lowFre, float *highFre,
@@ -25,7 +26,7 @@ void bftObj_setResultType(BFTObj bftObj, int type);               /* :568-571, 0
 void bftObj_setDataNormValue(BFTObj bftObj, float normValue);     /* :573-578 */
 /* :397-540.  mRealArr3/mImageArr3: timeLength x num (mImageArr3 untouched when resultType=1). */
 void bftObj_bft(BFTObj bftObj, float *dataArr, int dataLength, float *mRealArr3, float *mImageArr3);
-void bftObj_getTemporalData(BFTObj bftObj, float **eArr, float **rArr, float **zArr); /* :543-548, unsupported */
+void bftObj_getTemporalData(BFTObj bftObj, float **eArr, float **rArr, float **zArr); /* :541-547, arrays of the last bftObj_bft call (isTemporal = 1) */
 void bftObj_free(BFTObj bftObj);                                  /* :580-626 */
 
 #ifdef __cplusplus

@@ -29,7 +29,7 @@ void stftObj_stft(STFTObj stftObj, float *dataArr, int dataLength, float *mRealA
 /* :304-409.  mRealArr/mImageArr: timeLength x fftLength (full spectrum); dataArr: (timeLength-1)*slide + fftLength
  * samples, pre-zeroed by the caller (frames are added to its content, then divided by the window sum).
  * methodType 0 'weight' (synthesis window w, normaliser sum w^2), else 'overlap-add' (normaliser sum w).
- * fftLength <= 8192. */
+ * fftLength <= 16384 (the forward transform's range; 16384 takes an in-place shared-memory path). */
 void stftObj_istft(STFTObj stftObj, float *mRealArr, float *mImageArr, int timeLength, int methodType, float *dataArr);
 void stftObj_free(STFTObj stftObj);                                            /* :411-467, NULL-safe */
 void stftObj_debug(STFTObj stftObj);                                           /* :837-849 */

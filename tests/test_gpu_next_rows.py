@@ -430,3 +430,16 @@ def test_vqt_vs_oracle_and_reference(cuda_device, ref_lib, num, sr, beta, norm, 
     re, im = O.cqt(x, num, sr, bpo=bpo, beta=beta, norm=norm)
     assert rel_max(z.real, re.T) < 1e-4 and rel_max(z.imag, im.T) < 1e-4
     assert rel_max(z.real, zr.real) < 1e-4 and rel_max(z.imag, zr.imag) < 1e-4
+
+
+def test_istft_16384_round_trip(torch_cuda):
+    """fftLength 16384: the forward STFT accepted it, the inverse did not -- now an in-place shared-memory path"""
+    n, hop = 16384, 4096
+    x = noise(5, n + 9 * hop)
+    s = af.STFT(14, af.WindowType.HANN, hop)
+    re, im = O.stft(x, n, hop, O.fft_window(O.W_HANN, n))
+    y = s.istft_planes(re, im, 0)
+    want = O.istft(re, im, n, hop, O.fft_window(O.W_HANN, n), 0)
+    ok = istft_conditioned(n, hop, re.shape[0], O.fft_window(O.W_HANN, n), 0)
+    assert rel_max(y[ok], want[ok]) < 1e-4
+    assert rel_max(y[n:-n], x[n:-n]) < 1e-4                          # round trip where four windows overlap

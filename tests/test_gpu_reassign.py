@@ -93,3 +93,22 @@ def test_bft_with_reassign_vs_reference_build(cuda_device, ref_lib, result_type,
     err = np.linalg.norm(got - want) / np.linalg.norm(want)
     assert err <= 1e-2, err                      # cells within an ulp of a rounding boundary move by one bin (see above)
     assert rel_max(np.abs(got), np.abs(want)) < 5e-2
+
+
+def test_bft_temporal_descriptors_vs_reference_build(cuda_device, ref_lib):
+    """bftObj_new(isTemporal = 1): energy / rms / zero-crossing rate of the windowed frames (src/temporal_algorithm.c:93-146)"""
+    import audioflux_b200 as af
+    S = af.SpectralFilterBankScaleType
+    x = _signal(20000, 16000, 31)
+    outs = []
+    for lib in (None, ref_lib):
+        b = af.BFT(64, 10, 16000, slide_length=200, scale_type=S.MEL, is_temporal=True, _lib=lib)
+        b.bft(x, result_type=1)
+        outs.append(b.get_temporal_data(len(x)))
+    for g, w in zip(*outs):
+        assert g.shape == w.shape and g.shape[0] == (20000 - 1024) // 200 + 1
+        assert rel_max(g, w) < 1e-5
+    w = O.fft_window(O.W_HANN, 1024).astype(np.float64)
+    fr = np.stack([x[t * 200:t * 200 + 1024] * w for t in range(outs[0][0].shape[0])])
+    assert rel_max(outs[0][0], (fr ** 2).sum(1)) < 1e-5
+    assert np.array_equal(outs[0][2], ((fr[:, 1:] * fr[:, :-1] < 0).sum(1) / 1024).astype(np.float32))

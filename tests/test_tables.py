@@ -83,7 +83,8 @@ def test_bft_new_status_codes(product_lib):
     assert product_lib.bftObj_new(ctypes.byref(obj), 64, 11, *a3) == 0              # isReassign: supported (bank over the reassigned spectrum)
     product_lib.bftObj_free(obj)
     a4 = list(args); a4[11] = opt_int(1)
-    assert product_lib.bftObj_new(ctypes.byref(obj), 64, 11, *a4) == -2             # isTemporal: rejected loudly
+    assert product_lib.bftObj_new(ctypes.byref(obj), 64, 11, *a4) == 0              # isTemporal: supported (energy / rms / zcr)
+    product_lib.bftObj_free(obj)
     assert product_lib.stftObj_new(ctypes.byref(obj), 0, None, None, None) == -100
     assert product_lib.xxccObj_new(ctypes.byref(obj), 1) == -1
     assert product_lib.cqtObj_newWith(ctypes.byref(obj), 84, None, None, opt_int(10), *([None] * 8)) == -1
