@@ -233,6 +233,7 @@ typedef struct {
     int bankWidth;
     int *support;            /* device, 3 x num ints: per bank row the bins [lo, hi) above 2^-28 of its peak (+ scratch); NULL = no pruning */
     int *supportReady;       /* host flag of the owning object: 0 until the launcher has filled `support` */
+    int forwardOnly;         /* 1: only the forward transform of the `batch` real sequences -> workspace[batch][N] float2 (long-frame STFT) */
 } AfCwtArgs;
 size_t af_cwt_workspace_bytes(const AfCwtArgs *a);
 /* data == NULL: skip the forward transform and reuse the spectra a previous call left in `workspace` */

@@ -97,7 +97,7 @@ int bftObj_new(BFTObj *out, int num, int radix2Exp, int *samplate, float *lowFre
 int af_bft_create(const AfBftSpec *p, BFTObj *out) {
     const int num = p->num, r = p->radix2Exp, n = 1 << r, sr = p->samplate, scale = p->scaleType;
     *out = NULL;
-    if (r > 14) { af_fail(AF_ERR_UNSUPPORTED, "radix2Exp > 14 is not supported"); return -2; }
+    if (r > 20) { af_fail(AF_ERR_UNSUPPORTED, "radix2Exp > 20 is not supported"); return -2; }
     BFTObj b = (BFTObj)calloc(1, sizeof(struct OpaqueBFT));
     if (!b) return -1;
     b->num = num; b->radix2Exp = r; b->fftLength = n; b->samplate = sr; b->binPerOctave = p->binPerOctave;

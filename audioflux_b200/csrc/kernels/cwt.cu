@@ -703,6 +703,7 @@ extern "C" int af_launch_cwt(const AfCwtArgs *a, const float *data, void *worksp
             k_cwt_rows_w<0><<<dim3((unsigned)a->batch, rb), kWRows * 16, smR, st>>>(p);
             AF_LAUNCH_CHECK("k_cwt_rows_w<0>");
         }
+        if (a->forwardOnly) return AF_OK;
         if (cwt_fused_enabled(a)) {
             FusedParams f;
             f.p = p;
@@ -783,6 +784,7 @@ extern "C" int af_launch_cwt(const AfCwtArgs *a, const float *data, void *worksp
             AF_LAUNCH_CHECK("k_cwt_rows<0>");
         }
     }
+    if (a->forwardOnly) return AF_OK;
     // per (clip, scale): wavelet * spectrum -> inverse transform -> planes
     const unsigned items = (unsigned)(a->batch * a->num);
     k_cwt_cols<1><<<dim3(items, colBlocks), threads, smemC, st>>>(p);

@@ -1,4 +1,4 @@
-// stft_generic.cu -- framed real FFT for any power-of-two fftLength in [4, 16384].
+// stft_generic.cu -- framed real FFT for any power-of-two fftLength in [2, 2^20].
 //
 // Replaces the reference's per-frame loop `__vmul(window) ; fftObj_fft` (src/stft_algorithm.c:696-715,
 // 790-801), the Hermitian mirror of `_fftObj_fft` (src/dsp/fft_algorithm.c:309-317) and the
@@ -8,8 +8,11 @@
 // One CTA per frame.  The n real samples are packed as n/2 complex points, transformed by a
 // shared-memory Stockham radix-4 (+ one radix-2 when log2(n/2) is odd) autosort FFT and unpacked
 // with the real-FFT post-pass.  This is the general path; the MFCC configuration has its own
-// fused kernel (mfcc_fused.cu).
+// fused kernel (mfcc_fused.cu).  Frames longer than 16384 points (the reference accepts radix2Exp up to 30,
+// src/stft_algorithm.c:114-117) do not fit a CTA: they are gathered (window, padding) into a workspace, transformed by the
+// four-step kernels of the CWT path (kernels/cwt.cu, forward leg only) and written out by a mode-specific pass.
 #include <math.h>
+#include <string.h>
 #include "common.cuh"
 #include "stockham.cuh"
 
@@ -123,12 +126,53 @@ __global__ void k_stft_n2(StftParams p, long long frames) {
     }
 }
 
+
+// ---- long frames (n > 16384): gather -> four-step forward FFT (cwt.cu) -> mode-specific write-out ----
+__global__ void __launch_bounds__(256) k_frames_gather(StftParams p, long long frame0, int nf, float *__restrict__ frames) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= (long long)nf * p.n) return;
+    const long long f = frame0 + i / p.n;
+    const int j = (int)(i % p.n);
+    const int frame = (int)(f % p.timeLength), clip = (int)(f / p.timeLength);
+    float v = padded_sample(p, p.data + (long long)clip * p.dataStride, frame * p.hop - p.padLeft + j);
+    if (p.window) v *= p.window[j];
+    frames[i] = v;
+}
+
+__global__ void __launch_bounds__(256) k_long_post(StftParams p, long long frame0, int nf, const float2 *__restrict__ spec) {
+    const int nc = p.n / 2, width = nc + 1;
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= (long long)nf * width) return;
+    const long long f = i / width, row = frame0 + f;
+    const int k = (int)(i % width);
+    const float2 X = spec[f * p.n + k];
+    const float xr = X.x, xi = (k == 0 || k == nc) ? 0.0f : X.y;
+    const int n = p.n;
+    switch (p.mode) {
+    case AF_STFT_FULL: {
+        float *re = p.outRe + row * n, *im = p.outIm + row * n;
+        re[k] = xr; im[k] = xi;
+        if (k > 0 && k < nc) { re[n - k] = xr; im[n - k] = -xi; }
+    } break;
+    case AF_STFT_HALF: p.outRe[row * width + k] = xr; p.outIm[row * width + k] = xi; break;
+    case AF_STFT_SQUARE: p.outRe[row * width + k] = xr * xr - xi * xi; p.outIm[row * width + k] = 2.0f * xr * xi; break;
+    case AF_STFT_POWER: {
+        float v = xr * xr + xi * xi;
+        if (p.normValue != 1.0f) v = powf(v, p.normValue);
+        p.outRe[row * width + k] = v;
+    } break;
+    default: p.outRe[row * width + k] = sqrtf(xr * xr + xi * xi);
+    }
+}
+
 }  // namespace
+
+static int launch_stft_long(StftParams p, long long frames, cudaStream_t st);
 
 extern "C" int af_launch_stft(const AfFrameSrc *src, int mode, float normValue, float *outRe, float *outIm, void *stream) {
     const int n = src->fftLength;
     if (n < 2 || (n & (n - 1))) return af_fail(AF_ERR_ARG, "fftLength %d is not a power of two", n);
-    if (n > 16384) return af_fail(AF_ERR_UNSUPPORTED, "STFT fftLength %d > 16384 is not supported by the shared-memory FFT", n);
+    if (n > (1 << 20)) return af_fail(AF_ERR_UNSUPPORTED, "STFT fftLength %d > 2^20 is not supported", n);
     const long long frames = (long long)src->batch * src->timeLength;
     if (frames <= 0) return AF_OK;
     if (frames > 0x7fffffffLL) return af_fail(AF_ERR_ARG, "too many frames in one launch");
@@ -139,8 +183,9 @@ extern "C" int af_launch_stft(const AfFrameSrc *src, int mode, float normValue, 
     p.hop = src->slideLength; p.timeLength = src->timeLength; p.padLeft = src->padLeft;
     p.validLength = src->validLength; p.mode = mode; p.normValue = normValue;
     p.padMode = src->padMode; p.padValue1 = src->padValue1; p.padValue2 = src->padValue2;
-    p.tw = n >= 4 ? af_twiddle_table(p.log2nc) : nullptr;
     cudaStream_t st = (cudaStream_t)stream;
+    if (n > 16384) return launch_stft_long(p, frames, st);
+    p.tw = n >= 4 ? af_twiddle_table(p.log2nc) : nullptr;
     if (n == 2) {
         k_stft_n2<<<(unsigned)((frames + 255) / 256), 256, 0, st>>>(p, frames);
         AF_LAUNCH_CHECK("k_stft_n2");
@@ -155,6 +200,41 @@ extern "C" int af_launch_stft(const AfFrameSrc *src, int mode, float normValue, 
     k_stft_generic<<<(unsigned)frames, threads, smem, st>>>(p);
     AF_LAUNCH_CHECK("k_stft_generic");
     return AF_OK;
+}
+
+// frames of more than 16384 points: chunks of frames through a stream-ordered workspace (gathered frames + spectrum +
+// inter-leg buffer = 20 bytes per sample, <= 512 MB at a time)
+static int launch_stft_long(StftParams p, long long frames, cudaStream_t st) {
+    const int n = p.n;
+    int log2n = 0;
+    while ((1 << log2n) < n) log2n++;
+    const size_t perFrame = (size_t)n * (sizeof(float) + 2 * sizeof(float2));
+    long long chunk = (long long)(((size_t)512 << 20) / perFrame);
+    if (chunk < 1) chunk = 1;
+    if (chunk > frames) chunk = frames;
+    void *ws = nullptr;
+    cudaError_t e = cudaMallocAsync(&ws, perFrame * (size_t)chunk, st);
+    if (e != cudaSuccess) return af_cuda_check(e, "cudaMallocAsync(long-frame STFT workspace)");
+    float2 *spec = static_cast<float2 *>(ws);                              // [chunk][n] spectrum + [chunk][n] inter-leg buffer
+    float *dFrames = reinterpret_cast<float *>(spec + 2 * (size_t)chunk * n);
+    int rc = AF_OK;
+    for (long long f0 = 0; f0 < frames && rc == AF_OK; f0 += chunk) {
+        const int nf = (int)(frames - f0 < chunk ? frames - f0 : chunk);
+        const long long cells = (long long)nf * n;
+        k_frames_gather<<<(unsigned)((cells + 255) / 256), 256, 0, st>>>(p, f0, nf, dFrames);
+        af_count_launch(1);
+        AfCwtArgs a;
+        memset(&a, 0, sizeof(a));
+        a.log2n = log2n; a.num = 1; a.batch = nf; a.padLength = 0; a.dataLength = n; a.forwardOnly = 1;
+        // (the workspace handed to the CWT launcher: spectrum first, its inter-leg slots right behind)
+        if ((rc = af_launch_cwt(&a, dFrames, spec, nullptr, nullptr, st))) break;
+        const long long outCells = (long long)nf * (n / 2 + 1);
+        k_long_post<<<(unsigned)((outCells + 255) / 256), 256, 0, st>>>(p, f0, nf, spec);
+        af_count_launch(1);
+        if (cudaGetLastError() != cudaSuccess) rc = af_fail(AF_ERR_CUDA, "long-frame STFT launch failed");
+    }
+    cudaFreeAsync(ws, st);
+    return rc;
 }
 
 // ---- twiddle tables shared by the Stockham kernels (STFT general path, ISTFT) ----

@@ -13,7 +13,8 @@ typedef struct OpaqueSTFT *STFTObj;
 /* stft_algorithm.c:84-168.  radix2Exp in [1,30] else -100; NULL pointers = defaults
  * (rect window, slide = fftLength/4, isContinue 0).  isContinue=1 (streaming, :474-599): every stftObj_stft call
  * transforms the samples carried over from the previous calls followed by the new ones and keeps the rest that did not
- * complete a hop (non-padding mode only, as in the reference; the batched / device-pointer entry points are stateless). */
+ * complete a hop (non-padding mode only, as in the reference; the batched / device-pointer entry points are stateless).
+ * Transforms run for fftLength up to 2^20 (one CTA per frame up to 16384 points, the four-step kernels above that). */
 int stftObj_new(STFTObj *stftObj, int radix2Exp, WindowType *windowType, int *slideLength, int *isContinue);
 void stftObj_setSlideLength(STFTObj stftObj, int slideLength);                 /* :171-178 */
 void stftObj_enablePadding(STFTObj stftObj, int flag);                         /* :186-189 */
@@ -29,7 +30,7 @@ void stftObj_stft(STFTObj stftObj, float *dataArr, int dataLength, float *mRealA
 /* :304-409.  mRealArr/mImageArr: timeLength x fftLength (full spectrum); dataArr: (timeLength-1)*slide + fftLength
  * samples, pre-zeroed by the caller (frames are added to its content, then divided by the window sum).
  * methodType 0 'weight' (synthesis window w, normaliser sum w^2), else 'overlap-add' (normaliser sum w).
- * fftLength <= 16384 (the forward transform's range; 16384 takes an in-place shared-memory path). */
+ * fftLength <= 16384 (16384 takes an in-place shared-memory path). */
 void stftObj_istft(STFTObj stftObj, float *mRealArr, float *mImageArr, int timeLength, int methodType, float *dataArr);
 void stftObj_free(STFTObj stftObj);                                            /* :411-467, NULL-safe */
 void stftObj_debug(STFTObj stftObj);                                           /* :837-849 */
