@@ -74,7 +74,10 @@ int af_devbuf_reserve(AfDevBuf *b, size_t bytes) {
 
 void af_devbuf_free(AfDevBuf *b) { if (b->ptr) cudaFree(b->ptr); b->ptr = NULL; b->bytes = 0; }
 
+/* *dptr must be NULL or an earlier allocation of this call (object fields: calloc'ed); a table uploaded again after a
+ * failed lazy initialisation replaces the earlier copy instead of leaking it */
 int af_dev_upload(void **dptr, const void *host, size_t bytes) {
+    if (*dptr) { cudaFree(*dptr); }
     *dptr = NULL;
     if (bytes == 0) return AF_OK;
     int e = cudaMalloc(dptr, bytes);
@@ -85,6 +88,7 @@ int af_dev_upload(void **dptr, const void *host, size_t bytes) {
 void af_dev_free(void *p) { if (p) cudaFree(p); }
 
 int af_stream_create(void **s) {
+    if (*s) return AF_OK;                                  /* already created by an earlier, partially failed initialisation */
     cudaStream_t st;
     int e = cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking);
     if (e != cudaSuccess) { *s = NULL; return af_cuda_check(e, "cudaStreamCreate"); }

@@ -81,7 +81,8 @@ class OverlappedGather:
             o = compute(clips[lo:hi])
             outs.append(o)
             self.done[k].record(cur)
-        if self.gathered is None or len(self.gathered) != len(outs) or self.gathered[0].shape[1:] != outs[0].shape[1:]:
+        want = [(world * o.shape[0],) + tuple(o.shape[1:]) for o in outs]          # full shape of every chunk: batch / world size may change
+        if self.gathered is None or [tuple(g.shape) for g in self.gathered] != want or self.gathered[0].device != outs[0].device:
             self.gathered = [torch.empty((world * o.shape[0],) + tuple(o.shape[1:]), dtype=o.dtype, device=o.device) for o in outs]
         with torch.cuda.stream(self.comm):
             for k, o in enumerate(outs):

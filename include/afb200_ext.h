@@ -24,6 +24,11 @@
 extern "C" {
 #endif
 
+/* Memory kinds of the batched entry points.  AFB200_MEM_DEVICE calls are asynchronous on the caller's stream.
+ * An object is NOT thread-safe and is SINGLE-STREAM: its tables are bound to the device that was current at its first
+ * compute call, and the general (non-fused) paths use per-object scratch buffers (spectrum planes, frame buffers, the CWT
+ * workspace), so two calls on the same object must be ordered on one stream (or by events).  Different objects may run
+ * concurrently on different streams / threads. */
 #define AFB200_MEM_HOST 0
 #define AFB200_MEM_DEVICE 1
 
