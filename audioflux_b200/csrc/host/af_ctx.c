@@ -82,7 +82,12 @@ int af_dev_upload(void **dptr, const void *host, size_t bytes) {
     if (bytes == 0) return AF_OK;
     int e = cudaMalloc(dptr, bytes);
     if (e != cudaSuccess) { *dptr = NULL; return af_fail(AF_ERR_NOMEM, "cudaMalloc(%zu bytes): %s", bytes, cudaGetErrorString((cudaError_t)e)); }
-    return af_cuda_check(cudaMemcpy(*dptr, host, bytes, cudaMemcpyHostToDevice), "cudaMemcpy H2D (table)");
+    e = cudaMemcpy(*dptr, host, bytes, cudaMemcpyHostToDevice);
+    /* A pageable-source cudaMemcpy may return once the bytes sit in the driver's staging buffer, before the DMA has
+     * landed; the kernels that read the table run on non-blocking streams, which do not order themselves behind the
+     * legacy stream.  Wait for the copy itself (tables are uploaded once per object, never on a hot path). */
+    if (e == cudaSuccess) e = cudaStreamSynchronize(cudaStreamLegacy);
+    return af_cuda_check(e, "cudaMemcpy H2D (table)");
 }
 
 void af_dev_free(void *p) { if (p) cudaFree(p); }

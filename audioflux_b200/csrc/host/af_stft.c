@@ -158,6 +158,12 @@ static int stft_continue_assemble(STFTObj s, const float *data, int dataLength, 
     return 1;
 }
 
+/* the same bookkeeping for objects that frame through an STFT object of their own (SpectrogramObj streaming) */
+int af_stft_continue_assemble(STFTObj s, const float *data, int dataLength, const float **cur, int *curLength) {
+    if (!s || !data || dataLength <= 0) return 0;
+    return stft_continue_assemble(s, data, dataLength, cur, curLength);
+}
+
 void stftObj_stft(STFTObj s, float *dataArr, int dataLength, float *mRealArr, float *mImageArr) {
     if (!s || !dataArr || dataLength <= 0 || !mRealArr || !mImageArr) return;
     af_clear_error();

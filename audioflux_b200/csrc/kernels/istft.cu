@@ -6,7 +6,12 @@
 // with e = 1 ('weight', methodType 0) or e = 0 ('overlap-add'); a window sum below 1e-6 is replaced by 1.
 // Two kernels: frames (one CTA per frame, shared-memory Stockham FFT) and a gather over the <= n/hop frames that
 // cover an output sample, summed in ascending frame order like the reference's loop (bit-stable, no atomics).
+// Frames of 2^15 .. 2^20 points (the reference accepts radix2Exp up to 30, src/stft_algorithm.c:114-117) do not fit a
+// CTA: Re(IFFT_n(X)) is taken from ONE real-input forward transform of the four-step kernels (kernels/cwt.cu, forward
+// leg) by the Hartley identity -- with H = the Hermitian part of X (the only part Re(IFFT) sees) and the real sequence
+// c[k] = Re H[k] + Im H[k],  C = FFT_n(c):   Re(IFFT_n(X))[j] = (Re C[j] + Im C[j]) / n.
 #include <math.h>
+#include <string.h>
 #include "common.cuh"
 #include "stockham.cuh"
 
@@ -96,25 +101,91 @@ __global__ void k_istft_ola(const float *__restrict__ frames, int n, int hop, in
     data[i] = acc / norm;
 }
 
+// ---- long frames: c = Re H + Im H of the (mirrored) planes -> four-step forward FFT -> (Re C + Im C) / n ----
+__global__ void __launch_bounds__(256) k_istft_long_pre(const float *__restrict__ re, const float *__restrict__ im, int width, int n,
+                                                        long long row0, int nf, float *__restrict__ c) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= (long long)nf * n) return;
+    const long long f = i / n;
+    const int k = (int)(i - f * n), km = k ? n - k : 0;
+    const float *r = re + (row0 + f) * width, *q = im + (row0 + f) * width;
+    // X[k] as k_istft_frames reads it: the planes below `width`, the Hermitian mirror above
+    const float xr = k < width ? r[k] : r[n - k], xi = k < width ? q[k] : -q[n - k];
+    const float yr = km < width ? r[km] : r[n - km], yi = km < width ? q[km] : -q[n - km];
+    c[i] = 0.5f * (xr + yr) + 0.5f * (xi - yi);
+}
+
+__global__ void __launch_bounds__(256) k_istft_long_post(const float2 *__restrict__ spec, int n, long long row0, int nf,
+                                                         const float *__restrict__ window, int weightMode, float *__restrict__ frames) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= (long long)nf * n) return;
+    const int j = (int)(i % n);
+    const float2 C = spec[i];
+    float v = (C.x + C.y) * (1.0f / (float)n);
+    if (weightMode && window) v *= window[j];
+    frames[row0 * n + i] = v;
+}
+
 }  // namespace
+
+// frames of more than 16384 points: chunks of frames through a stream-ordered workspace (real sequence + spectrum +
+// inter-leg buffer = 20 bytes per sample, <= 512 MB at a time), as the forward side does (stft_generic.cu)
+static int launch_istft_frames_long(const float *re, const float *im, int width, int n, int log2n, long long rows,
+                                    const float *window, int weightMode, float *frames, cudaStream_t st) {
+    const size_t perFrame = (size_t)n * (sizeof(float) + 2 * sizeof(float2));
+    long long chunk = (long long)(((size_t)512 << 20) / perFrame);
+    if (chunk < 1) chunk = 1;
+    if (chunk > rows) chunk = rows;
+    void *ws = nullptr;
+    cudaError_t e = cudaMallocAsync(&ws, perFrame * (size_t)chunk, st);
+    if (e != cudaSuccess) return af_cuda_check(e, "cudaMallocAsync(long-frame ISTFT workspace)");
+    float2 *spec = static_cast<float2 *>(ws);                              // [chunk][n] spectrum + [chunk][n] inter-leg buffer
+    float *c = reinterpret_cast<float *>(spec + 2 * (size_t)chunk * n);
+    int rc = AF_OK;
+    for (long long r0 = 0; r0 < rows && rc == AF_OK; r0 += chunk) {
+        const int nf = (int)(rows - r0 < chunk ? rows - r0 : chunk);
+        const long long cells = (long long)nf * n;
+        k_istft_long_pre<<<(unsigned)((cells + 255) / 256), 256, 0, st>>>(re, im, width, n, r0, nf, c);
+        af_count_launch(1);
+        AfCwtArgs a;
+        memset(&a, 0, sizeof(a));
+        a.log2n = log2n; a.num = 1; a.batch = nf; a.padLength = 0; a.dataLength = n; a.forwardOnly = 1;
+        if ((rc = af_launch_cwt(&a, c, spec, nullptr, nullptr, st))) break;
+        k_istft_long_post<<<(unsigned)((cells + 255) / 256), 256, 0, st>>>(spec, n, r0, nf, window, weightMode, frames);
+        af_count_launch(1);
+        if (cudaGetLastError() != cudaSuccess) rc = af_fail(AF_ERR_CUDA, "long-frame ISTFT launch failed");
+    }
+    cudaFreeAsync(ws, st);
+    return rc;
+}
 
 extern "C" int af_launch_istft(const float *re, const float *im, int width, int fftLength, int slideLength, int timeLength,
                                int batch, const float *window, int methodType, float *frames, float *data, void *stream) {
     if (timeLength <= 0 || batch <= 0) return AF_OK;
     int log2n = 0;
     while ((1 << log2n) < fftLength) log2n++;
+    if (fftLength > (1 << 20)) return af_fail(AF_ERR_UNSUPPORTED, "istft: fftLength %d > 2^20 is not supported", fftLength);
+    const int weightMode = methodType == 0;
+    cudaStream_t st = (cudaStream_t)stream;
+    const int dataLength = (timeLength - 1) * slideLength + fftLength;
+    const long long total = (long long)batch * dataLength;
+    if (fftLength > 16384) {
+        int rc = launch_istft_frames_long(re, im, width, fftLength, log2n, (long long)batch * timeLength, window, weightMode, frames, st);
+        if (rc) return rc;
+        k_istft_ola<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(frames, fftLength, slideLength, timeLength, dataLength, window,
+                                                                    weightMode, data, total);
+        AF_LAUNCH_CHECK("k_istft_ola");
+        return AF_OK;
+    }
     size_t smem = sizeof(float2) * 2 * (size_t)fftLength;
     const bool inplace = smem > 200 * 1024;                     /* 16384 points: one buffer, in-place passes */
     if (inplace) smem /= 2;
-    if (smem > 200 * 1024) return af_fail(AF_ERR_UNSUPPORTED, "istft: fftLength %d > 16384 does not fit the shared-memory FFT", fftLength);
     if (smem > 48 * 1024) {
         cudaError_t e = inplace ? cudaFuncSetAttribute(k_istft_frames_inplace, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)
                                 : cudaFuncSetAttribute(k_istft_frames, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return af_cuda_check(e, "cudaFuncSetAttribute(k_istft_frames)");
     }
-    const int weightMode = methodType == 0;
     int threads = fftLength / 4; if (threads < 32) threads = 32; if (threads > 1024) threads = 1024;
-    cudaStream_t st = (cudaStream_t)stream;
     if (inplace)
         k_istft_frames_inplace<<<(unsigned)((long long)batch * timeLength), threads, smem, st>>>(re, im, width, fftLength, log2n, window,
                                                                                                 weightMode, frames, af_twiddle_table(log2n));
@@ -122,8 +193,6 @@ extern "C" int af_launch_istft(const float *re, const float *im, int width, int 
         k_istft_frames<<<(unsigned)((long long)batch * timeLength), threads, smem, st>>>(re, im, width, fftLength, log2n, window,
                                                                                         weightMode, frames, af_twiddle_table(log2n));
     AF_LAUNCH_CHECK("k_istft_frames");
-    const int dataLength = (timeLength - 1) * slideLength + fftLength;
-    const long long total = (long long)batch * dataLength;
     k_istft_ola<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(frames, fftLength, slideLength, timeLength, dataLength, window,
                                                                 weightMode, data, total);
     AF_LAUNCH_CHECK("k_istft_ola");

@@ -48,6 +48,12 @@ constexpr int kPairs = 513;         // bin pairs of the power-spectrum tile
 #ifndef AF2_ABLATE
 #define AF2_ABLATE 0                // diagnostic timing builds: 1 no bank, 2 no DCT, 4 no FFTs, 8 no transposes, 16 no loads
 #endif
+#ifndef AF2_WAIT
+#define AF2_WAIT 0                  // which mbarrier waits carry a suspend-time hint: 1 frame warps (power tile), 2 bank warps, 4 DCT warps, 8 frame warps (samples), 16 producer (tile protocol)
+#endif
+#ifndef AF2_WAIT_NS
+#define AF2_WAIT_NS 1000
+#endif
 constexpr int kFW = AF2_FRAME_WARPS;            // frame warps = max frames per tile (<= 16: one mma M tile)
 constexpr int kBW = AF2_BANK_WARPS;             // filter-bank warps (one interval per lane)
 constexpr int kDW = AF2_DCT_WARPS;              // DCT (tensor-core) + store warps, one tile behind the bank warps
@@ -111,6 +117,26 @@ __device__ __forceinline__ void bulk_store(void *dstGmem, const void *srcSmem, u
 __device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
 __device__ __forceinline__ void bulk_wait_read0() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
 __device__ __forceinline__ void bulk_wait0() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+
+// wait of one warp class: plain try_wait loop, or (AF2_WAIT bit set) try_wait with a suspend-time hint -- the warp sleeps in
+// hardware until the phase completes instead of polling through issue slots the compute warps need
+template <int BIT>
+__device__ __forceinline__ void wait_cls(uint64_t *bar, uint32_t parity) {
+    if (AF2_WAIT & BIT) {
+        uint32_t spins = 0, ok = 0;
+        while (true) {
+            asm volatile(
+                "{\n\t.reg .pred p;\n\t"
+                "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
+                "selp.u32 %0, 1, 0, p;\n\t}"
+                : "=r"(ok) : "r"(af_smem_u32(bar)), "r"(parity), "r"((uint32_t)AF2_WAIT_NS) : "memory");
+            if (ok) break;
+            if (++spins > (1u << 24)) __trap();
+        }
+    } else {
+        af_mbar_wait(bar, parity);
+    }
+}
 
 __device__ __forceinline__ float rectify_value(float v, int rectify) {
     if (rectify == CepstralRectify_CubicRoot) return powf(v, 1.0f / 3.0f);
@@ -203,7 +229,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_mfcc_fused2(const __grid_consta
             const int f0 = (int)(tile % (unsigned)p.tilesPerClip) * F;
             const int nf = min(F, p.timeLength - f0);
             const int sb = it & 1;
-            af_mbar_wait(&specFull[sb], (uint32_t)(it >> 1) & 1u);
+            wait_cls<16>(&specFull[sb], (uint32_t)(it >> 1) & 1u);
             // a[n2] = R_n2[0], b[n2] = R_n2[32] (both real).  kind 0: X[64 k2] = DFT32(a)[k2], k2 = 0..16;
             // kind 1: X[32 + 64 k2] = DFT32(b[n2] W_64^n2)[k2], k2 = 0..15
             c64 u[32];
@@ -217,7 +243,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_mfcc_fused2(const __grid_consta
                 if (n2 >= 16 && kind) u[n2] = c_mul_mi(u[n2]);                        // W_64^16 = -i
             }
             af_fft32(u);
-            af_mbar_wait(pEmpty, ((uint32_t)it & 1u) ^ 1u);                   // bank done with the previous tile
+            wait_cls<16>(pEmpty, ((uint32_t)it & 1u) ^ 1u);                   // bank done with the previous tile
             if (f < nf) {
                 float *dst = sP + 2 * f + (kind ? 32 * pitch : 0);                    // bin 64 k2 + 32 kind -> pair 32 k2 + 16 kind
 #pragma unroll
@@ -251,8 +277,8 @@ __global__ void __launch_bounds__(kThreads, 1) k_mfcc_fused2(const __grid_consta
             float *L = sL + (size_t)lbuf * 16 * kLPitch;
             float *stage = sStage + (size_t)lbuf * (p.stageBytes / 8);   // (filter-bank output mode: two staging tiles)
             const int stagePitch = p.num + 4;                              // padded rows (bank conflicts)
-            af_mbar_wait(pFull, (uint32_t)it & 1u);
-            if (!p.rawMel) af_mbar_wait(&lEmpty[lbuf], ((uint32_t)(it >> 1) & 1u) ^ 1u);    // DCT done with tile it - 2
+            wait_cls<2>(pFull, (uint32_t)it & 1u);
+            if (!p.rawMel) wait_cls<2>(&lEmpty[lbuf], ((uint32_t)(it >> 1) & 1u) ^ 1u);    // DCT done with tile it - 2
             // ---- phase 1: ONE PIECE (<= Lmax bin pairs of one interval) PER LANE AND PASS, all frames of the tile in
             // registers: one LDS.128 of weights (rise of filter i, fall of filter i-1) and, per frame, one LDS.64 of the
             // power pair + two FFMA2 -- kFW independent accumulator chains per lane.  Pass 0 walks the low rows of the
@@ -371,7 +397,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_mfcc_fused2(const __grid_consta
             const int nf = min(F, p.timeLength - f0);
             const int lbuf = it & 1;
             const float *L = sL + (size_t)lbuf * 16 * kLPitch;
-            af_mbar_wait(&lFull[lbuf], (uint32_t)(it >> 1) & 1u);
+            wait_cls<4>(&lFull[lbuf], (uint32_t)(it >> 1) & 1u);
             // out[16 x 8 CT] = L[16 x 128] . D^T[128 x 8 CT]: mma.sync m16n8k8 TF32, 3xTF32 split (hi by truncation,
             // lo = x - hi exact), separate accumulators for hi*hi and the cross terms
             float acc[kNB][4], acx[kNB][4];
@@ -479,7 +505,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_mfcc_fused2(const __grid_consta
         const bool active = warp < nf;
         const int sb = it & 1;
 
-        af_mbar_wait(&fullBar[stage], stagePhase);
+        wait_cls<8>(&fullBar[stage], stagePhase);
 
         c64 z[32];
         if (active) {
@@ -495,7 +521,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_mfcc_fused2(const __grid_consta
         if (!active) {
             // keep the tile protocols in step (one arrival per warp per tile and barrier)
             if (lane == 0) af_mbar_arrive(&specFull[sb]);
-            af_mbar_wait(pEmpty, ((uint32_t)it & 1u) ^ 1u);
+            wait_cls<1>(pEmpty, ((uint32_t)it & 1u) ^ 1u);
             if (lane == 0) af_mbar_arrive(pFull);
             continue;
         }
@@ -551,7 +577,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_mfcc_fused2(const __grid_consta
         }
         // ---- D: 32-point DFT over n2 in lane k1: bins k1 + 64 k2 and, mirrored, 64 (32 - k2) - k1 ----
         if (!(AF2_ABLATE & 4)) af_fft32(z);
-        af_mbar_wait(pEmpty, ((uint32_t)it & 1u) ^ 1u);     // bank done with the previous tile's spectra
+        wait_cls<1>(pEmpty, ((uint32_t)it & 1u) ^ 1u);      // bank done with the previous tile's spectra
         if (lane) {
             if (p.dataType == SpectralData_Mag) {                  // (uniform branch: no sqrt sequence in the power path)
 #pragma unroll

@@ -259,7 +259,9 @@ const float2 *af_twiddle_table(int log2n) {
     }
     float2 *d = nullptr;
     if (cudaMalloc(&d, sizeof(float2) * h.size()) != cudaSuccess) { cudaGetLastError(); return nullptr; }
-    if (cudaMemcpy(d, h.data(), sizeof(float2) * h.size(), cudaMemcpyHostToDevice) != cudaSuccess) { cudaGetLastError(); cudaFree(d); return nullptr; }
+    // (pageable source: wait for the DMA itself, the Stockham kernels run on non-blocking streams -- see af_dev_upload)
+    if (cudaMemcpy(d, h.data(), sizeof(float2) * h.size(), cudaMemcpyHostToDevice) != cudaSuccess ||
+        cudaStreamSynchronize(cudaStreamLegacy) != cudaSuccess) { cudaGetLastError(); cudaFree(d); return nullptr; }
     cache[dev][log2n] = d;
     return d;
 }

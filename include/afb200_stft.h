@@ -30,7 +30,8 @@ void stftObj_stft(STFTObj stftObj, float *dataArr, int dataLength, float *mRealA
 /* :304-409.  mRealArr/mImageArr: timeLength x fftLength (full spectrum); dataArr: (timeLength-1)*slide + fftLength
  * samples, pre-zeroed by the caller (frames are added to its content, then divided by the window sum).
  * methodType 0 'weight' (synthesis window w, normaliser sum w^2), else 'overlap-add' (normaliser sum w).
- * fftLength <= 16384 (16384 takes an in-place shared-memory path). */
+ * fftLength up to 2^20: one CTA per frame up to 16384 points (16384 takes an in-place shared-memory path), above that
+ * Re(IFFT) comes from one real-input forward transform of the four-step kernels (Hartley identity, kernels/istft.cu). */
 void stftObj_istft(STFTObj stftObj, float *mRealArr, float *mImageArr, int timeLength, int methodType, float *dataArr);
 void stftObj_free(STFTObj stftObj);                                            /* :411-467, NULL-safe */
 void stftObj_debug(STFTObj stftObj);                                           /* :837-849 */
