@@ -24,6 +24,31 @@ class Base(object):
         return getattr(self._lib, name)
 
 
+class BandAxis:
+    """Plot-axis helper of the banded transforms (reference: the y_coords of bft.py / cqt.py / cwt.py / pwt.py / wsst.py):
+    the band frequencies with the lower edge in front."""
+
+    def y_coords(self):
+        return np.concatenate(([self.low_fre], self.get_fre_band_arr()))
+
+
+class FrameAxis:
+    """Time axis of a framed transform: data_length / samplate seconds cut into cal_time_length frames."""
+    _needs_full_frame = True
+
+    def x_coords(self, data_length):
+        if self._needs_full_frame and data_length < self.fft_length:
+            raise ValueError(f"radix2_exp={self.radix2_exp}(fft_length={self.fft_length}) is too large for data_length={data_length}")
+        return np.linspace(0, data_length / self.samplate, self.cal_time_length(data_length) + 1)
+
+
+class SampleAxis:
+    """Time axis of a per-sample transform (CWT family): one column per sample of the 2**radix2_exp window."""
+
+    def x_coords(self):
+        return np.linspace(0, self.fft_length / self.samplate, self.fft_length + 1)
+
+
 def as_f32(a):
     return np.ascontiguousarray(np.asarray(a, dtype=np.float32))
 

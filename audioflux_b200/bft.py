@@ -6,14 +6,14 @@ import ctypes as C
 
 import numpy as np
 
-from .base import Base, as_f32, np_ptr, split_batch, swap_last2
+from .base import Base, BandAxis, FrameAxis, as_f32, np_ptr, split_batch, swap_last2
 from .capi import opt_int, opt_float
 from .lib import check
 from .types import (WindowType, SpectralFilterBankScaleType, SpectralFilterBankStyleType,
                     SpectralFilterBankNormalType, SpectralDataType, CepstralRectifyType, enum_value)
 
 
-class BFT(Base):
+class BFT(BandAxis, FrameAxis, Base):
     def __init__(self, num, radix2_exp=12, samplate=32000, low_fre=None, high_fre=None,
                  bin_per_octave=12, window_type=WindowType.HANN, slide_length=None,
                  scale_type=SpectralFilterBankScaleType.LINEAR,

@@ -6,7 +6,7 @@ import ctypes as C
 
 import numpy as np
 
-from .base import Base, as_f32, np_ptr, split_batch, swap_last2
+from .base import Base, BandAxis, FrameAxis, as_f32, np_ptr, split_batch, swap_last2
 from .capi import opt_int, opt_float
 from .lib import check
 from .types import (WindowType, SpectralFilterBankNormalType, SpectralDataType, ChromaDataNormalType,
@@ -15,7 +15,8 @@ from .types import (WindowType, SpectralFilterBankNormalType, SpectralDataType, 
 C1_HZ = 32.703196
 
 
-class CQT(Base):
+class CQT(BandAxis, FrameAxis, Base):
+    _needs_full_frame = False            # padded frames: any data length gives data_length // slide + 1 columns
     def __init__(self, num=84, samplate=32000, low_fre=C1_HZ, bin_per_octave=12, factor=1., beta=0.,
                  thresh=0.01, window_type=WindowType.HANN, slide_length=None,
                  normal_type=SpectralFilterBankNormalType.AREA, is_scale=True, is_continue=False, _lib=None):

@@ -146,16 +146,25 @@ static int cwt_batch(CWTObj c, const float *data, int batch, int det, float *mRe
         st = stream;
         return cwt_compute(c, data, batch, det, mReal4, mImag4, st);
     }
-    /* host pointers: stream clip by clip so the device footprint stays one clip's planes */
+    /* host pointers: chunks of clips whose planes fit a bounded staging buffer (<= 512 MB per plane, at least one clip):
+     * one copy in, one launch sequence over chunk x num items, two copies out per chunk.  Long transforms (2^19 points:
+     * 176 MB per plane and clip) go two clips at a time, the short windows of CWT.ccwt (2^12 points) hundreds at a time
+     * instead of one latency-bound round trip per window. */
     const size_t inB = sizeof(float) * (size_t)c->dataLength, outB = sizeof(float) * (size_t)c->num * c->dataLength;
-    if ((rc = af_devbuf_reserve(&c->dIn, inB)) || (rc = af_devbuf_reserve(&c->dOutRe, outB)) || (rc = af_devbuf_reserve(&c->dOutIm, outB))) return rc;
-    for (int b = 0; b < batch; b++) {
-        if ((rc = af_memcpy_h2d(c->dIn.ptr, data + (size_t)b * c->dataLength, inB, st))) return rc;
-        if ((rc = cwt_compute(c, (const float *)c->dIn.ptr, 1, det, (float *)c->dOutRe.ptr, (float *)c->dOutIm.ptr, st))) return rc;
-        if ((rc = af_memcpy_d2h(mReal4 + (size_t)b * c->num * c->dataLength, c->dOutRe.ptr, outB, st)) ||
-            (rc = af_memcpy_d2h(mImag4 + (size_t)b * c->num * c->dataLength, c->dOutIm.ptr, outB, st))) return rc;
+    size_t chunk = ((size_t)512 << 20) / outB;
+    if (chunk < 1) chunk = 1;
+    if (chunk > (size_t)batch) chunk = (size_t)batch;
+    if ((rc = af_devbuf_reserve(&c->dIn, chunk * inB)) || (rc = af_devbuf_reserve(&c->dOutRe, chunk * outB)) ||
+        (rc = af_devbuf_reserve(&c->dOutIm, chunk * outB))) return rc;
+    for (int b = 0; b < batch; b += (int)chunk) {
+        const size_t nb = (size_t)(batch - b) < chunk ? (size_t)(batch - b) : chunk;
+        if ((rc = af_memcpy_h2d(c->dIn.ptr, data + (size_t)b * c->dataLength, nb * inB, st))) return rc;
+        if ((rc = cwt_compute(c, (const float *)c->dIn.ptr, (int)nb, det, (float *)c->dOutRe.ptr, (float *)c->dOutIm.ptr, st))) return rc;
+        if ((rc = af_memcpy_d2h(mReal4 + (size_t)b * c->num * c->dataLength, c->dOutRe.ptr, nb * outB, st)) ||
+            (rc = af_memcpy_d2h(mImag4 + (size_t)b * c->num * c->dataLength, c->dOutIm.ptr, nb * outB, st))) return rc;
         if ((rc = af_stream_sync(st))) return rc;
     }
+    if (batch > 1) c->haveSpec = 0;      /* cwtObj_cwtDet(NULL) continues a SINGLE-clip call only */
     return AF_OK;
 }
 
@@ -286,6 +295,7 @@ void pwtObj_free(PWTObj p) {
     CWTObj c = &p->c;
     af_devbuf_free(&c->dIn); af_devbuf_free(&c->dWork); af_devbuf_free(&c->dOutRe); af_devbuf_free(&c->dOutIm);
     af_dev_free(c->dScale); af_dev_free(c->dBank);
+    af_devbuf_free(&c->dSupport);
     af_stream_destroy(c->stream);
     free(c->bankHost); free(c->freBandArr); free(c->binBandArr); free(c->scaleArr);
     free(p);

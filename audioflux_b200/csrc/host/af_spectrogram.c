@@ -20,6 +20,7 @@ struct OpaqueSpectrogram {
     float *freBandArr;      /* Linear: own arrays (grid of __vlinspace); else borrowed from the core */
     int *binBandArr;
     int ownBands;
+    STFTObj stream;         /* isContinue = 1: an STFT object that only keeps the tail between calls (stft_algorithm.c:474-599) */
 };
 
 int spectrogramObj_new(SpectrogramObj *out, int num, int *samplate, float *lowFre, float *highFre, int *binPerOctave,
@@ -41,7 +42,7 @@ int spectrogramObj_new(SpectrogramObj *out, int num, int *samplate, float *lowFr
         af_fail(AF_ERR_UNSUPPORTED, "spectrogramObj_new: scale type %d (Chroma / Deep family) is not supported", (int)scale);
         return -2;
     }
-    if (isContinue && *isContinue) { af_fail(AF_ERR_UNSUPPORTED, "spectrogramObj_new: isContinue=1 (streaming) is not supported"); return -2; }
+    const int streaming = isContinue && *isContinue;
     int bpo = 12;
     if (binPerOctave && *binPerOctave > 0) bpo = *binPerOctave;
     if (bpo % 12 != 0) bpo = 12;
@@ -82,6 +83,13 @@ int spectrogramObj_new(SpectrogramObj *out, int num, int *samplate, float *lowFr
     if (rc) { free(s); return rc; }
     bftObj_setResultType(s->core, 1);
     if (xxccObj_new(&s->cc, num)) { spectrogramObj_free(s); return -1; }
+    if (streaming) {
+        /* the reference hands isContinue to its STFT object (spectrogram_algorithm.c:655-664): samples that did not
+         * complete a frame wait for the next call.  Same bookkeeping here, in front of the fused / general kernels. */
+        WindowType wt = (WindowType)spec.windowType;
+        int one = 1;
+        if (stftObj_new(&s->stream, r, &wt, &spec.slideLength, &one)) { spectrogramObj_free(s); return -1; }
+    }
     s->num = num; s->fftLength = n; s->samplate = sr; s->lowIndex = spec.lowIndex; s->highIndex = spec.highIndex;
     s->scaleType = scale; s->styleType = (SpectralFilterBankStyleType)spec.styleType;
     if (scale == SpectralFilterBankScale_Linear) {
@@ -142,7 +150,10 @@ int spectrogramObj_newDeepChroma(SpectrogramObj *o, int samplate, int radix2Exp,
 void spectrogramObj_enableDebug(SpectrogramObj s, int flag) { (void)s; (void)flag; }   /* the reference only prints */
 
 void spectrogramObj_setDataNormValue(SpectrogramObj s, float v) { if (s) bftObj_setDataNormValue(s->core, v); }
-int spectrogramObj_calTimeLength(SpectrogramObj s, int dataLength) { return s ? bftObj_calTimeLength(s->core, dataLength) : 0; }
+int spectrogramObj_calTimeLength(SpectrogramObj s, int dataLength) {
+    if (!s) return 0;
+    return s->stream ? stftObj_calTimeLength(s->stream, dataLength) : bftObj_calTimeLength(s->core, dataLength);   /* :848-853 */
+}
 float *spectrogramObj_getFreBandArr(SpectrogramObj s) { return s ? s->freBandArr : NULL; }
 int *spectrogramObj_getBinBandArr(SpectrogramObj s) { return s ? s->binBandArr : NULL; }
 int spectrogramObj_getBandNum(SpectrogramObj s) { return s ? s->num : 0; }
@@ -168,8 +179,13 @@ int spectrogramObj_mfccBatch(SpectrogramObj s, const float *data, int dataLength
 
 void spectrogramObj_spectrogram(SpectrogramObj s, float *dataArr, int dataLength, float *mSpectArr, float *mPhaseArr) {
     if (!s || !dataArr || dataLength <= 0 || !mSpectArr) return;      /* :966-978: nothing to do without data */
+    const float *x = dataArr;
+    if (s->stream) {                                                  /* streaming: tail of the earlier calls ++ dataArr */
+        s->timeLength = 0;
+        if (!af_stft_continue_assemble(s->stream, dataArr, dataLength, &x, &dataLength)) return;
+    }
     s->timeLength = bftObj_calTimeLength(s->core, dataLength);
-    spectrogramObj_spectrogramBatch(s, dataArr, dataLength, 1, mSpectArr, mPhaseArr, AFB200_MEM_HOST, NULL);
+    spectrogramObj_spectrogramBatch(s, x, dataLength, 1, mSpectArr, mPhaseArr, AFB200_MEM_HOST, NULL);
 }
 
 void spectrogramObj_xxcc(SpectrogramObj s, float *mDataArr1, int ccNum, CepstralRectifyType *rectifyType, float *mDataArr2) {
@@ -201,6 +217,7 @@ void spectrogramObj_free(SpectrogramObj s) {
     if (!s) return;
     if (s->ownBands) { free(s->freBandArr); free(s->binBandArr); }
     xxccObj_free(s->cc);
+    stftObj_free(s->stream);
     bftObj_free(s->core);
     free(s);
 }

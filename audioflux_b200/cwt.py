@@ -6,7 +6,7 @@ import ctypes as C
 
 import numpy as np
 
-from .base import Base, as_f32, np_ptr, split_batch
+from .base import Base, BandAxis, SampleAxis, as_f32, np_ptr, split_batch
 from .capi import opt_int, opt_float
 from .lib import check
 from .types import WaveletContinueType, SpectralFilterBankScaleType, enum_value
@@ -15,7 +15,7 @@ _DEFAULT_GAMMA_BETA = {0: (3, 20), 1: (6, 2), 2: (5, 0.6), 3: (4, 0), 4: (2, 2),
                        6: (5, 2), 7: (4, 0)}
 
 
-class CWT(Base):
+class CWT(BandAxis, SampleAxis, Base):
     def __init__(self, num=84, radix2_exp=12, samplate=32000, low_fre=None, high_fre=None,
                  bin_per_octave=12, wavelet_type=WaveletContinueType.MORSE,
                  scale_type=SpectralFilterBankScaleType.OCTAVE, gamma=None, beta=None,
@@ -76,6 +76,29 @@ class CWT(Base):
             re, im = self.cwt_planes(x2[i])
             outs.append((re + 1j * im)[::-1])
         return np.ascontiguousarray(np.stack(outs).reshape(*lead, self.num, N))
+
+    def ccwt(self, data_arr):
+        """Continuous CWT of long audio (reference: cwt.py:280-320): windows of 2**radix2_exp samples every half window, the
+        middle half of each kept (the first / last window also keep their outer quarter) -> [..., num, time].  With the
+        product library all windows go through ONE cwtObj_cwtBatch call (every (window, scale) item is one CTA-resident
+        transform for the default radix2_exp); any other library takes the reference's per-window loop."""
+        x = as_f32(data_arr)
+        N = self.fft_length
+        quarter, step = N // 4, N // 2
+        count = x.shape[-1] // step - 1
+        if count < 1:
+            raise ValueError(f"data length {x.shape[-1]} is shorter than one window of {N} samples")
+        lead = x.shape[:-1]
+        x2 = x.reshape(-1, x.shape[-1])
+        win = np.lib.stride_tricks.sliding_window_view(x2, N, axis=-1)[:, ::step][:, :count]      # [B, count, N]
+        if self._is_product and hasattr(self._lib, "cwtObj_cwtBatch"):
+            re, im = self.cwt_batch(np.ascontiguousarray(win).reshape(-1, N))
+            spec = (re + 1j * im).reshape(x2.shape[0], count, self.num, N)[:, :, ::-1]
+        else:
+            spec = self.cwt(np.ascontiguousarray(win))
+        parts = [spec[:, i, :, (0 if i == 0 else quarter):(N if i == count - 1 else 3 * quarter)] for i in range(count)]
+        out = np.concatenate(parts, axis=-1)
+        return np.ascontiguousarray(out.reshape(*lead, self.num, out.shape[-1]))
 
     def enable_det(self, flag=True):
         self._lib.cwtObj_enableDet(self._obj, int(flag))

@@ -6,13 +6,13 @@ import ctypes as C
 
 import numpy as np
 
-from .base import Base, as_f32, np_ptr, split_batch
+from .base import Base, BandAxis, SampleAxis, as_f32, np_ptr, split_batch
 from .capi import opt_int, opt_float
 from .lib import check
 from .types import (SpectralFilterBankScaleType, SpectralFilterBankStyleType, SpectralFilterBankNormalType, enum_value)
 
 
-class PWT(Base):
+class PWT(BandAxis, SampleAxis, Base):
     def __init__(self, num=84, radix2_exp=12, samplate=32000, low_fre=None, high_fre=None, bin_per_octave=12,
                  scale_type=SpectralFilterBankScaleType.OCTAVE, style_type=SpectralFilterBankStyleType.SLANEY,
                  normal_type=SpectralFilterBankNormalType.NONE, is_padding=True, _lib=None):

@@ -94,6 +94,15 @@ class STFT(Base):
     def cal_data_length(self, time_length):
         return self._lib.stftObj_calDataLength(self._obj, int(time_length))
 
+    def y_coords(self, samplate=32000):
+        """Bin frequencies 0 .. samplate//2 with a leading 0 (plot axis, stft.py of the reference)."""
+        return np.concatenate(([0.0], np.linspace(0, samplate // 2, self.fft_length // 2 + 1)))
+
+    def x_coords(self, data_length, samplate=32000):
+        if data_length < self.fft_length:
+            raise ValueError(f"radix2_exp={self.radix2_exp}(fft_length={self.fft_length}) is too large for data_length={data_length}")
+        return np.linspace(0, data_length / samplate, self.cal_time_length(data_length) + 1)
+
     def istft_planes(self, re, im, method_type=0):
         """Raw C layout: planes [T, fft_length] (full mirrored spectrum) -> data [(T-1)*slide + fft_length]."""
         re, im = as_f32(re), as_f32(im)

@@ -6,13 +6,13 @@ import ctypes as C
 
 import numpy as np
 
-from .base import Base, as_f32, np_ptr
+from .base import Base, BandAxis, SampleAxis, as_f32, np_ptr
 from .capi import opt_int, opt_float
 from .types import WaveletContinueType, SpectralFilterBankScaleType, enum_value
 from .cwt import _DEFAULT_GAMMA_BETA
 
 
-class WSST(Base):
+class WSST(BandAxis, SampleAxis, Base):
     def __init__(self, num=84, radix2_exp=12, samplate=32000, low_fre=None, high_fre=None, bin_per_octave=12,
                  wavelet_type=WaveletContinueType.MORLET, scale_type=SpectralFilterBankScaleType.OCTAVE,
                  gamma=None, beta=None, thresh=0.001, is_padding=True, _lib=None):

@@ -469,3 +469,31 @@ def test_istft_long_frames(torch_cuda, r, hop, wt, method):
     assert rel_max(y2[ok], want2[ok]) < 1e-4
     if method == 0 and n // hop >= 4:
         assert rel_max(y[n:-n], x[n:-n]) < 1e-4                              # round trip where the windows overlap fully
+
+
+# ---- streaming spectrogram front door (spectrogramObj_new(isContinue = 1), spectrogram_algorithm.c:655-664) ----
+@pytest.mark.parametrize("r,hop,scale,chunks", [(9, 128, "MEL", (1000, 37, 500, 3000, 129, 512)), (10, 1024, "BARK", (700, 700, 2048, 5000, 1)),
+                                                (11, 512, "MEL", (5000, 3000, 100, 2048)), (8, 300, "LINEAR", (100, 100, 100, 1000, 40, 2000))])
+def test_spectrogram_streaming_matches_reference_and_one_shot(cuda_device, ref_lib, r, hop, scale, chunks):
+    """chunk by chunk through spectrogramObj_spectrogram(isContinue = 1): the same frame counts and values as the reference
+    build fed the same chunks, and all frames together equal the one-shot transform (to rounding: a chunk may take the general path where the whole clip takes the fused one)"""
+    S = af.SpectralFilterBankScaleType
+    kw = dict(radix2_exp=r, samplate=16000, slide_length=hop, filter_bank_type=getattr(S, scale))
+    num = 40 if scale != "LINEAR" else (1 << r) // 2 + 1
+    x = noise(78, sum(chunks))
+    s = af.Spectrogram(num, is_continue=True, **kw)
+    q = af.Spectrogram(num, is_continue=True, _lib=ref_lib, **kw)
+    got, pos = [], 0
+    for c in chunks:
+        piece = x[pos:pos + c]
+        pos += c
+        assert s.cal_time_length(c) == q.cal_time_length(c)
+        a, b = s.spectrogram_planes(piece), q.spectrogram_planes(piece)
+        assert a.shape == b.shape
+        if a.shape[0]:
+            assert rel_max(a, b) < 1e-4
+            got.append(a)
+    whole = af.Spectrogram(num, **kw).spectrogram_planes(x)
+    allf = np.concatenate(got)
+    assert allf.shape[0] == whole.shape[0] or hop > (1 << r)
+    assert rel_max(allf, whole[:allf.shape[0]]) < 1e-5

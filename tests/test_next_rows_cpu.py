@@ -141,7 +141,9 @@ def test_spectrogram_new_status_codes(product_lib):
     assert product_lib.spectrogramObj_new(C.byref(obj), 12, *a) == -2                    # Chroma family: loud
     assert b"not supported" in product_lib.afb200_lastError()
     a = list(none); a[7] = opt_int(1)
-    assert product_lib.spectrogramObj_new(C.byref(obj), 12, *a) == -2                    # isContinue
+    assert product_lib.spectrogramObj_new(C.byref(obj), 12, *a) == 0                     # isContinue: streaming front door
+    assert product_lib.spectrogramObj_calTimeLength(obj, 4096) == 1 and product_lib.spectrogramObj_calTimeLength(obj, 100) == 0
+    product_lib.spectrogramObj_free(obj)
     a = list(none); a[9] = opt_int(5)
     assert product_lib.spectrogramObj_new(C.byref(obj), 240, *a) == -1                   # Octave overflow
     for ctor, args in (("spectrogramObj_newMel", (128, 48000, 11)), ("spectrogramObj_newBark", (64, 32000, 10)),
