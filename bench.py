@@ -525,6 +525,11 @@ def bench_cwt_c4(dev, peaks, args, cores):
     e2e_s_per_clip = (time.perf_counter() - t0) / (n_chunks * chunk)
     bytes_clip = 4 * CWT_SAMPLES + 2 * 4 * CWT_NUM * N
     achieved = B * bytes_clip / (ms_step * 1e-3) / 1e9
+    # DRAM bytes of the dominant kernel (k_cwt_fused_w) from the committed ncu capture: tools/cwt_prof.py transforms 4 clips per
+    # launch, the bench chunk-size clips -- the kernel walks (clip, scale) items in groups of 4, so its traffic scales with the clips
+    cwt_summary, cwt_capture_clips = "r2_final_cwt_ncu.txt", 4
+    t4 = ncu_traffic(cwt_summary)
+    cwt_traffic = int(t4 / cwt_capture_clips * chunk) if t4 else None
     out = {"metric": "cwt_clips_per_s", "value": B / (ms_step * 1e-3), "unit": "clips/s", "ms_per_step": ms_step, "per_step_ms": ms,
            "config": {"workload": f"BASELINE config 4: batch={B} x 10 s 48 kHz clips (480000 samples zero-padded to 2^19), CWT morlet {CWT_NUM} scales (octave)",
                       "chunk_clips": chunk, "output": "two planes of 352 MB per clip; each chunk's planes overwrite one device buffer",
@@ -533,7 +538,9 @@ def bench_cwt_c4(dev, peaks, args, cores):
                    "sample": f"{n_chunks} of the {B // chunk} chunks of a step, each through cwtObj_cwtBatch with HOST pointers"},
            "gpu_launches": int(launches),
            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": achieved / peaks["hbm_gbs"],
-                        "traffic": None, "algorithmic_bytes_per_step": B * bytes_clip}}
+                        "traffic": cwt_traffic, "traffic_source": f"profiles/{cwt_summary} ({cwt_capture_clips} clips per launch) scaled to the bench's {chunk}-clip launches" if cwt_traffic else None,
+                        "kernel": "k_cwt_fused_w", "algorithmic_bytes_per_launch": chunk * bytes_clip,
+                        "algorithmic_bytes_per_step": B * bytes_clip}}
     del x, re, im
     if not args.no_cpu_baseline:
         workers = max(1, min(cores, 32))                            # 0.6 GB per worker (bank table + planes at N = 2^19)
@@ -757,8 +764,11 @@ def run_b200_arm(args):
         cpu = cpu_reference_rate(per_cpu, cores)
     kernel_name = "k_mfcc_fused<5,0>" if os.environ.get("AFB200_MFCC_KERNEL") == "v1" else "k_mfcc_fused2<5>"
     summary = os.environ.get("AFB200_NCU_SUMMARY", "r1_final_mfcc_fused_ncu_summary.txt" if "fused<" in kernel_name
-                             else "r2_mfcc_fused2_ncu_summary.txt")
+                             else "r2_final_mfcc_fused2_ncu_summary.txt")
     traffic = ncu_traffic(summary) if (B == 1024 and L == 240000) else None
+    if traffic is None and "fused2" in kernel_name and B == 1024 and L == 240000:
+        summary = "r2_mfcc_fused2_ncu_summary.txt"                   # the capture at the start of the round
+        traffic = ncu_traffic(summary)
     line = {
         "metric": "mfcc_frames_per_s", "value": value, "unit": "frames/s", "n_gpus": world, "steps": args.steps,
         "warmup": max(args.warmup, 3), "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
