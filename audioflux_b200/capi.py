@@ -120,6 +120,7 @@ REFERENCE_API = {
     "spectrogramObj_spectrogram": (None, [vp, vp, C.c_int, vp, vp]),
     "spectrogramObj_xxcc": (None, [vp, vp, C.c_int, c_int_p, vp]),
     "spectrogramObj_mfcc": (None, [vp, vp, C.c_int, vp]),
+    "spectrogramObj_deconv": (None, [vp, vp, vp, vp]),
     "spectrogramObj_bfcc": (None, [vp, vp, C.c_int, vp]),
     "spectrogramObj_gtcc": (None, [vp, vp, C.c_int, vp]),
     "spectrogramObj_lfcc": (None, [vp, vp, C.c_int, vp]),
@@ -158,6 +159,7 @@ EXTENSION_API = {
                                             vp, vp, vp, C.c_int, vp]),
     "spectrogramObj_spectrogramBatch": (C.c_int, [vp, vp, C.c_int, C.c_int, vp, vp, C.c_int, vp]),
     "spectrogramObj_mfccBatch": (C.c_int, [vp, vp, C.c_int, C.c_int, C.c_int, C.c_int, vp, C.c_int, vp]),
+    "spectrogramObj_deconvBatch": (C.c_int, [vp, vp, C.c_int, vp, vp, C.c_int, vp]),
     "cwtObj_cwtBatch": (C.c_int, [vp, vp, C.c_int, vp, vp, C.c_int, vp]),
     "cwtObj_cwtDetBatch": (C.c_int, [vp, vp, C.c_int, vp, vp, C.c_int, vp]),
     "cwtObj_getFilterBankArr": (C.c_int, [vp, vp]),

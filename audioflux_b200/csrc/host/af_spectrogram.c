@@ -20,6 +20,8 @@ struct OpaqueSpectrogram {
     float *freBandArr;      /* Linear: own arrays (grid of __vlinspace); else borrowed from the core */
     int *binBandArr;
     int ownBands;
+    void *cuStream;         /* deconv with host pointers: staging buffers and the stream they are filled on */
+    AfDevBuf dPostA, dPostB, dPostOut;
     STFTObj stream;         /* isContinue = 1: an STFT object that only keeps the tail between calls (stft_algorithm.c:474-599) */
 };
 
@@ -213,8 +215,37 @@ void spectrogramObj_xxccStandard(SpectrogramObj s, float *a, int *d, CepstralEne
     (void)s; (void)a; (void)d; (void)e; (void)r; (void)b;          /* empty in the reference too (:1533-1537) */
 }
 
+/* ---- cepstral deconvolution of the band spectra (spectrogram_algorithm.c:1545-1612): the same per-frame transform
+ * as cqtObj_deconv (rows zero-padded to ceilPow2(2 num); timbre = Re IFFT(|FFT(row)|), pitch = Re IFFT(FFT(row) /
+ * max(|FFT(row)|, 1e-16))), so the same kernel (kernels/deconv.cu) ---- */
+int spectrogramObj_deconvBatch(SpectrogramObj s, const float *in, int rows, float *timbre, float *pitch, int memKind, void *stream) {
+    if (!s || !in || !timbre || !pitch || rows < 0) return af_fail(AF_ERR_ARG, "spectrogramObj_deconvBatch: bad argument");
+    af_clear_error();
+    int rc = af_device_ready();
+    if (rc) return rc;
+    if (rows == 0) return AF_OK;
+    if (memKind == AFB200_MEM_DEVICE) return af_launch_cq_deconv(in, rows, s->num, 1, 0, 12, timbre, pitch, stream);
+    if (!s->cuStream && (rc = af_stream_create(&s->cuStream))) return rc;
+    void *st = stream ? stream : s->cuStream;
+    const size_t bytes = sizeof(float) * (size_t)rows * s->num;
+    if ((rc = af_devbuf_reserve(&s->dPostA, bytes)) || (rc = af_devbuf_reserve(&s->dPostOut, bytes)) ||
+        (rc = af_devbuf_reserve(&s->dPostB, bytes))) return rc;
+    if ((rc = af_memcpy_h2d(s->dPostA.ptr, in, bytes, st))) return rc;
+    if ((rc = af_launch_cq_deconv((const float *)s->dPostA.ptr, rows, s->num, 1, 0, 12, (float *)s->dPostOut.ptr, (float *)s->dPostB.ptr, st))) return rc;
+    if ((rc = af_memcpy_d2h(timbre, s->dPostOut.ptr, bytes, st)) || (rc = af_memcpy_d2h(pitch, s->dPostB.ptr, bytes, st))) return rc;
+    return af_stream_sync(st);
+}
+
+/* mDataArr1: timeLength x num of the LAST spectrogram call -> mDataArr2 (timbre / tone), mDataArr3 (pitch) */
+void spectrogramObj_deconv(SpectrogramObj s, float *mDataArr1, float *mDataArr2, float *mDataArr3) {
+    if (!s || !mDataArr1 || !mDataArr2 || !mDataArr3 || s->timeLength <= 0) return;
+    spectrogramObj_deconvBatch(s, mDataArr1, s->timeLength, mDataArr2, mDataArr3, AFB200_MEM_HOST, NULL);
+}
+
 void spectrogramObj_free(SpectrogramObj s) {
     if (!s) return;
+    af_devbuf_free(&s->dPostA); af_devbuf_free(&s->dPostB); af_devbuf_free(&s->dPostOut);
+    af_stream_destroy(s->cuStream);
     if (s->ownBands) { free(s->freBandArr); free(s->binBandArr); }
     xxccObj_free(s->cc);
     stftObj_free(s->stream);

@@ -158,6 +158,26 @@ class Spectrogram(Base):
             raise ValueError("gtcc needs the GAMMATONE style")
         return self._cc("spectrogramObj_gtcc", m_data_arr, cc_num)
 
+    def deconv(self, m_data_arr):
+        """[num, T] of the LAST spectrogram call -> (tone, pitch), each [num, T] (spectrogram.py:328-362 of the reference)."""
+        m = as_f32(m_data_arr)
+        if m.ndim != 2:
+            raise ValueError("deconv works on the [num, T] result of the preceding spectrogram() call")
+        mt = np.ascontiguousarray(m.T)
+        tone, pitch = np.zeros_like(mt), np.zeros_like(mt)
+        self._lib.spectrogramObj_deconv(self._obj, np_ptr(mt), np_ptr(tone), np_ptr(pitch))
+        return np.ascontiguousarray(tone.T), np.ascontiguousarray(pitch.T)
+
+    def deconv_batch(self, m_tn):
+        """Additive: [..., T, num] (numpy host | torch cuda, time-major as spectrogram_batch returns it) -> (tone, pitch)."""
+        fn = self._require_ext("spectrogramObj_deconvBatch")
+        x2, lead, kind, ptr, stream, alloc = split_batch(m_tn)
+        if x2.shape[-1] != self.num:
+            raise ValueError(f"last dimension must be num={self.num}")
+        tone, pitch = alloc(*x2.shape), alloc(*x2.shape)
+        check(fn(self._obj, ptr(x2), x2.shape[0], ptr(tone), ptr(pitch), kind, stream), "spectrogramObj_deconvBatch")
+        return tone.reshape(*lead, self.num), pitch.reshape(*lead, self.num)
+
     def __del__(self):
         if getattr(self, "_is_created", False):
             self._lib.spectrogramObj_free(self._obj)

@@ -59,6 +59,9 @@ int spectrogramObj_spectrogramBatch(SpectrogramObj spectrogramObj, const float *
                                     float *spect, float *phase, int memKind, void *stream);
 int spectrogramObj_mfccBatch(SpectrogramObj spectrogramObj, const float *data, int dataLength, int batch, int ccNum,
                              int rectifyType, float *out, int memKind, void *stream);
+/* spectrogramObj_deconv for any number of rows (frames of any number of clips): in, timbre, pitch rows x bandNum */
+int spectrogramObj_deconvBatch(SpectrogramObj spectrogramObj, const float *in, int rows, float *timbre, float *pitch,
+                               int memKind, void *stream);
 /* MFCC + all-gather as ONE kernel (multi-GPU, one process per GPU).  Device pointers only: `out` is this GPU's
  * destination, peerOut[0..nPeer) (nPeer <= 15) the same logical location inside the other GPUs' gathered buffers,
  * mapped with afb200_ipcOpenHandle.  The kernel epilogue stores every finished tile to all of them (NVLink P2P

@@ -2,8 +2,8 @@
  * benchmark times, benchmark/run_audioflux.py:14-29).  Replaces the part of
  * /root/reference/src/spectrogram_algorithm.h:40-119 that lies on the time-frequency path:
  * construction, spectrogram (STFT -> power/magnitude -> Linear slice or mel/bark/erb/... bank) and the cepstral
- * calls.  Chroma / Deep scale types, the spectral-descriptor functions (flatness, centroid, ...) and deconv are
- * outside the path: `_new` rejects those scale types with -2, the functions are not exported. */
+ * calls and the cepstral deconvolution.  Chroma / Deep scale types and the spectral-descriptor functions (flatness,
+ * centroid, ...) are outside the path: `_new` rejects those scale types with -2, the functions are not exported. */
 #ifndef AFB200_SPECTROGRAM_H
 #define AFB200_SPECTROGRAM_H
 #include "afb200_types.h"
@@ -16,7 +16,8 @@ typedef struct OpaqueSpectrogram *SpectrogramObj;
 /* spectrogram_algorithm.c:326-583.  Defaults: samplate 32000, lowFre 0 (Octave/Log: C1..B7), highFre samplate/2,
  * binPerOctave 12, radix2Exp 12, hann, slideLength fftLength/4, power, Linear, Slaney, no normalisation.
  * Linear: num is ignored and becomes round(highFre/det)-round(lowFre/det)+1 (spectrogramObj_getBandNum).
- * Returns 0; -100 bad radix2Exp; -1 bad num / Octave overflow; -2 unsupported (Chroma/Deep scales, isContinue). */
+ * Returns 0; -100 bad radix2Exp; -1 bad num / Octave overflow; -2 unsupported (Chroma/Deep scales).
+ * isContinue = 1: samples that did not complete a frame wait for the next spectrogramObj_spectrogram call (:655-664). */
 int spectrogramObj_new(SpectrogramObj *spectrogramObj, int num, int *samplate, float *lowFre, float *highFre,
                        int *binPerOctave, int *radix2Exp, WindowType *windowType, int *slideLength,
                        int *isContinue, SpectralDataType *dataType,
@@ -54,6 +55,10 @@ void spectrogramObj_mfccStandard(SpectrogramObj spectrogramObj, float *mDataArr1
                                  CepstralEnergyType *energyType, CepstralRectifyType *rectifyType, float *mDataArr2);
 void spectrogramObj_xxccStandard(SpectrogramObj spectrogramObj, float *mDataArr1, int *deltaWindowLength,
                                  CepstralEnergyType *energyType, CepstralRectifyType *rectifyType, float *mDataArr2);
+/* :1545-1612.  mDataArr1: timeLength x bandNum of the last spectrogram call -> mDataArr2 (timbre / tone) and mDataArr3
+ * (pitch), same shape: per frame, zero-padded to ceilPow2(2 bandNum), Re IFFT(|FFT|) and Re IFFT(FFT / max(|FFT|, 1e-16)).
+ * bandNum <= 2048 (one CTA-resident transform per frame); larger band counts are refused on stderr. */
+void spectrogramObj_deconv(SpectrogramObj spectrogramObj, float *mDataArr1, float *mDataArr2, float *mDataArr3);
 void spectrogramObj_free(SpectrogramObj spectrogramObj);                                    /* :3029-3169 */
 
 #ifdef __cplusplus

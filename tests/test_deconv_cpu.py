@@ -25,3 +25,17 @@ def test_oracle_deconv_cqhc_vs_reference_build(ref_lib, num, bpo, hc):
     assert rel_max(o_tone, tone) < 1e-5 and rel_max(o_pitch, pitch) < 1e-4
     got = c.cqhc_planes(m, hc)
     assert rel_max(O.cqhc(m, hc, bpo), got) < 1e-5
+
+
+@pytest.mark.parametrize("num,scale,r", [(128, "MEL", 11), (40, "BARK", 10), (257, "LINEAR", 9)])
+def test_oracle_deconv_vs_reference_spectrogram_deconv(ref_lib, num, scale, r):
+    """spectrogramObj_deconv (spectrogram_algorithm.c:1545-1612) is the same per-frame transform as cqtObj_deconv"""
+    import audioflux_b200 as af
+    x = (0.1 * np.random.default_rng(2).standard_normal(12000)).astype(np.float32)
+    s = af.Spectrogram(num, radix2_exp=r, samplate=16000, filter_bank_type=getattr(af.SpectralFilterBankScaleType, scale), _lib=ref_lib)
+    spec = s.spectrogram(x)                           # [num, T]; sets the object's timeLength
+    assert spec.shape[0] == num
+    tone, pitch = s.deconv(spec)
+    o_tone, o_pitch = O.cq_deconv(np.ascontiguousarray(spec.T))
+    assert tone.shape == spec.shape
+    assert rel_max(o_tone, tone.T) < 1e-5 and rel_max(o_pitch, pitch.T) < 1e-4

@@ -43,3 +43,27 @@ def test_deconv_batch_any_rows_host_and_device(cuda_device):
     torch.cuda.synchronize()
     assert np.array_equal(td.cpu().numpy(), tone) and np.array_equal(pd.cpu().numpy(), pitch)
     assert rel_max(hd.cpu().numpy().reshape(-1, 20), O.cqhc(m.reshape(-1, 84), 20)) < 1e-4
+
+
+@pytest.mark.parametrize("num,scale,r", [(128, "MEL", 11), (40, "BARK", 10), (257, "LINEAR", 9)])
+def test_spectrogram_deconv_vs_oracle_and_reference(cuda_device, ref_lib, num, scale, r):
+    """spectrogramObj_deconv / spectrogramObj_deconvBatch: same kernel as cqtObj_deconv, band count of the spectrogram"""
+    import torch
+    import audioflux_b200 as af
+    x = (0.1 * np.random.default_rng(3).standard_normal(12000)).astype(np.float32)
+    kw = dict(radix2_exp=r, samplate=16000, filter_bank_type=getattr(af.SpectralFilterBankScaleType, scale))
+    s, q = af.Spectrogram(num, **kw), af.Spectrogram(num, _lib=ref_lib, **kw)
+    spec, spec_r = s.spectrogram(x), q.spectrogram(x)
+    assert rel_max(spec, spec_r) < 1e-4
+    tone, pitch = s.deconv(spec_r)                     # same input for all three
+    r_tone, r_pitch = q.deconv(spec_r)
+    o_tone, o_pitch = O.cq_deconv(np.ascontiguousarray(spec_r.T))
+    assert tone.shape == spec_r.shape
+    assert rel_max(tone.T, o_tone) < 1e-4 and rel_max(pitch.T, o_pitch) < 1e-4
+    assert rel_max(tone, r_tone) < 1e-4 and rel_max(pitch, r_pitch) < 1e-4
+    m = np.ascontiguousarray(np.stack([spec_r.T, 2.0 * spec_r.T]))            # [2, T, num]
+    bt, bp = s.deconv_batch(m)
+    assert np.array_equal(bt[0], tone.T) and rel_max(bt[1], 2.0 * tone.T) < 1e-5
+    dt, dp = s.deconv_batch(torch.from_numpy(m).cuda())
+    torch.cuda.synchronize()
+    assert np.array_equal(dt.cpu().numpy(), bt) and np.array_equal(dp.cpu().numpy(), bp)
