@@ -7,7 +7,7 @@ import ctypes as C
 
 import numpy as np
 
-from .base import Base, as_f32, np_ptr, split_batch, swap_last2
+from .base import Base, BandAxis, as_f32, np_ptr, split_batch, swap_last2
 from .capi import opt_int, opt_float
 from .lib import check
 from .types import (WindowType, SpectralFilterBankScaleType, SpectralFilterBankStyleType,
@@ -16,7 +16,7 @@ from .types import (WindowType, SpectralFilterBankScaleType, SpectralFilterBankS
 _LOG_LIKE = (5, 6)
 
 
-class Spectrogram(Base):
+class Spectrogram(BandAxis, Base):
     def __init__(self, num=0, samplate=32000, low_fre=None, high_fre=None, bin_per_octave=12, radix2_exp=12,
                  window_type=None, slide_length=None, data_type=SpectralDataType.POWER,
                  filter_bank_type=SpectralFilterBankScaleType.LINEAR,
@@ -157,6 +157,12 @@ class Spectrogram(Base):
         if enum_value(self.style_type) != 2:
             raise ValueError("gtcc needs the GAMMATONE style")
         return self._cc("spectrogramObj_gtcc", m_data_arr, cc_num)
+
+    def x_coords(self, data_length):
+        """Frame start times in seconds: slide_length / samplate apart (plot axis of the reference's spectrogram classes)."""
+        if data_length < self.fft_length:
+            raise ValueError(f"radix2_exp={self.radix2_exp}(fft_length={self.fft_length}) is too large for data_length={data_length}")
+        return np.arange(self.cal_time_length(data_length) + 1) * (self.slide_length / self.samplate)
 
     def deconv(self, m_data_arr):
         """[num, T] of the LAST spectrogram call -> (tone, pitch), each [num, T] (spectrogram.py:328-362 of the reference)."""

@@ -34,6 +34,9 @@ def test_axis_helpers_match_the_reference_package(raf, ref_lib):
     for mine, ref, xargs in pairs:
         np.testing.assert_allclose(mine.y_coords(), ref.y_coords(), rtol=1e-6)
         np.testing.assert_allclose(mine.x_coords(*xargs), ref.x_coords(*xargs), rtol=1e-12)
+    ms, rs = af.MelSpectrogram(64, 16000, radix2_exp=10, _lib=ref_lib), raf.MelSpectrogram(num=64, samplate=16000, radix2_exp=10)
+    np.testing.assert_allclose(ms.y_coords(), rs.y_coords(), rtol=1e-6)
+    np.testing.assert_allclose(ms.x_coords(5000), rs.x_coords(5000), rtol=1e-12)
     s, q = af.STFT(10, _lib=ref_lib), raf.STFT(radix2_exp=10)
     np.testing.assert_allclose(s.y_coords(16000), q.y_coords(16000))
     np.testing.assert_allclose(s.x_coords(5000, 16000), q.x_coords(5000, 16000))
