@@ -248,6 +248,7 @@ typedef struct {
 } AfBftSpec;
 /* streaming bookkeeping of an STFT object (af_stft.c): tail of the earlier calls ++ data -> *cur / *curLength; 0 = no frame yet */
 int af_stft_continue_assemble(STFTObj s, const float *data, int dataLength, const float **cur, int *curLength);
+int af_filterbank_clipped(void);   /* non-zero weights the last af_auditory_filterbank call (this thread) dropped above the Nyquist bin */
 int af_bft_create(const AfBftSpec *spec, BFTObj *out);      /* 0, -1 (memory), -2 (unsupported bank) */
 int af_bft_phase(BFTObj b, const float *data, int dataLength, int batch, int lowIndex, int count, float *phase,
                  int memKind, void *stream);

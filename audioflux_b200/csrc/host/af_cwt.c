@@ -50,6 +50,13 @@ int cwtObj_new(CWTObj *out, int num, int radix2Exp, int *samplate, float *lowFre
     if (num < 2 || num > N / 2 + 1) { printf("num is error!\n"); return -1; }
     AfWavelet w;
     if (af_wavelet_setup(&w, waveletType ? (int)*waveletType : WaveletContinue_Morse, gamma, beta)) return -1;
+    if (w.waveletType == WaveletContinue_Bump && w.beta > w.gamma) {
+        /* psi_hat(s w) = e^{1 - 1/(1 - ((s w - gamma)/beta)^2)} on |s w - gamma| < beta: with beta > gamma that interval
+         * reaches w <= 0, and the reference (which evaluates the bump on its negative-frequency bins too,
+         * cwt_filterBank.c:428-462) keeps those bins.  Every kernel of this library is one-sided. */
+        af_fail(AF_ERR_UNSUPPORTED, "cwtObj_new: bump wavelet with beta %g > gamma %g has support on negative frequencies", w.beta, w.gamma);
+        return -2;
+    }
     int pad = 0;
     if (isPad && *isPad) pad = N <= 1e5 ? N / 2 : (int)ceilf(log2f((float)N));
     const int fftLength = N + 2 * pad;
@@ -262,9 +269,24 @@ int pwtObj_new(PWTObj *out, int num, int radix2Exp, int *samplate, float *lowFre
     c->binBandArr = (int *)calloc((size_t)num + 2, sizeof(int));
     c->scaleArr = (float *)calloc((size_t)num, sizeof(float));
     if (!c->bankHost || !c->freBandArr || !c->binBandArr || !c->scaleArr) { pwtObj_free(p); return -1; }
-    if (af_auditory_filterbank(num, fftLength, sr, scale, styleType ? (int)*styleType : SpectralFilterBankStyle_Slaney,
+    const int style = styleType ? (int)*styleType : SpectralFilterBankStyle_Slaney;
+    if (style == SpectralFilterBankStyle_Gammatone) {
+        /* the reference writes the gammatone rows of its pseudo bank fftLength/2+1 apart into rows that are fftLength long
+         * (auditory_filterBank.c:541-549 with isPseudo = 1): the rows it then transforms with overlap one another */
+        af_fail(AF_ERR_UNSUPPORTED, "pwtObj_new: the Gammatone style is not supported (the reference's pseudo bank rows overlap)");
+        pwtObj_free(p); return -2;
+    }
+    if (af_auditory_filterbank(num, fftLength, sr, scale, style,
                                normalType ? (int)*normalType : SpectralFilterBankNormal_None, c->lowFre, c->highFre, bpo,
                                c->bankHost, c->freBandArr, c->binBandArr)) { pwtObj_free(p); return -2; }
+    if (af_filterbank_clipped()) {
+        /* band edges beyond samplate / 2 (Log / Linspace scales with highFre at Nyquist): the reference's pseudo bank keeps
+         * those weights on the negative-frequency bins; this library's transform is one-sided.  (Linear scale from bin 0:
+         * the reference writes the first weight in front of its bank buffer.) */
+        af_fail(AF_ERR_UNSUPPORTED, "pwtObj_new: %d filter weights fall outside bins [0, fftLength/2] (band edges beyond the "
+                "Nyquist frequency or below bin 0); move lowFre / highFre inwards", af_filterbank_clipped());
+        pwtObj_free(p); return -2;
+    }
     *out = p;
     return 0;
 }

@@ -140,8 +140,15 @@ void af_band_edges(int num, int fftLength, int samplate, float lowFre, float hig
     }
 }
 
+/* weights that fall above the Nyquist bin (band edges beyond samplate / 2: Log / Linspace scales with highFre at Nyquist)
+ * or below bin 0 (Linear scale starting at bin 0) have no place in the one-sided bank; they are counted so that callers whose reference counterpart keeps them -- the
+ * pseudo banks of pwtObj_new span all fftLength bins -- can refuse instead of dropping them silently */
+static __thread int g_clipped;
+int af_filterbank_clipped(void) { return g_clipped; }
+
 static void put(float *bank, int width, int row, int col, float v) {
     if (col >= 0 && col < width) bank[(size_t)row * width + col] = v;
+    else if (v != 0.0f) g_clipped++;
 }
 
 static void window_half_fill(float *bank, int width, int row, int style, int from, int to, int rising) {
@@ -242,6 +249,7 @@ int af_auditory_filterbank(int num, int fftLength, int samplate, int scale, int 
                            float lowFre, float highFre, int bpo, float *bank, float *freBandArr,
                            int *binBandArr) {
     if (num < 1 || fftLength < 2 || !bank) return AF_ERR_ARG;
+    g_clipped = 0;
     if (style == SpectralFilterBankStyle_Gammatone) {
         float *cfre = (float *)calloc((size_t)num + 2, sizeof(float));
         int *cbin = (int *)calloc((size_t)num + 2, sizeof(int));

@@ -249,6 +249,39 @@ __global__ void k_cqt_octave(OctParams p) {
     }
 }
 
+// Last resort for geometries whose polyphase tile does not fit shared memory at all (hops in the thousands: long kernels
+// -- large factor, many bins per octave -- over few octaves): one warp per (frame, bin), the lanes stride over the taps
+// straight from global memory (coalesced signal and kernel reads), warp-shuffle reduction.  Same sums as k_cqt_octave in
+// another order (float32, <= 2^14 terms in 32 partial sums).
+__global__ void __launch_bounds__(256) k_cqt_octave_direct(OctParams p) {
+    const int lane = threadIdx.x & 31;
+    const long long w = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);     // (frame, bin) of this warp
+    const int clip = blockIdx.y;
+    if (w >= (long long)p.T * p.bpo) return;
+    const int t = (int)(w / p.bpo), j = (int)(w - (long long)t * p.bpo);
+    const float *sig = p.sig + (long long)clip * p.sigStride;
+    const long long m0 = (long long)t * p.hop - p.padLeft;
+    const float2 *kap = p.kappa + (size_t)j * p.N;
+    float ar = 0.0f, ai = 0.0f;
+    for (int n = lane; n < p.N; n += 32) {
+        const long long m = m0 + n;
+        const float x = (m >= 0 && m < p.validLength) ? sig[m] : 0.0f;
+        const float2 c = kap[n];
+        ar = fmaf(x, c.x, ar);
+        ai = fmaf(x, c.y, ai);
+    }
+    for (int o = 16; o; o >>= 1) {
+        ar += __shfl_xor_sync(0xffffffffu, ar, o);
+        ai += __shfl_xor_sync(0xffffffffu, ai, o);
+    }
+    if (lane == 0) {
+        const float sc = p.scale[j];
+        const long long o = (long long)clip * p.outStride + (long long)t * p.num + p.colOff + j;
+        p.outRe[o] = ar * sc;
+        p.outIm[o] = ai * sc;
+    }
+}
+
 
 // ---- tensor-core octave kernel ---------------------------------------------------------------------------------
 // One octave is a GEMM  out[T x 24] = A[T x N] . B[N x 24]  with a Hankel A operand, A[t][n] = xpad[t*hop + n]
@@ -425,7 +458,15 @@ extern "C" int af_launch_cqt_octave(const float *sig, int sigLength, int sigStri
             if (bytes <= (size_t)(pass == 0 ? 100 : 200) * 1024) { TT = tt; p.rowLen = rowLen; smem = bytes; break; }
         }
     }
-    if (TT == 0) return af_fail(AF_ERR_UNSUPPORTED, "cqt octave: fftLength %d with hop %d exceeds shared memory", fftLength, hop);
+    if (TT == 0) {
+        // no tile of the polyphase kernel fits (hop x (8 + fftLength / hop) floats > 150 KB): warp-per-output kernel
+        p.TT = 0; p.rowLen = 0; p.segs = 1;
+        const long long outs = (long long)timeLength * bpo;
+        const dim3 g((unsigned)((outs + 7) / 8), (unsigned)batch);
+        k_cqt_octave_direct<<<g, 256, 0, (cudaStream_t)stream>>>(p);
+        AF_LAUNCH_CHECK("k_cqt_octave_direct");
+        return AF_OK;
+    }
     p.TT = TT;
     // enough threads per CTA: split the taps of a frame over up to rowsA segments until the CTA has >= 512 threads
     p.segs = 1;

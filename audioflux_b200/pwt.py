@@ -106,7 +106,9 @@ class PWT(BandAxis, SampleAxis, Base):
 
     def get_filter_bank_arr(self):
         fn = self._require_ext("pwtObj_getFilterBankArr")
-        out = np.zeros((self.num, self.fft_length), np.float32)
+        # rows of the TRANSFORM length: 2 * fft_length when the object pads (is_padding, data lengths up to 1e5)
+        width = 2 * self.fft_length if self.is_padding else self.fft_length
+        out = np.zeros((self.num, width), np.float32)
         check(fn(self._obj, np_ptr(out)), "pwtObj_getFilterBankArr")
         return out
 

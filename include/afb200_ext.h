@@ -101,11 +101,11 @@ int cwtObj_cwtBatch(CWTObj cwtObj, const float *data, int batch, float *mReal4, 
 /* derivative transform (after cwtObj_enableDet); data may be NULL with batch = 1 to reuse the last spectrum */
 int cwtObj_cwtDetBatch(CWTObj cwtObj, const float *data, int batch, float *mReal4, float *mImag4,
                        int memKind, void *stream);
-int cwtObj_getFilterBankArr(CWTObj cwtObj, float *bank /* num x fftLength host */);
+int cwtObj_getFilterBankArr(CWTObj cwtObj, float *bank /* num x fftLength host; fftLength = the TRANSFORM length: 2^radix2Exp, twice that with isPad */);
 /* PWT: data batch x 2^radix2Exp -> planes batch x num x 2^radix2Exp */
 int pwtObj_pwtBatch(PWTObj pwtObj, const float *data, int batch, float *mReal3, float *mImag3, int memKind, void *stream);
 int pwtObj_pwtDetBatch(PWTObj pwtObj, const float *data, int batch, float *mReal3, float *mImag3, int memKind, void *stream);
-int pwtObj_getFilterBankArr(PWTObj pwtObj, float *bank /* num x fftLength host */);
+int pwtObj_getFilterBankArr(PWTObj pwtObj, float *bank /* num x fftLength host; fftLength as for cwtObj_getFilterBankArr */);
 
 /* setup-time table builders, exported for parity tests against the reference's
  * window_calFFTWindow (src/dsp/flux_window.c:890-940), auditory_filterBank

@@ -13,6 +13,7 @@ from audioflux_b200 import capi
 _HERE = os.path.dirname(os.path.realpath(__file__))
 REF_PATH = os.path.join(_HERE, "_ref", "libaudioflux_ref.so")
 REF_OMP_PATH = os.path.join(_HERE, "_ref", "libaudioflux_ref_omp.so")
+REF_ASAN_PATH = os.path.join(_HERE, "_ref", "libaudioflux_ref_asan.so")     # needs LD_PRELOAD=libasan in the loading process
 
 _cache = {}
 
@@ -21,8 +22,8 @@ def available(omp: bool = False) -> bool:
     return os.path.exists(REF_OMP_PATH if omp else REF_PATH)
 
 
-def get_ref_lib(omp: bool = False):
-    path = REF_OMP_PATH if omp else REF_PATH
+def get_ref_lib(omp: bool = False, asan: bool = False):
+    path = REF_ASAN_PATH if asan else REF_OMP_PATH if omp else REF_PATH
     if path not in _cache:
         if not os.path.exists(path):
             raise FileNotFoundError(f"{path} missing: run `make -C oracle` where /root/reference exists")

@@ -5,9 +5,12 @@ forked child because the reference corrupts its heap on some legal parameter set
 Deliberate deviations, asserted as such:
   * cqtObj_newWith returns -1 where slideLength cannot be halved octaveNum - 1 times (the reference builds the object
     and then frames with hop 0 inside cqtObj_cqt);
-  * pwtObj_new with the Linear scale and the Gammatone style: the reference's `__auditory_linearFilterBank`
-    (auditory_filterBank.c:339-365) decrements binBandArr[1..num] of an array that has only num entries in this layout
-    (heap overflow), so its bin array comes back as [b0, b1-1, b2-1, ...]; the product returns b."""
+  * pwtObj_new refuses (-2, message) the Gammatone style -- the reference writes the rows of that pseudo bank
+    fftLength/2+1 apart into rows that are fftLength long, and with the Linear scale its `__auditory_linearFilterBank`
+    (auditory_filterBank.c:339-365) also overruns the band array -- and banks whose edges lie beyond samplate/2 (Log /
+    Linspace scales with highFre at Nyquist: the reference keeps those weights on negative-frequency bins) or below bin 0
+    (Linear scale from bin 0: the reference writes in front of its buffer);
+  * cwtObj_new refuses (-2) a bump wavelet with beta > gamma (support on negative frequencies, same reason)."""
 import ctypes as C
 import os
 import pickle
@@ -163,16 +166,36 @@ def test_constructors_agree_with_the_reference_build(ref_lib, product_lib, kind,
             # the documented refusal: hop 0 at the lowest octave
             assert RUN[kind](product_lib, a)[0] == -1 and b"cannot be halved" in product_lib.afb200_lastError(), a
             continue
+        if kind in ("cwt", "pwt") and want[0] == 0 and got[0] == -2:
+            RUN[kind](product_lib, a)                          # (the child's error text does not reach this process)
+            msg = product_lib.afb200_lastError()
+            assert (b"Gammatone" in msg or b"outside bins" in msg or b"negative frequencies" in msg or b"power-of-two" in msg), (a, msg)
+            if kind == "pwt" and b"Gammatone" in msg:
+                assert a["style"] == 2, (a, msg)
+            if kind == "pwt" and b"outside bins" in msg:       # edges at / beyond Nyquist, or the Linear scale starting at bin 0
+                assert a["scale"] in (0, 1, 6), (a, msg)
+            if kind == "cwt" and b"negative frequencies" in msg:
+                assert a["wave"] == 2, (a, msg)
+            continue
         assert want[0] == got[0], (kind, a, want[0], got[0])
         if want[0] != 0:
             continue
         compared += 1
         assert want[3] == got[3], (kind, a, want[3], got[3])
         assert np.allclose(want[1], got[1], rtol=1e-6, atol=1e-6), (kind, a)
-        if kind == "pwt" and a["scale"] == 0 and a["style"] == 2:
-            quirk = want[2].copy()
-            quirk[1:] += 1                                     # the reference's overflowing decrement (see the module docstring)
-            assert np.array_equal(got[2], quirk), (kind, a)
-            continue
         assert np.array_equal(want[2], got[2]), (kind, a, want[2][:6], got[2][:6])
     assert compared >= cases // 4, (kind, compared, crashed)
+
+
+def test_documented_refusals_are_loud(product_lib):
+    """the three parameter regions where the product returns -2 with a message instead of the reference's result"""
+    import audioflux_b200 as af
+    S, ST, W = af.SpectralFilterBankScaleType, af.SpectralFilterBankStyleType, af.WaveletContinueType
+    for make, text in ((lambda: af.PWT(40, 10, 16000, style_type=ST.GAMMATONE), "Gammatone"),
+                       (lambda: af.PWT(40, 10, 16000, low_fre=32.703196, high_fre=8000.0, scale_type=S.LOG), "outside bins"),
+                       (lambda: af.CWT(40, 10, 16000, wavelet_type=W.BUMP, gamma=4.0, beta=20.0), "negative frequencies")):
+        with pytest.raises(ValueError, match="status -2"):
+            make()
+        assert text in af.lib.last_error()
+    af.CWT(40, 10, 16000, wavelet_type=W.BUMP)                               # defaults (gamma 5, beta 0.6) are fine
+    af.PWT(40, 10, 16000, low_fre=32.703196, high_fre=4000.0, scale_type=S.LOG)
