@@ -281,10 +281,9 @@ int pwtObj_new(PWTObj *out, int num, int radix2Exp, int *samplate, float *lowFre
                                c->bankHost, c->freBandArr, c->binBandArr)) { pwtObj_free(p); return -2; }
     if (af_filterbank_clipped()) {
         /* band edges beyond samplate / 2 (Log / Linspace scales with highFre at Nyquist): the reference's pseudo bank keeps
-         * those weights on the negative-frequency bins; this library's transform is one-sided.  (Linear scale from bin 0:
-         * the reference writes the first weight in front of its bank buffer.) */
-        af_fail(AF_ERR_UNSUPPORTED, "pwtObj_new: %d filter weights fall outside bins [0, fftLength/2] (band edges beyond the "
-                "Nyquist frequency or below bin 0); move lowFre / highFre inwards", af_filterbank_clipped());
+         * those weights on the negative-frequency bins; this library's transform is one-sided */
+        af_fail(AF_ERR_UNSUPPORTED, "pwtObj_new: %d filter weights fall above the Nyquist bin (band edges beyond samplate/2); "
+                "lower highFre", af_filterbank_clipped());
         pwtObj_free(p); return -2;
     }
     *out = p;

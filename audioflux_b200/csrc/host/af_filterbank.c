@@ -140,15 +140,17 @@ void af_band_edges(int num, int fftLength, int samplate, float lowFre, float hig
     }
 }
 
-/* weights that fall above the Nyquist bin (band edges beyond samplate / 2: Log / Linspace scales with highFre at Nyquist)
- * or below bin 0 (Linear scale starting at bin 0) have no place in the one-sided bank; they are counted so that callers whose reference counterpart keeps them -- the
- * pseudo banks of pwtObj_new span all fftLength bins -- can refuse instead of dropping them silently */
+/* Weights that fall above the Nyquist bin (band edges beyond samplate / 2: Log / Linspace scales with highFre at Nyquist)
+ * have no place in the one-sided bank; they are counted so that callers whose reference counterpart keeps them -- the
+ * pseudo banks of pwtObj_new span all fftLength bins -- can refuse instead of dropping them silently.  A weight at bin -1
+ * (Linear scale starting at bin 0: the reference writes it in FRONT of its bank buffer, auditory_filterBank.c:358-364, so
+ * the first band is empty there too) is dropped without counting. */
 static __thread int g_clipped;
 int af_filterbank_clipped(void) { return g_clipped; }
 
 static void put(float *bank, int width, int row, int col, float v) {
     if (col >= 0 && col < width) bank[(size_t)row * width + col] = v;
-    else if (v != 0.0f) g_clipped++;
+    else if (col >= width && v != 0.0f) g_clipped++;
 }
 
 static void window_half_fill(float *bank, int width, int row, int style, int from, int to, int rising) {

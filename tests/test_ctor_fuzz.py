@@ -8,8 +8,7 @@ Deliberate deviations, asserted as such:
   * pwtObj_new refuses (-2, message) the Gammatone style -- the reference writes the rows of that pseudo bank
     fftLength/2+1 apart into rows that are fftLength long, and with the Linear scale its `__auditory_linearFilterBank`
     (auditory_filterBank.c:339-365) also overruns the band array -- and banks whose edges lie beyond samplate/2 (Log /
-    Linspace scales with highFre at Nyquist: the reference keeps those weights on negative-frequency bins) or below bin 0
-    (Linear scale from bin 0: the reference writes in front of its buffer);
+    Linspace scales with highFre at Nyquist: the reference keeps those weights on negative-frequency bins);
   * cwtObj_new refuses (-2) a bump wavelet with beta > gamma (support on negative frequencies, same reason)."""
 import ctypes as C
 import os
@@ -169,11 +168,11 @@ def test_constructors_agree_with_the_reference_build(ref_lib, product_lib, kind,
         if kind in ("cwt", "pwt") and want[0] == 0 and got[0] == -2:
             RUN[kind](product_lib, a)                          # (the child's error text does not reach this process)
             msg = product_lib.afb200_lastError()
-            assert (b"Gammatone" in msg or b"outside bins" in msg or b"negative frequencies" in msg or b"power-of-two" in msg), (a, msg)
+            assert (b"Gammatone" in msg or b"above the Nyquist bin" in msg or b"negative frequencies" in msg or b"power-of-two" in msg), (a, msg)
             if kind == "pwt" and b"Gammatone" in msg:
                 assert a["style"] == 2, (a, msg)
-            if kind == "pwt" and b"outside bins" in msg:       # edges at / beyond Nyquist, or the Linear scale starting at bin 0
-                assert a["scale"] in (0, 1, 6), (a, msg)
+            if kind == "pwt" and b"above the Nyquist bin" in msg:       # Log / Linspace band edges at / beyond Nyquist
+                assert a["scale"] in (1, 6), (a, msg)
             if kind == "cwt" and b"negative frequencies" in msg:
                 assert a["wave"] == 2, (a, msg)
             continue
@@ -192,7 +191,7 @@ def test_documented_refusals_are_loud(product_lib):
     import audioflux_b200 as af
     S, ST, W = af.SpectralFilterBankScaleType, af.SpectralFilterBankStyleType, af.WaveletContinueType
     for make, text in ((lambda: af.PWT(40, 10, 16000, style_type=ST.GAMMATONE), "Gammatone"),
-                       (lambda: af.PWT(40, 10, 16000, low_fre=32.703196, high_fre=8000.0, scale_type=S.LOG), "outside bins"),
+                       (lambda: af.PWT(40, 10, 16000, low_fre=32.703196, high_fre=8000.0, scale_type=S.LOG), "above the Nyquist bin"),
                        (lambda: af.CWT(40, 10, 16000, wavelet_type=W.BUMP, gamma=4.0, beta=20.0), "negative frequencies")):
         with pytest.raises(ValueError, match="status -2"):
             make()

@@ -52,7 +52,7 @@ def known_deviation(kind, a, got, want):
         # documented refusals (status -2; tests/test_ctor_fuzz.py): Gammatone pseudo banks, band edges outside [0, Nyquist],
         # bump wavelets with beta > gamma, padded lengths that are not a power of two
         msg = __import__("audioflux_b200").lib.last_error()
-        return any(t in msg for t in ("Gammatone", "outside bins", "negative frequencies", "power-of-two"))
+        return any(t in msg for t in ("Gammatone", "above the Nyquist bin", "negative frequencies", "power-of-two"))
     return False
 
 

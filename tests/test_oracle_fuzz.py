@@ -83,7 +83,7 @@ def declines(kind, a):
     """parameter regions the oracle (like the product) does not restate: the reference's own quirks there are documented in
     DESIGN.md section 1 and asserted in tests/test_ctor_fuzz.py"""
     if kind == "pwt":
-        return a["style"] == 2 or (a["scale"] in (0, 1, 6))      # Gammatone pseudo banks; edges at / beyond Nyquist or below bin 0
+        return a["style"] == 2 or (a["scale"] in (1, 6) and a["hi"] >= a["sr"] / 2)     # Gammatone pseudo banks; band edges beyond Nyquist
     if kind == "cwt":
         g, b = a["gamma"], a["beta"]
         return a["wave"] == 2 and g is not None and b is not None and b > g
