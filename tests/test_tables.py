@@ -343,3 +343,38 @@ def test_mfcc_bank_plan2_rejects_other_banks(product_lib):
     bad = tri.copy()
     bad[10, 900] = 0.5                                              # a third filter on a high bin
     assert _bank_plan2(product_lib, bad)["n"] == -1
+
+
+def test_mfcc_bank_plan2_random_banks(product_lib):
+    """the fused kernel's host planner on 150 random banks of fftLength 2048 (every scale / style / normalisation the bank
+    builder knows, 1 .. 128 bands, odd ranges): whenever it accepts a bank, its pieces, passes and lane assignment reproduce
+    B . P exactly as the helper warps evaluate them; banks it declines go to the v1 / general kernels"""
+    rng = np.random.default_rng(77)
+    accepted = 0
+    for _ in range(150):
+        scale = int(rng.integers(1, 7))
+        style = int(rng.choice([0, 0, 1, 3, 4, 5]))
+        norm = int(rng.integers(0, 3))
+        sr = int(rng.choice([8000, 16000, 22050, 32000, 44100, 48000]))
+        num = int(rng.integers(1, 129))
+        if scale == 5:
+            num = int(rng.choice([12, 24, 36, 48, 60, 72, 84]))
+        low = float(rng.choice([0.0, 20.0, 100.0, 300.0])) if scale not in (5, 6) else 32.703196
+        high = float(rng.choice([sr / 2, 0.45 * sr, sr / 4]))
+        try:
+            lo, hi, _, _ = O.bft_revise_range(num, 2048, sr, low, high, scale, 12)
+            bank, _, _ = O.auditory_filterbank(num, 2048, sr, scale, style, norm, float(lo), float(hi), 12)
+        except (IndexError, ValueError, ZeroDivisionError):
+            continue                                               # (band edges beyond Nyquist: no one-sided bank)
+        if not np.isfinite(bank).all() or not bank.any():
+            continue
+        plan = _bank_plan2(product_lib, np.ascontiguousarray(bank, np.float32))
+        if plan["n"] < 0:
+            continue
+        accepted += 1
+        assert plan["n"] <= 1408 and 1 <= plan["pieces"] <= 256
+        B = bank.astype(np.float64)
+        P = rng.random(1025) ** 6 * 50
+        want, got = B @ P, _plan2_mel(num, P, plan)
+        assert np.abs(got - want).max() <= 1e-12 * max(np.abs(want).max(), 1e-300), (scale, style, norm, num, sr, low, high)
+    assert accepted >= 40, accepted
