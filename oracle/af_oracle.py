@@ -214,7 +214,7 @@ def _fre_to_scale(fre, scale, ref=0.0):
     if scale == SCALE_LINSPACE:
         return fre
     if scale == SCALE_MEL:
-        return f32(f32(2595) * f32(math.log10(float(f32(f32(1) + f32(fre / f32(700)))))))
+        return f32(f32(2595) * f32(libm.log10f(f32(f32(1) + f32(fre / f32(700))))))        # log10f of the C library, as :1054
     if scale == SCALE_BARK:
         b = 26.81 * float(fre) / float(f32(f32(1960) + fre)) - 0.53    # double expression
         b = f32(b)
@@ -225,7 +225,7 @@ def _fre_to_scale(fre, scale, ref=0.0):
         return b
     if scale == SCALE_ERB:
         a = f32(21.3654)
-        return f32(a * f32(math.log10(float(f32(1.0 + float(fre) * 0.004368)))))
+        return f32(a * f32(libm.log10f(f32(1.0 + float(fre) * 0.004368))))
     if scale == SCALE_OCTAVE:
         return f32(np.round(f32(float(f32(ref)) * math.log2(float(f32(fre / f32(440)))))))
     if scale == SCALE_LOG:
@@ -240,7 +240,7 @@ def _scale_to_fre(v, scale, ref=0.0):
     if scale == SCALE_LINSPACE:
         return v
     if scale == SCALE_MEL:
-        return f32(f32(700) * f32(f32(math.pow(10.0, float(f32(v / f32(2595))))) - f32(1)))
+        return f32(f32(700) * f32(f32(libm.powf(10.0, f32(v / f32(2595)))) - f32(1)))          # powf of the C library, as :1062
     if scale == SCALE_BARK:
         b = v
         if b < 2:
@@ -250,7 +250,7 @@ def _scale_to_fre(v, scale, ref=0.0):
         return f32(1960 * (float(b) + 0.53) / (26.28 - float(b)))
     if scale == SCALE_ERB:
         a = f32(21.3654)
-        return f32(float(f32(f32(math.pow(10.0, float(f32(v / a)))) - f32(1))) / 0.004368)
+        return f32(float(f32(f32(libm.powf(10.0, f32(v / a))) - f32(1))) / 0.004368)
     if scale == SCALE_OCTAVE:
         return f32(math.pow(2.0, float(f32(v / f32(ref)))) * 440)
     if scale == SCALE_LOG:
@@ -327,7 +327,7 @@ import ctypes as _C
 import ctypes.util as _Cu
 
 _libm = _C.CDLL(_Cu.find_library("m") or "libm.so.6")
-for _n in ("cosf", "sinf", "expf", "powf"):
+for _n in ("cosf", "sinf", "expf", "powf", "log10f"):
     _fn = getattr(_libm, _n)
     _fn.restype = _C.c_float
     _fn.argtypes = [_C.c_float] * (2 if _n == "powf" else 1)
@@ -338,6 +338,7 @@ class libm:                                   # float32 in, float32 out, glibc r
     sinf = staticmethod(lambda x: _libm.sinf(float(x)))
     expf = staticmethod(lambda x: _libm.expf(float(x)))
     powf = staticmethod(lambda x, y: _libm.powf(float(x), float(y)))
+    log10f = staticmethod(lambda x: _libm.log10f(float(x)))
 
 
 cosf = lambda x: f32(libm.cosf(x))            # noqa: E731

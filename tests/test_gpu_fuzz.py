@@ -20,6 +20,17 @@ from _fuzz_cases import compute
 
 pytestmark = pytest.mark.gpu
 HERE = os.path.dirname(os.path.realpath(__file__))
+# the two planes of a complex result are judged on their common scale: the imaginary plane of a symmetric frame is pure
+# rounding noise in both libraries
+PAIRS = {"re": "im", "im": "re", "zre": "zim", "zim": "zre", "dre": "dim", "dim": "dre"}
+
+
+def plane_scale(want, k):
+    s = float(np.abs(want[k]).max()) if want[k].size else 0.0
+    q = PAIRS.get(k)
+    if q in want and want[q].size:
+        s = max(s, float(np.abs(want[q]).max()))
+    return s
 TOL = 1e-4
 
 
@@ -91,7 +102,7 @@ def test_random_configurations_match_the_reference_build(cuda_device, kind, seed
                 continue
             if want[k].size == 0:
                 continue
-            scale = float(np.abs(want[k]).max())
+            scale = plane_scale(want, k)
             if scale < 1e-30:
                 if not float(np.abs(got[k]).max()) < 1e-20:
                     fails.append(("nonzero", k, a))
@@ -99,7 +110,7 @@ def test_random_configurations_match_the_reference_build(cuda_device, kind, seed
             if not np.isfinite(got[k]).all():
                 fails.append(("nonfinite", k, a))
                 continue
-            err = rel_max(got[k], want[k])
+            err = float(np.abs(got[k].astype(np.float64) - want[k]).max() / scale)
             if err > worst[0]:
                 worst = (err, k, a)
             if not err < TOL:

@@ -18,6 +18,17 @@ from oracle import ref_lib as R
 from _fuzz_cases import _sig
 
 HERE = os.path.dirname(os.path.realpath(__file__))
+# the two planes of a complex result are judged on their common scale: the imaginary plane of a symmetric frame is pure
+# rounding noise in both libraries
+PAIRS = {"re": "im", "im": "re", "zre": "zim", "zim": "zre", "dre": "dim", "dim": "dre"}
+
+
+def plane_scale(want, k):
+    s = float(np.abs(want[k]).max()) if want[k].size else 0.0
+    q = PAIRS.get(k)
+    if q in want and want[q].size:
+        s = max(s, float(np.abs(want[q]).max()))
+    return s
 
 
 def reference_results(kind, seed, cases):
@@ -140,8 +151,8 @@ def test_oracle_matches_the_reference_build_on_random_configurations(ref_lib, ki
                 continue
             if got[k].shape != want[k].shape:
                 fails.append(("shape", k, got[k].shape, want[k].shape, a))
-            elif want[k].size and np.abs(want[k]).max() > 1e-30:
-                err = rel_max(got[k], want[k])
+            elif want[k].size and plane_scale(want, k) > 1e-30:
+                err = float(np.abs(got[k].astype(np.float64) - want[k]).max() / plane_scale(want, k))
                 if not err < tol:
                     fails.append(("parity", k, err, a))
     assert not fails, (kind, len(fails), fails[:6])
